@@ -1,0 +1,423 @@
+// capi.cu -- C-ABI (include/elector_poa.h) over the sm_100a kernels.  Host side of the
+// `poa` drop-in: matrix analysis, size-class binning, scratch management, launches.
+// There is NO CPU implementation of the alignment here: every entry point either runs
+// the CUDA kernels or returns an error.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/elector_poa.h"
+#include "host_io.hpp"
+#include "poa_kernel.cuh"
+#include "host_setup.hpp"
+#include "tally_kernel.cuh"
+
+using namespace elector;
+
+namespace {
+
+thread_local std::string g_init_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct SizeClass {
+  ClassLayout L;
+  bool large = false;
+  std::vector<int32_t> items;
+};
+
+}  // namespace
+
+struct elector_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ScoreMatrix mat;
+  ScoringSetup sc;
+  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl;
+  DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
+  DevBuf d_tally_in, d_tally_off, d_tally_out, d_readfirst;
+  std::string err;
+  float last_ms = 0.f;
+  int last_launches = 0;
+
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+
+const int kSmallRowsMax = 256;  // shared-memory column tier handles max(lc,lu) <= this
+const size_t kCtrlWords = 16384;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..] class work counters
+
+template <bool GC, bool GS>
+cudaError_t launch_class(elector_ctx *ctx, PoaArgs &a, int grid, size_t smem) {
+  auto k = poa_tpw_kernel<GC, GS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<grid, 128, smem, ctx->stream>>>(a, ctx->d_tab.as<SymbolTables>());
+  return cudaGetLastError();
+}
+
+template <bool GC, bool GS>
+int occupancy(size_t smem) {
+  auto k = poa_tpw_kernel<GC, GS>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 128, smem);
+  return nb;
+}
+
+// Core: all pointers are device pointers except the h_* offsets.
+int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
+               const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, const int64_t *h_roff,
+               const int64_t *h_coff, const int64_t *h_uoff, char *d_rows, int64_t rows_cap, int64_t *d_rowoff,
+               int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2, int64_t *d_cells,
+               unsigned long long *d_cursor, int32_t *d_errflag) {
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  if (n == 0) return ELECTOR_OK;
+  if (n > 0x7fffffff) return ctx->fail(ELECTOR_EINVAL, "too many windows in one call");
+  // ---- bin windows into size classes (rows bucket x reference-length bucket) ----
+  static const int ybuckets[] = {16, 24, 32, 40, 48, 56, 64, 80, 96, 128, 160, 192, 256};
+  const int NYB = sizeof(ybuckets) / sizeof(int);
+  std::vector<SizeClass> classes;
+  std::vector<int> class_of_key(64 * 64, -1);
+  std::vector<int32_t> cls(n);
+  for (int64_t w = 0; w < n; ++w) {
+    const int64_t lr = h_roff[w + 1] - h_roff[w], lc = h_coff[w + 1] - h_coff[w], lu = h_uoff[w + 1] - h_uoff[w];
+    if (lr <= 0 || lc <= 0 || lu <= 0)
+      return ctx->fail(ELECTOR_EINVAL, "window %lld has an empty sequence (undefined in the reference)", (long long)w);
+    if (lr > 30000 || lc > 30000 || lu > 30000)
+      return ctx->fail(ELECTOR_ETOOLARGE, "window %lld longer than 30000 letters", (long long)w);
+    const int ly = (int)std::max(lc, lu);
+    const bool large = ly > kSmallRowsMax || (lr + lc + lu) * (int64_t)std::max(1, ctx->sc.maxabs) > 30000;
+    int yb = 0;
+    if (large) { yb = NYB; int t = 512; while (t < ly) { t <<= 1; ++yb; } }
+    else while (ybuckets[yb] < ly) ++yb;
+    int xb = 0;
+    { int t = 64; while (t < lr) { t <<= 1; ++xb; } }
+    const int key = yb * 64 + xb;
+    int ci = class_of_key[key];
+    if (ci < 0) {
+      ci = (int)classes.size();
+      class_of_key[key] = ci;
+      classes.emplace_back();
+      classes.back().large = large;
+      classes.back().L.LR = classes.back().L.LC = classes.back().L.LU = 0;
+    }
+    ClassLayout &L = classes[ci].L;
+    L.LR = std::max<int>(L.LR, (int)lr); L.LC = std::max<int>(L.LC, (int)lc); L.LU = std::max<int>(L.LU, (int)lu);
+    cls[w] = ci;
+  }
+  // counting sort inside each class by total length, longest first
+  {
+    std::vector<std::vector<int32_t>> cnt(classes.size());
+    for (size_t c = 0; c < classes.size(); ++c) cnt[c].assign(classes[c].L.LR + classes[c].L.LC + classes[c].L.LU + 2, 0);
+    for (int64_t w = 0; w < n; ++w) {
+      const int t = (int)((h_roff[w + 1] - h_roff[w]) + (h_coff[w + 1] - h_coff[w]) + (h_uoff[w + 1] - h_uoff[w]));
+      ++cnt[cls[w]][t];
+    }
+    for (size_t c = 0; c < classes.size(); ++c) {
+      int32_t acc = 0;
+      for (size_t t = cnt[c].size(); t-- > 0;) { const int32_t k = cnt[c][t]; cnt[c][t] = acc; acc += k; }
+      classes[c].items.resize(acc);
+    }
+    for (int64_t w = 0; w < n; ++w) {
+      const int t = (int)((h_roff[w + 1] - h_roff[w]) + (h_coff[w + 1] - h_coff[w]) + (h_uoff[w + 1] - h_uoff[w]));
+      classes[cls[w]].items[cnt[cls[w]][t]++] = (int32_t)w;
+    }
+  }
+  // ---- device work lists + counters ----
+  CU(ctx->d_items.reserve((size_t)n * sizeof(int32_t)));
+  if (classes.size() + 4 > kCtrlWords) return ctx->fail(ELECTOR_EINVAL, "too many size classes");
+  CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(int32_t) * (classes.size() + 4), ctx->stream));
+  {
+    size_t pos = 0;
+    for (auto &c : classes) {
+      CU(cudaMemcpyAsync(ctx->d_items.as<int32_t>() + pos, c.items.data(), c.items.size() * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, ctx->stream));
+      pos += c.items.size();
+    }
+  }
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  size_t pos = 0;
+  for (size_t ci = 0; ci < classes.size(); ++ci) {
+    SizeClass &c = classes[ci];
+    make_layout(c.L, c.L.LR, c.L.LC, c.L.LU, c.large);
+    const size_t smem = sizeof(SymbolTables) + (c.large ? 0 : (size_t)4 * 2 * (c.L.LY + 1) * 32 * 4);
+    if (smem > ctx->smem_optin) return ctx->fail(ELECTOR_ECUDA, "class needs %zu B shared memory", smem);
+    int nb;
+    if (c.large) nb = ctx->sc.generic_sub ? occupancy<true, true>(smem) : occupancy<true, false>(smem);
+    else nb = ctx->sc.generic_sub ? occupancy<false, true>(smem) : occupancy<false, false>(smem);
+    if (nb < 1) return ctx->fail(ELECTOR_ECUDA, "kernel does not fit (smem %zu)", smem);
+    const int64_t groups = ((int64_t)c.items.size() + 31) / 32;
+    int grid = (int)std::min<int64_t>((int64_t)nb * ctx->sm_count, (groups + 3) / 4);
+    if (grid < 1) grid = 1;
+    // bound the scratch of big classes: fewer resident warps when windows are huge
+    const size_t per_warp = (size_t)c.L.total * 32 * 4;
+    const size_t budget = (size_t)8 << 30;
+    while (grid > 1 && per_warp * 4 * (size_t)grid > budget) grid = (grid + 1) / 2;
+    if (per_warp * 4 * (size_t)grid > ((size_t)48 << 30))
+      return ctx->fail(ELECTOR_ETOOLARGE, "window class %dx%dx%d needs %zu MiB scratch per warp", c.L.LR, c.L.LC, c.L.LU, per_warp >> 20);
+    CU(ctx->d_scratch.reserve(per_warp * 4 * (size_t)grid));
+    PoaArgs a;
+    a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
+    a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
+    a.items = ctx->d_items.as<int32_t>() + pos;
+    a.n_items = (int32_t)c.items.size();
+    a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
+    a.scratch = ctx->d_scratch.as<uint32_t>();
+    a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + ci;
+    a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
+    a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
+    a.error_flag = d_errflag;
+    a.L = c.L;
+    cudaError_t e;
+    if (c.large) e = ctx->sc.generic_sub ? launch_class<true, true>(ctx, a, grid, smem) : launch_class<true, false>(ctx, a, grid, smem);
+    else e = ctx->sc.generic_sub ? launch_class<false, true>(ctx, a, grid, smem) : launch_class<false, false>(ctx, a, grid, smem);
+    if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    ++ctx->last_launches;
+    pos += c.items.size();
+  }
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  return ELECTOR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
+  if (!out) return ELECTOR_EINVAL;
+  *out = nullptr;
+  elector_ctx *ctx = new elector_ctx();
+  auto bail = [&](int code) {
+    g_init_error = ctx->err;
+    elector_poa_free(ctx);
+    return code;
+  };
+  if (matrix_path) {
+    if (ctx->mat.load(matrix_path) <= 0) {
+      ctx->fail(ELECTOR_EMATRIX, "Error reading matrix file %s", matrix_path);
+      return bail(ELECTOR_EMATRIX);
+    }
+  } else ctx->mat.set_default();
+  if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    ctx->fail(ELECTOR_ECUDA, "no CUDA device available (%s); this library has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return bail(ELECTOR_ECUDA);
+  }
+  if (device < 0 || device >= ndev) { ctx->fail(ELECTOR_EINVAL, "device %d out of range (0..%d)", device, ndev - 1); return bail(ELECTOR_EINVAL); }
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { ctx->fail(ELECTOR_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); return bail(ELECTOR_ECUDA); }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = ctx->d_tab.reserve(sizeof(SymbolTables))) != cudaSuccess ||
+      (e = ctx->d_ctrl.reserve(kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMemcpy(ctx->d_tab.p, &ctx->sc.tab, sizeof(SymbolTables), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
+    return bail(ELECTOR_ECUDA);
+  }
+  *out = ctx;
+  return ELECTOR_OK;
+}
+
+void elector_poa_free(elector_ctx *ctx) {
+  if (!ctx) return;
+  DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
+                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
+                    &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_tally_in, &ctx->d_tally_off,
+                    &ctx->d_tally_out, &ctx->d_readfirst};
+  for (DevBuf *b : bufs) b->release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *elector_last_error(const elector_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int64_t elector_poa_rows_bound(int64_t n, const int64_t *ro, const int64_t *co, const int64_t *uo) {
+  int64_t t = 0;
+  for (int64_t w = 0; w < n; ++w)
+    t += 3 * (((ro[w + 1] - ro[w]) + (co[w + 1] - co[w]) + (uo[w + 1] - uo[w]) + 3) & ~(int64_t)3);
+  return t;
+}
+
+int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
+                           const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, const int64_t *h_roff,
+                           const int64_t *h_coff, const int64_t *h_uoff, char *d_rows, int64_t rows_cap,
+                           int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2,
+                           int64_t *d_cells, int64_t *d_rows_used) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (n < 0 || (n > 0 && (!d_ref || !d_cor || !d_unc || !d_roff || !d_coff || !d_uoff || !h_roff || !h_coff || !h_uoff ||
+                          !d_rows || !d_rowoff || !d_stride || !d_nring)))
+    return ctx->fail(ELECTOR_EINVAL, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  int rc = run_device(ctx, n, d_ref, d_roff, d_cor, d_coff, d_unc, d_uoff, h_roff, h_coff, h_uoff, d_rows, rows_cap,
+                      d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells, ctx->d_ctrl.as<unsigned long long>(),
+                      ctx->d_ctrl.as<int32_t>() + 2);
+  if (rc != ELECTOR_OK) return rc;
+  if (d_rows_used)
+    CU(cudaMemcpyAsync(d_rows_used, ctx->d_ctrl.p, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  int32_t ctrl[4] = {0, 0, 0, 0};
+  CU(cudaMemcpyAsync(ctrl, ctx->d_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (n > 0) cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+  if (ctrl[2]) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small", (long long)rows_cap);
+  return ELECTOR_OK;
+}
+
+int elector_poa_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ro, const char *cor, const int64_t *co,
+                    const char *unc, const int64_t *uo, char *rows_out, int64_t rows_cap, int64_t *row_off,
+                    int32_t *row_stride, int32_t *nring, int32_t *score1, int32_t *score2, int64_t *cells) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (n < 0 || (n > 0 && (!ref || !cor || !unc || !ro || !co || !uo || !rows_out || !row_off || !row_stride || !nring)))
+    return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  const int64_t br = ro[n] - ro[0], bc = co[n] - co[0], bu = uo[n] - uo[0];
+  if (ro[0] != 0 || co[0] != 0 || uo[0] != 0) return ctx->fail(ELECTOR_EINVAL, "offsets must start at 0");
+  const int64_t bound = elector_poa_rows_bound(n, ro, co, uo);
+  CU(ctx->d_ref.reserve(br)); CU(ctx->d_cor.reserve(bc)); CU(ctx->d_unc.reserve(bu));
+  CU(ctx->d_roff.reserve((n + 1) * 8)); CU(ctx->d_coff.reserve((n + 1) * 8)); CU(ctx->d_uoff.reserve((n + 1) * 8));
+  CU(ctx->d_rows.reserve(bound)); CU(ctx->d_rowoff.reserve(n * 8)); CU(ctx->d_stride.reserve(n * 4));
+  CU(ctx->d_nring.reserve(n * 4)); CU(ctx->d_s1.reserve(n * 4)); CU(ctx->d_s2.reserve(n * 4)); CU(ctx->d_cells.reserve(n * 8));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->d_ref.p, ref, br, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_cor.p, cor, bc, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_unc.p, unc, bu, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_roff.p, ro, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_coff.p, co, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_uoff.p, uo, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  int rc = run_device(ctx, n, ctx->d_ref.as<char>(), ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>(),
+                      ctx->d_coff.as<int64_t>(), ctx->d_unc.as<char>(), ctx->d_uoff.as<int64_t>(), ro, co, uo,
+                      ctx->d_rows.as<char>(), bound, ctx->d_rowoff.as<int64_t>(), ctx->d_stride.as<int32_t>(),
+                      ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(), ctx->d_s2.as<int32_t>(),
+                      ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2);
+  if (rc != ELECTOR_OK) return rc;
+  int64_t ctrl[2] = {0, 0};
+  CU(cudaMemcpyAsync(ctrl, ctx->d_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(row_off, ctx->d_rowoff.p, n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(row_stride, ctx->d_stride.p, n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(nring, ctx->d_nring.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (score1) CU(cudaMemcpyAsync(score1, ctx->d_s1.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (score2) CU(cudaMemcpyAsync(score2, ctx->d_s2.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (cells) CU(cudaMemcpyAsync(cells, ctx->d_cells.p, n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+  const int64_t used = ctrl[0];
+  if ((int32_t)(ctrl[1] & 0xffffffff)) return ctx->fail(ELECTOR_ECAPACITY, "internal rows buffer too small");
+  if (used > rows_cap) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld < %lld needed", (long long)rows_cap, (long long)used);
+  CU(cudaMemcpyAsync(rows_out, ctx->d_rows.p, used, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ELECTOR_OK;
+}
+
+int elector_poa_files(elector_ctx *ctx, const char *ref_fa, const char *cor_fa, const char *unc_fa, const char *pir_out,
+                      int print_perm) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (!ref_fa || !cor_fa || !unc_fa || !pir_out) return ctx->fail(ELECTOR_EINVAL, "null path");
+  FastaFile C, U, R;
+  // same open order and failure behaviour as main.c:242-262
+  if (read_fasta_file(cor_fa, C) < 0) return ctx->fail(ELECTOR_EIO, "Couldn't open sequence file %s", cor_fa);
+  if (read_fasta_file(unc_fa, U) < 0) return ctx->fail(ELECTOR_EIO, "Couldn't open sequence file %s", cor_fa);
+  if (read_fasta_file(ref_fa, R) < 0) return ctx->fail(ELECTOR_EIO, "Couldn't open sequence file %s", cor_fa);
+  if (R.rec.empty()) return ctx->fail(ELECTOR_EIO, "Error reading sequence file %s", cor_fa);
+  // The reference indexes all three arrays with the reference count and runs off the end
+  // when they disagree (undefined); we align the common prefix and report the mismatch.
+  size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
+  const bool ragged = !(R.rec.size() == C.rec.size() && R.rec.size() == U.rec.size());
+  FILE *out = fopen(pir_out, "w");
+  if (!out) return ctx->fail(ELECTOR_EIO, "cannot write %s", pir_out);
+  int rc = ELECTOR_OK;
+  if (n > 0) {
+    std::vector<int64_t> ro = R.offsets(), co = C.offsets(), uo = U.offsets();
+    ro.resize(n + 1); co.resize(n + 1); uo.resize(n + 1);
+    const int64_t bound = elector_poa_rows_bound((int64_t)n, ro.data(), co.data(), uo.data());
+    std::vector<char> rows(bound);
+    std::vector<int64_t> roff(n);
+    std::vector<int32_t> stride(n), nring(n);
+    rc = elector_poa_run(ctx, (int64_t)n, R.seq.data(), ro.data(), C.seq.data(), co.data(), U.seq.data(), uo.data(),
+                         rows.data(), bound, roff.data(), stride.data(), nring.data(), nullptr, nullptr, nullptr);
+    if (rc == ELECTOR_OK) {
+      std::string buf;
+      buf.reserve(1 << 20);
+      for (size_t w = 0; w < n; ++w) {
+        const FastaRecord *recs[3] = {&R.rec[w], &C.rec[w], &U.rec[w]};
+        for (int s = 0; s < 3; ++s) {
+          buf += '>'; buf += recs[s]->name; buf += ' '; buf += recs[s]->title; buf += '\n';
+          buf.append(rows.data() + roff[w] + (int64_t)s * stride[w], nring[w]);
+          buf += '\n';
+        }
+        if (buf.size() > (1 << 20) - 65536) { fwrite(buf.data(), 1, buf.size(), out); buf.clear(); }
+      }
+      fwrite(buf.data(), 1, buf.size(), out);
+      if (print_perm) {
+        std::string perm;
+        for (size_t w = 0; w < n; ++w) perm += "0 1 2 \n";
+        fwrite(perm.data(), 1, perm.size(), stdout);
+      }
+    }
+  }
+  fclose(out);
+  if (rc != ELECTOR_OK) return rc;
+  if (ragged) return ctx->fail(ELECTOR_EIO, "record counts differ (ref %zu, corrected %zu, uncorrected %zu); aligned the first %zu", R.rec.size(), C.rec.size(), U.rec.size(), n);
+  return ELECTOR_OK;
+}
+
+int elector_last_kernel_ms(const elector_ctx *ctx, float *ms, int *launches) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (ms) *ms = ctx->last_ms;
+  if (launches) *launches = ctx->last_launches;
+  return ELECTOR_OK;
+}
+
+}  // extern "C"
+
+#include "tally_capi.inl"

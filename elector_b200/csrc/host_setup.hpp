@@ -1,0 +1,102 @@
+// host_setup.hpp -- host-side preparation shared by the C-ABI and the CPU emulation test
+// harness: which matrix class the kernels can run, the device symbol tables, and the
+// per-thread scratch layout of a size class.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "host_io.hpp"
+#include "poa_kernel.cuh"
+
+namespace elector {
+
+struct ScoringSetup {
+  SymbolTables tab;
+  int match = 0, mismatch = 0, open = 0, ext = 0, maxabs = 0;
+  bool generic_sub = false;
+  std::string error;
+
+  bool fail(const char *fmt, int a = 0, int b = 0, int c = 0) {
+    char buf[256];
+    snprintf(buf, sizeof buf, fmt, a, b, c);
+    error = buf;
+    return false;
+  }
+
+  // Supported class: alphabet <= 32 symbols, identical x/y gap sets,
+  // and an extension penalty that is flat over gap lengths 1..T+D, so that the reference's
+  // 0..T+D+1 gap-length state (align_lpo_po2.c:224-249) collapses to "in a gap or not".
+  bool analyse(const ScoreMatrix &m) {
+    if (m.nsymbol <= 0 || m.nsymbol > 32) return fail("matrix alphabet has %d symbols; 1..32 supported", m.nsymbol);
+    const int M = m.trunc_len + m.decay_len;
+    if (M < 1) return fail("gap truncation+decay length must be >= 1");
+    for (int i = 0; i <= M; ++i)
+      if (m.pen_x[i] != m.pen_y[i]) return fail("GAP-PENALTIES-X differing from GAP-PENALTIES is not supported");
+    for (int i = 2; i <= M; ++i)
+      if (m.pen_x[i] != m.pen_x[1])
+        return fail("gap extension penalty must be flat (A1 == A2 or decay length 0); got %d vs %d at length %d", m.pen_x[1], m.pen_x[i], i);
+    open = m.pen_x[0];
+    ext = m.pen_x[1];
+    memset(&tab, 0, sizeof tab);
+    bool reach[32] = {false};
+    for (int b = 0; b < 256; ++b) {
+      const int c = m.code_of(b);
+      tab.code_lut[b] = (uint8_t)c;
+      if (b) reach[c] = true;
+    }
+    for (int i = 0; i < m.nsymbol; ++i) tab.sym[i] = (uint8_t)m.symbol[i];
+    maxabs = std::max(std::abs(open), std::abs(ext));
+    for (int i = 0; i < m.nsymbol; ++i)
+      for (int j = 0; j < m.nsymbol; ++j) {
+        const int s = m.score[(size_t)i * m.nsymbol + j];
+        if (s < -32000 || s > 32000) return fail("score %d out of range", s);
+        tab.sub[i * 32 + j] = (int16_t)s;
+        if (reach[i] && reach[j]) maxabs = std::max(maxabs, std::abs(s));
+      }
+    // uniform match/mismatch over the reachable symbols -> compare-select instead of a table
+    bool uniform = true, have_d = false, have_o = false;
+    int dval = 0, oval = 0;
+    for (int i = 0; i < m.nsymbol && uniform; ++i)
+      for (int j = 0; j < m.nsymbol && uniform; ++j) {
+        if (!reach[i] || !reach[j]) continue;
+        const int s = m.score[(size_t)i * m.nsymbol + j];
+        if (i == j) { if (!have_d) { dval = s; have_d = true; } else if (s != dval) uniform = false; }
+        else { if (!have_o) { oval = s; have_o = true; } else if (s != oval) uniform = false; }
+      }
+    generic_sub = !uniform;
+    match = dval;
+    mismatch = have_o ? oval : dval;
+    return true;
+  }
+};
+
+inline uint32_t cdiv_u(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// Per-thread scratch layout of a size class with caps (LR, LC, LU); `large` adds the two
+// global-memory column buffers of the large tier.
+inline void make_layout(ClassLayout &L, int LR, int LC, int LU, bool large) {
+  L.LR = LR; L.LC = LC; L.LU = LU;
+  L.LY = std::max(LC, LU);
+  const uint32_t N1 = (uint32_t)LR + LC;
+  uint32_t o = 0;
+  L.o_ref = o; o += cdiv_u(LR, 4);
+  L.o_cor = o; o += cdiv_u(LC, 4);
+  L.o_unc = o; o += cdiv_u(LU, 4);
+  L.o_nodeA = o; o += N1;
+  L.o_nodeB = o; o += N1;
+  L.o_moves = o; o += std::max((uint32_t)LR * cdiv_u(LC, 16), N1 * cdiv_u(LU, 16));
+  L.ord_wpn = cdiv_u(LU + 1, 8);
+  L.o_ord = o; o += ((uint32_t)std::min(LR, LC) + 2) * L.ord_wpn;
+  L.o_x2y = o; o += N1;
+  L.o_y2x = o; o += L.LY;
+  L.row_words = cdiv_u(LR + LC + LU, 4);
+  L.o_rows = o; o += 3 * L.row_words;
+  L.o_cols = o;
+  if (large) o += 2u * 2u * (L.LY + 1);
+  L.total = o;
+}
+
+}  // namespace elector

@@ -1,0 +1,133 @@
+/* elector_poa.h -- C-ABI of the B200-native ELECTOR POA hot path.
+ *
+ * The reference has no in-process API for this path: its boundary is the `poa`
+ * executable (src/poa-graph/main.c) driven by elector/alignment.py:59-63, and the
+ * tally is elector/computeStats.py reading msa.fa.  These entry points are what a
+ * cgo / ctypes / JNI binding of that path would bind; each cites the reference
+ * interface it replaces (paths relative to the reference tree).  Plain pointers and
+ * sizes only; the caller owns every host buffer; all functions return 0 on success
+ * and a negative ELECTOR_E* code on error (elector_last_error() gives the text).
+ * There is no CPU fallback: without a CUDA device elector_poa_init fails.
+ */
+#ifndef ELECTOR_POA_H
+#define ELECTOR_POA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELECTOR_OK 0
+#define ELECTOR_EINVAL (-1)   /* bad argument (NULL pointer, empty window, ...) */
+#define ELECTOR_EMATRIX (-2)  /* matrix file unreadable / malformed (main.c:149-155 -> exit 1) */
+#define ELECTOR_EUNSUPPORTED (-3) /* matrix outside the supported class */
+#define ELECTOR_ECUDA (-4)    /* CUDA runtime error, no device, out of memory */
+#define ELECTOR_EIO (-5)      /* FASTA / output file unreadable (main.c:245-262 -> exit 1) */
+#define ELECTOR_ETOOLARGE (-6) /* window larger than the large tier supports */
+#define ELECTOR_ECAPACITY (-7) /* caller's output buffer too small */
+
+typedef struct elector_ctx elector_ctx;
+
+/* Number of per-read tally counters written by elector_tally_run (see ELECTOR_T_*). */
+#define ELECTOR_TALLY_K 24
+enum {
+  ELECTOR_T_TP = 0, ELECTOR_T_FP, ELECTOR_T_FN,
+  ELECTOR_T_COR, ELECTOR_T_UNCOR,           /* corBases / uncorBases   (computeStats.py:371-393) */
+  ELECTOR_T_UNCORCOR, ELECTOR_T_UNCORUNCOR, /* uncorCorBases / uncorUncorBases */
+  ELECTOR_T_INSC, ELECTOR_T_DELC, ELECTOR_T_SUBSC, /* indels() corrected (:309-317) */
+  ELECTOR_T_INSU, ELECTOR_T_DELU, ELECTOR_T_SUBSU, /* indels() uncorrected (:318-328) */
+  ELECTOR_T_GCREF, ELECTOR_T_GCCOR,         /* GC counts over all columns (:421-424) */
+  ELECTOR_T_LENREF, ELECTOR_T_LENCOR, ELECTOR_T_LENUNC, /* non-gap lengths (getLen :268) */
+  ELECTOR_T_GAPSLEFT, ELECTOR_T_GAPSRIGHT,  /* gapsAndExtensions (:472-488) */
+  ELECTOR_T_MISSING,                        /* missingSize after clamping (:489-495) */
+  ELECTOR_T_EXTENDED,                       /* extended bases, -1 when the read is not extended */
+  ELECTOR_T_NCOLS,                          /* msa line length */
+  ELECTOR_T_ASSESSED                        /* 1 when len(reference row) > 10 (:577) */
+};
+
+/* Replaces: process start of `poa` -- black_flag_init + read_score_matrix
+ * (main.c:38,149-155; seq_util.c:82-217).  device = CUDA ordinal.  matrix_path may be
+ * NULL for the shipped blosum80.mat values (identity 0/-10, gaps 10 5 5, T=10, D=5). */
+int elector_poa_init(int device, const char *matrix_path, elector_ctx **ctx);
+
+/* Replaces: process exit of `poa` (main.c:293-312). */
+void elector_poa_free(elector_ctx *ctx);
+
+/* Text of the last error on this context (or of the last failed init when ctx==NULL). */
+const char *elector_last_error(const elector_ctx *ctx);
+
+/* Replaces: the per-window loop of `poa` (main.c:265-284): for each window
+ * initialize_seqs_as_lpo x3, buildup_progressive_lpo (align_lpo_po + fuse_lpo, twice)
+ * and xlate_lpo_to_al.  Inputs are raw FASTA letters (any case; normalised on the
+ * device like create_seq.c:39-43 + seq_util.c:253-263,37-52), concatenated, with
+ * n+1 offsets per sequence kind; every window must have >=1 letter in each sequence.
+ * Outputs (host): nring[w] = MSA columns; the three rows of window w start at
+ * rows_out + row_off[w] + s*row_stride[w], s = 0 ref, 1 corrected, 2 uncorrected
+ * (lpo_format.c:407-421 order), row_stride[w] = nring[w] rounded up to 4;
+ * score1/score2 = best_score of the two align_lpo_po calls (align_lpo_po2.c:486);
+ * cells[w] = DP inner-loop iterations (align_lpo_po2.c:309-320).  score1, score2 and
+ * cells may be NULL.  rows_cap >= elector_poa_rows_bound(...) always suffices. */
+int elector_poa_run(elector_ctx *ctx, int64_t n_windows,
+                    const char *ref, const int64_t *ref_off,
+                    const char *cor, const int64_t *cor_off,
+                    const char *unc, const int64_t *unc_off,
+                    char *rows_out, int64_t rows_cap, int64_t *row_off, int32_t *row_stride,
+                    int32_t *nring, int32_t *score1, int32_t *score2, int64_t *cells);
+
+/* Upper bound of the bytes elector_poa_run can write to rows_out. */
+int64_t elector_poa_rows_bound(int64_t n_windows, const int64_t *ref_off,
+                               const int64_t *cor_off, const int64_t *unc_off);
+
+/* Same computation with every buffer already resident in device memory (pointers
+ * from cudaMalloc / torch); nothing is copied to the host.  Used for the
+ * device-resident throughput figure and by callers that chain the tally on device.
+ * d_rows_used receives (on the device) the bytes used in d_rows_out.  lens_host_*
+ * are host copies of the offsets (needed to bin windows by size). */
+int elector_poa_run_device(elector_ctx *ctx, int64_t n_windows,
+                           const char *d_ref, const int64_t *d_ref_off,
+                           const char *d_cor, const int64_t *d_cor_off,
+                           const char *d_unc, const int64_t *d_unc_off,
+                           const int64_t *h_ref_off, const int64_t *h_cor_off,
+                           const int64_t *h_unc_off,
+                           char *d_rows_out, int64_t rows_cap, int64_t *d_row_off,
+                           int32_t *d_row_stride, int32_t *d_nring, int32_t *d_score1,
+                           int32_t *d_score2, int64_t *d_cells, int64_t *d_rows_used);
+
+/* Replaces: the whole `poa` process body for one shard (main.c:241-287) -- reads the
+ * three FASTA files (fasta_format.c:10-66 semantics), aligns every record triplet and
+ * writes the PIR file (lpo_format.c:398-426 format).  print_perm != 0 also prints the
+ * reference's "0 1 2 \n" line per window on stdout (buildup_lpo.c:545).  Returns 0, or
+ * ELECTOR_EIO when a file cannot be opened / holds no record (reference exit code 1). */
+int elector_poa_files(elector_ctx *ctx, const char *ref_fasta, const char *cor_fasta,
+                      const char *unc_fasta, const char *pir_out, int print_perm);
+
+/* Replaces: Donatello's per-read merge (src/split/Donatello.cpp:13-31,50-84: windows
+ * concatenated per read, columns whose corrected row is 'n' dropped) followed by the
+ * integer part of computeStats.py's per-read tally (gapsAndExtensions :472-498,
+ * findGapStretches :104-189, getCorrectedPositions :712-752, getTPFNFP :399-440).
+ * Input: n_reads merged reads; row pointers are given as offsets into three
+ * concatenated row buffers (ref, corrected, uncorrected; n_reads+1 offsets shared by
+ * the three, all rows of one read have equal length).  counters_out[r*ELECTOR_TALLY_K+k].
+ * Ratios (recall, precision, rates) stay with the caller, as in computeStats.py:444-468. */
+int elector_tally_run(elector_ctx *ctx, int64_t n_reads, const char *row_ref,
+                      const char *row_cor, const char *row_unc, const int64_t *row_off,
+                      int64_t *counters_out);
+
+/* Device-side merge of window MSAs into per-read rows (Donatello semantics) chained on
+ * the output of elector_poa_run_device, followed by the tally, all on the device.
+ * read_first[r] .. read_first[r+1]-1 are the windows of read r (host array, n_reads+1).
+ * d_counters_out: n_reads*ELECTOR_TALLY_K int64 on the device. */
+int elector_merge_tally_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first,
+                               int64_t n_windows, const char *d_rows, const int64_t *d_row_off,
+                               const int32_t *d_row_stride, const int32_t *d_nring,
+                               int64_t *d_counters_out);
+
+/* Timing of the kernels launched by the last run on this context, measured with CUDA
+ * events on the launching stream: total ms and number of kernel launches. */
+int elector_last_kernel_ms(const elector_ctx *ctx, float *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
