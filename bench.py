@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the ELECTOR POA hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+One step = one pass of the hot path (three-way POA of every window of every triplet, then
+the per-read merge + tally once those kernels exist) over the workload: BASELINE.json
+configs[1], 10 000 triplets of 10 kb reads at 10 % / 1 % error, cut into ~1.95 M windows by
+the unchanged reference splitter.  Per-GPU work is fixed (weak scaling): rank r owns read
+ids [r*10000, (r+1)*10000).  The window arrays (~300 MB) exceed the 126 MB L2, so no
+flush is needed between steps.
+
+  value     triplets/s with the window arrays already resident in HBM (elector_poa_run_device)
+  e2e       the same through the host-buffer C-ABI call (elector_poa_run): pinned host
+            arrays in, MSA rows out, H2D/D2H inside the timed region
+  roofline  INT32 issue roofline of the DP kernel (15 integer ops per DP cell)
+            against the peak measured on this device by elector_int32_peak
+  cpu_baseline  the reference poa binary (oracle/_ref/poa) or the oracle port, timed on
+            this box's host cores on a bounded prefix of the same workload
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+INT_OPS_PER_CELL = 15  # SURVEY.md 8d convention
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_throughput(wl, n_triplets, procs, kind):
+    """Times the reference's CPU implementation on the first n_triplets triplets of wl.
+    kind 'reference': oracle/_ref/poa, one single-threaded process per shard file, `procs`
+    concurrently (how elector/alignment.py:117-119 runs it), shards balanced by windows.
+    kind 'port': the oracle (oracle/poa_oracle.c) with `procs` OpenMP threads."""
+    import workloads
+    sub = workloads.slice_windows(wl, 0, n_triplets)
+    n = len(sub["ref_off"]) - 1
+    lr, lc, lu = np.diff(sub["ref_off"]), np.diff(sub["cor_off"]), np.diff(sub["unc_off"])
+    if kind == "port":
+        from oracle import oracle
+        t0 = time.perf_counter()
+        o = oracle.batch(sub["ref"], sub["ref_off"], sub["cor"], sub["cor_off"], sub["unc"], sub["unc_off"], nthreads=procs)
+        dt = time.perf_counter() - t0
+        cells = int(o["cells"].sum())
+    else:
+        work = tempfile.mkdtemp(prefix="elref_")
+        try:
+            bounds = [(n * i) // procs for i in range(procs + 1)]
+            for i in range(procs):
+                a, b = bounds[i], bounds[i + 1]
+                for key, name in (("ref", "out1"), ("unc", "out2"), ("cor", "out3")):
+                    off, seq = sub[key + "_off"], sub[key]
+                    with open("%s/%s%d" % (work, name, i), "wb") as f:
+                        for w in range(a, b):
+                            f.write(b">w%d\n" % w)
+                            f.write(seq[int(off[w]):int(off[w + 1])].tobytes())
+                            f.write(b"\n")
+            exe, mat = os.path.join(ROOT, "oracle", "_ref", "poa"), os.path.join(ROOT, "oracle", "_ref", "blosum80.mat")
+            t0 = time.perf_counter()
+            ps = [subprocess.Popen([exe, "-pir", "%s/smsa%d" % (work, i), "-preserve_seqorder", "-corrected_reads_fasta",
+                                    "%s/out3%d" % (work, i), "-reference_reads_fasta", "%s/out1%d" % (work, i),
+                                    "-uncorrected_reads_fasta", "%s/out2%d" % (work, i), "-preserve_seqorder", "-threads", "1",
+                                    "-pathMatrix", mat], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                  for i in range(procs) if bounds[i + 1] > bounds[i]]
+            for p in ps:
+                p.wait()
+            dt = time.perf_counter() - t0
+            cells = int((lr * lc + np.maximum(lr, lc) * lu).sum())  # lower bound on the cells (len(P1) >= max(lr, lc))
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+    return {"seconds": dt, "triplets_per_s": n_triplets / dt, "windows_per_s": n / dt, "gcups": cells / dt / 1e9,
+            "windows": n, "triplets": n_triplets}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1)
+    ap.add_argument("--reads", type=int, default=0, help="triplets per GPU (default: the config's full size, capped at 10000)")
+    ap.add_argument("--cpu-triplets", type=int, default=0, help="triplets of the CPU baseline sample (default: sized for ~10-20 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+
+    import workloads
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    n_reads = args.reads or min(workloads.CONFIG_READS[args.config], 10000)
+    ncores = os.cpu_count() or 1
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "poa"))
+    workload_name = workloads.CONFIG_NAMES[args.config] + (" [%d triplets per GPU]" % n_reads)
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        kind = "reference" if have_ref else "port"
+        # bounded sample: ~26 triplets/s/core for 10 kb reads -> ~15 s per step
+        per_step = args.cpu_triplets or int(min(n_reads, max(16, ncores * 26 * 12)))
+        wl = workloads.make_windows(args.config, per_step, 0)
+        per_step = len(wl["read_first"]) - 1
+        for _ in range(args.warmup):
+            cpu_reference_throughput(wl, max(1, per_step // 8), ncores, kind)
+        times, last = [], None
+        for _ in range(max(1, args.steps)):
+            last = cpu_reference_throughput(wl, per_step, ncores, kind)
+            times.append(last["seconds"])
+        val = per_step * len(times) / sum(times)
+        sample = "first %d triplets (%d windows) of the workload per step" % (per_step, last["windows"])
+        print(json.dumps({
+            "impl": "reference", "metric": "triplets_per_sec", "value": val, "unit": "triplets/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "gcups": last["gcups"], "windows_per_sec": last["windows_per_s"],
+            "config": {"workload": workload_name, "windows_from": wl["source"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "triplets/s", "cores": ncores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import elector_b200
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    wl = workloads.make_windows(args.config, n_reads, rank * n_reads)
+    n_trip = len(wl["read_first"]) - 1
+    n = len(wl["ref_off"]) - 1
+    ctx = elector_b200.PoaContext(device=local)
+    lib = ctx._lib
+
+    # host (pinned) and device copies of the inputs
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    hp = {k: pinned(wl[k]) for k in ("ref", "ref_off", "cor", "cor_off", "unc", "unc_off")}
+    dv = {k: hp[k][0].to(dev, non_blocking=False) for k in hp}
+    bound = int(lib.elector_poa_rows_bound(n, hp["ref_off"][1].ctypes.data, hp["cor_off"][1].ctypes.data, hp["unc_off"][1].ctypes.data))
+    d_rows = torch.empty(bound, dtype=torch.uint8, device=dev)
+    d_rowoff = torch.empty(n, dtype=torch.int64, device=dev)
+    d_stride = torch.empty(n, dtype=torch.int32, device=dev)
+    d_nring = torch.empty(n, dtype=torch.int32, device=dev)
+    d_s1 = torch.empty(n, dtype=torch.int32, device=dev)
+    d_s2 = torch.empty(n, dtype=torch.int32, device=dev)
+    d_cells = torch.empty(n, dtype=torch.int64, device=dev)
+    d_used = torch.zeros(1, dtype=torch.int64, device=dev)
+    h_rows = torch.empty(bound, dtype=torch.uint8).pin_memory()
+    h_out = {"row_off": torch.empty(n, dtype=torch.int64).pin_memory(), "stride": torch.empty(n, dtype=torch.int32).pin_memory(),
+             "nring": torch.empty(n, dtype=torch.int32).pin_memory()}
+    torch.cuda.synchronize()
+
+    def step_device():
+        rc = lib.elector_poa_run_device(ctx._ctx, n, dv["ref"].data_ptr(), dv["ref_off"].data_ptr(), dv["cor"].data_ptr(),
+                                        dv["cor_off"].data_ptr(), dv["unc"].data_ptr(), dv["unc_off"].data_ptr(),
+                                        hp["ref_off"][1].ctypes.data, hp["cor_off"][1].ctypes.data, hp["unc_off"][1].ctypes.data,
+                                        d_rows.data_ptr(), bound, d_rowoff.data_ptr(), d_stride.data_ptr(), d_nring.data_ptr(),
+                                        d_s1.data_ptr(), d_s2.data_ptr(), d_cells.data_ptr(), d_used.data_ptr())
+        ctx._check(rc)
+
+    def step_e2e():
+        rc = lib.elector_poa_run(ctx._ctx, n, hp["ref"][1].ctypes.data, hp["ref_off"][1].ctypes.data, hp["cor"][1].ctypes.data,
+                                 hp["cor_off"][1].ctypes.data, hp["unc"][1].ctypes.data, hp["unc_off"][1].ctypes.data,
+                                 h_rows.data_ptr(), bound, h_out["row_off"].data_ptr(), h_out["stride"].data_ptr(),
+                                 h_out["nring"].data_ptr(), None, None, None)
+        ctx._check(rc)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """device time of `steps` calls, CUDA events on the library's launching stream; also kernel-only ms"""
+        import ctypes
+        barrier()
+        ctx._check(lib.elector_event_record(ctx._ctx, 0))
+        kms, launches = 0.0, 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+            m, k = ctx.last_kernel_ms()
+            kms += m
+            launches += k
+        ctx._check(lib.elector_event_record(ctx._ctx, 1))
+        ms = ctypes.c_float(0)
+        ctx._check(lib.elector_event_elapsed_ms(ctx._ctx, ctypes.byref(ms)))
+        wall = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t = torch.tensor([ms.value, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), kms, launches
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_ms, dev_wall, kern_ms, launches = timed(step_device, args.steps)
+    clocks = sampler.summary()
+    cells = int(d_cells.sum().item())
+    used = int(d_used.item())
+    for _ in range(args.warmup):
+        step_e2e()
+    e2e_ms, e2e_wall, _, _ = timed(step_e2e, args.steps)
+
+    # parity spot check of what was just timed (not in the timed region): first 2000 windows vs the oracle
+    parity = None
+    try:
+        from oracle import oracle
+        k = min(n, 2000)
+        o = oracle.batch(wl["ref"], wl["ref_off"][:k + 1], wl["cor"], wl["cor_off"][:k + 1], wl["unc"], wl["unc_off"][:k + 1], nthreads=min(8, ncores))
+        nr = h_out["nring"].numpy()[:k]
+        ok = bool(np.array_equal(nr, o["nring"]))
+        rows = h_rows.numpy()
+        ro, st = h_out["row_off"].numpy(), h_out["stride"].numpy()
+        for w in range(k):
+            if not ok:
+                break
+            for s in range(3):
+                a = rows[ro[w] + s * st[w]: ro[w] + s * st[w] + nr[w]]
+                b = o["rows"][o["row_off"][w] + s * nr[w]: o["row_off"][w] + (s + 1) * nr[w]]
+                if not np.array_equal(a, b):
+                    ok = False
+                    break
+        parity = "bit-exact vs oracle on %d windows" % k if ok else "MISMATCH vs oracle"
+    except Exception as e:  # the oracle is only a checker here
+        parity = "not checked (%s)" % e
+
+    # roofline of the dominant kernel
+    import ctypes
+    mixed, alu = ctypes.c_double(0), ctypes.c_double(0)
+    ctx._check(lib.elector_int32_peak(ctx._ctx, ctypes.byref(mixed), ctypes.byref(alu)))
+    kern_s_per_step = kern_ms / 1e3 / args.steps
+    achieved = INT_OPS_PER_CELL * cells / kern_s_per_step / 1e12
+    hbm_peak = 6552.6
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    in_bytes = int(wl["ref_off"][-1] + wl["cor_off"][-1] + wl["unc_off"][-1]) + 3 * 8 * (n + 1)
+    out_bytes = used + n * (8 + 4 + 4)
+    alg_bytes = in_bytes + used + n * 36
+
+    value = n_trip * world * args.steps / (dev_ms / 1e3)
+    e2e_val = n_trip * world * args.steps / (e2e_ms / 1e3)
+    line = {
+        "metric": "triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 (int16 score storage)", "data": "synthetic",
+        "gcups": cells * world * args.steps / (dev_ms / 1e3) / 1e9,
+        "gcups_kernel_only": cells / kern_s_per_step / 1e9,
+        "windows_per_sec": n * world * args.steps / (dev_ms / 1e3),
+        "config": {"workload": workload_name, "windows_per_gpu": n, "cells_per_gpu": cells, "windows_from": wl["source"],
+                   "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush" % (in_bytes / 1e6), "parity": parity},
+        "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": kern_ms / args.steps,
+        "host_ms_per_step": max(0.0, (dev_wall - kern_ms) / args.steps),
+        "clocks": clocks,
+        "roofline": {"bound": "int32", "achieved": achieved, "peak": mixed.value, "unit": "TIOP/s",
+                     "frac": achieved / mixed.value if mixed.value else None, "traffic": None,
+                     "peak_alu_pipe_only": alu.value, "ops_per_cell": INT_OPS_PER_CELL,
+                     "kernel": "poa_tpw_kernel (all size-class launches of one step)",
+                     "peak_source": "measured on this device by elector_int32_peak (IMAD/IADD3/VIMNMX/LOP3 chains)"},
+        "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kern_s_per_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / kern_s_per_step / 1e9 / hbm_peak, "traffic": None,
+                         "note": "algorithmic bytes = letters + offsets in, MSA rows + per-window results out"},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        kind = "reference" if have_ref else "port"
+        k = args.cpu_triplets or int(min(n_trip, max(8, ncores * 26 * 10)))
+        cb = cpu_reference_throughput(wl, k, ncores, kind)
+        line["cpu_baseline"] = {"value": cb["triplets_per_s"], "unit": "triplets/s", "cores": ncores, "kind": kind,
+                                "sample": "first %d triplets (%d windows), %.1f s, %d concurrent single-threaded poa processes" %
+                                          (k, cb["windows"], cb["seconds"], ncores) if kind == "reference" else
+                                          "first %d triplets (%d windows), %.1f s, oracle with %d OpenMP threads" % (k, cb["windows"], cb["seconds"], ncores),
+                                "gcups": cb["gcups"]}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

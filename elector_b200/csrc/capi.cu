@@ -15,6 +15,7 @@
 #include "poa_kernel.cuh"
 #include "host_setup.hpp"
 #include "tally_kernel.cuh"
+#include "peak_kernel.cuh"
 
 using namespace elector;
 
@@ -56,7 +57,7 @@ struct elector_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
   ScoreMatrix mat;
   ScoringSetup sc;
   DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl;
@@ -126,8 +127,8 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
     const int64_t lr = h_roff[w + 1] - h_roff[w], lc = h_coff[w + 1] - h_coff[w], lu = h_uoff[w + 1] - h_uoff[w];
     if (lr <= 0 || lc <= 0 || lu <= 0)
       return ctx->fail(ELECTOR_EINVAL, "window %lld has an empty sequence (undefined in the reference)", (long long)w);
-    if (lr > 30000 || lc > 30000 || lu > 30000)
-      return ctx->fail(ELECTOR_ETOOLARGE, "window %lld longer than 30000 letters", (long long)w);
+    if (lr > 60000 || lc > 60000 || lu > 60000)
+      return ctx->fail(ELECTOR_ETOOLARGE, "window %lld longer than 60000 letters", (long long)w);
     const int ly = (int)std::max(lc, lu);
     const bool large = ly > kSmallRowsMax || (lr + lc + lu) * (int64_t)std::max(1, ctx->sc.maxabs) > 30000;
     int yb = 0;
@@ -257,6 +258,7 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->uev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->uev1)) != cudaSuccess ||
       (e = ctx->d_tab.reserve(sizeof(SymbolTables))) != cudaSuccess ||
       (e = ctx->d_ctrl.reserve(kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(ctx->d_tab.p, &ctx->sc.tab, sizeof(SymbolTables), cudaMemcpyHostToDevice)) != cudaSuccess) {
@@ -276,6 +278,8 @@ void elector_poa_free(elector_ctx *ctx) {
   for (DevBuf *b : bufs) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->uev0) cudaEventDestroy(ctx->uev0);
+  if (ctx->uev1) cudaEventDestroy(ctx->uev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -408,6 +412,48 @@ int elector_poa_files(elector_ctx *ctx, const char *ref_fa, const char *cor_fa, 
   fclose(out);
   if (rc != ELECTOR_OK) return rc;
   if (ragged) return ctx->fail(ELECTOR_EIO, "record counts differ (ref %zu, corrected %zu, uncorrected %zu); aligned the first %zu", R.rec.size(), C.rec.size(), U.rec.size(), n);
+  return ELECTOR_OK;
+}
+
+int elector_event_record(elector_ctx *ctx, int which) {
+  if (!ctx) return ELECTOR_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(which ? ctx->uev1 : ctx->uev0, ctx->stream));
+  return ELECTOR_OK;
+}
+
+int elector_event_elapsed_ms(elector_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return ELECTOR_EINVAL;
+  CU(cudaEventSynchronize(ctx->uev1));
+  CU(cudaEventElapsedTime(ms, ctx->uev0, ctx->uev1));
+  return ELECTOR_OK;
+}
+
+int elector_int32_peak(elector_ctx *ctx, double *tiops_mixed, double *tiops_alu) {
+  if (!ctx) return ELECTOR_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  const int grid = ctx->sm_count * 8, iters = 4096;
+  CU(ctx->d_scratch.reserve((size_t)grid * 256 * 4));
+  double res[2] = {0, 0};
+  for (int mode = 0; mode < 2; ++mode) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      CU(cudaEventRecord(ctx->ev0, ctx->stream));
+      if (mode == 0) int32_peak_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->d_scratch.as<int>(), iters, 3, 7);
+      else int32_peak_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->d_scratch.as<int>(), iters, 3, 7);
+      CU(cudaEventRecord(ctx->ev1, ctx->stream));
+      CU(cudaEventSynchronize(ctx->ev1));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    // lane-operations per iteration of the unrolled body: mixed = 8*(4 IMAD + 2*(IADD+IMNMX) + 2*(LOP+IADD)) = 8*12,
+    // alu-only = 8*(4*(IADD+IMNMX) + 4*(LOP+IADD)) = 8*16
+    const double ops = (double)grid * 256 * iters * (mode == 0 ? 96.0 : 128.0);
+    res[mode] = ops / (best * 1e-3) / 1e12;
+  }
+  if (tiops_mixed) *tiops_mixed = res[0];
+  if (tiops_alu) *tiops_alu = res[1];
   return ELECTOR_OK;
 }
 

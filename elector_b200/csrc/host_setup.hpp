@@ -86,7 +86,7 @@ inline void make_layout(ClassLayout &L, int LR, int LC, int LU, bool large) {
   L.o_cor = o; o += cdiv_u(LC, 4);
   L.o_unc = o; o += cdiv_u(LU, 4);
   L.o_nodeA = o; o += N1;
-  L.o_nodeB = o; o += N1;
+  L.o_nodeB = o; o += 2 * N1;
   L.o_moves = o; o += std::max((uint32_t)LR * cdiv_u(LC, 16), N1 * cdiv_u(LU, 16));
   L.ord_wpn = cdiv_u(LU + 1, 8);
   L.o_ord = o; o += ((uint32_t)std::min(LR, LC) + 2) * L.ord_wpn;

@@ -80,7 +80,7 @@ enum : uint32_t {
   NF_FINAL = 1u << 11,   // carries the last position of some source (:54-56)
   NF_SAMERING = 1u << 12,// on the same align ring as the previous node
   NF_VIRT = 1u << 13,    // left list starts with the virtual -1 link (:69-75)
-  NF_COMB = 1u << 14     // left list has >1 entries: ordinals stored in slot (bits 16..31)
+  NF_COMB = 1u << 14     // left list has >1 entries: winning ordinals are kept in an o_ord slot
 };
 
 #define EL_WARP_FULL 0xffffffffu
@@ -190,7 +190,8 @@ struct WindowCtx {
       }
       if (virt) ra |= NF_VIRT;
       sw(L->o_nodeA + j) = ra;
-      sw(L->o_nodeB + j) = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
+      sw(L->o_nodeB + 2 * j) = (uint32_t)pA;
+      sw(L->o_nodeB + 2 * j + 1) = (uint32_t)pB;
 
       // main column loop
       int pS, pG, S, G, diagS, upG;
@@ -242,8 +243,7 @@ struct WindowCtx {
           const uint32_t nib = (sw(L->o_ord + (ra >> 16) * L->ord_wpn + (rr >> 3)) >> ((rr & 7) * 4)) & 15u;
           ord = (kind & 1u) ? (nib & 3u) : (nib >> 2);
         }
-        const uint32_t rb = sw(L->o_nodeB + j);
-        const int pA = (int)(int16_t)(rb & 0xffffu), pB = (int)(int16_t)(rb >> 16);
+        const int pA = (int)sw(L->o_nodeB + 2 * j), pB = (int)sw(L->o_nodeB + 2 * j + 1);
         int nj;
         if (ra & NF_VIRT) nj = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
         else nj = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone

@@ -1,0 +1,128 @@
+"""Host-side mirror of the `poa` boundary over the C-ABI (include/elector_poa.h).
+
+The reference's interface for this path is the `poa` command line (main.c:85-113) and
+its PIR output (lpo_format.c:398-426); `PoaContext.files()` is that call in-process,
+`PoaContext.run()` is the same computation on in-memory windows, `PoaContext.tally()`
+the integer part of computeStats.py's per-read tally.  numpy is used for the host
+buffers only; all arithmetic happens in the CUDA library.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from .lib import load_library
+
+TALLY_FIELDS = ["TP", "FP", "FN", "cor", "uncor", "uncorCor", "uncorUncor", "insC", "delC", "subsC",
+                "insU", "delU", "subsU", "GCref", "GCcor", "lenRef", "lenCor", "lenUnc", "gapsLeft",
+                "gapsRight", "missing", "extended", "ncols", "assessed"]
+
+
+class ElectorError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("elector error %d: %s" % (code, msg))
+        self.code = code
+
+
+def windows_to_csr(seqs):
+    """list of str/bytes -> (uint8 array of all letters, int64 offsets[n+1])"""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    cat = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    return cat, off
+
+
+@dataclass
+class PoaResult:
+    rows: np.ndarray        # uint8 buffer holding every row
+    row_off: np.ndarray     # int64[n]
+    row_stride: np.ndarray  # int32[n]
+    nring: np.ndarray       # int32[n]
+    score1: np.ndarray
+    score2: np.ndarray
+    cells: np.ndarray       # int64[n]
+
+    def window_rows(self, w):
+        o, st, k = int(self.row_off[w]), int(self.row_stride[w]), int(self.nring[w])
+        return tuple(self.rows[o + s * st:o + s * st + k].tobytes().decode("latin-1") for s in range(3))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class PoaContext:
+    """One context per device per thread (like one `poa` process)."""
+
+    def __init__(self, device=0, matrix_path=None):
+        self._lib = load_library()
+        self._ctx = ctypes.c_void_p()
+        mp = matrix_path.encode() if matrix_path else None
+        rc = self._lib.elector_poa_init(int(device), mp, ctypes.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.elector_last_error(None).decode()
+            self._ctx = None
+            raise ElectorError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.elector_poa_free(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ElectorError(rc, self._lib.elector_last_error(self._ctx).decode())
+
+    def run_csr(self, ref, ref_off, cor, cor_off, unc, unc_off, rows=None):
+        n = len(ref_off) - 1
+        ref_off, cor_off, unc_off = (np.ascontiguousarray(o, dtype=np.int64) for o in (ref_off, cor_off, unc_off))
+        ref, cor, unc = (np.ascontiguousarray(s, dtype=np.uint8) for s in (ref, cor, unc))
+        bound = self._lib.elector_poa_rows_bound(n, _p(ref_off), _p(cor_off), _p(unc_off)) if n else 0
+        if rows is None or len(rows) < bound:
+            rows = np.empty(max(bound, 1), dtype=np.uint8)
+        res = PoaResult(rows, np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.int32),
+                        np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int64))
+        self._check(self._lib.elector_poa_run(self._ctx, n, _p(ref), _p(ref_off), _p(cor), _p(cor_off), _p(unc),
+                                              _p(unc_off), _p(res.rows), len(res.rows), _p(res.row_off),
+                                              _p(res.row_stride), _p(res.nring), _p(res.score1), _p(res.score2),
+                                              _p(res.cells)))
+        return res
+
+    def run(self, refs, cors, uncs):
+        """refs/cors/uncs: equal-length lists of window sequences (str or bytes)."""
+        r, ro = windows_to_csr(refs)
+        c, co = windows_to_csr(cors)
+        u, uo = windows_to_csr(uncs)
+        return self.run_csr(r, ro, c, co, u, uo)
+
+    def files(self, ref_fasta, cor_fasta, unc_fasta, pir_out, print_perm=False):
+        """The body of one `poa` process (main.c:241-287)."""
+        self._check(self._lib.elector_poa_files(self._ctx, ref_fasta.encode(), cor_fasta.encode(), unc_fasta.encode(),
+                                                pir_out.encode(), int(bool(print_perm))))
+
+    def tally(self, rows_ref, rows_cor, rows_unc):
+        """Per-read integer counters (computeStats.py) for merged MSA rows; returns int64[n, K]."""
+        r, off = windows_to_csr(rows_ref)
+        c, off_c = windows_to_csr(rows_cor)
+        u, off_u = windows_to_csr(rows_unc)
+        if not (np.array_equal(off, off_c) and np.array_equal(off, off_u)):
+            raise ValueError("the three rows of a read must have equal length")
+        n = len(off) - 1
+        out = np.zeros((n, len(TALLY_FIELDS)), dtype=np.int64)
+        self._check(self._lib.elector_tally_run(self._ctx, n, _p(r), _p(c), _p(u), _p(off), _p(out)))
+        return out
+
+    def last_kernel_ms(self):
+        ms, k = ctypes.c_float(0), ctypes.c_int(0)
+        self._lib.elector_last_kernel_ms(self._ctx, ctypes.byref(ms), ctypes.byref(k))
+        return ms.value, k.value

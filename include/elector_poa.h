@@ -123,6 +123,17 @@ int elector_merge_tally_device(elector_ctx *ctx, int64_t n_reads, const int64_t 
                                const int32_t *d_row_stride, const int32_t *d_nring,
                                int64_t *d_counters_out);
 
+/* Device-side timing for callers (bench.py): which = 0 records the start event, 1 the stop
+ * event, both on the context's launching stream; elapsed returns the milliseconds between
+ * them after synchronising on the stop event. */
+int elector_event_record(elector_ctx *ctx, int which);
+int elector_event_elapsed_ms(elector_ctx *ctx, float *ms);
+
+/* Measured INT32 issue peak of this device (the roofline denominator of the DP kernel):
+ * a register-only chain of IMAD / IADD3 / VIMNMX on every SM; returns tera integer
+ * lane-operations per second (an fma-pipe IMAD counts once, like an alu-pipe op). */
+int elector_int32_peak(elector_ctx *ctx, double *tiops_mixed, double *tiops_alu_only);
+
 /* Timing of the kernels launched by the last run on this context, measured with CUDA
  * events on the launching stream: total ms and number of kernel launches. */
 int elector_last_kernel_ms(const elector_ctx *ctx, float *ms, int *launches);

@@ -609,6 +609,49 @@ int ora_poa_files(const char *matrix, const char *ref_fa, const char *cor_fa,
   return n;
 }
 
+/* same text format as oracle/ref_harness.c (the dump of the compiled reference) */
+static void dump_map(FILE *f, const char *tag, int n, const int *m)
+{
+  int i;
+  fprintf(f, "%s %d", tag, n);
+  for (i = 0; i < n; i++) fprintf(f, " %d", m[i]);
+  fputc('\n', f);
+}
+
+int ora_dump_files(const char *matrix, const char *ref_fa, const char *cor_fa,
+                   const char *unc_fa, const char *dump_out)
+{
+  ora_matrix m;
+  fa_list R, C, U;
+  FILE *out;
+  int i, n;
+  if (ora_read_matrix(matrix, &m) <= 0) return 1;
+  if (fa_read(cor_fa, &C) < 0) return 1;
+  if (fa_read(unc_fa, &U) < 0) { fa_free(&C); return 1; }
+  if (fa_read(ref_fa, &R) < 0) { fa_free(&C); fa_free(&U); return 1; }
+  n = R.n;
+  if (C.n < n) n = C.n;
+  if (U.n < n) n = U.n;
+  out = fopen(dump_out, "w");
+  if (!out) return 1;
+  for (i = 0; i < n; i++) {
+    ora_result r;
+    ora_window(&m, R.r[i].seq, R.r[i].len, C.r[i].seq, C.r[i].len, U.r[i].seq, U.r[i].len, &r);
+    fprintf(out, "W %d %d %d %d\n", i, R.r[i].len, C.r[i].len, U.r[i].len);
+    fprintf(out, "S1 %d\n", r.score1);
+    dump_map(out, "X1", R.r[i].len, r.x2y1);
+    dump_map(out, "Y1", C.r[i].len, r.y2x1);
+    fprintf(out, "S2 %d %d\n", r.score2, r.len_p1);
+    dump_map(out, "X2", r.len_p1, r.x2y2);
+    dump_map(out, "Y2", U.r[i].len, r.y2x2);
+    fprintf(out, "L %d\n", r.len_p2);
+    ora_free_result(&r);
+  }
+  fclose(out);
+  fa_free(&R); fa_free(&C); fa_free(&U);
+  return 0;
+}
+
 #ifdef ORA_MAIN
 /* oracle CLI with the reference's five flags (main.c:85-113) */
 int main(int argc, char **argv)

@@ -74,6 +74,10 @@ int ora_batch(const ora_matrix *m, int n, const char *ref, const long long *ref_
 int ora_poa_files(const char *matrix, const char *ref_fa, const char *cor_fa,
                   const char *unc_fa, const char *pir_out, int print_perm);
 
+/* writes scores + alignment maps in the text format of oracle/ref_harness.c */
+int ora_dump_files(const char *matrix, const char *ref_fa, const char *cor_fa,
+                   const char *unc_fa, const char *dump_out);
+
 #ifdef __cplusplus
 }
 #endif
