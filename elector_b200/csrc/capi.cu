@@ -94,7 +94,7 @@ cudaError_t launch_class(elector_ctx *ctx, PoaArgs &a, int grid, size_t smem) {
   auto k = poa_tpw_kernel<GC, GS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<grid, 128, smem, ctx->stream>>>(a, ctx->d_tab.as<SymbolTables>());
+  k<<<grid, 32, smem, ctx->stream>>>(a, ctx->d_tab.as<SymbolTables>());
   return cudaGetLastError();
 }
 
@@ -103,7 +103,7 @@ int occupancy(size_t smem) {
   auto k = poa_tpw_kernel<GC, GS>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 128, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32, smem);
   return nb;
 }
 
@@ -184,22 +184,23 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   for (size_t ci = 0; ci < classes.size(); ++ci) {
     SizeClass &c = classes[ci];
     make_layout(c.L, c.L.LR, c.L.LC, c.L.LU, c.large);
-    const size_t smem = sizeof(SymbolTables) + (c.large ? 0 : (size_t)4 * 2 * (c.L.LY + 1) * 32 * 4);
+    const size_t smem = (ctx->sc.generic_sub ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) +
+                        (c.large ? 0 : (size_t)2 * (c.L.LY + 1) * 32 * 4);
     if (smem > ctx->smem_optin) return ctx->fail(ELECTOR_ECUDA, "class needs %zu B shared memory", smem);
     int nb;
     if (c.large) nb = ctx->sc.generic_sub ? occupancy<true, true>(smem) : occupancy<true, false>(smem);
     else nb = ctx->sc.generic_sub ? occupancy<false, true>(smem) : occupancy<false, false>(smem);
     if (nb < 1) return ctx->fail(ELECTOR_ECUDA, "kernel does not fit (smem %zu)", smem);
     const int64_t groups = ((int64_t)c.items.size() + 31) / 32;
-    int grid = (int)std::min<int64_t>((int64_t)nb * ctx->sm_count, (groups + 3) / 4);
+    int grid = (int)std::min<int64_t>((int64_t)nb * ctx->sm_count, groups);
     if (grid < 1) grid = 1;
     // bound the scratch of big classes: fewer resident warps when windows are huge
     const size_t per_warp = (size_t)c.L.total * 32 * 4;
     const size_t budget = (size_t)8 << 30;
-    while (grid > 1 && per_warp * 4 * (size_t)grid > budget) grid = (grid + 1) / 2;
-    if (per_warp * 4 * (size_t)grid > ((size_t)48 << 30))
+    while (grid > 1 && per_warp * (size_t)grid > budget) grid = (grid + 1) / 2;
+    if (per_warp * (size_t)grid > ((size_t)48 << 30))
       return ctx->fail(ELECTOR_ETOOLARGE, "window class %dx%dx%d needs %zu MiB scratch per warp", c.L.LR, c.L.LC, c.L.LU, per_warp >> 20);
-    CU(ctx->d_scratch.reserve(per_warp * 4 * (size_t)grid));
+    CU(ctx->d_scratch.reserve(per_warp * (size_t)grid));
     PoaArgs a;
     a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
     a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;

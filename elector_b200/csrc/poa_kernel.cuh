@@ -28,6 +28,7 @@
 // to S, G = S - pen(g): the value a successor uses for a gap move out of this cell.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace elector {
@@ -348,21 +349,22 @@ struct WindowCtx {
   }
 };
 
-// Persistent kernel: each warp repeatedly takes 32 consecutive items of the (size-sorted)
-// work list; lane l owns item base+l.
+// Persistent kernel, one warp per CTA (up to 32 CTAs per SM; shared memory per CTA is what
+// bounds residency): each warp repeatedly takes 32 consecutive items of the size-sorted
+// work list; lane l owns item base+l.  Shared memory: symbol tables (the 2 KB substitution
+// table only for non-uniform matrices) followed by the two column buffers.
 template <bool GLOBAL_COLS, bool GENERIC_SUB>
-__global__ void __launch_bounds__(128) poa_tpw_kernel(PoaArgs a, const SymbolTables *g_tab) {
+__global__ void __launch_bounds__(32) poa_tpw_kernel(PoaArgs a, const SymbolTables *g_tab) {
   extern __shared__ uint32_t smem[];
   SymbolTables *tab = reinterpret_cast<SymbolTables *>(smem);
+  constexpr int kTabWords = (GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4;
   {
     const uint32_t *s = reinterpret_cast<const uint32_t *>(g_tab);
-    uint32_t *d = reinterpret_cast<uint32_t *>(tab);
-    for (int i = threadIdx.x; i < (int)(sizeof(SymbolTables) / 4); i += blockDim.x) d[i] = s[i];
+    for (int i = threadIdx.x; i < kTabWords; i += 32) smem[i] = s[i];
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const size_t warp_slot = (size_t)blockIdx.x * warps_per_block + wib;
+  __syncwarp();
+  const int lane = threadIdx.x;
+  const size_t warp_slot = blockIdx.x;
 
   WindowCtx<GLOBAL_COLS, GENERIC_SUB> c;
   c.scr = a.scratch + warp_slot * (size_t)a.L.total * 32;
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(128) poa_tpw_kernel(PoaArgs a, const SymbolTab
   c.lane = lane;
   c.match = a.match; c.mismatch = a.mismatch; c.open = a.open; c.ext = a.ext;
   c.colrows = a.L.LY + 1;
-  c.cols = smem + sizeof(SymbolTables) / 4 + (size_t)wib * 2 * c.colrows * 32;
+  c.cols = smem + kTabWords;
 
   for (;;) {
     int base = 0;
