@@ -62,7 +62,7 @@ struct elector_ctx {
   ScoringSetup sc;
   DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
-  DevBuf d_tally_in, d_tally_off, d_tally_out, d_readfirst;
+  DevBuf d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
   std::string err;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -274,8 +274,8 @@ void elector_poa_free(elector_ctx *ctx) {
   if (!ctx) return;
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
                     &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
-                    &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_tally_in, &ctx->d_tally_off,
-                    &ctx->d_tally_out, &ctx->d_readfirst};
+                    &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_tally_scan, &ctx->d_tally_out,
+                    &ctx->d_readfirst, &ctx->d_mtot, &ctx->d_moff, &ctx->d_mlen, &ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
   for (DevBuf *b : bufs) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

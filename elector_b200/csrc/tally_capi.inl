@@ -1,12 +1,130 @@
 // tally_capi.inl -- C-ABI entry points of the merge + tally (included by capi.cu)
+namespace {
+
+// scan + count on device-resident merged rows; counters land in d_counters
+int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uint8_t *dC, const uint8_t *dU,
+                 const int64_t *d_off, const int32_t *d_len, int64_t *d_counters) {
+  if (n_reads == 0) return ELECTOR_OK;
+  CU(ctx->d_tally_scan.reserve((size_t)n_reads * sizeof(ReadScan)));
+  ReadScan *sc = ctx->d_tally_scan.as<ReadScan>();
+  tally_scan_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, ctx->stream>>>(n_reads, dR, dC, dU, d_off, d_len, sc);
+  tally_count_kernel<<<(unsigned)n_reads, 128, 0, ctx->stream>>>(n_reads, dR, dC, dU, d_off, d_len, sc, d_counters);
+  CU(cudaGetLastError());
+  ctx->last_launches += 2;
+  return ELECTOR_OK;
+}
+
+// offsets + merge on device-resident window rows; merged rows land in ctx->d_m{ref,cor,unc}
+int merge_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first, int64_t n_windows, const uint8_t *d_rows,
+                 int64_t rows_bytes, const int64_t *d_row_off, const int32_t *d_row_stride, const int32_t *d_nring) {
+  if (h_read_first[0] != 0 || h_read_first[n_reads] != n_windows) return ctx->fail(ELECTOR_EINVAL, "read_first must span 0..n_windows");
+  const int64_t cap = rows_bytes / 3 + 16 * n_reads + 16;
+  CU(ctx->d_readfirst.reserve((n_reads + 1) * 8));
+  CU(ctx->d_mtot.reserve((n_reads + 1) * 8));
+  CU(ctx->d_moff.reserve((n_reads + 1) * 8));
+  CU(ctx->d_mlen.reserve((n_reads + 1) * 4));
+  CU(ctx->d_mref.reserve(cap)); CU(ctx->d_mcor.reserve(cap)); CU(ctx->d_munc.reserve(cap));
+  CU(cudaMemcpyAsync(ctx->d_readfirst.p, h_read_first, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  read_totals_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_nring, ctx->d_mtot.as<int64_t>());
+  scan_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_reads, ctx->d_mtot.as<int64_t>(), ctx->d_moff.as<int64_t>());
+  merge_rows_kernel<<<(unsigned)((n_reads + 3) / 4), 128, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_rows, d_row_off, d_row_stride, d_nring,
+                                                                            ctx->d_moff.as<int64_t>(), ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(),
+                                                                            ctx->d_munc.as<uint8_t>(), ctx->d_mlen.as<int32_t>());
+  CU(cudaGetLastError());
+  ctx->last_launches += 3;
+  return ELECTOR_OK;
+}
+
+int check_scan_overflow(elector_ctx *ctx, int64_t n_reads) {
+  std::vector<ReadScan> h(n_reads);
+  CU(cudaMemcpyAsync(h.data(), ctx->d_tally_scan.p, n_reads * sizeof(ReadScan), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int64_t r = 0; r < n_reads; ++r)
+    if (h[r].overflow) return ctx->fail(ELECTOR_EUNSUPPORTED, "read %lld has more than %d gap stretches at its borders", (long long)r, kMaxStretchKeys);
+  return ELECTOR_OK;
+}
+
+}  // namespace
+
 extern "C" {
-int elector_tally_run(elector_ctx *ctx, int64_t, const char *, const char *, const char *, const int64_t *, int64_t *) {
+
+int elector_tally_run(elector_ctx *ctx, int64_t n_reads, const char *row_ref, const char *row_cor, const char *row_unc,
+                      const int64_t *row_off, int64_t *counters_out) {
   if (!ctx) return ELECTOR_EINVAL;
-  return ctx->fail(ELECTOR_EUNSUPPORTED, "tally kernels not built yet");
+  if (n_reads < 0 || (n_reads > 0 && (!row_ref || !row_cor || !row_unc || !row_off || !counters_out))) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_reads == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  const int64_t bytes = row_off[n_reads];
+  CU(ctx->d_mref.reserve(bytes + 16)); CU(ctx->d_mcor.reserve(bytes + 16)); CU(ctx->d_munc.reserve(bytes + 16));
+  CU(ctx->d_moff.reserve((n_reads + 1) * 8));
+  CU(ctx->d_tally_out.reserve(n_reads * ELECTOR_TALLY_K * 8));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->d_mref.p, row_ref, bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_mcor.p, row_cor, bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_munc.p, row_unc, bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_moff.p, row_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+  ctx->last_launches = 0;
+  CU(cudaEventRecord(ctx->ev0, st));
+  int rc = tally_device(ctx, n_reads, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
+                        ctx->d_moff.as<int64_t>(), nullptr, ctx->d_tally_out.as<int64_t>());
+  if (rc != ELECTOR_OK) return rc;
+  CU(cudaEventRecord(ctx->ev1, st));
+  CU(cudaMemcpyAsync(counters_out, ctx->d_tally_out.p, n_reads * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+  rc = check_scan_overflow(ctx, n_reads);
+  cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+  return rc;
 }
-int elector_merge_tally_device(elector_ctx *ctx, int64_t, const int64_t *, int64_t, const char *, const int64_t *,
-                               const int32_t *, const int32_t *, int64_t *) {
+
+int elector_merge_run(elector_ctx *ctx, int64_t n_reads, const int64_t *read_first, int64_t n_windows, const char *rows,
+                      int64_t rows_bytes, const int64_t *row_off, const int32_t *row_stride, const int32_t *nring,
+                      char *m_ref, char *m_cor, char *m_unc, int64_t m_cap, int64_t *m_off, int32_t *m_len) {
   if (!ctx) return ELECTOR_EINVAL;
-  return ctx->fail(ELECTOR_EUNSUPPORTED, "tally kernels not built yet");
+  if (n_reads < 0 || n_windows < 0 || (n_reads > 0 && (!read_first || !rows || !row_off || !row_stride || !nring || !m_ref || !m_cor || !m_unc || !m_off || !m_len)))
+    return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_reads == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(ctx->d_rows.reserve(rows_bytes)); CU(ctx->d_rowoff.reserve(n_windows * 8)); CU(ctx->d_stride.reserve(n_windows * 4)); CU(ctx->d_nring.reserve(n_windows * 4));
+  CU(cudaMemcpyAsync(ctx->d_rows.p, rows, rows_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_rowoff.p, row_off, n_windows * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_stride.p, row_stride, n_windows * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_nring.p, nring, n_windows * 4, cudaMemcpyHostToDevice, st));
+  ctx->last_launches = 0;
+  int rc = merge_device(ctx, n_reads, read_first, n_windows, ctx->d_rows.as<uint8_t>(), rows_bytes, ctx->d_rowoff.as<int64_t>(),
+                        ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>());
+  if (rc != ELECTOR_OK) return rc;
+  std::vector<int64_t> off(n_reads + 1);
+  CU(cudaMemcpyAsync(off.data(), ctx->d_moff.p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(m_len, ctx->d_mlen.p, n_reads * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (off[n_reads] > m_cap) return ctx->fail(ELECTOR_ECAPACITY, "merged rows need %lld bytes per buffer, capacity %lld", (long long)off[n_reads], (long long)m_cap);
+  memcpy(m_off, off.data(), n_reads * 8);
+  CU(cudaMemcpyAsync(m_ref, ctx->d_mref.p, off[n_reads], cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(m_cor, ctx->d_mcor.p, off[n_reads], cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(m_unc, ctx->d_munc.p, off[n_reads], cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ELECTOR_OK;
 }
+
+int elector_merge_tally_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first, int64_t n_windows,
+                               const char *d_rows, int64_t rows_bytes, const int64_t *d_row_off, const int32_t *d_row_stride,
+                               const int32_t *d_nring, int64_t *d_counters_out) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (n_reads < 0 || (n_reads > 0 && (!h_read_first || !d_rows || !d_row_off || !d_row_stride || !d_nring || !d_counters_out)))
+    return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_reads == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  ctx->last_launches = 0;
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = merge_device(ctx, n_reads, h_read_first, n_windows, (const uint8_t *)d_rows, rows_bytes, d_row_off, d_row_stride, d_nring);
+  if (rc != ELECTOR_OK) return rc;
+  rc = tally_device(ctx, n_reads, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
+                    ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(), d_counters_out);
+  if (rc != ELECTOR_OK) return rc;
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  rc = check_scan_overflow(ctx, n_reads);
+  cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+  return rc;
 }
+
+}  // extern "C"

@@ -48,7 +48,9 @@ def load_library():
     lib.elector_poa_files.restype = c.c_int
     lib.elector_tally_run.argtypes = [vp, c.c_int64, vp, vp, vp, vp, vp]
     lib.elector_tally_run.restype = c.c_int
-    lib.elector_merge_tally_device.argtypes = [vp, c.c_int64, vp, c.c_int64, vp, vp, vp, vp, vp]
+    lib.elector_merge_run.argtypes = [vp, c.c_int64, vp, c.c_int64, vp, c.c_int64, vp, vp, vp, vp, vp, vp, c.c_int64, vp, vp]
+    lib.elector_merge_run.restype = c.c_int
+    lib.elector_merge_tally_device.argtypes = [vp, c.c_int64, vp, c.c_int64, vp, c.c_int64, vp, vp, vp, vp]
     lib.elector_merge_tally_device.restype = c.c_int
     lib.elector_last_kernel_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_int)]
     lib.elector_last_kernel_ms.restype = c.c_int

@@ -122,6 +122,19 @@ class PoaContext:
         self._check(self._lib.elector_tally_run(self._ctx, n, _p(r), _p(c), _p(u), _p(off), _p(out)))
         return out
 
+    def merge(self, res, read_first):
+        """Donatello's per-read merge of a PoaResult (Donatello.cpp:50-84); returns list of (R, C, U) strings."""
+        read_first = np.ascontiguousarray(read_first, dtype=np.int64)
+        n_reads, n_win = len(read_first) - 1, len(res.nring)
+        used = int((res.row_off + 3 * res.row_stride.astype(np.int64)).max()) if n_win else 0
+        cap = int(res.nring.sum()) + 16 * n_reads + 16
+        m = [np.zeros(cap, np.uint8) for _ in range(3)]
+        m_off, m_len = np.zeros(n_reads, np.int64), np.zeros(n_reads, np.int32)
+        self._check(self._lib.elector_merge_run(self._ctx, n_reads, _p(read_first), n_win, _p(res.rows), used, _p(res.row_off),
+                                                _p(res.row_stride), _p(res.nring), _p(m[0]), _p(m[1]), _p(m[2]), cap,
+                                                _p(m_off), _p(m_len)))
+        return [tuple(m[s][m_off[r]:m_off[r] + m_len[r]].tobytes().decode("latin-1") for s in range(3)) for r in range(n_reads)]
+
     def last_kernel_ms(self):
         ms, k = ctypes.c_float(0), ctypes.c_int(0)
         self._lib.elector_last_kernel_ms(self._ctx, ctypes.byref(ms), ctypes.byref(k))

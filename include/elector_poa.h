@@ -114,14 +114,24 @@ int elector_tally_run(elector_ctx *ctx, int64_t n_reads, const char *row_ref,
                       const char *row_cor, const char *row_unc, const int64_t *row_off,
                       int64_t *counters_out);
 
-/* Device-side merge of window MSAs into per-read rows (Donatello semantics) chained on
- * the output of elector_poa_run_device, followed by the tally, all on the device.
- * read_first[r] .. read_first[r+1]-1 are the windows of read r (host array, n_reads+1).
- * d_counters_out: n_reads*ELECTOR_TALLY_K int64 on the device. */
+/* Replaces: `Donatello smsa<i> msa.fa` (Donatello.cpp:50-84) on in-memory window MSAs: the
+ * windows read_first[r] .. read_first[r+1]-1 (consecutive records with the same header) are
+ * concatenated and every column whose corrected row is 'n' is dropped (clean_msa :13-31).
+ * Window rows are addressed as in elector_poa_run's output.  Merged read r occupies
+ * m_len[r] bytes at offset m_off[r] in each of m_ref / m_cor / m_unc (m_cap bytes each;
+ * the sum of nring plus 16 bytes per read always suffices). */
+int elector_merge_run(elector_ctx *ctx, int64_t n_reads, const int64_t *read_first, int64_t n_windows,
+                      const char *rows, int64_t rows_bytes, const int64_t *row_off, const int32_t *row_stride,
+                      const int32_t *nring, char *m_ref, char *m_cor, char *m_unc, int64_t m_cap,
+                      int64_t *m_off, int32_t *m_len);
+
+/* The same merge followed by the tally, chained on the device-resident output of
+ * elector_poa_run_device (nothing returns to the host except through d_counters_out, which
+ * is device memory: n_reads*ELECTOR_TALLY_K int64).  h_read_first is a host array. */
 int elector_merge_tally_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first,
-                               int64_t n_windows, const char *d_rows, const int64_t *d_row_off,
-                               const int32_t *d_row_stride, const int32_t *d_nring,
-                               int64_t *d_counters_out);
+                               int64_t n_windows, const char *d_rows, int64_t rows_bytes,
+                               const int64_t *d_row_off, const int32_t *d_row_stride,
+                               const int32_t *d_nring, int64_t *d_counters_out);
 
 /* Device-side timing for callers (bench.py): which = 0 records the start event, 1 the stop
  * event, both on the context's launching stream; elapsed returns the milliseconds between

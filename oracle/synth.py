@@ -147,3 +147,42 @@ def reads(n, length_fn, seed, raw_rate=0.10, keep=0.1, ratios=(1, 1, 1), homopol
 
 def loguniform(lo, hi):
     return lambda rng: int(math.exp(math.log(lo) + rng.unit() * (math.log(hi) - math.log(lo))))
+
+
+def random_msa_rows(n, seed=21):
+    """gap-rich random 3-row MSAs (ref, corrected, uncorrected) for the tally: long '.' runs at the
+    borders (trimmed / extended reads), gap stretches inside, 'n' never present (Donatello drops
+    those columns).  Returns list of (R, C, U) strings of equal length."""
+    rng = SplitMix64(seed)
+    out = []
+    for _ in range(n):
+        L = 11 + rng.below(400) if rng.below(8) else 1 + rng.below(14)
+        rows = []
+        base = [("acgt")[rng.below(4)] for _ in range(L)]
+        for k in range(3):
+            row = []
+            p_gap = [0.02, 0.05, 0.15][rng.below(3)]
+            p_mut = [0.0, 0.02, 0.2][rng.below(3)]
+            i = 0
+            while i < L:
+                if rng.unit() < p_gap / 4:
+                    run = 1 + rng.below([3, 8, 30, 60][rng.below(4)])
+                    row.extend("." * min(run, L - i))
+                    i += min(run, L - i)
+                else:
+                    row.append("acgt"[rng.below(4)] if rng.unit() < p_mut else base[i])
+                    i += 1
+            # border effects
+            t = rng.below(10)
+            if t == 0:
+                g = min(L, 3 + rng.below(40)); row[:g] = "." * g
+            elif t == 1:
+                g = min(L, 3 + rng.below(40)); row[L - g:] = "." * g
+            elif t == 2:
+                g = min(L // 2, 3 + rng.below(30)); row[:g] = "." * g; row[L - g:] = "." * g
+            row = row[:L]
+            if all(ch == "." for ch in row):  # the reference divides by the non-gap length
+                row[rng.below(L)] = base[0]
+            rows.append("".join(row))
+        out.append((rows[0], rows[1], rows[2]))
+    return out

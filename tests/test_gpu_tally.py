@@ -1,0 +1,127 @@
+"""GPU: merge (Donatello) + tally (computeStats) kernels through the C-ABI against the
+reference-generated goldens and the oracle."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, parse_pir
+
+pytestmark = pytest.mark.gpu
+INT_FIELDS = ["TP", "FP", "FN", "cor", "uncor", "uncorCor", "uncorUncor", "insC", "delC", "subsC", "insU", "delU",
+              "subsU", "lenRef", "lenCor", "lenUnc", "gapsLeft", "gapsRight", "missing", "extended", "ncols", "assessed"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import elector_b200
+    c = elector_b200.PoaContext(device=0)
+    yield c
+    c.close()
+
+
+def load(name):
+    return json.loads(gzip.open(os.path.join(GOLD, name)).read())
+
+
+def check(fields, got_row, exp):
+    got = dict(zip(fields, (int(v) for v in got_row)))
+    if not exp["assessed"]:
+        assert got["assessed"] == 0 and got["ncols"] == exp["ncols"]
+        return
+    for k in INT_FIELDS:
+        assert got[k] == exp[k], (k, got[k], exp[k])
+    assert round(got["GCref"] * 1.0 / got["lenRef"], 3) == exp["GCrateRef"]
+    assert round(got["GCcor"] * 1.0 / got["lenCor"], 3) == exp["GCrateCor"]
+
+
+def test_tally_equals_computestats_on_example_reads(ctx):
+    from elector_b200 import TALLY_FIELDS
+    ex = load("tally_example.json.gz")
+    out = ctx.tally([e["R"] for e in ex], [e["C"] for e in ex], [e["U"] for e in ex])
+    for e, row in zip(ex, out):
+        check(TALLY_FIELDS, row, e["expect"])
+
+
+def test_tally_equals_computestats_on_random_rows(ctx):
+    from elector_b200 import TALLY_FIELDS
+    from oracle import synth
+    exp = load("tally_random.json.gz")
+    rows = synth.random_msa_rows(3000, 21)
+    out = ctx.tally([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows])
+    for e, row in zip(exp, out):
+        check(TALLY_FIELDS, row, e)
+
+
+def test_tally_vs_oracle_fresh_seed(ctx):
+    from elector_b200 import TALLY_FIELDS
+    from oracle import synth, tally_oracle as to
+    rows = synth.random_msa_rows(4000, 777)
+    out = ctx.tally([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows])
+    for (R, C, U), row in zip(rows, out):
+        exp = to.tally_read(R, C, U)
+        assert [int(v) for v in row] == [exp[k] for k in TALLY_FIELDS]
+
+
+def test_merge_equals_donatello(ctx, golden_dir):
+    """poa windows of 6 example reads -> merged rows identical to the reference Donatello's msa file"""
+    from elector_b200 import windows_to_csr
+    from conftest import read_fasta_simple
+    recs = parse_pir(golden_dir + "/donatello.pir")
+    exp = open(golden_dir + "/donatello.msa").read().split("\n")
+    # rebuild the window inputs from the PIR rows themselves (a row without '.' is the sequence)
+    refs = [r[1][0].replace(".", "") for r in recs]; cors = [r[1][1].replace(".", "") for r in recs]; uncs = [r[1][2].replace(".", "") for r in recs]
+    res = ctx.run(refs, cors, uncs)
+    for w, r in enumerate(recs):
+        assert res.window_rows(w) == r[1]
+    heads = [r[0][2] for r in recs]
+    first = [0] + [i for i in range(1, len(heads)) if heads[i] != heads[i - 1]] + [len(heads)]
+    merged = ctx.merge(res, first)
+    got = []
+    for k, (a, b, c) in enumerate(merged):
+        h = heads[first[k]]
+        h = h[:len(h) - 11] + " "
+        got += [h, a, h, b, h, c]
+    assert got == exp[:-1]
+
+
+def test_device_chain_poa_merge_tally_vs_oracle():
+    """elector_poa_run_device -> elector_merge_tally_device (everything resident on the device)
+    equals oracle POA -> oracle merge -> oracle tally on a config-1 slice with N windows"""
+    import torch
+    import elector_b200
+    import workloads
+    from elector_b200 import TALLY_FIELDS
+    from oracle import oracle, tally_oracle as to
+    wl = workloads.make_windows(2, 40)          # config 2: trimmed / split reads, `N` windows
+    n, n_reads = len(wl["ref_off"]) - 1, len(wl["read_first"]) - 1
+    dev = torch.device("cuda", 0)
+    with elector_b200.PoaContext(0) as c:
+        lib = c._lib
+        h = {k: np.ascontiguousarray(wl[k]) for k in ("ref", "ref_off", "cor", "cor_off", "unc", "unc_off", "read_first")}
+        d = {k: torch.from_numpy(h[k]).to(dev) for k in ("ref", "ref_off", "cor", "cor_off", "unc", "unc_off")}
+        bound = int(lib.elector_poa_rows_bound(n, h["ref_off"].ctypes.data, h["cor_off"].ctypes.data, h["unc_off"].ctypes.data))
+        d_rows = torch.empty(bound, dtype=torch.uint8, device=dev)
+        d_rowoff = torch.empty(n, dtype=torch.int64, device=dev)
+        d_stride = torch.empty(n, dtype=torch.int32, device=dev)
+        d_nring = torch.empty(n, dtype=torch.int32, device=dev)
+        d_used = torch.zeros(1, dtype=torch.int64, device=dev)
+        d_cnt = torch.zeros(n_reads * len(TALLY_FIELDS), dtype=torch.int64, device=dev)
+        c._check(lib.elector_poa_run_device(c._ctx, n, d["ref"].data_ptr(), d["ref_off"].data_ptr(), d["cor"].data_ptr(), d["cor_off"].data_ptr(),
+                                            d["unc"].data_ptr(), d["unc_off"].data_ptr(), h["ref_off"].ctypes.data, h["cor_off"].ctypes.data,
+                                            h["unc_off"].ctypes.data, d_rows.data_ptr(), bound, d_rowoff.data_ptr(), d_stride.data_ptr(),
+                                            d_nring.data_ptr(), None, None, None, d_used.data_ptr()))
+        c._check(lib.elector_merge_tally_device(c._ctx, n_reads, h["read_first"].ctypes.data, n, d_rows.data_ptr(), int(d_used.item()),
+                                                d_rowoff.data_ptr(), d_stride.data_ptr(), d_nring.data_ptr(), d_cnt.data_ptr()))
+        got = d_cnt.cpu().numpy().reshape(n_reads, -1)
+    o = oracle.batch(h["ref"], h["ref_off"], h["cor"], h["cor_off"], h["unc"], h["unc_off"], nthreads=os.cpu_count() or 1)
+    rf = h["read_first"]
+    for r in range(n_reads):
+        rows = [oracle.window_rows(o, w) for w in range(rf[r], rf[r + 1])]
+        R = "".join(x[0] for x in rows); C = "".join(x[1] for x in rows); U = "".join(x[2] for x in rows)
+        keep = [i for i, ch in enumerate(C) if ch != "n"]
+        R, C, U = ("".join(s[i] for i in keep) for s in (R, C, U))
+        exp = to.tally_read(R, C, U)
+        assert [int(v) for v in got[r]] == [exp[k] for k in TALLY_FIELDS], r
