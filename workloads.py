@@ -12,6 +12,7 @@ import os
 import shutil
 import subprocess
 import tempfile
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -30,10 +31,17 @@ CONFIG_NAMES = {
 CONFIG_READS = {1: 10000, 2: 100000, 3: 20000, 4: 1000000}
 
 
+_GEN_LOCK = threading.Lock()
+
+
 def ensure_gen():
+    """builds tools/gen_reads once (threads of make_windows call this concurrently)"""
     src = os.path.join(ROOT, "tools", "gen_reads.c")
-    if not os.path.exists(GEN) or os.path.getmtime(GEN) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-o", GEN, src, "-lm"])
+    with _GEN_LOCK:
+        if not os.path.exists(GEN) or os.path.getmtime(GEN) < os.path.getmtime(src):
+            tmp = "%s.tmp%d" % (GEN, os.getpid())
+            subprocess.check_call(["gcc", "-O2", "-o", tmp, src, "-lm"])
+            os.replace(tmp, GEN)
     return GEN
 
 
