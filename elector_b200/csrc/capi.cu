@@ -13,6 +13,7 @@
 #include "../../include/elector_poa.h"
 #include "host_io.hpp"
 #include "poa_kernel.cuh"
+#include "bin_kernel.cuh"
 #include "host_setup.hpp"
 #include "tally_kernel.cuh"
 #include "peak_kernel.cuh"
@@ -44,23 +45,21 @@ struct DevBuf {
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-struct SizeClass {
-  ClassLayout L;
-  bool large = false;
-  std::vector<int32_t> items;
-};
-
 }  // namespace
 
 struct elector_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
+  int resident_warps = 0;  // POA kernel CTAs (one warp each) resident per SM
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr;
+  cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
+  elector::BinTable *h_bintab = nullptr;  // pinned
   ScoreMatrix mat;
   ScoringSetup sc;
-  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl;
+  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   DevBuf d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
   std::string err;
@@ -86,141 +85,124 @@ struct elector_ctx {
 
 namespace {
 
-const int kSmallRowsMax = 256;  // shared-memory column tier handles max(lc,lu) <= this
-const size_t kCtrlWords = 16384;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..] class work counters
+const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..] segment work counters
+const int kSideStreams = 3;
 
-template <bool GC, bool GS>
-cudaError_t launch_class(elector_ctx *ctx, PoaArgs &a, int grid, size_t smem) {
-  auto k = poa_tpw_kernel<GC, GS>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<grid, 32, smem, ctx->stream>>>(a, ctx->d_tab.as<SymbolTables>());
+template <bool GS>
+cudaError_t launch_segment(cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
+  poa_tpw_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
   return cudaGetLastError();
 }
 
-template <bool GC, bool GS>
-int occupancy(size_t smem) {
-  auto k = poa_tpw_kernel<GC, GS>;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool GS>
+int resident_warps_per_sm() {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, poa_tpw_kernel<GS>, 32, 0);
   return nb;
 }
 
-// Core: all pointers are device pointers except the h_* offsets.
+// Core: all pointers are device pointers.  Launch structure of one call:
+//   main stream : bin_count -> bin_scan -> bin_scatter -> (table to host) -> the bulk segments
+//   side streams: the segments holding the largest windows (few items, long per-item time),
+//                 started first so that their tail overlaps the bulk
 int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
-               const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, const int64_t *h_roff,
-               const int64_t *h_coff, const int64_t *h_uoff, char *d_rows, int64_t rows_cap, int64_t *d_rowoff,
-               int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2, int64_t *d_cells,
+               const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, char *d_rows, int64_t rows_cap,
+               int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2, int64_t *d_cells,
                unsigned long long *d_cursor, int32_t *d_errflag) {
   ctx->last_ms = 0.f;
   ctx->last_launches = 0;
   if (n == 0) return ELECTOR_OK;
-  if (n > 0x7fffffff) return ctx->fail(ELECTOR_EINVAL, "too many windows in one call");
-  // ---- bin windows into size classes (rows bucket x reference-length bucket) ----
-  static const int ybuckets[] = {16, 24, 32, 40, 48, 56, 64, 80, 96, 128, 160, 192, 256};
-  const int NYB = sizeof(ybuckets) / sizeof(int);
-  std::vector<SizeClass> classes;
-  std::vector<int> class_of_key(64 * 64, -1);
-  std::vector<int32_t> cls(n);
-  for (int64_t w = 0; w < n; ++w) {
-    const int64_t lr = h_roff[w + 1] - h_roff[w], lc = h_coff[w + 1] - h_coff[w], lu = h_uoff[w + 1] - h_uoff[w];
-    if (lr <= 0 || lc <= 0 || lu <= 0)
-      return ctx->fail(ELECTOR_EINVAL, "window %lld has an empty sequence (undefined in the reference)", (long long)w);
-    if (lr > 60000 || lc > 60000 || lu > 60000)
-      return ctx->fail(ELECTOR_ETOOLARGE, "window %lld longer than 60000 letters", (long long)w);
-    const int ly = (int)std::max(lc, lu);
-    const bool large = ly > kSmallRowsMax || (lr + lc + lu) * (int64_t)std::max(1, ctx->sc.maxabs) > 30000;
-    int yb = 0;
-    if (large) { yb = NYB; int t = 512; while (t < ly) { t <<= 1; ++yb; } }
-    else while (ybuckets[yb] < ly) ++yb;
-    int xb = 0;
-    { int t = 64; while (t < lr) { t <<= 1; ++xb; } }
-    const int key = yb * 64 + xb;
-    int ci = class_of_key[key];
-    if (ci < 0) {
-      ci = (int)classes.size();
-      class_of_key[key] = ci;
-      classes.emplace_back();
-      classes.back().large = large;
-      classes.back().L.LR = classes.back().L.LC = classes.back().L.LU = 0;
-    }
-    ClassLayout &L = classes[ci].L;
-    L.LR = std::max<int>(L.LR, (int)lr); L.LC = std::max<int>(L.LC, (int)lc); L.LU = std::max<int>(L.LU, (int)lu);
-    cls[w] = ci;
-  }
-  // counting sort inside each class by total length, longest first
-  {
-    std::vector<std::vector<int32_t>> cnt(classes.size());
-    for (size_t c = 0; c < classes.size(); ++c) cnt[c].assign(classes[c].L.LR + classes[c].L.LC + classes[c].L.LU + 2, 0);
-    for (int64_t w = 0; w < n; ++w) {
-      const int t = (int)((h_roff[w + 1] - h_roff[w]) + (h_coff[w + 1] - h_coff[w]) + (h_uoff[w + 1] - h_uoff[w]));
-      ++cnt[cls[w]][t];
-    }
-    for (size_t c = 0; c < classes.size(); ++c) {
-      int32_t acc = 0;
-      for (size_t t = cnt[c].size(); t-- > 0;) { const int32_t k = cnt[c][t]; cnt[c][t] = acc; acc += k; }
-      classes[c].items.resize(acc);
-    }
-    for (int64_t w = 0; w < n; ++w) {
-      const int t = (int)((h_roff[w + 1] - h_roff[w]) + (h_coff[w + 1] - h_coff[w]) + (h_uoff[w + 1] - h_uoff[w]));
-      classes[cls[w]].items[cnt[cls[w]][t]++] = (int32_t)w;
-    }
-  }
-  // ---- device work lists + counters ----
+  if (n > 0x7fffffff - 64) return ctx->fail(ELECTOR_EINVAL, "too many windows in one call");
+  cudaStream_t st = ctx->stream;
   CU(ctx->d_items.reserve((size_t)n * sizeof(int32_t)));
-  if (classes.size() + 4 > kCtrlWords) return ctx->fail(ELECTOR_EINVAL, "too many size classes");
-  CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(int32_t) * (classes.size() + 4), ctx->stream));
+  CU(ctx->d_hist.reserve((size_t)kNumBins * sizeof(int32_t)));
+  CU(ctx->d_bintab.reserve(sizeof(BinTable)));
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(int32_t) * kCtrlWords, st));
+  CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)kNumBins * sizeof(int32_t), st));
   {
-    size_t pos = 0;
-    for (auto &c : classes) {
-      CU(cudaMemcpyAsync(ctx->d_items.as<int32_t>() + pos, c.items.data(), c.items.size() * sizeof(int32_t),
-                         cudaMemcpyHostToDevice, ctx->stream));
-      pos += c.items.size();
-    }
+    BinTable init;
+    memset(&init, 0, sizeof init);
+    init.err_window = 0x7fffffff;
+    memcpy(ctx->h_bintab, &init, sizeof init);
+    CU(cudaMemcpyAsync(ctx->d_bintab.p, ctx->h_bintab, sizeof(BinTable), cudaMemcpyHostToDevice, st));
   }
-  CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  size_t pos = 0;
-  for (size_t ci = 0; ci < classes.size(); ++ci) {
-    SizeClass &c = classes[ci];
-    make_layout(c.L, c.L.LR, c.L.LC, c.L.LU, c.large);
-    const size_t smem = (ctx->sc.generic_sub ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) +
-                        (c.large ? 0 : (size_t)2 * (c.L.LY + 1) * 32 * 4);
-    if (smem > ctx->smem_optin) return ctx->fail(ELECTOR_ECUDA, "class needs %zu B shared memory", smem);
-    int nb;
-    if (c.large) nb = ctx->sc.generic_sub ? occupancy<true, true>(smem) : occupancy<true, false>(smem);
-    else nb = ctx->sc.generic_sub ? occupancy<false, true>(smem) : occupancy<false, false>(smem);
-    if (nb < 1) return ctx->fail(ELECTOR_ECUDA, "kernel does not fit (smem %zu)", smem);
-    const int64_t groups = ((int64_t)c.items.size() + 31) / 32;
-    int grid = (int)std::min<int64_t>((int64_t)nb * ctx->sm_count, groups);
-    if (grid < 1) grid = 1;
-    // bound the scratch of big classes: fewer resident warps when windows are huge
-    const size_t per_warp = (size_t)c.L.total * 32 * 4;
-    const size_t budget = (size_t)8 << 30;
-    while (grid > 1 && per_warp * (size_t)grid > budget) grid = (grid + 1) / 2;
-    if (per_warp * (size_t)grid > ((size_t)48 << 30))
-      return ctx->fail(ELECTOR_ETOOLARGE, "window class %dx%dx%d needs %zu MiB scratch per warp", c.L.LR, c.L.LC, c.L.LU, per_warp >> 20);
-    CU(ctx->d_scratch.reserve(per_warp * (size_t)grid));
+  const int bgrid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+  bin_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_hist.as<int32_t>(), ctx->d_bintab.as<BinTable>());
+  bin_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_hist.as<int32_t>(), ctx->d_bintab.as<BinTable>());
+  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_hist.as<int32_t>(), ctx->d_items.as<int32_t>());
+  CU(cudaGetLastError());
+  ctx->last_launches += 3;
+  CU(cudaMemcpyAsync(ctx->h_bintab, ctx->d_bintab.p, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const BinTable &bt = *ctx->h_bintab;
+  if (bt.err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", bt.err_window);
+  if (bt.err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d longer than %d letters", bt.err_window, kMaxWindowLen);
+
+  // ---- plan the segment launches: grid and scratch ----
+  const int resident = std::max(1, ctx->resident_warps) * ctx->sm_count;
+  struct Plan { int seg, grid; size_t warp_words, scratch_off; };
+  std::vector<Plan> plan;
+  size_t scratch_words = 0;
+  const size_t budget_words = ((size_t)24 << 30) / 4;
+  for (int s = 0; s < kNumSegs; ++s) {
+    const SegInfo &si = bt.seg[s];
+    if (si.count <= 0) continue;
+    ClassLayout L;
+    make_layout(L, si.max_lr, si.max_lc, si.max_lu);
+    Plan p;
+    p.seg = s;
+    p.warp_words = L.total;
+    const int64_t groups = ((int64_t)si.count + 31) / 32;
+    p.grid = (int)std::min<int64_t>(resident, groups);
+    // bound the scratch of segments with huge windows: fewer resident warps
+    const size_t per_warp = (size_t)L.total * 32;
+    while (p.grid > 1 && per_warp * (size_t)p.grid > budget_words / 2) p.grid = (p.grid + 1) / 2;
+    if (per_warp * (size_t)p.grid > budget_words)
+      return ctx->fail(ELECTOR_ETOOLARGE, "windows of %d x %d x %d letters need %zu MiB scratch per warp", si.max_lr, si.max_lc, si.max_lu, (per_warp * 4) >> 20);
+    p.scratch_off = scratch_words;
+    scratch_words += per_warp * (size_t)p.grid;
+    plan.push_back(p);
+  }
+  if (scratch_words > 2 * budget_words) return ctx->fail(ELECTOR_ETOOLARGE, "call needs %zu MiB of scratch", (scratch_words * 4) >> 20);
+  CU(ctx->d_scratch.reserve(scratch_words * 4));
+
+  // ---- launch: big-window segments first, on side streams ----
+  CU(cudaEventRecord(ctx->ev_fork, st));
+  int side = 0, used_side = 0;
+  for (size_t k = 0; k < plan.size(); ++k) {
+    const Plan &p = plan[k];
+    const SegInfo &si = bt.seg[p.seg];
+    const bool bulk = k + 1 == plan.size() || (int64_t)si.count * 8 > n;  // the last (smallest windows) and any large share stay on the main stream
+    cudaStream_t ls = st;
+    if (!bulk) {
+      ls = ctx->side[side];
+      if (!(used_side & (1 << side))) { CU(cudaStreamWaitEvent(ls, ctx->ev_fork, 0)); used_side |= 1 << side; }
+      side = (side + 1) % kSideStreams;
+    }
     PoaArgs a;
     a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
     a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
-    a.items = ctx->d_items.as<int32_t>() + pos;
-    a.n_items = (int32_t)c.items.size();
+    a.items = ctx->d_items.as<int32_t>() + si.start;
+    a.n_items = si.count;
     a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
-    a.scratch = ctx->d_scratch.as<uint32_t>();
-    a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + ci;
+    a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
+    a.warp_words = (uint32_t)p.warp_words;
+    a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + p.seg;
     a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
     a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
     a.error_flag = d_errflag;
-    a.L = c.L;
-    cudaError_t e;
-    if (c.large) e = ctx->sc.generic_sub ? launch_class<true, true>(ctx, a, grid, smem) : launch_class<true, false>(ctx, a, grid, smem);
-    else e = ctx->sc.generic_sub ? launch_class<false, true>(ctx, a, grid, smem) : launch_class<false, false>(ctx, a, grid, smem);
+    const cudaError_t e = ctx->sc.generic_sub ? launch_segment<true>(ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
+                                              : launch_segment<false>(ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
-    pos += c.items.size();
   }
-  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  for (int k = 0; k < kSideStreams; ++k)
+    if (used_side & (1 << k)) {
+      CU(cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
+      CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
+    }
+  CU(cudaEventRecord(ctx->ev1, st));
   return ELECTOR_OK;
 }
 
@@ -260,12 +242,22 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->uev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->uev1)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->side[1], cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->side[2], cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_join[2], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaMallocHost((void **)&ctx->h_bintab, sizeof(BinTable))) != cudaSuccess ||
       (e = ctx->d_tab.reserve(sizeof(SymbolTables))) != cudaSuccess ||
       (e = ctx->d_ctrl.reserve(kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(ctx->d_tab.p, &ctx->sc.tab, sizeof(SymbolTables), cudaMemcpyHostToDevice)) != cudaSuccess) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
+  ctx->resident_warps = ctx->sc.generic_sub ? resident_warps_per_sm<true>() : resident_warps_per_sm<false>();
+  if (ctx->resident_warps < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;
 }
@@ -273,7 +265,7 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
 void elector_poa_free(elector_ctx *ctx) {
   if (!ctx) return;
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
-                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
+                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
                     &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_tally_scan, &ctx->d_tally_out,
                     &ctx->d_readfirst, &ctx->d_mtot, &ctx->d_moff, &ctx->d_mlen, &ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
   for (DevBuf *b : bufs) b->release();
@@ -281,6 +273,12 @@ void elector_poa_free(elector_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->uev0) cudaEventDestroy(ctx->uev0);
   if (ctx->uev1) cudaEventDestroy(ctx->uev1);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int k = 0; k < 3; ++k) {
+    if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+  }
+  if (ctx->h_bintab) cudaFreeHost(ctx->h_bintab);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -300,11 +298,11 @@ int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const
                            int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2,
                            int64_t *d_cells, int64_t *d_rows_used) {
   if (!ctx) return ELECTOR_EINVAL;
-  if (n < 0 || (n > 0 && (!d_ref || !d_cor || !d_unc || !d_roff || !d_coff || !d_uoff || !h_roff || !h_coff || !h_uoff ||
-                          !d_rows || !d_rowoff || !d_stride || !d_nring)))
+  if (n < 0 || (n > 0 && (!d_ref || !d_cor || !d_unc || !d_roff || !d_coff || !d_uoff || !d_rows || !d_rowoff || !d_stride || !d_nring)))
     return ctx->fail(ELECTOR_EINVAL, "null argument");
   CU(cudaSetDevice(ctx->device));
-  int rc = run_device(ctx, n, d_ref, d_roff, d_cor, d_coff, d_unc, d_uoff, h_roff, h_coff, h_uoff, d_rows, rows_cap,
+  (void)h_roff; (void)h_coff; (void)h_uoff;  // binning happens on the device
+  int rc = run_device(ctx, n, d_ref, d_roff, d_cor, d_coff, d_unc, d_uoff, d_rows, rows_cap,
                       d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells, ctx->d_ctrl.as<unsigned long long>(),
                       ctx->d_ctrl.as<int32_t>() + 2);
   if (rc != ELECTOR_OK) return rc;
@@ -341,7 +339,7 @@ int elector_poa_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t 
   CU(cudaMemcpyAsync(ctx->d_coff.p, co, (n + 1) * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_uoff.p, uo, (n + 1) * 8, cudaMemcpyHostToDevice, st));
   int rc = run_device(ctx, n, ctx->d_ref.as<char>(), ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>(),
-                      ctx->d_coff.as<int64_t>(), ctx->d_unc.as<char>(), ctx->d_uoff.as<int64_t>(), ro, co, uo,
+                      ctx->d_coff.as<int64_t>(), ctx->d_unc.as<char>(), ctx->d_uoff.as<int64_t>(),
                       ctx->d_rows.as<char>(), bound, ctx->d_rowoff.as<int64_t>(), ctx->d_stride.as<int32_t>(),
                       ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(), ctx->d_s2.as<int32_t>(),
                       ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2);

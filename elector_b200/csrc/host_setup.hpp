@@ -73,30 +73,4 @@ struct ScoringSetup {
   }
 };
 
-inline uint32_t cdiv_u(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
-
-// Per-thread scratch layout of a size class with caps (LR, LC, LU); `large` adds the two
-// global-memory column buffers of the large tier.
-inline void make_layout(ClassLayout &L, int LR, int LC, int LU, bool large) {
-  L.LR = LR; L.LC = LC; L.LU = LU;
-  L.LY = std::max(LC, LU);
-  const uint32_t N1 = (uint32_t)LR + LC;
-  uint32_t o = 0;
-  L.o_ref = o; o += cdiv_u(LR, 4);
-  L.o_cor = o; o += cdiv_u(LC, 4);
-  L.o_unc = o; o += cdiv_u(LU, 4);
-  L.o_nodeA = o; o += N1;
-  L.o_nodeB = o; o += 2 * N1;
-  L.o_moves = o; o += std::max((uint32_t)LR * cdiv_u(LC, 16), N1 * cdiv_u(LU, 16));
-  L.ord_wpn = cdiv_u(LU + 1, 8);
-  L.o_ord = o; o += ((uint32_t)std::min(LR, LC) + 2) * L.ord_wpn;
-  L.o_x2y = o; o += N1;
-  L.o_y2x = o; o += L.LY;
-  L.row_words = cdiv_u(LR + LC + LU, 4);
-  L.o_rows = o; o += 3 * L.row_words;
-  L.o_cols = o;
-  if (large) o += 2u * 2u * (L.LY + 1);
-  L.total = o;
-}
-
 }  // namespace elector

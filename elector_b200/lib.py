@@ -11,7 +11,8 @@ class LibraryNotBuilt(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libelector_poa.so")
+    # ELECTOR_POA_LIB selects another build of the same library (A/B runs of kernel variants)
+    return os.environ.get("ELECTOR_POA_LIB") or os.path.join(_HERE, "libelector_poa.so")
 
 
 def poa_binary_path():

@@ -1,10 +1,10 @@
 // TEST INFRASTRUCTURE ONLY -- runs the per-window device code (WindowCtx::run_window in
 // elector_b200/csrc/poa_kernel.cuh, compiled as host code) on the CPU, so that the
-// kernel's algorithmic restructuring (column-major sweep, two frontier buffers, 2-bit
+// kernel's algorithmic restructuring (8-row register bands, two frontier sets, 2-bit
 // moves, fused emit) can be checked against the oracle in the GPU-less container.
 // It is never linked into the product library; the product has no CPU path.
 //
-// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores] [large]
+// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores]
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -14,24 +14,21 @@
 
 using namespace elector;
 
-template <bool GC, bool GS>
+template <bool GS>
 static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores) {
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
     const int lr = R.rec[w].len, lc = C.rec[w].len, lu = U.rec[w].len;
     ClassLayout L;
     // caps deliberately larger than the window, as in a real size class
-    make_layout(L, lr + (int)(w % 3), lc + (int)(w % 5), lu + (int)(w % 2), GC);
+    make_layout(L, lr + (int)(w % 3), lc + (int)(w % 5), lu + (int)(w % 2));
     std::vector<uint32_t> scratch((size_t)L.total * 32, 0xdeadbeefu);
-    std::vector<uint32_t> cols((size_t)2 * (L.LY + 1) * 32, 0xdeadbeefu);
-    WindowCtx<GC, GS> c;
+    WindowCtx<GS> c;
     c.scr = scratch.data();
-    c.cols = cols.data();
     c.tab = &sc.tab;
-    c.L = &L;
+    c.Lp = &L;
     c.lane = (int)(w % 32);
     c.match = sc.match; c.mismatch = sc.mismatch; c.open = sc.open; c.ext = sc.ext;
-    c.colrows = GC ? std::max(lc, lu) + 1 : L.LY + 1;
     int s1, s2, n1;
     const int nring = c.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc,
                                    (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s1, s2, n1);
@@ -47,7 +44,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
 }
 
 int main(int argc, char **argv) {
-  if (argc < 6) { fprintf(stderr, "usage: %s MATRIX|- REF COR UNC OUT.pir [OUT.scores] [large]\n", argv[0]); return 2; }
+  if (argc < 6) { fprintf(stderr, "usage: %s MATRIX|- REF COR UNC OUT.pir [OUT.scores]\n", argv[0]); return 2; }
   ScoreMatrix m;
   if (std::string(argv[1]) == "-") m.set_default();
   else if (m.load(argv[1]) <= 0) { fprintf(stderr, "cannot read matrix\n"); return 1; }
@@ -57,10 +54,8 @@ int main(int argc, char **argv) {
   if (read_fasta_file(argv[3], C) < 0 || read_fasta_file(argv[4], U) < 0 || read_fasta_file(argv[2], R) < 0) return 1;
   FILE *pir = fopen(argv[5], "w");
   FILE *scores = argc > 6 && argv[6][0] != '-' ? fopen(argv[6], "w") : nullptr;
-  const bool large = argc > 7;
   if (!pir) return 1;
-  if (large) { if (sc.generic_sub) run<true, true>(sc, R, C, U, pir, scores); else run<true, false>(sc, R, C, U, pir, scores); }
-  else { if (sc.generic_sub) run<false, true>(sc, R, C, U, pir, scores); else run<false, false>(sc, R, C, U, pir, scores); }
+  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores); else run<false>(sc, R, C, U, pir, scores);
   fclose(pir);
   if (scores) fclose(scores);
   return 0;

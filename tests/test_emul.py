@@ -1,6 +1,6 @@
 """CPU: the per-window DEVICE code (elector_b200/csrc/poa_kernel.cuh) compiled as host code
 and run by tests/emul/poa_emul.cu, against the reference goldens.  This checks the kernel's
-restructuring (column-major sweep, two frontier buffers, 2-bit moves + ordinals, fused
+restructuring (8-row register bands, two frontier sets, 2-bit moves + ordinals, fused
 emit) without a GPU; the GPU tests then check the real launch path."""
 import subprocess
 
@@ -9,15 +9,12 @@ import pytest
 from conftest import GOLDEN_SETS, parse_dump
 
 
-@pytest.mark.parametrize("tier", ["smem", "large"])
 @pytest.mark.parametrize("name", GOLDEN_SETS)
-def test_emulated_kernel_equals_reference(golden_dir, emul_bin, name, tier, tmp_path):
+def test_emulated_kernel_equals_reference(golden_dir, emul_bin, name, tmp_path):
     d = golden_dir
     pir, sc = str(tmp_path / "e.pir"), str(tmp_path / "e.scores")
     cmd = [emul_bin, d + "/blosum80.mat", "%s/%s.ref.fa" % (d, name), "%s/%s.cor.fa" % (d, name),
            "%s/%s.unc.fa" % (d, name), pir, sc]
-    if tier == "large":
-        cmd.append("large")
     assert subprocess.call(cmd) == 0
     assert open(pir, "rb").read() == open("%s/%s.pir" % (d, name), "rb").read()
     gold = parse_dump("%s/%s.dump" % (d, name))
