@@ -11,22 +11,23 @@
 // DP; the bound is the integer issue rate.
 //
 // DP data placement (the part that decides the speed)
-//   * The DP matrix is swept in BANDS of kBand = 8 rows (y = rows, always a linear sequence
-//     here; x = columns, the nodes of the growing partial order).  Inside a band a thread
-//     keeps the 8 (S, G) cells of the previous column in REGISTERS and updates them in
-//     place, fully unrolled: no shared or global memory access per cell.
-//   * A node of the 2-sequence PO P1 can only have as predecessors the latest ref-carrying
-//     node and the latest cor-carrying node, so at most two "frontier" columns are alive:
-//     two register sets A and B (plus which frontier each holds) replace the reference's
-//     (len_y+1) x (len_x+1) matrix.  The hot in-place update always runs on set A; the rare
-//     nodes that need the other frontier swap / copy / merge the sets first.
-//   * Between bands only the band's bottom row travels: one (S, G) pair per node in a
-//     per-thread boundary array (global scratch, read once and overwritten once per band).
-//   * Moves: 2 bits per cell, 16 bits per (band, node), for the traceback.
-//   * Everything per window that is not in registers (codes, node records, moves, boundary
-//     row, alignment maps, MSA rows) lives in a per-warp scratch area of global memory,
-//     interleaved by lane at 4-byte granularity so that lock-step lanes produce fully
-//     coalesced 128-byte transactions; it is L1/L2 resident and recycled by the persistent warp.
+//   * The DP matrix is swept in BANDS of 16 rows (a last band of 8 when at most 8 rows are
+//     left); y = rows, always a linear sequence here; x = columns, the nodes of the growing
+//     partial order.  Inside a band a thread keeps the (S, G) cells of the previous column
+//     in REGISTERS and updates them in place, fully unrolled: no memory access per cell.
+//   * DP1 is linear x linear: one register column, predecessor j-1, nothing else.
+//   * DP2 runs over P1.  A node of the 2-sequence PO P1 can only have as predecessors the
+//     latest ref-carrying node and the latest cor-carrying node, so at most two "frontier"
+//     columns are alive: the register set A plus a spare set B in shared memory replace the
+//     reference's (len_y+1) x (len_x+1) matrix.  The hot in-place update always runs on A;
+//     the few nodes that need the other frontier swap / copy / merge the sets first.
+//   * Between bands only the band's bottom row travels: one (S, G) pair per node (global
+//     scratch, read once and overwritten once per band).
+//   * Moves: 2 bits per cell, one 32-bit word per (band, node), for the traceback.
+//   * Everything per window that is not in registers lives in a per-warp scratch area of
+//     global memory, interleaved by lane at 4-byte granularity so that lock-step lanes
+//     produce fully coalesced 128-byte transactions; per-node data is one record
+//     (array of structures) walked with a single running pointer.
 //
 // Scoring (align_lpo_po2.c:224-249,384-407 with DOUBLE_GAP_SCORING 0): a cell keeps the
 // winning move's score S and gap length g; with a gap table that is flat after the opening
@@ -39,16 +40,16 @@
 
 namespace elector {
 
-constexpr int kBand = 8;  // rows per register band
+constexpr int kBand = 16;     // rows per register band (the last band may have 8)
+constexpr int kRecWords = 5;  // fixed words of a node record, followed by one moves word per band
 
-struct ClassLayout {  // per-thread scratch layout (32-bit words), computed on the host per size class
-  int32_t LR, LC, LU;  // caps of the class: max ref / cor / unc length
+struct ClassLayout {  // per-thread scratch layout (32-bit words) of a group of windows
+  int32_t LR, LC, LU;  // caps: max ref / cor / unc length of the group
   uint32_t o_ref, o_cor, o_unc;  // packed symbol codes, 4 per word
-  uint32_t o_nodeA, o_nodeB;     // node records of the current PO (P0 = lin(ref), then P1)
-  uint32_t o_bnd;                // boundary row between bands: (S, G) per node, 2 words
-  uint32_t o_moves;              // 16 bits per (band, node): 2 bits per DP cell
-  uint32_t o_ord;                // one word per (combined node, band): winning predecessor ordinals
-  uint32_t o_x2y, o_y2x;         // alignment maps, one word per entry
+  uint32_t o_nodes;              // node records: LR+LC records of rec_words words
+  uint32_t rec_words;            //   +0 node flags|letter  +1 boundary S  +2 boundary G  +3 preds  +4 x2y  +5+b moves of band b
+  uint32_t o_ord;                // two words per (combined node, band): winning predecessor ordinals
+  uint32_t ord_bands;            // bands per ordinal slot
   uint32_t o_rows;               // 3 MSA rows, bytes packed 4 per word
   uint32_t row_words;            // words per row in o_rows
   uint32_t total;                // words per thread
@@ -67,18 +68,15 @@ EL_HD uint32_t max_u(uint32_t a, uint32_t b) { return a > b ? a : b; }
 EL_HD void make_layout(ClassLayout &L, int LR, int LC, int LU) {
   L.LR = LR; L.LC = LC; L.LU = LU;
   const uint32_t N1 = (uint32_t)LR + (uint32_t)LC;             // cap of len(P1)
-  const uint32_t nb1 = cdiv_u(LC, kBand), nb2 = cdiv_u(LU, kBand);
+  const uint32_t nb = max_u(cdiv_u(LC, kBand), cdiv_u(LU, kBand));
   uint32_t o = 0;
-  L.o_ref = o; o += cdiv_u(LR, 4) + 1;                         // +1: a band reads two code words at once
-  L.o_cor = o; o += cdiv_u(LC, 4) + 1;
-  L.o_unc = o; o += cdiv_u(LU, 4) + 1;
-  L.o_nodeA = o; o += N1;
-  L.o_nodeB = o; o += 2 * N1;
-  L.o_bnd = o; o += 2 * N1;
-  L.o_moves = o; o += cdiv_u(max_u(nb1 * (uint32_t)LR, nb2 * N1), 2);
-  L.o_ord = o; o += ((uint32_t)(LR < LC ? LR : LC) + 2) * max_u(nb1, nb2);
-  L.o_x2y = o; o += N1;
-  L.o_y2x = o; o += max_u(LC, LU);
+  L.o_ref = o; o += cdiv_u(LR, 4) + 4;                         // +4: a band reads four code words at once
+  L.o_cor = o; o += cdiv_u(LC, 4) + 4;
+  L.o_unc = o; o += cdiv_u(LU, 4) + 4;
+  L.rec_words = kRecWords + nb;
+  L.o_nodes = o; o += N1 * L.rec_words;
+  L.ord_bands = nb;
+  L.o_ord = o; o += ((uint32_t)(LR < LC ? LR : LC) + 2) * nb * 2;
   L.row_words = cdiv_u(LR + LC + LU, 4);
   L.o_rows = o; o += 3 * L.row_words;
   L.total = o;
@@ -123,31 +121,96 @@ enum : uint32_t {
   NF_PREDC = 1u << 16,   // the single real predecessor is the latest cor-carrying node
   NF_SLOT_SHIFT = 17     // combined nodes (VIRT or TWO): index of their ordinal slot
 };
+enum : uint32_t { REC_NODE = 0, REC_BS = 1, REC_BG = 2, REC_PRED = 3, REC_X2Y = 4, REC_MOVES = 5 };
 
-struct ColSet {  // one frontier column inside the current band
-  int S[kBand], G[kBand];
-  int h;         // S of the row just above the band (row -1 in band 0)
-};
+// shifts the sign bit of t into the move word (a negative difference = the move was taken)
+EL_HD uint32_t shift_in_sign(uint32_t mv, int t) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l((uint32_t)t, mv, 1);
+#else
+  return (mv << 1) | ((uint32_t)t >> 31);
+#endif
+}
+
+constexpr int kSlotWords = (2 * kBand + 1) * 32;  // one frontier set of a warp in shared memory: S[R], G[R], h, lane-interleaved
+
+// Uncommon nodes of DP2 (first nodes, nodes around a ref/cor difference): the left list is
+// not "the column held in set A".  Works on shared-memory copies of both sets, [k*32] per
+// lane: sa = set A (holds frontier(s) kindA), sb = set B (kindB); 1 = ref frontier, 2 = cor
+// frontier, 3 = both.  On return the node's SOURCE column (first strict maximum over its
+// left list, align_lpo_po2.c:334-371, with the winning ordinals in po[0] (match) / po[32]
+// (X-gap)) is in A and the frontier the node does not replace is in B.
+// Returns kindA | kindB << 2 | 16 if the sets traded places (A is now in sb).
+__host__ __device__ __noinline__ inline uint32_t arrange_sets(uint32_t *sa, uint32_t *sb, int R, int r0, uint32_t ra, int kindA,
+                                                        int kindB, int open, int ext, uint32_t *po) {
+  const int m = (ra >> 8) & 3;
+  uint32_t flipped = 0;
+  auto swap_sets = [&]() {
+    uint32_t *t = sa; sa = sb; sb = t;
+    const int k = kindA; kindA = kindB; kindB = k;
+    flipped ^= 16u;
+  };
+  auto vS = [&](int row) { return row < 0 ? 0 : -(open + ext * row); };          // virtual column -1
+  auto vG = [&](int row) { return row < 0 ? -open : -(open + ext * row) - ext; };
+  if (ra & NF_TWO) {
+    if (kindA == 2) swap_sets();   // list order: ref predecessor, then cor
+  } else if (!(ra & NF_NOPRED)) {
+    const int pk = (ra & NF_PREDC) ? 2 : 1;
+    if (!(kindA & pk)) swap_sets();
+    if (kindA & ~m) {              // the node leaves one of A's frontiers behind: B := A
+      for (int k = 0; k <= 2 * R; ++k) sb[k * 32] = sa[k * 32];
+      kindB = kindA & ~m;
+    }
+  } else if (kindA & ~m) swap_sets();
+  if (ra & NF_NOPRED) {
+    sa[2 * R * 32] = (uint32_t)vS(r0 - 1);
+    for (int r = 0; r < R; ++r) { sa[r * 32] = (uint32_t)vS(r0 + r); sa[(R + r) * 32] = (uint32_t)vG(r0 + r); }
+  } else if (ra & (NF_VIRT | NF_TWO)) {
+    const bool virt = ra & NF_VIRT, two = ra & NF_TWO;
+    const uint32_t oA = virt ? 1u : 0u, oB = oA + 1u;
+    uint32_t owM = 0, owX = 0;
+    {
+      int bS = (int)sa[2 * R * 32]; uint32_t o = oA;
+      if (virt) { const int a = bS; bS = vS(r0 - 1); o = 0; if (a > bS) { bS = a; o = oA; } }
+      if (two) { const int hb = (int)sb[2 * R * 32]; if (hb > bS) { bS = hb; o = oB; } }
+      sa[2 * R * 32] = (uint32_t)bS; owM |= o;
+    }
+    for (int r = 0; r < R; ++r) {
+      const int aS = (int)sa[r * 32], aG = (int)sa[(R + r) * 32];
+      int bS = aS, bG = aG; uint32_t oM = oA, oX = oA;
+      if (virt) {
+        bS = vS(r0 + r); bG = vG(r0 + r); oM = oX = 0;
+        if (aS > bS) { bS = aS; oM = oA; }
+        if (aG > bG) { bG = aG; oX = oA; }
+      }
+      if (two) {
+        const int sS = (int)sb[r * 32], sG = (int)sb[(R + r) * 32];
+        if (sS > bS) { bS = sS; oM = oB; }
+        if (sG > bG) { bG = sG; oX = oB; }
+      }
+      sa[r * 32] = (uint32_t)bS; sa[(R + r) * 32] = (uint32_t)bG;
+      if (r < kBand - 1) owM |= oM << (2 * (r + 1));   // row r0+15's ordinal is the next band's halo
+      owX |= oX << (2 * r);
+    }
+    po[0] = owM; po[32] = owX;
+  }
+  kindA = m;
+  kindB &= ~m;
+  return (uint32_t)kindA | ((uint32_t)kindB << 2) | flipped;
+}
 
 template <bool GENERIC_SUB>
 struct WindowCtx {
-  uint32_t *scr;   // this warp's scratch, indexed [word*32 + lane]
+  uint32_t *scr;          // this warp's scratch, indexed [word*32 + lane]
+  uint32_t *bset;         // two frontier-set slots of kSlotWords words, + lane (shared memory on the device)
   const SymbolTables *tab;
   const ClassLayout *Lp;  // scratch layout of the current 32-window group (shared memory on the device)
   int lane;
   int match, mismatch, open, ext;
 
   EL_HD uint32_t &sw(uint32_t w) const { return scr[(size_t)w * 32 + lane]; }
-
-  EL_HD int code_at(uint32_t off, int i) const {
-    return (sw(off + (i >> 2)) >> ((i & 3) * 8)) & 0xff;
-  }
-  EL_HD void st_mv(uint32_t e, uint32_t v) const {
-    reinterpret_cast<uint16_t *>(&sw(Lp->o_moves + (e >> 1)))[e & 1] = (uint16_t)v;
-  }
-  EL_HD uint32_t ld_mv(uint32_t e) const {
-    return reinterpret_cast<const uint16_t *>(&sw(Lp->o_moves + (e >> 1)))[e & 1];
-  }
+  EL_HD uint32_t *rec(uint32_t j) const { return scr + ((size_t)(Lp->o_nodes + j * Lp->rec_words) * 32 + lane); }  // field f at [f*32]
+  EL_HD int code_at(uint32_t off, int i) const { return (sw(off + (i >> 2)) >> ((i & 3) * 8)) & 0xff; }
 
   // K1: raw letters -> symbol indices, 4 per scratch word
   EL_HDN void pack_codes(const uint8_t *src, int len, uint32_t off) const {
@@ -163,14 +226,89 @@ struct WindowCtx {
   EL_HD int virt_S(int row) const { return row < 0 ? 0 : -(open + ext * row); }
   EL_HD int virt_G(int row) const { return row < 0 ? -open : -(open + ext * row) - ext; }
 
-  // ---- node preparation (align_lpo_po2.c:46-79 + row -1, :272-286) ----
+  // The in-place update of one register column by one node (align_lpo_po2.c:322-407) for R rows:
+  // S/G hold the predecessor column on entry and the node's column on exit; returns the move bits.
+  template <int R>
+  EL_HD uint32_t update_column(int (&S)[R], int (&G)[R], const uint32_t (&yw)[R / 4], int xl, int diag, int up) const {
+    uint32_t mv = 0;
+    const uint32_t x4 = (uint32_t)xl * 0x01010101u;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pS = S[r], pG = G[r];
+      int sub;
+      if (GENERIC_SUB) sub = (int)tab->sub[xl * 32 + ((yw[r >> 2] >> ((r & 3) * 8)) & 31)];
+      else sub = ((x4 ^ yw[r >> 2]) & (0xffu << ((r & 3) * 8))) ? mismatch : match;
+      const int M = diag + sub;
+      const int gap = pG > up ? pG : up;     // ties: Y-gap beats X-gap (:392)
+      const bool isM = M > gap;              // match must beat both (:384)
+      const int s = isM ? M : gap;
+      const int g = s - (isM ? open : ext);
+      mv = shift_in_sign(mv, gap - M);       // bit 1 of the cell: match
+      mv = shift_in_sign(mv, up - pG);       // bit 0 of the cell: X-gap (when not a match)
+      S[r] = s; G[r] = g;
+      diag = pS; up = g;
+    }
+    if (R < kBand) mv <<= 2 * (kBand - R);   // align an 8-row band like the first half of a 16-row one
+    return mv;
+  }
+
+  template <int R>
+  EL_HD void load_y(uint32_t (&yw)[R / 4], uint32_t o_y, int r0) const {
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) yw[k] = sw(o_y + (r0 >> 2) + k);
+  }
+
+  template <int R>
+  static EL_HD int pick_row(const int (&S)[R], int k) {
+    int s = S[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) if (k == r) s = S[r];
+    return s;
+  }
+
+  // ---- DP1: linear x linear (lin(ref) columns, lin(cor) rows), one band ----
+  template <int R>
+  EL_HDN int band_linear(int lr, uint32_t o_y, int ly, int b, bool last) const {
+    const int r0 = b * kBand;
+    uint32_t yw[R / 4];
+    load_y<R>(yw, o_y, r0);
+    int S[R], G[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { S[r] = virt_S(r0 + r); G[r] = virt_G(r0 + r); }
+    int h = virt_S(r0 - 1);
+    uint32_t *p = rec(0);
+    const uint32_t step = Lp->rec_words * 32;
+    uint32_t xw = 0;
+    int upS_n = 0, upG_n = 0;
+    if (b > 0) { upS_n = (int)p[REC_BS * 32]; upG_n = (int)p[REC_BG * 32]; }
+    for (int j = 0; j < lr; ++j, p += step) {
+      if ((j & 3) == 0) xw = sw(Lp->o_ref + (j >> 2));
+      const int xl = xw & 0xff; xw >>= 8;
+      int upS, upG;
+      if (b == 0) { upS = -(open + ext * j); upG = upS - ext; }   // row -1 (:275-286)
+      else {
+        upS = upS_n; upG = upG_n;
+        const uint32_t *pn = j + 1 < lr ? p + step : p;
+        upS_n = (int)pn[REC_BS * 32]; upG_n = (int)pn[REC_BG * 32];
+      }
+      const uint32_t mv = update_column<R>(S, G, yw, xl, h, upG);
+      h = upS;
+      if (!last) { p[REC_BS * 32] = (uint32_t)S[R - 1]; p[REC_BG * 32] = (uint32_t)G[R - 1]; }
+      p[(REC_MOVES + b) * 32] = mv;
+    }
+    return last ? pick_row<R>(S, ly - 1 - r0) : 0;
+  }
+
+  // ---- node preparation for DP2 (align_lpo_po2.c:46-79 + row -1, :272-286) ----
   // Derives every node's left list from the two frontiers, stores its shape in the node
-  // record (NF_VIRT / NF_TWO / NF_NOPRED / NF_PREDC / slot), its real predecessors in
-  // o_nodeB (for the traceback) and row -1 of the DP in the boundary array.
+  // record (NF_VIRT / NF_TWO / NF_NOPRED / NF_PREDC / slot), its real predecessors (for the
+  // traceback) and row -1 of the DP as the first boundary row.
   EL_HDN void prepare(int nx) const {
     int lastR = -1, lastC = -1, gR = 0, gC = 0, nslot = 0;
-    for (int j = 0; j < nx; ++j) {
-      uint32_t ra = sw(Lp->o_nodeA + j) & NF_KEEP;
+    uint32_t *p = rec(0);
+    const uint32_t step = Lp->rec_words * 32;
+    for (int j = 0; j < nx; ++j, p += step) {
+      uint32_t ra = p[REC_NODE * 32] & NF_KEEP;
       const bool hasR = ra & NF_REF, hasC = ra & NF_COR;
       int pA = -1, pB = -1, gA = 0, gB = 0;
       if (hasR && lastR >= 0) { pA = lastR; gA = gR; }
@@ -188,173 +326,130 @@ struct WindowCtx {
         if (virt || pB >= 0) ra |= (uint32_t)(nslot++) << NF_SLOT_SHIFT;
       }
       const int bG = bS - ext;
-      sw(Lp->o_nodeA + j) = ra;
-      sw(Lp->o_nodeB + 2 * j) = (uint32_t)pA;
-      sw(Lp->o_nodeB + 2 * j + 1) = (uint32_t)pB;
-      sw(Lp->o_bnd + 2 * j) = (uint32_t)bS;
-      sw(Lp->o_bnd + 2 * j + 1) = (uint32_t)bG;
+      p[REC_NODE * 32] = ra;
+      p[REC_PRED * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
+      p[REC_BS * 32] = (uint32_t)bS;
+      p[REC_BG * 32] = (uint32_t)bG;
       if (hasR) { lastR = j; gR = bG; }
       if (hasC) { lastC = j; gC = bG; }
     }
   }
 
-  static EL_HD void swap_sets(ColSet &a, ColSet &b, int &ka, int &kb) {
+  // ---- DP2: P1 columns x lin(unc) rows, one band (align_lpo_po2.c:269-433) ----
+  template <int R>
+  EL_HDN void band_po(int nx, uint32_t o_y, int ly, int b, bool last, int &best, int &best_j) const {
+    const int r0 = b * kBand;
+    uint32_t yw[R / 4];
+    load_y<R>(yw, o_y, r0);
+    int S[R], G[R], h = 0;   // set A
 #pragma unroll
-    for (int r = 0; r < kBand; ++r) {
-      int t = a.S[r]; a.S[r] = b.S[r]; b.S[r] = t;
-      t = a.G[r]; a.G[r] = b.G[r]; b.G[r] = t;
+    for (int r = 0; r < R; ++r) S[r] = G[r] = 0;
+    int kindA = 0, kindB = 0;  // which frontiers the sets hold: 1 = ref, 2 = cor, 3 = both
+    int bsel = 0;              // which shared-memory slot holds set B
+    uint32_t *p = rec(0);
+    const uint32_t step = Lp->rec_words * 32;
+    uint32_t ra = p[REC_NODE * 32];
+    int upS = (int)p[REC_BS * 32], upG = (int)p[REC_BG * 32];
+    for (int j = 0; j < nx; ++j, p += step) {
+      // prefetch the next node while this one is computed
+      const uint32_t *pn = j + 1 < nx ? p + step : p;
+      const uint32_t ra_n = pn[REC_NODE * 32];
+      const int upS_n = (int)pn[REC_BS * 32], upG_n = (int)pn[REC_BG * 32];
+
+      const int m = (ra >> 8) & 3;
+      // -- uncommon: bring the source column into set A, keep the frontier this node leaves behind in B.
+      // Done out of line on shared-memory copies of both sets, so that the hot loop stays small.
+      if ((ra & (NF_TWO | NF_NOPRED | NF_VIRT | NF_PREDC)) || kindA != m) {
+        uint32_t *sa = bset + (1 - bsel) * kSlotWords, *sb = bset + bsel * kSlotWords;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { sa[r * 32] = (uint32_t)S[r]; sa[(R + r) * 32] = (uint32_t)G[r]; }
+        sa[2 * R * 32] = (uint32_t)h;
+        uint32_t *po = nullptr;
+        if (ra & (NF_VIRT | NF_TWO)) po = &sw(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
+        const uint32_t st = arrange_sets(sa, sb, R, r0, ra, kindA, kindB, open, ext, po);
+        kindA = st & 3; kindB = (st >> 2) & 3;
+        if (st & 16u) { bsel = 1 - bsel; sa = sb; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) { S[r] = (int)sa[r * 32]; G[r] = (int)sa[(R + r) * 32]; }
+        h = (int)sa[2 * R * 32];
+      }
+      // -- hot: in-place update of set A with node j
+      const uint32_t mv = update_column<R>(S, G, yw, ra & 0xff, h, upG);
+      h = upS;
+      if (!last) { p[REC_BS * 32] = (uint32_t)S[R - 1]; p[REC_BG * 32] = (uint32_t)G[R - 1]; }
+      p[(REC_MOVES + b) * 32] = mv;
+      if (last && (ra & NF_FINAL)) {
+        const int s = pick_row<R>(S, ly - 1 - r0);
+        if (s > best) { best = s; best_j = j; }  // ties keep the smaller j (:410-417)
+      }
+      ra = ra_n; upS = upS_n; upG = upG_n;
     }
-    int t = a.h; a.h = b.h; b.h = t;
-    t = ka; ka = kb; kb = t;
   }
 
-  // ---- DP over the nodes of the current PO (align_lpo_po2.c:269-433), band by band ----
-  EL_HDN int dp_sweep(int nx, uint32_t o_y, int ly, int &best_j) const {
+  // bands of 16 rows; the last one has 8 when at most 8 rows remain
+  EL_HDN int dp_linear(int lr, uint32_t o_y, int ly) const {
+    const int nb = (ly + kBand - 1) / kBand;
+    for (int b = 0; b < nb - 1; ++b) band_linear<kBand>(lr, o_y, ly, b, false);
+    return (ly - (nb - 1) * kBand <= 8) ? band_linear<8>(lr, o_y, ly, nb - 1, true) : band_linear<kBand>(lr, o_y, ly, nb - 1, true);
+  }
+  EL_HDN int dp_po(int nx, uint32_t o_y, int ly, int &best_j) const {
     prepare(nx);
     const int nb = (ly + kBand - 1) / kBand;
     int best = -999999;
     best_j = -1;
-    for (int b = 0; b < nb; ++b) {
-      const int r0 = b * kBand;
-      int yc[kBand];
-      {
-        const uint32_t w0 = sw(o_y + (r0 >> 2)), w1 = sw(o_y + (r0 >> 2) + 1);
-#pragma unroll
-        for (int r = 0; r < kBand; ++r) yc[r] = ((r < 4 ? w0 : w1) >> ((r & 3) * 8)) & 0xff;
-      }
-      const bool last_band = b == nb - 1;
-      ColSet A, B;
-#pragma unroll
-      for (int r = 0; r < kBand; ++r) A.S[r] = A.G[r] = B.S[r] = B.G[r] = 0;
-      A.h = B.h = 0;
-      int kindA = 0, kindB = 0;  // which frontiers the sets hold: 1 = ref, 2 = cor, 3 = both
-      uint32_t ra = sw(Lp->o_nodeA);
-      int upS = (int)sw(Lp->o_bnd), upG = (int)sw(Lp->o_bnd + 1);
-      const uint32_t mv_base = (uint32_t)b * (uint32_t)nx;
-      for (int j = 0; j < nx; ++j) {
-        // prefetch the next node while this one is computed
-        const int jn = j + 1 < nx ? j + 1 : j;
-        const uint32_t ra_n = sw(Lp->o_nodeA + jn);
-        const int upS_n = (int)sw(Lp->o_bnd + 2 * jn), upG_n = (int)sw(Lp->o_bnd + 2 * jn + 1);
-
-        const int m = (ra >> 8) & 3;
-        const int xl = ra & 0xff;
-        // -- rare: bring the source column into set A, keep the frontier this node leaves behind in B
-        if ((ra & (NF_TWO | NF_NOPRED | NF_VIRT | NF_PREDC)) || kindA != m) {
-          if (ra & NF_TWO) {
-            if (kindA == 2) swap_sets(A, B, kindA, kindB);   // list order: ref predecessor, then cor
-          } else if (!(ra & NF_NOPRED)) {
-            const int pk = (ra & NF_PREDC) ? 2 : 1;
-            if (!(kindA & pk)) swap_sets(A, B, kindA, kindB);
-            if (kindA & ~m) { B = A; kindB = kindA & ~m; }
-          } else if (kindA & ~m) swap_sets(A, B, kindA, kindB);
-          if (ra & NF_NOPRED) {
-            A.h = virt_S(r0 - 1);
-#pragma unroll
-            for (int r = 0; r < kBand; ++r) { A.S[r] = virt_S(r0 + r); A.G[r] = virt_G(r0 + r); }
-          } else if (ra & (NF_VIRT | NF_TWO)) {
-            // first strict maximum over the left list, per row, S and G separately, with ordinals
-            const bool virt = ra & NF_VIRT, two = ra & NF_TWO;
-            const uint32_t oA = virt ? 1u : 0u, oB = oA + 1u;
-            uint32_t ow = 0;
-            {
-              int bS = A.h; uint32_t o = oA;
-              if (virt) { bS = virt_S(r0 - 1); o = 0; if (A.h > bS) { bS = A.h; o = oA; } }
-              if (two && B.h > bS) { bS = B.h; o = oB; }
-              A.h = bS; ow |= o;
-            }
-#pragma unroll
-            for (int r = 0; r < kBand; ++r) {
-              int bS = A.S[r], bG = A.G[r]; uint32_t oM = oA, oX = oA;
-              if (virt) {
-                bS = virt_S(r0 + r); bG = virt_G(r0 + r); oM = oX = 0;
-                if (A.S[r] > bS) { bS = A.S[r]; oM = oA; }
-                if (A.G[r] > bG) { bG = A.G[r]; oX = oA; }
-              }
-              if (two) {
-                if (B.S[r] > bS) { bS = B.S[r]; oM = oB; }
-                if (B.G[r] > bG) { bG = B.G[r]; oX = oB; }
-              }
-              A.S[r] = bS; A.G[r] = bG;
-              if (r < kBand - 1) ow |= oM << (2 * (r + 1));
-              ow |= oX << (16 + 2 * r);
-            }
-            sw(Lp->o_ord + (ra >> NF_SLOT_SHIFT) * (uint32_t)nb + b) = ow;
-          }
-          kindA = m;
-          kindB &= ~m;
-        }
-        // -- hot: in-place update of set A with node j (align_lpo_po2.c:322-407)
-        int diag = A.h, up = upG;
-        uint32_t mv = 0;
-#pragma unroll
-        for (int r = 0; r < kBand; ++r) {
-          const int pS = A.S[r], pG = A.G[r];
-          const int sub = GENERIC_SUB ? (int)tab->sub[xl * 32 + (yc[r] & 31)] : (yc[r] == xl ? match : mismatch);
-          const int M = diag + sub;
-          const bool xg = pG > up;               // ties: Y-gap beats X-gap (:392)
-          const int gap = xg ? pG : up;
-          const bool isM = M > gap;              // match must beat both (:384)
-          const int s = isM ? M : gap;
-          const int g = s - (isM ? open : ext);
-          if (isM) mv |= 1u << (2 * r);
-          if (xg) mv |= 2u << (2 * r);
-          A.S[r] = s; A.G[r] = g;
-          diag = pS; up = g;
-        }
-        A.h = upS;
-        sw(Lp->o_bnd + 2 * j) = (uint32_t)A.S[kBand - 1];
-        sw(Lp->o_bnd + 2 * j + 1) = (uint32_t)A.G[kBand - 1];
-        st_mv(mv_base + j, mv);
-        if (last_band && (ra & NF_FINAL)) {
-          const int k = (ly - 1) & (kBand - 1);
-          int s = A.S[0];
-#pragma unroll
-          for (int r = 1; r < kBand; ++r) if (k == r) s = A.S[r];
-          if (s > best) { best = s; best_j = j; }  // ties keep the smaller j (:410-417)
-        }
-        ra = ra_n; upS = upS_n; upG = upG_n;
-      }
-    }
+    for (int b = 0; b < nb - 1; ++b) band_po<kBand>(nx, o_y, ly, b, false, best, best_j);
+    if (ly - (nb - 1) * kBand <= 8) band_po<8>(nx, o_y, ly, nb - 1, true, best, best_j);
+    else band_po<kBand>(nx, o_y, ly, nb - 1, true, best, best_j);
     return best;
   }
 
-  // ---- traceback (align_lpo_po2.c:108-168) ----
+  // ---- traceback (align_lpo_po2.c:108-168): fills the x2y field of every node record ----
+  template <bool LINEAR>
   EL_HDN void traceback(int nx, int ly, int best_j) const {
-    const int nb = (ly + kBand - 1) / kBand;
-    for (int j = 0; j < nx; ++j) sw(Lp->o_x2y + j) = 0xffffffffu;
-    for (int r = 0; r < ly; ++r) sw(Lp->o_y2x + r) = 0xffffffffu;
+    {
+      uint32_t *p = rec(0) + REC_X2Y * 32;
+      const uint32_t step = Lp->rec_words * 32;
+      for (int j = 0; j < nx; ++j, p += step) *p = 0xffffffffu;
+    }
     int j = best_j, r = ly - 1;
     while (j >= 0 && r >= 0) {
-      const int b = r >> 3, k = r & 7;
-      const uint32_t kind = (ld_mv((uint32_t)b * nx + j) >> (2 * k)) & 3u;
-      const uint32_t ra = sw(Lp->o_nodeA + j);
-      if (kind & 1u) { sw(Lp->o_x2y + j) = (uint32_t)r; sw(Lp->o_y2x + r) = (uint32_t)j; }
+      const int b = r >> 4, sh = 2 * (15 - (r & 15));
+      uint32_t *p = rec((uint32_t)j);
+      const uint32_t kind = (p[(REC_MOVES + b) * 32] >> sh) & 3u;   // bit 1 match, bit 0 X-gap
+      if (kind & 2u) p[REC_X2Y * 32] = (uint32_t)r;
       if (kind) {  // match or X-gap: step to a predecessor of j
-        int ord = 0;
-        if (ra & (NF_VIRT | NF_TWO)) {
-          const uint32_t w = sw(Lp->o_ord + (ra >> NF_SLOT_SHIFT) * (uint32_t)nb + b);
-          ord = (int)(((kind & 1u) ? (w >> (2 * k)) : (w >> (16 + 2 * k))) & 3u);
+        if (LINEAR) --j;
+        else {
+          const uint32_t ra = p[REC_NODE * 32];
+          int ord = 0;
+          if (ra & (NF_VIRT | NF_TWO)) {
+            const uint32_t *po = &sw(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
+            ord = (int)((((kind & 2u) ? po[0] : po[32]) >> (2 * (r & 15))) & 3u);
+          }
+          const uint32_t pr = p[REC_PRED * 32];
+          const int pA = (pr & 0xffffu) == 0xffffu ? -1 : (int)(pr & 0xffffu), pB = (pr >> 16) == 0xffffu ? -1 : (int)(pr >> 16);
+          if (ra & NF_VIRT) j = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
+          else j = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
         }
-        const int pA = (int)sw(Lp->o_nodeB + 2 * j), pB = (int)sw(Lp->o_nodeB + 2 * j + 1);
-        int nj;
-        if (ra & NF_VIRT) nj = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
-        else nj = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
-        j = nj;
       }
-      if (kind != 2u) --r;  // match or Y-gap: step up
+      if (kind != 1u) --r;  // match or Y-gap: step up
     }
   }
 
+  EL_HD int x2y(int j) const { return (int)rec((uint32_t)j)[REC_X2Y * 32]; }
+  EL_HD uint32_t node(int j) const { return rec((uint32_t)j)[REC_NODE * 32]; }
+  EL_HD void set_node(int j, uint32_t v) const { rec((uint32_t)j)[REC_NODE * 32] = v; }
+
   // ---- fuse 1 (lpo.c:413-463,602-656 for two linear sequences): build P1's node records ----
+  // In place: record n >= ix is written after x2y of record ix has been read.
   EL_HDN int fuse1(int lr, int lc) const {
     int n = 0, iy = 0;
     for (int ix = 0; ix < lr; ++ix) {
-      const int q = (int)sw(Lp->o_x2y + ix);
+      const int q = x2y(ix);
       const int xl = code_at(Lp->o_ref, ix);
       if (q >= 0)
         while (iy < q) {
-          sw(Lp->o_nodeA + n) = (uint32_t)code_at(Lp->o_cor, iy) | NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
+          set_node(n, (uint32_t)code_at(Lp->o_cor, iy) | NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u));
           ++n; ++iy;
         }
       uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
@@ -362,14 +457,14 @@ struct WindowCtx {
         const int yl = code_at(Lp->o_cor, iy);
         const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
         if (yl == xl) fl |= yf;  // identical letters share the node
-        else { sw(Lp->o_nodeA + n) = (uint32_t)yl | yf; ++n; fl |= NF_SAMERING; }  // own node just before x, same ring
+        else { set_node(n, (uint32_t)yl | yf); ++n; fl |= NF_SAMERING; }  // own node just before x, same ring
         ++iy;
       }
-      sw(Lp->o_nodeA + n) = (uint32_t)xl | fl;
+      set_node(n, (uint32_t)xl | fl);
       ++n;
     }
     while (iy < lc) {
-      sw(Lp->o_nodeA + n) = (uint32_t)code_at(Lp->o_cor, iy) | NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
+      set_node(n, (uint32_t)code_at(Lp->o_cor, iy) | NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u));
       ++n; ++iy;
     }
     return n;
@@ -391,7 +486,7 @@ struct WindowCtx {
         if ((col & 3) == 3) { sw(r0 + (col >> 2)) = w0; sw(r1 + (col >> 2)) = w1; sw(r2 + (col >> 2)) = w2; w0 = w1 = w2 = 0; }
       }
     };
-    auto node = [&](int key, uint32_t letter, uint32_t srcmask) {
+    auto emit = [&](int key, uint32_t letter, uint32_t srcmask) {
       if (key != prev_key) { flush(); ++col; c0 = c1 = c2 = '.'; prev_key = key; }
       const uint32_t ch = sym[letter];
       if (srcmask & 1u) c0 = ch;
@@ -399,25 +494,25 @@ struct WindowCtx {
       if (srcmask & 4u) c2 = ch;
     };
     for (int ix = 0; ix < n1; ++ix) {
-      const uint32_t ra = sw(Lp->o_nodeA + ix);
+      const uint32_t ra = node(ix);
       if (!(ra & NF_SAMERING)) rs = ix;
       // scan x's ring from ix on: unaligned y letters go before the first aligned member
       for (int ir = ix;;) {
-        const int q = (int)sw(Lp->o_x2y + ir);
-        if (q >= 0) { while (iy < q) { node(n1 + iy, code_at(Lp->o_unc, iy), 4u); ++iy; } break; }
+        const int q = x2y(ir);
+        if (q >= 0) { while (iy < q) { emit(n1 + iy, code_at(Lp->o_unc, iy), 4u); ++iy; } break; }
         ++ir;
-        if (ir >= n1 || !(sw(Lp->o_nodeA + ir) & NF_SAMERING)) break;
+        if (ir >= n1 || !(node(ir) & NF_SAMERING)) break;
       }
       uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
-      if ((int)sw(Lp->o_x2y + ix) >= 0 && iy < lu) {
+      if (x2y(ix) >= 0 && iy < lu) {
         const uint32_t yl = code_at(Lp->o_unc, iy);
         if (yl == (ra & 0xffu)) mask |= 4u;
-        else node(rs, yl, 4u);
+        else emit(rs, yl, 4u);
         ++iy;
       }
-      node(rs, ra & 0xffu, mask);
+      emit(rs, ra & 0xffu, mask);
     }
-    while (iy < lu) { node(n1 + iy, code_at(Lp->o_unc, iy), 4u); ++iy; }
+    while (iy < lu) { emit(n1 + iy, code_at(Lp->o_unc, iy), 4u); ++iy; }
     flush();
     if ((col & 3) != 3) { sw(r0 + (col >> 2)) = w0; sw(r1 + (col >> 2)) = w1; sw(r2 + (col >> 2)) = w2; }
     return col + 1;
@@ -429,22 +524,20 @@ struct WindowCtx {
     pack_codes(ref, lr, Lp->o_ref);
     pack_codes(cor, lc, Lp->o_cor);
     pack_codes(unc, lu, Lp->o_unc);
-    for (int j = 0; j < lr; ++j)  // P0 = lin(ref) (lpo.c:11-32)
-      sw(Lp->o_nodeA + j) = (uint32_t)code_at(Lp->o_ref, j) | NF_REF | (j == 0 ? NF_INITIAL : 0u) | (j == lr - 1 ? NF_FINAL : 0u);
-    int bj;
-    s1 = dp_sweep(lr, Lp->o_cor, lc, bj);
-    traceback(lr, lc, bj);
+    s1 = dp_linear(lr, Lp->o_cor, lc);       // P0 = lin(ref) (lpo.c:11-32): only node lr-1 is FINAL
+    traceback<true>(lr, lc, lr - 1);
     n1 = fuse1(lr, lc);
-    s2 = dp_sweep(n1, Lp->o_unc, lu, bj);
-    traceback(n1, lu, bj);
+    int bj;
+    s2 = dp_po(n1, Lp->o_unc, lu, bj);
+    traceback<false>(n1, lu, bj);
     return fuse2_emit(n1, lu);
   }
 };
 
 // Persistent kernel, one warp per CTA (up to 32 CTAs per SM; registers bound residency):
 // each warp repeatedly takes 32 consecutive items of the size-sorted work list; lane l owns
-// item base+l.  Shared memory holds only the symbol tables (the 2 KB substitution table
-// only for non-uniform matrices).
+// item base+l.  Shared memory holds the symbol tables (the 2 KB substitution table only for
+// non-uniform matrices), the group's scratch layout and two frontier-set slots (8.25 KB).
 #ifndef EL_MIN_WARPS_PER_SM
 #define EL_MIN_WARPS_PER_SM 24  // register cap 80: measured best trade between occupancy and spills
 #endif
@@ -453,6 +546,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PER_SM) poa_tpw_kernel(PoaArg
   constexpr int kTabWords = (GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4;
   __shared__ uint32_t smem[kTabWords];
   __shared__ ClassLayout s_layout;
+  __shared__ uint32_t s_bset[2 * kSlotWords];
   SymbolTables *tab = reinterpret_cast<SymbolTables *>(smem);
   {
     const uint32_t *s = reinterpret_cast<const uint32_t *>(g_tab);
@@ -466,6 +560,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PER_SM) poa_tpw_kernel(PoaArg
   c.scr = a.scratch + warp_slot * (size_t)a.warp_words * 32;
   c.tab = tab;
   c.Lp = &s_layout;
+  c.bset = s_bset + threadIdx.x;
   c.lane = lane;
   c.match = a.match; c.mismatch = a.mismatch; c.open = a.open; c.ext = a.ext;
 

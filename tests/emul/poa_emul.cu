@@ -25,6 +25,8 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     std::vector<uint32_t> scratch((size_t)L.total * 32, 0xdeadbeefu);
     WindowCtx<GS> c;
     c.scr = scratch.data();
+    std::vector<uint32_t> bset((size_t)2 * kSlotWords, 0xdeadbeefu);
+    c.bset = bset.data() + (w % 32);
     c.tab = &sc.tab;
     c.Lp = &L;
     c.lane = (int)(w % 32);

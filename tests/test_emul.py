@@ -48,3 +48,29 @@ def test_emulated_kernel_rejects_unsupported_matrix(golden_dir, emul_bin, tmp_pa
     rc = subprocess.call([emul_bin, mp, d + "/edge.ref.fa", d + "/edge.cor.fa", d + "/edge.unc.fa", str(tmp_path / "x.pir")],
                          stderr=subprocess.DEVNULL)
     assert rc == 3
+
+
+def test_emulated_kernel_long_windows(golden_dir, emul_bin, tmp_path):
+    """many bands, 8- and 16-row last bands, long placeholder / trimmed windows, vs the oracle"""
+    from oracle import oracle, synth
+    rng = synth.SplitMix64(4242)
+    wins = []
+    for L in (15, 16, 17, 24, 25, 31, 32, 33, 40, 41, 129, 257, 300, 511, 700, 1100):
+        ref = "".join("ACGT"[rng.below(4)] for _ in range(L))
+        wins.append((ref, synth.mutate(rng, ref, 0.03, "ACGT") or "A", synth.mutate(rng, ref, 0.12, "ACGT") or "A"))
+        wins.append((ref, synth.mutate(rng, ref, 0.3, "AC") or "A", synth.mutate(rng, ref, 0.3, "AC") or "A"))
+    wins.append((wins[-2][0], "N", wins[-2][2]))
+    wins.append((wins[-3][0], wins[-3][1][:40], wins[-3][2]))
+    wins.append(("ACGT" * 30, "ACGT" * 30, "A"))
+    paths = []
+    for k, key in enumerate(("ref", "cor", "unc")):
+        p = str(tmp_path / (key + ".fa"))
+        with open(p, "w") as f:
+            for i, w in enumerate(wins):
+                f.write(">w%d\n%s\n" % (i, w[k]))
+        paths.append(p)
+    pir, opir = str(tmp_path / "e.pir"), str(tmp_path / "o.pir")
+    mp = golden_dir + "/blosum80.mat"
+    assert subprocess.call([emul_bin, mp, paths[0], paths[1], paths[2], pir]) == 0
+    assert oracle.poa_files(mp, paths[0], paths[1], paths[2], opir) == 0
+    assert open(pir, "rb").read() == open(opir, "rb").read()
