@@ -1,120 +1,147 @@
 // bin_kernel.cuh -- device-side scheduling of the windows of one call.
 //
-// The POA kernel runs one window per thread in lock step, so a warp is only efficient when
-// its 32 windows have the same loop shape: the same number of 8-row bands in both DPs and a
-// similar number of columns.  These three small kernels sort the window ids by
-// (bands of DP2, bands of DP1, reference length / 4), largest first, with a counting sort
-// (histogram -> single-CTA scan -> scatter), and cut the sorted list into a few SEGMENTS
-// (one launch each) whose per-warp scratch is sized by the segment's own maxima.
-// Everything stays on the device; the host reads back one 1 KB table.
+// The POA kernels run one window per thread in lock step, so a warp is only efficient when
+// its 32 windows have the same loop shape.  Each phase therefore sorts the window ids with a
+// counting sort (histogram -> chunked scan -> scatter), largest first, and cuts the sorted
+// list into a few SEGMENTS (one launch each) whose per-warp scratch is sized by the segment's
+// own maxima:
+//   phase 1 (DP1, cost ~ bands(cor) x len(ref)):  key = (8-row half-bands of cor, len(ref)/2)
+//   phase 2 (DP2, cost ~ bands(unc) x len(P1)):   key = (half-bands of unc, len(P1)/4, where and how
+//            ref and cor first differ) -- computed by the phase-1 kernel itself (bin2_of)
+// Everything stays on the device; the host reads back one small table per phase.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "poa_kernel.cuh"
+
 namespace elector {
 
-constexpr int kBigTiers = 8;          // windows with a sequence longer than 256: one bin per power of two
-constexpr int kSmallMax = 256;        // longest sequence of a "small" window
-constexpr int kNbMax = kSmallMax / 8; // bands of a small window: 1..32
-constexpr int kXq = 65;               // reference-length quanta (lr / 4: 0..64)
-constexpr int kSmallBins = kNbMax * kNbMax * kXq;
-constexpr int kNumBins = kBigTiers + kSmallBins;
-constexpr int kNumSegs = kBigTiers + 4;
-constexpr int kMaxWindowLen = 32000;  // node records index their ordinal slot with 15 bits
+constexpr int kXq1 = 129;                         // len(ref)/2 quanta of a small window
+constexpr int kSmallBins1 = kNbMax * kXq1;
+constexpr int kNumBins1 = kBigTiers + kSmallBins1;
+constexpr int kNumSegs1 = kBigTiers + 3;
+constexpr int kMaxSegs = kNumSegs2 > kNumSegs1 ? kNumSegs2 : kNumSegs1;
+constexpr int kMaxBins = kNumBins2 > kNumBins1 ? kNumBins2 : kNumBins1;
+constexpr int kScanChunk = 1024;
+constexpr int kMaxChunks = (kMaxBins + kScanChunk - 1) / kScanChunk;
+constexpr int kMaxWindowLen = 32000;              // node records hold predecessors in 16 bits, ordinal slots in 15
 
-struct SegInfo {      // one launch of the POA kernel
-  int32_t count;      // windows
-  int32_t start;      // first position in the sorted item list
-  int32_t max_lr, max_lc, max_lu;
-  int32_t pad[3];
+struct SegInfo {      // one launch of a POA kernel
+  int32_t first_bin;  // in: first bin of the segment (bins of a segment are contiguous)
+  int32_t start;      // out: first position in the sorted item list
+  int32_t count;      // out: windows
+  int32_t pad;
 };
 
 struct BinTable {
-  SegInfo seg[kNumSegs];
+  SegInfo seg[kMaxSegs + 1];   // [nseg].first_bin = number of bins
+  int32_t seg_max[kMaxSegs * 4];  // per segment maxima: phase 1 {lr, lc}, phase 2 {n1, lu}
+  int32_t nseg, nbins;
   int32_t err_code;    // 0 ok, 1 empty sequence, 2 sequence longer than kMaxWindowLen
   int32_t err_window;  // smallest offending window id
 };
 
-__device__ __forceinline__ int seg_of_small(int nb2) { return kBigTiers + (nb2 > 16 ? 0 : nb2 > 8 ? 1 : nb2 > 4 ? 2 : 3); }
-
-__device__ __forceinline__ void bin_of(int lr, int lc, int lu, int &bin, int &seg) {
-  const int mx = max(lr, max(lc, lu));
+__host__ __device__ inline int seg1_of_nb(int nb8) { return kBigTiers + (nb8 > 16 ? 0 : nb8 > 8 ? 1 : 2); }
+__host__ __device__ inline void bin1_of(int lr, int lc, int &bin, int &seg) {
+  const int mx = lr > lc ? lr : lc;
   if (mx > kSmallMax) {
-    int t = 1;
-    while ((kSmallMax << t) < mx) ++t;  // t = 1: <= 512, 2: <= 1024, ...
-    t = min(t, kBigTiers);
-    bin = seg = kBigTiers - t;          // the largest tier comes first
+    bin = seg = kBigTiers - big_tier(mx);   // the largest tier comes first
   } else {
-    const int nb2 = (lu + 7) >> 3, nb1 = (lc + 7) >> 3, xq = lr >> 2;
-    const int small = ((nb2 - 1) * kNbMax + (nb1 - 1)) * kXq + xq;
-    bin = kBigTiers + (kSmallBins - 1 - small);
-    seg = seg_of_small(nb2);
+    const int nb8 = (lc + 7) >> 3;
+    const int small = (nb8 - 1) * kXq1 + (lr >> 1);
+    bin = kBigTiers + (kSmallBins1 - 1 - small);
+    seg = seg1_of_nb(nb8);
   }
 }
+// first bin of every segment (host side, goes into BinTable::seg[].first_bin)
+inline void fill_segments1(BinTable &t) {
+  t.nseg = kNumSegs1; t.nbins = kNumBins1;
+  for (int s = 0; s < kBigTiers; ++s) t.seg[s].first_bin = s;
+  const int hi[3] = {32, 16, 8};
+  for (int k = 0; k < 3; ++k) t.seg[kBigTiers + k].first_bin = kBigTiers + (kSmallBins1 - 1 - ((hi[k] - 1) * kXq1 + (kXq1 - 1)));
+  t.seg[kNumSegs1].first_bin = kNumBins1;
+}
+inline void fill_segments2(BinTable &t) {
+  t.nseg = kNumSegs2; t.nbins = kNumBins2;
+  for (int s = 0; s < kBigTiers; ++s) t.seg[s].first_bin = s;
+  const int hi[4] = {32, 16, 8, 4};
+  for (int k = 0; k < 4; ++k)
+    t.seg[kBigTiers + k].first_bin = kBigTiers + (kSmallBins2 - 1 - (((hi[k] - 1) * kN1q + (kN1q - 1)) * kSpCodes + (kSpCodes - 1)));
+  t.seg[kNumSegs2].first_bin = kNumBins2;
+}
 
-// hist[bin] += 1; per-segment maxima; validation
-__global__ void __launch_bounds__(256) bin_count_kernel(int32_t n, const int64_t *ro, const int64_t *co, const int64_t *uo,
-                                                         int32_t *hist, BinTable *tab) {
+// phase 1: key[w] = bin (or -1 for an invalid window), hist[bin] += 1, segment maxima
+__global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_t *ro, const int64_t *co, const int64_t *uo,
+                                                          int32_t *key, int32_t *hist, BinTable *tab) {
   for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
-    const int64_t lr64 = ro[w + 1] - ro[w], lc64 = co[w + 1] - co[w], lu64 = uo[w + 1] - uo[w];
-    if (lr64 <= 0 || lc64 <= 0 || lu64 <= 0) { atomicMax(&tab->err_code, 1); atomicMin(&tab->err_window, w); continue; }
-    if (lr64 > kMaxWindowLen || lc64 > kMaxWindowLen || lu64 > kMaxWindowLen) { atomicMax(&tab->err_code, 2); atomicMin(&tab->err_window, w); continue; }
-    const int lr = (int)lr64, lc = (int)lc64, lu = (int)lu64;
-    int bin, seg;
-    bin_of(lr, lc, lu, bin, seg);
-    atomicAdd(&hist[bin], 1);
-    SegInfo *s = &tab->seg[seg];
-    if (lr > s->max_lr) atomicMax(&s->max_lr, lr);
-    if (lc > s->max_lc) atomicMax(&s->max_lc, lc);
-    if (lu > s->max_lu) atomicMax(&s->max_lu, lu);
+    const int64_t lr = ro[w + 1] - ro[w], lc = co[w + 1] - co[w], lu = uo[w + 1] - uo[w];
+    int bin = -1;
+    if (lr <= 0 || lc <= 0 || lu <= 0) { atomicMax(&tab->err_code, 1); atomicMin(&tab->err_window, w); }
+    else if (lr > kMaxWindowLen || lc > kMaxWindowLen || lu > kMaxWindowLen) { atomicMax(&tab->err_code, 2); atomicMin(&tab->err_window, w); }
+    else {
+      int seg;
+      bin1_of((int)lr, (int)lc, bin, seg);
+      atomicAdd(&hist[bin], 1);
+      int32_t *mx = &tab->seg_max[seg * 4];
+      if ((int)lr > mx[0]) atomicMax(&mx[0], (int)lr);
+      if ((int)lc > mx[1]) atomicMax(&mx[1], (int)lc);
+    }
+    key[w] = bin;
   }
 }
 
-// exclusive scan of the histogram in place (hist[bin] becomes the bin's first position) and
-// the start / count of every segment; one CTA (67 608 bins: a few microseconds)
-__global__ void __launch_bounds__(1024) bin_scan_kernel(int32_t *hist, BinTable *tab) {
-  __shared__ int32_t part[1024];
-  constexpr int per = (kNumBins + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(lo + per, kNumBins);
-  int32_t sum = 0;
-  for (int i = lo; i < hi; ++i) sum += hist[i];
-  part[threadIdx.x] = sum;
+// exclusive scan of each 1024-bin chunk in place + the chunk totals
+__global__ void __launch_bounds__(kScanChunk) bin_scan_chunks_kernel(int32_t nbins, int32_t *hist, int32_t *chunk_total) {
+  __shared__ int32_t warp_sum[32];
+  const int i = blockIdx.x * kScanChunk + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int32_t v = i < nbins ? hist[i] : 0;
+  int32_t incl = v;
+  for (int d = 1; d < 32; d <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) warp_sum[wid] = incl;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan of the partial sums
+  if (wid == 0) {
+    int32_t s = warp_sum[lane];
+    for (int d = 1; d < 32; d <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += t; }
+    warp_sum[lane] = s;
+  }
+  __syncthreads();
+  const int32_t before = (wid ? warp_sum[wid - 1] : 0) + incl - v;
+  if (i < nbins) hist[i] = before;
+  if (threadIdx.x == kScanChunk - 1) chunk_total[blockIdx.x] = before + v;
+}
+
+// exclusive scan of the chunk totals (in place -> chunk bases) and the start / count of every segment
+__global__ void __launch_bounds__(1024) bin_scan_totals_kernel(int32_t nchunks, int32_t *chunk_total, const int32_t *hist, BinTable *tab) {
+  __shared__ int32_t part[1024];
+  const int32_t v = (int)threadIdx.x < nchunks ? chunk_total[threadIdx.x] : 0;
+  part[threadIdx.x] = v;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
     const int32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
     __syncthreads();
     part[threadIdx.x] += t;
     __syncthreads();
   }
-  int32_t run = part[threadIdx.x] - sum;
-  for (int i = lo; i < hi; ++i) { const int32_t c = hist[i]; hist[i] = run; run += c; }
+  const int32_t total = part[1023];
+  if ((int)threadIdx.x < nchunks) chunk_total[threadIdx.x] = part[threadIdx.x] - v;
   __syncthreads();
-  if (threadIdx.x < kNumSegs) {
-    // first bin of every segment (bins are ordered largest first; small bins descend in nb2)
-    auto first_bin = [](int seg) {
-      if (seg < kBigTiers) return seg;
-      if (seg >= kNumSegs) return kNumBins;
-      const int nb2_hi = seg == kBigTiers ? 32 : seg == kBigTiers + 1 ? 16 : seg == kBigTiers + 2 ? 8 : 4;
-      const int small_hi = ((nb2_hi - 1) * kNbMax + (kNbMax - 1)) * kXq + (kXq - 1);
-      return kBigTiers + (kSmallBins - 1 - small_hi);
-    };
+  if ((int)threadIdx.x < tab->nseg) {
     const int s = threadIdx.x;
-    const int b0 = first_bin(s), b1 = first_bin(s + 1);
-    const int32_t total = part[1023];
-    const int32_t p0 = b0 < kNumBins ? hist[b0] : total, p1 = b1 < kNumBins ? hist[b1] : total;
+    auto pos_of = [&](int bin) { return bin >= tab->nbins ? total : chunk_total[bin / kScanChunk] + hist[bin]; };
+    const int32_t p0 = pos_of(tab->seg[s].first_bin), p1 = pos_of(tab->seg[s + 1].first_bin);
     tab->seg[s].start = p0;
     tab->seg[s].count = p1 - p0;
   }
 }
 
-__global__ void __launch_bounds__(256) bin_scatter_kernel(int32_t n, const int64_t *ro, const int64_t *co, const int64_t *uo,
-                                                           int32_t *cursor, int32_t *items) {
+__global__ void __launch_bounds__(256) bin_scatter_kernel(int32_t n, const int32_t *key, int32_t *cursor, const int32_t *chunk_base,
+                                                           int32_t *items) {
   for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
-    const int64_t lr = ro[w + 1] - ro[w], lc = co[w + 1] - co[w], lu = uo[w + 1] - uo[w];
-    if (lr <= 0 || lc <= 0 || lu <= 0 || lr > kMaxWindowLen || lc > kMaxWindowLen || lu > kMaxWindowLen) continue;  // reported by bin_count_kernel
-    int bin, seg;
-    bin_of((int)lr, (int)lc, (int)lu, bin, seg);
-    items[atomicAdd(&cursor[bin], 1)] = w;
+    const int bin = key[w];
+    if (bin < 0) continue;  // invalid window, reported by bin1_count_kernel
+    items[chunk_base[bin / kScanChunk] + atomicAdd(&cursor[bin], 1)] = w;
   }
 }
 

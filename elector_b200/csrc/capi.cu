@@ -51,7 +51,8 @@ struct elector_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int resident_warps = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int resident_ph1 = 0, resident_ph2 = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr;
@@ -59,7 +60,7 @@ struct elector_ctx {
   elector::BinTable *h_bintab = nullptr;  // pinned
   ScoreMatrix mat;
   ScoringSetup sc;
-  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab;
+  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   DevBuf d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
   std::string err;
@@ -85,26 +86,92 @@ struct elector_ctx {
 
 namespace {
 
-const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..] segment work counters
+const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..19] phase-1 and [20..35] phase-2 work counters
 const int kSideStreams = 3;
 
 template <bool GS>
-cudaError_t launch_segment(cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
-  poa_tpw_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
+cudaError_t launch_phase(int phase, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
+  if (phase == 1) poa_dp1_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
+  else poa_dp2_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
   return cudaGetLastError();
 }
 
 template <bool GS>
-int resident_warps_per_sm() {
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, poa_tpw_kernel<GS>, 32, 0);
-  return nb;
+void resident_warps_per_sm(int &ph1, int &ph2) {
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1, poa_dp1_kernel<GS>, 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2, poa_dp2_kernel<GS>, 32, 0);
+}
+
+struct SegPlan { int seg, grid; size_t warp_words, scratch_off; };
+
+// grid and scratch of every non-empty segment of one phase
+int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<SegPlan> &plan, size_t &scratch_words) {
+  const int resident = std::max(1, phase == 1 ? ctx->resident_ph1 : ctx->resident_ph2) * ctx->sm_count;
+  const size_t budget_words = ((size_t)24 << 30) / 4;
+  plan.clear();
+  scratch_words = 0;
+  for (int s = 0; s < bt.nseg; ++s) {
+    const SegInfo &si = bt.seg[s];
+    if (si.count <= 0) continue;
+    const int m0 = bt.seg_max[s * 4], m1 = bt.seg_max[s * 4 + 1];
+    size_t total;
+    if (phase == 1) { Layout1 L; make_layout1(L, m0, m1); total = L.total; }
+    else { Layout2 L; make_layout2(L, m0, m1); total = L.total; }
+    SegPlan p;
+    p.seg = s;
+    p.warp_words = total;
+    p.grid = (int)std::min<int64_t>(resident, ((int64_t)si.count + 31) / 32);
+    // bound the scratch of segments with huge windows: fewer resident warps
+    const size_t per_warp = total * 32;
+    while (p.grid > 1 && per_warp * (size_t)p.grid > budget_words / 2) p.grid = (p.grid + 1) / 2;
+    if (per_warp * (size_t)p.grid > budget_words)
+      return ctx->fail(ELECTOR_ETOOLARGE, "windows of %d x %d letters need %zu MiB scratch per warp in phase %d", m0, m1, (per_warp * 4) >> 20, phase);
+    p.scratch_off = scratch_words;
+    scratch_words += per_warp * (size_t)p.grid;
+    plan.push_back(p);
+  }
+  if (scratch_words > 2 * budget_words) return ctx->fail(ELECTOR_ETOOLARGE, "call needs %zu MiB of scratch", (scratch_words * 4) >> 20);
+  return ELECTOR_OK;
+}
+
+// One phase: the segments holding the largest windows (few items, long per-item time) start
+// first, on side streams, so that their tail overlaps the bulk on the main stream.
+int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, const std::vector<SegPlan> &plan, PoaArgs base) {
+  cudaStream_t st = ctx->stream;
+  CU(cudaEventRecord(ctx->ev_fork, st));
+  int side = 0, used_side = 0;
+  for (size_t k = 0; k < plan.size(); ++k) {
+    const SegPlan &p = plan[k];
+    const SegInfo &si = bt.seg[p.seg];
+    const bool bulk = k + 1 == plan.size() || (int64_t)si.count * 8 > n;  // the smallest windows and any large share stay on the main stream
+    cudaStream_t ls = st;
+    if (!bulk) {
+      ls = ctx->side[side];
+      if (!(used_side & (1 << side))) { CU(cudaStreamWaitEvent(ls, ctx->ev_fork, 0)); used_side |= 1 << side; }
+      side = (side + 1) % kSideStreams;
+    }
+    PoaArgs a = base;
+    a.items = ctx->d_items.as<int32_t>() + si.start;
+    a.n_items = si.count;
+    a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
+    a.warp_words = (uint32_t)p.warp_words;
+    a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + (phase == 1 ? 0 : 16) + p.seg;
+    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
+                                              : launch_phase<false>(phase, ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
+    if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    ++ctx->last_launches;
+  }
+  for (int k = 0; k < kSideStreams; ++k)
+    if (used_side & (1 << k)) {
+      CU(cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
+      CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
+    }
+  return ELECTOR_OK;
 }
 
 // Core: all pointers are device pointers.  Launch structure of one call:
-//   main stream : bin_count -> bin_scan -> bin_scatter -> (table to host) -> the bulk segments
-//   side streams: the segments holding the largest windows (few items, long per-item time),
-//                 started first so that their tail overlaps the bulk
+//   sort 1 (3 kernels) -> table to host -> phase-1 segments -> sort 2 (scan + scatter; its
+//   histogram was filled by phase 1) -> table to host -> phase-2 segments
 int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
                const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, char *d_rows, int64_t rows_cap,
                int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2, int64_t *d_cells,
@@ -115,93 +182,71 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   if (n > 0x7fffffff - 64) return ctx->fail(ELECTOR_EINVAL, "too many windows in one call");
   cudaStream_t st = ctx->stream;
   CU(ctx->d_items.reserve((size_t)n * sizeof(int32_t)));
-  CU(ctx->d_hist.reserve((size_t)kNumBins * sizeof(int32_t)));
-  CU(ctx->d_bintab.reserve(sizeof(BinTable)));
+  CU(ctx->d_key.reserve((size_t)n * sizeof(int32_t)));
+  CU(ctx->d_n1.reserve((size_t)n * sizeof(int32_t)));
+  CU(ctx->d_hist.reserve((size_t)(kNumBins1 + kNumBins2 + 2 * kMaxChunks) * sizeof(int32_t)));
+  CU(ctx->d_bintab.reserve(2 * sizeof(BinTable)));
+  int32_t *hist1 = ctx->d_hist.as<int32_t>(), *hist2 = hist1 + kNumBins1, *chunks1 = hist2 + kNumBins2, *chunks2 = chunks1 + kMaxChunks;
+  BinTable *dtab1 = ctx->d_bintab.as<BinTable>(), *dtab2 = dtab1 + 1;
+  BinTable *htab1 = ctx->h_bintab, *htab2 = ctx->h_bintab + 1;
   CU(cudaEventRecord(ctx->ev0, st));
   CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(int32_t) * kCtrlWords, st));
-  CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)kNumBins * sizeof(int32_t), st));
-  {
-    BinTable init;
-    memset(&init, 0, sizeof init);
-    init.err_window = 0x7fffffff;
-    memcpy(ctx->h_bintab, &init, sizeof init);
-    CU(cudaMemcpyAsync(ctx->d_bintab.p, ctx->h_bintab, sizeof(BinTable), cudaMemcpyHostToDevice, st));
-  }
+  CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)(kNumBins1 + kNumBins2) * sizeof(int32_t), st));
+  memset(htab1, 0, 2 * sizeof(BinTable));
+  fill_segments1(*htab1);
+  fill_segments2(*htab2);
+  htab1->err_window = 0x7fffffff;
+  CU(cudaMemcpyAsync(dtab1, htab1, 2 * sizeof(BinTable), cudaMemcpyHostToDevice, st));
   const int bgrid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
-  bin_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_hist.as<int32_t>(), ctx->d_bintab.as<BinTable>());
-  bin_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_hist.as<int32_t>(), ctx->d_bintab.as<BinTable>());
-  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_hist.as<int32_t>(), ctx->d_items.as<int32_t>());
+  const int nch1 = (kNumBins1 + kScanChunk - 1) / kScanChunk, nch2 = (kNumBins2 + kScanChunk - 1) / kScanChunk;
+  // ---- sort 1 ----
+  bin1_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_key.as<int32_t>(), hist1, dtab1);
+  bin_scan_chunks_kernel<<<nch1, kScanChunk, 0, st>>>(kNumBins1, hist1, chunks1);
+  bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch1, chunks1, hist1, dtab1);
+  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key.as<int32_t>(), hist1, chunks1, ctx->d_items.as<int32_t>());
+  CU(cudaGetLastError());
+  ctx->last_launches += 4;
+  CU(cudaMemcpyAsync(htab1, dtab1, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&ctx->h_totals[0], d_roff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&ctx->h_totals[1], d_coff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (htab1->err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", htab1->err_window);
+  if (htab1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d longer than %d letters", htab1->err_window, kMaxWindowLen);
+  CU(ctx->d_p1.reserve((size_t)(ctx->h_totals[0] + ctx->h_totals[1]) * sizeof(uint16_t) + 16));
+
+  PoaArgs a;
+  memset(&a, 0, sizeof a);
+  a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
+  a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
+  a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
+  a.p1_nodes = ctx->d_p1.as<uint16_t>(); a.n1 = ctx->d_n1.as<int32_t>(); a.key2 = ctx->d_key.as<int32_t>();
+  a.hist2 = hist2; a.seg2_max = dtab2->seg_max;
+  a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
+  a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
+  a.error_flag = d_errflag;
+
+  // ---- phase 1 ----
+  std::vector<SegPlan> plan;
+  size_t scratch_words = 0;
+  int rc = plan_segments(ctx, 1, *htab1, plan, scratch_words);
+  if (rc != ELECTOR_OK) return rc;
+  CU(ctx->d_scratch.reserve(scratch_words * 4));
+  rc = launch_segments(ctx, 1, n, *htab1, plan, a);
+  if (rc != ELECTOR_OK) return rc;
+  // ---- sort 2 (phase 1 filled key2, hist2 and the segment maxima) ----
+  bin_scan_chunks_kernel<<<nch2, kScanChunk, 0, st>>>(kNumBins2, hist2, chunks2);
+  bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch2, chunks2, hist2, dtab2);
+  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key.as<int32_t>(), hist2, chunks2, ctx->d_items.as<int32_t>());
   CU(cudaGetLastError());
   ctx->last_launches += 3;
-  CU(cudaMemcpyAsync(ctx->h_bintab, ctx->d_bintab.p, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(htab2, dtab2, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  const BinTable &bt = *ctx->h_bintab;
-  if (bt.err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", bt.err_window);
-  if (bt.err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d longer than %d letters", bt.err_window, kMaxWindowLen);
-
-  // ---- plan the segment launches: grid and scratch ----
-  const int resident = std::max(1, ctx->resident_warps) * ctx->sm_count;
-  struct Plan { int seg, grid; size_t warp_words, scratch_off; };
-  std::vector<Plan> plan;
-  size_t scratch_words = 0;
-  const size_t budget_words = ((size_t)24 << 30) / 4;
-  for (int s = 0; s < kNumSegs; ++s) {
-    const SegInfo &si = bt.seg[s];
-    if (si.count <= 0) continue;
-    ClassLayout L;
-    make_layout(L, si.max_lr, si.max_lc, si.max_lu);
-    Plan p;
-    p.seg = s;
-    p.warp_words = L.total;
-    const int64_t groups = ((int64_t)si.count + 31) / 32;
-    p.grid = (int)std::min<int64_t>(resident, groups);
-    // bound the scratch of segments with huge windows: fewer resident warps
-    const size_t per_warp = (size_t)L.total * 32;
-    while (p.grid > 1 && per_warp * (size_t)p.grid > budget_words / 2) p.grid = (p.grid + 1) / 2;
-    if (per_warp * (size_t)p.grid > budget_words)
-      return ctx->fail(ELECTOR_ETOOLARGE, "windows of %d x %d x %d letters need %zu MiB scratch per warp", si.max_lr, si.max_lc, si.max_lu, (per_warp * 4) >> 20);
-    p.scratch_off = scratch_words;
-    scratch_words += per_warp * (size_t)p.grid;
-    plan.push_back(p);
-  }
-  if (scratch_words > 2 * budget_words) return ctx->fail(ELECTOR_ETOOLARGE, "call needs %zu MiB of scratch", (scratch_words * 4) >> 20);
+  // ---- phase 2 ----
+  rc = plan_segments(ctx, 2, *htab2, plan, scratch_words);
+  if (rc != ELECTOR_OK) return rc;
   CU(ctx->d_scratch.reserve(scratch_words * 4));
-
-  // ---- launch: big-window segments first, on side streams ----
-  CU(cudaEventRecord(ctx->ev_fork, st));
-  int side = 0, used_side = 0;
-  for (size_t k = 0; k < plan.size(); ++k) {
-    const Plan &p = plan[k];
-    const SegInfo &si = bt.seg[p.seg];
-    const bool bulk = k + 1 == plan.size() || (int64_t)si.count * 8 > n;  // the last (smallest windows) and any large share stay on the main stream
-    cudaStream_t ls = st;
-    if (!bulk) {
-      ls = ctx->side[side];
-      if (!(used_side & (1 << side))) { CU(cudaStreamWaitEvent(ls, ctx->ev_fork, 0)); used_side |= 1 << side; }
-      side = (side + 1) % kSideStreams;
-    }
-    PoaArgs a;
-    a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
-    a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
-    a.items = ctx->d_items.as<int32_t>() + si.start;
-    a.n_items = si.count;
-    a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
-    a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
-    a.warp_words = (uint32_t)p.warp_words;
-    a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + p.seg;
-    a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
-    a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
-    a.error_flag = d_errflag;
-    const cudaError_t e = ctx->sc.generic_sub ? launch_segment<true>(ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
-                                              : launch_segment<false>(ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
-    if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
-    ++ctx->last_launches;
-  }
-  for (int k = 0; k < kSideStreams; ++k)
-    if (used_side & (1 << k)) {
-      CU(cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
-      CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
-    }
+  rc = launch_segments(ctx, 2, n, *htab2, plan, a);
+  if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev1, st));
   return ELECTOR_OK;
 }
@@ -249,15 +294,17 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_join[2], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaMallocHost((void **)&ctx->h_bintab, sizeof(BinTable))) != cudaSuccess ||
+      (e = cudaMallocHost((void **)&ctx->h_bintab, 2 * sizeof(BinTable))) != cudaSuccess ||
+      (e = cudaMallocHost((void **)&ctx->h_totals, 2 * sizeof(int64_t))) != cudaSuccess ||
       (e = ctx->d_tab.reserve(sizeof(SymbolTables))) != cudaSuccess ||
       (e = ctx->d_ctrl.reserve(kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(ctx->d_tab.p, &ctx->sc.tab, sizeof(SymbolTables), cudaMemcpyHostToDevice)) != cudaSuccess) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
-  ctx->resident_warps = ctx->sc.generic_sub ? resident_warps_per_sm<true>() : resident_warps_per_sm<false>();
-  if (ctx->resident_warps < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
+  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2);
+  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2);
+  if (ctx->resident_ph1 < 1 || ctx->resident_ph2 < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;
 }
@@ -265,7 +312,7 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
 void elector_poa_free(elector_ctx *ctx) {
   if (!ctx) return;
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
-                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
+                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
                     &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_tally_scan, &ctx->d_tally_out,
                     &ctx->d_readfirst, &ctx->d_mtot, &ctx->d_moff, &ctx->d_mlen, &ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
   for (DevBuf *b : bufs) b->release();
@@ -279,6 +326,7 @@ void elector_poa_free(elector_ctx *ctx) {
     if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
   }
   if (ctx->h_bintab) cudaFreeHost(ctx->h_bintab);
+  if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

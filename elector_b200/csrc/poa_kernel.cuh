@@ -5,10 +5,18 @@
 //   align_lpo_po(lin(ref), lin(cor)) -> fuse_lpo -> P1
 //   align_lpo_po(P1, lin(unc))       -> fuse_lpo -> P2 -> xlate_lpo_to_al (3-row MSA)
 // Hundreds of millions of such tiny integer DPs are independent, so the device mapping
-// is inter-task: ONE THREAD OWNS ONE WINDOW for the whole pipeline (pack, DP1, traceback,
-// fuse, DP2, traceback, fuse, emit), 32 windows of similar size per warp, persistent
-// warps pulling 32-window groups from a global counter.  No tensor cores: this is INT32
-// DP; the bound is the integer issue rate.
+// is inter-task: ONE THREAD OWNS ONE WINDOW, 32 windows of the same loop shape per warp,
+// persistent warps pulling 32-window groups from a global counter.  No tensor cores: this
+// is INT32 DP; the bound is the integer issue rate.
+//
+// Two kernels, each with its own device-side sort of the windows (bin_kernel.cuh):
+//   poa_dp1_kernel : pack ref/cor, DP1 (linear x linear), traceback, fuse 1 -> P1 node list
+//                    (16 bits per node, window-major in global memory) + the sort key of phase 2
+//   poa_dp2_kernel : pack unc, node preparation, DP2 (P1 x linear), traceback, fuse 2 + MSA emit
+// Splitting keeps each kernel's code inside the 32 KB instruction cache (the fused kernel
+// stalled on instruction fetch), lets phase 2 be sorted by len(P1) and by WHERE ref and cor
+// first differ (lanes of a warp then take the uncommon path of DP2 together instead of one
+// after the other), and gives DP1 a smaller register footprint.
 //
 // DP data placement (the part that decides the speed)
 //   * The DP matrix is swept in BANDS of 16 rows (a last band of 8 when at most 8 rows are
@@ -40,20 +48,7 @@
 
 namespace elector {
 
-constexpr int kBand = 16;     // rows per register band (the last band may have 8)
-constexpr int kRecWords = 5;  // fixed words of a node record, followed by one moves word per band
-
-struct ClassLayout {  // per-thread scratch layout (32-bit words) of a group of windows
-  int32_t LR, LC, LU;  // caps: max ref / cor / unc length of the group
-  uint32_t o_ref, o_cor, o_unc;  // packed symbol codes, 4 per word
-  uint32_t o_nodes;              // node records: LR+LC records of rec_words words
-  uint32_t rec_words;            //   +0 node flags|letter  +1 boundary S  +2 boundary G  +3 preds  +4 x2y  +5+b moves of band b
-  uint32_t o_ord;                // two words per (combined node, band): winning predecessor ordinals
-  uint32_t ord_bands;            // bands per ordinal slot
-  uint32_t o_rows;               // 3 MSA rows, bytes packed 4 per word
-  uint32_t row_words;            // words per row in o_rows
-  uint32_t total;                // words per thread
-};
+constexpr int kBand = 16;  // rows per register band (the last band may have 8)
 
 #define EL_WARP_FULL 0xffffffffu
 #define EL_HD __host__ __device__ __forceinline__
@@ -62,22 +57,46 @@ struct ClassLayout {  // per-thread scratch layout (32-bit words) of a group of 
 EL_HD uint32_t cdiv_u(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 EL_HD uint32_t max_u(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
-// Scratch layout for windows with ref / cor / unc lengths up to (LR, LC, LU).  Every term is
-// monotone in each cap, so a layout for the maxima of a launch bounds the layout of any of
-// its 32-window groups (which compute their own, tighter one on the device).
-EL_HD void make_layout(ClassLayout &L, int LR, int LC, int LU) {
-  L.LR = LR; L.LC = LC; L.LU = LU;
-  const uint32_t N1 = (uint32_t)LR + (uint32_t)LC;             // cap of len(P1)
-  const uint32_t nb = max_u(cdiv_u(LC, kBand), cdiv_u(LU, kBand));
+// ---- per-thread scratch layouts (32-bit words), one per phase ------------------------------
+// Every term is monotone in each cap, so a layout for the maxima of a launch bounds the
+// layout of any of its 32-window groups (which compute their own, tighter one on the device).
+enum : uint32_t { R1_BS = 0, R1_BG = 1, R1_X2Y = 2, R1_MOVES = 3 };                                      // phase-1 node record
+enum : uint32_t { R2_NODE = 0, R2_BS = 1, R2_BG = 2, R2_PRED = 3, R2_X2Y = 4, R2_MOVES = 5 };            // phase-2 node record
+
+struct Layout1 {            // phase 1: windows with ref / cor lengths up to (LR, LC)
+  uint32_t o_ref, o_cor;    // packed symbol codes, 4 per word
+  uint32_t o_nodes;         // LR records of rec_words words: boundary S, boundary G, x2y, one moves word per band
+  uint32_t rec_words;
+  uint32_t total;
+};
+struct Layout2 {            // phase 2: windows with len(P1) / unc length up to (N1, LU)
+  uint32_t o_unc;           // packed symbol codes
+  uint32_t o_nodes;         // N1 records: node flags|letter, boundary S, boundary G, preds, x2y, moves per band
+  uint32_t rec_words;
+  uint32_t o_ord;           // two words per (combined node, band): winning predecessor ordinals
+  uint32_t ord_bands;
+  uint32_t o_rows;          // 3 MSA rows, bytes packed 4 per word
+  uint32_t row_words;
+  uint32_t total;
+};
+
+EL_HD void make_layout1(Layout1 &L, int LR, int LC) {
   uint32_t o = 0;
-  L.o_ref = o; o += cdiv_u(LR, 4) + 4;                         // +4: a band reads four code words at once
-  L.o_cor = o; o += cdiv_u(LC, 4) + 4;
+  L.o_ref = o; o += cdiv_u(LR, 4) + 1;
+  L.o_cor = o; o += cdiv_u(LC, 4) + 4;                          // +4: a band reads four code words at once
+  L.rec_words = R1_MOVES + cdiv_u(LC, kBand);
+  L.o_nodes = o; o += (uint32_t)LR * L.rec_words;
+  L.total = o;
+}
+EL_HD void make_layout2(Layout2 &L, int N1, int LU) {
+  const uint32_t nb = cdiv_u(LU, kBand);
+  uint32_t o = 0;
   L.o_unc = o; o += cdiv_u(LU, 4) + 4;
-  L.rec_words = kRecWords + nb;
-  L.o_nodes = o; o += N1 * L.rec_words;
+  L.rec_words = R2_MOVES + nb;
+  L.o_nodes = o; o += (uint32_t)N1 * L.rec_words;
   L.ord_bands = nb;
-  L.o_ord = o; o += ((uint32_t)(LR < LC ? LR : LC) + 2) * nb * 2;
-  L.row_words = cdiv_u(LR + LC + LU, 4);
+  L.o_ord = o; o += ((uint32_t)N1 / 2 + 2) * nb * 2;            // combined nodes carry ref AND cor: at most N1/2, + 2 initial ones
+  L.row_words = cdiv_u(N1 + LU, 4);
   L.o_rows = o; o += 3 * L.row_words;
   L.total = o;
 }
@@ -85,12 +104,19 @@ EL_HD void make_layout(ClassLayout &L, int LR, int LC, int LU) {
 struct PoaArgs {
   const uint8_t *ref, *cor, *unc;  // raw FASTA letters, concatenated
   const int64_t *ref_off, *cor_off, *unc_off;
-  const int32_t *items;  // window ids of this launch (one segment of the size-sorted list), largest first
+  const int32_t *items;  // window ids of this launch (one segment of the sorted list), largest first
   int32_t n_items;
   int32_t match, mismatch, open, ext;
   uint32_t *scratch;     // grid x warp_words x 32 words
   uint32_t warp_words;   // scratch words per thread (layout of the segment's maxima)
   int32_t *work_counter;
+  // phase 1 -> phase 2
+  uint16_t *p1_nodes;    // P1 node list of window w at [ref_off[w] + cor_off[w]], n1[w] entries
+  int32_t *n1;
+  int32_t *key2;         // phase-2 sort bin of the window
+  int32_t *hist2;        // phase-2 histogram (filled by phase 1)
+  int32_t *seg2_max;     // phase-2 segment maxima: [seg*4 + {0: n1, 1: lu}]
+  // results
   uint8_t *rows_out;
   unsigned long long *rows_cursor;
   int64_t rows_cap;
@@ -114,14 +140,42 @@ enum : uint32_t {
   NF_INITIAL = 1u << 10, // carries position 0 of some source (align_lpo_po2.c:50-53)
   NF_FINAL = 1u << 11,   // carries the last position of some source (:54-56)
   NF_SAMERING = 1u << 12,// on the same align ring as the previous node
-  NF_KEEP = 0x1fffu,     // the bits above + the letter: what fuse writes, what survives prepare()
+  NF_KEEP = 0x1fffu,     // the bits above + the letter: what fuse 1 writes (16-bit node list)
   NF_VIRT = 1u << 13,    // left list starts with the virtual -1 link (:69-75)
   NF_TWO = 1u << 14,     // two real predecessors (latest ref node and latest cor node differ)
   NF_NOPRED = 1u << 15,  // no real predecessor: the left list is the virtual link alone
   NF_PREDC = 1u << 16,   // the single real predecessor is the latest cor-carrying node
   NF_SLOT_SHIFT = 17     // combined nodes (VIRT or TWO): index of their ordinal slot
 };
-enum : uint32_t { REC_NODE = 0, REC_BS = 1, REC_BG = 2, REC_PRED = 3, REC_X2Y = 4, REC_MOVES = 5 };
+
+// ---- phase-2 sort bins (shared with bin_kernel.cuh) -------------------------------------------
+constexpr int kBigTiers = 8;            // windows beyond the "small" limits: one bin per power of two
+constexpr int kSmallMax = 256;          // longest sequence of a small window
+constexpr int kNbMax = kSmallMax / 8;   // 8-row half-bands of a small window: 1..32
+constexpr int kN1q = 128;               // len(P1) / 4 quanta of a small window (len(P1) <= 511)
+constexpr int kSpCodes = 98;            // 0 = ref and cor identical; 1 + 3*min(pos/2, 31) + type otherwise
+constexpr int kSmallBins2 = kNbMax * kN1q * kSpCodes;
+constexpr int kNumBins2 = kBigTiers + kSmallBins2;
+constexpr int kNumSegs2 = kBigTiers + 4;
+
+EL_HD int big_tier(int mx) {            // mx > kSmallMax: 1: <= 512, 2: <= 1024, ...
+  int t = 1;
+  while ((kSmallMax << t) < mx && t < kBigTiers) ++t;
+  return t;
+}
+EL_HD int seg2_of_nb(int nb8) { return kBigTiers + (nb8 > 16 ? 0 : nb8 > 8 ? 1 : nb8 > 4 ? 2 : 3); }
+// largest first: big tiers, then small bins descending in (half-bands of unc, len(P1)/4, spcode)
+EL_HD void bin2_of(int n1, int lu, int spcode, int &bin, int &seg) {
+  if (lu > kSmallMax || n1 >= 4 * kN1q) {
+    const int t = big_tier(n1 > lu ? n1 : lu);
+    bin = seg = kBigTiers - t;
+  } else {
+    const int nb8 = (lu + 7) >> 3;
+    const int small = ((nb8 - 1) * kN1q + (n1 >> 2)) * kSpCodes + spcode;
+    bin = kBigTiers + (kSmallBins2 - 1 - small);
+    seg = seg2_of_nb(nb8);
+  }
+}
 
 // shifts the sign bit of t into the move word (a negative difference = the move was taken)
 EL_HD uint32_t shift_in_sign(uint32_t mv, int t) {
@@ -132,6 +186,179 @@ EL_HD uint32_t shift_in_sign(uint32_t mv, int t) {
 #endif
 }
 
+struct Scoring {
+  const SymbolTables *tab;
+  int match, mismatch, open, ext;
+  // virtual column -1 (align_lpo_po2.c:272-273,290-302) at row `row` (-1 = the corner)
+  EL_HD int virt_S(int row) const { return row < 0 ? 0 : -(open + ext * row); }
+  EL_HD int virt_G(int row) const { return row < 0 ? -open : -(open + ext * row) - ext; }
+};
+
+// The in-place update of one register column by one node (align_lpo_po2.c:322-407) for R rows:
+// S/G hold the predecessor column on entry and the node's column on exit; returns the move bits
+// (cell r: bit 2(15-r)+1 = match, bit 2(15-r) = X-gap when not a match).
+template <int R, bool GENERIC_SUB>
+EL_HD uint32_t update_column(const Scoring &sc, int (&S)[R], int (&G)[R], const uint32_t (&yw)[R / 4], int xl, int diag, int up) {
+  uint32_t mv = 0;
+  const uint32_t x4 = (uint32_t)xl * 0x01010101u;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pS = S[r], pG = G[r];
+    int sub;
+    if (GENERIC_SUB) sub = (int)sc.tab->sub[xl * 32 + ((yw[r >> 2] >> ((r & 3) * 8)) & 31)];
+    else sub = ((x4 ^ yw[r >> 2]) & (0xffu << ((r & 3) * 8))) ? sc.mismatch : sc.match;
+    const int M = diag + sub;
+    const int gap = pG > up ? pG : up;     // ties: Y-gap beats X-gap (:392)
+    const bool isM = M > gap;              // match must beat both (:384)
+    const int s = isM ? M : gap;
+    const int g = s - (isM ? sc.open : sc.ext);
+    mv = shift_in_sign(mv, gap - M);
+    mv = shift_in_sign(mv, up - pG);
+    S[r] = s; G[r] = g;
+    diag = pS; up = g;
+  }
+  if (R < kBand) mv <<= 2 * (kBand - R);   // align an 8-row band like the first half of a 16-row one
+  return mv;
+}
+
+template <int R>
+EL_HD int pick_row(const int (&S)[R], int k) {
+  int s = S[0];
+#pragma unroll
+  for (int r = 1; r < R; ++r) if (k == r) s = S[r];
+  return s;
+}
+
+// scratch access of one lane: word w of the lane at [w*32]
+struct LaneScratch {
+  uint32_t *base;  // warp scratch + lane
+  EL_HD uint32_t &w(uint32_t i) const { return base[(size_t)i * 32]; }
+  EL_HD uint32_t *at(uint32_t i) const { return base + (size_t)i * 32; }
+  EL_HD int code_at(uint32_t off, int i) const { return (w(off + (i >> 2)) >> ((i & 3) * 8)) & 0xff; }
+  // raw letters -> symbol indices, 4 per scratch word
+  EL_HDN void pack_codes(const SymbolTables *tab, const uint8_t *src, int len, uint32_t off) const {
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int i = 0; i < len; ++i) {
+      acc |= (uint32_t)tab->code_lut[src[i]] << ((i & 3) * 8);
+      if ((i & 3) == 3) { w(off + (i >> 2)) = acc; acc = 0; }
+    }
+    if (len & 3) w(off + (len >> 2)) = acc;
+  }
+};
+
+// =============================== phase 1 ========================================================
+template <bool GENERIC_SUB>
+struct Phase1 {
+  LaneScratch scr;
+  Scoring sc;
+  const Layout1 *Lp;  // layout of the current group (shared memory on the device)
+
+  // DP1: linear x linear (lin(ref) columns, lin(cor) rows), one band
+  template <int R>
+  EL_HDN int band(int lr, int ly, int b, bool last) const {
+    const int r0 = b * kBand;
+    uint32_t yw[R / 4];
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) yw[k] = scr.w(Lp->o_cor + (r0 >> 2) + k);
+    int S[R], G[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { S[r] = sc.virt_S(r0 + r); G[r] = sc.virt_G(r0 + r); }
+    int h = sc.virt_S(r0 - 1);
+    uint32_t *p = scr.at(Lp->o_nodes);
+    const uint32_t step = Lp->rec_words * 32;
+    uint32_t xw = 0;
+    int upS_n = 0, upG_n = 0;
+    if (b > 0) { upS_n = (int)p[R1_BS * 32]; upG_n = (int)p[R1_BG * 32]; }
+    for (int j = 0; j < lr; ++j, p += step) {
+      if ((j & 3) == 0) xw = scr.w(Lp->o_ref + (j >> 2));
+      const int xl = xw & 0xff; xw >>= 8;
+      int upS, upG;
+      if (b == 0) { upS = -(sc.open + sc.ext * j); upG = upS - sc.ext; }   // row -1 (:275-286)
+      else {
+        upS = upS_n; upG = upG_n;
+        const uint32_t *pn = j + 1 < lr ? p + step : p;
+        upS_n = (int)pn[R1_BS * 32]; upG_n = (int)pn[R1_BG * 32];
+      }
+      const uint32_t mv = update_column<R, GENERIC_SUB>(sc, S, G, yw, xl, h, upG);
+      h = upS;
+      if (!last) { p[R1_BS * 32] = (uint32_t)S[R - 1]; p[R1_BG * 32] = (uint32_t)G[R - 1]; }
+      p[(R1_MOVES + b) * 32] = mv;
+    }
+    return last ? pick_row<R>(S, ly - 1 - r0) : 0;
+  }
+
+  // bands of 16 rows; the last one has 8 when at most 8 rows remain.  P0 = lin(ref)
+  // (lpo.c:11-32): only node lr-1 is FINAL, so the best score is the last cell.
+  EL_HDN int dp(int lr, int ly) const {
+    const int nb = (ly + kBand - 1) / kBand;
+    for (int b = 0; b < nb - 1; ++b) band<kBand>(lr, ly, b, false);
+    return (ly - (nb - 1) * kBand <= 8) ? band<8>(lr, ly, nb - 1, true) : band<kBand>(lr, ly, nb - 1, true);
+  }
+
+  // traceback (align_lpo_po2.c:108-168): fills the x2y field of every record
+  EL_HDN void traceback(int lr, int ly) const {
+    const uint32_t step = Lp->rec_words * 32;
+    {
+      uint32_t *p = scr.at(Lp->o_nodes) + R1_X2Y * 32;
+      for (int j = 0; j < lr; ++j, p += step) *p = 0xffffffffu;
+    }
+    int j = lr - 1, r = ly - 1;
+    while (j >= 0 && r >= 0) {
+      uint32_t *p = scr.at(Lp->o_nodes) + (size_t)j * step;
+      const uint32_t kind = (p[(R1_MOVES + (r >> 4)) * 32] >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
+      if (kind & 2u) p[R1_X2Y * 32] = (uint32_t)r;
+      if (kind) --j;
+      if (kind != 1u) --r;
+    }
+  }
+
+  // fuse 1 (lpo.c:413-463,602-656 for two linear sequences): P1's node list, 16 bits per node,
+  // to out[]; returns len(P1) and the phase-2 sort code of the window: 0 when ref and cor are
+  // identical (P1 is linear), else 1 + 3*min(pos/2, 31) + type of the first node that does not
+  // carry both letters (type 0: ref only, 1: cor only followed by its ref partner = a
+  // substitution, 2: cor only = an insertion).
+  EL_HDN int fuse(int lr, int lc, uint16_t *out, int &spcode) const {
+    int n = 0, iy = 0, sp = -1, sptype = 0;
+    const uint32_t step = Lp->rec_words * 32;
+    const uint32_t *px = scr.at(Lp->o_nodes) + R1_X2Y * 32;
+    auto cor_only = [&](int n_, int iy_) {
+      out[n_] = (uint16_t)((uint32_t)scr.code_at(Lp->o_cor, iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
+    };
+    for (int ix = 0; ix < lr; ++ix, px += step) {
+      const int q = (int)*px;
+      const int xl = scr.code_at(Lp->o_ref, ix);
+      if (q >= 0)
+        while (iy < q) { if (sp < 0) { sp = n; sptype = 2; } cor_only(n, iy); ++n; ++iy; }
+      uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
+      if (q >= 0 && iy < lc) {
+        const int yl = scr.code_at(Lp->o_cor, iy);
+        const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
+        if (yl == xl) fl |= yf;  // identical letters share the node
+        else {                   // own node just before x, same ring
+          if (sp < 0) { sp = n; sptype = 1; }
+          out[n] = (uint16_t)((uint32_t)yl | yf); ++n; fl |= NF_SAMERING;
+        }
+        ++iy;
+      } else if (sp < 0) { sp = n; sptype = 0; }
+      out[n] = (uint16_t)((uint32_t)xl | fl);
+      ++n;
+    }
+    while (iy < lc) { if (sp < 0) { sp = n; sptype = 2; } cor_only(n, iy); ++n; ++iy; }
+    spcode = sp < 0 ? 0 : 1 + 3 * ((sp >> 1) < 31 ? (sp >> 1) : 31) + sptype;
+    return n;
+  }
+
+  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode) const {
+    scr.pack_codes(sc.tab, ref, lr, Lp->o_ref);
+    scr.pack_codes(sc.tab, cor, lc, Lp->o_cor);
+    s1 = dp(lr, lc);
+    traceback(lr, lc);
+    return fuse(lr, lc, p1_out, spcode);
+  }
+};
+
+// =============================== phase 2 ========================================================
 constexpr int kSlotWords = (2 * kBand + 1) * 32;  // one frontier set of a warp in shared memory: S[R], G[R], h, lane-interleaved
 
 // Uncommon nodes of DP2 (first nodes, nodes around a ref/cor difference): the left list is
@@ -200,115 +427,26 @@ __host__ __device__ __noinline__ inline uint32_t arrange_sets(uint32_t *sa, uint
 }
 
 template <bool GENERIC_SUB>
-struct WindowCtx {
-  uint32_t *scr;          // this warp's scratch, indexed [word*32 + lane]
-  uint32_t *bset;         // two frontier-set slots of kSlotWords words, + lane (shared memory on the device)
-  const SymbolTables *tab;
-  const ClassLayout *Lp;  // scratch layout of the current 32-window group (shared memory on the device)
-  int lane;
-  int match, mismatch, open, ext;
+struct Phase2 {
+  LaneScratch scr;
+  uint32_t *bset;     // two frontier-set slots of kSlotWords words, + lane (shared memory on the device)
+  Scoring sc;
+  const Layout2 *Lp;  // layout of the current group (shared memory on the device)
 
-  EL_HD uint32_t &sw(uint32_t w) const { return scr[(size_t)w * 32 + lane]; }
-  EL_HD uint32_t *rec(uint32_t j) const { return scr + ((size_t)(Lp->o_nodes + j * Lp->rec_words) * 32 + lane); }  // field f at [f*32]
-  EL_HD int code_at(uint32_t off, int i) const { return (sw(off + (i >> 2)) >> ((i & 3) * 8)) & 0xff; }
+  EL_HD uint32_t *rec(uint32_t j) const { return scr.at(Lp->o_nodes + j * Lp->rec_words); }  // field f at [f*32]
 
-  // K1: raw letters -> symbol indices, 4 per scratch word
-  EL_HDN void pack_codes(const uint8_t *src, int len, uint32_t off) const {
-    uint32_t w = 0;
-    for (int i = 0; i < len; ++i) {
-      w |= (uint32_t)tab->code_lut[src[i]] << ((i & 3) * 8);
-      if ((i & 3) == 3) { sw(off + (i >> 2)) = w; w = 0; }
-    }
-    if (len & 3) sw(off + (len >> 2)) = w;
-  }
-
-  // virtual column -1 (align_lpo_po2.c:272-273,290-302) at row `row` (-1 = the corner)
-  EL_HD int virt_S(int row) const { return row < 0 ? 0 : -(open + ext * row); }
-  EL_HD int virt_G(int row) const { return row < 0 ? -open : -(open + ext * row) - ext; }
-
-  // The in-place update of one register column by one node (align_lpo_po2.c:322-407) for R rows:
-  // S/G hold the predecessor column on entry and the node's column on exit; returns the move bits.
-  template <int R>
-  EL_HD uint32_t update_column(int (&S)[R], int (&G)[R], const uint32_t (&yw)[R / 4], int xl, int diag, int up) const {
-    uint32_t mv = 0;
-    const uint32_t x4 = (uint32_t)xl * 0x01010101u;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int pS = S[r], pG = G[r];
-      int sub;
-      if (GENERIC_SUB) sub = (int)tab->sub[xl * 32 + ((yw[r >> 2] >> ((r & 3) * 8)) & 31)];
-      else sub = ((x4 ^ yw[r >> 2]) & (0xffu << ((r & 3) * 8))) ? mismatch : match;
-      const int M = diag + sub;
-      const int gap = pG > up ? pG : up;     // ties: Y-gap beats X-gap (:392)
-      const bool isM = M > gap;              // match must beat both (:384)
-      const int s = isM ? M : gap;
-      const int g = s - (isM ? open : ext);
-      mv = shift_in_sign(mv, gap - M);       // bit 1 of the cell: match
-      mv = shift_in_sign(mv, up - pG);       // bit 0 of the cell: X-gap (when not a match)
-      S[r] = s; G[r] = g;
-      diag = pS; up = g;
-    }
-    if (R < kBand) mv <<= 2 * (kBand - R);   // align an 8-row band like the first half of a 16-row one
-    return mv;
-  }
-
-  template <int R>
-  EL_HD void load_y(uint32_t (&yw)[R / 4], uint32_t o_y, int r0) const {
-#pragma unroll
-    for (int k = 0; k < R / 4; ++k) yw[k] = sw(o_y + (r0 >> 2) + k);
-  }
-
-  template <int R>
-  static EL_HD int pick_row(const int (&S)[R], int k) {
-    int s = S[0];
-#pragma unroll
-    for (int r = 1; r < R; ++r) if (k == r) s = S[r];
-    return s;
-  }
-
-  // ---- DP1: linear x linear (lin(ref) columns, lin(cor) rows), one band ----
-  template <int R>
-  EL_HDN int band_linear(int lr, uint32_t o_y, int ly, int b, bool last) const {
-    const int r0 = b * kBand;
-    uint32_t yw[R / 4];
-    load_y<R>(yw, o_y, r0);
-    int S[R], G[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { S[r] = virt_S(r0 + r); G[r] = virt_G(r0 + r); }
-    int h = virt_S(r0 - 1);
-    uint32_t *p = rec(0);
-    const uint32_t step = Lp->rec_words * 32;
-    uint32_t xw = 0;
-    int upS_n = 0, upG_n = 0;
-    if (b > 0) { upS_n = (int)p[REC_BS * 32]; upG_n = (int)p[REC_BG * 32]; }
-    for (int j = 0; j < lr; ++j, p += step) {
-      if ((j & 3) == 0) xw = sw(Lp->o_ref + (j >> 2));
-      const int xl = xw & 0xff; xw >>= 8;
-      int upS, upG;
-      if (b == 0) { upS = -(open + ext * j); upG = upS - ext; }   // row -1 (:275-286)
-      else {
-        upS = upS_n; upG = upG_n;
-        const uint32_t *pn = j + 1 < lr ? p + step : p;
-        upS_n = (int)pn[REC_BS * 32]; upG_n = (int)pn[REC_BG * 32];
-      }
-      const uint32_t mv = update_column<R>(S, G, yw, xl, h, upG);
-      h = upS;
-      if (!last) { p[REC_BS * 32] = (uint32_t)S[R - 1]; p[REC_BG * 32] = (uint32_t)G[R - 1]; }
-      p[(REC_MOVES + b) * 32] = mv;
-    }
-    return last ? pick_row<R>(S, ly - 1 - r0) : 0;
-  }
-
-  // ---- node preparation for DP2 (align_lpo_po2.c:46-79 + row -1, :272-286) ----
-  // Derives every node's left list from the two frontiers, stores its shape in the node
-  // record (NF_VIRT / NF_TWO / NF_NOPRED / NF_PREDC / slot), its real predecessors (for the
-  // traceback) and row -1 of the DP as the first boundary row.
-  EL_HDN void prepare(int nx) const {
+  // ---- node preparation (align_lpo_po2.c:46-79 + row -1, :272-286) ----
+  // Reads P1's 16-bit node list, derives every node's left list from the two frontiers and
+  // stores: the node with its shape (NF_VIRT / NF_TWO / NF_NOPRED / NF_PREDC / slot), its real
+  // predecessors (for the traceback) and row -1 of the DP as the first boundary row.
+  EL_HDN void prepare(const uint16_t *nodes, int nx) const {
     int lastR = -1, lastC = -1, gR = 0, gC = 0, nslot = 0;
     uint32_t *p = rec(0);
     const uint32_t step = Lp->rec_words * 32;
+    const int open = sc.open, ext = sc.ext;
+#pragma unroll 1
     for (int j = 0; j < nx; ++j, p += step) {
-      uint32_t ra = p[REC_NODE * 32] & NF_KEEP;
+      uint32_t ra = nodes[j];
       const bool hasR = ra & NF_REF, hasC = ra & NF_COR;
       int pA = -1, pB = -1, gA = 0, gB = 0;
       if (hasR && lastR >= 0) { pA = lastR; gA = gR; }
@@ -326,10 +464,11 @@ struct WindowCtx {
         if (virt || pB >= 0) ra |= (uint32_t)(nslot++) << NF_SLOT_SHIFT;
       }
       const int bG = bS - ext;
-      p[REC_NODE * 32] = ra;
-      p[REC_PRED * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
-      p[REC_BS * 32] = (uint32_t)bS;
-      p[REC_BG * 32] = (uint32_t)bG;
+      p[R2_NODE * 32] = ra;
+      p[R2_PRED * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
+      p[R2_BS * 32] = (uint32_t)bS;
+      p[R2_BG * 32] = (uint32_t)bG;
+      p[R2_X2Y * 32] = 0xffffffffu;
       if (hasR) { lastR = j; gR = bG; }
       if (hasC) { lastC = j; gC = bG; }
     }
@@ -337,10 +476,11 @@ struct WindowCtx {
 
   // ---- DP2: P1 columns x lin(unc) rows, one band (align_lpo_po2.c:269-433) ----
   template <int R>
-  EL_HDN void band_po(int nx, uint32_t o_y, int ly, int b, bool last, int &best, int &best_j) const {
+  EL_HDN void band(int nx, int ly, int b, bool last, int &best, int &best_j) const {
     const int r0 = b * kBand;
     uint32_t yw[R / 4];
-    load_y<R>(yw, o_y, r0);
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) yw[k] = scr.w(Lp->o_unc + (r0 >> 2) + k);
     int S[R], G[R], h = 0;   // set A
 #pragma unroll
     for (int r = 0; r < R; ++r) S[r] = G[r] = 0;
@@ -348,13 +488,13 @@ struct WindowCtx {
     int bsel = 0;              // which shared-memory slot holds set B
     uint32_t *p = rec(0);
     const uint32_t step = Lp->rec_words * 32;
-    uint32_t ra = p[REC_NODE * 32];
-    int upS = (int)p[REC_BS * 32], upG = (int)p[REC_BG * 32];
+    uint32_t ra = p[R2_NODE * 32];
+    int upS = (int)p[R2_BS * 32], upG = (int)p[R2_BG * 32];
     for (int j = 0; j < nx; ++j, p += step) {
       // prefetch the next node while this one is computed
       const uint32_t *pn = j + 1 < nx ? p + step : p;
-      const uint32_t ra_n = pn[REC_NODE * 32];
-      const int upS_n = (int)pn[REC_BS * 32], upG_n = (int)pn[REC_BG * 32];
+      const uint32_t ra_n = pn[R2_NODE * 32];
+      const int upS_n = (int)pn[R2_BS * 32], upG_n = (int)pn[R2_BG * 32];
 
       const int m = (ra >> 8) & 3;
       // -- uncommon: bring the source column into set A, keep the frontier this node leaves behind in B.
@@ -365,8 +505,8 @@ struct WindowCtx {
         for (int r = 0; r < R; ++r) { sa[r * 32] = (uint32_t)S[r]; sa[(R + r) * 32] = (uint32_t)G[r]; }
         sa[2 * R * 32] = (uint32_t)h;
         uint32_t *po = nullptr;
-        if (ra & (NF_VIRT | NF_TWO)) po = &sw(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
-        const uint32_t st = arrange_sets(sa, sb, R, r0, ra, kindA, kindB, open, ext, po);
+        if (ra & (NF_VIRT | NF_TWO)) po = scr.at(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
+        const uint32_t st = arrange_sets(sa, sb, R, r0, ra, kindA, kindB, sc.open, sc.ext, po);
         kindA = st & 3; kindB = (st >> 2) & 3;
         if (st & 16u) { bsel = 1 - bsel; sa = sb; }
 #pragma unroll
@@ -374,10 +514,10 @@ struct WindowCtx {
         h = (int)sa[2 * R * 32];
       }
       // -- hot: in-place update of set A with node j
-      const uint32_t mv = update_column<R>(S, G, yw, ra & 0xff, h, upG);
+      const uint32_t mv = update_column<R, GENERIC_SUB>(sc, S, G, yw, ra & 0xff, h, upG);
       h = upS;
-      if (!last) { p[REC_BS * 32] = (uint32_t)S[R - 1]; p[REC_BG * 32] = (uint32_t)G[R - 1]; }
-      p[(REC_MOVES + b) * 32] = mv;
+      if (!last) { p[R2_BS * 32] = (uint32_t)S[R - 1]; p[R2_BG * 32] = (uint32_t)G[R - 1]; }
+      p[(R2_MOVES + b) * 32] = mv;
       if (last && (ra & NF_FINAL)) {
         const int s = pick_row<R>(S, ly - 1 - r0);
         if (s > best) { best = s; best_j = j; }  // ties keep the smaller j (:410-417)
@@ -386,95 +526,48 @@ struct WindowCtx {
     }
   }
 
-  // bands of 16 rows; the last one has 8 when at most 8 rows remain
-  EL_HDN int dp_linear(int lr, uint32_t o_y, int ly) const {
-    const int nb = (ly + kBand - 1) / kBand;
-    for (int b = 0; b < nb - 1; ++b) band_linear<kBand>(lr, o_y, ly, b, false);
-    return (ly - (nb - 1) * kBand <= 8) ? band_linear<8>(lr, o_y, ly, nb - 1, true) : band_linear<kBand>(lr, o_y, ly, nb - 1, true);
-  }
-  EL_HDN int dp_po(int nx, uint32_t o_y, int ly, int &best_j) const {
-    prepare(nx);
+  EL_HDN int dp(int nx, int ly, int &best_j) const {
     const int nb = (ly + kBand - 1) / kBand;
     int best = -999999;
     best_j = -1;
-    for (int b = 0; b < nb - 1; ++b) band_po<kBand>(nx, o_y, ly, b, false, best, best_j);
-    if (ly - (nb - 1) * kBand <= 8) band_po<8>(nx, o_y, ly, nb - 1, true, best, best_j);
-    else band_po<kBand>(nx, o_y, ly, nb - 1, true, best, best_j);
+    for (int b = 0; b < nb - 1; ++b) band<kBand>(nx, ly, b, false, best, best_j);
+    if (ly - (nb - 1) * kBand <= 8) band<8>(nx, ly, nb - 1, true, best, best_j);
+    else band<kBand>(nx, ly, nb - 1, true, best, best_j);
     return best;
   }
 
-  // ---- traceback (align_lpo_po2.c:108-168): fills the x2y field of every node record ----
-  template <bool LINEAR>
-  EL_HDN void traceback(int nx, int ly, int best_j) const {
-    {
-      uint32_t *p = rec(0) + REC_X2Y * 32;
-      const uint32_t step = Lp->rec_words * 32;
-      for (int j = 0; j < nx; ++j, p += step) *p = 0xffffffffu;
-    }
+  // ---- traceback (align_lpo_po2.c:108-168): fills the x2y field of the node records ----
+  EL_HDN void traceback(int ly, int best_j) const {
     int j = best_j, r = ly - 1;
     while (j >= 0 && r >= 0) {
-      const int b = r >> 4, sh = 2 * (15 - (r & 15));
+      const int b = r >> 4;
       uint32_t *p = rec((uint32_t)j);
-      const uint32_t kind = (p[(REC_MOVES + b) * 32] >> sh) & 3u;   // bit 1 match, bit 0 X-gap
-      if (kind & 2u) p[REC_X2Y * 32] = (uint32_t)r;
+      const uint32_t kind = (p[(R2_MOVES + b) * 32] >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
+      if (kind & 2u) p[R2_X2Y * 32] = (uint32_t)r;
       if (kind) {  // match or X-gap: step to a predecessor of j
-        if (LINEAR) --j;
-        else {
-          const uint32_t ra = p[REC_NODE * 32];
-          int ord = 0;
-          if (ra & (NF_VIRT | NF_TWO)) {
-            const uint32_t *po = &sw(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
-            ord = (int)((((kind & 2u) ? po[0] : po[32]) >> (2 * (r & 15))) & 3u);
-          }
-          const uint32_t pr = p[REC_PRED * 32];
-          const int pA = (pr & 0xffffu) == 0xffffu ? -1 : (int)(pr & 0xffffu), pB = (pr >> 16) == 0xffffu ? -1 : (int)(pr >> 16);
-          if (ra & NF_VIRT) j = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
-          else j = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
+        const uint32_t ra = p[R2_NODE * 32];
+        int ord = 0;
+        if (ra & (NF_VIRT | NF_TWO)) {
+          const uint32_t *po = scr.at(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
+          ord = (int)((((kind & 2u) ? po[0] : po[32]) >> (2 * (r & 15))) & 3u);
         }
+        const uint32_t pr = p[R2_PRED * 32];
+        const int pA = (pr & 0xffffu) == 0xffffu ? -1 : (int)(pr & 0xffffu), pB = (pr >> 16) == 0xffffu ? -1 : (int)(pr >> 16);
+        if (ra & NF_VIRT) j = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
+        else j = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
       }
       if (kind != 1u) --r;  // match or Y-gap: step up
     }
   }
 
-  EL_HD int x2y(int j) const { return (int)rec((uint32_t)j)[REC_X2Y * 32]; }
-  EL_HD uint32_t node(int j) const { return rec((uint32_t)j)[REC_NODE * 32]; }
-  EL_HD void set_node(int j, uint32_t v) const { rec((uint32_t)j)[REC_NODE * 32] = v; }
-
-  // ---- fuse 1 (lpo.c:413-463,602-656 for two linear sequences): build P1's node records ----
-  // In place: record n >= ix is written after x2y of record ix has been read.
-  EL_HDN int fuse1(int lr, int lc) const {
-    int n = 0, iy = 0;
-    for (int ix = 0; ix < lr; ++ix) {
-      const int q = x2y(ix);
-      const int xl = code_at(Lp->o_ref, ix);
-      if (q >= 0)
-        while (iy < q) {
-          set_node(n, (uint32_t)code_at(Lp->o_cor, iy) | NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u));
-          ++n; ++iy;
-        }
-      uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
-      if (q >= 0 && iy < lc) {
-        const int yl = code_at(Lp->o_cor, iy);
-        const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
-        if (yl == xl) fl |= yf;  // identical letters share the node
-        else { set_node(n, (uint32_t)yl | yf); ++n; fl |= NF_SAMERING; }  // own node just before x, same ring
-        ++iy;
-      }
-      set_node(n, (uint32_t)xl | fl);
-      ++n;
-    }
-    while (iy < lc) {
-      set_node(n, (uint32_t)code_at(Lp->o_cor, iy) | NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u));
-      ++n; ++iy;
-    }
-    return n;
-  }
+  EL_HD int x2y(int j) const { return (int)rec((uint32_t)j)[R2_X2Y * 32]; }
+  EL_HD uint32_t node(int j) const { return rec((uint32_t)j)[R2_NODE * 32]; }
 
   // ---- fuse 2 + MSA emit (lpo.c:413-463 with rings, lpo_format.c:346-371) ----
   // Walks the final node order without materialising P2; a column closes whenever the
   // align ring changes.  Returns nring; rows go to o_rows (3 x row_words words).
-  EL_HDN int fuse2_emit(int n1, int lu) const {
-    const uint8_t *sym = tab->sym;
+  EL_HDN int fuse_emit(int n1, int lu) const {
+    const uint8_t *sym = sc.tab->sym;
     int iy = 0, col = -1, prev_key = -1, rs = 0;
     uint32_t c0 = '.', c1 = '.', c2 = '.';
     uint32_t w0 = 0, w1 = 0, w2 = 0;
@@ -483,7 +576,7 @@ struct WindowCtx {
       if (col >= 0) {
         const int sh = (col & 3) * 8;
         w0 |= c0 << sh; w1 |= c1 << sh; w2 |= c2 << sh;
-        if ((col & 3) == 3) { sw(r0 + (col >> 2)) = w0; sw(r1 + (col >> 2)) = w1; sw(r2 + (col >> 2)) = w2; w0 = w1 = w2 = 0; }
+        if ((col & 3) == 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; w0 = w1 = w2 = 0; }
       }
     };
     auto emit = [&](int key, uint32_t letter, uint32_t srcmask) {
@@ -499,99 +592,145 @@ struct WindowCtx {
       // scan x's ring from ix on: unaligned y letters go before the first aligned member
       for (int ir = ix;;) {
         const int q = x2y(ir);
-        if (q >= 0) { while (iy < q) { emit(n1 + iy, code_at(Lp->o_unc, iy), 4u); ++iy; } break; }
+        if (q >= 0) { while (iy < q) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; } break; }
         ++ir;
         if (ir >= n1 || !(node(ir) & NF_SAMERING)) break;
       }
       uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
       if (x2y(ix) >= 0 && iy < lu) {
-        const uint32_t yl = code_at(Lp->o_unc, iy);
+        const uint32_t yl = scr.code_at(Lp->o_unc, iy);
         if (yl == (ra & 0xffu)) mask |= 4u;
         else emit(rs, yl, 4u);
         ++iy;
       }
       emit(rs, ra & 0xffu, mask);
     }
-    while (iy < lu) { emit(n1 + iy, code_at(Lp->o_unc, iy), 4u); ++iy; }
+    while (iy < lu) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
     flush();
-    if ((col & 3) != 3) { sw(r0 + (col >> 2)) = w0; sw(r1 + (col >> 2)) = w1; sw(r2 + (col >> 2)) = w2; }
+    if ((col & 3) != 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; }
     return col + 1;
   }
 
-  // ---- the whole per-window pipeline (main.c:265-274 + buildup_lpo.c:562-589) ----
-  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, const uint8_t *unc, int lu,
-                        int &s1, int &s2, int &n1) const {
-    pack_codes(ref, lr, Lp->o_ref);
-    pack_codes(cor, lc, Lp->o_cor);
-    pack_codes(unc, lu, Lp->o_unc);
-    s1 = dp_linear(lr, Lp->o_cor, lc);       // P0 = lin(ref) (lpo.c:11-32): only node lr-1 is FINAL
-    traceback<true>(lr, lc, lr - 1);
-    n1 = fuse1(lr, lc);
+  EL_HDN int run_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2) const {
+    scr.pack_codes(sc.tab, unc, lu, Lp->o_unc);
+    prepare(p1, n1);
     int bj;
-    s2 = dp_po(n1, Lp->o_unc, lu, bj);
-    traceback<false>(n1, lu, bj);
-    return fuse2_emit(n1, lu);
+    s2 = dp(n1, lu, bj);
+    traceback(lu, bj);
+    return fuse_emit(n1, lu);
   }
 };
 
-// Persistent kernel, one warp per CTA (up to 32 CTAs per SM; registers bound residency):
-// each warp repeatedly takes 32 consecutive items of the size-sorted work list; lane l owns
-// item base+l.  Shared memory holds the symbol tables (the 2 KB substitution table only for
-// non-uniform matrices), the group's scratch layout and two frontier-set slots (8.25 KB).
-#ifndef EL_MIN_WARPS_PER_SM
-#define EL_MIN_WARPS_PER_SM 24  // register cap 80: measured best trade between occupancy and spills
+// ================================ kernels =======================================================
+// Persistent kernels, one warp per CTA (up to 32 CTAs per SM; registers bound residency): each
+// warp repeatedly takes 32 consecutive items of the sorted work list; lane l owns item base+l.
+// Shared memory holds the symbol tables (the 2 KB substitution table only for non-uniform
+// matrices), the group's scratch layout and, in phase 2, two frontier-set slots (8.25 KB).
+#ifndef EL_MIN_WARPS_PH1
+#define EL_MIN_WARPS_PH1 24
 #endif
+#ifndef EL_MIN_WARPS_PH2
+#define EL_MIN_WARPS_PH2 24
+#endif
+
 template <bool GENERIC_SUB>
-__global__ void __launch_bounds__(32, EL_MIN_WARPS_PER_SM) poa_tpw_kernel(PoaArgs a, const SymbolTables *g_tab) {
+__device__ __forceinline__ const SymbolTables *stage_tables(uint32_t *smem, const SymbolTables *g_tab) {
   constexpr int kTabWords = (GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4;
-  __shared__ uint32_t smem[kTabWords];
-  __shared__ ClassLayout s_layout;
-  __shared__ uint32_t s_bset[2 * kSlotWords];
-  SymbolTables *tab = reinterpret_cast<SymbolTables *>(smem);
-  {
-    const uint32_t *s = reinterpret_cast<const uint32_t *>(g_tab);
-    for (int i = threadIdx.x; i < kTabWords; i += 32) smem[i] = s[i];
-  }
+  const uint32_t *s = reinterpret_cast<const uint32_t *>(g_tab);
+  for (int i = threadIdx.x; i < kTabWords; i += 32) smem[i] = s[i];
   __syncwarp();
+  return reinterpret_cast<const SymbolTables *>(smem);
+}
+
+template <bool GENERIC_SUB>
+__global__ void __launch_bounds__(32, EL_MIN_WARPS_PH1) poa_dp1_kernel(PoaArgs a, const SymbolTables *g_tab) {
+  __shared__ uint32_t s_tab[(GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4];
+  __shared__ Layout1 s_layout;
   const int lane = threadIdx.x;
-  const size_t warp_slot = blockIdx.x;
-
-  WindowCtx<GENERIC_SUB> c;
-  c.scr = a.scratch + warp_slot * (size_t)a.warp_words * 32;
-  c.tab = tab;
+  Phase1<GENERIC_SUB> c;
+  c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
+  c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
+  c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
   c.Lp = &s_layout;
-  c.bset = s_bset + threadIdx.x;
-  c.lane = lane;
-  c.match = a.match; c.mismatch = a.mismatch; c.open = a.open; c.ext = a.ext;
-
   for (;;) {
     int base = 0;
     if (lane == 0) base = atomicAdd(a.work_counter, 32);
     base = __shfl_sync(EL_WARP_FULL, base, 0);
     if (base >= a.n_items) break;
     const bool active = base + lane < a.n_items;
-    int nring = 0, w = -1, lr = 0, lc = 0, lu = 0;
-    int64_t ro = 0, co = 0, uo = 0;
+    int w = -1, lr = 0, lc = 0;
+    int64_t ro = 0, co = 0;
     if (active) {
       w = a.items[base + lane];
-      ro = a.ref_off[w]; co = a.cor_off[w]; uo = a.unc_off[w];
-      lr = (int)(a.ref_off[w + 1] - ro); lc = (int)(a.cor_off[w + 1] - co); lu = (int)(a.unc_off[w + 1] - uo);
+      ro = a.ref_off[w]; co = a.cor_off[w];
+      lr = (int)(a.ref_off[w + 1] - ro); lc = (int)(a.cor_off[w + 1] - co);
     }
-    // the group's own scratch layout: tight, so that its footprint stays in L1/L2
-    {
-      const int mr = __reduce_max_sync(EL_WARP_FULL, lr), mc = __reduce_max_sync(EL_WARP_FULL, lc), mu = __reduce_max_sync(EL_WARP_FULL, lu);
+    {  // the group's own scratch layout: tight, so that its footprint stays in L1/L2
+      const int mr = __reduce_max_sync(EL_WARP_FULL, lr), mc = __reduce_max_sync(EL_WARP_FULL, lc);
       __syncwarp();
-      if (lane == 0) make_layout(s_layout, mr, mc, mu);
+      if (lane == 0) make_layout1(s_layout, mr, mc);
       __syncwarp();
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     if (active) {
-      int s1, s2, n1;
-      nring = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.unc + uo, lu, s1, s2, n1);
-      a.nring[w] = nring;
+      int s1, spcode;
+      const int n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + (ro + co), s1, spcode);
+      const int lu = (int)(a.unc_off[w + 1] - a.unc_off[w]);
+      int bin, seg;
+      bin2_of(n1, lu, spcode, bin, seg);
+      a.n1[w] = n1;
+      a.key2[w] = bin;
       if (a.score1) a.score1[w] = s1;
+      atomicAdd(&a.hist2[bin], 1);
+      if (n1 > a.seg2_max[seg * 4]) atomicMax(&a.seg2_max[seg * 4], n1);
+      if (lu > a.seg2_max[seg * 4 + 1]) atomicMax(&a.seg2_max[seg * 4 + 1], lu);
+    }
+    __syncwarp();
+  }
+}
+
+template <bool GENERIC_SUB>
+__global__ void __launch_bounds__(32, EL_MIN_WARPS_PH2) poa_dp2_kernel(PoaArgs a, const SymbolTables *g_tab) {
+  __shared__ uint32_t s_tab[(GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4];
+  __shared__ Layout2 s_layout;
+  __shared__ uint32_t s_bset[2 * kSlotWords];
+  const int lane = threadIdx.x;
+  Phase2<GENERIC_SUB> c;
+  c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
+  c.bset = s_bset + lane;
+  c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
+  c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
+  c.Lp = &s_layout;
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(a.work_counter, 32);
+    base = __shfl_sync(EL_WARP_FULL, base, 0);
+    if (base >= a.n_items) break;
+    const bool active = base + lane < a.n_items;
+    int nring = 0, w = -1, n1 = 0, lu = 0;
+    int64_t ro = 0, co = 0, uo = 0;
+    if (active) {
+      w = a.items[base + lane];
+      ro = a.ref_off[w]; co = a.cor_off[w]; uo = a.unc_off[w];
+      lu = (int)(a.unc_off[w + 1] - uo);
+      n1 = a.n1[w];
+    }
+    {
+      const int mn = __reduce_max_sync(EL_WARP_FULL, n1), mu = __reduce_max_sync(EL_WARP_FULL, lu);
+      __syncwarp();
+      if (lane == 0) make_layout2(s_layout, mn, mu);
+      __syncwarp();
+    }
+    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
+    if (active) {
+      int s2;
+      nring = c.run_window(a.p1_nodes + (ro + co), n1, a.unc + uo, lu, s2);
+      a.nring[w] = nring;
       if (a.score2) a.score2[w] = s2;
-      if (a.cells) a.cells[w] = (int64_t)lr * lc + (int64_t)n1 * lu;
+      if (a.cells) {
+        const int64_t lr = a.ref_off[w + 1] - ro, lc = a.cor_off[w + 1] - co;
+        a.cells[w] = lr * lc + (int64_t)n1 * lu;
+      }
     }
     __syncwarp();
     // output allocation: warp prefix sum of 3*stride, one atomic per warp
@@ -615,7 +754,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PER_SM) poa_tpw_kernel(PoaArg
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.rows_out + off);
         const int sw4 = stride >> 2;
         for (int s = 0; s < 3; ++s)
-          for (int k = 0; k < sw4; ++k) dst[s * sw4 + k] = c.sw(s_layout.o_rows + s * s_layout.row_words + k);
+          for (int k = 0; k < sw4; ++k) dst[s * sw4 + k] = c.scr.w(s_layout.o_rows + s * s_layout.row_words + k);
       }
     }
     __syncwarp();

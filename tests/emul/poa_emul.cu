@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY -- runs the per-window device code (WindowCtx::run_window in
+// TEST INFRASTRUCTURE ONLY -- runs the per-window device code (Phase1 / Phase2 ::run_window in
 // elector_b200/csrc/poa_kernel.cuh, compiled as host code) on the CPU, so that the
 // kernel's algorithmic restructuring (8-row register bands, two frontier sets, 2-bit
 // moves, fused emit) can be checked against the oracle in the GPU-less container.
@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../elector_b200/csrc/host_setup.hpp"
+#include "../../elector_b200/csrc/bin_kernel.cuh"
 
 using namespace elector;
 
@@ -19,25 +20,40 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
     const int lr = R.rec[w].len, lc = C.rec[w].len, lu = U.rec[w].len;
-    ClassLayout L;
-    // caps deliberately larger than the window, as in a real size class
-    make_layout(L, lr + (int)(w % 3), lc + (int)(w % 5), lu + (int)(w % 2));
-    std::vector<uint32_t> scratch((size_t)L.total * 32, 0xdeadbeefu);
-    WindowCtx<GS> c;
-    c.scr = scratch.data();
+    const int lane = (int)(w % 32);
+    Scoring s;
+    s.tab = &sc.tab; s.match = sc.match; s.mismatch = sc.mismatch; s.open = sc.open; s.ext = sc.ext;
+    // ---- phase 1 (caps deliberately larger than the window, as in a real group) ----
+    Layout1 L1;
+    make_layout1(L1, lr + (int)(w % 3), lc + (int)(w % 5));
+    std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
+    Phase1<GS> p1;
+    p1.scr.base = scratch1.data() + lane;
+    p1.sc = s;
+    p1.Lp = &L1;
+    std::vector<uint16_t> nodes((size_t)lr + lc, 0xdeadu);
+    int s1, spcode;
+    const int n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc,
+                                 nodes.data(), s1, spcode);
+    int bin, seg;
+    bin2_of(n1, lu, spcode, bin, seg);
+    if (bin < 0 || bin >= kNumBins2 || seg < 0 || seg >= kNumSegs2) { fprintf(stderr, "bad phase-2 bin\n"); return 1; }
+    // ---- phase 2 ----
+    Layout2 L2;
+    make_layout2(L2, n1 + (int)(w % 4), lu + (int)(w % 2));
+    std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
     std::vector<uint32_t> bset((size_t)2 * kSlotWords, 0xdeadbeefu);
-    c.bset = bset.data() + (w % 32);
-    c.tab = &sc.tab;
-    c.Lp = &L;
-    c.lane = (int)(w % 32);
-    c.match = sc.match; c.mismatch = sc.mismatch; c.open = sc.open; c.ext = sc.ext;
-    int s1, s2, n1;
-    const int nring = c.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc,
-                                   (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s1, s2, n1);
+    Phase2<GS> p2;
+    p2.scr.base = scratch2.data() + lane;
+    p2.bset = bset.data() + lane;
+    p2.sc = s;
+    p2.Lp = &L2;
+    int s2;
+    const int nring = p2.run_window(nodes.data(), n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
     const FastaRecord *recs[3] = {&R.rec[w], &C.rec[w], &U.rec[w]};
-    for (int s = 0; s < 3; ++s) {
-      fprintf(pir, ">%s %s\n", recs[s]->name.c_str(), recs[s]->title.c_str());
-      for (int k = 0; k < nring; ++k) fputc((c.sw(L.o_rows + s * L.row_words + (k >> 2)) >> ((k & 3) * 8)) & 0xff, pir);
+    for (int r = 0; r < 3; ++r) {
+      fprintf(pir, ">%s %s\n", recs[r]->name.c_str(), recs[r]->title.c_str());
+      for (int k = 0; k < nring; ++k) fputc((p2.scr.w(L2.o_rows + r * L2.row_words + (k >> 2)) >> ((k & 3) * 8)) & 0xff, pir);
       fputc('\n', pir);
     }
     if (scores) fprintf(scores, "%d %d %d %d\n", s1, s2, n1, nring);
