@@ -212,7 +212,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   CU(cudaStreamSynchronize(st));
   if (htab1->err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", htab1->err_window);
   if (htab1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d longer than %d letters", htab1->err_window, kMaxWindowLen);
-  CU(ctx->d_p1.reserve((size_t)(ctx->h_totals[0] + ctx->h_totals[1]) * sizeof(uint16_t) + 16));
+  CU(ctx->d_p1.reserve((size_t)(ctx->h_totals[0] + ctx->h_totals[1] + 8 * n + 8) * sizeof(uint16_t)));
 
   PoaArgs a;
   memset(&a, 0, sizeof a);

@@ -75,6 +75,7 @@ struct Layout2 {            // phase 2: windows with len(P1) / unc length up to 
   uint32_t rec_words;
   uint32_t o_ord;           // two words per (combined node, band): winning predecessor ordinals
   uint32_t ord_bands;
+  uint32_t o_nt;            // bitmap: node j has a predecessor list other than [j-1]
   uint32_t o_rows;          // 3 MSA rows, bytes packed 4 per word
   uint32_t row_words;
   uint32_t total;
@@ -96,6 +97,7 @@ EL_HD void make_layout2(Layout2 &L, int N1, int LU) {
   L.o_nodes = o; o += (uint32_t)N1 * L.rec_words;
   L.ord_bands = nb;
   L.o_ord = o; o += ((uint32_t)N1 / 2 + 2) * nb * 2;            // combined nodes carry ref AND cor: at most N1/2, + 2 initial ones
+  L.o_nt = o; o += cdiv_u(N1, 32) + 1;
   L.row_words = cdiv_u(N1 + LU, 4);
   L.o_rows = o; o += 3 * L.row_words;
   L.total = o;
@@ -111,7 +113,7 @@ struct PoaArgs {
   uint32_t warp_words;   // scratch words per thread (layout of the segment's maxima)
   int32_t *work_counter;
   // phase 1 -> phase 2
-  uint16_t *p1_nodes;    // P1 node list of window w at [ref_off[w] + cor_off[w]], n1[w] entries
+  uint16_t *p1_nodes;    // P1 node list of window w at [p1_offset(ref_off[w], cor_off[w], w)], n1[w] entries
   int32_t *n1;
   int32_t *key2;         // phase-2 sort bin of the window
   int32_t *hist2;        // phase-2 histogram (filled by phase 1)
@@ -177,6 +179,9 @@ EL_HD void bin2_of(int n1, int lu, int spcode, int &bin, int &seg) {
   }
 }
 
+// P1 node list of window w: 16-bit entries at this index of PoaArgs::p1_nodes (8-byte aligned, lr+lc+5 entries free)
+EL_HD int64_t p1_offset(int64_t ref_off, int64_t cor_off, int64_t w) { return (ref_off + cor_off + 8 * w) & ~(int64_t)3; }
+
 // shifts the sign bit of t into the move word (a negative difference = the move was taken)
 EL_HD uint32_t shift_in_sign(uint32_t mv, int t) {
 #ifdef __CUDA_ARCH__
@@ -235,15 +240,26 @@ struct LaneScratch {
   EL_HD uint32_t &w(uint32_t i) const { return base[(size_t)i * 32]; }
   EL_HD uint32_t *at(uint32_t i) const { return base + (size_t)i * 32; }
   EL_HD int code_at(uint32_t off, int i) const { return (w(off + (i >> 2)) >> ((i & 3) * 8)) & 0xff; }
-  // raw letters -> symbol indices, 4 per scratch word
+  // raw letters -> symbol indices, 4 per scratch word.  Reads the letters as aligned 32-bit
+  // words (only words that hold at least one letter of the sequence), one word ahead.
   EL_HDN void pack_codes(const SymbolTables *tab, const uint8_t *src, int len, uint32_t off) const {
-    uint32_t acc = 0;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const int mis = (int)(a & 3), sh = mis * 8;
+    const int nin = (len + mis + 3) >> 2;   // aligned input words that hold letters
+    const int nout = (len + 3) >> 2;
+    const uint8_t *lut = tab->code_lut;
+    uint32_t cur = wp[0], nxt = nin > 1 ? wp[1] : 0;
 #pragma unroll 1
-    for (int i = 0; i < len; ++i) {
-      acc |= (uint32_t)tab->code_lut[src[i]] << ((i & 3) * 8);
-      if ((i & 3) == 3) { w(off + (i >> 2)) = acc; acc = 0; }
+    for (int k = 0; k < nout; ++k) {
+      const uint32_t nn = k + 2 < nin ? wp[k + 2] : 0;
+      const uint32_t v = sh ? (cur >> sh) | (nxt << (32 - sh)) : cur;
+      uint32_t c = (uint32_t)lut[v & 0xff] | ((uint32_t)lut[(v >> 8) & 0xff] << 8) | ((uint32_t)lut[(v >> 16) & 0xff] << 16) |
+                   ((uint32_t)lut[v >> 24] << 24);
+      if (k == nout - 1 && (len & 3)) c &= 0xffffffffu >> (8 * (4 - (len & 3)));
+      w(off + k) = c;
+      cur = nxt; nxt = nn;
     }
-    if (len & 3) w(off + (len >> 2)) = acc;
   }
 };
 
@@ -296,20 +312,31 @@ struct Phase1 {
     return (ly - (nb - 1) * kBand <= 8) ? band<8>(lr, ly, nb - 1, true) : band<kBand>(lr, ly, nb - 1, true);
   }
 
-  // traceback (align_lpo_po2.c:108-168): fills the x2y field of every record
+  // traceback (align_lpo_po2.c:108-168): fills the x2y field of every record.  The walk reads
+  // one moves word per step; the words of the next three columns of the band are loaded ahead.
   EL_HDN void traceback(int lr, int ly) const {
-    const uint32_t step = Lp->rec_words * 32;
+    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
     {
       uint32_t *p = scr.at(Lp->o_nodes) + R1_X2Y * 32;
       for (int j = 0; j < lr; ++j, p += step) *p = 0xffffffffu;
     }
     int j = lr - 1, r = ly - 1;
     while (j >= 0 && r >= 0) {
-      uint32_t *p = scr.at(Lp->o_nodes) + (size_t)j * step;
-      const uint32_t kind = (p[(R1_MOVES + (r >> 4)) * 32] >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
-      if (kind & 2u) p[R1_X2Y * 32] = (uint32_t)r;
-      if (kind) --j;
-      if (kind != 1u) --r;
+      const int b = r >> 4;
+      uint32_t *p = scr.at(Lp->o_nodes) + (ptrdiff_t)j * step;   // record j
+      const uint32_t *pm = p + (R1_MOVES + b) * 32;
+      uint32_t w0 = pm[0], w1 = j >= 1 ? pm[-step] : 0, w2 = j >= 2 ? pm[-2 * step] : 0, w3 = j >= 3 ? pm[-3 * step] : 0;
+      for (;;) {
+        const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
+        if (kind & 2u) p[R1_X2Y * 32] = (uint32_t)r;
+        if (kind != 1u) --r;
+        if (kind) {
+          --j; p -= step; pm -= step;
+          w0 = w1; w1 = w2; w2 = w3;
+          w3 = j >= 3 ? pm[-3 * step] : 0;
+        }
+        if (j < 0 || r < 0 || (r >> 4) != b) break;
+      }
     }
   }
 
@@ -320,16 +347,28 @@ struct Phase1 {
   // substitution, 2: cor only = an insertion).
   EL_HDN int fuse(int lr, int lc, uint16_t *out, int &spcode) const {
     int n = 0, iy = 0, sp = -1, sptype = 0;
-    const uint32_t step = Lp->rec_words * 32;
+    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
     const uint32_t *px = scr.at(Lp->o_nodes) + R1_X2Y * 32;
-    auto cor_only = [&](int n_, int iy_) {
-      out[n_] = (uint16_t)((uint32_t)scr.code_at(Lp->o_cor, iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
+    uint64_t *out4 = reinterpret_cast<uint64_t *>(out);   // 4 nodes per store (the list is 8-byte aligned)
+    uint64_t acc = 0;
+    auto put = [&](uint32_t v) {
+      acc |= (uint64_t)(v & 0xffffu) << (16 * (n & 3));
+      if ((n & 3) == 3) { out4[n >> 2] = acc; acc = 0; }
+      ++n;
     };
-    for (int ix = 0; ix < lr; ++ix, px += step) {
-      const int q = (int)*px;
-      const int xl = scr.code_at(Lp->o_ref, ix);
+    auto cor_only = [&](int iy_) {
+      put((uint32_t)scr.code_at(Lp->o_cor, iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
+    };
+    int q0 = (int)px[0], q1 = lr > 1 ? (int)px[step] : -1;
+    uint32_t xw = 0;
+    for (int ix = 0; ix < lr; ++ix) {
+      const int q = q0;
+      q0 = q1;
+      q1 = ix + 2 < lr ? (int)px[(ptrdiff_t)(ix + 2) * step] : -1;
+      if ((ix & 3) == 0) xw = scr.w(Lp->o_ref + (ix >> 2));
+      const int xl = xw & 0xff; xw >>= 8;
       if (q >= 0)
-        while (iy < q) { if (sp < 0) { sp = n; sptype = 2; } cor_only(n, iy); ++n; ++iy; }
+        while (iy < q) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
       uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
       if (q >= 0 && iy < lc) {
         const int yl = scr.code_at(Lp->o_cor, iy);
@@ -337,14 +376,14 @@ struct Phase1 {
         if (yl == xl) fl |= yf;  // identical letters share the node
         else {                   // own node just before x, same ring
           if (sp < 0) { sp = n; sptype = 1; }
-          out[n] = (uint16_t)((uint32_t)yl | yf); ++n; fl |= NF_SAMERING;
+          put((uint32_t)yl | yf); fl |= NF_SAMERING;
         }
         ++iy;
       } else if (sp < 0) { sp = n; sptype = 0; }
-      out[n] = (uint16_t)((uint32_t)xl | fl);
-      ++n;
+      put((uint32_t)xl | fl);
     }
-    while (iy < lc) { if (sp < 0) { sp = n; sptype = 2; } cor_only(n, iy); ++n; ++iy; }
+    while (iy < lc) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
+    if (n & 3) out4[n >> 2] = acc;
     spcode = sp < 0 ? 0 : 1 + 3 * ((sp >> 1) < 31 ? (sp >> 1) : 31) + sptype;
     return n;
   }
@@ -444,9 +483,13 @@ struct Phase2 {
     uint32_t *p = rec(0);
     const uint32_t step = Lp->rec_words * 32;
     const int open = sc.open, ext = sc.ext;
+    const uint64_t *n4 = reinterpret_cast<const uint64_t *>(nodes);   // 4 nodes per load, one load ahead
+    uint64_t quad = n4[0], quad_n = nx > 4 ? n4[1] : 0;
+    uint32_t nt = 0;
 #pragma unroll 1
     for (int j = 0; j < nx; ++j, p += step) {
-      uint32_t ra = nodes[j];
+      if (j && (j & 3) == 0) { quad = quad_n; quad_n = j + 4 < nx ? n4[(j >> 2) + 1] : 0; }
+      uint32_t ra = (uint32_t)(quad >> (16 * (j & 3))) & 0xffffu;
       const bool hasR = ra & NF_REF, hasC = ra & NF_COR;
       int pA = -1, pB = -1, gA = 0, gB = 0;
       if (hasR && lastR >= 0) { pA = lastR; gA = gR; }
@@ -469,9 +512,12 @@ struct Phase2 {
       p[R2_BS * 32] = (uint32_t)bS;
       p[R2_BG * 32] = (uint32_t)bG;
       p[R2_X2Y * 32] = 0xffffffffu;
+      if (pA != j - 1 || (ra & (NF_VIRT | NF_TWO))) nt |= 1u << (j & 31);   // the traceback must look this node up
+      if ((j & 31) == 31) { scr.w(Lp->o_nt + (j >> 5)) = nt; nt = 0; }
       if (hasR) { lastR = j; gR = bG; }
       if (hasC) { lastC = j; gC = bG; }
     }
+    if (nx & 31) scr.w(Lp->o_nt + (nx >> 5)) = nt;
   }
 
   // ---- DP2: P1 columns x lin(unc) rows, one band (align_lpo_po2.c:269-433) ----
@@ -537,26 +583,45 @@ struct Phase2 {
   }
 
   // ---- traceback (align_lpo_po2.c:108-168): fills the x2y field of the node records ----
+  // The walk reads one moves word per step; the words of the next three columns of the band
+  // are loaded ahead.  Only nodes flagged in the bitmap need their record looked up.
   EL_HDN void traceback(int ly, int best_j) const {
+    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
     int j = best_j, r = ly - 1;
+    uint32_t ntw = 0;
+    int ntbase = -1;
     while (j >= 0 && r >= 0) {
       const int b = r >> 4;
       uint32_t *p = rec((uint32_t)j);
-      const uint32_t kind = (p[(R2_MOVES + b) * 32] >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
-      if (kind & 2u) p[R2_X2Y * 32] = (uint32_t)r;
-      if (kind) {  // match or X-gap: step to a predecessor of j
-        const uint32_t ra = p[R2_NODE * 32];
-        int ord = 0;
-        if (ra & (NF_VIRT | NF_TWO)) {
-          const uint32_t *po = scr.at(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
-          ord = (int)((((kind & 2u) ? po[0] : po[32]) >> (2 * (r & 15))) & 3u);
+      const uint32_t *pm = p + (R2_MOVES + b) * 32;
+      uint32_t w0 = pm[0], w1 = j >= 1 ? pm[-step] : 0, w2 = j >= 2 ? pm[-2 * step] : 0, w3 = j >= 3 ? pm[-3 * step] : 0;
+      for (;;) {
+        const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
+        if (kind & 2u) p[R2_X2Y * 32] = (uint32_t)r;
+        bool jump = false;
+        if (kind) {  // match or X-gap: step to a predecessor of j
+          if ((j >> 5) != ntbase) { ntbase = j >> 5; ntw = scr.w(Lp->o_nt + ntbase); }
+          if ((ntw >> (j & 31)) & 1u) {
+            const uint32_t ra = p[R2_NODE * 32];
+            int ord = 0;
+            if (ra & (NF_VIRT | NF_TWO)) {
+              const uint32_t *po = scr.at(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
+              ord = (int)((((kind & 2u) ? po[0] : po[32]) >> (2 * (r & 15))) & 3u);
+            }
+            const uint32_t pr = p[R2_PRED * 32];
+            const int pA = (pr & 0xffffu) == 0xffffu ? -1 : (int)(pr & 0xffffu), pB = (pr >> 16) == 0xffffu ? -1 : (int)(pr >> 16);
+            if (ra & NF_VIRT) j = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
+            else j = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
+            jump = true;
+          } else {
+            --j; p -= step; pm -= step;
+            w0 = w1; w1 = w2; w2 = w3;
+            w3 = j >= 3 ? pm[-3 * step] : 0;
+          }
         }
-        const uint32_t pr = p[R2_PRED * 32];
-        const int pA = (pr & 0xffffu) == 0xffffu ? -1 : (int)(pr & 0xffffu), pB = (pr >> 16) == 0xffffu ? -1 : (int)(pr >> 16);
-        if (ra & NF_VIRT) j = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
-        else j = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
+        if (kind != 1u) --r;  // match or Y-gap: step up
+        if (jump || j < 0 || r < 0 || (r >> 4) != b) break;
       }
-      if (kind != 1u) --r;  // match or Y-gap: step up
     }
   }
 
@@ -586,18 +651,28 @@ struct Phase2 {
       if (srcmask & 2u) c1 = ch;
       if (srcmask & 4u) c2 = ch;
     };
-    for (int ix = 0; ix < n1; ++ix) {
-      const uint32_t ra = node(ix);
+    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
+    const uint32_t *pr = rec(0);
+    // (node, x2y) of records ix, ix+1 in registers, ix+2 in flight
+    uint32_t ra0 = pr[R2_NODE * 32], ra1 = n1 > 1 ? pr[step + R2_NODE * 32] : 0;
+    int q0 = (int)pr[R2_X2Y * 32], q1 = n1 > 1 ? (int)pr[step + R2_X2Y * 32] : -1;
+    for (int ix = 0; ix < n1; ++ix, pr += step) {
+      const uint32_t ra = ra0, ra_next = ra1;
+      const int qx = q0, q_next = q1;
+      ra0 = ra1; q0 = q1;
+      if (ix + 2 < n1) { ra1 = pr[2 * step + R2_NODE * 32]; q1 = (int)pr[2 * step + R2_X2Y * 32]; }
       if (!(ra & NF_SAMERING)) rs = ix;
       // scan x's ring from ix on: unaligned y letters go before the first aligned member
-      for (int ir = ix;;) {
-        const int q = x2y(ir);
-        if (q >= 0) { while (iy < q) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; } break; }
-        ++ir;
-        if (ir >= n1 || !(node(ir) & NF_SAMERING)) break;
+      {
+        int q = qx;
+        if (q < 0 && ix + 1 < n1 && (ra_next & NF_SAMERING)) {
+          q = q_next;
+          for (int ir = ix + 2; q < 0 && ir < n1 && (node(ir) & NF_SAMERING); ++ir) q = x2y(ir);
+        }
+        if (q >= 0) while (iy < q) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
       }
       uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
-      if (x2y(ix) >= 0 && iy < lu) {
+      if (qx >= 0 && iy < lu) {
         const uint32_t yl = scr.code_at(Lp->o_unc, iy);
         if (yl == (ra & 0xffu)) mask |= 4u;
         else emit(rs, yl, 4u);
@@ -627,10 +702,10 @@ struct Phase2 {
 // Shared memory holds the symbol tables (the 2 KB substitution table only for non-uniform
 // matrices), the group's scratch layout and, in phase 2, two frontier-set slots (8.25 KB).
 #ifndef EL_MIN_WARPS_PH1
-#define EL_MIN_WARPS_PH1 24
+#define EL_MIN_WARPS_PH1 28  // register caps 72 / 96: measured best
 #endif
 #ifndef EL_MIN_WARPS_PH2
-#define EL_MIN_WARPS_PH2 24
+#define EL_MIN_WARPS_PH2 20
 #endif
 
 template <bool GENERIC_SUB>
@@ -674,7 +749,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PH1) poa_dp1_kernel(PoaArgs a
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     if (active) {
       int s1, spcode;
-      const int n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + (ro + co), s1, spcode);
+      const int n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro, co, w), s1, spcode);
       const int lu = (int)(a.unc_off[w + 1] - a.unc_off[w]);
       int bin, seg;
       bin2_of(n1, lu, spcode, bin, seg);
@@ -724,7 +799,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PH2) poa_dp2_kernel(PoaArgs a
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     if (active) {
       int s2;
-      nring = c.run_window(a.p1_nodes + (ro + co), n1, a.unc + uo, lu, s2);
+      nring = c.run_window(a.p1_nodes + p1_offset(ro, co, w), n1, a.unc + uo, lu, s2);
       a.nring[w] = nring;
       if (a.score2) a.score2[w] = s2;
       if (a.cells) {
@@ -753,8 +828,12 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PH2) poa_dp2_kernel(PoaArgs a
       else {
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.rows_out + off);
         const int sw4 = stride >> 2;
-        for (int s = 0; s < 3; ++s)
-          for (int k = 0; k < sw4; ++k) dst[s * sw4 + k] = c.scr.w(s_layout.o_rows + s * s_layout.row_words + k);
+        for (int s = 0; s < 3; ++s) {
+          const uint32_t *srow = c.scr.at(s_layout.o_rows + s * s_layout.row_words);
+          uint32_t *drow = dst + s * sw4;
+#pragma unroll 4
+          for (int k = 0; k < sw4; ++k) drow[k] = srow[k * 32];
+        }
       }
     }
     __syncwarp();

@@ -31,10 +31,11 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     p1.scr.base = scratch1.data() + lane;
     p1.sc = s;
     p1.Lp = &L1;
-    std::vector<uint16_t> nodes((size_t)lr + lc, 0xdeadu);
+    std::vector<uint64_t> nodes64(((size_t)lr + lc) / 4 + 2, 0xdeaddeaddeaddeadull);
+    uint16_t *nodes_p = reinterpret_cast<uint16_t *>(nodes64.data());
     int s1, spcode;
     const int n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc,
-                                 nodes.data(), s1, spcode);
+                                 nodes_p, s1, spcode);
     int bin, seg;
     bin2_of(n1, lu, spcode, bin, seg);
     if (bin < 0 || bin >= kNumBins2 || seg < 0 || seg >= kNumSegs2) { fprintf(stderr, "bad phase-2 bin\n"); return 1; }
@@ -49,7 +50,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     p2.sc = s;
     p2.Lp = &L2;
     int s2;
-    const int nring = p2.run_window(nodes.data(), n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
+    const int nring = p2.run_window(nodes_p, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
     const FastaRecord *recs[3] = {&R.rec[w], &C.rec[w], &U.rec[w]};
     for (int r = 0; r < 3; ++r) {
       fprintf(pir, ">%s %s\n", recs[r]->name.c_str(), recs[r]->title.c_str());
