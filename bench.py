@@ -5,15 +5,16 @@
   python bench.py --impl reference --gpus N --steps K --warmup W
 
 One step = one pass of the hot path (three-way POA of every window of every triplet, then
-the per-read merge + tally once those kernels exist) over the workload: BASELINE.json
+the per-read merge + tally + global counter sum) over the workload: BASELINE.json
 configs[1], 10 000 triplets of 10 kb reads at 10 % / 1 % error, cut into ~1.95 M windows by
 the unchanged reference splitter.  Per-GPU work is fixed (weak scaling): rank r owns read
 ids [r*10000, (r+1)*10000).  The window arrays (~300 MB) exceed the 126 MB L2, so no
 flush is needed between steps.
 
-  value     triplets/s with the window arrays already resident in HBM (elector_poa_run_device)
-  e2e       the same through the host-buffer C-ABI call (elector_poa_run): pinned host
-            arrays in, MSA rows out, H2D/D2H inside the timed region
+  value     triplets/s with the window arrays already resident in HBM (elector_poa_run_device +
+            elector_merge_tally_device + elector_tally_sum_device)
+  e2e       the same through the host-buffer C-ABI call (elector_pipeline_run): pinned host
+            arrays in, MSA rows + per-read counters out, H2D/D2H inside the timed region
   roofline  INT32 issue roofline of the DP kernel (15 integer ops per DP cell)
             against the peak measured on this device by elector_int32_peak
   cpu_baseline  the reference poa binary (oracle/_ref/poa) or the oracle port, timed on
@@ -173,13 +174,16 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    import ctypes
     import torch
     import elector_b200
+    from elector_b200 import TALLY_FIELDS
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    K = len(TALLY_FIELDS)
 
     wl = workloads.make_windows(args.config, n_reads, rank * n_reads)
     n_trip = len(wl["read_first"]) - 1
@@ -191,9 +195,10 @@ def main():
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
-    hp = {k: pinned(wl[k]) for k in ("ref", "ref_off", "cor", "cor_off", "unc", "unc_off")}
-    dv = {k: hp[k][0].to(dev, non_blocking=False) for k in hp}
-    bound = int(lib.elector_poa_rows_bound(n, hp["ref_off"][1].ctypes.data, hp["cor_off"][1].ctypes.data, hp["unc_off"][1].ctypes.data))
+    hp = {k: pinned(wl[k]) for k in ("ref", "ref_off", "cor", "cor_off", "unc", "unc_off", "read_first")}
+    dv = {k: hp[k][0].to(dev, non_blocking=False) for k in hp if k != "read_first"}
+    hptr = {k: hp[k][1].ctypes.data for k in hp}
+    bound = int(lib.elector_poa_rows_bound(n, hptr["ref_off"], hptr["cor_off"], hptr["unc_off"]))
     d_rows = torch.empty(bound, dtype=torch.uint8, device=dev)
     d_rowoff = torch.empty(n, dtype=torch.int64, device=dev)
     d_stride = torch.empty(n, dtype=torch.int32, device=dev)
@@ -202,25 +207,49 @@ def main():
     d_s2 = torch.empty(n, dtype=torch.int32, device=dev)
     d_cells = torch.empty(n, dtype=torch.int64, device=dev)
     d_used = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_cnt = torch.zeros(n_trip * K, dtype=torch.int64, device=dev)
+    d_sums = torch.zeros(K, dtype=torch.int64, device=dev)
     h_rows = torch.empty(bound, dtype=torch.uint8).pin_memory()
     h_out = {"row_off": torch.empty(n, dtype=torch.int64).pin_memory(), "stride": torch.empty(n, dtype=torch.int32).pin_memory(),
-             "nring": torch.empty(n, dtype=torch.int32).pin_memory()}
+             "nring": torch.empty(n, dtype=torch.int32).pin_memory(), "counters": torch.empty(n_trip * K, dtype=torch.int64).pin_memory(),
+             "sums": torch.empty(K, dtype=torch.int64).pin_memory()}
+    h_used = torch.zeros(1, dtype=torch.int64).pin_memory()
     torch.cuda.synchronize()
+    phase = {"p1": 0.0, "tot": 0.0, "launches": 0, "tally_ms": 0.0}
 
     def step_device():
-        rc = lib.elector_poa_run_device(ctx._ctx, n, dv["ref"].data_ptr(), dv["ref_off"].data_ptr(), dv["cor"].data_ptr(),
-                                        dv["cor_off"].data_ptr(), dv["unc"].data_ptr(), dv["unc_off"].data_ptr(),
-                                        hp["ref_off"][1].ctypes.data, hp["cor_off"][1].ctypes.data, hp["unc_off"][1].ctypes.data,
-                                        d_rows.data_ptr(), bound, d_rowoff.data_ptr(), d_stride.data_ptr(), d_nring.data_ptr(),
-                                        d_s1.data_ptr(), d_s2.data_ptr(), d_cells.data_ptr(), d_used.data_ptr())
-        ctx._check(rc)
+        """inputs resident in HBM: POA (both phases) -> merge -> tally -> global counters [-> all-reduce]"""
+        ctx._check(lib.elector_poa_run_device(ctx._ctx, n, dv["ref"].data_ptr(), dv["ref_off"].data_ptr(), dv["cor"].data_ptr(),
+                                              dv["cor_off"].data_ptr(), dv["unc"].data_ptr(), dv["unc_off"].data_ptr(),
+                                              hptr["ref_off"], hptr["cor_off"], hptr["unc_off"],
+                                              d_rows.data_ptr(), bound, d_rowoff.data_ptr(), d_stride.data_ptr(), d_nring.data_ptr(),
+                                              d_s1.data_ptr(), d_s2.data_ptr(), d_cells.data_ptr(), d_used.data_ptr()))
+        a, b = ctypes.c_float(0), ctypes.c_float(0)
+        lib.elector_last_phase_ms(ctx._ctx, ctypes.byref(a), ctypes.byref(b))
+        m, k = ctx.last_kernel_ms()
+        phase["p1"] += a.value; phase["tot"] += b.value; phase["launches"] += k
+        h_used.copy_(d_used)
+        ctx._check(lib.elector_merge_tally_device(ctx._ctx, n_trip, hptr["read_first"], n, d_rows.data_ptr(), int(h_used.item()),
+                                                  d_rowoff.data_ptr(), d_stride.data_ptr(), d_nring.data_ptr(), d_cnt.data_ptr()))
+        m, k = ctx.last_kernel_ms()
+        phase["tally_ms"] += m; phase["launches"] += k
+        d_sums.zero_()
+        torch.cuda.current_stream().synchronize()   # the library launches on its own stream
+        ctx._check(lib.elector_tally_sum_device(ctx._ctx, n_trip, d_cnt.data_ptr(), d_sums.data_ptr()))
+        phase["launches"] += 1
+        if world > 1:
+            dist.all_reduce(d_sums)       # the one collective of the path: 24 int64 counters
 
     def step_e2e():
-        rc = lib.elector_poa_run(ctx._ctx, n, hp["ref"][1].ctypes.data, hp["ref_off"][1].ctypes.data, hp["cor"][1].ctypes.data,
-                                 hp["cor_off"][1].ctypes.data, hp["unc"][1].ctypes.data, hp["unc_off"][1].ctypes.data,
-                                 h_rows.data_ptr(), bound, h_out["row_off"].data_ptr(), h_out["stride"].data_ptr(),
-                                 h_out["nring"].data_ptr(), None, None, None)
-        ctx._check(rc)
+        """the call a user makes: host buffers in, MSA rows + per-read counters + global counters out"""
+        ctx._check(lib.elector_pipeline_run(ctx._ctx, n, hptr["ref"], hptr["ref_off"], hptr["cor"], hptr["cor_off"], hptr["unc"],
+                                            hptr["unc_off"], n_trip, hptr["read_first"], h_rows.data_ptr(), bound,
+                                            h_out["row_off"].data_ptr(), h_out["stride"].data_ptr(), h_out["nring"].data_ptr(),
+                                            None, None, None, h_out["counters"].data_ptr(), h_out["sums"].data_ptr()))
+        if world > 1:
+            t = h_out["sums"].to(dev)
+            dist.all_reduce(t)
+            h_out["sums"].copy_(t)
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,40 +258,45 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        """device time of `steps` calls, CUDA events on the library's launching stream; also kernel-only ms"""
-        import ctypes
+        """device time of `steps` calls: CUDA events on the library's launching stream, max over ranks"""
         barrier()
         ctx._check(lib.elector_event_record(ctx._ctx, 0))
-        kms, launches = 0.0, 0
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
-            m, k = ctx.last_kernel_ms()
-            kms += m
-            launches += k
         ctx._check(lib.elector_event_record(ctx._ctx, 1))
         ms = ctypes.c_float(0)
         ctx._check(lib.elector_event_elapsed_ms(ctx._ctx, ctypes.byref(ms)))
+        torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         barrier()
-        t = torch.tensor([ms.value, wall], dtype=torch.float64, device=dev)
+        t = torch.tensor([max(ms.value, 0.0), wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), kms, launches
+        return float(t[0]), float(t[1])
 
     for _ in range(args.warmup):
         step_device()
+    for k in phase:
+        phase[k] = 0
     sampler = ClockSampler(local)
     sampler.start()
-    dev_ms, dev_wall, kern_ms, launches = timed(step_device, args.steps)
+    dev_ms, dev_wall = timed(step_device, args.steps)
     clocks = sampler.summary()
+    # the library's stream events bracket the steps; the tally launches and the all-reduce end on other streams, so the
+    # wall clock around the synchronised loop is the safe upper bound: report the larger of the two
+    step_ms = max(dev_ms, dev_wall) / args.steps
     cells = int(d_cells.sum().item())
     used = int(d_used.item())
+    sums_dev = d_sums.cpu().numpy().copy()
     for _ in range(args.warmup):
         step_e2e()
-    e2e_ms, e2e_wall, _, _ = timed(step_e2e, args.steps)
+    e2e_ms, e2e_wall = timed(step_e2e, args.steps)
+    e2e_step_ms = max(e2e_ms, e2e_wall) / args.steps
+    sums_e2e = h_out["sums"].numpy().copy()
 
-    # parity spot check of what was just timed (not in the timed region): first 2000 windows vs the oracle
+    # parity spot check of what was just timed (not in the timed region): first 2000 windows vs the oracle,
+    # and the two paths (device-resident / pipelined host call) against each other
     parity = None
     try:
         from oracle import oracle
@@ -281,57 +315,75 @@ def main():
                 if not np.array_equal(a, b):
                     ok = False
                     break
-        parity = "bit-exact vs oracle on %d windows" % k if ok else "MISMATCH vs oracle"
+        ok = ok and bool(np.array_equal(sums_dev, sums_e2e))
+        ok = ok and bool(np.array_equal(h_out["counters"].numpy(), d_cnt.cpu().numpy()))
+        parity = "bit-exact vs oracle on %d windows; device and host paths agree on all per-read counters" % k if ok else "MISMATCH"
     except Exception as e:  # the oracle is only a checker here
         parity = "not checked (%s)" % e
 
-    # roofline of the dominant kernel
-    import ctypes
+    # roofline of the dominant kernel (poa_dp2_kernel: DP2 phase incl. its sort), and of the DP1 phase beside it
     mixed, alu = ctypes.c_double(0), ctypes.c_double(0)
     ctx._check(lib.elector_int32_peak(ctx._ctx, ctypes.byref(mixed), ctypes.byref(alu)))
-    kern_s_per_step = kern_ms / 1e3 / args.steps
-    achieved = INT_OPS_PER_CELL * cells / kern_s_per_step / 1e12
+    lr, lc = np.diff(wl["ref_off"]), np.diff(wl["cor_off"])
+    cells1 = int((lr * lc).sum())
+    cells2 = cells - cells1
+    p1_s = phase["p1"] / 1e3 / args.steps
+    p2_s = (phase["tot"] - phase["p1"]) / 1e3 / args.steps
+    poa_s = phase["tot"] / 1e3 / args.steps
+    ach2 = INT_OPS_PER_CELL * cells2 / p2_s / 1e12
+    ach1 = INT_OPS_PER_CELL * cells1 / p1_s / 1e12
     hbm_peak = 6552.6
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    in_bytes = int(wl["ref_off"][-1] + wl["cor_off"][-1] + wl["unc_off"][-1]) + 3 * 8 * (n + 1)
-    out_bytes = used + n * (8 + 4 + 4)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    in_bytes = int(wl["ref_off"][-1] + wl["cor_off"][-1] + wl["unc_off"][-1]) + 3 * 8 * (n + 1) + 8 * (n_trip + 1)
+    out_bytes = used + n * (8 + 4 + 4) + n_trip * K * 8 + K * 8
     alg_bytes = in_bytes + used + n * 36
 
-    value = n_trip * world * args.steps / (dev_ms / 1e3)
-    e2e_val = n_trip * world * args.steps / (e2e_ms / 1e3)
+    value = n_trip * world / (step_ms / 1e3)
+    e2e_val = n_trip * world / (e2e_step_ms / 1e3)
     line = {
         "metric": "triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32 (int16 score storage)", "data": "synthetic",
-        "gcups": cells * world * args.steps / (dev_ms / 1e3) / 1e9,
-        "gcups_kernel_only": cells / kern_s_per_step / 1e9,
-        "windows_per_sec": n * world * args.steps / (dev_ms / 1e3),
-        "config": {"workload": workload_name, "windows_per_gpu": n, "cells_per_gpu": cells, "windows_from": wl["source"],
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "gcups": cells * world / (step_ms / 1e3) / 1e9,
+        "gcups_poa_kernels_only": cells / poa_s / 1e9,
+        "windows_per_sec": n * world / (step_ms / 1e3),
+        "config": {"workload": workload_name, "step": "POA of every window (DP1 + DP2 phases) + per-read merge + tally + counter sum",
+                   "windows_per_gpu": n, "cells_per_gpu": cells, "windows_from": wl["source"],
                    "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush" % (in_bytes / 1e6), "parity": parity},
         "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches,
-        "kernel_ms_per_step": kern_ms / args.steps,
-        "host_ms_per_step": max(0.0, (dev_wall - kern_ms) / args.steps),
+                "ms_per_step": e2e_step_ms, "call": "elector_pipeline_run (pinned host buffers in, MSA rows + counters out)"},
+        "gpu_launches": phase["launches"],
+        "kernel_ms_per_step": {"sort1+poa_dp1_kernel": phase["p1"] / args.steps, "sort2+poa_dp2_kernel": (phase["tot"] - phase["p1"]) / args.steps,
+                               "merge+tally": phase["tally_ms"] / args.steps},
         "clocks": clocks,
-        "roofline": {"bound": "int32", "achieved": achieved, "peak": mixed.value, "unit": "TIOP/s",
-                     "frac": achieved / mixed.value if mixed.value else None, "traffic": None,
-                     "peak_alu_pipe_only": alu.value, "ops_per_cell": INT_OPS_PER_CELL,
-                     "kernel": "poa_tpw_kernel (all size-class launches of one step)",
-                     "peak_source": "measured on this device by elector_int32_peak (IMAD/IADD3/VIMNMX/LOP3 chains)"},
-        "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / kern_s_per_step / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": alg_bytes / kern_s_per_step / 1e9 / hbm_peak, "traffic": None,
-                         "note": "algorithmic bytes = letters + offsets in, MSA rows + per-window results out"},
+        "roofline": {"bound": "int32", "achieved": ach2, "peak": mixed.value, "unit": "TIOP/s",
+                     "frac": ach2 / mixed.value if mixed.value else None,
+                     "traffic": (traffic or {}).get("poa_dp2_kernel_bytes_per_launch_set"),
+                     "kernel": "poa_dp2_kernel (all segment launches of one step, with its sort)",
+                     "ops_per_cell": INT_OPS_PER_CELL, "cells_per_step": cells2,
+                     "peak_alu_pipe_only": alu.value,
+                     "peak_source": "measured on this device by elector_int32_peak (IMAD/IADD3/VIMNMX/LOP3 chains)",
+                     "also": {"kernel": "poa_dp1_kernel", "achieved": ach1, "frac": ach1 / mixed.value if mixed.value else None,
+                              "cells_per_step": cells1}},
+        "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / poa_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / poa_s / 1e9 / hbm_peak, "traffic": (traffic or {}).get("poa_step_dram_bytes"),
+                         "note": "algorithmic bytes = letters + offsets in, MSA rows + per-window results out; the path is integer-issue bound, not HBM bound"},
+        "counters": {f: int(v) for f, v in zip(TALLY_FIELDS, sums_dev) if f in ("TP", "FP", "FN", "insU", "delU", "subsU", "insC", "delC", "subsC", "assessed")},
     }
     if rank == 0 and not args.no_cpu_baseline:
         kind = "reference" if have_ref else "port"
         k = args.cpu_triplets or int(min(n_trip, max(8, ncores * 26 * 10)))
         cb = cpu_reference_throughput(wl, k, ncores, kind)
         line["cpu_baseline"] = {"value": cb["triplets_per_s"], "unit": "triplets/s", "cores": ncores, "kind": kind,
-                                "sample": "first %d triplets (%d windows), %.1f s, %d concurrent single-threaded poa processes" %
+                                "sample": "first %d triplets (%d windows), %.1f s, %d concurrent single-threaded poa processes (alignment only, no Donatello / computeStats)" %
                                           (k, cb["windows"], cb["seconds"], ncores) if kind == "reference" else
                                           "first %d triplets (%d windows), %.1f s, oracle with %d OpenMP threads" % (k, cb["windows"], cb["seconds"], ncores),
                                 "gcups": cb["gcups"]}

@@ -55,14 +55,18 @@ struct elector_ctx {
   int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr;
+  float last_ms_phase1 = 0.f;  // sort 1 + phase-1 kernels of the last run (last_ms covers everything)
   cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
   elector::BinTable *h_bintab = nullptr;  // pinned
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H of the pipelined host entry point
+  std::vector<cudaEvent_t> chunk_ev;                    // 2 per chunk: inputs resident, results ready
   ScoreMatrix mat;
   ScoringSetup sc;
   DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
-  DevBuf d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
+  int64_t merged_cap = 0;  // bytes per merged-row buffer of the last merge
+  DevBuf d_wdst, d_sums, d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
   std::string err;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -85,6 +89,12 @@ struct elector_ctx {
   } while (0)
 
 namespace {
+
+int merge_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first, int64_t n_windows, const uint8_t *d_rows,
+                 int64_t rows_bytes, const int64_t *d_row_off, const int32_t *d_row_stride, const int32_t *d_nring);
+int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uint8_t *dC, const uint8_t *dU,
+                 const int64_t *d_off, const int32_t *d_len, int64_t *d_counters, int64_t total_bytes);
+int check_scan_overflow(elector_ctx *ctx, int64_t n_reads);
 
 const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..19] phase-1 and [20..35] phase-2 work counters
 const int kSideStreams = 3;
@@ -175,9 +185,7 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
 int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
                const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, char *d_rows, int64_t rows_cap,
                int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2, int64_t *d_cells,
-               unsigned long long *d_cursor, int32_t *d_errflag) {
-  ctx->last_ms = 0.f;
-  ctx->last_launches = 0;
+               unsigned long long *d_cursor, int32_t *d_errflag, bool keep_cursor = false) {
   if (n == 0) return ELECTOR_OK;
   if (n > 0x7fffffff - 64) return ctx->fail(ELECTOR_EINVAL, "too many windows in one call");
   cudaStream_t st = ctx->stream;
@@ -190,7 +198,8 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   BinTable *dtab1 = ctx->d_bintab.as<BinTable>(), *dtab2 = dtab1 + 1;
   BinTable *htab1 = ctx->h_bintab, *htab2 = ctx->h_bintab + 1;
   CU(cudaEventRecord(ctx->ev0, st));
-  CU(cudaMemsetAsync(ctx->d_ctrl.p, 0, sizeof(int32_t) * kCtrlWords, st));
+  // rows cursor (words 0..1) survives between the chunks of one pipelined call
+  CU(cudaMemsetAsync(ctx->d_ctrl.as<int32_t>() + (keep_cursor ? 2 : 0), 0, sizeof(int32_t) * (kCtrlWords - (keep_cursor ? 2 : 0)), st));
   CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)(kNumBins1 + kNumBins2) * sizeof(int32_t), st));
   memset(htab1, 0, 2 * sizeof(BinTable));
   fill_segments1(*htab1);
@@ -209,16 +218,19 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   CU(cudaMemcpyAsync(htab1, dtab1, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&ctx->h_totals[0], d_roff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&ctx->h_totals[1], d_coff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&ctx->h_totals[2], d_roff, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&ctx->h_totals[3], d_coff, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (htab1->err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", htab1->err_window);
   if (htab1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d longer than %d letters", htab1->err_window, kMaxWindowLen);
-  CU(ctx->d_p1.reserve((size_t)(ctx->h_totals[0] + ctx->h_totals[1] + 8 * n + 8) * sizeof(uint16_t)));
+  CU(ctx->d_p1.reserve((size_t)(ctx->h_totals[0] - ctx->h_totals[2] + ctx->h_totals[1] - ctx->h_totals[3] + 8 * n + 8) * sizeof(uint16_t)));
 
   PoaArgs a;
   memset(&a, 0, sizeof a);
   a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
   a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
   a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
+  a.ro0 = ctx->h_totals[2]; a.co0 = ctx->h_totals[3];
   a.p1_nodes = ctx->d_p1.as<uint16_t>(); a.n1 = ctx->d_n1.as<int32_t>(); a.key2 = ctx->d_key.as<int32_t>();
   a.hist2 = hist2; a.seg2_max = dtab2->seg_max;
   a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
@@ -233,6 +245,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   CU(ctx->d_scratch.reserve(scratch_words * 4));
   rc = launch_segments(ctx, 1, n, *htab1, plan, a);
   if (rc != ELECTOR_OK) return rc;
+  CU(cudaEventRecord(ctx->ev_mid, st));
   // ---- sort 2 (phase 1 filled key2, hist2 and the segment maxima) ----
   bin_scan_chunks_kernel<<<nch2, kScanChunk, 0, st>>>(kNumBins2, hist2, chunks2);
   bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch2, chunks2, hist2, dtab2);
@@ -249,6 +262,13 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev1, st));
   return ELECTOR_OK;
+}
+
+// adds the device time between ev0 and ev1 (both already reached) to the running total of a call
+void add_kernel_ms(elector_ctx *ctx) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms += ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) ctx->last_ms_phase1 += ms;
 }
 
 }  // namespace
@@ -286,6 +306,7 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->uev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->uev1)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
@@ -294,10 +315,13 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_join[2], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMallocHost((void **)&ctx->h_bintab, 2 * sizeof(BinTable))) != cudaSuccess ||
-      (e = cudaMallocHost((void **)&ctx->h_totals, 2 * sizeof(int64_t))) != cudaSuccess ||
+      (e = cudaMallocHost((void **)&ctx->h_totals, 8 * sizeof(int64_t))) != cudaSuccess ||
       (e = ctx->d_tab.reserve(sizeof(SymbolTables))) != cudaSuccess ||
       (e = ctx->d_ctrl.reserve(kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMemset(ctx->d_ctrl.p, 0, kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemcpy(ctx->d_tab.p, &ctx->sc.tab, sizeof(SymbolTables), cudaMemcpyHostToDevice)) != cudaSuccess) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
@@ -313,11 +337,12 @@ void elector_poa_free(elector_ctx *ctx) {
   if (!ctx) return;
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
                     &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
-                    &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_tally_scan, &ctx->d_tally_out,
+                    &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_wdst, &ctx->d_sums, &ctx->d_tally_scan, &ctx->d_tally_out,
                     &ctx->d_readfirst, &ctx->d_mtot, &ctx->d_moff, &ctx->d_mlen, &ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
   for (DevBuf *b : bufs) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
   if (ctx->uev0) cudaEventDestroy(ctx->uev0);
   if (ctx->uev1) cudaEventDestroy(ctx->uev1);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -326,6 +351,9 @@ void elector_poa_free(elector_ctx *ctx) {
     if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
   }
   if (ctx->h_bintab) cudaFreeHost(ctx->h_bintab);
+  for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -350,6 +378,8 @@ int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const
     return ctx->fail(ELECTOR_EINVAL, "null argument");
   CU(cudaSetDevice(ctx->device));
   (void)h_roff; (void)h_coff; (void)h_uoff;  // binning happens on the device
+  ctx->last_ms = ctx->last_ms_phase1 = 0.f;
+  ctx->last_launches = 0;
   int rc = run_device(ctx, n, d_ref, d_roff, d_cor, d_coff, d_unc, d_uoff, d_rows, rows_cap,
                       d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells, ctx->d_ctrl.as<unsigned long long>(),
                       ctx->d_ctrl.as<int32_t>() + 2);
@@ -359,7 +389,7 @@ int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const
   int32_t ctrl[4] = {0, 0, 0, 0};
   CU(cudaMemcpyAsync(ctrl, ctx->d_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (n > 0) cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+  if (n > 0) add_kernel_ms(ctx);
   if (ctrl[2]) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small", (long long)rows_cap);
   return ELECTOR_OK;
 }
@@ -367,46 +397,134 @@ int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const
 int elector_poa_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ro, const char *cor, const int64_t *co,
                     const char *unc, const int64_t *uo, char *rows_out, int64_t rows_cap, int64_t *row_off,
                     int32_t *row_stride, int32_t *nring, int32_t *score1, int32_t *score2, int64_t *cells) {
+  return elector_pipeline_run(ctx, n, ref, ro, cor, co, unc, uo, 0, nullptr, rows_out, rows_cap, row_off, row_stride, nring,
+                              score1, score2, cells, nullptr, nullptr);
+}
+
+// Host buffers in, host buffers out, in chunks of whole reads: the inputs of all chunks are
+// queued on a copy stream up front, every chunk's kernels wait for its own inputs only, and a
+// chunk's results travel back on a second copy stream while the next chunk computes.
+int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ro, const char *cor, const int64_t *co,
+                         const char *unc, const int64_t *uo, int64_t n_reads, const int64_t *read_first, char *rows_out,
+                         int64_t rows_cap, int64_t *row_off, int32_t *row_stride, int32_t *nring, int32_t *score1,
+                         int32_t *score2, int64_t *cells, int64_t *counters_out, int64_t *sums_out) {
   if (!ctx) return ELECTOR_EINVAL;
-  if (n < 0 || (n > 0 && (!ref || !cor || !unc || !ro || !co || !uo || !rows_out || !row_off || !row_stride || !nring)))
+  if (n < 0 || n_reads < 0 || (n > 0 && (!ref || !cor || !unc || !ro || !co || !uo || !rows_out || !row_off || !row_stride || !nring)))
     return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_reads > 0 && (!read_first || !counters_out)) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (sums_out) memset(sums_out, 0, ELECTOR_TALLY_K * sizeof(int64_t));
+  ctx->last_ms = ctx->last_ms_phase1 = 0.f;
+  ctx->last_launches = 0;
   if (n == 0) return ELECTOR_OK;
-  CU(cudaSetDevice(ctx->device));
-  const int64_t br = ro[n] - ro[0], bc = co[n] - co[0], bu = uo[n] - uo[0];
   if (ro[0] != 0 || co[0] != 0 || uo[0] != 0) return ctx->fail(ELECTOR_EINVAL, "offsets must start at 0");
-  const int64_t bound = elector_poa_rows_bound(n, ro, co, uo);
+  if (n_reads > 0 && (read_first[0] != 0 || read_first[n_reads] != n)) return ctx->fail(ELECTOR_EINVAL, "read_first must span 0..n_windows");
+  CU(cudaSetDevice(ctx->device));
+  // ---- chunk boundaries (windows; whole reads when reads are given) ----
+  // Few, large chunks: every chunk pays the latency of its longest windows once per phase (a warp
+  // that holds 200-letter windows runs for milliseconds), which only a bulk of >= ~0.5 M windows hides.
+  int want_chunks = 3;
+  if (const char *e = getenv("ELECTOR_PIPELINE_CHUNKS")) want_chunks = std::max(1, atoi(e));
+  const int64_t target = std::max<int64_t>(std::min<int64_t>(n, 524288), (n + want_chunks - 1) / want_chunks);
+  std::vector<int64_t> wcut(1, 0), rcut(1, 0);
+  if (n_reads > 0) {
+    int64_t r = 0;
+    while (r < n_reads) {
+      // first read boundary at or after the target (binary search on read_first)
+      const int64_t want = std::min<int64_t>(n, wcut.back() + target);
+      int64_t lo = r + 1, hi = n_reads;
+      while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (read_first[mid] >= want) hi = mid; else lo = mid + 1; }
+      r = lo;
+      rcut.push_back(r);
+      wcut.push_back(read_first[r]);
+    }
+  } else {
+    while (wcut.back() < n) wcut.push_back(std::min<int64_t>(n, wcut.back() + target));
+  }
+  const size_t nchunks = wcut.size() - 1;
+  while (ctx->chunk_ev.size() < 2 * nchunks) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->chunk_ev.push_back(e);
+  }
+  // ---- device buffers for the whole call ----
+  const int64_t br = ro[n], bc = co[n], bu = uo[n];
   CU(ctx->d_ref.reserve(br)); CU(ctx->d_cor.reserve(bc)); CU(ctx->d_unc.reserve(bu));
   CU(ctx->d_roff.reserve((n + 1) * 8)); CU(ctx->d_coff.reserve((n + 1) * 8)); CU(ctx->d_uoff.reserve((n + 1) * 8));
-  CU(ctx->d_rows.reserve(bound)); CU(ctx->d_rowoff.reserve(n * 8)); CU(ctx->d_stride.reserve(n * 4));
+  CU(ctx->d_rows.reserve(rows_cap)); CU(ctx->d_rowoff.reserve(n * 8)); CU(ctx->d_stride.reserve(n * 4));
   CU(ctx->d_nring.reserve(n * 4)); CU(ctx->d_s1.reserve(n * 4)); CU(ctx->d_s2.reserve(n * 4)); CU(ctx->d_cells.reserve(n * 8));
-  cudaStream_t st = ctx->stream;
-  CU(cudaMemcpyAsync(ctx->d_ref.p, ref, br, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_cor.p, cor, bc, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_unc.p, unc, bu, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_roff.p, ro, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_coff.p, co, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_uoff.p, uo, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  int rc = run_device(ctx, n, ctx->d_ref.as<char>(), ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>(),
-                      ctx->d_coff.as<int64_t>(), ctx->d_unc.as<char>(), ctx->d_uoff.as<int64_t>(),
-                      ctx->d_rows.as<char>(), bound, ctx->d_rowoff.as<int64_t>(), ctx->d_stride.as<int32_t>(),
-                      ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(), ctx->d_s2.as<int32_t>(),
-                      ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2);
-  if (rc != ELECTOR_OK) return rc;
-  int64_t ctrl[2] = {0, 0};
-  CU(cudaMemcpyAsync(ctrl, ctx->d_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(row_off, ctx->d_rowoff.p, n * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(row_stride, ctx->d_stride.p, n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(nring, ctx->d_nring.p, n * 4, cudaMemcpyDeviceToHost, st));
-  if (score1) CU(cudaMemcpyAsync(score1, ctx->d_s1.p, n * 4, cudaMemcpyDeviceToHost, st));
-  if (score2) CU(cudaMemcpyAsync(score2, ctx->d_s2.p, n * 4, cudaMemcpyDeviceToHost, st));
-  if (cells) CU(cudaMemcpyAsync(cells, ctx->d_cells.p, n * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
-  const int64_t used = ctrl[0];
-  if ((int32_t)(ctrl[1] & 0xffffffff)) return ctx->fail(ELECTOR_ECAPACITY, "internal rows buffer too small");
-  if (used > rows_cap) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld < %lld needed", (long long)rows_cap, (long long)used);
-  CU(cudaMemcpyAsync(rows_out, ctx->d_rows.p, used, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  if (n_reads > 0) { CU(ctx->d_tally_out.reserve(n_reads * ELECTOR_TALLY_K * 8)); CU(ctx->d_sums.reserve(ELECTOR_TALLY_K * 8)); }
+  cudaStream_t st = ctx->stream, cin = ctx->copy_in, cout = ctx->copy_out;
+  // ---- all inputs, chunk by chunk, on the H2D stream ----
+  for (size_t k = 0; k < nchunks; ++k) {
+    const int64_t w0 = wcut[k], w1 = wcut[k + 1];
+    CU(cudaMemcpyAsync(ctx->d_ref.as<char>() + ro[w0], ref + ro[w0], ro[w1] - ro[w0], cudaMemcpyHostToDevice, cin));
+    CU(cudaMemcpyAsync(ctx->d_cor.as<char>() + co[w0], cor + co[w0], co[w1] - co[w0], cudaMemcpyHostToDevice, cin));
+    CU(cudaMemcpyAsync(ctx->d_unc.as<char>() + uo[w0], unc + uo[w0], uo[w1] - uo[w0], cudaMemcpyHostToDevice, cin));
+    CU(cudaMemcpyAsync(ctx->d_roff.as<int64_t>() + w0, ro + w0, (w1 - w0 + 1) * 8, cudaMemcpyHostToDevice, cin));
+    CU(cudaMemcpyAsync(ctx->d_coff.as<int64_t>() + w0, co + w0, (w1 - w0 + 1) * 8, cudaMemcpyHostToDevice, cin));
+    CU(cudaMemcpyAsync(ctx->d_uoff.as<int64_t>() + w0, uo + w0, (w1 - w0 + 1) * 8, cudaMemcpyHostToDevice, cin));
+    CU(cudaEventRecord(ctx->chunk_ev[2 * k], cin));
+  }
+  if (n_reads > 0) CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
+  // ---- chunks: kernels on the main stream, results back on the D2H stream ----
+  int64_t used_before = 0;
+  std::vector<int64_t> rf;
+  for (size_t k = 0; k < nchunks; ++k) {
+    const int64_t w0 = wcut[k], w1 = wcut[k + 1], nw = w1 - w0;
+    CU(cudaStreamWaitEvent(st, ctx->chunk_ev[2 * k], 0));
+    int rc = run_device(ctx, nw, ctx->d_ref.as<char>(), ctx->d_roff.as<int64_t>() + w0, ctx->d_cor.as<char>(),
+                        ctx->d_coff.as<int64_t>() + w0, ctx->d_unc.as<char>(), ctx->d_uoff.as<int64_t>() + w0,
+                        ctx->d_rows.as<char>(), rows_cap, ctx->d_rowoff.as<int64_t>() + w0, ctx->d_stride.as<int32_t>() + w0,
+                        ctx->d_nring.as<int32_t>() + w0, ctx->d_s1.as<int32_t>() + w0, ctx->d_s2.as<int32_t>() + w0,
+                        ctx->d_cells.as<int64_t>() + w0, ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2, k > 0);
+    if (rc != ELECTOR_OK) { cudaStreamSynchronize(cin); cudaStreamSynchronize(cout); return rc; }
+    CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    const int64_t r0 = n_reads > 0 ? rcut[k] : 0, r1 = n_reads > 0 ? rcut[k + 1] : 0;
+    if (r1 > r0) {
+      rf.assign(read_first + r0, read_first + r1 + 1);
+      for (int64_t &v : rf) v -= w0;
+      rc = merge_device(ctx, r1 - r0, rf.data(), nw, ctx->d_rows.as<uint8_t>(), 3 * ((ro[w1] - ro[w0]) + (co[w1] - co[w0]) + (uo[w1] - uo[w0])),
+                        ctx->d_rowoff.as<int64_t>() + w0, ctx->d_stride.as<int32_t>() + w0, ctx->d_nring.as<int32_t>() + w0);
+      if (rc == ELECTOR_OK)
+        rc = tally_device(ctx, r1 - r0, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
+                          ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(), ctx->d_tally_out.as<int64_t>() + r0 * ELECTOR_TALLY_K, ctx->merged_cap);
+      if (rc != ELECTOR_OK) { cudaStreamSynchronize(cin); cudaStreamSynchronize(cout); return rc; }
+      tally_sum_kernel<<<std::min<int>(64, (int)((r1 - r0 + 7) / 8)), 256, 0, st>>>(r1 - r0, ctx->d_tally_out.as<int64_t>() + r0 * ELECTOR_TALLY_K,
+                                                                                 ctx->d_sums.as<unsigned long long>());
+      CU(cudaGetLastError());
+      ++ctx->last_launches;
+      CU(cudaEventRecord(ctx->ev1, st));   // the chunk's device time now covers merge + tally too
+    }
+    CU(cudaEventRecord(ctx->chunk_ev[2 * k + 1], st));
+    CU(cudaStreamSynchronize(st));
+    add_kernel_ms(ctx);
+    const int64_t used = ctx->h_totals[4];
+    if ((int32_t)(ctx->h_totals[5] & 0xffffffff) || used > rows_cap) {
+      cudaStreamSynchronize(cin); cudaStreamSynchronize(cout);
+      return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small", (long long)rows_cap);
+    }
+    CU(cudaStreamWaitEvent(cout, ctx->chunk_ev[2 * k + 1], 0));
+    CU(cudaMemcpyAsync(rows_out + used_before, ctx->d_rows.as<char>() + used_before, used - used_before, cudaMemcpyDeviceToHost, cout));
+    CU(cudaMemcpyAsync(row_off + w0, ctx->d_rowoff.as<int64_t>() + w0, nw * 8, cudaMemcpyDeviceToHost, cout));
+    CU(cudaMemcpyAsync(row_stride + w0, ctx->d_stride.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
+    CU(cudaMemcpyAsync(nring + w0, ctx->d_nring.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
+    if (score1) CU(cudaMemcpyAsync(score1 + w0, ctx->d_s1.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
+    if (score2) CU(cudaMemcpyAsync(score2 + w0, ctx->d_s2.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
+    if (cells) CU(cudaMemcpyAsync(cells + w0, ctx->d_cells.as<int64_t>() + w0, nw * 8, cudaMemcpyDeviceToHost, cout));
+    if (r1 > r0)
+      CU(cudaMemcpyAsync(counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.as<int64_t>() + r0 * ELECTOR_TALLY_K,
+                         (r1 - r0) * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, cout));
+    used_before = used;
+  }
+  if (n_reads > 0) {
+    int rc = check_scan_overflow(ctx, n_reads);
+    if (rc != ELECTOR_OK) { cudaStreamSynchronize(cout); return rc; }
+    if (sums_out) {
+      CU(cudaMemcpyAsync(sums_out, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  CU(cudaStreamSynchronize(cout));
   return ELECTOR_OK;
 }
 
@@ -501,6 +619,13 @@ int elector_int32_peak(elector_ctx *ctx, double *tiops_mixed, double *tiops_alu)
   }
   if (tiops_mixed) *tiops_mixed = res[0];
   if (tiops_alu) *tiops_alu = res[1];
+  return ELECTOR_OK;
+}
+
+int elector_last_phase_ms(const elector_ctx *ctx, float *ms_phase1, float *ms_total) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (ms_phase1) *ms_phase1 = ctx->last_ms_phase1;
+  if (ms_total) *ms_total = ctx->last_ms;
   return ELECTOR_OK;
 }
 

@@ -113,7 +113,8 @@ struct PoaArgs {
   uint32_t warp_words;   // scratch words per thread (layout of the segment's maxima)
   int32_t *work_counter;
   // phase 1 -> phase 2
-  uint16_t *p1_nodes;    // P1 node list of window w at [p1_offset(ref_off[w], cor_off[w], w)], n1[w] entries
+  uint16_t *p1_nodes;    // P1 node list of window w at [p1_offset(ref_off[w] - ref_off[0], cor_off[w] - cor_off[0], w)], n1[w] entries
+  int64_t ro0, co0;      // ref_off[0], cor_off[0] of this call (offsets may be absolute positions in a larger buffer)
   int32_t *n1;
   int32_t *key2;         // phase-2 sort bin of the window
   int32_t *hist2;        // phase-2 histogram (filled by phase 1)
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PH1) poa_dp1_kernel(PoaArgs a
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     if (active) {
       int s1, spcode;
-      const int n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro, co, w), s1, spcode);
+      const int n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), s1, spcode);
       const int lu = (int)(a.unc_off[w + 1] - a.unc_off[w]);
       int bin, seg;
       bin2_of(n1, lu, spcode, bin, seg);
@@ -799,7 +800,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PH2) poa_dp2_kernel(PoaArgs a
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     if (active) {
       int s2;
-      nring = c.run_window(a.p1_nodes + p1_offset(ro, co, w), n1, a.unc + uo, lu, s2);
+      nring = c.run_window(a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), n1, a.unc + uo, lu, s2);
       a.nring[w] = nring;
       if (a.score2) a.score2[w] = s2;
       if (a.cells) {

@@ -3,14 +3,15 @@ namespace {
 
 // scan + count on device-resident merged rows; counters land in d_counters
 int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uint8_t *dC, const uint8_t *dU,
-                 const int64_t *d_off, const int32_t *d_len, int64_t *d_counters) {
+                 const int64_t *d_off, const int32_t *d_len, int64_t *d_counters, int64_t total_bytes) {
   if (n_reads == 0) return ELECTOR_OK;
-  CU(ctx->d_tally_scan.reserve((size_t)n_reads * sizeof(ReadScan)));
-  ReadScan *sc = ctx->d_tally_scan.as<ReadScan>();
-  tally_scan_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, ctx->stream>>>(n_reads, dR, dC, dU, d_off, d_len, sc);
-  tally_count_kernel<<<(unsigned)n_reads, 128, 0, ctx->stream>>>(n_reads, dR, dC, dU, d_off, d_len, sc, d_counters);
+  // dot bitmasks: read r's words start at (off[r] >> 5) + r in each of the three planes
+  const int64_t plane_words = (total_bytes >> 5) + n_reads + 2;
+  CU(ctx->d_tally_scan.reserve((size_t)plane_words * 3 * sizeof(uint32_t)));
+  tally_read_kernel<<<(unsigned)n_reads, 128, 0, ctx->stream>>>(n_reads, dR, dC, dU, d_off, d_len, ctx->d_tally_scan.as<uint32_t>(), plane_words,
+                                                               d_counters, ctx->d_ctrl.as<int32_t>() + 3);
   CU(cudaGetLastError());
-  ctx->last_launches += 2;
+  ctx->last_launches += 1;
   return ELECTOR_OK;
 }
 
@@ -27,20 +28,28 @@ int merge_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first,
   CU(cudaMemcpyAsync(ctx->d_readfirst.p, h_read_first, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   read_totals_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_nring, ctx->d_mtot.as<int64_t>());
   scan_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_reads, ctx->d_mtot.as<int64_t>(), ctx->d_moff.as<int64_t>());
-  merge_rows_kernel<<<(unsigned)((n_reads + 3) / 4), 128, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_rows, d_row_off, d_row_stride, d_nring,
-                                                                            ctx->d_moff.as<int64_t>(), ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(),
-                                                                            ctx->d_munc.as<uint8_t>(), ctx->d_mlen.as<int32_t>());
+  CU(ctx->d_wdst.reserve((size_t)n_windows * 8));
+  merge_plan_kernel<<<(unsigned)((n_reads + 3) / 4), 128, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_rows, d_row_off, d_row_stride, d_nring,
+                                                                            ctx->d_moff.as<int64_t>(), ctx->d_wdst.as<int64_t>(), ctx->d_mlen.as<int32_t>());
+  merge_copy_kernel<<<(unsigned)std::min<int64_t>((n_windows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+      n_windows, d_rows, d_row_off, d_row_stride, d_nring, ctx->d_wdst.as<int64_t>(), ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(),
+      ctx->d_munc.as<uint8_t>());
   CU(cudaGetLastError());
-  ctx->last_launches += 3;
+  ctx->last_launches += 4;
+  ctx->merged_cap = cap;
   return ELECTOR_OK;
 }
 
+// d_ctrl[3]: set by tally_scan_kernel when a read has more border gap stretches than ReadScan holds
 int check_scan_overflow(elector_ctx *ctx, int64_t n_reads) {
-  std::vector<ReadScan> h(n_reads);
-  CU(cudaMemcpyAsync(h.data(), ctx->d_tally_scan.p, n_reads * sizeof(ReadScan), cudaMemcpyDeviceToHost, ctx->stream));
+  (void)n_reads;
+  int32_t flag = 0;
+  CU(cudaMemcpyAsync(&flag, ctx->d_ctrl.as<int32_t>() + 3, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  for (int64_t r = 0; r < n_reads; ++r)
-    if (h[r].overflow) return ctx->fail(ELECTOR_EUNSUPPORTED, "read %lld has more than %d gap stretches at its borders", (long long)r, kMaxStretchKeys);
+  if (flag) {
+    cudaMemsetAsync(ctx->d_ctrl.as<int32_t>() + 3, 0, sizeof flag, ctx->stream);
+    return ctx->fail(ELECTOR_EUNSUPPORTED, "a read has more than %d gap stretches at its borders", kMaxStretchKeys);
+  }
   return ELECTOR_OK;
 }
 
@@ -66,7 +75,7 @@ int elector_tally_run(elector_ctx *ctx, int64_t n_reads, const char *row_ref, co
   ctx->last_launches = 0;
   CU(cudaEventRecord(ctx->ev0, st));
   int rc = tally_device(ctx, n_reads, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
-                        ctx->d_moff.as<int64_t>(), nullptr, ctx->d_tally_out.as<int64_t>());
+                        ctx->d_moff.as<int64_t>(), nullptr, ctx->d_tally_out.as<int64_t>(), bytes);
   if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev1, st));
   CU(cudaMemcpyAsync(counters_out, ctx->d_tally_out.p, n_reads * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
@@ -119,12 +128,23 @@ int elector_merge_tally_device(elector_ctx *ctx, int64_t n_reads, const int64_t 
   int rc = merge_device(ctx, n_reads, h_read_first, n_windows, (const uint8_t *)d_rows, rows_bytes, d_row_off, d_row_stride, d_nring);
   if (rc != ELECTOR_OK) return rc;
   rc = tally_device(ctx, n_reads, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
-                    ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(), d_counters_out);
+                    ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(), d_counters_out, ctx->merged_cap);
   if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   rc = check_scan_overflow(ctx, n_reads);
   cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
   return rc;
+}
+
+int elector_tally_sum_device(elector_ctx *ctx, int64_t n_reads, const int64_t *d_counters, int64_t *d_sums) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (n_reads < 0 || (n_reads > 0 && (!d_counters || !d_sums))) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_reads == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  tally_sum_kernel<<<std::min<int>(64, (int)((n_reads + 7) / 8)), 256, 0, ctx->stream>>>(n_reads, d_counters, reinterpret_cast<unsigned long long *>(d_sums));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return ELECTOR_OK;
 }
 
 }  // extern "C"

@@ -1,14 +1,15 @@
 // tally_kernel.cuh -- device merge (Donatello semantics) + per-read tally (computeStats.py).
 //
 //   read_totals_kernel / scan_offsets_kernel  : where each read's merged rows start
-//   merge_rows_kernel  (Donatello.cpp:13-31,50-84): concatenate a read's window MSAs, dropping
-//                       every column whose corrected row is 'n'; one warp per read
-//   tally_scan_kernel  (computeStats.py:61-98,104-189,472-498): the sequential scanners --
-//                       left/right gaps, extension, gap stretches; one thread per read
-//   tally_count_kernel (computeStats.py:291-328,371-440,712-752): per-column classification
-//                       under the "existing corrected positions" mask; one CTA per read,
-//                       warp-shuffle reduction of the counters
-// All three are byte streaming kernels (HBM-bound, 3 bytes per MSA column).
+//   merge_plan_kernel / merge_copy_kernel (Donatello.cpp:13-31,50-84): concatenate a read's window
+//                       MSAs, dropping every column whose corrected row is 'n'; plan = one warp per
+//                       read (destination of every window), copy = one warp per window
+//   tally_read_kernel  one CTA per read: dot bitmasks of the three rows, the sequential scanners of
+//                       computeStats.py (:61-98,104-189,472-498: left/right gaps, extension, gap
+//                       stretches) run on those bitmasks from dot run to dot run, then the
+//                       per-column classification (:291-328,371-440,712-752) under the resulting
+//                       mask with a warp-shuffle reduction of the counters
+// All are byte streaming kernels (HBM-bound, 3 bytes per MSA column).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -73,10 +74,11 @@ __global__ void __launch_bounds__(1024) scan_offsets_kernel(int64_t n, const int
 }
 
 // ---- merge ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) merge_rows_kernel(int64_t n_reads, const int64_t *read_first, const uint8_t *rows,
+// plan: one warp per read; lanes take the read's windows 32 at a time, count the columns each
+// window keeps (corrected row != 'n') and turn them into the window's destination offset.
+__global__ void __launch_bounds__(128) merge_plan_kernel(int64_t n_reads, const int64_t *read_first, const uint8_t *rows,
                                                           const int64_t *row_off, const int32_t *row_stride, const int32_t *nring,
-                                                          const int64_t *m_off, uint8_t *m_ref, uint8_t *m_cor, uint8_t *m_unc,
-                                                          int32_t *m_len) {
+                                                          const int64_t *m_off, int64_t *wdst, int32_t *m_len) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_reads) return;
@@ -85,44 +87,121 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(int64_t n_reads, const 
   int64_t done = 0;
   for (int64_t wb = w0; wb < w1; wb += 32) {
     const int64_t w = wb + lane;
-    int kept = 0, k = 0, st = 0;
-    const uint8_t *src = nullptr;
+    int kept = 0;
     if (w < w1) {
-      k = nring[w]; st = row_stride[w]; src = rows + row_off[w];
-      for (int i = 0; i < k; ++i) kept += (src[st + i] != 'n');
+      const int k = nring[w], st = row_stride[w];
+      const uint32_t *cor = reinterpret_cast<const uint32_t *>(rows + row_off[w] + st);   // rows are 4-byte aligned, padded with 0
+      int dropped = 0;
+      for (int i = 0; i < (k + 3) >> 2; ++i) {
+        const uint32_t x = cor[i] ^ 0x6e6e6e6eu;                                         // 'n' bytes become 0
+        dropped += __popc(~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu));          // exact count of zero bytes
+      }
+      kept = k - dropped;
     }
     int incl = kept;
     for (int d = 1; d < 32; d <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (w < w1) {
-      int64_t o = base + done + incl - kept;
-      for (int i = 0; i < k; ++i) {
-        const uint8_t c = src[st + i];
-        if (c != 'n') { m_ref[o] = src[i]; m_cor[o] = c; m_unc[o] = src[2 * st + i]; ++o; }
-      }
-    }
-    done += total;
+    if (w < w1) wdst[w] = base + done + incl - kept;
+    done += __shfl_sync(0xffffffffu, incl, 31);
   }
   if (lane == 0) m_len[r] = (int32_t)done;
 }
 
-// ---- sequential scanners ---------------------------------------------------------------
-__device__ __forceinline__ int nb_left_gaps(const uint8_t *s, int L) {
-  int gaps = 0, nt = 0, total = 0;
-  for (int i = 0; i < L && nt <= T_THRESH; ++i) {
-    if (s[i] == '.') { ++gaps; nt = 0; }
-    else { if (gaps >= T_THRESH) total = i; gaps = 0; ++nt; }
+// copy: one warp per window, lanes over columns, ballot compaction of the kept columns
+__global__ void __launch_bounds__(256) merge_copy_kernel(int64_t n_windows, const uint8_t *rows, const int64_t *row_off,
+                                                          const int32_t *row_stride, const int32_t *nring, const int64_t *wdst,
+                                                          uint8_t *m_ref, uint8_t *m_cor, uint8_t *m_unc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_windows; w += nwarps) {
+    const int k = nring[w], st = row_stride[w];
+    const uint8_t *src = rows + row_off[w];
+    int64_t o = wdst[w];
+    for (int c0 = 0; c0 < k; c0 += 32) {
+      const int i = c0 + lane;
+      uint8_t c = 'n', a = 0, u = 0;
+      if (i < k) { a = src[i]; c = src[st + i]; u = src[2 * st + i]; }
+      const unsigned keep = __ballot_sync(0xffffffffu, c != 'n');
+      if (c != 'n') {
+        const int64_t d = o + __popc(keep & ((1u << lane) - 1u));
+        m_ref[d] = a; m_cor[d] = c; m_unc[d] = u;
+      }
+      o += __popc(keep);
+    }
+  }
+}
+
+// ---- scanners on dot bitmasks (bit i of word i>>5 = column i is '.'; bits beyond L are 0) ----
+struct BitRow {
+  const uint32_t *m;
+  int L;
+  __device__ __forceinline__ bool bit(int i) const { return (m[i >> 5] >> (i & 31)) & 1u; }
+  // first column >= i that is a dot, or L
+  __device__ int next_set(int i) const {
+    while (i < L) {
+      const uint32_t w = m[i >> 5] >> (i & 31);
+      if (w) return min(L, i + __ffs(w) - 1);
+      i = (i | 31) + 1;
+    }
+    return L;
+  }
+  // length of the run of columns equal to v that starts at i (i < L), going right
+  __device__ int run_fwd(int i, bool v) const {
+    const int s = i;
+    while (i < L) {
+      uint32_t w = m[i >> 5] >> (i & 31);
+      if (v) w = ~w;                       // look for the first column that differs
+      const int room = 32 - (i & 31);
+      const int k = w ? __ffs(w) - 1 : 32;
+      if (k < room) return min(L, i + k) - s;
+      i += room;
+    }
+    return L - s;
+  }
+  // length of the run of columns equal to v that ends at i, going left
+  __device__ int run_bwd(int i, bool v) const {
+    const int s = i;
+    while (i >= 0) {
+      uint32_t w = m[i >> 5] << (31 - (i & 31));   // column i at bit 31
+      if (v) w = ~w;
+      const int room = (i & 31) + 1;
+      const int k = w ? __clz(w) : 32;
+      if (k < room) return s - (i - k);
+      i -= room;
+    }
+    return s + 1;
+  }
+  // dots in [a, b)
+  __device__ int count(int a, int b) const {
+    int n = 0;
+    while (a < b) {
+      const int hi = min(b, (a | 31) + 1);
+      uint32_t w = m[a >> 5] >> (a & 31);
+      const int len = hi - a;
+      if (len < 32) w &= (1u << len) - 1u;
+      n += __popc(w);
+      a = hi;
+    }
+    return n;
+  }
+};
+
+// nbLeftGaps / nbRightGaps (computeStats.py:61-98): dot runs are consumed whole
+__device__ int nb_left_gaps(const BitRow &d) {
+  int gaps = 0, nt = 0, total = 0, i = 0;
+  while (i < d.L && nt <= T_THRESH) {
+    if (d.bit(i)) { const int k = d.run_fwd(i, true); gaps += k; nt = 0; i += k; }
+    else { if (gaps >= T_THRESH) total = i; gaps = 0; ++nt; ++i; }
   }
   return total;
 }
-__device__ __forceinline__ int nb_right_gaps(const uint8_t *s, int L) {
-  int gaps = 0, nt = 0, total = 0;
-  for (int i = L - 1; i >= 0 && nt <= T_THRESH; --i) {
-    if (s[i] == '.') { ++gaps; nt = 0; }
-    else { if (gaps >= T_THRESH) total = L - i; gaps = 0; ++nt; }
+__device__ int nb_right_gaps(const BitRow &d) {
+  int gaps = 0, nt = 0, total = 0, i = d.L - 1;
+  while (i >= 0 && nt <= T_THRESH) {
+    if (d.bit(i)) { const int k = d.run_bwd(i, true); gaps += k; nt = 0; i -= k; }
+    else { if (gaps >= T_THRESH) total = d.L - i; gaps = 0; ++nt; --i; }
   }
   return total;
 }
@@ -161,72 +240,121 @@ struct StretchState {  // streaming form of findGapStretches' borders / merge / 
   }
 };
 
-__global__ void __launch_bounds__(128) tally_scan_kernel(int64_t n_reads, const uint8_t *R, const uint8_t *C, const uint8_t *U,
-                                                          const int64_t *off, const int32_t *len, ReadScan *out) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  const int L = len ? len[r] : (int)(off[r + 1] - off[r]);
-  const uint8_t *rr = R + off[r], *cc = C + off[r], *uu = U + off[r];
-  ReadScan o;
-  o.gl = o.gr = 0; o.ext = -1; o.nkeys = 0; o.overflow = 0;
-  for (int k = 0; k < kMaxStretchKeys; ++k) o.key_a[k] = o.key_b[k] = 0;
-  if (L > 10) {
-    o.gl = min(nb_left_gaps(rr, L), nb_left_gaps(uu, L));
-    o.gr = min(nb_right_gaps(rr, L), nb_right_gaps(uu, L));
-    int ext = -1;
-    if (o.gl >= T_THRESH2) { int dots = 0; for (int i = 0; i < o.gl; ++i) dots += cc[i] == '.'; ext = (ext < 0 ? 0 : ext) + o.gl - dots; }
-    if (o.gr >= T_THRESH2) { int dots = 0; for (int i = L - o.gr + 1; i < L; ++i) dots += cc[i] == '.'; ext = (ext < 0 ? 0 : ext) + o.gr - dots; }
-    o.ext = ext;
-    // findGapStretches scan (:111-142), slots consumed as soon as they are final
-    StretchState s;
-    s.L = L; s.has0 = s.end0 = s.nkeys = s.overflow = s.pend = s.pa = s.pb = s.merge = 0;
-    int nslots = 0, cg = 0, cr = 0, ca = 0, cb = 0;
-    bool have_cur = false, cur_set = false, prev_dot = false;
-    for (int pos = 0; pos < L; ++pos) {
-      const bool cd = cc[pos] == '.', rd = rr[pos] == '.';
-      if (pos == 0) { cg += cd; cr += rd; }
-      else if (prev_dot) {
-        if (cd) cg = cg > 0 ? cg + 1 : 2;
-        if (rd) cr = cr > 0 ? cr + 1 : 2;
+// findGapStretches (computeStats.py:104-189) restated over the RUNS of dots of the corrected row.
+// Per column the reference keeps cg (corrected-gap run: 0 on a run's first column unless it is
+// column 0, then the run length so far) and cr (reference-gap counter that only advances while the
+// previous corrected column was a gap and resets on every reference base).  Only runs that reach
+// cg >= 5 can mark columns, a run with cg > 0 closes the current slot when a base follows it, and cr
+// at any column follows from the reference-gap run it sits in -- so the scan jumps from run to run.
+__device__ void find_gap_stretches(const BitRow &dc, const BitRow &dr, ReadScan &o) {
+  const int L = dc.L;
+  StretchState s;
+  s.L = L; s.has0 = s.end0 = s.nkeys = s.overflow = s.pend = s.pa = s.pb = s.merge = 0;
+  int nslots = 0, ca = 0, cb = 0;
+  bool have_cur = false, cur_set = false;
+  int i = 0;
+  while (i < L) {
+    const int st = dc.next_set(i);
+    if (st >= L) break;
+    const int len = dc.run_fwd(st, true), e = st + len - 1;
+    const bool counts = st == 0 || len >= 2;            // cg > 0 when the run ends
+    if (counts && len >= T_THRESH) {
+      // cr after column st (the run's first column never advances cr: its predecessor is a base)
+      int cr = 0;
+      if (dr.bit(st)) {
+        const int sr = st - dr.run_bwd(st, true) + 1;    // start of the reference-gap run holding st
+        const int k = dc.count(max(sr, 1) - 1, st);
+        cr = sr == 0 ? 1 + k : (k == 0 ? 0 : k + 1);
       }
-      if (!cd) {
-        if (cg > 0) {
-          if (have_cur && cur_set) s.finalize(ca, cb, true);
-          have_cur = true; cur_set = false; ++nslots;
+      int first = -1, last = -1;
+      int p = st + 1;
+      while (p <= e) {
+        const int wend = min(e, p | 31);
+        uint32_t rb = dr.m[p >> 5] >> (p & 31);
+        const int n = wend - p + 1;
+        if (n < 32) rb &= (1u << n) - 1u;
+        if (rb == 0) {                                    // reference bases only: cr = 0 on all of them
+          cr = 0;
+          const int lo = max(p, st + T_THRESH - 1);
+          if (lo <= wend) { if (first < 0) first = lo; last = wend; }
+        } else {
+          for (int q = p; q <= wend; ++q) {
+            if (dr.bit(q)) cr = cr > 0 ? cr + 1 : 2; else cr = 0;
+            if (q >= st + T_THRESH - 1 && cr < T_THRESH2) { if (first < 0) first = q; last = q; }
+          }
         }
-        cg = 0;
+        p = wend + 1;
       }
-      if (!rd) cr = 0;
-      if (cg >= T_THRESH && cr < T_THRESH2) {
-        if (nslots == 0) { have_cur = true; cur_set = true; nslots = 1; ca = pos - T_THRESH + 1; cb = pos; }
-        else { if (!cur_set) { cur_set = true; ca = pos - T_THRESH + 1; } cb = pos; }
+      if (first >= 0) {
+        if (nslots == 0) { have_cur = true; cur_set = true; nslots = 1; ca = first - T_THRESH + 1; cb = last; }
+        else { if (!cur_set) { cur_set = true; ca = first - T_THRESH + 1; } cb = last; }
       }
-      prev_dot = cd;
     }
-    if (have_cur && cur_set) s.finalize(ca, cb, nslots > 1);
-    if (s.pend && !s.merge) s.emit2(s.pa, s.pb);
-    if (s.has0) { o.key_a[o.nkeys] = 0; o.key_b[o.nkeys] = s.end0; ++o.nkeys; }
-    for (int k = 0; k < s.nkeys && o.nkeys < kMaxStretchKeys; ++k) { o.key_a[o.nkeys] = s.key[k]; o.key_b[o.nkeys] = L - 1; ++o.nkeys; }
-    o.overflow = s.overflow || (s.has0 + s.nkeys > kMaxStretchKeys);
+    if (counts && e + 1 < L) {                            // a base follows: the run closes the current slot
+      if (have_cur && cur_set) s.finalize(ca, cb, true);
+      have_cur = true; cur_set = false; ++nslots;
+    }
+    i = e + 1;
   }
-  out[r] = o;
+  if (have_cur && cur_set) s.finalize(ca, cb, nslots > 1);
+  if (s.pend && !s.merge) s.emit2(s.pa, s.pb);
+  if (s.has0) { o.key_a[o.nkeys] = 0; o.key_b[o.nkeys] = s.end0; ++o.nkeys; }
+  for (int k = 0; k < s.nkeys && o.nkeys < kMaxStretchKeys; ++k) { o.key_a[o.nkeys] = s.key[k]; o.key_b[o.nkeys] = L - 1; ++o.nkeys; }
+  o.overflow = s.overflow || (s.has0 + s.nkeys > kMaxStretchKeys);
 }
 
-// ---- per-column counters ---------------------------------------------------------------
+// ---- the per-read tally: one CTA per read ------------------------------------------------------
+//   A  all threads: one pass over the three rows -> dot bitmasks (global scratch, 3 bits per column)
+//   B  thread 0: the sequential scanners of computeStats.py on the bitmasks (run to run, not column
+//      to column): left / right gaps, extension, gap stretches -> the column mask
+//   C  all threads: second pass, per-column classification under the mask (computeStats.py:291-328,
+//      371-440, 712-752), warp-shuffle + shared-memory reduction of the counters
 constexpr int kNAcc = 19;  // accumulators reduced per read (see below)
 
-__global__ void __launch_bounds__(128) tally_count_kernel(int64_t n_reads, const uint8_t *R, const uint8_t *C, const uint8_t *U,
-                                                           const int64_t *off, const int32_t *len, const ReadScan *scan,
-                                                           int64_t *counters) {
+__global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const uint8_t *R, const uint8_t *C, const uint8_t *U,
+                                                          const int64_t *off, const int32_t *len, uint32_t *bits, int64_t plane_words,
+                                                          int64_t *counters, int32_t *overflow_flag) {
   const int64_t r = blockIdx.x;
   if (r >= n_reads) return;
   const int L = len ? len[r] : (int)(off[r + 1] - off[r]);
   const uint8_t *rr = R + off[r], *cc = C + off[r], *uu = U + off[r];
-  const ReadScan sc = scan[r];
-  int acc[kNAcc];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool assessed = L > 10;
+  __shared__ ReadScan sc;
+  __shared__ int sm[4][kNAcc];
+  uint32_t *br = bits + (off[r] >> 5) + r, *bc = br + plane_words, *bu = bc + plane_words;
+  if (assessed) {
+    for (int base = wid * 32; base < L; base += 128) {   // A
+      const int i = base + lane;
+      const bool in = i < L;
+      const unsigned mr = __ballot_sync(0xffffffffu, in && rr[i] == '.');
+      const unsigned mc = __ballot_sync(0xffffffffu, in && cc[i] == '.');
+      const unsigned mu = __ballot_sync(0xffffffffu, in && uu[i] == '.');
+      if (lane == 0) { br[base >> 5] = mr; bc[base >> 5] = mc; bu[base >> 5] = mu; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                                // B
+    ReadScan o;
+    o.gl = o.gr = 0; o.ext = -1; o.nkeys = 0; o.overflow = 0;
+    for (int k = 0; k < kMaxStretchKeys; ++k) o.key_a[k] = o.key_b[k] = 0;
+    if (assessed) {
+      const BitRow dr{br, L}, dc{bc, L}, du{bu, L};
+      o.gl = min(nb_left_gaps(dr), nb_left_gaps(du));
+      o.gr = min(nb_right_gaps(dr), nb_right_gaps(du));
+      int ext = -1;
+      if (o.gl >= T_THRESH2) ext = (ext < 0 ? 0 : ext) + o.gl - dc.count(0, o.gl);
+      if (o.gr >= T_THRESH2) ext = (ext < 0 ? 0 : ext) + o.gr - dc.count(L - o.gr + 1, L);
+      o.ext = ext;
+      find_gap_stretches(dc, dr, o);
+      if (o.overflow) atomicExch(overflow_flag, 1);
+    }
+    sc = o;
+  }
+  __syncthreads();
+  int acc[kNAcc];                                        // C
 #pragma unroll
   for (int k = 0; k < kNAcc; ++k) acc[k] = 0;
-  const bool assessed = L > 10;
   const int lmask = sc.gl >= T_THRESH ? sc.gl : 0;                 // columns [0, gl) masked
   const int rmask = sc.gr >= T_THRESH ? L - sc.gr : L - 1;         // columns (L-gr, L-1] masked
   if (assessed) {
@@ -253,8 +381,6 @@ __global__ void __launch_bounds__(128) tally_count_kernel(int64_t n_reads, const
       }
     }
   }
-  __shared__ int sm[4][kNAcc];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < kNAcc; ++k) {
     int v = acc[k];
@@ -282,6 +408,22 @@ __global__ void __launch_bounds__(128) tally_count_kernel(int64_t n_reads, const
       o[ELECTOR_T_ASSESSED] = 1;
     }
   }
+}
+
+// ---- global counters: sums[k] += sum over reads of counters[r][k] (the "final counter reduction") ----
+__global__ void __launch_bounds__(256) tally_sum_kernel(int64_t n_reads, const int64_t *counters, unsigned long long *sums) {
+  __shared__ unsigned long long part[ELECTOR_TALLY_K];
+  if (threadIdx.x < ELECTOR_TALLY_K) part[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t total = n_reads * ELECTOR_TALLY_K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ELECTOR_TALLY_K);
+    const int64_t v = counters[i];
+    // "extended" is -1 for reads that were not extended: only extended reads count
+    if (k != ELECTOR_T_EXTENDED || v >= 0) atomicAdd(&part[k], (unsigned long long)v);
+  }
+  __syncthreads();
+  if (threadIdx.x < ELECTOR_TALLY_K && part[threadIdx.x]) atomicAdd(&sums[threadIdx.x], part[threadIdx.x]);
 }
 
 }  // namespace elector

@@ -53,6 +53,12 @@ def load_library():
     lib.elector_merge_run.restype = c.c_int
     lib.elector_merge_tally_device.argtypes = [vp, c.c_int64, vp, c.c_int64, vp, c.c_int64, vp, vp, vp, vp]
     lib.elector_merge_tally_device.restype = c.c_int
+    lib.elector_pipeline_run.argtypes = [vp, c.c_int64, vp, vp, vp, vp, vp, vp, c.c_int64, vp, vp, c.c_int64] + [vp] * 8
+    lib.elector_pipeline_run.restype = c.c_int
+    lib.elector_tally_sum_device.argtypes = [vp, c.c_int64, vp, vp]
+    lib.elector_tally_sum_device.restype = c.c_int
+    lib.elector_last_phase_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_float)]
+    lib.elector_last_phase_ms.restype = c.c_int
     lib.elector_last_kernel_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_int)]
     lib.elector_last_kernel_ms.restype = c.c_int
     lib.elector_event_record.argtypes = [vp, c.c_int]

@@ -105,6 +105,24 @@ class PoaContext:
         u, uo = windows_to_csr(uncs)
         return self.run_csr(r, ro, c, co, u, uo)
 
+    def pipeline_csr(self, ref, ref_off, cor, cor_off, unc, unc_off, read_first):
+        """alignment.py's Pool(fpoa) + Donatello + the integer part of computeStats in one call
+        (elector_pipeline_run).  Returns (PoaResult, counters int64[n_reads, K], sums int64[K])."""
+        n = len(ref_off) - 1
+        ref_off, cor_off, unc_off, read_first = (np.ascontiguousarray(o, dtype=np.int64) for o in (ref_off, cor_off, unc_off, read_first))
+        ref, cor, unc = (np.ascontiguousarray(s, dtype=np.uint8) for s in (ref, cor, unc))
+        n_reads = len(read_first) - 1
+        bound = self._lib.elector_poa_rows_bound(n, _p(ref_off), _p(cor_off), _p(unc_off)) if n else 0
+        res = PoaResult(np.empty(max(bound, 1), dtype=np.uint8), np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.int32),
+                        np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int64))
+        counters = np.zeros((n_reads, len(TALLY_FIELDS)), dtype=np.int64)
+        sums = np.zeros(len(TALLY_FIELDS), dtype=np.int64)
+        self._check(self._lib.elector_pipeline_run(self._ctx, n, _p(ref), _p(ref_off), _p(cor), _p(cor_off), _p(unc), _p(unc_off),
+                                                   n_reads, _p(read_first), _p(res.rows), len(res.rows), _p(res.row_off),
+                                                   _p(res.row_stride), _p(res.nring), _p(res.score1), _p(res.score2), _p(res.cells),
+                                                   _p(counters), _p(sums)))
+        return res, counters, sums
+
     def files(self, ref_fasta, cor_fasta, unc_fasta, pir_out, print_perm=False):
         """The body of one `poa` process (main.c:241-287)."""
         self._check(self._lib.elector_poa_files(self._ctx, ref_fasta.encode(), cor_fasta.encode(), unc_fasta.encode(),

@@ -133,6 +133,29 @@ int elector_merge_tally_device(elector_ctx *ctx, int64_t n_reads, const int64_t 
                                const int64_t *d_row_off, const int32_t *d_row_stride,
                                const int32_t *d_nring, int64_t *d_counters_out);
 
+/* Replaces: one round of elector/alignment.py:98-129 plus the integer part of
+ * computeStats.py for the windows of n_reads reads -- Pool(fpoa) (main.c:265-284 per window),
+ * Donatello (Donatello.cpp:50-84) and the per-read tally (computeStats.py:371-498) -- as ONE
+ * call on host buffers.  Windows read_first[r] .. read_first[r+1]-1 belong to read r.  The work
+ * is cut into chunks of whole reads; the host->device copies of all chunks are queued up
+ * front and a chunk's results return while the next chunk computes.  Outputs as in
+ * elector_poa_run plus counters_out[r*ELECTOR_TALLY_K + k] and sums_out[k] = sum over reads
+ * (k = ELECTOR_T_EXTENDED sums the extended bases of extended reads only).  With n_reads == 0
+ * (read_first, counters_out, sums_out NULL) only the alignment runs. */
+int elector_pipeline_run(elector_ctx *ctx, int64_t n_windows,
+                         const char *ref, const int64_t *ref_off,
+                         const char *cor, const int64_t *cor_off,
+                         const char *unc, const int64_t *unc_off,
+                         int64_t n_reads, const int64_t *read_first,
+                         char *rows_out, int64_t rows_cap, int64_t *row_off, int32_t *row_stride,
+                         int32_t *nring, int32_t *score1, int32_t *score2, int64_t *cells,
+                         int64_t *counters_out, int64_t *sums_out);
+
+/* Global counters on the device: d_sums[k] += sum over reads of d_counters[r*ELECTOR_TALLY_K+k]
+ * (ELECTOR_T_EXTENDED: extended reads only).  d_sums is ELECTOR_TALLY_K int64 the caller zeroes;
+ * with one rank per GPU this vector is what the final all-reduce carries. */
+int elector_tally_sum_device(elector_ctx *ctx, int64_t n_reads, const int64_t *d_counters, int64_t *d_sums);
+
 /* Device-side timing for callers (bench.py): which = 0 records the start event, 1 the stop
  * event, both on the context's launching stream; elapsed returns the milliseconds between
  * them after synchronising on the stop event. */
@@ -147,6 +170,10 @@ int elector_int32_peak(elector_ctx *ctx, double *tiops_mixed, double *tiops_alu_
 /* Timing of the kernels launched by the last run on this context, measured with CUDA
  * events on the launching stream: total ms and number of kernel launches. */
 int elector_last_kernel_ms(const elector_ctx *ctx, float *ms, int *launches);
+
+/* Split of that time for the last alignment run: ms_phase1 = sort 1 + the DP1-phase kernels
+ * (poa_dp1_kernel), ms_total - ms_phase1 = sort 2 + the DP2-phase kernels (poa_dp2_kernel). */
+int elector_last_phase_ms(const elector_ctx *ctx, float *ms_phase1, float *ms_total);
 
 #ifdef __cplusplus
 }

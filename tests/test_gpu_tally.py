@@ -125,3 +125,41 @@ def test_device_chain_poa_merge_tally_vs_oracle():
         R, C, U = ("".join(s[i] for i in keep) for s in (R, C, U))
         exp = to.tally_read(R, C, U)
         assert [int(v) for v in got[r]] == [exp[k] for k in TALLY_FIELDS], r
+
+
+def test_pipeline_call_equals_oracle_chain():
+    """elector_pipeline_run (host buffers, chunked, copies overlapped) on a multi-chunk workload equals
+    oracle POA -> oracle merge -> oracle tally read by read; the sums equal the column sums"""
+    import elector_b200
+    import workloads
+    from elector_b200 import TALLY_FIELDS
+    from oracle import oracle, tally_oracle as to
+    wl = workloads.make_windows(2, 900)            # ~250k windows: several chunks; trimmed / split reads
+    with elector_b200.PoaContext(0) as c:
+        res, counters, sums = c.pipeline_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"], wl["read_first"])
+        res2 = c.run_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"])
+    n, rf = len(wl["ref_off"]) - 1, wl["read_first"]
+    assert np.array_equal(res.nring, res2.nring) and np.array_equal(res.score1, res2.score1) and np.array_equal(res.score2, res2.score2)
+    ext = TALLY_FIELDS.index("extended")
+    exp_sums = counters.sum(axis=0)
+    exp_sums[ext] = counters[:, ext][counters[:, ext] >= 0].sum()
+    assert np.array_equal(sums, exp_sums)
+    k_reads = 60
+    k = int(rf[k_reads])
+    o = oracle.batch(wl["ref"], wl["ref_off"][:k + 1], wl["cor"], wl["cor_off"][:k + 1], wl["unc"], wl["unc_off"][:k + 1], nthreads=os.cpu_count() or 1)
+    for r in list(range(k_reads)):
+        rows = [oracle.window_rows(o, w) for w in range(rf[r], rf[r + 1])]
+        for w in range(rf[r], rf[r + 1]):
+            assert res.window_rows(w) == rows[w - rf[r]]
+        R = "".join(x[0] for x in rows); C = "".join(x[1] for x in rows); U = "".join(x[2] for x in rows)
+        keep = [i for i, ch in enumerate(C) if ch != "n"]
+        R, C, U = ("".join(s[i] for i in keep) for s in (R, C, U))
+        exp = to.tally_read(R, C, U)
+        assert [int(v) for v in counters[r]] == [exp[f] for f in TALLY_FIELDS], r
+    # the last read of the call (last chunk) against the oracle as well
+    r = len(rf) - 2
+    w0, w1 = int(rf[r]), int(rf[r + 1])
+    sub = workloads.slice_windows(wl, r, r + 1)
+    o = oracle.batch(sub["ref"], sub["ref_off"], sub["cor"], sub["cor_off"], sub["unc"], sub["unc_off"], nthreads=1)
+    for w in range(w0, w1):
+        assert res.window_rows(w) == oracle.window_rows(o, w - w0)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Profiling driver (run under ncu): N plain steps of the hot path through the host C-ABI on a
 cached workload; no torch, no subprocesses, so the profiler only sees our kernels.
-  python tools/profile_step.py [reads] [steps] [config]"""
+  python tools/profile_step.py [reads] [steps] [config] [poa|pipeline]"""
 import os
 import sys
 
@@ -12,9 +12,13 @@ import workloads  # noqa: E402
 reads = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+mode = sys.argv[4] if len(sys.argv) > 4 else "poa"   # "poa": alignment only; "pipeline": + merge + tally (elector_pipeline_run)
 wl = workloads.make_windows(cfg, reads)
 with elector_b200.PoaContext(0) as ctx:
     for _ in range(steps):
-        res = ctx.run_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"])
+        if mode == "pipeline":
+            res, counters, sums = ctx.pipeline_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"], wl["read_first"])
+        else:
+            res = ctx.run_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"])
         ms, k = ctx.last_kernel_ms()
         print("step: %d windows, %d launches, %.3f ms kernels, %.1f GCUPS" % (len(res.nring), k, ms, res.cells.sum() / ms / 1e6))
