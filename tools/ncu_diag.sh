@@ -1,16 +1,15 @@
 #!/bin/bash
-# diagnostics: why does ncu segfault on the GPU box?
+# full ncu capture of the DP kernels through the C `poa` shim (no Python in the profiled process:
+# ncu's multi-pass replay segfaults inside the interpreter on this image)
 set +e
-exec > gpurun_out/ncu_diag.log 2>&1
-echo "== env"; which ncu python; ncu --version | tail -1; echo HOME=$HOME TMPDIR=$TMPDIR; ls -ld /tmp /tmp/nsight* 2>&1; df -h /tmp | tail -1; ulimit -a | head -20
-echo "== 1 torch tiny"
-ncu --metrics gpu__time_duration.sum -c 2 python -c "import torch; x=torch.zeros(10,device='cuda'); x+=1; torch.cuda.synchronize(); print('ok')"; echo rc=$?
-echo "== 2 torch tiny clock-control none"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2 python -c "import torch; x=torch.zeros(10,device='cuda'); x+=1; torch.cuda.synchronize(); print('ok')"; echo rc=$?
-echo "== 3 profile_step 100 reads"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 5 python tools/profile_step.py 100 1; echo rc=$?
-echo "== 4 csv log-file"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 5 --csv --log-file gpurun_out/diag4.csv python tools/profile_step.py 100 1; echo rc=$?
-echo "== 5 absolute python"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 5 $(readlink -f $(which python)) tools/profile_step.py 100 1; echo rc=$?
-echo "== dmesg"; dmesg 2>/dev/null | tail -5
+O=gpurun_out
+TAG=${1:-r1c}
+READS=${2:-2000}
+mkdir -p $O
+exec > $O/${TAG}_ncu.log 2>&1
+python tools/dump_fasta.py $READS 1 /tmp/prof
+python -c "import elector_b200; elector_b200.write_default_matrix('/tmp/blosum80.mat')"
+CMD="elector_b200/bin/poa -pir /tmp/prof.pir -corrected_reads_fasta /tmp/prof.cor.fa -reference_reads_fasta /tmp/prof.ref.fa -uncorrected_reads_fasta /tmp/prof.unc.fa -pathMatrix /tmp/blosum80.mat"
+$CMD > /dev/null; echo plain rc=$?
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:poa_dp -c 10 -o $O/${TAG}_full -f $CMD > /dev/null; echo rc=$?
+ls -la $O
