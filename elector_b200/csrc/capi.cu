@@ -13,6 +13,7 @@
 #include "../../include/elector_poa.h"
 #include "host_io.hpp"
 #include "poa_kernel.cuh"
+#include "poa_packed.cuh"
 #include "bin_kernel.cuh"
 #include "host_setup.hpp"
 #include "tally_kernel.cuh"
@@ -51,7 +52,7 @@ struct elector_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int resident_ph1 = 0, resident_ph2 = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0;  // POA kernel CTAs (one warp each) resident per SM
   int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
@@ -99,24 +100,31 @@ int check_scan_overflow(elector_ctx *ctx, int64_t n_reads);
 const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..19] phase-1 and [20..35] phase-2 work counters
 const int kSideStreams = 3;
 
+#ifndef EL_MIN_WARPS_PH1P
+#define EL_MIN_WARPS_PH1P 32  // packed DP1: register cap 64 (32 one-warp CTAs per SM is the hardware limit)
+#endif
+
+// packed = the segment runs the 16-bit packed kernel (poa_packed.cuh)
 template <bool GS>
-cudaError_t launch_phase(int phase, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
-  if (phase == 1) poa_dp1_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
-  else poa_dp2_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
+cudaError_t launch_phase(int phase, bool packed, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
+  if (phase == 1) {
+    if (packed) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
+    else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
+  } else poa_dp2_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
   return cudaGetLastError();
 }
 
 template <bool GS>
-void resident_warps_per_sm(int &ph1, int &ph2) {
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1, poa_dp1_kernel<GS>, 32, 0);
+void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p) {
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1, poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2, poa_dp2_kernel<GS>, 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1p, poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P>, 32, 0);
 }
 
-struct SegPlan { int seg, grid; size_t warp_words, scratch_off; };
+struct SegPlan { int seg, grid; size_t warp_words, scratch_off; bool packed; };
 
 // grid and scratch of every non-empty segment of one phase
 int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<SegPlan> &plan, size_t &scratch_words) {
-  const int resident = std::max(1, phase == 1 ? ctx->resident_ph1 : ctx->resident_ph2) * ctx->sm_count;
   const size_t budget_words = ((size_t)24 << 30) / 4;
   plan.clear();
   scratch_words = 0;
@@ -125,9 +133,13 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     if (si.count <= 0) continue;
     const int m0 = bt.seg_max[s * 4], m1 = bt.seg_max[s * 4 + 1];
     size_t total;
-    if (phase == 1) { Layout1 L; make_layout1(L, m0, m1); total = L.total; }
-    else { Layout2 L; make_layout2(L, m0, m1); total = L.total; }
     SegPlan p;
+    // 16-bit packed kernel when the matrix allows it and no score of the segment can leave 16 bits
+    p.packed = phase == 1 && ctx->sc.packed_ok && (int64_t)ctx->sc.maxabs * (m0 + m1 + 4) <= kPackedSpan;
+    if (p.packed) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; }
+    else if (phase == 1) { Layout1 L; make_layout1(L, m0, m1); total = L.total; }
+    else { Layout2 L; make_layout2(L, m0, m1); total = L.total; }
+    const int resident = std::max(1, p.packed ? ctx->resident_ph1p : phase == 1 ? ctx->resident_ph1 : ctx->resident_ph2) * ctx->sm_count;
     p.seg = s;
     p.warp_words = total;
     p.grid = (int)std::min<int64_t>(resident, ((int64_t)si.count + 31) / 32);
@@ -166,8 +178,8 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
     a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
     a.warp_words = (uint32_t)p.warp_words;
     a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + (phase == 1 ? 0 : 16) + p.seg;
-    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
-                                              : launch_phase<false>(phase, ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
+    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.packed, ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
+                                              : launch_phase<false>(phase, p.packed, ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
   }
@@ -326,8 +338,8 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
-  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2);
-  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2);
+  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p);
+  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p);
   if (ctx->resident_ph1 < 1 || ctx->resident_ph2 < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;

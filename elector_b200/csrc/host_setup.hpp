@@ -17,6 +17,7 @@ struct ScoringSetup {
   SymbolTables tab;
   int match = 0, mismatch = 0, open = 0, ext = 0, maxabs = 0;
   bool generic_sub = false;
+  bool packed_ok = false;  // the 16-bit packed kernels (poa_packed.cuh) are exact for this matrix
   std::string error;
 
   bool fail(const char *fmt, int a = 0, int b = 0, int c = 0) {
@@ -69,6 +70,15 @@ struct ScoringSetup {
     generic_sub = !uniform;
     match = dval;
     mismatch = have_o ? oval : dval;
+    // Packed class (poa_packed.cuh): match 0, mismatch in [-16, -1] (min.u16x2 of the letter difference), open >= ext > 0,
+    // and every score a multiple of q >= open - ext.  Then "a match beats the gap" implies M - gap >= open - ext, which
+    // makes s - pen(move) == max(M - open, gap - ext): one packed add-max instead of a select on the move.
+    {
+      auto gcd = [](int a, int b) { a = std::abs(a); b = std::abs(b); while (b) { const int t = a % b; a = b; b = t; } return a; };
+      const int q = gcd(gcd(mismatch, open), ext);
+      packed_ok = uniform && match == 0 && mismatch < 0 && mismatch >= -16 && ext > 0 && open >= ext && open - ext <= q;
+      if (const char *e = getenv("ELECTOR_NO_PACKED")) if (e[0] == '1') packed_ok = false;
+    }
     return true;
   }
 };

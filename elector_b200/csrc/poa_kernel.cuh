@@ -264,9 +264,59 @@ struct LaneScratch {
   }
 };
 
+// fuse 1 (lpo.c:413-463,602-656 for two linear sequences): P1's node list, 16 bits per node,
+// to out[] (px = x2y field of node 0, step words between nodes); returns len(P1) and the phase-2 sort code of the window: 0 when ref and cor are
+// identical (P1 is linear), else 1 + 3*min(pos/2, 31) + type of the first node that does not
+// carry both letters (type 0: ref only, 1: cor only followed by its ref partner = a
+// substitution, 2: cor only = an insertion).
+EL_HDN inline int fuse1(const LaneScratch &scr, uint32_t o_ref, uint32_t o_cor, const uint32_t *px, ptrdiff_t step, int lr, int lc,
+                      uint16_t *out, int &spcode) {
+  int n = 0, iy = 0, sp = -1, sptype = 0;
+  uint64_t *out4 = reinterpret_cast<uint64_t *>(out);   // 4 nodes per store (the list is 8-byte aligned)
+  uint64_t acc = 0;
+  auto put = [&](uint32_t v) {
+    acc |= (uint64_t)(v & 0xffffu) << (16 * (n & 3));
+    if ((n & 3) == 3) { out4[n >> 2] = acc; acc = 0; }
+    ++n;
+  };
+  auto cor_only = [&](int iy_) {
+    put((uint32_t)scr.code_at(o_cor, iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
+  };
+  int q0 = (int)px[0], q1 = lr > 1 ? (int)px[step] : -1;
+  uint32_t xw = 0;
+  for (int ix = 0; ix < lr; ++ix) {
+    const int q = q0;
+    q0 = q1;
+    q1 = ix + 2 < lr ? (int)px[(ptrdiff_t)(ix + 2) * step] : -1;
+    if ((ix & 3) == 0) xw = scr.w(o_ref + (ix >> 2));
+    const int xl = xw & 0xff; xw >>= 8;
+    if (q >= 0)
+      while (iy < q) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
+    uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
+    if (q >= 0 && iy < lc) {
+      const int yl = scr.code_at(o_cor, iy);
+      const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
+      if (yl == xl) fl |= yf;  // identical letters share the node
+      else {                   // own node just before x, same ring
+        if (sp < 0) { sp = n; sptype = 1; }
+        put((uint32_t)yl | yf); fl |= NF_SAMERING;
+      }
+      ++iy;
+    } else if (sp < 0) { sp = n; sptype = 0; }
+    put((uint32_t)xl | fl);
+  }
+  while (iy < lc) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
+  if (n & 3) out4[n >> 2] = acc;
+  spcode = sp < 0 ? 0 : 1 + 3 * ((sp >> 1) < 31 ? (sp >> 1) : 31) + sptype;
+  return n;
+}
+
 // =============================== phase 1 ========================================================
 template <bool GENERIC_SUB>
 struct Phase1 {
+  typedef Layout1 Layout;
+  static constexpr bool kGenericSub = GENERIC_SUB;
+  static EL_HD void make_layout(Layout1 &L, int LR, int LC) { make_layout1(L, LR, LC); }
   LaneScratch scr;
   Scoring sc;
   const Layout1 *Lp;  // layout of the current group (shared memory on the device)
@@ -341,60 +391,12 @@ struct Phase1 {
     }
   }
 
-  // fuse 1 (lpo.c:413-463,602-656 for two linear sequences): P1's node list, 16 bits per node,
-  // to out[]; returns len(P1) and the phase-2 sort code of the window: 0 when ref and cor are
-  // identical (P1 is linear), else 1 + 3*min(pos/2, 31) + type of the first node that does not
-  // carry both letters (type 0: ref only, 1: cor only followed by its ref partner = a
-  // substitution, 2: cor only = an insertion).
-  EL_HDN int fuse(int lr, int lc, uint16_t *out, int &spcode) const {
-    int n = 0, iy = 0, sp = -1, sptype = 0;
-    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
-    const uint32_t *px = scr.at(Lp->o_nodes) + R1_X2Y * 32;
-    uint64_t *out4 = reinterpret_cast<uint64_t *>(out);   // 4 nodes per store (the list is 8-byte aligned)
-    uint64_t acc = 0;
-    auto put = [&](uint32_t v) {
-      acc |= (uint64_t)(v & 0xffffu) << (16 * (n & 3));
-      if ((n & 3) == 3) { out4[n >> 2] = acc; acc = 0; }
-      ++n;
-    };
-    auto cor_only = [&](int iy_) {
-      put((uint32_t)scr.code_at(Lp->o_cor, iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
-    };
-    int q0 = (int)px[0], q1 = lr > 1 ? (int)px[step] : -1;
-    uint32_t xw = 0;
-    for (int ix = 0; ix < lr; ++ix) {
-      const int q = q0;
-      q0 = q1;
-      q1 = ix + 2 < lr ? (int)px[(ptrdiff_t)(ix + 2) * step] : -1;
-      if ((ix & 3) == 0) xw = scr.w(Lp->o_ref + (ix >> 2));
-      const int xl = xw & 0xff; xw >>= 8;
-      if (q >= 0)
-        while (iy < q) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
-      uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
-      if (q >= 0 && iy < lc) {
-        const int yl = scr.code_at(Lp->o_cor, iy);
-        const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
-        if (yl == xl) fl |= yf;  // identical letters share the node
-        else {                   // own node just before x, same ring
-          if (sp < 0) { sp = n; sptype = 1; }
-          put((uint32_t)yl | yf); fl |= NF_SAMERING;
-        }
-        ++iy;
-      } else if (sp < 0) { sp = n; sptype = 0; }
-      put((uint32_t)xl | fl);
-    }
-    while (iy < lc) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
-    if (n & 3) out4[n >> 2] = acc;
-    spcode = sp < 0 ? 0 : 1 + 3 * ((sp >> 1) < 31 ? (sp >> 1) : 31) + sptype;
-    return n;
-  }
-
   EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode) const {
     scr.pack_codes(sc.tab, ref, lr, Lp->o_ref);
     scr.pack_codes(sc.tab, cor, lc, Lp->o_cor);
     s1 = dp(lr, lc);
     traceback(lr, lc);
-    return fuse(lr, lc, p1_out, spcode);
+    return fuse1(scr, Lp->o_ref, Lp->o_cor, scr.at(Lp->o_nodes) + R1_X2Y * 32, (ptrdiff_t)Lp->rec_words * 32, lr, lc, p1_out, spcode);
   }
 };
 
@@ -718,12 +720,14 @@ __device__ __forceinline__ const SymbolTables *stage_tables(uint32_t *smem, cons
   return reinterpret_cast<const SymbolTables *>(smem);
 }
 
-template <bool GENERIC_SUB>
-__global__ void __launch_bounds__(32, EL_MIN_WARPS_PH1) poa_dp1_kernel(PoaArgs a, const SymbolTables *g_tab) {
+// PH = Phase1<GENERIC_SUB> (INT32 cells) or Phase1P (poa_packed.cuh: two 16-bit cells per instruction)
+template <class PH, int MIN_WARPS>
+__global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const SymbolTables *g_tab) {
+  constexpr bool GENERIC_SUB = PH::kGenericSub;
   __shared__ uint32_t s_tab[(GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4];
-  __shared__ Layout1 s_layout;
+  __shared__ typename PH::Layout s_layout;
   const int lane = threadIdx.x;
-  Phase1<GENERIC_SUB> c;
+  PH c;
   c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
@@ -744,7 +748,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PH1) poa_dp1_kernel(PoaArgs a
     {  // the group's own scratch layout: tight, so that its footprint stays in L1/L2
       const int mr = __reduce_max_sync(EL_WARP_FULL, lr), mc = __reduce_max_sync(EL_WARP_FULL, lc);
       __syncwarp();
-      if (lane == 0) make_layout1(s_layout, mr, mc);
+      if (lane == 0) PH::make_layout(s_layout, mr, mc);
       __syncwarp();
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)

@@ -1,0 +1,265 @@
+// poa_packed.cuh -- the 16-bit packed variant of the DP kernels (the one the bulk of the windows runs).
+//
+// poa_kernel.cuh computes one DP cell per ~15 INT32 instructions and its bulk launches sit at
+// 60-77 % ALU-pipe utilisation (profiles/r1c_*): the integer issue rate is the limit.  sm_100a has
+// packed halfword integer instructions (VIMNMX.S16x2 with predicate outputs, VIADDMNMX.S16x2,
+// VIMNMX.U16x2); this file computes TWO cells per instruction with them.
+//
+// Two cells of one window can only be updated together if they do not depend on each other.  A
+// band of 2R rows (R = 6, 7 or 8) is split into a low half (rows r0 .. r0+R-1) and a high half
+// (rows r0+R .. r0+2R-1) that runs ONE COLUMN BEHIND: iteration j updates (r0+k, j) in the low
+// 16 bits and (r0+R+k, j-1) in the high 16 bits of the same registers.  The high half's first row
+// takes its "up" and "diagonal" inputs from the low half's last row of the previous iterations.
+// Iteration 0 makes the high half reproduce the virtual column -1 by itself (its registers start
+// at 0 = minus infinity, so every cell takes the Y-gap move from the cell above), and the last
+// iteration (j = len_x) only completes the high half; no masking is needed anywhere.
+//
+// Arithmetic.  Halves hold S + kBiasP (always in [1, 32767]), so plain 32-bit add / subtract of
+// packed operands never borrows across the halves where it is used.  Per pair of cells:
+//   eq  = x2 ^ y2[k]                       letters (code << 4) differ  <=>  half >= 16
+//   t   = min.u16x2(eq, |mismatch|)        substitution penalty
+//   M   = diag - t
+//   gap = max.s16x2(up, pG)  -> predicates (pG > up): the Y-gap wins ties     (align_lpo_po2.c:392)
+//   s   = max.s16x2(gap, M)  -> predicates (M > gap): a match must beat both  (:384)
+//   g   = max.s16x2(M - open, gap - ext)   = s - pen(move)      [see packed_ok()]
+//   4 predicated ORs set the two move bits of the two cells
+// = 11 instructions for 2 cells.  Exact for matrices in the class packed_ok() describes (the shipped
+// blosum80.mat is); every other matrix, and windows whose scores could leave 16 bits, run the
+// INT32 kernels of poa_kernel.cuh.
+#pragma once
+#include "poa_kernel.cuh"
+
+namespace elector {
+
+constexpr int kBiasP = 16384;       // halves hold S + kBiasP
+constexpr int kPackedSpan = 16000;  // a segment runs packed when maxabs * (len_x + len_y + 4) <= kPackedSpan
+
+// rows per half-band of a group whose longest row sequence has ly letters: ceil(ly / 16) bands of 2R rows
+EL_HD int packed_rows(int ly) {
+  const int nb = (ly + 15) >> 4;
+  const int need = (ly + 2 * nb - 1) / (2 * nb);
+  return need <= 6 ? 6 : need <= 7 ? 7 : 8;
+}
+
+// ---- packed halfword primitives (single instructions on sm_100a; plain C on the host for tests/emul) ----
+EL_HD uint32_t pk_minu(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __vminu2(a, b);
+#else
+  const uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
+  return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+#endif
+}
+// per-half signed max(a, b); ORs bit_lo / bit_hi into mv where b beats a (b > a) in the low / high half.
+// The PTX below is the pattern ptxas turns into ONE VIMNMX.S16x2 with two predicate outputs (the same
+// pattern as CUDA's __vibmax_s16x2) followed by two predicated LOP3.
+EL_HD uint32_t pk_maxs_flag(uint32_t a, uint32_t b, uint32_t &mv, uint32_t bit_lo, uint32_t bit_hi) {
+#ifdef __CUDA_ARCH__
+  uint32_t val;
+  asm("{.reg .pred pu, pv;\n\t"
+      ".reg .s16 rs0, rs1, rs2, rs3;\n\t"
+      "max.s16x2 %0, %2, %3;\n\t"
+      "mov.b32 {rs0, rs1}, %0;\n\t"
+      "mov.b32 {rs2, rs3}, %2;\n\t"
+      "setp.eq.s16 pv, rs0, rs2;\n\t"
+      "setp.eq.s16 pu, rs1, rs3;\n\t"
+      "@!pv or.b32 %1, %1, %4;\n\t"
+      "@!pu or.b32 %1, %1, %5;}\n\t"
+      : "=r"(val), "+r"(mv) : "r"(a), "r"(b), "r"(bit_lo), "r"(bit_hi));
+  return val;
+#else
+  const int16_t al = (int16_t)(a & 0xffffu), bl = (int16_t)(b & 0xffffu), ah = (int16_t)(a >> 16), bh = (int16_t)(b >> 16);
+  if (bl > al) mv |= bit_lo;
+  if (bh > ah) mv |= bit_hi;
+  return (uint32_t)(uint16_t)(al >= bl ? al : bl) | ((uint32_t)(uint16_t)(ah >= bh ? ah : bh) << 16);
+#endif
+}
+// per-half signed max(a + b, c)
+EL_HD uint32_t pk_addmaxs(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+  return __viaddmax_s16x2(a, b, c);
+#else
+  const int16_t sl = (int16_t)((a + b) & 0xffffu), sh = (int16_t)(((a >> 16) + (b >> 16)) & 0xffffu);
+  const int16_t cl = (int16_t)(c & 0xffffu), ch = (int16_t)(c >> 16);
+  return (uint32_t)(uint16_t)(sl > cl ? sl : cl) | ((uint32_t)(uint16_t)(sh > ch ? sh : ch) << 16);
+#endif
+}
+EL_HD uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+EL_HD uint32_t pk_lo_hi(uint32_t lo_src, uint32_t hi_src) {   // low half of lo_src, high half of hi_src
+  return (lo_src & 0xffffu) | (hi_src & 0xffff0000u);
+}
+
+struct PackedConsts {
+  uint32_t mis2, nopen2, ext2;   // |mismatch|, -open, ext in both halves
+  EL_HD void set(const Scoring &sc) {
+    mis2 = pk2(-sc.mismatch, -sc.mismatch);
+    nopen2 = pk2(-sc.open, -sc.open);
+    ext2 = pk2(sc.ext, sc.ext);
+  }
+};
+
+// The packed update of one iteration: the low halves of S/G move from column j-1 to column j, the
+// high halves from the column before to the column of the previous iteration.  Returns the move
+// bits: cell (half h, row k) at bits 16h + 2k + 1 (match) and 16h + 2k (X-gap when not a match).
+template <int R>
+EL_HD uint32_t update_packed(const PackedConsts &pc, uint32_t (&S)[R], uint32_t (&G)[R], const uint32_t (&y2)[R], uint32_t x2,
+                             uint32_t diag, uint32_t up) {
+  uint32_t mv = 0;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t pS = S[k], pG = G[k];
+    const uint32_t t = pk_minu(x2 ^ y2[k], pc.mis2);
+    const uint32_t M = diag - t;
+    const uint32_t gap = pk_maxs_flag(up, pG, mv, 1u << (2 * k), 1u << (16 + 2 * k));   // X-gap only when it beats the Y-gap
+    const uint32_t s = pk_maxs_flag(gap, M, mv, 2u << (2 * k), 2u << (16 + 2 * k));     // match only when it beats both
+    const uint32_t g = pk_addmaxs(M, pc.nopen2, gap - pc.ext2);
+    S[k] = s; G[k] = g;
+    diag = pS; up = g;
+  }
+  return mv;
+}
+
+template <int R>
+EL_HD int pick_half(const uint32_t (&S)[R], int k, bool hi) {
+  uint32_t s = S[0];
+#pragma unroll
+  for (int r = 1; r < R; ++r) if (k == r) s = S[r];
+  return (int)(hi ? s >> 16 : s & 0xffffu) - kBiasP;
+}
+
+// =============================== phase 1, packed ===============================================
+// node record: node j lives in record j + 1 (record 0 = the virtual column -1, which the high half
+// produces in iteration 0 like any other column)
+enum : uint32_t { P1_BSG = 0, P1_X2Y = 1, P1_MOVES = 2 };   // boundary S | G << 16 below the band, x2y, one moves word per band
+
+struct Layout1P {
+  uint32_t o_ref, o_cor, o_nodes, rec_words, R, total;
+};
+EL_HD void make_layout1p(Layout1P &L, int LR, int LC) {
+  uint32_t o = 0;
+  L.o_ref = o; o += cdiv_u(LR, 4) + 2;                         // the last iteration reads one letter past the end
+  L.o_cor = o; o += cdiv_u(LC, 4) + 5;                         // rows up to 16 * ceil(LC / 16) - 1 are read
+  L.R = (uint32_t)packed_rows(LC);
+  L.rec_words = P1_MOVES + cdiv_u(LC, 16);
+  L.o_nodes = o; o += ((uint32_t)LR + 3) * L.rec_words;        // record 0, LR nodes, two records of look-ahead
+  L.total = o;
+}
+
+struct Phase1P {
+  typedef Layout1P Layout;
+  static constexpr bool kGenericSub = false;
+  LaneScratch scr;
+  Scoring sc;
+  const Layout1P *Lp;
+  static EL_HD void make_layout(Layout1P &L, int LR, int LC) { make_layout1p(L, LR, LC); }
+
+  EL_HD uint32_t *rec(int j) const { return scr.at(Lp->o_nodes + (uint32_t)(j + 1) * Lp->rec_words); }
+
+  // one band of 2R rows of DP1 (lin(ref) columns x lin(cor) rows); returns the score of the last cell
+  // when this is the band that holds row ly - 1
+  template <int R>
+  EL_HDN int band(int lr, int ly, int b, bool last) const {
+    const int r0 = b * 2 * R;
+    PackedConsts pc;
+    pc.set(sc);
+    uint32_t y2[R], S[R], G[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      y2[k] = ((uint32_t)scr.code_at(Lp->o_cor, r0 + k) | ((uint32_t)scr.code_at(Lp->o_cor, r0 + R + k) << 16)) << 4;
+      const int v = kBiasP + sc.virt_S(r0 + k);                // virtual column -1 (align_lpo_po2.c:290-302); high half: -inf
+      S[k] = (uint32_t)v;
+      G[k] = (uint32_t)(v - sc.ext);
+    }
+    const int rr = ly - 1 - r0;                                // row of the last cell inside this band (when last)
+    uint32_t *p = rec(-1);
+    const uint32_t step = Lp->rec_words * 32;
+    // boundary row r0 - 1 at nodes j-1 / j: S in the low half, G in the high half
+    uint32_t bsg, bsg_n;
+    if (b == 0) {                                              // row -1 (:272-286): corner, then -(open + ext * j)
+      bsg = pk2(kBiasP, kBiasP - sc.open);
+      bsg_n = pk2(kBiasP - sc.open, kBiasP - sc.open - sc.ext);
+    } else {
+      bsg = p[P1_BSG * 32];
+      bsg_n = p[step + P1_BSG * 32];
+    }
+    uint32_t xw = 0, x2 = 0, d7 = 0, mlo = 0;
+    int best = 0;
+    for (int j = 0; j <= lr; ++j, p += step) {                 // p = record of node j - 1
+      if ((j & 3) == 0) xw = scr.w(Lp->o_ref + (j >> 2));
+      x2 = (x2 << 16) | ((xw & 0xffu) << 4);
+      xw >>= 8;
+      const uint32_t bsg_p = bsg;
+      bsg = bsg_n;
+      if (b == 0) bsg_n = bsg - pc.ext2;
+      else bsg_n = p[2 * step + P1_BSG * 32];                  // node j + 1, one iteration ahead
+      const uint32_t diag0 = pk_lo_hi(bsg_p, d7 << 16);        // S(r0-1, j-1) | S(r0+R-1, j-2)
+      const uint32_t up0 = (bsg >> 16) | (G[R - 1] << 16);     // G(r0-1, j)   | G(r0+R-1, j-1)
+      d7 = S[R - 1];
+      const uint32_t mv = update_packed<R>(pc, S, G, y2, x2, diag0, up0);
+      // node j - 1 is now complete in the high half
+      if (!last) p[P1_BSG * 32] = (S[R - 1] >> 16) | (G[R - 1] & 0xffff0000u);
+      p[(P1_MOVES + b) * 32] = pk_lo_hi(mlo, mv);
+      mlo = mv;
+      if (last && j == lr - 1 && rr < R) best = pick_half<R>(S, rr, false);
+    }
+    if (last && rr >= R) best = pick_half<R>(S, rr - R, true);
+    return best;
+  }
+
+  template <int R>
+  EL_HDN int dp(int lr, int ly) const {
+    const int nb = (ly + 2 * R - 1) / (2 * R);
+    for (int b = 0; b < nb - 1; ++b) band<R>(lr, ly, b, false);
+    return band<R>(lr, ly, nb - 1, true);
+  }
+
+  // traceback (align_lpo_po2.c:108-168): fills the x2y field of every record
+  template <int R>
+  EL_HDN void traceback(int lr, int ly) const {
+    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
+    {
+      uint32_t *p = rec(0) + P1_X2Y * 32;
+      for (int j = 0; j < lr; ++j, p += step) *p = 0xffffffffu;
+    }
+    int j = lr - 1, r = ly - 1;
+    while (j >= 0 && r >= 0) {
+      const int b = r / (2 * R);
+      int rr = r - b * 2 * R;
+      uint32_t *p = rec(j);
+      const uint32_t *pm = p + (P1_MOVES + b) * 32;
+      uint32_t w0 = pm[0], w1 = j >= 1 ? pm[-step] : 0, w2 = j >= 2 ? pm[-2 * step] : 0, w3 = j >= 3 ? pm[-3 * step] : 0;
+      for (;;) {
+        const uint32_t kind = (w0 >> (rr < R ? 2 * rr : 16 + 2 * (rr - R))) & 3u;   // bit 1 match, bit 0 X-gap
+        if (kind & 2u) p[P1_X2Y * 32] = (uint32_t)r;
+        if (kind != 1u) { --r; --rr; }
+        if (kind) {
+          --j; p -= step; pm -= step;
+          w0 = w1; w1 = w2; w2 = w3;
+          w3 = j >= 3 ? pm[-3 * step] : 0;
+        }
+        if (j < 0 || r < 0 || rr < 0) break;
+      }
+    }
+  }
+
+  template <int R>
+  EL_HDN int run_r(int lr, int lc, uint16_t *p1_out, int &s1, int &spcode) const {
+    s1 = dp<R>(lr, lc);
+    traceback<R>(lr, lc);
+    return fuse1(scr, Lp->o_ref, Lp->o_cor, rec(0) + P1_X2Y * 32, (ptrdiff_t)Lp->rec_words * 32, lr, lc, p1_out, spcode);
+  }
+
+  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode) const {
+    scr.pack_codes(sc.tab, ref, lr, Lp->o_ref);
+    scr.pack_codes(sc.tab, cor, lc, Lp->o_cor);
+    // the last band reads up to 15 letters past the end of cor, the last iteration one past the end of ref:
+    // defined values (which ones does not matter, they only feed cells outside the window)
+    for (uint32_t k = 0; k < 5; ++k) scr.w(Lp->o_cor + cdiv_u((uint32_t)lc, 4) + k) = 0;
+    scr.w(Lp->o_ref + cdiv_u((uint32_t)lr, 4)) = 0;
+    if (Lp->R == 6) return run_r<6>(lr, lc, p1_out, s1, spcode);   // R is uniform over the warp
+    if (Lp->R == 7) return run_r<7>(lr, lc, p1_out, s1, spcode);
+    return run_r<8>(lr, lc, p1_out, s1, spcode);
+  }
+};
+
+}  // namespace elector

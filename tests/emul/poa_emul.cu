@@ -4,7 +4,8 @@
 // moves, fused emit) can be checked against the oracle in the GPU-less container.
 // It is never linked into the product library; the product has no CPU path.
 //
-// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores]
+// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores|-] [packed]
+// packed: windows the library would run through the 16-bit packed kernels (poa_packed.cuh) do so here too
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -12,11 +13,13 @@
 
 #include "../../elector_b200/csrc/host_setup.hpp"
 #include "../../elector_b200/csrc/bin_kernel.cuh"
+#include "../../elector_b200/csrc/poa_packed.cuh"
 
 using namespace elector;
 
 template <bool GS>
-static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores) {
+static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed) {
+  long n_packed1 = 0;
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
     const int lr = R.rec[w].len, lc = C.rec[w].len, lu = U.rec[w].len;
@@ -24,18 +27,30 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     Scoring s;
     s.tab = &sc.tab; s.match = sc.match; s.mismatch = sc.mismatch; s.open = sc.open; s.ext = sc.ext;
     // ---- phase 1 (caps deliberately larger than the window, as in a real group) ----
-    Layout1 L1;
-    make_layout1(L1, lr + (int)(w % 3), lc + (int)(w % 5));
-    std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
-    Phase1<GS> p1;
-    p1.scr.base = scratch1.data() + lane;
-    p1.sc = s;
-    p1.Lp = &L1;
     std::vector<uint64_t> nodes64(((size_t)lr + lc) / 4 + 2, 0xdeaddeaddeaddeadull);
     uint16_t *nodes_p = reinterpret_cast<uint16_t *>(nodes64.data());
-    int s1, spcode;
-    const int n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc,
-                                 nodes_p, s1, spcode);
+    int s1, spcode, n1;
+    const int cap_r = lr + (int)(w % 3), cap_c = lc + (int)(w % 5);
+    if (packed && sc.packed_ok && (long)sc.maxabs * (cap_r + cap_c + 4) <= kPackedSpan) {
+      Layout1P L1;
+      make_layout1p(L1, cap_r, cap_c);
+      std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
+      Phase1P p1;
+      p1.scr.base = scratch1.data() + lane;
+      p1.sc = s;
+      p1.Lp = &L1;
+      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode);
+      ++n_packed1;
+    } else {
+      Layout1 L1;
+      make_layout1(L1, cap_r, cap_c);
+      std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
+      Phase1<GS> p1;
+      p1.scr.base = scratch1.data() + lane;
+      p1.sc = s;
+      p1.Lp = &L1;
+      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode);
+    }
     int bin, seg;
     bin2_of(n1, lu, spcode, bin, seg);
     if (bin < 0 || bin >= kNumBins2 || seg < 0 || seg >= kNumSegs2) { fprintf(stderr, "bad phase-2 bin\n"); return 1; }
@@ -59,6 +74,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     }
     if (scores) fprintf(scores, "%d %d %d %d\n", s1, s2, n1, nring);
   }
+  if (packed) fprintf(stderr, "packed: %ld of %zu windows in phase 1\n", n_packed1, n);
   return 0;
 }
 
@@ -74,7 +90,8 @@ int main(int argc, char **argv) {
   FILE *pir = fopen(argv[5], "w");
   FILE *scores = argc > 6 && argv[6][0] != '-' ? fopen(argv[6], "w") : nullptr;
   if (!pir) return 1;
-  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores); else run<false>(sc, R, C, U, pir, scores);
+  const bool packed = argc > 7 && std::string(argv[7]) == "packed";
+  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores, packed); else run<false>(sc, R, C, U, pir, scores, packed);
   fclose(pir);
   if (scores) fclose(scores);
   return 0;

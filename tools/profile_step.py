@@ -2,6 +2,7 @@
 """Profiling driver (run under ncu): N plain steps of the hot path through the host C-ABI on a
 cached workload; no torch, no subprocesses, so the profiler only sees our kernels.
   python tools/profile_step.py [reads] [steps] [config] [poa|pipeline]"""
+import ctypes
 import os
 import sys
 
@@ -21,4 +22,7 @@ with elector_b200.PoaContext(0) as ctx:
         else:
             res = ctx.run_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"])
         ms, k = ctx.last_kernel_ms()
-        print("step: %d windows, %d launches, %.3f ms kernels, %.1f GCUPS" % (len(res.nring), k, ms, res.cells.sum() / ms / 1e6))
+        a, b = ctypes.c_float(0), ctypes.c_float(0)
+        ctx._lib.elector_last_phase_ms(ctx._ctx, ctypes.byref(a), ctypes.byref(b))
+        print("step: %d windows, %d launches, %.3f ms kernels (phase 1 %.3f, phase 2 %.3f of %.3f), %.1f GCUPS"
+              % (len(res.nring), k, ms, a.value, b.value - a.value, b.value, res.cells.sum() / ms / 1e6))
