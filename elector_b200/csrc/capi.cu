@@ -3,6 +3,7 @@
 // There is NO CPU implementation of the alignment here: every entry point either runs
 // the CUDA kernels or returns an error.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -453,11 +454,16 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
     while (wcut.back() < n) wcut.push_back(std::min<int64_t>(n, wcut.back() + target));
   }
   const size_t nchunks = wcut.size() - 1;
-  while (ctx->chunk_ev.size() < 2 * nchunks) {
+  while (ctx->chunk_ev.size() < 3 * nchunks + 1) {   // per chunk: inputs resident, results ready, results on the host; + call start
     cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreate(&e));
     ctx->chunk_ev.push_back(e);
   }
+  const bool trace = getenv("ELECTOR_TRACE") != nullptr;
+  const cudaEvent_t ev_start = ctx->chunk_ev[3 * nchunks];
+  const auto host_t0 = std::chrono::steady_clock::now();
+  auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+  std::vector<double> host_sync(nchunks, 0.0);
   // ---- device buffers for the whole call ----
   const int64_t br = ro[n], bc = co[n], bu = uo[n];
   CU(ctx->d_ref.reserve(br)); CU(ctx->d_cor.reserve(bc)); CU(ctx->d_unc.reserve(bu));
@@ -467,6 +473,7 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   if (n_reads > 0) { CU(ctx->d_tally_out.reserve(n_reads * ELECTOR_TALLY_K * 8)); CU(ctx->d_sums.reserve(ELECTOR_TALLY_K * 8)); }
   cudaStream_t st = ctx->stream, cin = ctx->copy_in, cout = ctx->copy_out;
   // ---- all inputs, chunk by chunk, on the H2D stream ----
+  CU(cudaEventRecord(ev_start, cin));
   for (size_t k = 0; k < nchunks; ++k) {
     const int64_t w0 = wcut[k], w1 = wcut[k + 1];
     CU(cudaMemcpyAsync(ctx->d_ref.as<char>() + ro[w0], ref + ro[w0], ro[w1] - ro[w0], cudaMemcpyHostToDevice, cin));
@@ -509,6 +516,7 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
     }
     CU(cudaEventRecord(ctx->chunk_ev[2 * k + 1], st));
     CU(cudaStreamSynchronize(st));
+    host_sync[k] = host_ms();
     add_kernel_ms(ctx);
     const int64_t used = ctx->h_totals[4];
     if ((int32_t)(ctx->h_totals[5] & 0xffffffff) || used > rows_cap) {
@@ -526,6 +534,7 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
     if (r1 > r0)
       CU(cudaMemcpyAsync(counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.as<int64_t>() + r0 * ELECTOR_TALLY_K,
                          (r1 - r0) * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, cout));
+    CU(cudaEventRecord(ctx->chunk_ev[2 * nchunks + k], cout));
     used_before = used;
   }
   if (n_reads > 0) {
@@ -537,6 +546,17 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
     }
   }
   CU(cudaStreamSynchronize(cout));
+  if (trace) {   // ELECTOR_TRACE: device timeline of the call (ms after the first copy was queued), one line per chunk
+    for (size_t k = 0; k < nchunks; ++k) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, ev_start, ctx->chunk_ev[2 * k]);
+      cudaEventElapsedTime(&b, ev_start, ctx->chunk_ev[2 * k + 1]);
+      cudaEventElapsedTime(&c, ev_start, ctx->chunk_ev[2 * nchunks + k]);
+      fprintf(stderr, "[elector trace] chunk %zu: %lld windows, inputs resident %.2f ms, results ready %.2f ms (host saw it at %.2f), results on host %.2f ms\n",
+              k, (long long)(wcut[k + 1] - wcut[k]), a, b, host_sync[k], c);
+    }
+    fprintf(stderr, "[elector trace] call returned at %.2f ms (host clock)\n", host_ms());
+  }
   return ELECTOR_OK;
 }
 

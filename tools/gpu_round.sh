@@ -13,7 +13,6 @@ echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 > $O/${TAG}_be
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
   python tools/profile_step.py 10000 2 1 pipeline > $O/${TAG}_launches.log 2>&1; tail -2 $O/${TAG}_launches.log
-echo "== ncu full (bulk DP2 + DP1 launches)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:poa_dp -c 12 -o $O/${TAG}_full \
-  python tools/profile_step.py 2000 1 1 poa > $O/${TAG}_full.log 2>&1; tail -2 $O/${TAG}_full.log
+echo "== ncu full (bulk DP launches, through the C poa shim)"
+bash tools/ncu_diag.sh ${TAG} 2000; tail -3 $O/${TAG}_ncu.log
 ls -la $O | tail -12

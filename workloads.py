@@ -172,22 +172,4 @@ def make_windows(cfg, n_reads, first_read=0, procs=None, minfrac=0.1, cache=True
     return d
 
 
-def shard_reads(n_reads, rank, world):
-    """contiguous read-id ranges, one per rank"""
-    lo = (n_reads * rank) // world
-    hi = (n_reads * (rank + 1)) // world
-    return lo, hi
-
-
-def slice_windows(d, read_lo, read_hi):
-    """sub-workload holding reads [read_lo, read_hi) of d"""
-    rf = d["read_first"]
-    w0, w1 = int(rf[read_lo]), int(rf[read_hi])
-    out = {}
-    for k in ("ref", "cor", "unc"):
-        off = d[k + "_off"]
-        out[k] = d[k][int(off[w0]):int(off[w1])]
-        out[k + "_off"] = off[w0:w1 + 1] - off[w0]
-    out["read_first"] = rf[read_lo:read_hi + 1] - w0
-    out["source"] = d.get("source", "")
-    return out
+from elector_b200.shard import shard_reads, slice_windows  # noqa: E402,F401  (host logic of SURVEY.md 8e lives in the package)
