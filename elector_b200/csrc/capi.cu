@@ -53,7 +53,7 @@ struct elector_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0, resident_ph2p = 0;  // POA kernel CTAs (one warp each) resident per SM
   int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
@@ -65,6 +65,7 @@ struct elector_ctx {
   std::vector<cudaEvent_t> chunk_ev;                    // 2 per chunk: inputs resident, results ready
   ScoreMatrix mat;
   ScoringSetup sc;
+  bool no_packed2 = false;  // ELECTOR_NO_PACKED2=1: phase 2 on the INT32 kernel (A/B measurements)
   DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   int64_t merged_cap = 0;  // bytes per merged-row buffer of the last merge
@@ -104,6 +105,9 @@ const int kSideStreams = 3;
 #ifndef EL_MIN_WARPS_PH1P
 #define EL_MIN_WARPS_PH1P 32  // packed DP1: register cap 64 (32 one-warp CTAs per SM is the hardware limit)
 #endif
+#ifndef EL_MIN_WARPS_PH2P
+#define EL_MIN_WARPS_PH2P 24  // packed DP2: register cap 80
+#endif
 
 // packed = the segment runs the 16-bit packed kernel (poa_packed.cuh)
 template <bool GS>
@@ -111,15 +115,17 @@ cudaError_t launch_phase(int phase, bool packed, cudaStream_t st, PoaArgs &a, in
   if (phase == 1) {
     if (packed) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
     else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
-  } else poa_dp2_kernel<GS><<<grid, 32, 0, st>>>(a, tab);
+  } else if (packed) poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P><<<grid, 32, 0, st>>>(a, tab);
+  else poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2><<<grid, 32, 0, st>>>(a, tab);
   return cudaGetLastError();
 }
 
 template <bool GS>
-void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p) {
+void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p, int &ph2p) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1, poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1>, 32, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2, poa_dp2_kernel<GS>, 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2, poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1p, poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P>, 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2p, poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P>, 32, 0);
 }
 
 struct SegPlan { int seg, grid; size_t warp_words, scratch_off; bool packed; };
@@ -136,11 +142,16 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     size_t total;
     SegPlan p;
     // 16-bit packed kernel when the matrix allows it and no score of the segment can leave 16 bits
-    p.packed = phase == 1 && ctx->sc.packed_ok && (int64_t)ctx->sc.maxabs * (m0 + m1 + 4) <= kPackedSpan;
-    if (p.packed) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; }
-    else if (phase == 1) { Layout1 L; make_layout1(L, m0, m1); total = L.total; }
-    else { Layout2 L; make_layout2(L, m0, m1); total = L.total; }
-    const int resident = std::max(1, p.packed ? ctx->resident_ph1p : phase == 1 ? ctx->resident_ph1 : ctx->resident_ph2) * ctx->sm_count;
+    p.packed = ctx->sc.packed_ok && (phase == 1 || !ctx->no_packed2) && (int64_t)ctx->sc.maxabs * (m0 + m1 + 4) <= kPackedSpan;
+    if (phase == 1) {
+      if (p.packed) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; }
+      else { Layout1 L; make_layout1(L, m0, m1); total = L.total; }
+    } else {
+      if (p.packed) { Layout2P L; make_layout2p(L, m0, m1); total = L.total; }
+      else { Layout2 L; make_layout2(L, m0, m1); total = L.total; }
+    }
+    const int per_sm = phase == 1 ? (p.packed ? ctx->resident_ph1p : ctx->resident_ph1) : (p.packed ? ctx->resident_ph2p : ctx->resident_ph2);
+    const int resident = std::max(1, per_sm) * ctx->sm_count;
     p.seg = s;
     p.warp_words = total;
     p.grid = (int)std::min<int64_t>(resident, ((int64_t)si.count + 31) / 32);
@@ -304,6 +315,7 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     }
   } else ctx->mat.set_default();
   if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
+  if (const char *e = getenv("ELECTOR_NO_PACKED2")) ctx->no_packed2 = e[0] == '1';
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0) {
@@ -339,8 +351,12 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
-  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p);
-  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p);
+  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p);
+  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p);
+  // experiment knobs: cap the resident warps per SM of a kernel (scratch footprint vs. latency hiding)
+  auto cap = [](int &v, const char *name) { if (const char *e = getenv(name)) { const int c = atoi(e); if (c > 0 && c < v) v = c; } };
+  cap(ctx->resident_ph1, "ELECTOR_WARPS_PH1"); cap(ctx->resident_ph2, "ELECTOR_WARPS_PH2");
+  cap(ctx->resident_ph1p, "ELECTOR_WARPS_PH1P"); cap(ctx->resident_ph2p, "ELECTOR_WARPS_PH2P");
   if (ctx->resident_ph1 < 1 || ctx->resident_ph2 < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;

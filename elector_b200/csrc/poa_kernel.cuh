@@ -468,8 +468,122 @@ __host__ __device__ __noinline__ inline uint32_t arrange_sets(uint32_t *sa, uint
   return (uint32_t)kindA | ((uint32_t)kindB << 2) | flipped;
 }
 
+// ---- fuse 2 + MSA emit (lpo.c:413-463 with rings, lpo_format.c:346-371) ----
+// Walks the final node order without materialising P2; a column closes whenever the
+// align ring changes.  Returns nring; rows go to o_rows (3 x row_words words).
+template <class PH>
+EL_HDN int fuse_emit_rows(const PH &ph, int n1, int lu) {
+  const LaneScratch &scr = ph.scr;
+  const auto *Lp = ph.Lp;
+  constexpr uint32_t kNode = PH::kRecNode, kX2Y = PH::kRecX2Y;
+  const uint8_t *sym = ph.sc.tab->sym;
+  int iy = 0, col = -1, prev_key = -1, rs = 0;
+  uint32_t c0 = '.', c1 = '.', c2 = '.';
+  uint32_t w0 = 0, w1 = 0, w2 = 0;
+  const uint32_t r0 = Lp->o_rows, r1 = Lp->o_rows + Lp->row_words, r2 = Lp->o_rows + 2 * Lp->row_words;
+  auto flush = [&]() {
+    if (col >= 0) {
+      const int sh = (col & 3) * 8;
+      w0 |= c0 << sh; w1 |= c1 << sh; w2 |= c2 << sh;
+      if ((col & 3) == 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; w0 = w1 = w2 = 0; }
+    }
+  };
+  auto emit = [&](int key, uint32_t letter, uint32_t srcmask) {
+    if (key != prev_key) { flush(); ++col; c0 = c1 = c2 = '.'; prev_key = key; }
+    const uint32_t ch = sym[letter];
+    if (srcmask & 1u) c0 = ch;
+    if (srcmask & 2u) c1 = ch;
+    if (srcmask & 4u) c2 = ch;
+  };
+  const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
+  const uint32_t *pr = ph.node_rec(0);
+  // (node, x2y) of records ix, ix+1 in registers, ix+2 in flight
+  uint32_t ra0 = pr[kNode * 32], ra1 = n1 > 1 ? pr[step + kNode * 32] : 0;
+  int q0 = (int)pr[kX2Y * 32], q1 = n1 > 1 ? (int)pr[step + kX2Y * 32] : -1;
+  for (int ix = 0; ix < n1; ++ix, pr += step) {
+    const uint32_t ra = ra0, ra_next = ra1;
+    const int qx = q0, q_next = q1;
+    ra0 = ra1; q0 = q1;
+    if (ix + 2 < n1) { ra1 = pr[2 * step + kNode * 32]; q1 = (int)pr[2 * step + kX2Y * 32]; }
+    if (!(ra & NF_SAMERING)) rs = ix;
+    // scan x's ring from ix on: unaligned y letters go before the first aligned member
+    {
+      int q = qx;
+      if (q < 0 && ix + 1 < n1 && (ra_next & NF_SAMERING)) {
+        q = q_next;
+        for (int ir = ix + 2; q < 0 && ir < n1 && (ph.node_rec(ir)[kNode * 32] & NF_SAMERING); ++ir) q = (int)ph.node_rec(ir)[kX2Y * 32];
+      }
+      if (q >= 0) while (iy < q) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
+    }
+    uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
+    if (qx >= 0 && iy < lu) {
+      const uint32_t yl = scr.code_at(Lp->o_unc, iy);
+      if (yl == (ra & 0xffu)) mask |= 4u;
+      else emit(rs, yl, 4u);
+      ++iy;
+    }
+    emit(rs, ra & 0xffu, mask);
+  }
+  while (iy < lu) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
+  flush();
+  if ((col & 3) != 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; }
+  return col + 1;
+}
+
+// ---- node preparation (align_lpo_po2.c:46-79 + row -1, :272-286) ----
+// Reads P1's 16-bit node list, derives every node's left list from the two frontiers and
+// stores: the node with its shape (NF_VIRT / NF_TWO / NF_NOPRED / NF_PREDC / slot), its real
+// predecessors (for the traceback) and row -1 of the DP as the first boundary row.
+template <class PH>
+EL_HDN void prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
+  const LaneScratch &scr = ph.scr;
+  const auto *Lp = ph.Lp;
+  int lastR = -1, lastC = -1, gR = 0, gC = 0, nslot = 0;
+  uint32_t *p = ph.node_rec(0);
+  const uint32_t step = Lp->rec_words * 32;
+  const int open = ph.sc.open, ext = ph.sc.ext;
+  const uint64_t *n4 = reinterpret_cast<const uint64_t *>(nodes);   // 4 nodes per load, one load ahead
+  uint64_t quad = n4[0], quad_n = nx > 4 ? n4[1] : 0;
+  uint32_t nt = 0;
+#pragma unroll 1
+  for (int j = 0; j < nx; ++j, p += step) {
+    if (j && (j & 3) == 0) { quad = quad_n; quad_n = j + 4 < nx ? n4[(j >> 2) + 1] : 0; }
+    uint32_t ra = (uint32_t)(quad >> (16 * (j & 3))) & 0xffffu;
+    const bool hasR = ra & NF_REF, hasC = ra & NF_COR;
+    int pA = -1, pB = -1, gA = 0, gB = 0;
+    if (hasR && lastR >= 0) { pA = lastR; gA = gR; }
+    if (hasC && lastC >= 0 && lastC != pA) {
+      if (pA < 0) { pA = lastC; gA = gC; ra |= NF_PREDC; }
+      else { pB = lastC; gB = gC; ra |= NF_TWO; }
+    }
+    const bool virt = (ra & NF_INITIAL) && pA >= 0;
+    int bS;  // S(-1, j): first strict maximum of G(-1, p) over the left list
+    if (pA < 0) { ra |= NF_NOPRED; bS = -open; }
+    else {
+      bS = gA;
+      if (virt) { ra |= NF_VIRT; bS = -open; if (gA > bS) bS = gA; }
+      if (pB >= 0 && gB > bS) bS = gB;
+      if (virt || pB >= 0) ra |= (uint32_t)(nslot++) << NF_SLOT_SHIFT;
+    }
+    const int bG = bS - ext;
+    p[PH::kRecNode * 32] = ra;
+    p[PH::kRecPred * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
+    PH::put_row0(p, bS, bG);
+    p[PH::kRecX2Y * 32] = 0xffffffffu;
+    if (pA != j - 1 || (ra & (NF_VIRT | NF_TWO))) nt |= 1u << (j & 31);   // the traceback must look this node up
+    if ((j & 31) == 31) { scr.w(Lp->o_nt + (j >> 5)) = nt; nt = 0; }
+    if (hasR) { lastR = j; gR = bG; }
+    if (hasC) { lastC = j; gC = bG; }
+  }
+  if (nx & 31) scr.w(Lp->o_nt + (nx >> 5)) = nt;
+}
+
 template <bool GENERIC_SUB>
 struct Phase2 {
+  typedef Layout2 Layout;
+  static constexpr bool kGenericSub = GENERIC_SUB;
+  static constexpr int kSetWords = kSlotWords;
+  static EL_HD void make_layout(Layout2 &L, int N1, int LU) { make_layout2(L, N1, LU); }
   LaneScratch scr;
   uint32_t *bset;     // two frontier-set slots of kSlotWords words, + lane (shared memory on the device)
   Scoring sc;
@@ -477,51 +591,8 @@ struct Phase2 {
 
   EL_HD uint32_t *rec(uint32_t j) const { return scr.at(Lp->o_nodes + j * Lp->rec_words); }  // field f at [f*32]
 
-  // ---- node preparation (align_lpo_po2.c:46-79 + row -1, :272-286) ----
-  // Reads P1's 16-bit node list, derives every node's left list from the two frontiers and
-  // stores: the node with its shape (NF_VIRT / NF_TWO / NF_NOPRED / NF_PREDC / slot), its real
-  // predecessors (for the traceback) and row -1 of the DP as the first boundary row.
-  EL_HDN void prepare(const uint16_t *nodes, int nx) const {
-    int lastR = -1, lastC = -1, gR = 0, gC = 0, nslot = 0;
-    uint32_t *p = rec(0);
-    const uint32_t step = Lp->rec_words * 32;
-    const int open = sc.open, ext = sc.ext;
-    const uint64_t *n4 = reinterpret_cast<const uint64_t *>(nodes);   // 4 nodes per load, one load ahead
-    uint64_t quad = n4[0], quad_n = nx > 4 ? n4[1] : 0;
-    uint32_t nt = 0;
-#pragma unroll 1
-    for (int j = 0; j < nx; ++j, p += step) {
-      if (j && (j & 3) == 0) { quad = quad_n; quad_n = j + 4 < nx ? n4[(j >> 2) + 1] : 0; }
-      uint32_t ra = (uint32_t)(quad >> (16 * (j & 3))) & 0xffffu;
-      const bool hasR = ra & NF_REF, hasC = ra & NF_COR;
-      int pA = -1, pB = -1, gA = 0, gB = 0;
-      if (hasR && lastR >= 0) { pA = lastR; gA = gR; }
-      if (hasC && lastC >= 0 && lastC != pA) {
-        if (pA < 0) { pA = lastC; gA = gC; ra |= NF_PREDC; }
-        else { pB = lastC; gB = gC; ra |= NF_TWO; }
-      }
-      const bool virt = (ra & NF_INITIAL) && pA >= 0;
-      int bS;  // S(-1, j): first strict maximum of G(-1, p) over the left list
-      if (pA < 0) { ra |= NF_NOPRED; bS = -open; }
-      else {
-        bS = gA;
-        if (virt) { ra |= NF_VIRT; bS = -open; if (gA > bS) bS = gA; }
-        if (pB >= 0 && gB > bS) bS = gB;
-        if (virt || pB >= 0) ra |= (uint32_t)(nslot++) << NF_SLOT_SHIFT;
-      }
-      const int bG = bS - ext;
-      p[R2_NODE * 32] = ra;
-      p[R2_PRED * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
-      p[R2_BS * 32] = (uint32_t)bS;
-      p[R2_BG * 32] = (uint32_t)bG;
-      p[R2_X2Y * 32] = 0xffffffffu;
-      if (pA != j - 1 || (ra & (NF_VIRT | NF_TWO))) nt |= 1u << (j & 31);   // the traceback must look this node up
-      if ((j & 31) == 31) { scr.w(Lp->o_nt + (j >> 5)) = nt; nt = 0; }
-      if (hasR) { lastR = j; gR = bG; }
-      if (hasC) { lastC = j; gC = bG; }
-    }
-    if (nx & 31) scr.w(Lp->o_nt + (nx >> 5)) = nt;
-  }
+  static EL_HD void put_row0(uint32_t *p, int bS, int bG) { p[R2_BS * 32] = (uint32_t)bS; p[R2_BG * 32] = (uint32_t)bG; }
+  EL_HDN void prepare(const uint16_t *nodes, int nx) const { prepare_nodes(*this, nodes, nx); }
 
   // ---- DP2: P1 columns x lin(unc) rows, one band (align_lpo_po2.c:269-433) ----
   template <int R>
@@ -628,66 +699,9 @@ struct Phase2 {
     }
   }
 
-  EL_HD int x2y(int j) const { return (int)rec((uint32_t)j)[R2_X2Y * 32]; }
-  EL_HD uint32_t node(int j) const { return rec((uint32_t)j)[R2_NODE * 32]; }
-
-  // ---- fuse 2 + MSA emit (lpo.c:413-463 with rings, lpo_format.c:346-371) ----
-  // Walks the final node order without materialising P2; a column closes whenever the
-  // align ring changes.  Returns nring; rows go to o_rows (3 x row_words words).
-  EL_HDN int fuse_emit(int n1, int lu) const {
-    const uint8_t *sym = sc.tab->sym;
-    int iy = 0, col = -1, prev_key = -1, rs = 0;
-    uint32_t c0 = '.', c1 = '.', c2 = '.';
-    uint32_t w0 = 0, w1 = 0, w2 = 0;
-    const uint32_t r0 = Lp->o_rows, r1 = Lp->o_rows + Lp->row_words, r2 = Lp->o_rows + 2 * Lp->row_words;
-    auto flush = [&]() {
-      if (col >= 0) {
-        const int sh = (col & 3) * 8;
-        w0 |= c0 << sh; w1 |= c1 << sh; w2 |= c2 << sh;
-        if ((col & 3) == 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; w0 = w1 = w2 = 0; }
-      }
-    };
-    auto emit = [&](int key, uint32_t letter, uint32_t srcmask) {
-      if (key != prev_key) { flush(); ++col; c0 = c1 = c2 = '.'; prev_key = key; }
-      const uint32_t ch = sym[letter];
-      if (srcmask & 1u) c0 = ch;
-      if (srcmask & 2u) c1 = ch;
-      if (srcmask & 4u) c2 = ch;
-    };
-    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
-    const uint32_t *pr = rec(0);
-    // (node, x2y) of records ix, ix+1 in registers, ix+2 in flight
-    uint32_t ra0 = pr[R2_NODE * 32], ra1 = n1 > 1 ? pr[step + R2_NODE * 32] : 0;
-    int q0 = (int)pr[R2_X2Y * 32], q1 = n1 > 1 ? (int)pr[step + R2_X2Y * 32] : -1;
-    for (int ix = 0; ix < n1; ++ix, pr += step) {
-      const uint32_t ra = ra0, ra_next = ra1;
-      const int qx = q0, q_next = q1;
-      ra0 = ra1; q0 = q1;
-      if (ix + 2 < n1) { ra1 = pr[2 * step + R2_NODE * 32]; q1 = (int)pr[2 * step + R2_X2Y * 32]; }
-      if (!(ra & NF_SAMERING)) rs = ix;
-      // scan x's ring from ix on: unaligned y letters go before the first aligned member
-      {
-        int q = qx;
-        if (q < 0 && ix + 1 < n1 && (ra_next & NF_SAMERING)) {
-          q = q_next;
-          for (int ir = ix + 2; q < 0 && ir < n1 && (node(ir) & NF_SAMERING); ++ir) q = x2y(ir);
-        }
-        if (q >= 0) while (iy < q) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
-      }
-      uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
-      if (qx >= 0 && iy < lu) {
-        const uint32_t yl = scr.code_at(Lp->o_unc, iy);
-        if (yl == (ra & 0xffu)) mask |= 4u;
-        else emit(rs, yl, 4u);
-        ++iy;
-      }
-      emit(rs, ra & 0xffu, mask);
-    }
-    while (iy < lu) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
-    flush();
-    if ((col & 3) != 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; }
-    return col + 1;
-  }
+  static constexpr uint32_t kRecNode = R2_NODE, kRecX2Y = R2_X2Y, kRecPred = R2_PRED;
+  EL_HD uint32_t *node_rec(int j) const { return rec((uint32_t)j); }
+  EL_HDN int fuse_emit(int n1, int lu) const { return fuse_emit_rows(*this, n1, lu); }
 
   EL_HDN int run_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2) const {
     scr.pack_codes(sc.tab, unc, lu, Lp->o_unc);
@@ -769,13 +783,15 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
   }
 }
 
-template <bool GENERIC_SUB>
-__global__ void __launch_bounds__(32, EL_MIN_WARPS_PH2) poa_dp2_kernel(PoaArgs a, const SymbolTables *g_tab) {
+// PH = Phase2<GENERIC_SUB> (INT32 cells) or Phase2P (poa_packed.cuh)
+template <class PH, int MIN_WARPS>
+__global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const SymbolTables *g_tab) {
+  constexpr bool GENERIC_SUB = PH::kGenericSub;
   __shared__ uint32_t s_tab[(GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4];
-  __shared__ Layout2 s_layout;
-  __shared__ uint32_t s_bset[2 * kSlotWords];
+  __shared__ typename PH::Layout s_layout;
+  __shared__ uint32_t s_bset[2 * PH::kSetWords];
   const int lane = threadIdx.x;
-  Phase2<GENERIC_SUB> c;
+  PH c;
   c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
   c.bset = s_bset + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
@@ -798,7 +814,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_PH2) poa_dp2_kernel(PoaArgs a
     {
       const int mn = __reduce_max_sync(EL_WARP_FULL, n1), mu = __reduce_max_sync(EL_WARP_FULL, lu);
       __syncwarp();
-      if (lane == 0) make_layout2(s_layout, mn, mu);
+      if (lane == 0) PH::make_layout(s_layout, mn, mu);
       __syncwarp();
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)

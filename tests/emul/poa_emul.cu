@@ -19,7 +19,7 @@ using namespace elector;
 
 template <bool GS>
 static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed) {
-  long n_packed1 = 0;
+  long n_packed1 = 0, n_packed2 = 0;
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
     const int lr = R.rec[w].len, lc = C.rec[w].len, lu = U.rec[w].len;
@@ -55,26 +55,47 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     bin2_of(n1, lu, spcode, bin, seg);
     if (bin < 0 || bin >= kNumBins2 || seg < 0 || seg >= kNumSegs2) { fprintf(stderr, "bad phase-2 bin\n"); return 1; }
     // ---- phase 2 ----
-    Layout2 L2;
-    make_layout2(L2, n1 + (int)(w % 4), lu + (int)(w % 2));
-    std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
-    std::vector<uint32_t> bset((size_t)2 * kSlotWords, 0xdeadbeefu);
-    Phase2<GS> p2;
-    p2.scr.base = scratch2.data() + lane;
-    p2.bset = bset.data() + lane;
-    p2.sc = s;
-    p2.Lp = &L2;
-    int s2;
-    const int nring = p2.run_window(nodes_p, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
+    const int cap_n = n1 + (int)(w % 4), cap_u = lu + (int)(w % 2);
+    int s2, nring;
+    std::vector<uint32_t> rows;   // the three MSA rows, 4 letters per word, row_words words each
+    uint32_t row_words;
+    if (packed && sc.packed_ok && (long)sc.maxabs * (cap_n + cap_u + 4) <= kPackedSpan) {
+      Layout2P L2;
+      make_layout2p(L2, cap_n, cap_u);
+      std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
+      std::vector<uint32_t> bset((size_t)2 * kSetWordsP, 0xdeadbeefu);
+      Phase2P p2;
+      p2.scr.base = scratch2.data() + lane;
+      p2.bset = bset.data() + lane;
+      p2.sc = s;
+      p2.Lp = &L2;
+      nring = p2.run_window(nodes_p, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
+      row_words = L2.row_words;
+      for (uint32_t k = 0; k < 3 * row_words; ++k) rows.push_back(p2.scr.w(L2.o_rows + k));
+      ++n_packed2;
+    } else {
+      Layout2 L2;
+      make_layout2(L2, cap_n, cap_u);
+      std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
+      std::vector<uint32_t> bset((size_t)2 * kSlotWords, 0xdeadbeefu);
+      Phase2<GS> p2;
+      p2.scr.base = scratch2.data() + lane;
+      p2.bset = bset.data() + lane;
+      p2.sc = s;
+      p2.Lp = &L2;
+      nring = p2.run_window(nodes_p, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
+      row_words = L2.row_words;
+      for (uint32_t k = 0; k < 3 * row_words; ++k) rows.push_back(p2.scr.w(L2.o_rows + k));
+    }
     const FastaRecord *recs[3] = {&R.rec[w], &C.rec[w], &U.rec[w]};
     for (int r = 0; r < 3; ++r) {
       fprintf(pir, ">%s %s\n", recs[r]->name.c_str(), recs[r]->title.c_str());
-      for (int k = 0; k < nring; ++k) fputc((p2.scr.w(L2.o_rows + r * L2.row_words + (k >> 2)) >> ((k & 3) * 8)) & 0xff, pir);
+      for (int k = 0; k < nring; ++k) fputc((rows[r * row_words + (k >> 2)] >> ((k & 3) * 8)) & 0xff, pir);
       fputc('\n', pir);
     }
     if (scores) fprintf(scores, "%d %d %d %d\n", s1, s2, n1, nring);
   }
-  if (packed) fprintf(stderr, "packed: %ld of %zu windows in phase 1\n", n_packed1, n);
+  if (packed) fprintf(stderr, "packed: %ld (phase 1) and %ld (phase 2) of %zu windows\n", n_packed1, n_packed2, n);
   return 0;
 }
 
