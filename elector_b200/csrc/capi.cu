@@ -53,7 +53,7 @@ struct elector_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0, resident_ph2p = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0, resident_ph2p = 0, resident_ph2l = 0;  // POA kernel CTAs (one warp each) resident per SM
   int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
@@ -65,7 +65,8 @@ struct elector_ctx {
   std::vector<cudaEvent_t> chunk_ev;                    // 2 per chunk: inputs resident, results ready
   ScoreMatrix mat;
   ScoringSetup sc;
-  bool no_packed2 = false;  // ELECTOR_NO_PACKED2=1: phase 2 on the INT32 kernel (A/B measurements)
+  bool packed2 = false;     // ELECTOR_PACKED2=1: general windows of phase 2 on the packed kernel (A/B measurements)
+  bool no_linear2 = false;  // ELECTOR_NO_LINEAR2=1: linear windows of phase 2 on the general kernels
   DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   int64_t merged_cap = 0;  // bytes per merged-row buffer of the last merge
@@ -108,27 +109,35 @@ const int kSideStreams = 3;
 #ifndef EL_MIN_WARPS_PH2P
 #define EL_MIN_WARPS_PH2P 24  // packed DP2: register cap 80
 #endif
+#ifndef EL_MIN_WARPS_PH2L
+#define EL_MIN_WARPS_PH2L 32  // packed linear DP2: register cap 64
+#endif
 
-// packed = the segment runs the 16-bit packed kernel (poa_packed.cuh)
+// kind of a segment's kernel: INT32 cells (poa_kernel.cuh), 16-bit packed cells (poa_packed.cuh), or -- phase 2 only --
+// the packed linear x linear kernel for windows whose P1 is linear
+enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2 };
+
 template <bool GS>
-cudaError_t launch_phase(int phase, bool packed, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
+cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
   if (phase == 1) {
-    if (packed) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
+    if (kind == kPacked) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
     else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
-  } else if (packed) poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P><<<grid, 32, 0, st>>>(a, tab);
+  } else if (kind == kLinear) poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L><<<grid, 32, 0, st>>>(a, tab);
+  else if (kind == kPacked) poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P><<<grid, 32, 0, st>>>(a, tab);
   else poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2><<<grid, 32, 0, st>>>(a, tab);
   return cudaGetLastError();
 }
 
 template <bool GS>
-void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p, int &ph2p) {
+void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p, int &ph2p, int &ph2l) {
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2l, poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1, poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2, poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1p, poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2p, poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P>, 32, 0);
 }
 
-struct SegPlan { int seg, grid; size_t warp_words, scratch_off; bool packed; };
+struct SegPlan { int seg, grid; size_t warp_words, scratch_off; int kind; };
 
 // grid and scratch of every non-empty segment of one phase
 int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<SegPlan> &plan, size_t &scratch_words) {
@@ -142,15 +151,21 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     size_t total;
     SegPlan p;
     // 16-bit packed kernel when the matrix allows it and no score of the segment can leave 16 bits
-    p.packed = ctx->sc.packed_ok && (phase == 1 || !ctx->no_packed2) && (int64_t)ctx->sc.maxabs * (m0 + m1 + 4) <= kPackedSpan;
+    // 16-bit packed kernels when the matrix allows it and no score of the segment can leave 16 bits
+    const bool fits16 = ctx->sc.packed_ok && (int64_t)ctx->sc.maxabs * (m0 + m1 + 4) <= kPackedSpan;
+    int per_sm;
     if (phase == 1) {
-      if (p.packed) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; }
-      else { Layout1 L; make_layout1(L, m0, m1); total = L.total; }
+      p.kind = fits16 ? kPacked : kInt32;
+      if (p.kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1p; }
+      else { Layout1 L; make_layout1(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1; }
     } else {
-      if (p.packed) { Layout2P L; make_layout2p(L, m0, m1); total = L.total; }
-      else { Layout2 L; make_layout2(L, m0, m1); total = L.total; }
+      // windows whose P1 is linear have their own segments and, when 16 bits are enough, their own kernel; the general packed
+      // kernel is opt-in (its out-of-line frontier handling costs more than the packed cells save)
+      p.kind = !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->packed2 ? kPacked : kInt32;
+      if (p.kind == kLinear) { Layout2L L; make_layout2l(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2l; }
+      else if (p.kind == kPacked) { Layout2P L; make_layout2p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2p; }
+      else { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2; }
     }
-    const int per_sm = phase == 1 ? (p.packed ? ctx->resident_ph1p : ctx->resident_ph1) : (p.packed ? ctx->resident_ph2p : ctx->resident_ph2);
     const int resident = std::max(1, per_sm) * ctx->sm_count;
     p.seg = s;
     p.warp_words = total;
@@ -190,8 +205,8 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
     a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
     a.warp_words = (uint32_t)p.warp_words;
     a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + (phase == 1 ? 0 : 16) + p.seg;
-    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.packed, ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
-                                              : launch_phase<false>(phase, p.packed, ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
+    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
+                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
   }
@@ -315,7 +330,8 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     }
   } else ctx->mat.set_default();
   if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
-  if (const char *e = getenv("ELECTOR_NO_PACKED2")) ctx->no_packed2 = e[0] == '1';
+  if (const char *e = getenv("ELECTOR_PACKED2")) ctx->packed2 = e[0] == '1';
+  if (const char *e = getenv("ELECTOR_NO_LINEAR2")) ctx->no_linear2 = e[0] == '1';
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0) {
@@ -351,12 +367,12 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
-  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p);
-  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p);
+  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l);
+  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l);
   // experiment knobs: cap the resident warps per SM of a kernel (scratch footprint vs. latency hiding)
   auto cap = [](int &v, const char *name) { if (const char *e = getenv(name)) { const int c = atoi(e); if (c > 0 && c < v) v = c; } };
   cap(ctx->resident_ph1, "ELECTOR_WARPS_PH1"); cap(ctx->resident_ph2, "ELECTOR_WARPS_PH2");
-  cap(ctx->resident_ph1p, "ELECTOR_WARPS_PH1P"); cap(ctx->resident_ph2p, "ELECTOR_WARPS_PH2P");
+  cap(ctx->resident_ph1p, "ELECTOR_WARPS_PH1P"); cap(ctx->resident_ph2p, "ELECTOR_WARPS_PH2P"); cap(ctx->resident_ph2l, "ELECTOR_WARPS_PH2L");
   if (ctx->resident_ph1 < 1 || ctx->resident_ph2 < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;

@@ -158,8 +158,10 @@ constexpr int kNbMax = kSmallMax / 8;   // 8-row half-bands of a small window: 1
 constexpr int kN1q = 128;               // len(P1) / 4 quanta of a small window (len(P1) <= 511)
 constexpr int kSpCodes = 98;            // 0 = ref and cor identical; 1 + 3*min(pos/2, 31) + type otherwise
 constexpr int kSmallBins2 = kNbMax * kN1q * kSpCodes;
-constexpr int kNumBins2 = kBigTiers + kSmallBins2;
-constexpr int kNumSegs2 = kBigTiers + 4;
+constexpr int kLinBins2 = kNbMax * kN1q; // small windows whose P1 is linear (ref and cor identical): their own bins and segments
+constexpr int kNumBins2 = kBigTiers + kSmallBins2 + kLinBins2;
+constexpr int kNumSegs2 = kBigTiers + 8;
+constexpr int kFirstLinSeg2 = kBigTiers + 4;
 
 EL_HD int big_tier(int mx) {            // mx > kSmallMax: 1: <= 512, 2: <= 1024, ...
   int t = 1;
@@ -167,16 +169,23 @@ EL_HD int big_tier(int mx) {            // mx > kSmallMax: 1: <= 512, 2: <= 1024
   return t;
 }
 EL_HD int seg2_of_nb(int nb8) { return kBigTiers + (nb8 > 16 ? 0 : nb8 > 8 ? 1 : nb8 > 4 ? 2 : 3); }
-// largest first: big tiers, then small bins descending in (half-bands of unc, len(P1)/4, spcode)
+// largest first: big tiers, then the small general bins descending in (half-bands of unc, len(P1)/4, spcode),
+// then the small linear bins (spcode 0: DP2 is a linear x linear DP, run by Phase2L) descending in (half-bands, len(P1)/4)
 EL_HD void bin2_of(int n1, int lu, int spcode, int &bin, int &seg) {
   if (lu > kSmallMax || n1 >= 4 * kN1q) {
     const int t = big_tier(n1 > lu ? n1 : lu);
     bin = seg = kBigTiers - t;
   } else {
     const int nb8 = (lu + 7) >> 3;
-    const int small = ((nb8 - 1) * kN1q + (n1 >> 2)) * kSpCodes + spcode;
-    bin = kBigTiers + (kSmallBins2 - 1 - small);
-    seg = seg2_of_nb(nb8);
+    if (spcode == 0) {
+      const int lin = (nb8 - 1) * kN1q + (n1 >> 2);
+      bin = kBigTiers + kSmallBins2 + (kLinBins2 - 1 - lin);
+      seg = seg2_of_nb(nb8) + 4;
+    } else {
+      const int small = ((nb8 - 1) * kN1q + (n1 >> 2)) * kSpCodes + spcode;
+      bin = kBigTiers + (kSmallBins2 - 1 - small);
+      seg = seg2_of_nb(nb8);
+    }
   }
 }
 
@@ -582,6 +591,7 @@ template <bool GENERIC_SUB>
 struct Phase2 {
   typedef Layout2 Layout;
   static constexpr bool kGenericSub = GENERIC_SUB;
+  static constexpr bool kLinear = false;
   static constexpr int kSetWords = kSlotWords;
   static EL_HD void make_layout(Layout2 &L, int N1, int LU) { make_layout2(L, N1, LU); }
   LaneScratch scr;
@@ -820,7 +830,8 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     if (active) {
       int s2;
-      nring = c.run_window(a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), n1, a.unc + uo, lu, s2);
+      if constexpr (PH::kLinear) nring = c.run_linear(a.ref + ro, n1, a.unc + uo, lu, s2);   // P1 = lin(ref): no node list needed
+      else nring = c.run_window(a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), n1, a.unc + uo, lu, s2);
       a.nring[w] = nring;
       if (a.score2) a.score2[w] = s2;
       if (a.cells) {

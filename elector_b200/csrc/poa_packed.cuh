@@ -370,6 +370,7 @@ __host__ __device__ __noinline__ inline uint32_t arrange_half(uint32_t *wa, uint
 struct Phase2P {
   typedef Layout2P Layout;
   static constexpr bool kGenericSub = false;
+  static constexpr bool kLinear = false;
   static constexpr int kSetWords = kSetWordsP;
   static constexpr uint32_t kRecNode = Q2_NODE, kRecX2Y = Q2_X2Y, kRecPred = Q2_PRED;
   static EL_HD void make_layout(Layout2P &L, int N1, int LU) { make_layout2p(L, N1, LU); }
@@ -519,6 +520,88 @@ struct Phase2P {
     if (Lp->R == 6) return run_r<6>(n1, lu, s2);   // R is uniform over the warp
     if (Lp->R == 7) return run_r<7>(n1, lu, s2);
     return run_r<8>(n1, lu, s2);
+  }
+};
+
+// =============================== phase 2 of a window whose P1 is linear =========================
+// ref and cor identical (spcode 0, most windows at ELECTOR's corrected error rates): P1 = lin(ref) with
+// every node carrying both letters, so DP2 is the linear x linear DP of phase 1 with unc as the row
+// sequence.  Phase2L runs Phase1P's bands and traceback on (ref, unc) and emits the three MSA rows
+// (lpo.c:413-463, lpo_format.c:346-371 for a linear x): no node list, no frontier sets, no ordinals.
+struct Layout2L {
+  Layout1P dp;                      // o_ref = ref codes (columns), o_cor = unc codes (rows)
+  uint32_t o_rows, row_words, total;
+};
+EL_HD void make_layout2l(Layout2L &L, int N1, int LU) {
+  make_layout1p(L.dp, N1, LU);
+  uint32_t o = L.dp.total;
+  L.row_words = cdiv_u(N1 + LU, 4);
+  L.o_rows = o; o += 3 * L.row_words;
+  L.total = o;
+}
+
+struct Phase2L {
+  typedef Layout2L Layout;
+  static constexpr bool kGenericSub = false;
+  static constexpr bool kLinear = true;
+  static constexpr int kSetWords = 1;
+  static EL_HD void make_layout(Layout2L &L, int N1, int LU) { make_layout2l(L, N1, LU); }
+  LaneScratch scr;
+  uint32_t *bset;     // unused
+  Scoring sc;
+  const Layout2L *Lp;
+
+  // rows of the MSA from the x -> y map of the traceback; returns nring
+  EL_HDN int emit(const Phase1P &d, int n1, int lu) const {
+    const uint8_t *sym = sc.tab->sym;
+    const uint32_t o_x = Lp->dp.o_ref, o_y = Lp->dp.o_cor;
+    const uint32_t r0 = Lp->o_rows, r1 = Lp->o_rows + Lp->row_words, r2 = Lp->o_rows + 2 * Lp->row_words;
+    int col = 0, iy = 0;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    auto put = [&](uint32_t c0, uint32_t c1, uint32_t c2) {
+      const int sh = (col & 3) * 8;
+      w0 |= c0 << sh; w1 |= c1 << sh; w2 |= c2 << sh;
+      if ((col & 3) == 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; w0 = w1 = w2 = 0; }
+      ++col;
+    };
+    const ptrdiff_t step = (ptrdiff_t)Lp->dp.rec_words * 32;
+    const uint32_t *px = d.rec(0) + P1_X2Y * 32;
+    int q0 = (int)px[0], q1 = n1 > 1 ? (int)px[step] : -1;
+    uint32_t xw = 0;
+    for (int ix = 0; ix < n1; ++ix) {
+      const int q = q0;
+      q0 = q1;
+      q1 = ix + 2 < n1 ? (int)px[(ptrdiff_t)(ix + 2) * step] : -1;
+      if ((ix & 3) == 0) xw = scr.w(o_x + (ix >> 2));
+      const uint32_t xl = xw & 0xff; xw >>= 8;
+      const uint32_t xc = sym[xl];
+      if (q >= 0) while (iy < q) { put('.', '.', sym[scr.code_at(o_y, iy)]); ++iy; }   // unaligned unc letters: columns of their own
+      uint32_t c2 = '.';
+      if (q >= 0 && iy < lu) { c2 = sym[scr.code_at(o_y, iy)]; ++iy; }   // aligned: same column (same letter or same ring)
+      put(xc, xc, c2);
+    }
+    while (iy < lu) { put('.', '.', sym[scr.code_at(o_y, iy)]); ++iy; }
+    if (col & 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; }
+    return col;
+  }
+
+  template <int R>
+  EL_HDN int run_r(const Phase1P &d, int n1, int lu, int &s2) const {
+    s2 = d.dp<R>(n1, lu);
+    d.traceback<R>(n1, lu);
+    return emit(d, n1, lu);
+  }
+
+  EL_HDN int run_linear(const uint8_t *ref, int n1, const uint8_t *unc, int lu, int &s2) const {
+    Phase1P d;
+    d.scr = scr; d.sc = sc; d.Lp = &Lp->dp;
+    scr.pack_codes(sc.tab, ref, n1, Lp->dp.o_ref);
+    scr.pack_codes(sc.tab, unc, lu, Lp->dp.o_cor);
+    for (uint32_t k = 0; k < 5; ++k) scr.w(Lp->dp.o_cor + cdiv_u((uint32_t)lu, 4) + k) = 0;
+    scr.w(Lp->dp.o_ref + cdiv_u((uint32_t)n1, 4)) = 0;
+    if (Lp->dp.R == 6) return run_r<6>(d, n1, lu, s2);   // R is uniform over the warp
+    if (Lp->dp.R == 7) return run_r<7>(d, n1, lu, s2);
+    return run_r<8>(d, n1, lu, s2);
   }
 };
 

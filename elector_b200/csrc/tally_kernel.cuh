@@ -304,12 +304,55 @@ __device__ void find_gap_stretches(const BitRow &dc, const BitRow &dr, ReadScan 
 }
 
 // ---- the per-read tally: one CTA per read ------------------------------------------------------
-//   A  all threads: one pass over the three rows -> dot bitmasks (global scratch, 3 bits per column)
+//   A  all threads: one pass over the three rows -> dot bitmasks (3 bits per column).  The masks of a
+//      read of up to kSmemCols columns live in shared memory; longer reads use the global planes.
 //   B  thread 0: the sequential scanners of computeStats.py on the bitmasks (run to run, not column
 //      to column): left / right gaps, extension, gap stretches -> the column mask
 //   C  all threads: second pass, per-column classification under the mask (computeStats.py:291-328,
 //      371-440, 712-752), warp-shuffle + shared-memory reduction of the counters
+// Rows whose start is 16-byte aligned (the merge kernels always produce such rows) are read as
+// 16-byte vectors, 16 columns per thread and load; other rows take the byte path.
 constexpr int kNAcc = 19;  // accumulators reduced per read (see below)
+constexpr int kSmemCols = 32768;
+constexpr int kSmemMaskWords = kSmemCols / 32;
+
+// 4 bytes -> 4 bits: bit k set when byte k of x equals the byte replicated in pat
+__device__ __forceinline__ uint32_t eq_nibble(uint32_t x, uint32_t pat) {
+  const uint32_t z = x ^ pat;
+  const uint32_t m = ~(((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z | 0x7f7f7f7fu);   // 0x80 in every zero byte of z
+  return (((m >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+__device__ __forceinline__ uint32_t eq_mask16(const uint4 &v, uint32_t pat) {
+  return eq_nibble(v.x, pat) | (eq_nibble(v.y, pat) << 4) | (eq_nibble(v.z, pat) << 8) | (eq_nibble(v.w, pat) << 12);
+}
+
+struct ColumnMask {   // which columns the classification skips (gapsAndExtensions + gap stretches)
+  int lmask, rmask, nkeys;
+  int key_a[kMaxStretchKeys], key_b[kMaxStretchKeys];
+};
+
+// classification of one column (computeStats.py:291-328,371-440,712-752)
+__device__ __forceinline__ void classify_column(int i, uint32_t r_, uint32_t c_, uint32_t u_, const ColumnMask &cm, int (&acc)[kNAcc]) {
+  acc[13] += (r_ == 'g' || r_ == 'c' || r_ == 'G' || r_ == 'C');
+  acc[14] += (c_ == 'g' || c_ == 'c' || c_ == 'G' || c_ == 'C');
+  acc[15] += r_ == '.'; acc[16] += c_ == '.'; acc[17] += u_ == '.';
+  bool ok = i >= cm.lmask && i <= cm.rmask;
+  for (int k = 0; k < cm.nkeys; ++k) {
+    const bool in = i >= cm.key_a[k] && i <= cm.key_b[k];
+    if (in) { ok = false; acc[18] += (r_ == '.'); }           // dots of the reference row inside stretches
+  }
+  if (!ok) return;
+  if (c_ != r_) { if (r_ == '.') ++acc[7]; else if (c_ != '.') ++acc[9]; else ++acc[8]; }
+  if (u_ != r_) { if (r_ == '.') ++acc[10]; else if (u_ != '.') ++acc[12]; else ++acc[11]; }
+  if (r_ == u_) {
+    if (u_ != c_) { ++acc[1]; ++acc[4]; } else { ++acc[0]; ++acc[3]; }
+    ++acc[5];
+  } else {
+    if (r_ == c_) { ++acc[0]; ++acc[3]; }
+    else { if (u_ == c_) { ++acc[2]; ++acc[1]; } ++acc[4]; }
+    ++acc[6];
+  }
+}
 
 __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const uint8_t *R, const uint8_t *C, const uint8_t *U,
                                                           const int64_t *off, const int32_t *len, uint32_t *bits, int64_t plane_words,
@@ -320,17 +363,38 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
   const uint8_t *rr = R + off[r], *cc = C + off[r], *uu = U + off[r];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool assessed = L > 10;
+  const bool vec = (off[r] & 15) == 0;
   __shared__ ReadScan sc;
   __shared__ int sm[4][kNAcc];
-  uint32_t *br = bits + (off[r] >> 5) + r, *bc = br + plane_words, *bu = bc + plane_words;
-  if (assessed) {
-    for (int base = wid * 32; base < L; base += 128) {   // A
-      const int i = base + lane;
-      const bool in = i < L;
-      const unsigned mr = __ballot_sync(0xffffffffu, in && rr[i] == '.');
-      const unsigned mc = __ballot_sync(0xffffffffu, in && cc[i] == '.');
-      const unsigned mu = __ballot_sync(0xffffffffu, in && uu[i] == '.');
-      if (lane == 0) { br[base >> 5] = mr; bc[base >> 5] = mc; bu[base >> 5] = mu; }
+  __shared__ uint32_t s_bits[3 * kSmemMaskWords];
+  uint32_t *br, *bc, *bu;
+  if (L <= kSmemCols) { br = s_bits; bc = s_bits + kSmemMaskWords; bu = s_bits + 2 * kSmemMaskWords; }
+  else { br = bits + (off[r] >> 5) + r; bc = br + plane_words; bu = bc + plane_words; }
+  if (assessed) {                                        // A
+    if (vec) {
+      const uint4 *r4 = reinterpret_cast<const uint4 *>(rr), *c4 = reinterpret_cast<const uint4 *>(cc), *u4 = reinterpret_cast<const uint4 *>(uu);
+      const int nq = (L + 15) >> 4, nq2 = (nq + 1) & ~1;   // 16-column groups; lanes work in pairs (one mask word per pair)
+      for (int q = threadIdx.x; q < ((nq2 + 127) & ~127); q += 128) {
+        uint32_t mr = 0, mc = 0, mu = 0;
+        if (q < nq) {
+          const int left = L - q * 16;
+          const uint32_t valid = left >= 16 ? 0xffffu : (1u << left) - 1u;
+          mr = eq_mask16(r4[q], 0x2e2e2e2eu) & valid;
+          mc = eq_mask16(c4[q], 0x2e2e2e2eu) & valid;
+          mu = eq_mask16(u4[q], 0x2e2e2e2eu) & valid;
+        }
+        const uint32_t pr = __shfl_down_sync(0xffffffffu, mr, 1), pc = __shfl_down_sync(0xffffffffu, mc, 1), pu = __shfl_down_sync(0xffffffffu, mu, 1);
+        if (!(q & 1) && q < nq2) { br[q >> 1] = mr | (pr << 16); bc[q >> 1] = mc | (pc << 16); bu[q >> 1] = mu | (pu << 16); }
+      }
+    } else {
+      for (int base = wid * 32; base < L; base += 128) {
+        const int i = base + lane;
+        const bool in = i < L;
+        const unsigned mr = __ballot_sync(0xffffffffu, in && rr[i] == '.');
+        const unsigned mc = __ballot_sync(0xffffffffu, in && cc[i] == '.');
+        const unsigned mu = __ballot_sync(0xffffffffu, in && uu[i] == '.');
+        if (lane == 0) { br[base >> 5] = mr; bc[base >> 5] = mc; bu[base >> 5] = mu; }
+      }
     }
   }
   __syncthreads();
@@ -355,30 +419,27 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
   int acc[kNAcc];                                        // C
 #pragma unroll
   for (int k = 0; k < kNAcc; ++k) acc[k] = 0;
-  const int lmask = sc.gl >= T_THRESH ? sc.gl : 0;                 // columns [0, gl) masked
-  const int rmask = sc.gr >= T_THRESH ? L - sc.gr : L - 1;         // columns (L-gr, L-1] masked
+  ColumnMask cm;
+  cm.lmask = sc.gl >= T_THRESH ? sc.gl : 0;                        // columns [0, gl) masked
+  cm.rmask = sc.gr >= T_THRESH ? L - sc.gr : L - 1;                // columns (L-gr, L-1] masked
+  cm.nkeys = sc.nkeys;
+#pragma unroll
+  for (int k = 0; k < kMaxStretchKeys; ++k) { cm.key_a[k] = sc.key_a[k]; cm.key_b[k] = sc.key_b[k]; }
   if (assessed) {
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-      const uint8_t r_ = rr[i], c_ = cc[i], u_ = uu[i];
-      acc[13] += (r_ == 'g' || r_ == 'c' || r_ == 'G' || r_ == 'C');
-      acc[14] += (c_ == 'g' || c_ == 'c' || c_ == 'G' || c_ == 'C');
-      acc[15] += r_ == '.'; acc[16] += c_ == '.'; acc[17] += u_ == '.';
-      bool ok = i >= lmask && i <= rmask;
-      for (int k = 0; k < sc.nkeys; ++k) {
-        const bool in = i >= sc.key_a[k] && i <= sc.key_b[k];
-        if (in) { ok = false; acc[18] += (r_ == '.'); }           // dots of the reference row inside stretches
+    if (vec) {
+      const uint4 *r4 = reinterpret_cast<const uint4 *>(rr), *c4 = reinterpret_cast<const uint4 *>(cc), *u4 = reinterpret_cast<const uint4 *>(uu);
+      const int nq = (L + 15) >> 4;
+      for (int q = threadIdx.x; q < nq; q += 128) {
+        const uint4 vr = r4[q], vc = c4[q], vu = u4[q];
+        const uint32_t wr[4] = {vr.x, vr.y, vr.z, vr.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w}, wu[4] = {vu.x, vu.y, vu.z, vu.w};
+        const int i0 = q * 16, n = min(16, L - i0);
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+          if (b < n) classify_column(i0 + b, (wr[b >> 2] >> (8 * (b & 3))) & 0xffu, (wc[b >> 2] >> (8 * (b & 3))) & 0xffu,
+                                     (wu[b >> 2] >> (8 * (b & 3))) & 0xffu, cm, acc);
       }
-      if (!ok) continue;
-      if (c_ != r_) { if (r_ == '.') ++acc[7]; else if (c_ != '.') ++acc[9]; else ++acc[8]; }
-      if (u_ != r_) { if (r_ == '.') ++acc[10]; else if (u_ != '.') ++acc[12]; else ++acc[11]; }
-      if (r_ == u_) {
-        if (u_ != c_) { ++acc[1]; ++acc[4]; } else { ++acc[0]; ++acc[3]; }
-        ++acc[5];
-      } else {
-        if (r_ == c_) { ++acc[0]; ++acc[3]; }
-        else { if (u_ == c_) { ++acc[2]; ++acc[1]; } ++acc[4]; }
-        ++acc[6];
-      }
+    } else {
+      for (int i = threadIdx.x; i < L; i += blockDim.x) classify_column(i, rr[i], cc[i], uu[i], cm, acc);
     }
   }
 #pragma unroll

@@ -4,7 +4,7 @@
 // moves, fused emit) can be checked against the oracle in the GPU-less container.
 // It is never linked into the product library; the product has no CPU path.
 //
-// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores|-] [packed]
+// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores|-] [packed|packed-general]
 // packed: windows the library would run through the 16-bit packed kernels (poa_packed.cuh) do so here too
 #include <cstdio>
 #include <cstdlib>
@@ -18,8 +18,8 @@
 using namespace elector;
 
 template <bool GS>
-static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed) {
-  long n_packed1 = 0, n_packed2 = 0;
+static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed, bool general_only) {
+  long n_packed1 = 0, n_packed2 = 0, n_linear2 = 0;
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
     const int lr = R.rec[w].len, lc = C.rec[w].len, lu = U.rec[w].len;
@@ -59,7 +59,21 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     int s2, nring;
     std::vector<uint32_t> rows;   // the three MSA rows, 4 letters per word, row_words words each
     uint32_t row_words;
-    if (packed && sc.packed_ok && (long)sc.maxabs * (cap_n + cap_u + 4) <= kPackedSpan) {
+    const bool fits16 = packed && sc.packed_ok && (long)sc.maxabs * (cap_n + cap_u + 4) <= kPackedSpan;
+    if (fits16 && seg >= kFirstLinSeg2 && !general_only) {     // P1 linear: the library runs Phase2L
+      Layout2L L2;
+      make_layout2l(L2, cap_n, cap_u);
+      std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
+      Phase2L p2;
+      p2.scr.base = scratch2.data() + lane;
+      p2.bset = nullptr;
+      p2.sc = s;
+      p2.Lp = &L2;
+      nring = p2.run_linear((const uint8_t *)R.seq.data() + R.rec[w].off, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
+      row_words = L2.row_words;
+      for (uint32_t k = 0; k < 3 * row_words; ++k) rows.push_back(p2.scr.w(L2.o_rows + k));
+      ++n_linear2;
+    } else if (fits16) {
       Layout2P L2;
       make_layout2p(L2, cap_n, cap_u);
       std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
@@ -95,7 +109,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     }
     if (scores) fprintf(scores, "%d %d %d %d\n", s1, s2, n1, nring);
   }
-  if (packed) fprintf(stderr, "packed: %ld (phase 1) and %ld (phase 2) of %zu windows\n", n_packed1, n_packed2, n);
+  if (packed) fprintf(stderr, "packed: %ld (phase 1), %ld (phase 2 general) and %ld (phase 2 linear) of %zu windows\n", n_packed1, n_packed2, n_linear2, n);
   return 0;
 }
 
@@ -111,8 +125,9 @@ int main(int argc, char **argv) {
   FILE *pir = fopen(argv[5], "w");
   FILE *scores = argc > 6 && argv[6][0] != '-' ? fopen(argv[6], "w") : nullptr;
   if (!pir) return 1;
-  const bool packed = argc > 7 && std::string(argv[7]) == "packed";
-  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores, packed); else run<false>(sc, R, C, U, pir, scores, packed);
+  const bool packed = argc > 7 && (std::string(argv[7]) == "packed" || std::string(argv[7]) == "packed-general");
+  const bool general_only = argc > 7 && std::string(argv[7]) == "packed-general";   // linear windows through Phase2P as well
+  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores, packed, general_only); else run<false>(sc, R, C, U, pir, scores, packed, general_only);
   fclose(pir);
   if (scores) fclose(scores);
   return 0;

@@ -9,14 +9,15 @@ import pytest
 from conftest import GOLDEN_SETS, parse_dump
 
 
-@pytest.mark.parametrize("mode", ["int32", "packed"])
+@pytest.mark.parametrize("mode", ["int32", "packed", "packed-general"])
 @pytest.mark.parametrize("name", GOLDEN_SETS)
 def test_emulated_kernel_equals_reference(golden_dir, emul_bin, name, mode, tmp_path):
-    """mode packed: the 16-bit packed kernels (poa_packed.cuh) wherever the library would use them"""
+    """mode packed: the 16-bit packed kernels (poa_packed.cuh) wherever the library would use them (Phase1P, Phase2L for
+    windows whose P1 is linear, Phase2P for the rest); packed-general: Phase2P for every window"""
     d = golden_dir
     pir, sc = str(tmp_path / "e.pir"), str(tmp_path / "e.scores")
     cmd = [emul_bin, d + "/blosum80.mat", "%s/%s.ref.fa" % (d, name), "%s/%s.cor.fa" % (d, name),
-           "%s/%s.unc.fa" % (d, name), pir, sc] + (["packed"] if mode == "packed" else [])
+           "%s/%s.unc.fa" % (d, name), pir, sc] + ([mode] if mode != "int32" else [])
     assert subprocess.call(cmd) == 0
     assert open(pir, "rb").read() == open("%s/%s.pir" % (d, name), "rb").read()
     gold = parse_dump("%s/%s.dump" % (d, name))
@@ -52,7 +53,7 @@ def test_emulated_kernel_rejects_unsupported_matrix(golden_dir, emul_bin, tmp_pa
     assert rc == 3
 
 
-@pytest.mark.parametrize("mode", ["int32", "packed"])
+@pytest.mark.parametrize("mode", ["int32", "packed", "packed-general"])
 def test_emulated_kernel_long_windows(golden_dir, emul_bin, mode, tmp_path):
     """many bands, 8- and 16-row last bands, long placeholder / trimmed windows, vs the oracle"""
     from oracle import oracle, synth
@@ -74,6 +75,6 @@ def test_emulated_kernel_long_windows(golden_dir, emul_bin, mode, tmp_path):
         paths.append(p)
     pir, opir = str(tmp_path / "e.pir"), str(tmp_path / "o.pir")
     mp = golden_dir + "/blosum80.mat"
-    assert subprocess.call([emul_bin, mp, paths[0], paths[1], paths[2], pir] + (["-", "packed"] if mode == "packed" else [])) == 0
+    assert subprocess.call([emul_bin, mp, paths[0], paths[1], paths[2], pir] + (["-", mode] if mode != "int32" else [])) == 0
     assert oracle.poa_files(mp, paths[0], paths[1], paths[2], opir) == 0
     assert open(pir, "rb").read() == open(opir, "rb").read()
