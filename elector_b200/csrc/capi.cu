@@ -15,6 +15,7 @@
 #include "host_io.hpp"
 #include "poa_kernel.cuh"
 #include "poa_packed.cuh"
+#include "poa_coop.cuh"
 #include "bin_kernel.cuh"
 #include "host_setup.hpp"
 #include "tally_kernel.cuh"
@@ -53,7 +54,8 @@ struct elector_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0, resident_ph2p = 0, resident_ph2l = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0, resident_ph2p = 0, resident_ph2l = 0, resident_coop = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int coop_group = kCoopGroupDefault;  // windows per warp of the warp-cooperative kernel; 0 = the longest windows stay thread-per-window (ELECTOR_COOP_GROUP)
   int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
@@ -71,6 +73,16 @@ struct elector_ctx {
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   int64_t merged_cap = 0;  // bytes per merged-row buffer of the last merge
   DevBuf d_wdst, d_sums, d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
+  // ELECTOR_TRACE: start / stop events around every segment launch of the last run_device call
+  struct SegTrace { int phase, seg, kind, grid, count; cudaEvent_t e0, e1; };
+  std::vector<SegTrace> seg_trace;
+  std::vector<cudaEvent_t> seg_ev_pool;
+  size_t seg_ev_used = 0;
+  bool trace = false;
+  cudaEvent_t trace_event() {
+    if (seg_ev_used == seg_ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); seg_ev_pool.push_back(e); }
+    return seg_ev_pool[seg_ev_used++];
+  }
   std::string err;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -115,11 +127,14 @@ const int kSideStreams = 3;
 
 // kind of a segment's kernel: INT32 cells (poa_kernel.cuh), 16-bit packed cells (poa_packed.cuh), or -- phase 2 only --
 // the packed linear x linear kernel for windows whose P1 is linear
-enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2 };
+// or -- phase 2 only -- the warp-cooperative INT32 kernel for the segments that hold the longest windows (poa_coop.cuh)
+enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3 };
 
 template <bool GS>
-cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab) {
-  if (phase == 1) {
+cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab, int coop_group) {
+  if (kind == kCoop && phase == 1) poa_dp1_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group);
+  else if (kind == kCoop) poa_dp2_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group);
+  else if (phase == 1) {
     if (kind == kPacked) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
     else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
   } else if (kind == kLinear) poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L><<<grid, 32, 0, st>>>(a, tab);
@@ -129,7 +144,11 @@ cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int g
 }
 
 template <bool GS>
-void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p, int &ph2p, int &ph2l) {
+void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p, int &ph2p, int &ph2l, int &coop) {
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop, poa_dp2_coop_kernel<GS>, 32, 0);
+  int coop1 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop1, poa_dp1_coop_kernel<GS>, 32, 0);
+  coop = std::min(coop, coop1);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2l, poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1, poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1>, 32, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2, poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2>, 32, 0);
@@ -155,21 +174,27 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     const bool fits16 = ctx->sc.packed_ok && (int64_t)ctx->sc.maxabs * (m0 + m1 + 4) <= kPackedSpan;
     int per_sm;
     if (phase == 1) {
-      p.kind = fits16 ? kPacked : kInt32;
-      if (p.kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1p; }
+      // the segments of the longest windows (cor longer than 128 letters): a warp per window instead of a thread
+      p.kind = (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : fits16 ? kPacked : kInt32;
+      if (p.kind == kCoop) { LayoutC1 L; make_layout_c1(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
+      else if (p.kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1p; }
       else { Layout1 L; make_layout1(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1; }
     } else {
       // windows whose P1 is linear have their own segments and, when 16 bits are enough, their own kernel; the general packed
       // kernel is opt-in (its out-of-line frontier handling costs more than the packed cells save)
-      p.kind = !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->packed2 ? kPacked : kInt32;
-      if (p.kind == kLinear) { Layout2L L; make_layout2l(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2l; }
+      // the segments of the longest windows (more than 128 rows, general and linear): a warp per window instead of a thread
+      const bool longest = s <= kBigTiers || s == kFirstLinSeg2;
+      p.kind = (longest && ctx->coop_group > 0) ? kCoop : !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->packed2 ? kPacked : kInt32;
+      if (p.kind == kCoop) { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
+      else if (p.kind == kLinear) { Layout2L L; make_layout2l(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2l; }
       else if (p.kind == kPacked) { Layout2P L; make_layout2p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2p; }
       else { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2; }
     }
     const int resident = std::max(1, per_sm) * ctx->sm_count;
     p.seg = s;
     p.warp_words = total;
-    p.grid = (int)std::min<int64_t>(resident, ((int64_t)si.count + 31) / 32);
+    const int per_warp_items = p.kind == kCoop ? ctx->coop_group : 32;
+    p.grid = (int)std::min<int64_t>(resident, ((int64_t)si.count + per_warp_items - 1) / per_warp_items);
     // bound the scratch of segments with huge windows: fewer resident warps
     const size_t per_warp = total * 32;
     while (p.grid > 1 && per_warp * (size_t)p.grid > budget_words / 2) p.grid = (p.grid + 1) / 2;
@@ -180,6 +205,8 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     plan.push_back(p);
   }
   if (scratch_words > 2 * budget_words) return ctx->fail(ELECTOR_ETOOLARGE, "call needs %zu MiB of scratch", (scratch_words * 4) >> 20);
+  // launch order: the warp-cooperative segments first (they hold the longest windows and must not queue behind the bulk)
+  std::stable_partition(plan.begin(), plan.end(), [](const SegPlan &q) { return q.kind == kCoop; });
   return ELECTOR_OK;
 }
 
@@ -199,16 +226,19 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
       if (!(used_side & (1 << side))) { CU(cudaStreamWaitEvent(ls, ctx->ev_fork, 0)); used_side |= 1 << side; }
       side = (side + 1) % kSideStreams;
     }
+    elector_ctx::SegTrace tr{phase, p.seg, p.kind, p.grid, si.count, nullptr, nullptr};
+    if (ctx->trace) { tr.e0 = ctx->trace_event(); tr.e1 = ctx->trace_event(); CU(cudaEventRecord(tr.e0, ls)); }
     PoaArgs a = base;
     a.items = ctx->d_items.as<int32_t>() + si.start;
     a.n_items = si.count;
     a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
     a.warp_words = (uint32_t)p.warp_words;
     a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + (phase == 1 ? 0 : 16) + p.seg;
-    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>())
-                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>());
+    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group)
+                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group);
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
+    if (ctx->trace) { CU(cudaEventRecord(tr.e1, ls)); ctx->seg_trace.push_back(tr); }
   }
   for (int k = 0; k < kSideStreams; ++k)
     if (used_side & (1 << k)) {
@@ -306,6 +336,19 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
 // adds the device time between ev0 and ev1 (both already reached) to the running total of a call
 void add_kernel_ms(elector_ctx *ctx) {
   float ms = 0.f;
+  if (ctx->trace) {   // device timeline of the segment launches, ms after the start of the run_device call
+    static const char *kinds[] = {"int32", "packed", "linear", "coop"};
+    for (const auto &t : ctx->seg_trace) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ctx->ev0, t.e0);
+      cudaEventElapsedTime(&b, ctx->ev0, t.e1);
+      fprintf(stderr, "[elector trace]   phase %d segment %2d (%s): %8d windows, grid %5d, %7.3f -> %7.3f ms\n", t.phase, t.seg, kinds[t.kind], t.count, t.grid, a, b);
+    }
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) fprintf(stderr, "[elector trace]   phase 1 done %.3f ms", ms);
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) fprintf(stderr, ", all done %.3f ms\n", ms);
+    ctx->seg_trace.clear();
+    ctx->seg_ev_used = 0;
+  }
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms += ms;
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) ctx->last_ms_phase1 += ms;
 }
@@ -330,6 +373,7 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     }
   } else ctx->mat.set_default();
   if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
+  ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   if (const char *e = getenv("ELECTOR_PACKED2")) ctx->packed2 = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_LINEAR2")) ctx->no_linear2 = e[0] == '1';
   int ndev = 0;
@@ -367,12 +411,15 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
-  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l);
-  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l);
+  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l, ctx->resident_coop);
+  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l, ctx->resident_coop);
+  if (const char *e = getenv("ELECTOR_COOP_GROUP")) ctx->coop_group = std::max(0, std::min(32, atoi(e)));
+  if (ctx->resident_coop < 1) ctx->coop_group = 0;
   // experiment knobs: cap the resident warps per SM of a kernel (scratch footprint vs. latency hiding)
   auto cap = [](int &v, const char *name) { if (const char *e = getenv(name)) { const int c = atoi(e); if (c > 0 && c < v) v = c; } };
   cap(ctx->resident_ph1, "ELECTOR_WARPS_PH1"); cap(ctx->resident_ph2, "ELECTOR_WARPS_PH2");
   cap(ctx->resident_ph1p, "ELECTOR_WARPS_PH1P"); cap(ctx->resident_ph2p, "ELECTOR_WARPS_PH2P"); cap(ctx->resident_ph2l, "ELECTOR_WARPS_PH2L");
+  cap(ctx->resident_coop, "ELECTOR_WARPS_COOP");
   if (ctx->resident_ph1 < 1 || ctx->resident_ph2 < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;
@@ -397,6 +444,7 @@ void elector_poa_free(elector_ctx *ctx) {
   }
   if (ctx->h_bintab) cudaFreeHost(ctx->h_bintab);
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->seg_ev_pool) cudaEventDestroy(e);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -423,6 +471,7 @@ int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const
     return ctx->fail(ELECTOR_EINVAL, "null argument");
   CU(cudaSetDevice(ctx->device));
   (void)h_roff; (void)h_coff; (void)h_uoff;  // binning happens on the device
+  ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   ctx->last_ms = ctx->last_ms_phase1 = 0.f;
   ctx->last_launches = 0;
   int rc = run_device(ctx, n, d_ref, d_roff, d_cor, d_coff, d_unc, d_uoff, d_rows, rows_cap,
@@ -491,7 +540,7 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
     CU(cudaEventCreate(&e));
     ctx->chunk_ev.push_back(e);
   }
-  const bool trace = getenv("ELECTOR_TRACE") != nullptr;
+  const bool trace = ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   const cudaEvent_t ev_start = ctx->chunk_ev[3 * nchunks];
   const auto host_t0 = std::chrono::steady_clock::now();
   auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };

@@ -419,8 +419,10 @@ constexpr int kSlotWords = (2 * kBand + 1) * 32;  // one frontier set of a warp 
 // left list, align_lpo_po2.c:334-371, with the winning ordinals in po[0] (match) / po[32]
 // (X-gap)) is in A and the frontier the node does not replace is in B.
 // Returns kindA | kindB << 2 | 16 if the sets traded places (A is now in sb).
+// ordrow0 / ord_or (warp-cooperative DP, poa_coop.cuh): the set covers rows ordrow0 .. ordrow0+R-1 of its 16-row band, and
+// a set that does not start the band ORs its ordinals into the words the rows above it wrote one step earlier.
 __host__ __device__ __noinline__ inline uint32_t arrange_sets(uint32_t *sa, uint32_t *sb, int R, int r0, uint32_t ra, int kindA,
-                                                        int kindB, int open, int ext, uint32_t *po) {
+                                                        int kindB, int open, int ext, uint32_t *po, int ordrow0 = 0, bool ord_or = false) {
   const int m = (ra >> 8) & 3;
   uint32_t flipped = 0;
   auto swap_sets = [&]() {
@@ -451,7 +453,7 @@ __host__ __device__ __noinline__ inline uint32_t arrange_sets(uint32_t *sa, uint
       int bS = (int)sa[2 * R * 32]; uint32_t o = oA;
       if (virt) { const int a = bS; bS = vS(r0 - 1); o = 0; if (a > bS) { bS = a; o = oA; } }
       if (two) { const int hb = (int)sb[2 * R * 32]; if (hb > bS) { bS = hb; o = oB; } }
-      sa[2 * R * 32] = (uint32_t)bS; owM |= o;
+      sa[2 * R * 32] = (uint32_t)bS; owM |= o << (2 * ordrow0);
     }
     for (int r = 0; r < R; ++r) {
       const int aS = (int)sa[r * 32], aG = (int)sa[(R + r) * 32];
@@ -467,10 +469,12 @@ __host__ __device__ __noinline__ inline uint32_t arrange_sets(uint32_t *sa, uint
         if (sG > bG) { bG = sG; oX = oB; }
       }
       sa[r * 32] = (uint32_t)bS; sa[(R + r) * 32] = (uint32_t)bG;
-      if (r < kBand - 1) owM |= oM << (2 * (r + 1));   // row r0+15's ordinal is the next band's halo
-      owX |= oX << (2 * r);
+      const int mr = ordrow0 + r + 1;                  // the row whose match move starts from this cell
+      if (mr < kBand) owM |= oM << (2 * mr);           // the band's last row feeds the next band's halo
+      owX |= oX << (2 * (ordrow0 + r));
     }
-    po[0] = owM; po[32] = owX;
+    if (ord_or) { po[0] |= owM; po[32] |= owX; }
+    else { po[0] = owM; po[32] = owX; }
   }
   kindA = m;
   kindB &= ~m;
@@ -793,6 +797,42 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
   }
 }
 
+#ifdef __CUDACC__
+// The MSA rows of a group leave the scratch: output space is allocated with a warp prefix sum of 3*stride and ONE
+// atomic per warp; every lane then copies its three rows (window w, nring columns) as 32-bit words.
+__device__ __forceinline__ void store_window_rows(const PoaArgs &a, const LaneScratch &scr, uint32_t o_rows, uint32_t row_words,
+                                                  bool active, int w, int nring) {
+  const int lane = threadIdx.x;
+  const int stride = (nring + 3) & ~3;
+  const int bytes = 3 * stride;
+  int incl = bytes;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(EL_WARP_FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int total = __shfl_sync(EL_WARP_FULL, incl, 31);
+  unsigned long long wbase = 0;
+  if (lane == 0) wbase = atomicAdd(a.rows_cursor, (unsigned long long)total);
+  wbase = __shfl_sync(EL_WARP_FULL, wbase, 0);
+  if (active) {
+    const int64_t off = (int64_t)wbase + incl - bytes;
+    a.row_off[w] = off;
+    a.row_stride[w] = stride;
+    if (off + bytes > a.rows_cap) atomicExch(a.error_flag, 1);
+    else {
+      uint32_t *dst = reinterpret_cast<uint32_t *>(a.rows_out + off);
+      const int sw4 = stride >> 2;
+      for (int s = 0; s < 3; ++s) {
+        const uint32_t *srow = scr.at(o_rows + s * row_words);
+        uint32_t *drow = dst + s * sw4;
+#pragma unroll 4
+        for (int k = 0; k < sw4; ++k) drow[k] = srow[k * 32];
+      }
+    }
+  }
+}
+
+#endif
 // PH = Phase2<GENERIC_SUB> (INT32 cells) or Phase2P (poa_packed.cuh)
 template <class PH, int MIN_WARPS>
 __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const SymbolTables *g_tab) {
@@ -840,34 +880,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
       }
     }
     __syncwarp();
-    // output allocation: warp prefix sum of 3*stride, one atomic per warp
-    const int stride = (nring + 3) & ~3;
-    const int bytes = 3 * stride;
-    int incl = bytes;
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(EL_WARP_FULL, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const int total = __shfl_sync(EL_WARP_FULL, incl, 31);
-    unsigned long long wbase = 0;
-    if (lane == 0) wbase = atomicAdd(a.rows_cursor, (unsigned long long)total);
-    wbase = __shfl_sync(EL_WARP_FULL, wbase, 0);
-    if (active) {
-      const int64_t off = (int64_t)wbase + incl - bytes;
-      a.row_off[w] = off;
-      a.row_stride[w] = stride;
-      if (off + bytes > a.rows_cap) atomicExch(a.error_flag, 1);
-      else {
-        uint32_t *dst = reinterpret_cast<uint32_t *>(a.rows_out + off);
-        const int sw4 = stride >> 2;
-        for (int s = 0; s < 3; ++s) {
-          const uint32_t *srow = c.scr.at(s_layout.o_rows + s * s_layout.row_words);
-          uint32_t *drow = dst + s * sw4;
-#pragma unroll 4
-          for (int k = 0; k < sw4; ++k) drow[k] = srow[k * 32];
-        }
-      }
-    }
+    store_window_rows(a, c.scr, s_layout.o_rows, s_layout.row_words, active, w, nring);
     __syncwarp();
   }
 }

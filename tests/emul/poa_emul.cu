@@ -4,7 +4,7 @@
 // moves, fused emit) can be checked against the oracle in the GPU-less container.
 // It is never linked into the product library; the product has no CPU path.
 //
-// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores|-] [packed|packed-general]
+// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores|-] [packed|packed-general|coop]
 // packed: windows the library would run through the 16-bit packed kernels (poa_packed.cuh) do so here too
 #include <cstdio>
 #include <cstdlib>
@@ -14,11 +14,12 @@
 #include "../../elector_b200/csrc/host_setup.hpp"
 #include "../../elector_b200/csrc/bin_kernel.cuh"
 #include "../../elector_b200/csrc/poa_packed.cuh"
+#include "../../elector_b200/csrc/poa_coop.cuh"
 
 using namespace elector;
 
 template <bool GS>
-static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed, bool general_only) {
+static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed, bool general_only, bool coop) {
   long n_packed1 = 0, n_packed2 = 0, n_linear2 = 0;
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
@@ -31,7 +32,21 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     uint16_t *nodes_p = reinterpret_cast<uint16_t *>(nodes64.data());
     int s1, spcode, n1;
     const int cap_r = lr + (int)(w % 3), cap_c = lc + (int)(w % 5);
-    if (packed && sc.packed_ok && (long)sc.maxabs * (cap_r + cap_c + 4) <= kPackedSpan) {
+    if (coop) {   // phase 1 through the warp-cooperative wavefront (lin(ref) as a node list)
+      LayoutC1 L1;
+      make_layout_c1(L1, cap_r, cap_c);
+      std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
+      std::vector<uint32_t> bset((size_t)2 * kSlotWords, 0xdeadbeefu);
+      Phase2<GS> p1;
+      p1.scr.base = scratch1.data() + lane;
+      p1.bset = bset.data() + lane;
+      p1.sc = s;
+      p1.Lp = &L1.l2;
+      coop1_before<GS>(p1, L1, (const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p);
+      int bj = -1;
+      coop_dp_emulated<GS>(p1, bset.data(), lr, lc, s1, bj);
+      n1 = coop1_after<GS>(p1, L1, lr, lc, bj, nodes_p, spcode);
+    } else if (packed && sc.packed_ok && (long)sc.maxabs * (cap_r + cap_c + 4) <= kPackedSpan) {
       Layout1P L1;
       make_layout1p(L1, cap_r, cap_c);
       std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
@@ -60,7 +75,25 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     std::vector<uint32_t> rows;   // the three MSA rows, 4 letters per word, row_words words each
     uint32_t row_words;
     const bool fits16 = packed && sc.packed_ok && (long)sc.maxabs * (cap_n + cap_u + 4) <= kPackedSpan;
-    if (fits16 && seg >= kFirstLinSeg2 && !general_only) {     // P1 linear: the library runs Phase2L
+    if (coop) {   // the warp-cooperative DP2 of poa_coop.cuh (32 lanes emulated one after the other), serial steps of Phase2
+      Layout2 L2;
+      make_layout2(L2, cap_n, cap_u);
+      std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
+      std::vector<uint32_t> bset((size_t)2 * kSlotWords, 0xdeadbeefu);
+      Phase2<GS> p2;
+      p2.scr.base = scratch2.data() + lane;
+      p2.bset = bset.data() + lane;
+      p2.sc = s;
+      p2.Lp = &L2;
+      p2.scr.pack_codes(s.tab, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, L2.o_unc);
+      p2.prepare(nodes_p, n1);
+      int bj = -1;
+      coop_dp_emulated<GS>(p2, bset.data(), n1, lu, s2, bj);
+      p2.traceback(lu, bj);
+      nring = p2.fuse_emit(n1, lu);
+      row_words = L2.row_words;
+      for (uint32_t k = 0; k < 3 * row_words; ++k) rows.push_back(p2.scr.w(L2.o_rows + k));
+    } else if (fits16 && seg >= kFirstLinSeg2 && !general_only) {     // P1 linear: the library runs Phase2L
       Layout2L L2;
       make_layout2l(L2, cap_n, cap_u);
       std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
@@ -127,7 +160,8 @@ int main(int argc, char **argv) {
   if (!pir) return 1;
   const bool packed = argc > 7 && (std::string(argv[7]) == "packed" || std::string(argv[7]) == "packed-general");
   const bool general_only = argc > 7 && std::string(argv[7]) == "packed-general";   // linear windows through Phase2P as well
-  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores, packed, general_only); else run<false>(sc, R, C, U, pir, scores, packed, general_only);
+  const bool coop = argc > 7 && std::string(argv[7]) == "coop";   // phase 2 of every window through the warp-cooperative DP
+  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores, packed, general_only, coop); else run<false>(sc, R, C, U, pir, scores, packed, general_only, coop);
   fclose(pir);
   if (scores) fclose(scores);
   return 0;

@@ -92,6 +92,38 @@ def test_large_tier_vs_oracle(ctx):
         assert res.window_rows(w) == oracle.window_rows(o, w), w
 
 
+@pytest.mark.parametrize("group", ["0", "1", "8", "32"])
+def test_long_windows_warp_cooperative_vs_oracle(group, monkeypatch):
+    """windows of 120..600 letters (the segments the warp-cooperative kernel of poa_coop.cuh runs, one and several
+    256-row passes, odd and even lane counts, partial groups) against the oracle, for several group sizes;
+    group 0 = the same windows through the thread-per-window kernels"""
+    import elector_b200
+    from elector_b200 import windows_to_csr
+    from oracle import oracle, synth
+    rng = synth.SplitMix64(2025)
+    wins = []
+    for i in range(1203):
+        L = 120 + rng.below(200) if i % 4 else 257 + rng.below(350)
+        ab = ["ACGT", "AC", "ACGTN"][rng.below(3)]
+        ref = "".join(ab[rng.below(len(ab))] for _ in range(L))
+        cor = ref if i % 3 == 0 else (synth.mutate(rng, ref, [0.01, 0.05, 0.3][rng.below(3)], ab) or "A")
+        if i % 17 == 0:
+            cor = cor[len(cor) // 2:] or "N"
+        if i % 29 == 0:
+            cor = "N"
+        unc = synth.mutate(rng, ref, [0.1, 0.2][rng.below(2)], ab) or "A"
+        wins.append((ref, cor, unc))
+    r, ro = windows_to_csr([w[0] for w in wins]); c, co = windows_to_csr([w[1] for w in wins]); u, uo = windows_to_csr([w[2] for w in wins])
+    monkeypatch.setenv("ELECTOR_COOP_GROUP", group)
+    with elector_b200.PoaContext(0) as c2:
+        res = c2.run_csr(r, ro, c, co, u, uo)
+    o = oracle.batch(r, ro, c, co, u, uo, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(res.nring, o["nring"])
+    assert np.array_equal(res.score1, o["score1"]) and np.array_equal(res.score2, o["score2"])
+    for w in range(len(wins)):
+        assert res.window_rows(w) == oracle.window_rows(o, w), w
+
+
 def test_generic_matrix_vs_oracle(golden_dir, tmp_path):
     """non-uniform substitution scores and other gap penalties (table path of the kernel)"""
     import elector_b200
