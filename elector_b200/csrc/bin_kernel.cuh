@@ -19,8 +19,10 @@ namespace elector {
 
 constexpr int kXq1 = 129;                         // len(ref)/2 quanta of a small window
 constexpr int kSmallBins1 = kNbMax * kXq1;
-constexpr int kNumBins1 = kBigTiers + kSmallBins1;
-constexpr int kNumSegs1 = kBigTiers + 3;
+constexpr int kIdentBins1 = kXq1;                 // small windows whose corrected sequence IS the reference: by len(ref)/2
+constexpr int kNumBins1 = kBigTiers + kSmallBins1 + kIdentBins1;
+constexpr int kNumSegs1 = kBigTiers + 4;
+constexpr int kIdentSeg1 = kBigTiers + 3;
 constexpr int kMaxSegs = kNumSegs2 > kNumSegs1 ? kNumSegs2 : kNumSegs1;
 constexpr int kMaxBins = kNumBins2 > kNumBins1 ? kNumBins2 : kNumBins1;
 constexpr int kScanChunk = 1024;
@@ -40,13 +42,18 @@ struct BinTable {
   int32_t nseg, nbins;
   int32_t err_code;    // 0 ok, 1 empty sequence, 2 sequence longer than kMaxWindowLen
   int32_t err_window;  // smallest offending window id
+  unsigned long long lin_bytes;  // phase-2 table: row bytes (3 x columns bound, rounded to 4) of the windows in the linear segments
 };
 
 __host__ __device__ inline int seg1_of_nb(int nb8) { return kBigTiers + (nb8 > 16 ? 0 : nb8 > 8 ? 1 : 2); }
-__host__ __device__ inline void bin1_of(int lr, int lc, int &bin, int &seg) {
+// ident: cor equals ref letter for letter (and the matrix makes the diagonal the unique optimum): DP1 is skipped (Phase1I)
+__host__ __device__ inline void bin1_of(int lr, int lc, bool ident, int &bin, int &seg) {
   const int mx = lr > lc ? lr : lc;
   if (mx > kSmallMax) {
     bin = seg = kBigTiers - big_tier(mx);   // the largest tier comes first
+  } else if (ident) {
+    bin = kBigTiers + kSmallBins1 + (kIdentBins1 - 1 - (lr >> 1));
+    seg = kIdentSeg1;
   } else {
     const int nb8 = (lc + 7) >> 3;
     const int small = (nb8 - 1) * kXq1 + (lr >> 1);
@@ -60,6 +67,7 @@ inline void fill_segments1(BinTable &t) {
   for (int s = 0; s < kBigTiers; ++s) t.seg[s].first_bin = s;
   const int hi[3] = {32, 16, 8};
   for (int k = 0; k < 3; ++k) t.seg[kBigTiers + k].first_bin = kBigTiers + (kSmallBins1 - 1 - ((hi[k] - 1) * kXq1 + (kXq1 - 1)));
+  t.seg[kIdentSeg1].first_bin = kBigTiers + kSmallBins1;
   t.seg[kNumSegs1].first_bin = kNumBins1;
 }
 inline void fill_segments2(BinTable &t) {
@@ -73,17 +81,43 @@ inline void fill_segments2(BinTable &t) {
   t.seg[kNumSegs2].first_bin = kNumBins2;
 }
 
+// set-up of one call on the device: control words (rows cursor = words 0..1), both segment tables
+struct SegFirstBins { int32_t first1[kMaxSegs + 1], first2[kMaxSegs + 1], nseg1, nbins1, nseg2, nbins2; };
+__global__ void init_call_kernel(int32_t *ctrl, int nctrl, unsigned long long cursor_init, BinTable *tabs, SegFirstBins fb) {
+  int32_t *t = reinterpret_cast<int32_t *>(tabs);
+  for (int i = threadIdx.x; i < (int)(2 * sizeof(BinTable) / 4); i += blockDim.x) t[i] = 0;
+  for (int i = threadIdx.x; i < nctrl; i += blockDim.x) ctrl[i] = 0;
+  __syncthreads();
+  if ((int)threadIdx.x <= kMaxSegs) { tabs[0].seg[threadIdx.x].first_bin = fb.first1[threadIdx.x]; tabs[1].seg[threadIdx.x].first_bin = fb.first2[threadIdx.x]; }
+  if (threadIdx.x == 0) {
+    tabs[0].nseg = fb.nseg1; tabs[0].nbins = fb.nbins1; tabs[1].nseg = fb.nseg2; tabs[1].nbins = fb.nbins2;
+    tabs[0].err_window = 0x7fffffff;
+    *reinterpret_cast<unsigned long long *>(ctrl) = cursor_init;
+  }
+}
+
+__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+
 // phase 1: key[w] = bin (or -1 for an invalid window), hist[bin] += 1, segment maxima
+// ref / cor non-null: windows whose corrected letters equal the reference letters byte for byte get the ident bins
 __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_t *ro, const int64_t *co, const int64_t *uo,
-                                                          int32_t *key, int32_t *hist, BinTable *tab) {
+                                                          const uint8_t *ref, const uint8_t *cor, int32_t *key, int32_t *hist, BinTable *tab) {
   for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const int64_t lr = ro[w + 1] - ro[w], lc = co[w + 1] - co[w], lu = uo[w + 1] - uo[w];
     int bin = -1;
+    bool ident = false;
+    if (ref && lr == lc && lr > 0 && lr <= kSmallMax) {
+      const uint8_t *a = ref + ro[w], *b = cor + co[w];
+      int i = 0;
+      const int len = (int)lr;
+      while (i < len && a[i] == b[i]) ++i;
+      ident = i == len;
+    }
     if (lr <= 0 || lc <= 0 || lu <= 0) { atomicMax(&tab->err_code, 1); atomicMin(&tab->err_window, w); }
     else if (lr > kMaxWindowLen || lc > kMaxWindowLen || lu > kMaxWindowLen) { atomicMax(&tab->err_code, 2); atomicMin(&tab->err_window, w); }
     else {
       int seg;
-      bin1_of((int)lr, (int)lc, bin, seg);
+      bin1_of((int)lr, (int)lc, ident, bin, seg);
       atomicAdd(&hist[bin], 1);
       int32_t *mx = &tab->seg_max[seg * 4];
       if ((int)lr > mx[0]) atomicMax(&mx[0], (int)lr);

@@ -3,12 +3,14 @@
 // There is NO CPU implementation of the alignment here: every entry point either runs
 // the CUDA kernels or returns an error.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/elector_poa.h"
@@ -58,10 +60,10 @@ struct elector_ctx {
   int coop_group = kCoopGroupDefault;  // windows per warp of the warp-cooperative kernel; 0 = the longest windows stay thread-per-window (ELECTOR_COOP_GROUP)
   int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
-  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr;
+  cudaStream_t side[16] = {};   // one per segment that does not run on the main stream
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr, ev_rows = nullptr;
   float last_ms_phase1 = 0.f;  // sort 1 + phase-1 kernels of the last run (last_ms covers everything)
-  cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_join[16] = {};
   elector::BinTable *h_bintab = nullptr;  // pinned
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H of the pipelined host entry point
   std::vector<cudaEvent_t> chunk_ev;                    // 2 per chunk: inputs resident, results ready
@@ -72,6 +74,11 @@ struct elector_ctx {
   DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   int64_t merged_cap = 0;  // bytes per merged-row buffer of the last merge
+  // pipelined host entry point: child contexts (one per extra worker thread), per-worker sums and status of the call
+  std::vector<elector_ctx *> workers;
+  int64_t pipe_sums[ELECTOR_TALLY_K] = {};
+  int64_t *h_sums = nullptr;   // pinned: global counters of a chunk + the tally overflow flag
+  int pipe_rc = 0;
   DevBuf d_wdst, d_sums, d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
   // ELECTOR_TRACE: start / stop events around every segment launch of the last run_device call
   struct SegTrace { int phase, seg, kind, grid, count; cudaEvent_t e0, e1; };
@@ -79,6 +86,16 @@ struct elector_ctx {
   std::vector<cudaEvent_t> seg_ev_pool;
   size_t seg_ev_used = 0;
   bool trace = false;
+  bool all_side = false;
+  bool no_ident = false;   // ELECTOR_NO_IDENT=1: windows whose cor is ref run DP1 like every other window
+  // rows of a pipelined chunk in two regions: the windows of the linear segments of phase 2 (most windows, finished early)
+  // write theirs behind their own cursor, so that they can leave for the host while the general windows still compute
+  bool split_rows = false;          // set by process_chunk around run_device
+  int64_t region_b_base = 0;        // out: where the linear region starts in the caller's row buffer
+  cudaEvent_t ev_regb[8] = {};      // after each launch that writes to the linear region
+  cudaEvent_t ev_lin = nullptr;     // the linear region is complete and its cursor is in h_totals[7]
+  cudaEvent_t wait_in[2] = {nullptr, nullptr};   // run_device: phase 1 / phase 2 wait for these (letters still on their way), when set
+  cudaEvent_t ev_in[2] = {nullptr, nullptr};
   cudaEvent_t trace_event() {
     if (seg_ev_used == seg_ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); seg_ev_pool.push_back(e); }
     return seg_ev_pool[seg_ev_used++];
@@ -112,8 +129,8 @@ int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uin
                  const int64_t *d_off, const int32_t *d_len, int64_t *d_counters, int64_t total_bytes);
 int check_scan_overflow(elector_ctx *ctx, int64_t n_reads);
 
-const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [4..19] phase-1 and [20..35] phase-2 work counters
-const int kSideStreams = 3;
+const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [3] tally overflow, [4..19] phase-1 and [20..35] phase-2 work counters, [36..37] rows cursor of the linear region
+const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share a side stream
 
 #ifndef EL_MIN_WARPS_PH1P
 #define EL_MIN_WARPS_PH1P 32  // packed DP1: register cap 64 (32 one-warp CTAs per SM is the hardware limit)
@@ -128,12 +145,13 @@ const int kSideStreams = 3;
 // kind of a segment's kernel: INT32 cells (poa_kernel.cuh), 16-bit packed cells (poa_packed.cuh), or -- phase 2 only --
 // the packed linear x linear kernel for windows whose P1 is linear
 // or -- phase 2 only -- the warp-cooperative INT32 kernel for the segments that hold the longest windows (poa_coop.cuh)
-enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3 };
+enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3, kIdent = 4 };   // kIdent: phase 1 of windows whose cor is ref (Phase1I)
 
 template <bool GS>
 cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab, int coop_group) {
   if (kind == kCoop && phase == 1) poa_dp1_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group);
   else if (kind == kCoop) poa_dp2_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group);
+  else if (kind == kIdent) poa_dp1_kernel<Phase1I, 32><<<grid, 32, 0, st>>>(a, tab);
   else if (phase == 1) {
     if (kind == kPacked) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
     else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
@@ -156,7 +174,7 @@ void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p, int &ph2p, int &ph2l, 
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2p, poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P>, 32, 0);
 }
 
-struct SegPlan { int seg, grid; size_t warp_words, scratch_off; int kind; };
+struct SegPlan { int seg, grid; size_t warp_words, scratch_off; int kind; bool region_b; };
 
 // grid and scratch of every non-empty segment of one phase
 int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<SegPlan> &plan, size_t &scratch_words) {
@@ -175,8 +193,9 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     int per_sm;
     if (phase == 1) {
       // the segments of the longest windows (cor longer than 128 letters): a warp per window instead of a thread
-      p.kind = (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : fits16 ? kPacked : kInt32;
-      if (p.kind == kCoop) { LayoutC1 L; make_layout_c1(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
+      p.kind = s == kIdentSeg1 ? kIdent : (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : fits16 ? kPacked : kInt32;
+      if (p.kind == kIdent) { LayoutI L; Phase1I::make_layout(L, m0, m1); total = L.total; per_sm = 32; }
+      else if (p.kind == kCoop) { LayoutC1 L; make_layout_c1(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
       else if (p.kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1p; }
       else { Layout1 L; make_layout1(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1; }
     } else {
@@ -192,6 +211,7 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     }
     const int resident = std::max(1, per_sm) * ctx->sm_count;
     p.seg = s;
+    p.region_b = phase == 2 && ctx->split_rows && s >= kFirstLinSeg2;
     p.warp_words = total;
     const int per_warp_items = p.kind == kCoop ? ctx->coop_group : 32;
     p.grid = (int)std::min<int64_t>(resident, ((int64_t)si.count + per_warp_items - 1) / per_warp_items);
@@ -206,20 +226,26 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
   }
   if (scratch_words > 2 * budget_words) return ctx->fail(ELECTOR_ETOOLARGE, "call needs %zu MiB of scratch", (scratch_words * 4) >> 20);
   // launch order: the warp-cooperative segments first (they hold the longest windows and must not queue behind the bulk)
-  std::stable_partition(plan.begin(), plan.end(), [](const SegPlan &q) { return q.kind == kCoop; });
+  // then the segments that write to the linear region of the rows (it leaves for the host as soon as they are done)
+  std::stable_sort(plan.begin(), plan.end(), [](const SegPlan &x, const SegPlan &y) {
+    const int rx = x.kind == kCoop ? 0 : x.region_b ? 1 : 2, ry = y.kind == kCoop ? 0 : y.region_b ? 1 : 2;
+    return rx < ry;
+  });
   return ELECTOR_OK;
 }
 
 // One phase: the segments holding the largest windows (few items, long per-item time) start
 // first, on side streams, so that their tail overlaps the bulk on the main stream.
-int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, const std::vector<SegPlan> &plan, PoaArgs base) {
+int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, const std::vector<SegPlan> &plan, PoaArgs base,
+                    unsigned long long *cursor_b = nullptr, int64_t cap_a = 0) {
   cudaStream_t st = ctx->stream;
   CU(cudaEventRecord(ctx->ev_fork, st));
-  int side = 0, used_side = 0;
+  int side = 0, used_side = 0, nregb = 0;
   for (size_t k = 0; k < plan.size(); ++k) {
     const SegPlan &p = plan[k];
     const SegInfo &si = bt.seg[p.seg];
-    const bool bulk = k + 1 == plan.size() || (int64_t)si.count * 8 > n;  // the smallest windows and any large share stay on the main stream
+    // the last segment and (unless ELECTOR_ALL_SIDE=1) any large share stay on the main stream
+    const bool bulk = k + 1 == plan.size() || (!ctx->all_side && (int64_t)si.count * 8 > n);
     cudaStream_t ls = st;
     if (!bulk) {
       ls = ctx->side[side];
@@ -234,11 +260,23 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
     a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
     a.warp_words = (uint32_t)p.warp_words;
     a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + (phase == 1 ? 0 : 16) + p.seg;
+    if (cursor_b) {   // two row regions: general windows up to cap_a, the linear segments behind their own cursor
+      if (p.region_b) a.rows_cursor = cursor_b; else a.rows_cap = cap_a;
+    }
     const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group)
                                               : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group);
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
     if (ctx->trace) { CU(cudaEventRecord(tr.e1, ls)); ctx->seg_trace.push_back(tr); }
+    if (cursor_b && p.region_b && nregb < 8) {
+      CU(cudaEventRecord(ctx->ev_regb[nregb], ls));
+      CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_regb[nregb], 0));
+      ++nregb;
+    }
+  }
+  if (cursor_b) {   // the copy stream learns where the linear region ends as soon as its last segment is done
+    CU(cudaMemcpyAsync(&ctx->h_totals[7], cursor_b, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    CU(cudaEventRecord(ctx->ev_lin, ctx->copy_out));
   }
   for (int k = 0; k < kSideStreams; ++k)
     if (used_side & (1 << k)) {
@@ -254,7 +292,7 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
 int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
                const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, char *d_rows, int64_t rows_cap,
                int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2, int64_t *d_cells,
-               unsigned long long *d_cursor, int32_t *d_errflag, bool keep_cursor = false) {
+               unsigned long long *d_cursor, int32_t *d_errflag, int64_t cursor_init = 0) {
   if (n == 0) return ELECTOR_OK;
   if (n > 0x7fffffff - 64) return ctx->fail(ELECTOR_EINVAL, "too many windows in one call");
   cudaStream_t st = ctx->stream;
@@ -267,18 +305,30 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   BinTable *dtab1 = ctx->d_bintab.as<BinTable>(), *dtab2 = dtab1 + 1;
   BinTable *htab1 = ctx->h_bintab, *htab2 = ctx->h_bintab + 1;
   CU(cudaEventRecord(ctx->ev0, st));
-  // rows cursor (words 0..1) survives between the chunks of one pipelined call
-  CU(cudaMemsetAsync(ctx->d_ctrl.as<int32_t>() + (keep_cursor ? 2 : 0), 0, sizeof(int32_t) * (kCtrlWords - (keep_cursor ? 2 : 0)), st));
+  // control words, histograms and the two segment tables are set up by a kernel and memsets: nothing of a call's
+  // set-up goes through the host-to-device copy engine, where it would queue behind the letters of a pipelined call
   CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)(kNumBins1 + kNumBins2) * sizeof(int32_t), st));
   memset(htab1, 0, 2 * sizeof(BinTable));
   fill_segments1(*htab1);
   fill_segments2(*htab2);
   htab1->err_window = 0x7fffffff;
-  CU(cudaMemcpyAsync(dtab1, htab1, 2 * sizeof(BinTable), cudaMemcpyHostToDevice, st));
+  {
+    SegFirstBins fb;
+    for (int k = 0; k <= kMaxSegs; ++k) { fb.first1[k] = htab1->seg[k].first_bin; fb.first2[k] = htab2->seg[k].first_bin; }
+    fb.nseg1 = htab1->nseg; fb.nbins1 = htab1->nbins; fb.nseg2 = htab2->nseg; fb.nbins2 = htab2->nbins;
+    init_call_kernel<<<1, 128, 0, st>>>(ctx->d_ctrl.as<int32_t>(), (int)kCtrlWords, (unsigned long long)cursor_init, dtab1, fb);
+    CU(cudaGetLastError());
+    ++ctx->last_launches;
+  }
   const int bgrid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
   const int nch1 = (kNumBins1 + kScanChunk - 1) / kScanChunk, nch2 = (kNumBins2 + kScanChunk - 1) / kScanChunk;
   // ---- sort 1 ----
-  bin1_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_key.as<int32_t>(), hist1, dtab1);
+  // windows whose corrected letters are the reference letters skip DP1 (matrices of the packed class only): the sort
+  // then reads the letters, so it waits for them too
+  const bool ident_ok = ctx->sc.packed_ok && !ctx->no_ident;
+  if (ident_ok && ctx->wait_in[0]) CU(cudaStreamWaitEvent(st, ctx->wait_in[0], 0));
+  bin1_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ident_ok ? (const uint8_t *)d_ref : nullptr, (const uint8_t *)d_cor,
+                                           ctx->d_key.as<int32_t>(), hist1, dtab1);
   bin_scan_chunks_kernel<<<nch1, kScanChunk, 0, st>>>(kNumBins1, hist1, chunks1);
   bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch1, chunks1, hist1, dtab1);
   bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key.as<int32_t>(), hist1, chunks1, ctx->d_items.as<int32_t>());
@@ -301,7 +351,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
   a.ro0 = ctx->h_totals[2]; a.co0 = ctx->h_totals[3];
   a.p1_nodes = ctx->d_p1.as<uint16_t>(); a.n1 = ctx->d_n1.as<int32_t>(); a.key2 = ctx->d_key.as<int32_t>();
-  a.hist2 = hist2; a.seg2_max = dtab2->seg_max;
+  a.hist2 = hist2; a.seg2_max = dtab2->seg_max; a.lin_bytes = &dtab2->lin_bytes;
   a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
   a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
   a.error_flag = d_errflag;
@@ -312,6 +362,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   int rc = plan_segments(ctx, 1, *htab1, plan, scratch_words);
   if (rc != ELECTOR_OK) return rc;
   CU(ctx->d_scratch.reserve(scratch_words * 4));
+  if (ctx->wait_in[0]) CU(cudaStreamWaitEvent(st, ctx->wait_in[0], 0));
   rc = launch_segments(ctx, 1, n, *htab1, plan, a);
   if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev_mid, st));
@@ -327,6 +378,16 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   rc = plan_segments(ctx, 2, *htab2, plan, scratch_words);
   if (rc != ELECTOR_OK) return rc;
   CU(ctx->d_scratch.reserve(scratch_words * 4));
+  if (ctx->wait_in[1]) CU(cudaStreamWaitEvent(st, ctx->wait_in[1], 0));
+  if (ctx->split_rows) {
+    unsigned long long *cursor_b = reinterpret_cast<unsigned long long *>(ctx->d_ctrl.as<int32_t>() + 36);
+    const int64_t cap_a = rows_cap - (int64_t)htab2->lin_bytes;   // general region: [cursor_init, cap_a), linear region: [cap_a, rows_cap)
+    ctx->region_b_base = cap_a;
+    set_u64_kernel<<<1, 1, 0, st>>>(cursor_b, (unsigned long long)cap_a);
+    CU(cudaGetLastError());
+    ++ctx->last_launches;
+    rc = launch_segments(ctx, 2, n, *htab2, plan, a, cursor_b, cap_a);
+  } else
   rc = launch_segments(ctx, 2, n, *htab2, plan, a);
   if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev1, st));
@@ -337,21 +398,140 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
 void add_kernel_ms(elector_ctx *ctx) {
   float ms = 0.f;
   if (ctx->trace) {   // device timeline of the segment launches, ms after the start of the run_device call
-    static const char *kinds[] = {"int32", "packed", "linear", "coop"};
+    static const char *kinds[] = {"int32", "packed", "linear", "coop", "ident"};
+    const char *lvl = getenv("ELECTOR_TRACE");
+    if (lvl && lvl[0] >= '2')   // ELECTOR_TRACE=2: every segment launch
     for (const auto &t : ctx->seg_trace) {
       float a = 0.f, b = 0.f;
       cudaEventElapsedTime(&a, ctx->ev0, t.e0);
       cudaEventElapsedTime(&b, ctx->ev0, t.e1);
       fprintf(stderr, "[elector trace]   phase %d segment %2d (%s): %8d windows, grid %5d, %7.3f -> %7.3f ms\n", t.phase, t.seg, kinds[t.kind], t.count, t.grid, a, b);
     }
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) fprintf(stderr, "[elector trace]   phase 1 done %.3f ms", ms);
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) fprintf(stderr, ", all done %.3f ms\n", ms);
+    if (lvl && lvl[0] >= '2') {
+      if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) fprintf(stderr, "[elector trace]   phase 1 done %.3f ms", ms);
+      if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) fprintf(stderr, ", all done %.3f ms\n", ms);
+    }
     ctx->seg_trace.clear();
     ctx->seg_ev_used = 0;
   }
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms += ms;
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) ctx->last_ms_phase1 += ms;
 }
+
+
+struct ChunkJob { int64_t w0, w1, r0, r1, rows_base, rows_len; };
+struct PipeArgs {
+  int64_t n;
+  const char *ref; const int64_t *ro; const char *cor; const int64_t *co; const char *unc; const int64_t *uo;
+  int64_t n_reads; const int64_t *read_first;
+  char *rows_out; int64_t *row_off; int32_t *row_stride, *nring, *score1, *score2; int64_t *cells, *counters_out;
+  cudaEvent_t ev_call;   // start of the call on the device (ELECTOR_TRACE)
+};
+
+// One chunk of a pipelined call on one worker context: everything is queued on the worker's stream (the segment launches
+// fork to its side streams) and the function returns when the chunk's results are in the caller's host buffers.
+int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
+  CU(cudaSetDevice(ctx->device));
+  const int64_t w0 = j.w0, w1 = j.w1, nw = w1 - w0, r0 = j.r0, r1 = j.r1, nr = r1 - r0;
+  const int64_t br0 = pa.ro[w0], bc0 = pa.co[w0], bu0 = pa.uo[w0];
+  const int64_t br = pa.ro[w1] - br0, bc = pa.co[w1] - bc0, bu = pa.uo[w1] - bu0;
+  CU(ctx->d_ref.reserve(br)); CU(ctx->d_cor.reserve(bc)); CU(ctx->d_unc.reserve(bu));
+  CU(ctx->d_roff.reserve((nw + 1) * 8)); CU(ctx->d_coff.reserve((nw + 1) * 8)); CU(ctx->d_uoff.reserve((nw + 1) * 8));
+  CU(ctx->d_rows.reserve(j.rows_len)); CU(ctx->d_rowoff.reserve(nw * 8)); CU(ctx->d_stride.reserve(nw * 4));
+  CU(ctx->d_nring.reserve(nw * 4)); CU(ctx->d_s1.reserve(nw * 4)); CU(ctx->d_s2.reserve(nw * 4)); CU(ctx->d_cells.reserve(nw * 8));
+  if (nr > 0) { CU(ctx->d_tally_out.reserve(nr * ELECTOR_TALLY_K * 8)); CU(ctx->d_sums.reserve(ELECTOR_TALLY_K * 8)); }
+  cudaStream_t st = ctx->stream;
+  if (ctx->trace) CU(cudaEventRecord(ctx->uev0, st));
+  // the offsets first, on the compute stream: the size sort needs nothing else.  The letters follow on the copy stream --
+  // ref and cor (phase 1 waits for them), then unc (phase 2 waits for it) -- while the sort and phase 1 run.
+  CU(cudaMemcpyAsync(ctx->d_roff.p, pa.ro + w0, (nw + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_coff.p, pa.co + w0, (nw + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_uoff.p, pa.uo + w0, (nw + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(ctx->ev_fork, st));
+  CU(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));   // the copy engine serves the offsets first
+  CU(cudaMemcpyAsync(ctx->d_ref.p, pa.ref + br0, br, cudaMemcpyHostToDevice, ctx->copy_in));
+  CU(cudaMemcpyAsync(ctx->d_cor.p, pa.cor + bc0, bc, cudaMemcpyHostToDevice, ctx->copy_in));
+  CU(cudaEventRecord(ctx->ev_in[0], ctx->copy_in));
+  CU(cudaMemcpyAsync(ctx->d_unc.p, pa.unc + bu0, bu, cudaMemcpyHostToDevice, ctx->copy_in));
+  CU(cudaEventRecord(ctx->ev_in[1], ctx->copy_in));
+  ctx->wait_in[0] = ctx->ev_in[0]; ctx->wait_in[1] = ctx->ev_in[1];
+  // the offsets stay those of the whole call: the letter pointers are moved back by the chunk's first offset, the row
+  // pointer by the chunk's base in the caller's row buffer (row_off[] then indexes the caller's buffer directly)
+  char *d_rows_v = ctx->d_rows.as<char>() - j.rows_base;
+  ctx->split_rows = true;
+  int rc = run_device(ctx, nw, ctx->d_ref.as<char>() - br0, ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>() - bc0, ctx->d_coff.as<int64_t>(),
+                      ctx->d_unc.as<char>() - bu0, ctx->d_uoff.as<int64_t>(), d_rows_v, j.rows_base + j.rows_len, ctx->d_rowoff.as<int64_t>(),
+                      ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(), ctx->d_s2.as<int32_t>(),
+                      ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2, j.rows_base);
+  ctx->wait_in[0] = ctx->wait_in[1] = nullptr;
+  ctx->split_rows = false;
+  if (rc != ELECTOR_OK) { cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(st); return rc; }
+  CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(ctx->ev_rows, st));
+  if (nr > 0) {
+    std::vector<int64_t> rf(pa.read_first + r0, pa.read_first + r1 + 1);
+    for (int64_t &v : rf) v -= w0;
+    CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
+    rc = merge_device(ctx, nr, rf.data(), nw, reinterpret_cast<const uint8_t *>(d_rows_v), 3 * (br + bc + bu), ctx->d_rowoff.as<int64_t>(),
+                      ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>());
+    if (rc == ELECTOR_OK)
+      rc = tally_device(ctx, nr, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(), ctx->d_moff.as<int64_t>(),
+                        ctx->d_mlen.as<int32_t>(), ctx->d_tally_out.as<int64_t>(), ctx->merged_cap);
+    if (rc != ELECTOR_OK) { cudaStreamSynchronize(st); return rc; }
+    tally_sum_kernel<<<std::min<int>(64, (int)((nr + 7) / 8)), 256, 0, st>>>(nr, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
+    CU(cudaGetLastError());
+    ++ctx->last_launches;
+    CU(cudaEventRecord(ctx->ev1, st));   // the chunk's device time covers merge + tally too
+    CU(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_sums + ELECTOR_TALLY_K, ctx->d_ctrl.as<int32_t>() + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pa.counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.p, nr * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+  }
+  // the alignment results leave on the copy stream while merge and tally run: the host waits for the POA kernels only
+  // to learn how many row bytes the chunk used
+  cudaStream_t so = ctx->copy_out;
+  // the linear region first: its segments are launched before the general ones and finish early in phase 2
+  CU(cudaEventSynchronize(ctx->ev_lin));
+  const int64_t base_b = ctx->region_b_base, used_b = ctx->h_totals[7];
+  if (used_b > base_b && used_b <= j.rows_base + j.rows_len)
+    CU(cudaMemcpyAsync(pa.rows_out + base_b, d_rows_v + base_b, used_b - base_b, cudaMemcpyDeviceToHost, so));
+  CU(cudaEventSynchronize(ctx->ev_rows));
+  const int64_t used = ctx->h_totals[4];
+  if ((int32_t)(ctx->h_totals[5] & 0xffffffff) || used > base_b || used_b > j.rows_base + j.rows_len) {
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(so);
+    return ctx->fail(ELECTOR_ECAPACITY, "rows of a chunk exceed their bound (%lld + %lld > %lld)", (long long)(used - j.rows_base), (long long)(used_b - base_b),
+                     (long long)j.rows_len);
+  }
+  CU(cudaMemcpyAsync(pa.rows_out + j.rows_base, ctx->d_rows.p, used - j.rows_base, cudaMemcpyDeviceToHost, so));
+  CU(cudaMemcpyAsync(pa.row_off + w0, ctx->d_rowoff.p, nw * 8, cudaMemcpyDeviceToHost, so));
+  CU(cudaMemcpyAsync(pa.row_stride + w0, ctx->d_stride.p, nw * 4, cudaMemcpyDeviceToHost, so));
+  CU(cudaMemcpyAsync(pa.nring + w0, ctx->d_nring.p, nw * 4, cudaMemcpyDeviceToHost, so));
+  if (pa.score1) CU(cudaMemcpyAsync(pa.score1 + w0, ctx->d_s1.p, nw * 4, cudaMemcpyDeviceToHost, so));
+  if (pa.score2) CU(cudaMemcpyAsync(pa.score2 + w0, ctx->d_s2.p, nw * 4, cudaMemcpyDeviceToHost, so));
+  if (pa.cells) CU(cudaMemcpyAsync(pa.cells + w0, ctx->d_cells.p, nw * 8, cudaMemcpyDeviceToHost, so));
+  if (ctx->trace) CU(cudaEventRecord(ctx->uev1, so));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(so));
+  if (ctx->trace) {   // device timeline of the chunk, ms after the start of the call
+    float t[6] = {0, 0, 0, 0, 0, 0};
+    cudaEventElapsedTime(&t[0], pa.ev_call, ctx->uev0); cudaEventElapsedTime(&t[1], pa.ev_call, ctx->ev0);
+    cudaEventElapsedTime(&t[2], pa.ev_call, ctx->ev_mid); cudaEventElapsedTime(&t[3], pa.ev_call, ctx->ev_rows);
+    cudaEventElapsedTime(&t[4], pa.ev_call, ctx->ev1); cudaEventElapsedTime(&t[5], pa.ev_call, ctx->uev1);
+    fprintf(stderr, "[elector trace] chunk w%lld: h2d %.2f | sort1 %.2f | phase 1 done %.2f | phase 2 done %.2f | merge+tally done %.2f | rows on host %.2f\n",
+            (long long)w0, t[0], t[1], t[2], t[3], t[4], t[5]);
+  }
+  add_kernel_ms(ctx);
+  if (nr > 0) {
+    if ((int32_t)ctx->h_sums[ELECTOR_TALLY_K]) {
+      cudaMemsetAsync(ctx->d_ctrl.as<int32_t>() + 3, 0, sizeof(int32_t), st);
+      return ctx->fail(ELECTOR_EUNSUPPORTED, "a read has more than %d gap stretches at its borders", kMaxStretchKeys);
+    }
+    for (int f = 0; f < ELECTOR_TALLY_K; ++f) ctx->pipe_sums[f] += ctx->h_sums[f];
+  }
+  return ELECTOR_OK;
+}
+
+int create_context(int device, const ScoreMatrix &mat, elector_ctx **out);
 
 }  // namespace
 
@@ -360,20 +540,34 @@ extern "C" {
 int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
   if (!out) return ELECTOR_EINVAL;
   *out = nullptr;
+  ScoreMatrix mat;
+  if (matrix_path) {
+    if (mat.load(matrix_path) <= 0) {
+      char buf[512];
+      snprintf(buf, sizeof buf, "Error reading matrix file %s", matrix_path);
+      g_init_error = buf;
+      return ELECTOR_EMATRIX;
+    }
+  } else mat.set_default();
+  return create_context(device, mat, out);
+}
+
+}  // extern "C"
+
+namespace {
+// a context for `device` with the scoring of `mat` (elector_poa_init; worker contexts of the pipelined entry point)
+int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   elector_ctx *ctx = new elector_ctx();
   auto bail = [&](int code) {
     g_init_error = ctx->err;
     elector_poa_free(ctx);
     return code;
   };
-  if (matrix_path) {
-    if (ctx->mat.load(matrix_path) <= 0) {
-      ctx->fail(ELECTOR_EMATRIX, "Error reading matrix file %s", matrix_path);
-      return bail(ELECTOR_EMATRIX);
-    }
-  } else ctx->mat.set_default();
+  ctx->mat = mat;
   if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
   ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
+  if (const char *e = getenv("ELECTOR_ALL_SIDE")) ctx->all_side = e[0] == '1';
+  if (const char *e = getenv("ELECTOR_NO_IDENT")) ctx->no_ident = e[0] == '1';
   if (const char *e = getenv("ELECTOR_PACKED2")) ctx->packed2 = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_LINEAR2")) ctx->no_linear2 = e[0] == '1';
   int ndev = 0;
@@ -392,18 +586,17 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_rows)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_lin, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_in[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_in[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->uev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->uev1)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->side[1], cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->side[2], cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_join[2], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMallocHost((void **)&ctx->h_bintab, 2 * sizeof(BinTable))) != cudaSuccess ||
       (e = cudaMallocHost((void **)&ctx->h_totals, 8 * sizeof(int64_t))) != cudaSuccess ||
+      (e = cudaMallocHost((void **)&ctx->h_sums, (ELECTOR_TALLY_K + 1) * sizeof(int64_t))) != cudaSuccess ||
       (e = ctx->d_tab.reserve(sizeof(SymbolTables))) != cudaSuccess ||
       (e = ctx->d_ctrl.reserve(kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMemset(ctx->d_ctrl.p, 0, kCtrlWords * sizeof(int32_t))) != cudaSuccess ||
@@ -411,6 +604,17 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
+  for (int k = 0; k < 8; ++k)
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_regb[k], cudaEventDisableTiming)) != cudaSuccess) {
+      ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
+      return bail(ELECTOR_ECUDA);
+    }
+  for (int k = 0; k < kSideStreams; ++k)
+    if ((e = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming)) != cudaSuccess) {
+      ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
+      return bail(ELECTOR_ECUDA);
+    }
   if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l, ctx->resident_coop);
   else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l, ctx->resident_coop);
   if (const char *e = getenv("ELECTOR_COOP_GROUP")) ctx->coop_group = std::max(0, std::min(32, atoi(e)));
@@ -424,9 +628,15 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
   *out = ctx;
   return ELECTOR_OK;
 }
+}  // namespace
+
+extern "C" {
 
 void elector_poa_free(elector_ctx *ctx) {
   if (!ctx) return;
+  for (elector_ctx *w : ctx->workers) elector_poa_free(w);
+  ctx->workers.clear();
+  if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
                     &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
                     &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_wdst, &ctx->d_sums, &ctx->d_tally_scan, &ctx->d_tally_out,
@@ -435,10 +645,14 @@ void elector_poa_free(elector_ctx *ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+  if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
+  for (int k = 0; k < 2; ++k) if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+  for (int k = 0; k < 8; ++k) if (ctx->ev_regb[k]) cudaEventDestroy(ctx->ev_regb[k]);
+  if (ctx->ev_lin) cudaEventDestroy(ctx->ev_lin);
   if (ctx->uev0) cudaEventDestroy(ctx->uev0);
   if (ctx->uev1) cudaEventDestroy(ctx->uev1);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < kSideStreams; ++k) {
     if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
     if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
   }
@@ -454,11 +668,10 @@ void elector_poa_free(elector_ctx *ctx) {
 
 const char *elector_last_error(const elector_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
 
+// a window's three rows take 3 * (columns rounded up to 4) bytes and columns <= letters of the window
 int64_t elector_poa_rows_bound(int64_t n, const int64_t *ro, const int64_t *co, const int64_t *uo) {
-  int64_t t = 0;
-  for (int64_t w = 0; w < n; ++w)
-    t += 3 * (((ro[w + 1] - ro[w]) + (co[w + 1] - co[w]) + (uo[w + 1] - uo[w]) + 3) & ~(int64_t)3);
-  return t;
+  if (n <= 0 || !ro || !co || !uo) return 0;
+  return 3 * ((ro[n] - ro[0]) + (co[n] - co[0]) + (uo[n] - uo[0]) + 3 * n);
 }
 
 int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
@@ -495,9 +708,11 @@ int elector_poa_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t 
                               score1, score2, cells, nullptr, nullptr);
 }
 
-// Host buffers in, host buffers out, in chunks of whole reads: the inputs of all chunks are
-// queued on a copy stream up front, every chunk's kernels wait for its own inputs only, and a
-// chunk's results travel back on a second copy stream while the next chunk computes.
+// Host buffers in, host buffers out.  The call is cut into chunks of whole reads; every chunk is processed start to
+// finish -- inputs to the device, both POA phases, merge, tally, results back -- by one of a few WORKER contexts (this
+// context and children it creates once), each on its own host thread and streams.  While one worker's chunk computes,
+// another's inputs arrive and a third's results leave, and the idle moments of a chunk (the host reads the segment
+// table of each phase; the longest windows of a phase finish after its bulk) are filled by the other workers' kernels.
 int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ro, const char *cor, const int64_t *co,
                          const char *unc, const int64_t *uo, int64_t n_reads, const int64_t *read_first, char *rows_out,
                          int64_t rows_cap, int64_t *row_off, int32_t *row_stride, int32_t *nring, int32_t *score1,
@@ -513,131 +728,102 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   if (ro[0] != 0 || co[0] != 0 || uo[0] != 0) return ctx->fail(ELECTOR_EINVAL, "offsets must start at 0");
   if (n_reads > 0 && (read_first[0] != 0 || read_first[n_reads] != n)) return ctx->fail(ELECTOR_EINVAL, "read_first must span 0..n_windows");
   CU(cudaSetDevice(ctx->device));
-  // ---- chunk boundaries (windows; whole reads when reads are given) ----
-  // Few, large chunks: every chunk pays the latency of its longest windows once per phase (a warp
-  // that holds 200-letter windows runs for milliseconds), which only a bulk of >= ~0.5 M windows hides.
-  int want_chunks = 3;
-  if (const char *e = getenv("ELECTOR_PIPELINE_CHUNKS")) want_chunks = std::max(1, atoi(e));
-  const int64_t target = std::max<int64_t>(std::min<int64_t>(n, 524288), (n + want_chunks - 1) / want_chunks);
-  std::vector<int64_t> wcut(1, 0), rcut(1, 0);
-  if (n_reads > 0) {
-    int64_t r = 0;
-    while (r < n_reads) {
-      // first read boundary at or after the target (binary search on read_first)
-      const int64_t want = std::min<int64_t>(n, wcut.back() + target);
-      int64_t lo = r + 1, hi = n_reads;
-      while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (read_first[mid] >= want) hi = mid; else lo = mid + 1; }
-      r = lo;
-      rcut.push_back(r);
-      wcut.push_back(read_first[r]);
-    }
-  } else {
-    while (wcut.back() < n) wcut.push_back(std::min<int64_t>(n, wcut.back() + target));
-  }
-  const size_t nchunks = wcut.size() - 1;
-  while (ctx->chunk_ev.size() < 3 * nchunks + 1) {   // per chunk: inputs resident, results ready, results on the host; + call start
-    cudaEvent_t e;
-    CU(cudaEventCreate(&e));
-    ctx->chunk_ev.push_back(e);
-  }
   const bool trace = ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
-  const cudaEvent_t ev_start = ctx->chunk_ev[3 * nchunks];
+  // ---- chunk boundaries (windows; whole reads when reads are given) ----
+  // Large chunks: the kernels run 32 windows of one sorted size class in lock step and finish a class with its slowest
+  // group, so their throughput grows with the number of windows sorted together (measured on config 1: one chunk of
+  // 1.96 M windows 12.4 ms of kernels, six chunks of 0.33 M 23.5 ms).  ELECTOR_PIPELINE_CHUNKS forces a chunk count.
+  int64_t chunk_windows = 2000000;
+  int want_workers = 3;
+  if (const char *e = getenv("ELECTOR_PIPELINE_CHUNK_WINDOWS")) chunk_windows = std::max<int64_t>(1024, atoll(e));
+  if (const char *e = getenv("ELECTOR_PIPELINE_WORKERS")) want_workers = std::max(1, std::min(8, atoi(e)));
+  int64_t want_chunks = (n + chunk_windows - 1) / chunk_windows;
+  if (const char *e = getenv("ELECTOR_PIPELINE_CHUNKS")) want_chunks = std::max(1, atoi(e));
+  const int64_t target = std::max<int64_t>(std::min<int64_t>(n, 65536), (n + want_chunks - 1) / want_chunks);
+  std::vector<ChunkJob> jobs;
+  {
+    int64_t w = 0, r = 0;
+    while (w < n) {
+      ChunkJob j;
+      j.w0 = w; j.r0 = r;
+      const int64_t want = std::min<int64_t>(n, w + target);
+      if (n_reads > 0) {   // first read boundary at or after the target (binary search on read_first)
+        int64_t lo = r + 1, hi = n_reads;
+        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (read_first[mid] >= want) hi = mid; else lo = mid + 1; }
+        r = lo;
+        w = read_first[r];
+      } else w = want;
+      j.w1 = w; j.r1 = r;
+      jobs.push_back(j);
+    }
+  }
+  // rows of chunk k land at rows_out + rows_base(k): the bound of the windows before it.  The O(1) bound when the
+  // caller's buffer allows it, else the exact one (one pass over the offsets).
+  const bool loose = rows_cap >= elector_poa_rows_bound(n, ro, co, uo);
+  {
+    int64_t base = 0;
+    for (ChunkJob &j : jobs) {
+      j.rows_base = base;
+      if (loose) j.rows_len = elector_poa_rows_bound(j.w1 - j.w0, ro + j.w0, co + j.w0, uo + j.w0);
+      else {
+        int64_t t = 0;
+        for (int64_t w = j.w0; w < j.w1; ++w) t += ((ro[w + 1] - ro[w]) + (co[w + 1] - co[w]) + (uo[w + 1] - uo[w]) + 3) & ~(int64_t)3;
+        j.rows_len = 3 * t;
+      }
+      base += j.rows_len;
+    }
+    if (base > rows_cap) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small (%lld needed)", (long long)rows_cap, (long long)base);
+  }
+  // ---- workers ----
+  const int nworkers = (int)std::min<size_t>(jobs.size(), (size_t)want_workers);
+  while ((int)ctx->workers.size() < nworkers - 1) {
+    elector_ctx *child = nullptr;
+    const int rc = create_context(ctx->device, ctx->mat, &child);
+    if (rc != ELECTOR_OK) return ctx->fail(rc, "worker context: %s", g_init_error.c_str());
+    ctx->workers.push_back(child);
+  }
+  PipeArgs pa{n, ref, ro, cor, co, unc, uo, n_reads, read_first, rows_out, row_off, row_stride, nring, score1, score2, cells, counters_out, ctx->ev_fork};
+  if (trace) {
+    while (ctx->chunk_ev.empty()) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->chunk_ev.push_back(e); }
+    pa.ev_call = ctx->chunk_ev[0];
+    CU(cudaEventRecord(pa.ev_call, ctx->stream));
+  }
+  std::atomic<size_t> next{0};
+  std::atomic<int> first_error{ELECTOR_OK};
   const auto host_t0 = std::chrono::steady_clock::now();
-  auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
-  std::vector<double> host_sync(nchunks, 0.0);
-  // ---- device buffers for the whole call ----
-  const int64_t br = ro[n], bc = co[n], bu = uo[n];
-  CU(ctx->d_ref.reserve(br)); CU(ctx->d_cor.reserve(bc)); CU(ctx->d_unc.reserve(bu));
-  CU(ctx->d_roff.reserve((n + 1) * 8)); CU(ctx->d_coff.reserve((n + 1) * 8)); CU(ctx->d_uoff.reserve((n + 1) * 8));
-  CU(ctx->d_rows.reserve(rows_cap)); CU(ctx->d_rowoff.reserve(n * 8)); CU(ctx->d_stride.reserve(n * 4));
-  CU(ctx->d_nring.reserve(n * 4)); CU(ctx->d_s1.reserve(n * 4)); CU(ctx->d_s2.reserve(n * 4)); CU(ctx->d_cells.reserve(n * 8));
-  if (n_reads > 0) { CU(ctx->d_tally_out.reserve(n_reads * ELECTOR_TALLY_K * 8)); CU(ctx->d_sums.reserve(ELECTOR_TALLY_K * 8)); }
-  cudaStream_t st = ctx->stream, cin = ctx->copy_in, cout = ctx->copy_out;
-  // ---- all inputs, chunk by chunk, on the H2D stream ----
-  CU(cudaEventRecord(ev_start, cin));
-  for (size_t k = 0; k < nchunks; ++k) {
-    const int64_t w0 = wcut[k], w1 = wcut[k + 1];
-    CU(cudaMemcpyAsync(ctx->d_ref.as<char>() + ro[w0], ref + ro[w0], ro[w1] - ro[w0], cudaMemcpyHostToDevice, cin));
-    CU(cudaMemcpyAsync(ctx->d_cor.as<char>() + co[w0], cor + co[w0], co[w1] - co[w0], cudaMemcpyHostToDevice, cin));
-    CU(cudaMemcpyAsync(ctx->d_unc.as<char>() + uo[w0], unc + uo[w0], uo[w1] - uo[w0], cudaMemcpyHostToDevice, cin));
-    CU(cudaMemcpyAsync(ctx->d_roff.as<int64_t>() + w0, ro + w0, (w1 - w0 + 1) * 8, cudaMemcpyHostToDevice, cin));
-    CU(cudaMemcpyAsync(ctx->d_coff.as<int64_t>() + w0, co + w0, (w1 - w0 + 1) * 8, cudaMemcpyHostToDevice, cin));
-    CU(cudaMemcpyAsync(ctx->d_uoff.as<int64_t>() + w0, uo + w0, (w1 - w0 + 1) * 8, cudaMemcpyHostToDevice, cin));
-    CU(cudaEventRecord(ctx->chunk_ev[2 * k], cin));
-  }
-  if (n_reads > 0) CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
-  // ---- chunks: kernels on the main stream, results back on the D2H stream ----
-  int64_t used_before = 0;
-  std::vector<int64_t> rf;
-  for (size_t k = 0; k < nchunks; ++k) {
-    const int64_t w0 = wcut[k], w1 = wcut[k + 1], nw = w1 - w0;
-    CU(cudaStreamWaitEvent(st, ctx->chunk_ev[2 * k], 0));
-    int rc = run_device(ctx, nw, ctx->d_ref.as<char>(), ctx->d_roff.as<int64_t>() + w0, ctx->d_cor.as<char>(),
-                        ctx->d_coff.as<int64_t>() + w0, ctx->d_unc.as<char>(), ctx->d_uoff.as<int64_t>() + w0,
-                        ctx->d_rows.as<char>(), rows_cap, ctx->d_rowoff.as<int64_t>() + w0, ctx->d_stride.as<int32_t>() + w0,
-                        ctx->d_nring.as<int32_t>() + w0, ctx->d_s1.as<int32_t>() + w0, ctx->d_s2.as<int32_t>() + w0,
-                        ctx->d_cells.as<int64_t>() + w0, ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2, k > 0);
-    if (rc != ELECTOR_OK) { cudaStreamSynchronize(cin); cudaStreamSynchronize(cout); return rc; }
-    CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    const int64_t r0 = n_reads > 0 ? rcut[k] : 0, r1 = n_reads > 0 ? rcut[k + 1] : 0;
-    if (r1 > r0) {
-      rf.assign(read_first + r0, read_first + r1 + 1);
-      for (int64_t &v : rf) v -= w0;
-      rc = merge_device(ctx, r1 - r0, rf.data(), nw, ctx->d_rows.as<uint8_t>(), 3 * ((ro[w1] - ro[w0]) + (co[w1] - co[w0]) + (uo[w1] - uo[w0])),
-                        ctx->d_rowoff.as<int64_t>() + w0, ctx->d_stride.as<int32_t>() + w0, ctx->d_nring.as<int32_t>() + w0);
-      if (rc == ELECTOR_OK)
-        rc = tally_device(ctx, r1 - r0, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
-                          ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(), ctx->d_tally_out.as<int64_t>() + r0 * ELECTOR_TALLY_K, ctx->merged_cap);
-      if (rc != ELECTOR_OK) { cudaStreamSynchronize(cin); cudaStreamSynchronize(cout); return rc; }
-      tally_sum_kernel<<<std::min<int>(64, (int)((r1 - r0 + 7) / 8)), 256, 0, st>>>(r1 - r0, ctx->d_tally_out.as<int64_t>() + r0 * ELECTOR_TALLY_K,
-                                                                                 ctx->d_sums.as<unsigned long long>());
-      CU(cudaGetLastError());
-      ++ctx->last_launches;
-      CU(cudaEventRecord(ctx->ev1, st));   // the chunk's device time now covers merge + tally too
+  auto work = [&](elector_ctx *wk, int id) {
+    wk->trace = trace;
+    wk->last_ms = wk->last_ms_phase1 = 0.f;
+    wk->last_launches = 0;
+    memset(wk->pipe_sums, 0, sizeof wk->pipe_sums);
+    for (;;) {
+      const size_t k = next.fetch_add(1);
+      if (k >= jobs.size() || first_error.load() != ELECTOR_OK) break;
+      const double t_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+      const int rc = process_chunk(wk, pa, jobs[k]);
+      if (trace)
+        fprintf(stderr, "[elector trace] chunk %zu (worker %d): %lld windows, host clock %.2f -> %.2f ms\n", k, id, (long long)(jobs[k].w1 - jobs[k].w0), t_in,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+      if (rc != ELECTOR_OK) { int ok = ELECTOR_OK; first_error.compare_exchange_strong(ok, rc); wk->pipe_rc = rc; break; }
     }
-    CU(cudaEventRecord(ctx->chunk_ev[2 * k + 1], st));
-    CU(cudaStreamSynchronize(st));
-    host_sync[k] = host_ms();
-    add_kernel_ms(ctx);
-    const int64_t used = ctx->h_totals[4];
-    if ((int32_t)(ctx->h_totals[5] & 0xffffffff) || used > rows_cap) {
-      cudaStreamSynchronize(cin); cudaStreamSynchronize(cout);
-      return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small", (long long)rows_cap);
-    }
-    CU(cudaStreamWaitEvent(cout, ctx->chunk_ev[2 * k + 1], 0));
-    CU(cudaMemcpyAsync(rows_out + used_before, ctx->d_rows.as<char>() + used_before, used - used_before, cudaMemcpyDeviceToHost, cout));
-    CU(cudaMemcpyAsync(row_off + w0, ctx->d_rowoff.as<int64_t>() + w0, nw * 8, cudaMemcpyDeviceToHost, cout));
-    CU(cudaMemcpyAsync(row_stride + w0, ctx->d_stride.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
-    CU(cudaMemcpyAsync(nring + w0, ctx->d_nring.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
-    if (score1) CU(cudaMemcpyAsync(score1 + w0, ctx->d_s1.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
-    if (score2) CU(cudaMemcpyAsync(score2 + w0, ctx->d_s2.as<int32_t>() + w0, nw * 4, cudaMemcpyDeviceToHost, cout));
-    if (cells) CU(cudaMemcpyAsync(cells + w0, ctx->d_cells.as<int64_t>() + w0, nw * 8, cudaMemcpyDeviceToHost, cout));
-    if (r1 > r0)
-      CU(cudaMemcpyAsync(counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.as<int64_t>() + r0 * ELECTOR_TALLY_K,
-                         (r1 - r0) * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, cout));
-    CU(cudaEventRecord(ctx->chunk_ev[2 * nchunks + k], cout));
-    used_before = used;
+  };
+  for (elector_ctx *w : ctx->workers) w->pipe_rc = ELECTOR_OK;
+  ctx->pipe_rc = ELECTOR_OK;
+  std::vector<std::thread> threads;
+  for (int i = 1; i < nworkers; ++i) threads.emplace_back(work, ctx->workers[i - 1], i);
+  work(ctx, 0);
+  for (std::thread &t : threads) t.join();
+  for (int i = 1; i < nworkers; ++i) {
+    elector_ctx *w = ctx->workers[i - 1];
+    ctx->last_ms += w->last_ms; ctx->last_ms_phase1 += w->last_ms_phase1; ctx->last_launches += w->last_launches;
+    for (int f = 0; f < ELECTOR_TALLY_K; ++f) ctx->pipe_sums[f] += w->pipe_sums[f];
+    if (w->pipe_rc != ELECTOR_OK && ctx->pipe_rc == ELECTOR_OK) { ctx->pipe_rc = w->pipe_rc; ctx->err = w->err; }
   }
-  if (n_reads > 0) {
-    int rc = check_scan_overflow(ctx, n_reads);
-    if (rc != ELECTOR_OK) { cudaStreamSynchronize(cout); return rc; }
-    if (sums_out) {
-      CU(cudaMemcpyAsync(sums_out, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-    }
-  }
-  CU(cudaStreamSynchronize(cout));
-  if (trace) {   // ELECTOR_TRACE: device timeline of the call (ms after the first copy was queued), one line per chunk
-    for (size_t k = 0; k < nchunks; ++k) {
-      float a = 0, b = 0, c = 0;
-      cudaEventElapsedTime(&a, ev_start, ctx->chunk_ev[2 * k]);
-      cudaEventElapsedTime(&b, ev_start, ctx->chunk_ev[2 * k + 1]);
-      cudaEventElapsedTime(&c, ev_start, ctx->chunk_ev[2 * nchunks + k]);
-      fprintf(stderr, "[elector trace] chunk %zu: %lld windows, inputs resident %.2f ms, results ready %.2f ms (host saw it at %.2f), results on host %.2f ms\n",
-              k, (long long)(wcut[k + 1] - wcut[k]), a, b, host_sync[k], c);
-    }
-    fprintf(stderr, "[elector trace] call returned at %.2f ms (host clock)\n", host_ms());
-  }
+  if (ctx->pipe_rc != ELECTOR_OK) return ctx->pipe_rc;
+  if (first_error.load() != ELECTOR_OK) return first_error.load();
+  if (sums_out) memcpy(sums_out, ctx->pipe_sums, sizeof ctx->pipe_sums);
+  if (trace) fprintf(stderr, "[elector trace] call returned at %.2f ms (host clock), %zu chunks on %d workers\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(), jobs.size(), nworkers);
   return ELECTOR_OK;
 }
 

@@ -311,19 +311,9 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
       if (lane == i) { s1 = best; bj = best_j; }
     }
     __syncwarp();
-    if (owner) {
-      int spcode;
-      const int n1 = coop1_after<GENERIC_SUB>(c, s_layout, lr, lc, bj, p1_slot, spcode);
-      const int lu = (int)(a.unc_off[w + 1] - a.unc_off[w]);
-      int bin, seg;
-      bin2_of(n1, lu, spcode, bin, seg);
-      a.n1[w] = n1;
-      a.key2[w] = bin;
-      if (a.score1) a.score1[w] = s1;
-      atomicAdd(&a.hist2[bin], 1);
-      if (n1 > a.seg2_max[seg * 4]) atomicMax(&a.seg2_max[seg * 4], n1);
-      if (lu > a.seg2_max[seg * 4 + 1]) atomicMax(&a.seg2_max[seg * 4 + 1], lu);
-    }
+    int spcode = 0, n1 = 0;
+    if (owner) n1 = coop1_after<GENERIC_SUB>(c, s_layout, lr, lc, bj, p1_slot, spcode);
+    phase1_epilogue(a, owner, w, n1, s1, spcode, lr, lc);
     __syncwarp();
   }
 }

@@ -119,6 +119,7 @@ struct PoaArgs {
   int32_t *key2;         // phase-2 sort bin of the window
   int32_t *hist2;        // phase-2 histogram (filled by phase 1)
   int32_t *seg2_max;     // phase-2 segment maxima: [seg*4 + {0: n1, 1: lu}]
+  unsigned long long *lin_bytes;  // sum of the row-byte bounds of the windows that go to the linear segments of phase 2
   // results
   uint8_t *rows_out;
   unsigned long long *rows_cursor;
@@ -748,6 +749,28 @@ __device__ __forceinline__ const SymbolTables *stage_tables(uint32_t *smem, cons
   return reinterpret_cast<const SymbolTables *>(smem);
 }
 
+#ifdef __CUDACC__
+// What phase 1 leaves for phase 2 (all lanes call it; inactive lanes pass active = false): len(P1), the sort bin, the
+// histogram and maxima of sort 2, and the row bytes the windows of the linear segments can need (one atomic per warp).
+__device__ __forceinline__ void phase1_epilogue(const PoaArgs &a, bool active, int w, int n1, int s1, int spcode, int lr, int lc) {
+  unsigned lb = 0;
+  if (active) {
+    const int lu = (int)(a.unc_off[w + 1] - a.unc_off[w]);
+    int bin, seg;
+    bin2_of(n1, lu, spcode, bin, seg);
+    a.n1[w] = n1;
+    a.key2[w] = bin;
+    if (a.score1) a.score1[w] = s1;
+    atomicAdd(&a.hist2[bin], 1);
+    if (n1 > a.seg2_max[seg * 4]) atomicMax(&a.seg2_max[seg * 4], n1);
+    if (lu > a.seg2_max[seg * 4 + 1]) atomicMax(&a.seg2_max[seg * 4 + 1], lu);
+    if (seg >= kFirstLinSeg2) lb = 3u * (unsigned)((lr + lc + lu + 3) & ~3);
+  }
+  for (int d = 16; d > 0; d >>= 1) lb += __shfl_xor_sync(EL_WARP_FULL, lb, d);
+  if (lb && threadIdx.x == 0) atomicAdd(a.lin_bytes, (unsigned long long)lb);
+}
+#endif
+
 // PH = Phase1<GENERIC_SUB> (INT32 cells) or Phase1P (poa_packed.cuh: two 16-bit cells per instruction)
 template <class PH, int MIN_WARPS>
 __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const SymbolTables *g_tab) {
@@ -780,19 +803,9 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
       __syncwarp();
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
-    if (active) {
-      int s1, spcode;
-      const int n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), s1, spcode);
-      const int lu = (int)(a.unc_off[w + 1] - a.unc_off[w]);
-      int bin, seg;
-      bin2_of(n1, lu, spcode, bin, seg);
-      a.n1[w] = n1;
-      a.key2[w] = bin;
-      if (a.score1) a.score1[w] = s1;
-      atomicAdd(&a.hist2[bin], 1);
-      if (n1 > a.seg2_max[seg * 4]) atomicMax(&a.seg2_max[seg * 4], n1);
-      if (lu > a.seg2_max[seg * 4 + 1]) atomicMax(&a.seg2_max[seg * 4 + 1], lu);
-    }
+    int s1 = 0, spcode = 0, n1 = 0;
+    if (active) n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), s1, spcode);
+    phase1_epilogue(a, active, w, n1, s1, spcode, lr, lc);
     __syncwarp();
   }
 }

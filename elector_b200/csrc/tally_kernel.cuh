@@ -147,6 +147,18 @@ struct BitRow {
     }
     return L;
   }
+  // first column p >= i with dots at p and p + 1 (the start of a run of two or more dots when i is not inside a run), or L
+  __device__ int next_pair(int i) const {
+    const int nw = (L + 31) >> 5;
+    while (i < L) {
+      const int k = i >> 5;
+      const uint32_t w = m[k], nx = k + 1 < nw ? m[k + 1] : 0u;
+      const uint32_t p = (w & ((w >> 1) | (nx << 31))) >> (i & 31);
+      if (p) return min(L, i + __ffs(p) - 1);
+      i = (i | 31) + 1;
+    }
+    return L;
+  }
   // length of the run of columns equal to v that starts at i (i < L), going right
   __device__ int run_fwd(int i, bool v) const {
     const int s = i;
@@ -254,7 +266,10 @@ __device__ void find_gap_stretches(const BitRow &dc, const BitRow &dr, ReadScan 
   bool have_cur = false, cur_set = false;
   int i = 0;
   while (i < L) {
-    const int st = dc.next_set(i);
+    // A run of one dot that does not start at column 0 ends with cg == 0: it neither marks columns nor closes a slot.
+    // Most runs of the corrected row are such single dots (an inserted base of the uncorrected read), so the scan
+    // goes straight to the next run that counts: the one at column 0, or the next run of two or more dots.
+    const int st = (i == 0 && dc.bit(0)) ? 0 : dc.next_pair(i);
     if (st >= L) break;
     const int len = dc.run_fwd(st, true), e = st + len - 1;
     const bool counts = st == 0 || len >= 2;            // cg > 0 when the run ends

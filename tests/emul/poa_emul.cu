@@ -8,6 +8,7 @@
 // packed: windows the library would run through the 16-bit packed kernels (poa_packed.cuh) do so here too
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -20,7 +21,7 @@ using namespace elector;
 
 template <bool GS>
 static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed, bool general_only, bool coop) {
-  long n_packed1 = 0, n_packed2 = 0, n_linear2 = 0;
+  long n_packed1 = 0, n_packed2 = 0, n_linear2 = 0, n_ident1 = 0;
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
     const int lr = R.rec[w].len, lc = C.rec[w].len, lu = U.rec[w].len;
@@ -46,6 +47,17 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       int bj = -1;
       coop_dp_emulated<GS>(p1, bset.data(), lr, lc, s1, bj);
       n1 = coop1_after<GS>(p1, L1, lr, lc, bj, nodes_p, spcode);
+    } else if (packed && sc.packed_ok && lr == lc && lr <= kSmallMax &&
+               memcmp(R.seq.data() + R.rec[w].off, C.seq.data() + C.rec[w].off, (size_t)lr) == 0) {   // cor is ref: the library runs Phase1I
+      LayoutI L1;
+      Phase1I::make_layout(L1, cap_r, cap_c);
+      std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
+      Phase1I p1;
+      p1.scr.base = scratch1.data() + lane;
+      p1.sc = s;
+      p1.Lp = &L1;
+      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode);
+      ++n_ident1;
     } else if (packed && sc.packed_ok && (long)sc.maxabs * (cap_r + cap_c + 4) <= kPackedSpan) {
       Layout1P L1;
       make_layout1p(L1, cap_r, cap_c);
@@ -142,7 +154,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     }
     if (scores) fprintf(scores, "%d %d %d %d\n", s1, s2, n1, nring);
   }
-  if (packed) fprintf(stderr, "packed: %ld (phase 1), %ld (phase 2 general) and %ld (phase 2 linear) of %zu windows\n", n_packed1, n_packed2, n_linear2, n);
+  if (packed) fprintf(stderr, "packed: %ld (phase 1) + %ld (phase 1, cor is ref), %ld (phase 2 general) and %ld (phase 2 linear) of %zu windows\n", n_packed1, n_ident1, n_packed2, n_linear2, n);
   return 0;
 }
 

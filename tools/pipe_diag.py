@@ -75,6 +75,6 @@ with elector_b200.PoaContext(0) as ctx:
         t = timed(call, reps=5)
         ms, k = ctx.last_kernel_ms()
         print("chunks %d: %.2f ms per call (%.0f triplets/s), kernels %.2f ms, %d launches" % (chunks, t * 1e3, n_reads / t, ms, k), flush=True)
-        os.environ["ELECTOR_TRACE"] = "1"
+        os.environ["ELECTOR_TRACE"] = os.environ.get("DIAG_TRACE", "1")
         call()
         sys.stderr.flush()

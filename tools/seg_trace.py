@@ -15,7 +15,7 @@ wl = workloads.make_windows(cfg, reads)
 with elector_b200.PoaContext(0) as ctx:
     for k in range(3):
         if k == 2:
-            os.environ["ELECTOR_TRACE"] = "1"
+            os.environ["ELECTOR_TRACE"] = os.environ.get("DIAG_TRACE", "1")
         res, counters, sums = ctx.pipeline_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"], wl["read_first"])
         ms, n = ctx.last_kernel_ms()
         print("call %d: %d windows, %d launches, %.3f ms kernels" % (k, len(res.nring), n, ms), flush=True)
