@@ -381,7 +381,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   if (ctx->wait_in[1]) CU(cudaStreamWaitEvent(st, ctx->wait_in[1], 0));
   if (ctx->split_rows) {
     unsigned long long *cursor_b = reinterpret_cast<unsigned long long *>(ctx->d_ctrl.as<int32_t>() + 36);
-    const int64_t cap_a = rows_cap - (int64_t)htab2->lin_bytes;   // general region: [cursor_init, cap_a), linear region: [cap_a, rows_cap)
+    const int64_t cap_a = (rows_cap - (int64_t)htab2->lin_bytes) & ~(int64_t)15;   // general region: [cursor_init, cap_a), linear region: [cap_a, rows_cap)
     ctx->region_b_base = cap_a;
     set_u64_kernel<<<1, 1, 0, st>>>(cursor_b, (unsigned long long)cap_a);
     CU(cudaGetLastError());
@@ -419,7 +419,7 @@ void add_kernel_ms(elector_ctx *ctx) {
 }
 
 
-struct ChunkJob { int64_t w0, w1, r0, r1, rows_base, rows_len; };
+struct ChunkJob { int64_t w0, w1, r0, r1, rows_base, rows_len; bool split; };
 struct PipeArgs {
   int64_t n;
   const char *ref; const int64_t *ro; const char *cor; const int64_t *co; const char *unc; const int64_t *uo;
@@ -458,7 +458,9 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   // the offsets stay those of the whole call: the letter pointers are moved back by the chunk's first offset, the row
   // pointer by the chunk's base in the caller's row buffer (row_off[] then indexes the caller's buffer directly)
   char *d_rows_v = ctx->d_rows.as<char>() - j.rows_base;
-  ctx->split_rows = true;
+  ctx->split_rows = j.split;
+  ctx->region_b_base = j.rows_base + j.rows_len;
+  ctx->h_totals[7] = ctx->region_b_base;
   int rc = run_device(ctx, nw, ctx->d_ref.as<char>() - br0, ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>() - bc0, ctx->d_coff.as<int64_t>(),
                       ctx->d_unc.as<char>() - bu0, ctx->d_uoff.as<int64_t>(), d_rows_v, j.rows_base + j.rows_len, ctx->d_rowoff.as<int64_t>(),
                       ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(), ctx->d_s2.as<int32_t>(),
@@ -490,7 +492,7 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   // to learn how many row bytes the chunk used
   cudaStream_t so = ctx->copy_out;
   // the linear region first: its segments are launched before the general ones and finish early in phase 2
-  CU(cudaEventSynchronize(ctx->ev_lin));
+  if (j.split) CU(cudaEventSynchronize(ctx->ev_lin));
   const int64_t base_b = ctx->region_b_base, used_b = ctx->h_totals[7];
   if (used_b > base_b && used_b <= j.rows_base + j.rows_len)
     CU(cudaMemcpyAsync(pa.rows_out + base_b, d_rows_v + base_b, used_b - base_b, cudaMemcpyDeviceToHost, so));
@@ -671,7 +673,7 @@ const char *elector_last_error(const elector_ctx *ctx) { return ctx ? ctx->err.c
 // a window's three rows take 3 * (columns rounded up to 4) bytes and columns <= letters of the window
 int64_t elector_poa_rows_bound(int64_t n, const int64_t *ro, const int64_t *co, const int64_t *uo) {
   if (n <= 0 || !ro || !co || !uo) return 0;
-  return 3 * ((ro[n] - ro[0]) + (co[n] - co[0]) + (uo[n] - uo[0]) + 3 * n);
+  return (3 * ((ro[n] - ro[0]) + (co[n] - co[0]) + (uo[n] - uo[0]) + 3 * n) + 31) & ~(int64_t)15;   // 16-byte granules + one spare
 }
 
 int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
@@ -764,6 +766,7 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
     int64_t base = 0;
     for (ChunkJob &j : jobs) {
       j.rows_base = base;
+      j.split = loose;   // two row regions need the spare bytes of the O(1) bound (the boundary is aligned to 16 bytes)
       if (loose) j.rows_len = elector_poa_rows_bound(j.w1 - j.w0, ro + j.w0, co + j.w0, uo + j.w0);
       else {
         int64_t t = 0;
