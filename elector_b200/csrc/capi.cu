@@ -18,6 +18,7 @@
 #include "poa_kernel.cuh"
 #include "poa_packed.cuh"
 #include "poa_coop.cuh"
+#include "poa_dual.cuh"
 #include "bin_kernel.cuh"
 #include "host_setup.hpp"
 #include "tally_kernel.cuh"
@@ -87,6 +88,9 @@ struct elector_ctx {
   size_t seg_ev_used = 0;
   bool trace = false;
   bool all_side = false;
+  bool no_dual = false;    // ELECTOR_NO_DUAL=1: general windows of phase 2 on the INT32 kernel with frontier sets
+  int resident_ph2d = 0;
+  bool ph2d_alt = false;   // ELECTOR_PH2D_WARPS=20: the 96-register build of the dual-frontier kernel
   bool no_ident = false;   // ELECTOR_NO_IDENT=1: windows whose cor is ref run DP1 like every other window
   // rows of a pipelined chunk in two regions: the windows of the linear segments of phase 2 (most windows, finished early)
   // write theirs behind their own cursor, so that they can leave for the host while the general windows still compute
@@ -138,6 +142,9 @@ const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share 
 #ifndef EL_MIN_WARPS_PH2P
 #define EL_MIN_WARPS_PH2P 24  // packed DP2: register cap 80
 #endif
+#ifndef EL_MIN_WARPS_PH2D
+#define EL_MIN_WARPS_PH2D 20  // dual-frontier packed DP2: register cap 96 (measured: 9.94 ms per config-1 step against 10.26 ms at 24 warps / 80 registers)
+#endif
 #ifndef EL_MIN_WARPS_PH2L
 #define EL_MIN_WARPS_PH2L 32  // packed linear DP2: register cap 64
 #endif
@@ -145,7 +152,7 @@ const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share 
 // kind of a segment's kernel: INT32 cells (poa_kernel.cuh), 16-bit packed cells (poa_packed.cuh), or -- phase 2 only --
 // the packed linear x linear kernel for windows whose P1 is linear
 // or -- phase 2 only -- the warp-cooperative INT32 kernel for the segments that hold the longest windows (poa_coop.cuh)
-enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3, kIdent = 4 };   // kIdent: phase 1 of windows whose cor is ref (Phase1I)
+enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3, kIdent = 4, kDual = 5 };   // kIdent: phase 1 of windows whose cor is ref (Phase1I)
 
 template <bool GS>
 cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab, int coop_group) {
@@ -156,6 +163,8 @@ cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int g
     if (kind == kPacked) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
     else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
   } else if (kind == kLinear) poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L><<<grid, 32, 0, st>>>(a, tab);
+  else if (kind == kDual && coop_group < 0) poa_dp2_kernel<Phase2D, 20><<<grid, 32, 0, st>>>(a, tab);   // A/B: register cap 96 (ELECTOR_PH2D_WARPS=20)
+  else if (kind == kDual) poa_dp2_kernel<Phase2D, EL_MIN_WARPS_PH2D><<<grid, 32, 0, st>>>(a, tab);
   else if (kind == kPacked) poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P><<<grid, 32, 0, st>>>(a, tab);
   else poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2><<<grid, 32, 0, st>>>(a, tab);
   return cudaGetLastError();
@@ -203,8 +212,9 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
       // kernel is opt-in (its out-of-line frontier handling costs more than the packed cells save)
       // the segments of the longest windows (more than 128 rows, general and linear): a warp per window instead of a thread
       const bool longest = s <= kBigTiers || s == kFirstLinSeg2;
-      p.kind = (longest && ctx->coop_group > 0) ? kCoop : !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->packed2 ? kPacked : kInt32;
+      p.kind = (longest && ctx->coop_group > 0) ? kCoop : !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->packed2 ? kPacked : ctx->no_dual ? kInt32 : kDual;
       if (p.kind == kCoop) { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
+      else if (p.kind == kDual) { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2d; }
       else if (p.kind == kLinear) { Layout2L L; make_layout2l(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2l; }
       else if (p.kind == kPacked) { Layout2P L; make_layout2p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2p; }
       else { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2; }
@@ -264,7 +274,8 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
       if (p.region_b) a.rows_cursor = cursor_b; else a.rows_cap = cap_a;
     }
     const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group)
-                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group);
+                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(),
+                                                                    (p.kind == kDual && ctx->ph2d_alt) ? -1 : ctx->coop_group);
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
     if (ctx->trace) { CU(cudaEventRecord(tr.e1, ls)); ctx->seg_trace.push_back(tr); }
@@ -398,7 +409,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
 void add_kernel_ms(elector_ctx *ctx) {
   float ms = 0.f;
   if (ctx->trace) {   // device timeline of the segment launches, ms after the start of the run_device call
-    static const char *kinds[] = {"int32", "packed", "linear", "coop", "ident"};
+    static const char *kinds[] = {"int32", "packed", "linear", "coop", "ident", "dual"};
     const char *lvl = getenv("ELECTOR_TRACE");
     if (lvl && lvl[0] >= '2')   // ELECTOR_TRACE=2: every segment launch
     for (const auto &t : ctx->seg_trace) {
@@ -570,6 +581,7 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   if (const char *e = getenv("ELECTOR_ALL_SIDE")) ctx->all_side = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_IDENT")) ctx->no_ident = e[0] == '1';
+  if (const char *e = getenv("ELECTOR_NO_DUAL")) ctx->no_dual = e[0] == '1';
   if (const char *e = getenv("ELECTOR_PACKED2")) ctx->packed2 = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_LINEAR2")) ctx->no_linear2 = e[0] == '1';
   int ndev = 0;
@@ -626,6 +638,13 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   cap(ctx->resident_ph1, "ELECTOR_WARPS_PH1"); cap(ctx->resident_ph2, "ELECTOR_WARPS_PH2");
   cap(ctx->resident_ph1p, "ELECTOR_WARPS_PH1P"); cap(ctx->resident_ph2p, "ELECTOR_WARPS_PH2P"); cap(ctx->resident_ph2l, "ELECTOR_WARPS_PH2L");
   cap(ctx->resident_coop, "ELECTOR_WARPS_COOP");
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resident_ph2d, poa_dp2_kernel<Phase2D, EL_MIN_WARPS_PH2D>, 32, 0);
+  if (const char *e = getenv("ELECTOR_PH2D_WARPS")) if (atoi(e) == 20) {
+    ctx->ph2d_alt = true;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resident_ph2d, poa_dp2_kernel<Phase2D, 20>, 32, 0);
+  }
+  cap(ctx->resident_ph2d, "ELECTOR_WARPS_PH2D");
+  if (ctx->resident_ph2d < 1) ctx->no_dual = true;
   if (ctx->resident_ph1 < 1 || ctx->resident_ph2 < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;

@@ -65,7 +65,7 @@ EL_HD uint32_t pk_maxs_flag(uint32_t a, uint32_t b, uint32_t &mv, uint32_t bit_l
       "setp.eq.s16 pu, rs1, rs3;\n\t"
       "@!pv or.b32 %1, %1, %4;\n\t"
       "@!pu or.b32 %1, %1, %5;}\n\t"
-      : "=r"(val), "+r"(mv) : "r"(a), "r"(b), "r"(bit_lo), "r"(bit_hi));
+      : "=&r"(val), "+r"(mv) : "r"(a), "r"(b), "r"(bit_lo), "r"(bit_hi));   // early clobber: a is read after val is written
   return val;
 #else
   const int16_t al = (int16_t)(a & 0xffffu), bl = (int16_t)(b & 0xffffu), ah = (int16_t)(a >> 16), bh = (int16_t)(b >> 16);

@@ -4,7 +4,7 @@
 // moves, fused emit) can be checked against the oracle in the GPU-less container.
 // It is never linked into the product library; the product has no CPU path.
 //
-// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores|-] [packed|packed-general|coop]
+// usage: poa_emul MATRIX|- REF.fa COR.fa UNC.fa OUT.pir [OUT.scores|-] [packed|packed-general|dual-general|coop]
 // packed: windows the library would run through the 16-bit packed kernels (poa_packed.cuh) do so here too
 #include <cstdio>
 #include <cstdlib>
@@ -16,11 +16,12 @@
 #include "../../elector_b200/csrc/bin_kernel.cuh"
 #include "../../elector_b200/csrc/poa_packed.cuh"
 #include "../../elector_b200/csrc/poa_coop.cuh"
+#include "../../elector_b200/csrc/poa_dual.cuh"
 
 using namespace elector;
 
 template <bool GS>
-static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed, bool general_only, bool coop) {
+static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed, bool general_only, bool coop, bool dual) {
   long n_packed1 = 0, n_packed2 = 0, n_linear2 = 0, n_ident1 = 0;
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
@@ -118,6 +119,19 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       row_words = L2.row_words;
       for (uint32_t k = 0; k < 3 * row_words; ++k) rows.push_back(p2.scr.w(L2.o_rows + k));
       ++n_linear2;
+    } else if (fits16 && dual) {   // general windows: the dual-frontier packed kernel (poa_dual.cuh), as the library runs them
+      Layout2 L2;
+      make_layout2(L2, cap_n, cap_u);
+      std::vector<uint32_t> scratch2((size_t)L2.total * 32, 0xdeadbeefu);
+      Phase2D p2;
+      p2.scr.base = scratch2.data() + lane;
+      p2.bset = nullptr;
+      p2.sc = s;
+      p2.Lp = &L2;
+      nring = p2.run_window(nodes_p, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
+      row_words = L2.row_words;
+      for (uint32_t k = 0; k < 3 * row_words; ++k) rows.push_back(p2.scr.w(L2.o_rows + k));
+      ++n_packed2;
     } else if (fits16) {
       Layout2P L2;
       make_layout2p(L2, cap_n, cap_u);
@@ -170,10 +184,11 @@ int main(int argc, char **argv) {
   FILE *pir = fopen(argv[5], "w");
   FILE *scores = argc > 6 && argv[6][0] != '-' ? fopen(argv[6], "w") : nullptr;
   if (!pir) return 1;
-  const bool packed = argc > 7 && (std::string(argv[7]) == "packed" || std::string(argv[7]) == "packed-general");
-  const bool general_only = argc > 7 && std::string(argv[7]) == "packed-general";   // linear windows through Phase2P as well
+  const bool dual = argc > 7 && (std::string(argv[7]) == "packed" || std::string(argv[7]) == "dual-general");   // "packed" = what the library runs
+  const bool packed = argc > 7 && (std::string(argv[7]) == "packed" || std::string(argv[7]) == "packed-general" || dual);
+  const bool general_only = argc > 7 && (std::string(argv[7]) == "packed-general" || std::string(argv[7]) == "dual-general");   // linear windows through Phase2P as well
   const bool coop = argc > 7 && std::string(argv[7]) == "coop";   // phase 2 of every window through the warp-cooperative DP
-  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores, packed, general_only, coop); else run<false>(sc, R, C, U, pir, scores, packed, general_only, coop);
+  if (sc.generic_sub) run<true>(sc, R, C, U, pir, scores, packed, general_only, coop, dual); else run<false>(sc, R, C, U, pir, scores, packed, general_only, coop, dual);
   fclose(pir);
   if (scores) fclose(scores);
   return 0;
