@@ -19,10 +19,8 @@ namespace elector {
 
 constexpr int kXq1 = 129;                         // len(ref)/2 quanta of a small window
 constexpr int kSmallBins1 = kNbMax * kXq1;
-constexpr int kIdentBins1 = kXq1;                 // small windows whose corrected sequence IS the reference: by len(ref)/2
-constexpr int kNumBins1 = kBigTiers + kSmallBins1 + kIdentBins1;
-constexpr int kNumSegs1 = kBigTiers + 4;
-constexpr int kIdentSeg1 = kBigTiers + 3;
+constexpr int kNumBins1 = kBigTiers + kSmallBins1;
+constexpr int kNumSegs1 = kBigTiers + 3;
 constexpr int kMaxSegs = kNumSegs2 > kNumSegs1 ? kNumSegs2 : kNumSegs1;
 constexpr int kMaxBins = kNumBins2 > kNumBins1 ? kNumBins2 : kNumBins1;
 constexpr int kScanChunk = 1024;
@@ -46,14 +44,10 @@ struct BinTable {
 };
 
 __host__ __device__ inline int seg1_of_nb(int nb8) { return kBigTiers + (nb8 > 16 ? 0 : nb8 > 8 ? 1 : 2); }
-// ident: cor equals ref letter for letter (and the matrix makes the diagonal the unique optimum): DP1 is skipped (Phase1I)
-__host__ __device__ inline void bin1_of(int lr, int lc, bool ident, int &bin, int &seg) {
+__host__ __device__ inline void bin1_of(int lr, int lc, int &bin, int &seg) {
   const int mx = lr > lc ? lr : lc;
   if (mx > kSmallMax) {
     bin = seg = kBigTiers - big_tier(mx);   // the largest tier comes first
-  } else if (ident) {
-    bin = kBigTiers + kSmallBins1 + (kIdentBins1 - 1 - (lr >> 1));
-    seg = kIdentSeg1;
   } else {
     const int nb8 = (lc + 7) >> 3;
     const int small = (nb8 - 1) * kXq1 + (lr >> 1);
@@ -67,7 +61,6 @@ inline void fill_segments1(BinTable &t) {
   for (int s = 0; s < kBigTiers; ++s) t.seg[s].first_bin = s;
   const int hi[3] = {32, 16, 8};
   for (int k = 0; k < 3; ++k) t.seg[kBigTiers + k].first_bin = kBigTiers + (kSmallBins1 - 1 - ((hi[k] - 1) * kXq1 + (kXq1 - 1)));
-  t.seg[kIdentSeg1].first_bin = kBigTiers + kSmallBins1;
   t.seg[kNumSegs1].first_bin = kNumBins1;
 }
 inline void fill_segments2(BinTable &t) {
@@ -99,31 +92,58 @@ __global__ void init_call_kernel(int32_t *ctrl, int nctrl, unsigned long long cu
 __global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
 
 // phase 1: key[w] = bin (or -1 for an invalid window), hist[bin] += 1, segment maxima
-// ref / cor non-null: windows whose corrected letters equal the reference letters byte for byte get the ident bins
+// Windows whose corrected letters ARE the reference letters (byte for byte; most windows at ELECTOR's corrected error
+// rates) need no phase 1 at all when the matrix makes the diagonal the unique optimum of DP1 (match 0, everything else
+// negative: the packed class): P1 is lin(ref) with every node carrying both letters, best score 0.  With `id` non-null
+// the sort recognises them, leaves them out of the phase-1 work list (key -2) and does what phase 1 would have left for
+// phase 2: len(P1), the phase-2 sort bin and histogram, the segment maxima and the row bytes of the linear region.
+struct IdentArgs {
+  const uint8_t *ref, *cor;
+  int32_t *n1, *key2, *hist2, *seg2_max, *score1;
+  unsigned long long *lin_bytes;
+};
 __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_t *ro, const int64_t *co, const int64_t *uo,
-                                                          const uint8_t *ref, const uint8_t *cor, int32_t *key, int32_t *hist, BinTable *tab) {
+                                                          int32_t *key, int32_t *hist, BinTable *tab, bool use_ident, IdentArgs id) {
+  unsigned long long lin = 0;
   for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const int64_t lr = ro[w + 1] - ro[w], lc = co[w + 1] - co[w], lu = uo[w + 1] - uo[w];
     int bin = -1;
-    bool ident = false;
-    if (ref && lr == lc && lr > 0 && lr <= kSmallMax) {
-      const uint8_t *a = ref + ro[w], *b = cor + co[w];
-      int i = 0;
-      const int len = (int)lr;
-      while (i < len && a[i] == b[i]) ++i;
-      ident = i == len;
-    }
     if (lr <= 0 || lc <= 0 || lu <= 0) { atomicMax(&tab->err_code, 1); atomicMin(&tab->err_window, w); }
     else if (lr > kMaxWindowLen || lc > kMaxWindowLen || lu > kMaxWindowLen) { atomicMax(&tab->err_code, 2); atomicMin(&tab->err_window, w); }
     else {
-      int seg;
-      bin1_of((int)lr, (int)lc, ident, bin, seg);
-      atomicAdd(&hist[bin], 1);
-      int32_t *mx = &tab->seg_max[seg * 4];
-      if ((int)lr > mx[0]) atomicMax(&mx[0], (int)lr);
-      if ((int)lc > mx[1]) atomicMax(&mx[1], (int)lc);
+      bool ident = false;
+      if (use_ident && lr == lc && lr <= kSmallMax && lu <= kSmallMax) {
+        const uint8_t *a = id.ref + ro[w], *b = id.cor + co[w];
+        int i = 0;
+        const int len = (int)lr;
+        while (i < len && a[i] == b[i]) ++i;
+        ident = i == len;
+      }
+      if (ident) {
+        int bin2, seg2;
+        bin2_of((int)lr, (int)lu, 0, bin2, seg2);
+        id.n1[w] = (int)lr;
+        id.key2[w] = bin2;
+        if (id.score1) id.score1[w] = 0;
+        atomicAdd(&id.hist2[bin2], 1);
+        if ((int)lr > id.seg2_max[seg2 * 4]) atomicMax(&id.seg2_max[seg2 * 4], (int)lr);
+        if ((int)lu > id.seg2_max[seg2 * 4 + 1]) atomicMax(&id.seg2_max[seg2 * 4 + 1], (int)lu);
+        lin += 3ull * (unsigned long long)((lr + lc + lu + 3) & ~(int64_t)3);
+        bin = -2;
+      } else {
+        int seg;
+        bin1_of((int)lr, (int)lc, bin, seg);
+        atomicAdd(&hist[bin], 1);
+        int32_t *mx = &tab->seg_max[seg * 4];
+        if ((int)lr > mx[0]) atomicMax(&mx[0], (int)lr);
+        if ((int)lc > mx[1]) atomicMax(&mx[1], (int)lc);
+      }
     }
     key[w] = bin;
+  }
+  if (use_ident) {
+    for (int d = 16; d > 0; d >>= 1) lin += __shfl_xor_sync(0xffffffffu, lin, d);
+    if ((threadIdx.x & 31) == 0 && lin) atomicAdd(id.lin_bytes, lin);
   }
 }
 
@@ -176,7 +196,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(int32_t n, const int32
                                                            int32_t *items) {
   for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const int bin = key[w];
-    if (bin < 0) continue;  // invalid window, reported by bin1_count_kernel
+    if (bin < 0) continue;  // invalid window (reported by bin1_count_kernel), or a window that needs no phase 1
     items[chunk_base[bin / kScanChunk] + atomicAdd(&cursor[bin], 1)] = w;
   }
 }

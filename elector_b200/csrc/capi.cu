@@ -72,7 +72,7 @@ struct elector_ctx {
   ScoringSetup sc;
   bool packed2 = false;     // ELECTOR_PACKED2=1: general windows of phase 2 on the packed kernel (A/B measurements)
   bool no_linear2 = false;  // ELECTOR_NO_LINEAR2=1: linear windows of phase 2 on the general kernels
-  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_n1, d_p1;
+  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_key2, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   int64_t merged_cap = 0;  // bytes per merged-row buffer of the last merge
   // pipelined host entry point: child contexts (one per extra worker thread), per-worker sums and status of the call
@@ -152,13 +152,12 @@ const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share 
 // kind of a segment's kernel: INT32 cells (poa_kernel.cuh), 16-bit packed cells (poa_packed.cuh), or -- phase 2 only --
 // the packed linear x linear kernel for windows whose P1 is linear
 // or -- phase 2 only -- the warp-cooperative INT32 kernel for the segments that hold the longest windows (poa_coop.cuh)
-enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3, kIdent = 4, kDual = 5 };   // kIdent: phase 1 of windows whose cor is ref (Phase1I)
+enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3, kDual = 4 };
 
 template <bool GS>
-cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab, int coop_group) {
+cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab, int coop_group, bool linear_seg) {
   if (kind == kCoop && phase == 1) poa_dp1_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group);
-  else if (kind == kCoop) poa_dp2_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group);
-  else if (kind == kIdent) poa_dp1_kernel<Phase1I, 32><<<grid, 32, 0, st>>>(a, tab);
+  else if (kind == kCoop) poa_dp2_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group, linear_seg);
   else if (phase == 1) {
     if (kind == kPacked) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
     else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
@@ -202,9 +201,8 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
     int per_sm;
     if (phase == 1) {
       // the segments of the longest windows (cor longer than 128 letters): a warp per window instead of a thread
-      p.kind = s == kIdentSeg1 ? kIdent : (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : fits16 ? kPacked : kInt32;
-      if (p.kind == kIdent) { LayoutI L; Phase1I::make_layout(L, m0, m1); total = L.total; per_sm = 32; }
-      else if (p.kind == kCoop) { LayoutC1 L; make_layout_c1(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
+      p.kind = (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : fits16 ? kPacked : kInt32;
+      if (p.kind == kCoop) { LayoutC1 L; make_layout_c1(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
       else if (p.kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1p; }
       else { Layout1 L; make_layout1(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1; }
     } else {
@@ -273,9 +271,10 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
     if (cursor_b) {   // two row regions: general windows up to cap_a, the linear segments behind their own cursor
       if (p.region_b) a.rows_cursor = cursor_b; else a.rows_cap = cap_a;
     }
-    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group)
+    const bool linear_seg = phase == 2 && p.seg >= kFirstLinSeg2;
+    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group, linear_seg)
                                               : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(),
-                                                                    (p.kind == kDual && ctx->ph2d_alt) ? -1 : ctx->coop_group);
+                                                                    (p.kind == kDual && ctx->ph2d_alt) ? -1 : ctx->coop_group, linear_seg);
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
     if (ctx->trace) { CU(cudaEventRecord(tr.e1, ls)); ctx->seg_trace.push_back(tr); }
@@ -309,6 +308,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   cudaStream_t st = ctx->stream;
   CU(ctx->d_items.reserve((size_t)n * sizeof(int32_t)));
   CU(ctx->d_key.reserve((size_t)n * sizeof(int32_t)));
+  CU(ctx->d_key2.reserve((size_t)n * sizeof(int32_t)));
   CU(ctx->d_n1.reserve((size_t)n * sizeof(int32_t)));
   CU(ctx->d_hist.reserve((size_t)(kNumBins1 + kNumBins2 + 2 * kMaxChunks) * sizeof(int32_t)));
   CU(ctx->d_bintab.reserve(2 * sizeof(BinTable)));
@@ -334,12 +334,14 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   const int bgrid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
   const int nch1 = (kNumBins1 + kScanChunk - 1) / kScanChunk, nch2 = (kNumBins2 + kScanChunk - 1) / kScanChunk;
   // ---- sort 1 ----
-  // windows whose corrected letters are the reference letters skip DP1 (matrices of the packed class only): the sort
-  // then reads the letters, so it waits for them too
-  const bool ident_ok = ctx->sc.packed_ok && !ctx->no_ident;
+  // windows whose corrected letters are the reference letters need no phase 1 (bin_kernel.cuh): the sort then reads the
+  // letters, so it waits for them too.  Only when their phase 2 needs no node list: Phase2L for the small linear segments,
+  // the warp-cooperative kernel (which rebuilds lin(ref)) for the long ones.
+  const bool ident_ok = ctx->sc.packed_ok && !ctx->no_ident && !ctx->no_linear2 && ctx->coop_group > 0 &&
+                        (int64_t)ctx->sc.maxabs * (kSmallMax + 4 * kN1q + 4) <= kPackedSpan;
   if (ident_ok && ctx->wait_in[0]) CU(cudaStreamWaitEvent(st, ctx->wait_in[0], 0));
-  bin1_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ident_ok ? (const uint8_t *)d_ref : nullptr, (const uint8_t *)d_cor,
-                                           ctx->d_key.as<int32_t>(), hist1, dtab1);
+  IdentArgs ida{(const uint8_t *)d_ref, (const uint8_t *)d_cor, ctx->d_n1.as<int32_t>(), ctx->d_key2.as<int32_t>(), hist2, dtab2->seg_max, d_s1, &dtab2->lin_bytes};
+  bin1_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_key.as<int32_t>(), hist1, dtab1, ident_ok, ida);
   bin_scan_chunks_kernel<<<nch1, kScanChunk, 0, st>>>(kNumBins1, hist1, chunks1);
   bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch1, chunks1, hist1, dtab1);
   bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key.as<int32_t>(), hist1, chunks1, ctx->d_items.as<int32_t>());
@@ -361,7 +363,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
   a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
   a.ro0 = ctx->h_totals[2]; a.co0 = ctx->h_totals[3];
-  a.p1_nodes = ctx->d_p1.as<uint16_t>(); a.n1 = ctx->d_n1.as<int32_t>(); a.key2 = ctx->d_key.as<int32_t>();
+  a.p1_nodes = ctx->d_p1.as<uint16_t>(); a.n1 = ctx->d_n1.as<int32_t>(); a.key2 = ctx->d_key2.as<int32_t>();
   a.hist2 = hist2; a.seg2_max = dtab2->seg_max; a.lin_bytes = &dtab2->lin_bytes;
   a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
   a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
@@ -380,7 +382,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   // ---- sort 2 (phase 1 filled key2, hist2 and the segment maxima) ----
   bin_scan_chunks_kernel<<<nch2, kScanChunk, 0, st>>>(kNumBins2, hist2, chunks2);
   bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch2, chunks2, hist2, dtab2);
-  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key.as<int32_t>(), hist2, chunks2, ctx->d_items.as<int32_t>());
+  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key2.as<int32_t>(), hist2, chunks2, ctx->d_items.as<int32_t>());
   CU(cudaGetLastError());
   ctx->last_launches += 3;
   CU(cudaMemcpyAsync(htab2, dtab2, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
@@ -409,7 +411,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
 void add_kernel_ms(elector_ctx *ctx) {
   float ms = 0.f;
   if (ctx->trace) {   // device timeline of the segment launches, ms after the start of the run_device call
-    static const char *kinds[] = {"int32", "packed", "linear", "coop", "ident", "dual"};
+    static const char *kinds[] = {"int32", "packed", "linear", "coop", "dual"};
     const char *lvl = getenv("ELECTOR_TRACE");
     if (lvl && lvl[0] >= '2')   // ELECTOR_TRACE=2: every segment launch
     for (const auto &t : ctx->seg_trace) {
@@ -659,7 +661,7 @@ void elector_poa_free(elector_ctx *ctx) {
   ctx->workers.clear();
   if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
-                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
+                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_key2, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
                     &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_wdst, &ctx->d_sums, &ctx->d_tally_scan, &ctx->d_tally_out,
                     &ctx->d_readfirst, &ctx->d_mtot, &ctx->d_moff, &ctx->d_mlen, &ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
   for (DevBuf *b : bufs) b->release();

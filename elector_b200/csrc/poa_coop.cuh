@@ -124,11 +124,11 @@ EL_HD void make_layout_c1(LayoutC1 &L, int LR, int LC) {
   L.o_ref = L.l2.total;
   L.total = L.o_ref + cdiv_u((uint32_t)LR, 4) + 1;
 }
-EL_HDN inline void linear_node_list(const LaneScratch &scr, uint32_t o_ref, int lr, uint16_t *out) {
+EL_HDN inline void linear_node_list(const LaneScratch &scr, uint32_t o_ref, int lr, uint16_t *out, uint32_t carried = NF_REF) {
   uint64_t *out4 = reinterpret_cast<uint64_t *>(out);
   uint64_t acc = 0;
   for (int j = 0; j < lr; ++j) {
-    const uint32_t v = (uint32_t)scr.code_at(o_ref, j) | NF_REF | (j == 0 ? NF_INITIAL : 0u) | (j == lr - 1 ? NF_FINAL : 0u);
+    const uint32_t v = (uint32_t)scr.code_at(o_ref, j) | carried | (j == 0 ? NF_INITIAL : 0u) | (j == lr - 1 ? NF_FINAL : 0u);
     acc |= (uint64_t)v << (16 * (j & 3));
     if ((j & 3) == 3) { out4[j >> 2] = acc; acc = 0; }
   }
@@ -200,7 +200,9 @@ __device__ __forceinline__ void coop_dp(const Phase2<GENERIC_SUB> &win, uint32_t
 
 // Phase 2 of the longest windows: groups of `group` windows per warp (owners = lanes 0..group-1).
 template <bool GENERIC_SUB>
-__global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(PoaArgs a, const SymbolTables *g_tab, int group) {
+// linear_seg: the launch holds windows whose P1 is lin(ref) with every node carrying both letters (the linear segments of
+// sort 2); their node list is rebuilt from the reference letters (windows whose cor is ref never ran phase 1, bin_kernel.cuh).
+__global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(PoaArgs a, const SymbolTables *g_tab, int group, bool linear_seg) {
   __shared__ uint32_t s_tab[(GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4];
   __shared__ Layout2 s_layout;
   __shared__ uint32_t s_bset[2 * kSlotWords];
@@ -236,7 +238,12 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     if (owner) {
       c.scr.pack_codes(c.sc.tab, a.unc + uo, lu, s_layout.o_unc);
-      c.prepare(a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), n1);
+      uint16_t *p1 = a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w);
+      if (linear_seg) {   // the ref codes pass through the (still unused) MSA row area
+        c.scr.pack_codes(c.sc.tab, a.ref + ro, n1, s_layout.o_rows);
+        linear_node_list(c.scr, s_layout.o_rows, n1, p1, NF_REF | NF_COR);
+      }
+      c.prepare(p1, n1);
     }
     int s2 = 0, bj = -1;
     for (int i = 0; i < cnt; ++i) {

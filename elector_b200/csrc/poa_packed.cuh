@@ -262,38 +262,6 @@ struct Phase1P {
   }
 };
 
-// =============================== phase 1 of a window whose cor IS ref ===========================
-// The size sort (bin_kernel.cuh) puts the small windows whose corrected letters equal the reference letters byte for
-// byte into segments of their own.  With match 0 and every other score negative (the packed matrix class) the diagonal
-// is the unique optimum of DP1 (score 0; any other path pays at least one gap or mismatch), so P1 is lin(ref) with every
-// node carrying both letters (lpo.c:413-463): no DP, no traceback -- the node list is written directly.
-struct LayoutI { uint32_t o_ref, total; };
-struct Phase1I {
-  typedef LayoutI Layout;
-  static constexpr bool kGenericSub = false;
-  LaneScratch scr;
-  Scoring sc;
-  const LayoutI *Lp;
-  static EL_HD void make_layout(LayoutI &L, int LR, int) { L.o_ref = 0; L.total = cdiv_u((uint32_t)LR, 4) + 2; }
-  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *, int, uint16_t *p1_out, int &s1, int &spcode) const {
-    scr.pack_codes(sc.tab, ref, lr, Lp->o_ref);
-    uint64_t *out4 = reinterpret_cast<uint64_t *>(p1_out);
-    uint64_t acc = 0;
-    uint32_t xw = 0;
-    for (int j = 0; j < lr; ++j) {
-      if ((j & 3) == 0) xw = scr.w(Lp->o_ref + (j >> 2));
-      const uint32_t v = (xw & 0xffu) | NF_REF | NF_COR | (j == 0 ? NF_INITIAL : 0u) | (j == lr - 1 ? NF_FINAL : 0u);
-      xw >>= 8;
-      acc |= (uint64_t)v << (16 * (j & 3));
-      if ((j & 3) == 3) { out4[j >> 2] = acc; acc = 0; }
-    }
-    if (lr & 3) out4[lr >> 2] = acc;
-    s1 = 0;
-    spcode = 0;
-    return lr;
-  }
-};
-
 // =============================== phase 2, packed ===============================================
 // DP2 (P1 columns x lin(unc) rows) with the same skewed half-bands: iteration j updates node j in
 // the low halves and node j-1 in the high halves.  The two frontier sets of poa_kernel.cuh become

@@ -33,6 +33,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     std::vector<uint64_t> nodes64(((size_t)lr + lc) / 4 + 2, 0xdeaddeaddeaddeadull);
     uint16_t *nodes_p = reinterpret_cast<uint16_t *>(nodes64.data());
     int s1, spcode, n1;
+    bool ident = false;   // no node list was written
     const int cap_r = lr + (int)(w % 3), cap_c = lc + (int)(w % 5);
     if (coop) {   // phase 1 through the warp-cooperative wavefront (lin(ref) as a node list)
       LayoutC1 L1;
@@ -48,16 +49,11 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       int bj = -1;
       coop_dp_emulated<GS>(p1, bset.data(), lr, lc, s1, bj);
       n1 = coop1_after<GS>(p1, L1, lr, lc, bj, nodes_p, spcode);
-    } else if (packed && sc.packed_ok && lr == lc && lr <= kSmallMax &&
-               memcmp(R.seq.data() + R.rec[w].off, C.seq.data() + C.rec[w].off, (size_t)lr) == 0) {   // cor is ref: the library runs Phase1I
-      LayoutI L1;
-      Phase1I::make_layout(L1, cap_r, cap_c);
-      std::vector<uint32_t> scratch1((size_t)L1.total * 32, 0xdeadbeefu);
-      Phase1I p1;
-      p1.scr.base = scratch1.data() + lane;
-      p1.sc = s;
-      p1.Lp = &L1;
-      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode);
+    } else if (packed && !general_only && sc.packed_ok && lr == lc && lr <= kSmallMax && lu <= kSmallMax &&
+               memcmp(R.seq.data() + R.rec[w].off, C.seq.data() + C.rec[w].off, (size_t)lr) == 0) {
+      // cor is ref: the size sort of the library (bin1_count_kernel) skips phase 1 -- P1 = lin(ref), every node carries both letters
+      n1 = lr; s1 = 0; spcode = 0;
+      ident = true;
       ++n_ident1;
     } else if (packed && sc.packed_ok && (long)sc.maxabs * (cap_r + cap_c + 4) <= kPackedSpan) {
       Layout1P L1;
