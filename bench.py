@@ -326,6 +326,18 @@ def main():
     ctx._check(lib.elector_int32_peak(ctx._ctx, ctypes.byref(mixed), ctypes.byref(alu)))
     lr, lc = np.diff(wl["ref_off"]), np.diff(wl["cor_off"])
     cells1 = int((lr * lc).sum())
+    # DP1 cells the kernels really sweep: windows whose corrected letters are the reference letters are recognised by
+    # the size sort and skip phase 1 (their DP1 has one possible result); the algorithmic count above includes them
+    lu_ = np.diff(wl["unc_off"])
+    cand = np.flatnonzero((lr == lc) & (lr <= 256) & (lu_ <= 256))
+    if len(cand):
+        ln = lr[cand]
+        pos = np.arange(int(ln.sum()), dtype=np.int64) - np.repeat(np.cumsum(ln) - ln, ln)
+        diff = wl["ref"][np.repeat(wl["ref_off"][cand], ln) + pos] != wl["cor"][np.repeat(wl["cor_off"][cand], ln) + pos]
+        ident = cand[np.add.reduceat(diff.astype(np.int32), np.cumsum(ln) - ln) == 0]
+    else:
+        ident = cand
+    cells1_swept = cells1 - int((lr[ident] * lc[ident]).sum())
     cells2 = cells - cells1
     p1_s = phase["p1"] / 1e3 / args.steps
     p2_s = (phase["tot"] - phase["p1"]) / 1e3 / args.steps
@@ -351,7 +363,7 @@ def main():
     line = {
         "metric": "triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "s16x2 (packed halfword integer SIMD; int32 for scores beyond 16 bits)", "data": "synthetic",
         "gcups": cells * world / (step_ms / 1e3) / 1e9,
         "gcups_poa_kernels_only": cells / poa_s / 1e9,
         "windows_per_sec": n * world / (step_ms / 1e3),
@@ -372,7 +384,8 @@ def main():
                      "peak_alu_pipe_only": alu.value,
                      "peak_source": "measured on this device by elector_int32_peak (IMAD/IADD3/VIMNMX/LOP3 chains)",
                      "also": {"kernel": "poa_dp1_kernel", "achieved": ach1, "frac": ach1 / mixed.value if mixed.value else None,
-                              "cells_per_step": cells1}},
+                              "cells_per_step": cells1, "cells_swept_per_step": cells1_swept,
+                              "note": "algorithmic cells (SURVEY.md 8d); %d of %d windows have cor == ref and skip DP1, the kernels sweep cells_swept_per_step" % (len(ident), n)}},
         "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / poa_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg_bytes / poa_s / 1e9 / hbm_peak, "traffic": (traffic or {}).get("poa_step_dram_bytes"),
                          "note": "algorithmic bytes = letters + offsets in, MSA rows + per-window results out; the path is integer-issue bound, not HBM bound"},

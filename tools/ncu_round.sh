@@ -1,0 +1,17 @@
+#!/bin/bash
+# ncu evidence of one round through the C `poa` executable (no Python in the profiled process):
+#   ${TAG}_launches.csv : every kernel launch of one 10 000-read call with its duration (cold-cache, serialised)
+#   ${TAG}_full.ncu-rep : --set full of the first POA launches of a 2 000-read call (bulk launches included)
+#   ${TAG}_dp2_10k.ncu-rep + ${TAG}_traffic.json : --set full of the phase-2 launch set of the 10 000-read call (DRAM bytes per launch)
+set +e
+O=gpurun_out; TAG=${1:-r1d}; mkdir -p $O
+exec > $O/${TAG}_ncu.log 2>&1
+python -c "import elector_b200; elector_b200.write_default_matrix('/tmp/blosum80.mat')"
+for R in 10000 2000; do python tools/dump_fasta.py $R 1 /tmp/prof$R; done
+cmd() { echo "elector_b200/bin/poa -pir /tmp/prof$1.pir -corrected_reads_fasta /tmp/prof$1.cor.fa -reference_reads_fasta /tmp/prof$1.ref.fa -uncorrected_reads_fasta /tmp/prof$1.unc.fa -pathMatrix /tmp/blosum80.mat"; }
+$(cmd 2000) > /dev/null; echo plain rc=$?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/${TAG}_launches.csv $(cmd 10000) > /dev/null; echo launches rc=$?
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:poa_dp -c 14 -o $O/${TAG}_full -f $(cmd 2000) > /dev/null; echo full rc=$?
+timeout 900 ncu --set full --clock-control none -k regex:poa_dp2 -c 9 -o $O/${TAG}_dp2_10k -f $(cmd 10000) > /dev/null; echo dp2-10k rc=$?
+python tools/ncu_traffic.py $O/${TAG}_dp2_10k.ncu-rep $O/${TAG}_traffic.json
+ls -la $O
