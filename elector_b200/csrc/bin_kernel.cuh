@@ -114,10 +114,15 @@ __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_
       bool ident = false;
       if (use_ident && lr == lc && lr <= kSmallMax && lu <= kSmallMax) {
         const uint8_t *a = id.ref + ro[w], *b = id.cor + co[w];
-        int i = 0;
         const int len = (int)lr;
-        while (i < len && a[i] == b[i]) ++i;
-        ident = i == len;
+        uint32_t d = 0;
+        int i = 0;
+        for (; i + 8 <= len && !d; i += 8) {   // eight independent byte pairs per step (the letters are not aligned)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d |= (uint32_t)(a[i + k] ^ b[i + k]);
+        }
+        for (; i < len && !d; ++i) d |= (uint32_t)(a[i] ^ b[i]);
+        ident = d == 0;
       }
       if (ident) {
         int bin2, seg2;
@@ -197,7 +202,13 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(int32_t n, const int32
   for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const int bin = key[w];
     if (bin < 0) continue;  // invalid window (reported by bin1_count_kernel), or a window that needs no phase 1
-    items[chunk_base[bin / kScanChunk] + atomicAdd(&cursor[bin], 1)] = w;
+    // neighbouring windows often share a bin: one atomic per distinct bin of the warp's active lanes
+    const unsigned peers = __match_any_sync(__activemask(), bin);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[bin], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    items[chunk_base[bin / kScanChunk] + base + __popc(peers & ((1u << lane) - 1u))] = w;
   }
 }
 

@@ -12,6 +12,17 @@ int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uin
                                                                d_counters, ctx->d_ctrl.as<int32_t>() + 3);
   CU(cudaGetLastError());
   ctx->last_launches += 1;
+#ifdef ELECTOR_TALLY_TIMING
+  {
+    unsigned long long h[4];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpyFromSymbol(h, g_tally_clk, sizeof h);
+    fprintf(stderr, "[tally timing] clocks per read: A %.0f  B %.0f  C %.0f  reduce+store %.0f (cumulative over %lld reads)\n", (double)h[0] / n_reads, (double)h[1] / n_reads,
+            (double)h[2] / n_reads, (double)h[3] / n_reads, (long long)n_reads);
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_tally_clk, z, sizeof z);
+  }
+#endif
   return ELECTOR_OK;
 }
 

@@ -369,6 +369,12 @@ __device__ __forceinline__ void classify_column(int i, uint32_t r_, uint32_t c_,
   }
 }
 
+#ifdef ELECTOR_TALLY_TIMING
+__device__ unsigned long long g_tally_clk[4];
+#define TT(k) if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_tally_clk[k], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
+#else
+#define TT(k)
+#endif
 __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const uint8_t *R, const uint8_t *C, const uint8_t *U,
                                                           const int64_t *off, const int32_t *len, uint32_t *bits, int64_t plane_words,
                                                           int64_t *counters, int32_t *overflow_flag) {
@@ -379,6 +385,9 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool assessed = L > 10;
   const bool vec = (off[r] & 15) == 0;
+#ifdef ELECTOR_TALLY_TIMING
+  long long t_prev = clock64();
+#endif
   __shared__ ReadScan sc;
   __shared__ int sm[4][kNAcc];
   __shared__ uint32_t s_bits[3 * kSmemMaskWords];
@@ -413,6 +422,7 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
     }
   }
   __syncthreads();
+  TT(0)
   if (threadIdx.x == 0) {                                // B
     ReadScan o;
     o.gl = o.gr = 0; o.ext = -1; o.nkeys = 0; o.overflow = 0;
@@ -431,6 +441,7 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
     sc = o;
   }
   __syncthreads();
+  TT(1)
   int acc[kNAcc];                                        // C
 #pragma unroll
   for (int k = 0; k < kNAcc; ++k) acc[k] = 0;
@@ -457,6 +468,7 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
       for (int i = threadIdx.x; i < L; i += blockDim.x) classify_column(i, rr[i], cc[i], uu[i], cm, acc);
     }
   }
+  TT(2)
 #pragma unroll
   for (int k = 0; k < kNAcc; ++k) {
     int v = acc[k];
@@ -484,6 +496,7 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
       o[ELECTOR_T_ASSESSED] = 1;
     }
   }
+  TT(3)
 }
 
 // ---- global counters: sums[k] += sum over reads of counters[r][k] (the "final counter reduction") ----

@@ -63,7 +63,7 @@ def emul_bin():
     exe = os.path.join(ROOT, "tests", "emul", "poa_emul")
     deps = [src] + [os.path.join(ROOT, "elector_b200", "csrc", f) for f in ("poa_kernel.cuh", "poa_packed.cuh", "bin_kernel.cuh", "host_setup.hpp", "host_io.hpp")]
     if not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(p) for p in deps):
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src])
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-arch=sm_100a", "-Wno-deprecated-gpu-targets", "-o", exe, src])
     return exe
 
 
