@@ -159,6 +159,28 @@ struct BitRow {
     }
     return L;
   }
+  // the same for a whole warp that runs the scan redundantly (all lanes pass the same i): 32 words per step
+  __device__ int next_pair_warp(int i) const {
+    const int nw = (L + 31) >> 5, lane = threadIdx.x & 31;
+    if (i >= L) return L;
+    const int k0 = i >> 5;
+    for (int kb = k0; kb < nw; kb += 32) {
+      const int k = kb + lane;
+      uint32_t p = 0;
+      if (k < nw) {
+        const uint32_t w = m[k], nx = k + 1 < nw ? m[k + 1] : 0u;
+        p = w & ((w >> 1) | (nx << 31));
+        if (k == k0) p &= ~0u << (i & 31);
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, p != 0);
+      if (any) {
+        const int src = __ffs(any) - 1;
+        const uint32_t pp = __shfl_sync(0xffffffffu, p, src);
+        return min(L, (kb + src) * 32 + __ffs(pp) - 1);
+      }
+    }
+    return L;
+  }
   // length of the run of columns equal to v that starts at i (i < L), going right
   __device__ int run_fwd(int i, bool v) const {
     const int s = i;
@@ -252,7 +274,8 @@ struct StretchState {  // streaming form of findGapStretches' borders / merge / 
   }
 };
 
-// findGapStretches (computeStats.py:104-189) restated over the RUNS of dots of the corrected row.
+// findGapStretches (computeStats.py:104-189) restated over the RUNS of dots of the corrected row.  Run by all 32 lanes of
+// one warp with identical state (the search for the next run that counts is the only cooperative step).
 // Per column the reference keeps cg (corrected-gap run: 0 on a run's first column unless it is
 // column 0, then the run length so far) and cr (reference-gap counter that only advances while the
 // previous corrected column was a gap and resets on every reference base).  Only runs that reach
@@ -269,7 +292,7 @@ __device__ void find_gap_stretches(const BitRow &dc, const BitRow &dr, ReadScan 
     // A run of one dot that does not start at column 0 ends with cg == 0: it neither marks columns nor closes a slot.
     // Most runs of the corrected row are such single dots (an inserted base of the uncorrected read), so the scan
     // goes straight to the next run that counts: the one at column 0, or the next run of two or more dots.
-    const int st = (i == 0 && dc.bit(0)) ? 0 : dc.next_pair(i);
+    const int st = (i == 0 && dc.bit(0)) ? 0 : dc.next_pair_warp(i);
     if (st >= L) break;
     const int len = dc.run_fwd(st, true), e = st + len - 1;
     const bool counts = st == 0 || len >= 2;            // cg > 0 when the run ends
@@ -339,6 +362,23 @@ __device__ __forceinline__ uint32_t eq_nibble(uint32_t x, uint32_t pat) {
 }
 __device__ __forceinline__ uint32_t eq_mask16(const uint4 &v, uint32_t pat) {
   return eq_nibble(v.x, pat) | (eq_nibble(v.y, pat) << 4) | (eq_nibble(v.z, pat) << 8) | (eq_nibble(v.w, pat) << 12);
+}
+
+// 4 bytes -> 4 bits: bit k set when byte k of z is zero
+__device__ __forceinline__ uint32_t zero_nibble(uint32_t z) {
+  const uint32_t m = ~(((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z | 0x7f7f7f7fu);
+  return (((m >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+__device__ __forceinline__ uint32_t eq_pair16(const uint4 &a, const uint4 &b) {   // bit k: byte k of a equals byte k of b
+  return zero_nibble(a.x ^ b.x) | (zero_nibble(a.y ^ b.y) << 4) | (zero_nibble(a.z ^ b.z) << 8) | (zero_nibble(a.w ^ b.w) << 12);
+}
+__device__ __forceinline__ uint32_t gc_mask16(const uint4 &v) {                    // bit k: byte k is one of g c G C
+  const uint4 f = make_uint4(v.x | 0x20202020u, v.y | 0x20202020u, v.z | 0x20202020u, v.w | 0x20202020u);
+  return eq_mask16(f, 0x67676767u) | eq_mask16(f, 0x63636363u);
+}
+__device__ __forceinline__ uint32_t range_mask16(int lo, int hi) {                 // bits lo..hi (clamped to 0..15), empty when hi < lo
+  lo = max(lo, 0); hi = min(hi, 15);
+  return hi < lo ? 0u : ((2u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 
 struct ColumnMask {   // which columns the classification skips (gapsAndExtensions + gap stretches)
@@ -423,7 +463,7 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
   }
   __syncthreads();
   TT(0)
-  if (threadIdx.x == 0) {                                // B
+  if (threadIdx.x < 32) {                                // B (warp 0, every lane with the same state)
     ReadScan o;
     o.gl = o.gr = 0; o.ext = -1; o.nkeys = 0; o.overflow = 0;
     for (int k = 0; k < kMaxStretchKeys; ++k) o.key_a[k] = o.key_b[k] = 0;
@@ -436,9 +476,9 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
       if (o.gr >= T_THRESH2) ext = (ext < 0 ? 0 : ext) + o.gr - dc.count(L - o.gr + 1, L);
       o.ext = ext;
       find_gap_stretches(dc, dr, o);
-      if (o.overflow) atomicExch(overflow_flag, 1);
+      if (o.overflow && threadIdx.x == 0) atomicExch(overflow_flag, 1);
     }
-    sc = o;
+    if (threadIdx.x == 0) sc = o;
   }
   __syncthreads();
   TT(1)
@@ -455,14 +495,30 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
     if (vec) {
       const uint4 *r4 = reinterpret_cast<const uint4 *>(rr), *c4 = reinterpret_cast<const uint4 *>(cc), *u4 = reinterpret_cast<const uint4 *>(uu);
       const int nq = (L + 15) >> 4;
+      // 16 columns at a time as bitmasks: byte equalities (SWAR), dots, the column mask; every counter is a popcount
       for (int q = threadIdx.x; q < nq; q += 128) {
         const uint4 vr = r4[q], vc = c4[q], vu = u4[q];
-        const uint32_t wr[4] = {vr.x, vr.y, vr.z, vr.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w}, wu[4] = {vu.x, vu.y, vu.z, vu.w};
-        const int i0 = q * 16, n = min(16, L - i0);
-#pragma unroll
-        for (int b = 0; b < 16; ++b)
-          if (b < n) classify_column(i0 + b, (wr[b >> 2] >> (8 * (b & 3))) & 0xffu, (wc[b >> 2] >> (8 * (b & 3))) & 0xffu,
-                                     (wu[b >> 2] >> (8 * (b & 3))) & 0xffu, cm, acc);
+        const int i0 = q * 16;
+        const uint32_t V = range_mask16(0, L - 1 - i0);
+        const uint32_t Dr = eq_mask16(vr, 0x2e2e2e2eu) & V, Dc = eq_mask16(vc, 0x2e2e2e2eu) & V, Du = eq_mask16(vu, 0x2e2e2e2eu) & V;
+        const uint32_t Erc = eq_pair16(vr, vc), Eru = eq_pair16(vr, vu), Euc = eq_pair16(vu, vc);
+        acc[13] += __popc(gc_mask16(vr) & V); acc[14] += __popc(gc_mask16(vc) & V);
+        acc[15] += __popc(Dr); acc[16] += __popc(Dc); acc[17] += __popc(Du);
+        uint32_t OK = V & range_mask16(cm.lmask - i0, cm.rmask - i0);
+        for (int k = 0; k < cm.nkeys; ++k) {
+          const uint32_t in = V & range_mask16(cm.key_a[k] - i0, cm.key_b[k] - i0);
+          OK &= ~in;
+          acc[18] += __popc(Dr & in);                       // dots of the reference row inside stretches
+        }
+        const uint32_t Nrc = OK & ~Erc, Nru = OK & ~Eru;
+        acc[7] += __popc(Nrc & Dr); acc[9] += __popc(Nrc & ~Dr & ~Dc); acc[8] += __popc(Nrc & ~Dr & Dc);
+        acc[10] += __popc(Nru & Dr); acc[12] += __popc(Nru & ~Dr & ~Du); acc[11] += __popc(Nru & ~Dr & Du);
+        const uint32_t A = OK & Eru, X = A & ~Euc, Y = A & Euc;
+        const uint32_t B1 = Nru & Erc, B2 = Nru & ~Erc, B3 = B2 & Euc;
+        acc[5] += __popc(A); acc[6] += __popc(Nru);
+        acc[0] += __popc(Y) + __popc(B1); acc[3] += __popc(Y) + __popc(B1);
+        acc[1] += __popc(X) + __popc(B3); acc[4] += __popc(X) + __popc(B2);
+        acc[2] += __popc(B3);
       }
     } else {
       for (int i = threadIdx.x; i < L; i += blockDim.x) classify_column(i, rr[i], cc[i], uu[i], cm, acc);
