@@ -432,13 +432,18 @@ void add_kernel_ms(elector_ctx *ctx) {
 }
 
 
-struct ChunkJob { int64_t w0, w1, r0, r1, rows_base, rows_len; bool split; };
+struct ChunkJob { int64_t w0, w1, r0, r1, rows_base, rows_len; bool split; int index; };
 struct PipeArgs {
   int64_t n;
   const char *ref; const int64_t *ro; const char *cor; const int64_t *co; const char *unc; const int64_t *uo;
   int64_t n_reads; const int64_t *read_first;
   char *rows_out; int64_t *row_off; int32_t *row_stride, *nring, *score1, *score2; int64_t *cells, *counters_out;
   cudaEvent_t ev_call;   // start of the call on the device (ELECTOR_TRACE)
+  // the chunks' inputs cross PCIe in chunk order (a worker queues its copies when it is its chunk's turn, behind the
+  // previous chunk's): chunk 0 computes while chunk 1 is still arriving
+  std::atomic<int> *h2d_turn;
+  cudaEvent_t *h2d_prev;
+  std::atomic<int> *failed;
 };
 
 // One chunk of a pipelined call on one worker context: everything is queued on the worker's stream (the segment launches
@@ -454,6 +459,16 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   CU(ctx->d_nring.reserve(nw * 4)); CU(ctx->d_s1.reserve(nw * 4)); CU(ctx->d_s2.reserve(nw * 4)); CU(ctx->d_cells.reserve(nw * 8));
   if (nr > 0) { CU(ctx->d_tally_out.reserve(nr * ELECTOR_TALLY_K * 8)); CU(ctx->d_sums.reserve(ELECTOR_TALLY_K * 8)); }
   cudaStream_t st = ctx->stream;
+  while (pa.h2d_turn->load(std::memory_order_acquire) != j.index) {
+    if (pa.failed->load() != ELECTOR_OK) return ctx->fail(ELECTOR_ECUDA, "another chunk of the call failed");
+    std::this_thread::yield();
+  }
+  struct PassTurn {   // whatever happens below, the next chunk gets its turn
+    const PipeArgs &pa; int next; bool passed;
+    void pass() { if (!passed) { passed = true; pa.h2d_turn->store(next, std::memory_order_release); } }
+    ~PassTurn() { pass(); }
+  } pass_turn{pa, j.index + 1, false};
+  if (*pa.h2d_prev) CU(cudaStreamWaitEvent(st, *pa.h2d_prev, 0));
   if (ctx->trace) CU(cudaEventRecord(ctx->uev0, st));
   // the offsets first, on the compute stream: the size sort needs nothing else.  The letters follow on the copy stream --
   // ref and cor (phase 1 waits for them), then unc (phase 2 waits for it) -- while the sort and phase 1 run.
@@ -468,6 +483,8 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   CU(cudaMemcpyAsync(ctx->d_unc.p, pa.unc + bu0, bu, cudaMemcpyHostToDevice, ctx->copy_in));
   CU(cudaEventRecord(ctx->ev_in[1], ctx->copy_in));
   ctx->wait_in[0] = ctx->ev_in[0]; ctx->wait_in[1] = ctx->ev_in[1];
+  *pa.h2d_prev = ctx->ev_in[1];
+  pass_turn.pass();
   // the offsets stay those of the whole call: the letter pointers are moved back by the chunk's first offset, the row
   // pointer by the chunk's base in the caller's row buffer (row_off[] then indexes the caller's buffer directly)
   char *d_rows_v = ctx->d_rows.as<char>() - j.rows_base;
@@ -754,9 +771,11 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   const bool trace = ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   // ---- chunk boundaries (windows; whole reads when reads are given) ----
   // Large chunks: the kernels run 32 windows of one sorted size class in lock step and finish a class with its slowest
-  // group, so their throughput grows with the number of windows sorted together (measured on config 1: one chunk of
-  // 1.96 M windows 12.4 ms of kernels, six chunks of 0.33 M 23.5 ms).  ELECTOR_PIPELINE_CHUNKS forces a chunk count.
-  int64_t chunk_windows = 2000000;
+  // group, so their throughput grows with the number of windows sorted together (config 1, 1.96 M windows: 9 ms of
+  // kernels in one chunk, 11 ms in three, 13 ms in six) -- but chunks on several workers overlap their transfers with
+  // each other's kernels: three chunks of ~0.65 M windows on three workers are the measured best (14.0 ms per call against
+  // 16.0 ms in one chunk).  ELECTOR_PIPELINE_CHUNKS forces a chunk count.
+  int64_t chunk_windows = 700000;
   int want_workers = 3;
   if (const char *e = getenv("ELECTOR_PIPELINE_CHUNK_WINDOWS")) chunk_windows = std::max<int64_t>(1024, atoll(e));
   if (const char *e = getenv("ELECTOR_PIPELINE_WORKERS")) want_workers = std::max(1, std::min(8, atoi(e)));
@@ -783,17 +802,19 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   // rows of chunk k land at rows_out + rows_base(k): the bound of the windows before it.  The O(1) bound when the
   // caller's buffer allows it, else the exact one (one pass over the offsets).
   const bool loose = rows_cap >= elector_poa_rows_bound(n, ro, co, uo);
-  {
+  if (loose) {
+    // region k = [lo16(bound of the windows before it), lo16(bound of the windows up to its end)): the regions tile the O(1)
+    // bound of the call whatever the chunking; a window needs at least 6 bytes less than its share, which covers the rounding
+    auto before = [&](int64_t w) { return (3 * (ro[w] + co[w] + uo[w] + 3 * w)) & ~(int64_t)15; };
+    for (ChunkJob &j : jobs) { j.rows_base = before(j.w0); j.rows_len = before(j.w1) - j.rows_base; j.split = j.w1 - j.w0 >= 16; }
+  } else {
     int64_t base = 0;
     for (ChunkJob &j : jobs) {
       j.rows_base = base;
-      j.split = loose;   // two row regions need the spare bytes of the O(1) bound (the boundary is aligned to 16 bytes)
-      if (loose) j.rows_len = elector_poa_rows_bound(j.w1 - j.w0, ro + j.w0, co + j.w0, uo + j.w0);
-      else {
-        int64_t t = 0;
-        for (int64_t w = j.w0; w < j.w1; ++w) t += ((ro[w + 1] - ro[w]) + (co[w + 1] - co[w]) + (uo[w + 1] - uo[w]) + 3) & ~(int64_t)3;
-        j.rows_len = 3 * t;
-      }
+      j.split = false;   // two row regions need the spare bytes of the O(1) bound (the boundary is aligned to 16 bytes)
+      int64_t t = 0;
+      for (int64_t w = j.w0; w < j.w1; ++w) t += ((ro[w + 1] - ro[w]) + (co[w + 1] - co[w]) + (uo[w + 1] - uo[w]) + 3) & ~(int64_t)3;
+      j.rows_len = 3 * t;
       base += j.rows_len;
     }
     if (base > rows_cap) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small (%lld needed)", (long long)rows_cap, (long long)base);
@@ -806,14 +827,18 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
     if (rc != ELECTOR_OK) return ctx->fail(rc, "worker context: %s", g_init_error.c_str());
     ctx->workers.push_back(child);
   }
-  PipeArgs pa{n, ref, ro, cor, co, unc, uo, n_reads, read_first, rows_out, row_off, row_stride, nring, score1, score2, cells, counters_out, ctx->ev_fork};
+  std::atomic<int> h2d_turn{0};
+  std::atomic<int> first_error{ELECTOR_OK};
+  cudaEvent_t h2d_prev = nullptr;
+  for (size_t k = 0; k < jobs.size(); ++k) jobs[k].index = (int)k;
+  PipeArgs pa{n, ref, ro, cor, co, unc, uo, n_reads, read_first, rows_out, row_off, row_stride, nring, score1, score2, cells, counters_out, ctx->ev_fork,
+              &h2d_turn, &h2d_prev, &first_error};
   if (trace) {
     while (ctx->chunk_ev.empty()) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->chunk_ev.push_back(e); }
     pa.ev_call = ctx->chunk_ev[0];
     CU(cudaEventRecord(pa.ev_call, ctx->stream));
   }
   std::atomic<size_t> next{0};
-  std::atomic<int> first_error{ELECTOR_OK};
   const auto host_t0 = std::chrono::steady_clock::now();
   auto work = [&](elector_ctx *wk, int id) {
     wk->trace = trace;

@@ -127,14 +127,18 @@ def test_device_chain_poa_merge_tally_vs_oracle():
         assert [int(v) for v in got[r]] == [exp[k] for k in TALLY_FIELDS], r
 
 
-def test_pipeline_call_equals_oracle_chain():
-    """elector_pipeline_run (host buffers, chunked, copies overlapped) on a multi-chunk workload equals
-    oracle POA -> oracle merge -> oracle tally read by read; the sums equal the column sums"""
+@pytest.mark.parametrize("chunks,workers", [("1", "1"), ("4", "3"), ("7", "2")])
+def test_pipeline_call_equals_oracle_chain(chunks, workers, monkeypatch):
+    """elector_pipeline_run (host buffers; one chunk, or several chunks on several worker contexts, copies overlapped,
+    rows in two regions per chunk) equals oracle POA -> oracle merge -> oracle tally read by read; the sums equal the
+    column sums"""
+    monkeypatch.setenv("ELECTOR_PIPELINE_CHUNKS", chunks)
+    monkeypatch.setenv("ELECTOR_PIPELINE_WORKERS", workers)
     import elector_b200
     import workloads
     from elector_b200 import TALLY_FIELDS
     from oracle import oracle, tally_oracle as to
-    wl = workloads.make_windows(2, 900)            # ~250k windows: several chunks; trimmed / split reads
+    wl = workloads.make_windows(2, 900)            # ~250k windows; trimmed / split reads
     with elector_b200.PoaContext(0) as c:
         res, counters, sums = c.pipeline_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"], wl["read_first"])
         res2 = c.run_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"])
