@@ -75,7 +75,10 @@ int elector_poa_run(elector_ctx *ctx, int64_t n_windows,
                     char *rows_out, int64_t rows_cap, int64_t *row_off, int32_t *row_stride,
                     int32_t *nring, int32_t *score1, int32_t *score2, int64_t *cells);
 
-/* Upper bound of the bytes elector_poa_run can write to rows_out. */
+/* Upper bound of the bytes elector_poa_run / elector_pipeline_run can write to rows_out: O(1), 3 bytes per letter of the
+ * call plus 9 per window, in 16-byte granules.  Row positions inside the buffer are arbitrary (row_off[] says where
+ * each window's rows are); with a buffer of at least this size the pipelined entry point returns the rows in several
+ * regions while later windows still compute.  A smaller buffer is accepted as long as the exact need fits. */
 int64_t elector_poa_rows_bound(int64_t n_windows, const int64_t *ref_off,
                                const int64_t *cor_off, const int64_t *unc_off);
 
