@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_
         id.n1[w] = (int)lr;
         id.key2[w] = bin2;
         if (id.score1) id.score1[w] = 0;
-        atomicAdd(&id.hist2[bin2], 1);
+        warp_hist_add(id.hist2, bin2);
         if ((int)lr > id.seg2_max[seg2 * 4]) atomicMax(&id.seg2_max[seg2 * 4], (int)lr);
         if ((int)lu > id.seg2_max[seg2 * 4 + 1]) atomicMax(&id.seg2_max[seg2 * 4 + 1], (int)lu);
         lin += 3ull * (unsigned long long)((lr + lc + lu + 3) & ~(int64_t)3);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_
       } else {
         int seg;
         bin1_of((int)lr, (int)lc, bin, seg);
-        atomicAdd(&hist[bin], 1);
+        warp_hist_add(hist, bin);
         int32_t *mx = &tab->seg_max[seg * 4];
         if ((int)lr > mx[0]) atomicMax(&mx[0], (int)lr);
         if ((int)lc > mx[1]) atomicMax(&mx[1], (int)lc);

@@ -750,6 +750,12 @@ __device__ __forceinline__ const SymbolTables *stage_tables(uint32_t *smem, cons
 }
 
 #ifdef __CUDACC__
+// hist[bin] += 1 for the calling lanes, one atomic per distinct bin among them (neighbouring windows share bins)
+__device__ __forceinline__ void warp_hist_add(int32_t *hist, int bin) {
+  const unsigned peers = __match_any_sync(__activemask(), bin);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+}
+
 // What phase 1 leaves for phase 2 (all lanes call it; inactive lanes pass active = false): len(P1), the sort bin, the
 // histogram and maxima of sort 2, and the row bytes the windows of the linear segments can need (one atomic per warp).
 __device__ __forceinline__ void phase1_epilogue(const PoaArgs &a, bool active, int w, int n1, int s1, int spcode, int lr, int lc) {
@@ -761,7 +767,7 @@ __device__ __forceinline__ void phase1_epilogue(const PoaArgs &a, bool active, i
     a.n1[w] = n1;
     a.key2[w] = bin;
     if (a.score1) a.score1[w] = s1;
-    atomicAdd(&a.hist2[bin], 1);
+    warp_hist_add(a.hist2, bin);
     if (n1 > a.seg2_max[seg * 4]) atomicMax(&a.seg2_max[seg * 4], n1);
     if (lu > a.seg2_max[seg * 4 + 1]) atomicMax(&a.seg2_max[seg * 4 + 1], lu);
     if (seg >= kFirstLinSeg2) lb = 3u * (unsigned)((lr + lc + lu + 3) & ~3);

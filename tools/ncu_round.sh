@@ -2,6 +2,8 @@
 # ncu evidence of one round through the C `poa` executable (no Python in the profiled process):
 #   ${TAG}_launches.csv : every kernel launch of one 10 000-read call with its duration (cold-cache, serialised)
 #   ${TAG}_full.ncu-rep : --set full of the first POA launches of a 2 000-read call (bulk launches included)
+#   ${TAG}_launches_pipeline.csv : launch list of two pipelined calls (POA + merge + tally) through tools/pipe_driver.c
+#   ${TAG}_pipe_driver.txt / ${TAG}_pipe_trace.txt : host-clock time of 8 calls; device timeline (ELECTOR_TRACE=2) of one
 #   ${TAG}_dp2_10k.ncu-rep + ${TAG}_traffic.json : --set full of the phase-2 launch set of the 10 000-read call (DRAM bytes per launch)
 set +e
 O=gpurun_out; TAG=${1:-r1d}; mkdir -p $O
@@ -14,4 +16,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:poa_dp -c 14 -o $O/${TAG}_full -f $(cmd 2000) > /dev/null; echo full rc=$?
 timeout 900 ncu --set full --clock-control none -k regex:poa_dp2 -c 9 -o $O/${TAG}_dp2_10k -f $(cmd 10000) > /dev/null; echo dp2-10k rc=$?
 python tools/ncu_traffic.py $O/${TAG}_dp2_10k.ncu-rep $O/${TAG}_traffic.json
+# the whole pipelined call (POA + merge + tally) in one chunk on one worker, through the C driver of elector_pipeline_run
+python tools/dump_csr.py 10000 1 /tmp/c1 > /dev/null
+ELECTOR_PIPELINE_CHUNKS=1 ELECTOR_PIPELINE_WORKERS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
+elector_b200/bin/pipe_driver /tmp/c1 8 > $O/${TAG}_pipe_driver.txt 2>&1
+ELECTOR_TRACE=2 elector_b200/bin/pipe_driver /tmp/c1 3 2>&1 | tail -60 > $O/${TAG}_pipe_trace.txt
 ls -la $O
