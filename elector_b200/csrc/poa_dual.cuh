@@ -77,10 +77,13 @@ struct Phase2D : Phase2<false> {
     const int rr = ly - 1 - r0;
     uint32_t *p = rec(0);
     const uint32_t step = Lp->rec_words * 32;
+    // node j + 2 is loaded in iteration j (the scratch of a launch exceeds the L2; the long-scoreboard stall was this loop's top stall)
     uint32_t ra = p[R2_NODE * 32], bs = p[R2_BS * 32], bg = p[R2_BG * 32];
+    const uint32_t *p1 = nx > 1 ? p + step : p;
+    uint32_t ra_n = p1[R2_NODE * 32], bs_n = p1[R2_BS * 32], bg_n = p1[R2_BG * 32];
     for (int j = 0; j < nx; ++j, p += step) {
-      const uint32_t *pn = j + 1 < nx ? p + step : p;               // next node, one iteration ahead
-      const uint32_t ra_n = pn[R2_NODE * 32], bs_n = pn[R2_BS * 32], bg_n = pn[R2_BG * 32];
+      const uint32_t *pn = j + 2 < nx ? p + 2 * step : p;
+      const uint32_t ra_n2 = pn[R2_NODE * 32], bs_n2 = pn[R2_BS * 32], bg_n2 = pn[R2_BG * 32];
       const bool has_r = ra & NF_REF, both = has_r && (ra & NF_COR);
       if (both && !synced) {
         // end of a bubble: first strict maximum over [low half, high half]; for an INITIAL node whose real predecessor is
@@ -127,6 +130,7 @@ struct Phase2D : Phase2<false> {
         if (s > best) { best = s; best_j = j; }   // ties keep the smaller j (align_lpo_po2.c:410-417)
       }
       ra = ra_n; bs = bs_n; bg = bg_n;
+      ra_n = ra_n2; bs_n = bs_n2; bg_n = bg_n2;
     }
   }
 

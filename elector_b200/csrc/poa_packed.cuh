@@ -137,11 +137,11 @@ struct Layout1P {
 };
 EL_HD void make_layout1p(Layout1P &L, int LR, int LC) {
   uint32_t o = 0;
-  L.o_ref = o; o += cdiv_u(LR, 4) + 2;                         // the last iteration reads one letter past the end
+  L.o_ref = o; o += cdiv_u(LR, 4) + 3;                         // the last iteration reads one letter past the end, the look-ahead one word more
   L.o_cor = o; o += cdiv_u(LC, 4) + 5;                         // rows up to 16 * ceil(LC / 16) - 1 are read
   L.R = (uint32_t)packed_rows(LC);
   L.rec_words = P1_MOVES + cdiv_u(LC, 16);
-  L.o_nodes = o; o += ((uint32_t)LR + 3) * L.rec_words;        // record 0, LR nodes, two records of look-ahead
+  L.o_nodes = o; o += ((uint32_t)LR + 4) * L.rec_words;        // record 0, LR nodes, three records of look-ahead
   L.total = o;
 }
 
@@ -174,24 +174,27 @@ struct Phase1P {
     uint32_t *p = rec(-1);
     const uint32_t step = Lp->rec_words * 32;
     // boundary row r0 - 1 at nodes j-1 / j: S in the low half, G in the high half
-    uint32_t bsg, bsg_n;
+    // (loads run TWO iterations ahead of their use: the scratch of a launch exceeds the L2 and the long-scoreboard stall
+    // was the top stall reason of this loop, profiles/r1f)
+    uint32_t bsg, bsg_n, bsg_n2 = 0;
     if (b == 0) {                                              // row -1 (:272-286): corner, then -(open + ext * j)
       bsg = pk2(kBiasP, kBiasP - sc.open);
       bsg_n = pk2(kBiasP - sc.open, kBiasP - sc.open - sc.ext);
     } else {
       bsg = p[P1_BSG * 32];
       bsg_n = p[step + P1_BSG * 32];
+      bsg_n2 = p[2 * step + P1_BSG * 32];
     }
-    uint32_t xw = 0, x2 = 0, d7 = 0, mlo = 0;
+    uint32_t xw = 0, xw_next = scr.w(Lp->o_ref), x2 = 0, d7 = 0, mlo = 0;
     int best = 0;
     for (int j = 0; j <= lr; ++j, p += step) {                 // p = record of node j - 1
-      if ((j & 3) == 0) xw = scr.w(Lp->o_ref + (j >> 2));
+      if ((j & 3) == 0) { xw = xw_next; xw_next = scr.w(Lp->o_ref + (j >> 2) + 1); }   // the next four letters, one group ahead
       x2 = (x2 << 16) | ((xw & 0xffu) << 4);
       xw >>= 8;
       const uint32_t bsg_p = bsg;
       bsg = bsg_n;
       if (b == 0) bsg_n = bsg - pc.ext2;
-      else bsg_n = p[2 * step + P1_BSG * 32];                  // node j + 1, one iteration ahead
+      else { bsg_n = bsg_n2; bsg_n2 = p[3 * step + P1_BSG * 32]; }   // node j + 2
       const uint32_t diag0 = pk_lo_hi(bsg_p, d7 << 16);        // S(r0-1, j-1) | S(r0+R-1, j-2)
       const uint32_t up0 = (bsg >> 16) | (G[R - 1] << 16);     // G(r0-1, j)   | G(r0+R-1, j-1)
       d7 = S[R - 1];
