@@ -8,6 +8,8 @@
 set +e
 O=gpurun_out; TAG=${1:-r1d}; mkdir -p $O
 exec > $O/${TAG}_ncu.log 2>&1
+# the profiled calls run in ONE chunk on one worker, like the device-resident step bench.py's `value` and roofline time
+export ELECTOR_PIPELINE_CHUNKS=1 ELECTOR_PIPELINE_WORKERS=1
 python -c "import elector_b200; elector_b200.write_default_matrix('/tmp/blosum80.mat')"
 for R in 10000 2000; do python tools/dump_fasta.py $R 1 /tmp/prof$R; done
 cmd() { echo "elector_b200/bin/poa -pir /tmp/prof$1.pir -corrected_reads_fasta /tmp/prof$1.cor.fa -reference_reads_fasta /tmp/prof$1.ref.fa -uncorrected_reads_fasta /tmp/prof$1.unc.fa -pathMatrix /tmp/blosum80.mat"; }
@@ -18,7 +20,8 @@ timeout 900 ncu --set full --clock-control none -k regex:poa_dp2 -c 9 -o $O/${TA
 python tools/ncu_traffic.py $O/${TAG}_dp2_10k.ncu-rep $O/${TAG}_traffic.json
 # the whole pipelined call (POA + merge + tally) in one chunk on one worker, through the C driver of elector_pipeline_run
 python tools/dump_csr.py 10000 1 /tmp/c1 > /dev/null
-ELECTOR_PIPELINE_CHUNKS=1 ELECTOR_PIPELINE_WORKERS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
+unset ELECTOR_PIPELINE_CHUNKS ELECTOR_PIPELINE_WORKERS   # the default pipeline (chunks on worker contexts) for the host-clock numbers
 elector_b200/bin/pipe_driver /tmp/c1 8 > $O/${TAG}_pipe_driver.txt 2>&1
 ELECTOR_TRACE=2 elector_b200/bin/pipe_driver /tmp/c1 3 2>&1 | tail -60 > $O/${TAG}_pipe_trace.txt
 ls -la $O
