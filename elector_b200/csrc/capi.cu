@@ -781,14 +781,22 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   if (const char *e = getenv("ELECTOR_PIPELINE_WORKERS")) want_workers = std::max(1, std::min(8, atoi(e)));
   int64_t want_chunks = (n + chunk_windows - 1) / chunk_windows;
   if (const char *e = getenv("ELECTOR_PIPELINE_CHUNKS")) want_chunks = std::max(1, atoi(e));
-  const int64_t target = std::max<int64_t>(std::min<int64_t>(n, 65536), (n + want_chunks - 1) / want_chunks);
+  // ELECTOR_PIPELINE_TAPER=1: the first and the last chunk get half the windows of the others (the call starts computing
+  // and finishes copying sooner), at one more chunk than the size rule gives
+  bool taper = false;
+  if (const char *e = getenv("ELECTOR_PIPELINE_TAPER")) taper = e[0] == '1';
+  if (taper && want_chunks >= 2) ++want_chunks; else taper = false;
+  const double units = taper ? (double)(want_chunks - 1) : (double)want_chunks;   // chunk sizes in units: 0.5 1 ... 1 0.5, or all 1
   std::vector<ChunkJob> jobs;
   {
     int64_t w = 0, r = 0;
-    while (w < n) {
+    double done_units = 0.0;
+    for (int64_t k = 0; w < n; ++k) {
       ChunkJob j;
       j.w0 = w; j.r0 = r;
-      const int64_t want = std::min<int64_t>(n, w + target);
+      done_units += (taper && (k == 0 || k == want_chunks - 1)) ? 0.5 : 1.0;
+      int64_t want = k + 1 >= want_chunks ? n : (int64_t)((double)n * done_units / units);
+      want = std::min<int64_t>(n, std::max<int64_t>(want, w + std::min<int64_t>(n, 65536)));
       if (n_reads > 0) {   // first read boundary at or after the target (binary search on read_first)
         int64_t lo = r + 1, hi = n_reads;
         while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (read_first[mid] >= want) hi = mid; else lo = mid + 1; }
