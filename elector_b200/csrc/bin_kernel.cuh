@@ -69,7 +69,7 @@ inline void fill_segments2(BinTable &t) {
   const int hi[4] = {32, 16, 8, 4};
   for (int k = 0; k < 4; ++k) {
     t.seg[kBigTiers + k].first_bin = kBigTiers + (kSmallBins2 - 1 - (((hi[k] - 1) * kN1q + (kN1q - 1)) * kSpCodes + (kSpCodes - 1)));
-    t.seg[kFirstLinSeg2 + k].first_bin = kBigTiers + kSmallBins2 + (kLinBins2 - 1 - ((hi[k] - 1) * kN1q + (kN1q - 1)));
+    t.seg[kFirstLinSeg2 + k].first_bin = kBigTiers + kSmallBins2 + (kLinBins2 - 1 - (((hi[k] - 1) * kN1q + (kN1q - 1)) * kDcls + (kDcls - 1)));
   }
   t.seg[kNumSegs2].first_bin = kNumBins2;
 }

@@ -88,6 +88,7 @@ struct elector_ctx {
   size_t seg_ev_used = 0;
   bool trace = false;
   bool all_side = false;
+  int band_w = 6;          // ELECTOR_BAND_W: base half-width of the diagonal band of the packed linear kernels (+ rows/16 in phase 1, + rows/8 in phase 2; 0 = full DP)
   bool no_dual = false;    // ELECTOR_NO_DUAL=1: general windows of phase 2 on the INT32 kernel with frontier sets
   int resident_ph2d = 0;
   bool ph2d_alt = false;   // ELECTOR_PH2D_WARPS=20: the 96-register build of the dual-frontier kernel
@@ -137,7 +138,7 @@ const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error fl
 const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share a side stream
 
 #ifndef EL_MIN_WARPS_PH1P
-#define EL_MIN_WARPS_PH1P 32  // packed DP1: register cap 64 (32 one-warp CTAs per SM is the hardware limit)
+#define EL_MIN_WARPS_PH1P 28  // packed DP1: register cap 72 (64 spills since the diagonal band: 28 warps measured 0.2 ms per step faster than 32)
 #endif
 #ifndef EL_MIN_WARPS_PH2P
 #define EL_MIN_WARPS_PH2P 24  // packed DP2: register cap 80
@@ -146,7 +147,7 @@ const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share 
 #define EL_MIN_WARPS_PH2D 20  // dual-frontier packed DP2: register cap 96 (measured: 9.94 ms per config-1 step against 10.26 ms at 24 warps / 80 registers)
 #endif
 #ifndef EL_MIN_WARPS_PH2L
-#define EL_MIN_WARPS_PH2L 32  // packed linear DP2: register cap 64
+#define EL_MIN_WARPS_PH2L 28  // packed linear DP2: register cap 72
 #endif
 
 // kind of a segment's kernel: INT32 cells (poa_kernel.cuh), 16-bit packed cells (poa_packed.cuh), or -- phase 2 only --
@@ -368,6 +369,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
   a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
   a.error_flag = d_errflag;
+  a.band_w = ctx->band_w;
 
   // ---- phase 1 ----
   std::vector<SegPlan> plan;
@@ -601,6 +603,7 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   if (const char *e = getenv("ELECTOR_ALL_SIDE")) ctx->all_side = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_IDENT")) ctx->no_ident = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_DUAL")) ctx->no_dual = e[0] == '1';
+  if (const char *e = getenv("ELECTOR_BAND_W")) ctx->band_w = std::max(0, std::min(64, atoi(e)));
   if (const char *e = getenv("ELECTOR_PACKED2")) ctx->packed2 = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_LINEAR2")) ctx->no_linear2 = e[0] == '1';
   int ndev = 0;

@@ -128,6 +128,7 @@ struct PoaArgs {
   int32_t *row_stride, *nring, *score1, *score2;
   int64_t *cells;
   int32_t *error_flag;
+  int32_t band_w;        // half-width of the diagonal band of the packed linear kernels (0 = full DP), see BandW
 };
 
 // symbol tables: byte -> matrix index (lower-casing + limit_residues + index_symbols),
@@ -159,7 +160,8 @@ constexpr int kNbMax = kSmallMax / 8;   // 8-row half-bands of a small window: 1
 constexpr int kN1q = 128;               // len(P1) / 4 quanta of a small window (len(P1) <= 511)
 constexpr int kSpCodes = 98;            // 0 = ref and cor identical; 1 + 3*min(pos/2, 31) + type otherwise
 constexpr int kSmallBins2 = kNbMax * kN1q * kSpCodes;
-constexpr int kLinBins2 = kNbMax * kN1q; // small windows whose P1 is linear (ref and cor identical): their own bins and segments
+constexpr int kDcls = 4;                 // linear bins: classes of d = len(unc) - len(P1), so that the diagonal bands of a group overlap
+constexpr int kLinBins2 = kNbMax * kN1q * kDcls; // small windows whose P1 is linear (ref and cor identical): their own bins and segments
 constexpr int kNumBins2 = kBigTiers + kSmallBins2 + kLinBins2;
 constexpr int kNumSegs2 = kBigTiers + 8;
 constexpr int kFirstLinSeg2 = kBigTiers + 4;
@@ -179,7 +181,9 @@ EL_HD void bin2_of(int n1, int lu, int spcode, int &bin, int &seg) {
   } else {
     const int nb8 = (lu + 7) >> 3;
     if (spcode == 0) {
-      const int lin = (nb8 - 1) * kN1q + (n1 >> 2);
+      int dc = (lu - n1 + 6) >> 2;        // d in [-6,-3] [-2,1] [2,5] [6,9]; the tails join the outer classes
+      dc = dc < 0 ? 0 : dc > kDcls - 1 ? kDcls - 1 : dc;
+      const int lin = ((nb8 - 1) * kN1q + (n1 >> 2)) * kDcls + dc;
       bin = kBigTiers + kSmallBins2 + (kLinBins2 - 1 - lin);
       seg = seg2_of_nb(nb8) + 4;
     } else {
@@ -209,6 +213,24 @@ struct Scoring {
   EL_HD int virt_S(int row) const { return row < 0 ? 0 : -(open + ext * row); }
   EL_HD int virt_G(int row) const { return row < 0 ? -open : -(open + ext * row) - ext; }
 };
+
+// ---- diagonal band with an exactness test ----------------------------------------------
+// A global path that leaves the band of offsets (row - column) [min(0, d) - w, max(0, d) + w], d = len_y - len_x, has at
+// least two gaps with 2w + |d| gap symbols in all, so it scores at most band_bound(sc, w, d) (match scores are <= 0 in the
+// packed matrix class).  When the band-restricted DP ends ABOVE that bound every optimal path lies inside the band, the
+// cells on optimal paths have their exact values and every comparison the traceback re-reads is decided as in the full
+// DP (a predecessor that ties or wins there is on an optimal path itself): score, moves along the path and MSA are the
+// full DP's.  Otherwise the window is run again without a band.  Cells outside the band are "minus infinity" = kNegP, a
+// value every real score of a small window beats and that cannot leave the 16-bit range by the end of the DP.
+constexpr int kBandMaxSpan = 500;           // banding only for groups with len_x + len_y <= this: real scores stay above kNegP
+struct BandW {
+  int omin, omax;   // offsets swept (uniform over the warp: a superset of every lane's own band)
+  int w;            // half-width the exactness test assumes
+  bool on;
+};
+EL_HD int band_bound(const Scoring &sc, int w, int d) { return -(2 * sc.open + sc.ext * (2 * w + (d < 0 ? -d : d) - 2)); }
+
+
 
 // The in-place update of one register column by one node (align_lpo_po2.c:322-407) for R rows:
 // S/G hold the predecessor column on entry and the node's column on exit; returns the move bits
@@ -326,6 +348,7 @@ template <bool GENERIC_SUB>
 struct Phase1 {
   typedef Layout1 Layout;
   static constexpr bool kGenericSub = GENERIC_SUB;
+  static constexpr bool kBanded = false;
   static EL_HD void make_layout(Layout1 &L, int LR, int LC) { make_layout1(L, LR, LC); }
   LaneScratch scr;
   Scoring sc;
@@ -401,7 +424,8 @@ struct Phase1 {
     }
   }
 
-  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode) const {
+  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode, bool &exact) const {
+    exact = true;   // no band in the INT32 kernels
     scr.pack_codes(sc.tab, ref, lr, Lp->o_ref);
     scr.pack_codes(sc.tab, cor, lc, Lp->o_cor);
     s1 = dp(lr, lc);
@@ -597,6 +621,7 @@ struct Phase2 {
   typedef Layout2 Layout;
   static constexpr bool kGenericSub = GENERIC_SUB;
   static constexpr bool kLinear = false;
+  static constexpr bool kBanded = false;
   static constexpr int kSetWords = kSlotWords;
   static EL_HD void make_layout(Layout2 &L, int N1, int LU) { make_layout2(L, N1, LU); }
   LaneScratch scr;
@@ -750,6 +775,30 @@ __device__ __forceinline__ const SymbolTables *stage_tables(uint32_t *smem, cons
 }
 
 #ifdef __CUDACC__
+// the band of a group: offsets [min(0, d) - w, max(0, d) + w], d = rows - columns, of every active lane, UNITED over the
+// warp.  (Per-lane bands were measured slower than no band at all: lanes at different columns touch different node
+// records, and the lane-interleaved scratch is only coalesced when all lanes are at the same column.)
+__device__ __forceinline__ void group_band(BandW &bw, bool on, int w, bool active, int d) {
+  const int lo = active ? (d < 0 ? d : 0) : 0, hi = active ? (d > 0 ? d : 0) : 0;
+  bw.omin = __reduce_min_sync(EL_WARP_FULL, lo) - w;
+  bw.omax = __reduce_max_sync(EL_WARP_FULL, hi) + w;
+  bw.w = w;
+  bw.on = on;
+}
+// appends the failed lanes' windows to the warp's retry queue; true when 32 of them are ready (then nretry is already
+// reduced by 32 and the caller takes queue[nretry + lane])
+__device__ __forceinline__ bool queue_retries(int32_t *queue, int &nretry, bool failed, int w) {
+  const unsigned fm = __ballot_sync(EL_WARP_FULL, failed);
+  if (fm == 0) return false;
+  const int lane = threadIdx.x & 31;
+  if (failed) queue[nretry + __popc(fm & ((1u << lane) - 1u))] = w;
+  nretry += __popc(fm);
+  __syncwarp();
+  if (nretry < 32) return false;
+  nretry -= 32;
+  return true;
+}
+
 // hist[bin] += 1 for the calling lanes, one atomic per distinct bin among them (neighbouring windows share bins)
 __device__ __forceinline__ void warp_hist_add(int32_t *hist, int bin) {
   const unsigned peers = __match_any_sync(__activemask(), bin);
@@ -789,16 +838,13 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
   c.Lp = &s_layout;
-  for (;;) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(a.work_counter, 32);
-    base = __shfl_sync(EL_WARP_FULL, base, 0);
-    if (base >= a.n_items) break;
-    const bool active = base + lane < a.n_items;
-    int w = -1, lr = 0, lc = 0;
+  __shared__ int32_t s_retry[64];   // windows whose band-restricted DP failed its exactness test: run again without the band
+  int nretry = 0;
+  // one group: lane l owns window w (active lanes); returns true for a window that has to be run again without the band
+  auto process = [&](int w, bool active, bool banded) -> bool {
+    int lr = 0, lc = 0;
     int64_t ro = 0, co = 0;
     if (active) {
-      w = a.items[base + lane];
       ro = a.ref_off[w]; co = a.cor_off[w];
       lr = (int)(a.ref_off[w + 1] - ro); lc = (int)(a.cor_off[w + 1] - co);
     }
@@ -807,12 +853,31 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
       __syncwarp();
       if (lane == 0) PH::make_layout(s_layout, mr, mc);
       __syncwarp();
+      // half-width: the base plus 1/16 of the rows (cor differs from ref by ~1 %: scores stay near 0)
+      if constexpr (PH::kBanded) group_band(c.bw, banded && mr + mc <= kBandMaxSpan, a.band_w + (mc >> 4), active, lc - lr);
     }
-    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
+    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
     int s1 = 0, spcode = 0, n1 = 0;
-    if (active) n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), s1, spcode);
-    phase1_epilogue(a, active, w, n1, s1, spcode, lr, lc);
+    bool exact = true;
+    if (active) n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), s1, spcode, exact);
+    phase1_epilogue(a, active && exact, w, n1, s1, spcode, lr, lc);
     __syncwarp();
+    return active && !exact;
+  };
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(a.work_counter, 32);
+    base = __shfl_sync(EL_WARP_FULL, base, 0);
+    if (base >= a.n_items) break;
+    const bool active = base + lane < a.n_items;
+    const int w = active ? a.items[base + lane] : -1;
+    const bool failed = process(w, active, a.band_w > 0);
+    if constexpr (PH::kBanded) {
+      if (queue_retries(s_retry, nretry, failed, w)) { const int w2 = s_retry[nretry + lane]; __syncwarp(); process(w2, true, false); }
+    }
+  }
+  if constexpr (PH::kBanded) {
+    if (nretry > 0) { const bool act = lane < nretry; const int w2 = act ? s_retry[lane] : -1; __syncwarp(); process(w2, act, false); }
   }
 }
 
@@ -866,16 +931,13 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
   c.Lp = &s_layout;
-  for (;;) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(a.work_counter, 32);
-    base = __shfl_sync(EL_WARP_FULL, base, 0);
-    if (base >= a.n_items) break;
-    const bool active = base + lane < a.n_items;
-    int nring = 0, w = -1, n1 = 0, lu = 0;
+  __shared__ int32_t s_retry[64];   // windows whose band-restricted DP failed its exactness test: run again without the band
+  int nretry = 0;
+  // one group: lane l owns window w (active lanes); returns true for a window that has to be run again without the band
+  auto process = [&](int w, bool active, bool banded) -> bool {
+    int nring = 0, n1 = 0, lu = 0;
     int64_t ro = 0, co = 0, uo = 0;
     if (active) {
-      w = a.items[base + lane];
       ro = a.ref_off[w]; co = a.cor_off[w]; uo = a.unc_off[w];
       lu = (int)(a.unc_off[w + 1] - uo);
       n1 = a.n1[w];
@@ -885,22 +947,43 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
       __syncwarp();
       if (lane == 0) PH::make_layout(s_layout, mn, mu);
       __syncwarp();
+      // half-width: the base plus 1/8 of the rows (unc differs from ref by ~10 %: the score is about minus the length)
+      if constexpr (PH::kBanded) group_band(c.bw, banded && mn + mu <= kBandMaxSpan, a.band_w + (mu >> 3), active, lu - n1);
     }
-    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
+    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
+    bool exact = true;
     if (active) {
       int s2;
-      if constexpr (PH::kLinear) nring = c.run_linear(a.ref + ro, n1, a.unc + uo, lu, s2);   // P1 = lin(ref): no node list needed
+      if constexpr (PH::kLinear) nring = c.run_linear(a.ref + ro, n1, a.unc + uo, lu, s2, exact);   // P1 = lin(ref): no node list needed
       else nring = c.run_window(a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), n1, a.unc + uo, lu, s2);
-      a.nring[w] = nring;
-      if (a.score2) a.score2[w] = s2;
-      if (a.cells) {
-        const int64_t lr = a.ref_off[w + 1] - ro, lc = a.cor_off[w + 1] - co;
-        a.cells[w] = lr * lc + (int64_t)n1 * lu;
-      }
+      if (exact) {
+        a.nring[w] = nring;
+        if (a.score2) a.score2[w] = s2;
+        if (a.cells) {
+          const int64_t lr = a.ref_off[w + 1] - ro, lc = a.cor_off[w + 1] - co;
+          a.cells[w] = lr * lc + (int64_t)n1 * lu;
+        }
+      } else nring = 0;
     }
     __syncwarp();
-    store_window_rows(a, c.scr, s_layout.o_rows, s_layout.row_words, active, w, nring);
+    store_window_rows(a, c.scr, s_layout.o_rows, s_layout.row_words, active && exact, w, nring);
     __syncwarp();
+    return active && !exact;
+  };
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(a.work_counter, 32);
+    base = __shfl_sync(EL_WARP_FULL, base, 0);
+    if (base >= a.n_items) break;
+    const bool active = base + lane < a.n_items;
+    const int w = active ? a.items[base + lane] : -1;
+    const bool failed = process(w, active, a.band_w > 0);
+    if constexpr (PH::kBanded) {
+      if (queue_retries(s_retry, nretry, failed, w)) { const int w2 = s_retry[nretry + lane]; __syncwarp(); process(w2, true, false); }
+    }
+  }
+  if constexpr (PH::kBanded) {
+    if (nretry > 0) { const bool act = lane < nretry; const int w2 = act ? s_retry[lane] : -1; __syncwarp(); process(w2, act, false); }
   }
 }
 

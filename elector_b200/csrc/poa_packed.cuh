@@ -32,6 +32,7 @@
 namespace elector {
 
 constexpr int kBiasP = 16384;       // halves hold S + kBiasP
+constexpr int kNegP = kBiasP - 8000; // minus infinity of the diagonal band (biased): see BandW in poa_kernel.cuh
 constexpr int kPackedSpan = 16000;  // a segment runs packed when maxabs * (len_x + len_y + 4) <= kPackedSpan
 
 // rows per half-band of a group whose longest row sequence has ly letters: ceil(ly / 16) bands of 2R rows
@@ -148,20 +149,32 @@ EL_HD void make_layout1p(Layout1P &L, int LR, int LC) {
 struct Phase1P {
   typedef Layout1P Layout;
   static constexpr bool kGenericSub = false;
+  static constexpr bool kBanded = true;
   LaneScratch scr;
   Scoring sc;
   const Layout1P *Lp;
+  BandW bw = {0, 0, 0, false};   // set per group by the kernel
   static EL_HD void make_layout(Layout1P &L, int LR, int LC) { make_layout1p(L, LR, LC); }
 
   EL_HD uint32_t *rec(int j) const { return scr.at(Lp->o_nodes + (uint32_t)(j + 1) * Lp->rec_words); }
+  // the band-restricted DP of a window is exact when it ends above the best score a path leaving the band can have
+  EL_HD bool band_exact(int score, int lx, int ly) const { return !bw.on || score > band_bound(sc, bw.w, ly - lx); }
 
   // one band of 2R rows of DP1 (lin(ref) columns x lin(cor) rows); returns the score of the last cell
   // when this is the band that holds row ly - 1
   template <int R>
-  EL_HDN int band(int lr, int ly, int b, bool last) const {
+  EL_HDN int band(int lr, int ly, int b, bool last, const BandW &bw) const {
     const int r0 = b * 2 * R;
     PackedConsts pc;
     pc.set(sc);
+    // columns this band sweeps: all of them, or those whose offsets to the band's rows lie in [bw.omin, bw.omax]
+    int jlo = 0, jend = lr;                                    // iterations jlo .. jend (the last one only completes the high half)
+    if (bw.on) {
+      jlo = r0 - bw.omax > 0 ? r0 - bw.omax : 0;
+      const int jhi = r0 + 2 * R - 1 - bw.omin;
+      jend = jhi + 1 < lr ? jhi + 1 : lr;
+      if (jlo > jend) jlo = jend;
+    }
     uint32_t y2[R], S[R], G[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -169,9 +182,10 @@ struct Phase1P {
       const int v = kBiasP + sc.virt_S(r0 + k);                // virtual column -1 (align_lpo_po2.c:290-302); high half: -inf
       S[k] = (uint32_t)v;
       G[k] = (uint32_t)(v - sc.ext);
+      if (jlo > 0) S[k] = G[k] = pk2(kNegP, kNegP);            // the column before the band's first one is outside the band
     }
     const int rr = ly - 1 - r0;                                // row of the last cell inside this band (when last)
-    uint32_t *p = rec(-1);
+    uint32_t *p = rec(jlo - 1);
     const uint32_t step = Lp->rec_words * 32;
     // boundary row r0 - 1 at nodes j-1 / j: S in the low half, G in the high half
     // (loads run TWO iterations ahead of their use: the scratch of a launch exceeds the L2 and the long-scoreboard stall
@@ -185,10 +199,11 @@ struct Phase1P {
       bsg_n = p[step + P1_BSG * 32];
       bsg_n2 = p[2 * step + P1_BSG * 32];
     }
-    uint32_t xw = 0, xw_next = scr.w(Lp->o_ref), x2 = 0, d7 = 0, mlo = 0;
+    uint32_t xw = 0, xw_next = scr.w(Lp->o_ref + (jlo >> 2)), x2 = 0, d7 = 0, mlo = 0;
+    if (jlo > 0) { x2 = (uint32_t)scr.code_at(Lp->o_ref, jlo - 1) << 4; d7 = (uint32_t)kNegP; }
     int best = 0;
-    for (int j = 0; j <= lr; ++j, p += step) {                 // p = record of node j - 1
-      if ((j & 3) == 0) { xw = xw_next; xw_next = scr.w(Lp->o_ref + (j >> 2) + 1); }   // the next four letters, one group ahead
+    for (int j = jlo; j <= jend; ++j, p += step) {             // p = record of node j - 1
+      if ((j & 3) == 0 || j == jlo) { xw = xw_next >> (8 * (j & 3)); xw_next = scr.w(Lp->o_ref + (j >> 2) + 1); }   // the next letters, one group ahead
       x2 = (x2 << 16) | ((xw & 0xffu) << 4);
       xw >>= 8;
       const uint32_t bsg_p = bsg;
@@ -206,14 +221,18 @@ struct Phase1P {
       if (last && j == lr - 1 && rr < R) best = pick_half<R>(S, rr, false);
     }
     if (last && rr >= R) best = pick_half<R>(S, rr - R, true);
+    if (bw.on && !last) {                                      // the next band reads boundary rows 2R + 3 nodes further: outside this band
+      const int stop = jend + 2 * R + 3 < lr + 2 ? jend + 2 * R + 3 : lr + 2;
+      for (int j = jend; j <= stop; ++j, p += step) p[P1_BSG * 32] = pk2(kNegP, kNegP);   // p = record of node j
+    }
     return best;
   }
 
   template <int R>
-  EL_HDN int dp(int lr, int ly) const {
+  EL_HDN int dp(int lr, int ly, const BandW &bw) const {
     const int nb = (ly + 2 * R - 1) / (2 * R);
-    for (int b = 0; b < nb - 1; ++b) band<R>(lr, ly, b, false);
-    return band<R>(lr, ly, nb - 1, true);
+    for (int b = 0; b < nb - 1; ++b) band<R>(lr, ly, b, false, bw);
+    return band<R>(lr, ly, nb - 1, true, bw);
   }
 
   // traceback (align_lpo_po2.c:108-168): fills the x2y field of every record
@@ -246,22 +265,25 @@ struct Phase1P {
   }
 
   template <int R>
-  EL_HDN int run_r(int lr, int lc, uint16_t *p1_out, int &s1, int &spcode) const {
-    s1 = dp<R>(lr, lc);
+  EL_HDN int run_r(int lr, int lc, uint16_t *p1_out, int &s1, int &spcode, bool &exact) const {
+    s1 = dp<R>(lr, lc, bw);
+    exact = band_exact(s1, lr, lc);
+    if (!exact) return 0;                                      // to be run again without a band
     traceback<R>(lr, lc);
     return fuse1(scr, Lp->o_ref, Lp->o_cor, rec(0) + P1_X2Y * 32, (ptrdiff_t)Lp->rec_words * 32, lr, lc, p1_out, spcode);
   }
 
-  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode) const {
+  // exact = false (band on only): nothing was written to p1_out, the window has to be run again without a band
+  EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode, bool &exact) const {
     scr.pack_codes(sc.tab, ref, lr, Lp->o_ref);
     scr.pack_codes(sc.tab, cor, lc, Lp->o_cor);
     // the last band reads up to 15 letters past the end of cor, the last iteration one past the end of ref:
     // defined values (which ones does not matter, they only feed cells outside the window)
     for (uint32_t k = 0; k < 5; ++k) scr.w(Lp->o_cor + cdiv_u((uint32_t)lc, 4) + k) = 0;
     scr.w(Lp->o_ref + cdiv_u((uint32_t)lr, 4)) = 0;
-    if (Lp->R == 6) return run_r<6>(lr, lc, p1_out, s1, spcode);   // R is uniform over the warp
-    if (Lp->R == 7) return run_r<7>(lr, lc, p1_out, s1, spcode);
-    return run_r<8>(lr, lc, p1_out, s1, spcode);
+    if (Lp->R == 6) return run_r<6>(lr, lc, p1_out, s1, spcode, exact);   // R is uniform over the warp
+    if (Lp->R == 7) return run_r<7>(lr, lc, p1_out, s1, spcode, exact);
+    return run_r<8>(lr, lc, p1_out, s1, spcode, exact);
   }
 };
 
@@ -374,6 +396,7 @@ struct Phase2P {
   typedef Layout2P Layout;
   static constexpr bool kGenericSub = false;
   static constexpr bool kLinear = false;
+  static constexpr bool kBanded = false;
   static constexpr int kSetWords = kSetWordsP;
   static constexpr uint32_t kRecNode = Q2_NODE, kRecX2Y = Q2_X2Y, kRecPred = Q2_PRED;
   static EL_HD void make_layout(Layout2P &L, int N1, int LU) { make_layout2p(L, N1, LU); }
@@ -547,12 +570,14 @@ struct Phase2L {
   typedef Layout2L Layout;
   static constexpr bool kGenericSub = false;
   static constexpr bool kLinear = true;
+  static constexpr bool kBanded = true;
   static constexpr int kSetWords = 1;
   static EL_HD void make_layout(Layout2L &L, int N1, int LU) { make_layout2l(L, N1, LU); }
   LaneScratch scr;
   uint32_t *bset;     // unused
   Scoring sc;
   const Layout2L *Lp;
+  BandW bw = {0, 0, 0, false};   // set per group by the kernel
 
   // rows of the MSA from the x -> y map of the traceback; returns nring
   EL_HDN int emit(const Phase1P &d, int n1, int lu) const {
@@ -589,22 +614,24 @@ struct Phase2L {
   }
 
   template <int R>
-  EL_HDN int run_r(const Phase1P &d, int n1, int lu, int &s2) const {
-    s2 = d.dp<R>(n1, lu);
+  EL_HDN int run_r(const Phase1P &d, int n1, int lu, int &s2, bool &exact) const {
+    s2 = d.dp<R>(n1, lu, d.bw);
+    exact = d.band_exact(s2, n1, lu);
+    if (!exact) return 0;
     d.traceback<R>(n1, lu);
     return emit(d, n1, lu);
   }
 
-  EL_HDN int run_linear(const uint8_t *ref, int n1, const uint8_t *unc, int lu, int &s2) const {
+  EL_HDN int run_linear(const uint8_t *ref, int n1, const uint8_t *unc, int lu, int &s2, bool &exact) const {
     Phase1P d;
-    d.scr = scr; d.sc = sc; d.Lp = &Lp->dp;
+    d.scr = scr; d.sc = sc; d.Lp = &Lp->dp; d.bw = bw;
     scr.pack_codes(sc.tab, ref, n1, Lp->dp.o_ref);
     scr.pack_codes(sc.tab, unc, lu, Lp->dp.o_cor);
     for (uint32_t k = 0; k < 5; ++k) scr.w(Lp->dp.o_cor + cdiv_u((uint32_t)lu, 4) + k) = 0;
     scr.w(Lp->dp.o_ref + cdiv_u((uint32_t)n1, 4)) = 0;
-    if (Lp->dp.R == 6) return run_r<6>(d, n1, lu, s2);   // R is uniform over the warp
-    if (Lp->dp.R == 7) return run_r<7>(d, n1, lu, s2);
-    return run_r<8>(d, n1, lu, s2);
+    if (Lp->dp.R == 6) return run_r<6>(d, n1, lu, s2, exact);   // R is uniform over the warp
+    if (Lp->dp.R == 7) return run_r<7>(d, n1, lu, s2, exact);
+    return run_r<8>(d, n1, lu, s2, exact);
   }
 };
 

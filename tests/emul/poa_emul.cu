@@ -22,7 +22,8 @@ using namespace elector;
 
 template <bool GS>
 static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U, FILE *pir, FILE *scores, bool packed, bool general_only, bool coop, bool dual) {
-  long n_packed1 = 0, n_packed2 = 0, n_linear2 = 0, n_ident1 = 0;
+  long n_packed1 = 0, n_packed2 = 0, n_linear2 = 0, n_ident1 = 0, n_band_retry = 0;
+  const int band_w = packed ? (getenv("ELECTOR_BAND_W") ? atoi(getenv("ELECTOR_BAND_W")) : 10) : 0;   // diagonal band of the packed linear kernels
   const size_t n = std::min(R.rec.size(), std::min(C.rec.size(), U.rec.size()));
   for (size_t w = 0; w < n; ++w) {
     const int lr = R.rec[w].len, lc = C.rec[w].len, lu = U.rec[w].len;
@@ -63,7 +64,17 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       p1.scr.base = scratch1.data() + lane;
       p1.sc = s;
       p1.Lp = &L1;
-      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode);
+      bool exact = true;
+      if (band_w > 0 && cap_r + cap_c <= kBandMaxSpan) {   // diagonal band with the exactness test; run again without it when the test fails
+        const int d = lc - lr;
+        p1.bw = BandW{(d < 0 ? d : 0) - band_w - (int)(w % 3), (d > 0 ? d : 0) + band_w + (int)(w % 2), band_w, true};   // a superset, as in a warp
+      }
+      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode, exact);
+      if (!exact) {
+        ++n_band_retry;
+        p1.bw.on = false;
+        n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode, exact);
+      }
       ++n_packed1;
     } else {
       Layout1 L1;
@@ -73,7 +84,8 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       p1.scr.base = scratch1.data() + lane;
       p1.sc = s;
       p1.Lp = &L1;
-      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode);
+      bool exact;
+      n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode, exact);
     }
     int bin, seg;
     bin2_of(n1, lu, spcode, bin, seg);
@@ -111,7 +123,17 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       p2.bset = nullptr;
       p2.sc = s;
       p2.Lp = &L2;
-      nring = p2.run_linear((const uint8_t *)R.seq.data() + R.rec[w].off, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2);
+      bool exact = true;
+      if (band_w > 0 && cap_n + cap_u <= kBandMaxSpan) {
+        const int d = lu - n1;
+        p2.bw = BandW{(d < 0 ? d : 0) - band_w - (int)(w % 2), (d > 0 ? d : 0) + band_w + (int)(w % 3), band_w, true};
+      }
+      nring = p2.run_linear((const uint8_t *)R.seq.data() + R.rec[w].off, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2, exact);
+      if (!exact) {
+        ++n_band_retry;
+        p2.bw.on = false;
+        nring = p2.run_linear((const uint8_t *)R.seq.data() + R.rec[w].off, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2, exact);
+      }
       row_words = L2.row_words;
       for (uint32_t k = 0; k < 3 * row_words; ++k) rows.push_back(p2.scr.w(L2.o_rows + k));
       ++n_linear2;
@@ -164,7 +186,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     }
     if (scores) fprintf(scores, "%d %d %d %d\n", s1, s2, n1, nring);
   }
-  if (packed) fprintf(stderr, "packed: %ld (phase 1) + %ld (phase 1, cor is ref), %ld (phase 2 general) and %ld (phase 2 linear) of %zu windows\n", n_packed1, n_ident1, n_packed2, n_linear2, n);
+  if (packed) fprintf(stderr, "packed: %ld (phase 1) + %ld (phase 1, cor is ref), %ld (phase 2 general) and %ld (phase 2 linear) of %zu windows; band half-width %d, %ld DPs run again without the band\n", n_packed1, n_ident1, n_packed2, n_linear2, n, band_w, n_band_retry);
   return 0;
 }
 

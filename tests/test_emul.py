@@ -28,6 +28,22 @@ def test_emulated_kernel_equals_reference(golden_dir, emul_bin, name, mode, tmp_
         assert (g["s1"], g["s2"], g["n1"]) == e[:3]
 
 
+@pytest.mark.parametrize("band_w", ["1", "3", "6", "16"])
+@pytest.mark.parametrize("name", ["hard", "example_tail"])
+def test_emulated_band_dp_is_exact(golden_dir, emul_bin, name, band_w, tmp_path, monkeypatch):
+    """the diagonal-band DP of the packed linear kernels with its exactness test (poa_packed.cuh): whatever the half-width,
+    a window either passes the test and equals the reference, or is run again without the band"""
+    monkeypatch.setenv("ELECTOR_BAND_W", band_w)
+    d = golden_dir
+    pir, sc = str(tmp_path / "e.pir"), str(tmp_path / "e.scores")
+    cmd = [emul_bin, d + "/blosum80.mat", "%s/%s.ref.fa" % (d, name), "%s/%s.cor.fa" % (d, name), "%s/%s.unc.fa" % (d, name), pir, sc, "packed"]
+    assert subprocess.call(cmd) == 0
+    assert open(pir, "rb").read() == open("%s/%s.pir" % (d, name), "rb").read()
+    gold = parse_dump("%s/%s.dump" % (d, name))
+    got = [tuple(int(v) for v in line.split()) for line in open(sc)]
+    assert [(g["s1"], g["s2"], g["n1"]) for g in gold] == [e[:3] for e in got]
+
+
 def test_emulated_kernel_generic_matrix(golden_dir, emul_bin, tmp_path):
     """non-uniform substitution scores + other gap penalties: table path vs the oracle"""
     from elector_b200.matrix import ALPHABET
