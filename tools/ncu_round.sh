@@ -18,6 +18,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:poa_dp -c 14 -o $O/${TAG}_full -f $(cmd 2000) > /dev/null; echo full rc=$?
 timeout 900 ncu --set full --clock-control none -k regex:poa_dp2 -c 9 -o $O/${TAG}_dp2_10k -f $(cmd 10000) > /dev/null; echo dp2-10k rc=$?
 python tools/ncu_traffic.py $O/${TAG}_dp2_10k.ncu-rep $O/${TAG}_traffic.json
+# summaries are made here; the reports themselves (30 MB each) stay on the box unless KEEP_REPS=1 (gpurun_out/ is capped at 64 MiB)
+python tools/ncu_summary.py $O/${TAG}_full.ncu-rep > $O/${TAG}_ncu_full_summary_2k_reads.csv
+python tools/ncu_summary.py $O/${TAG}_dp2_10k.ncu-rep > $O/${TAG}_ncu_full_summary_dp2_10k_reads.csv
+python tools/ncu_stalls.py $O/${TAG}_dp2_10k.ncu-rep > $O/${TAG}_ncu_stalls_dp2_10k_reads.txt
+[ "$KEEP_REPS" = 1 ] || rm -f $O/${TAG}_full.ncu-rep $O/${TAG}_dp2_10k.ncu-rep
 # the whole pipelined call (POA + merge + tally) in one chunk on one worker, through the C driver of elector_pipeline_run
 python tools/dump_csr.py 10000 1 /tmp/c1 > /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
