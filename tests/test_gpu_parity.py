@@ -124,6 +124,31 @@ def test_long_windows_warp_cooperative_vs_oracle(group, monkeypatch):
         assert res.window_rows(w) == oracle.window_rows(o, w), w
 
 
+@pytest.mark.parametrize("band_w", ["0", "1", "3", "12"])
+def test_band_dp_is_exact_whatever_the_width(band_w, monkeypatch):
+    """the diagonal band of the packed linear kernels: windows that fail the exactness test are run again
+    without the band by the same launch (per-warp retry queue); results equal the oracle at any half-width, 0 = band off"""
+    import elector_b200
+    from elector_b200 import windows_to_csr
+    from oracle import oracle, synth
+    wins = synth.hard_windows(6000, seed=77)
+    rng = synth.SplitMix64(78)
+    for i in range(3000):                      # plus windows of the bulk's shape: cor == ref or nearly, unc at 10-20 %
+        L = 20 + rng.below(110)
+        ref = "".join("ACGT"[rng.below(4)] for _ in range(L))
+        cor = ref if i % 2 else (synth.mutate(rng, ref, 0.02, "ACGT") or "A")
+        wins.append(("b%d" % i, ref, cor, synth.mutate(rng, ref, [0.1, 0.2, 0.4][i % 3], "ACGT") or "A"))
+    r, ro = windows_to_csr([w[1] for w in wins]); c, co = windows_to_csr([w[2] for w in wins]); u, uo = windows_to_csr([w[3] for w in wins])
+    monkeypatch.setenv("ELECTOR_BAND_W", band_w)
+    with elector_b200.PoaContext(0) as c2:
+        res = c2.run_csr(r, ro, c, co, u, uo)
+    o = oracle.batch(r, ro, c, co, u, uo, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(res.nring, o["nring"])
+    assert np.array_equal(res.score1, o["score1"]) and np.array_equal(res.score2, o["score2"])
+    for w in range(len(wins)):
+        assert res.window_rows(w) == oracle.window_rows(o, w), w
+
+
 def test_generic_matrix_vs_oracle(golden_dir, tmp_path):
     """non-uniform substitution scores and other gap penalties (table path of the kernel)"""
     import elector_b200
