@@ -180,7 +180,11 @@ def main():
     from elector_b200 import TALLY_FIELDS
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / log off stdout: rank 0 prints ONE JSON line there
+        # rank 0 prints ONE JSON line on stdout: NCCL's log goes to stderr, and its version banner (a printf to stdout at
+        # the VERSION and WARN levels) is switched off unless the caller asked for INFO or more
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
