@@ -174,6 +174,18 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    # one rank per GPU: keep the rank's threads (and the pinned buffers they first touch) on the CPUs next to its GPU;
+    # with 8 ranks the host side of the pipelined call is otherwise bound by cross-socket traffic
+    full_affinity = os.sched_getaffinity(0)
+    numa_cpus = None
+    if world > 1 and not os.environ.get("ELECTOR_NO_AFFINITY"):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa_cpus = len(os.sched_getaffinity(0))
+        except Exception:
+            numa_cpus = None
     import ctypes
     import torch
     import elector_b200
@@ -396,6 +408,9 @@ def main():
                          "note": "algorithmic bytes = letters + offsets in, MSA rows + per-window results out; the path is integer-issue bound, not HBM bound"},
         "counters": {f: int(v) for f, v in zip(TALLY_FIELDS, sums_dev) if f in ("TP", "FP", "FN", "insU", "delU", "subsU", "insC", "delC", "subsC", "assessed")},
     }
+    os.sched_setaffinity(0, full_affinity)   # the CPU baseline below uses every host core
+    if numa_cpus:
+        line["config"]["host_affinity"] = "rank threads bound to the %d CPUs next to their GPU (NVML)" % numa_cpus
     if rank == 0 and not args.no_cpu_baseline:
         kind = "reference" if have_ref else "port"
         k = args.cpu_triplets or int(min(n_trip, max(8, ncores * 26 * 10)))
