@@ -140,8 +140,9 @@ int elector_merge_tally_device(elector_ctx *ctx, int64_t n_reads, const int64_t 
  * computeStats.py for the windows of n_reads reads -- Pool(fpoa) (main.c:265-284 per window),
  * Donatello (Donatello.cpp:50-84) and the per-read tally (computeStats.py:371-498) -- as ONE
  * call on host buffers.  Windows read_first[r] .. read_first[r+1]-1 belong to read r.  The work
- * is cut into chunks of whole reads; the host->device copies of all chunks are queued up
- * front and a chunk's results return while the next chunk computes.  Outputs as in
+ * is cut into chunks of whole reads, each processed by one of a few worker contexts the library
+ * creates (own host thread and streams): a chunk's inputs arrive and its results leave while
+ * other chunks compute (pin the host buffers for that).  Not reentrant per context.  Outputs as in
  * elector_poa_run plus counters_out[r*ELECTOR_TALLY_K + k] and sums_out[k] = sum over reads
  * (k = ELECTOR_T_EXTENDED sums the extended bases of extended reads only).  With n_reads == 0
  * (read_first, counters_out, sums_out NULL) only the alignment runs. */
