@@ -25,7 +25,12 @@ constexpr int kMaxSegs = kNumSegs2 > kNumSegs1 ? kNumSegs2 : kNumSegs1;
 constexpr int kMaxBins = kNumBins2 > kNumBins1 ? kNumBins2 : kNumBins1;
 constexpr int kScanChunk = 1024;
 constexpr int kMaxChunks = (kMaxBins + kScanChunk - 1) / kScanChunk;
-constexpr int kMaxWindowLen = 32000;              // node records hold predecessors in 16 bits, ordinal slots in 15
+// Longest window the kernels take.  The reference has no cap of its own (fasta_format.c:20 reads any line in 32 KiB chunks,
+// seq_util.h:22) but allocates len_y * len_x two-byte moves per DP (align_lpo_po2.c:258-266): 8.6 GB at these lengths.  Here
+// the node records hold predecessor indices in 16 bits (0xffff = none) and ordinal slots in 15, so len(P1) <= len(ref) +
+// len(cor) must stay below 65 535; the uncorrected sequence is bounded the same way (and by the scratch of the call).
+constexpr int kMaxWindowLen = 65534;              // each sequence of a window
+constexpr int kMaxNodes = 65534;                  // len(ref) + len(cor) >= len(P1)
 
 struct SegInfo {      // one launch of a POA kernel
   int32_t first_bin;  // in: first bin of the segment (bins of a segment are contiguous)
@@ -38,7 +43,7 @@ struct BinTable {
   SegInfo seg[kMaxSegs + 1];   // [nseg].first_bin = number of bins
   int32_t seg_max[kMaxSegs * 4];  // per segment maxima: phase 1 {lr, lc}, phase 2 {n1, lu}
   int32_t nseg, nbins;
-  int32_t err_code;    // 0 ok, 1 empty sequence, 2 sequence longer than kMaxWindowLen
+  int32_t err_code;    // 0 ok, 1 empty sequence, 2 sequence longer than kMaxWindowLen or len(ref) + len(cor) > kMaxNodes
   int32_t err_window;  // smallest offending window id
   unsigned long long lin_bytes;  // phase-2 table: row bytes (3 x columns bound, rounded to 4) of the windows in the linear segments
 };
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_
     const int64_t lr = ro[w + 1] - ro[w], lc = co[w + 1] - co[w], lu = uo[w + 1] - uo[w];
     int bin = -1;
     if (lr <= 0 || lc <= 0 || lu <= 0) { atomicMax(&tab->err_code, 1); atomicMin(&tab->err_window, w); }
-    else if (lr > kMaxWindowLen || lc > kMaxWindowLen || lu > kMaxWindowLen) { atomicMax(&tab->err_code, 2); atomicMin(&tab->err_window, w); }
+    else if (lr > kMaxWindowLen || lc > kMaxWindowLen || lu > kMaxWindowLen || lr + lc > kMaxNodes) { atomicMax(&tab->err_code, 2); atomicMin(&tab->err_window, w); }
     else {
       bool ident = false;
       if (use_ident && lr == lc && lr <= kSmallMax && lu <= kSmallMax) {

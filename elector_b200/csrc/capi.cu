@@ -355,7 +355,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   CU(cudaMemcpyAsync(&ctx->h_totals[3], d_coff, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (htab1->err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", htab1->err_window);
-  if (htab1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d longer than %d letters", htab1->err_window, kMaxWindowLen);
+  if (htab1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d: a sequence longer than %d letters, or reference + corrected longer than %d (16-bit node indices)", htab1->err_window, kMaxWindowLen, kMaxNodes);
   CU(ctx->d_p1.reserve((size_t)(ctx->h_totals[0] - ctx->h_totals[2] + ctx->h_totals[1] - ctx->h_totals[3] + 8 * n + 8) * sizeof(uint16_t)));
 
   PoaArgs a;
@@ -370,6 +370,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
   a.error_flag = d_errflag;
   a.band_w = ctx->band_w;
+  a.band_span = band_span_limit(ctx->sc.maxabs);
 
   // ---- phase 1 ----
   std::vector<SegPlan> plan;
@@ -815,9 +816,13 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   const bool loose = rows_cap >= elector_poa_rows_bound(n, ro, co, uo);
   if (loose) {
     // region k = [lo16(bound of the windows before it), lo16(bound of the windows up to its end)): the regions tile the O(1)
-    // bound of the call whatever the chunking; a window needs at least 6 bytes less than its share, which covers the rounding
+    // bound of the call whatever the chunking.  A window's share of the bound is 3 * (letters + 3) bytes and it needs at most
+    // 3 * ((columns + 3) & ~3) with columns <= letters - 1 (every DP aligns something or, at worst, ('AAAAA','C','G')-like
+    // inputs give letters - 1 columns): at least 3 spare bytes per window.  Two regions per chunk lose up to 30 bytes to the
+    // two 16-byte roundings, so a chunk is only split when it has 64 windows or more (192 spare bytes); the kernels check
+    // rows_cap anyway, so the failure mode of a wrong margin is ELECTOR_ECAPACITY, never a stray write.
     auto before = [&](int64_t w) { return (3 * (ro[w] + co[w] + uo[w] + 3 * w)) & ~(int64_t)15; };
-    for (ChunkJob &j : jobs) { j.rows_base = before(j.w0); j.rows_len = before(j.w1) - j.rows_base; j.split = j.w1 - j.w0 >= 16; }
+    for (ChunkJob &j : jobs) { j.rows_base = before(j.w0); j.rows_len = before(j.w1) - j.rows_base; j.split = j.w1 - j.w0 >= 64; }
   } else {
     int64_t base = 0;
     for (ChunkJob &j : jobs) {

@@ -129,6 +129,7 @@ struct PoaArgs {
   int64_t *cells;
   int32_t *error_flag;
   int32_t band_w;        // half-width of the diagonal band of the packed linear kernels (0 = full DP), see BandW
+  int32_t band_span;     // band only for groups with len_x + len_y <= this (band_span_limit(maxabs))
 };
 
 // symbol tables: byte -> matrix index (lower-casing + limit_residues + index_symbols),
@@ -222,7 +223,9 @@ struct Scoring {
 // DP (a predecessor that ties or wins there is on an optimal path itself): score, moves along the path and MSA are the
 // full DP's.  Otherwise the window is run again without a band.  Cells outside the band are "minus infinity" = kNegP, a
 // value every real score of a small window beats and that cannot leave the 16-bit range by the end of the DP.
-constexpr int kBandMaxSpan = 500;           // banding only for groups with len_x + len_y <= this: real scores stay above kNegP
+constexpr int kBandMaxSpan = 500;           // banding only for groups with len_x + len_y <= this ...
+constexpr int kBandMaxScore = 7000;         // ... and maxabs * (len_x + len_y + 4) <= this: real scores stay above kNegP (-8000), whatever the matrix
+EL_HD int band_span_limit(int maxabs) { const int s = kBandMaxScore / (maxabs > 0 ? maxabs : 1) - 4; return s < kBandMaxSpan ? s : kBandMaxSpan; }
 struct BandW {
   int omin, omax;   // offsets swept (uniform over the warp: a superset of every lane's own band)
   int w;            // half-width the exactness test assumes
@@ -854,7 +857,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
       if (lane == 0) PH::make_layout(s_layout, mr, mc);
       __syncwarp();
       // half-width: the base plus 1/16 of the rows (cor differs from ref by ~1 %: scores stay near 0)
-      if constexpr (PH::kBanded) group_band(c.bw, banded && mr + mc <= kBandMaxSpan, a.band_w + (mc >> 4), active, lc - lr);
+      if constexpr (PH::kBanded) group_band(c.bw, banded && mr + mc <= a.band_span, a.band_w + (mc >> 4), active, lc - lr);
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
     int s1 = 0, spcode = 0, n1 = 0;
@@ -948,7 +951,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
       if (lane == 0) PH::make_layout(s_layout, mn, mu);
       __syncwarp();
       // half-width: the base plus 1/8 of the rows (unc differs from ref by ~10 %: the score is about minus the length)
-      if constexpr (PH::kBanded) group_band(c.bw, banded && mn + mu <= kBandMaxSpan, a.band_w + (mu >> 3), active, lu - n1);
+      if constexpr (PH::kBanded) group_band(c.bw, banded && mn + mu <= a.band_span, a.band_w + (mu >> 3), active, lu - n1);
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
     bool exact = true;

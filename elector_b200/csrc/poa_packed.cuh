@@ -158,7 +158,12 @@ struct Phase1P {
 
   EL_HD uint32_t *rec(int j) const { return scr.at(Lp->o_nodes + (uint32_t)(j + 1) * Lp->rec_words); }
   // the band-restricted DP of a window is exact when it ends above the best score a path leaving the band can have
-  EL_HD bool band_exact(int score, int lx, int ly) const { return !bw.on || score > band_bound(sc, bw.w, ly - lx); }
+  // (the bound itself must lie above the band's minus infinity: out-of-band cells then never beat an in-band path that passes the test)
+  EL_HD bool band_exact(int score, int lx, int ly) const {
+    if (!bw.on) return true;
+    const int bound = band_bound(sc, bw.w, ly - lx);
+    return score > bound && bound > kNegP - kBiasP;
+  }
 
   // one band of 2R rows of DP1 (lin(ref) columns x lin(cor) rows); returns the score of the last cell
   // when this is the band that holds row ly - 1

@@ -51,24 +51,9 @@ def read_fa(path):
 
 
 def prep_example(work):
-    """Biopython-free emulation of elector/readAndSortFiles.py for the example
-    (formatHeader :212 sed, readAndSortFasta :150-166 sort by description,
-    duplicateRefReads :171-191)."""
-    ref = read_fa(os.path.join(EXAMPLE, "perfect_reads_elector.fa"))
-    unc = read_fa(os.path.join(EXAMPLE, "uncorrected_reads_elector.fa"))
-    cor = [(re.sub(r"_[0-9]*$", "", h), s) for h, s in read_fa(os.path.join(EXAMPLE, "corrected_reads_elector.fa"))]
-    ref.sort(key=lambda x: x[0]); unc.sort(key=lambda x: x[0]); cor.sort(key=lambda x: x[0])
-    occ = {}
-    for h, _ in cor:
-        occ[h] = occ.get(h, 0) + 1
-    with open(os.path.join(work, "cor.fa"), "w") as f:
-        for h, s in cor:
-            f.write(">%s\n%s\n" % (h, s))
-    with open(os.path.join(work, "ref.fa"), "w") as fr, open(os.path.join(work, "unc.fa"), "w") as fu:
-        for (hr, sr), (_, su) in zip(ref, unc):
-            for t in range(occ.get(hr, 0)):
-                fr.write(">%s_%d\n%s\n" % (hr, t, sr))
-                fu.write(">%s_%d\n%s\n" % (hr, t, su))
+    """Biopython-free emulation of elector/readAndSortFiles.py for the example (oracle/example_prep.py)."""
+    from oracle import example_prep
+    example_prep.sort_and_duplicate(EXAMPLE, work)
 
 
 def run_poa(prefix_in, out_pir):

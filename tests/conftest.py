@@ -61,7 +61,8 @@ def emul_bin():
     """CPU build of the per-window device code (tests/emul/poa_emul.cu)."""
     src = os.path.join(ROOT, "tests", "emul", "poa_emul.cu")
     exe = os.path.join(ROOT, "tests", "emul", "poa_emul")
-    deps = [src] + [os.path.join(ROOT, "elector_b200", "csrc", f) for f in ("poa_kernel.cuh", "poa_packed.cuh", "bin_kernel.cuh", "host_setup.hpp", "host_io.hpp")]
+    csrc = os.path.join(ROOT, "elector_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(p) for p in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-arch=sm_100a", "-Wno-deprecated-gpu-targets", "-o", exe, src])
     return exe
@@ -110,3 +111,31 @@ def parse_pir(path):
         lines.pop()
     assert len(lines) % 6 == 0
     return [((lines[i], lines[i + 2], lines[i + 4]), (lines[i + 1], lines[i + 3], lines[i + 5])) for i in range(0, len(lines), 6)]
+
+
+def load_example_golden():
+    import json
+    return json.loads(gzip.open(os.path.join(GOLD, "example_full.json.gz")).read())
+
+
+@pytest.fixture(scope="session")
+def example_chain(tmp_path_factory):
+    """The README example up to the `poa` inputs: reads unpacked from tests/golden/example_reads.tar.xz, sorted and
+    duplicated like readAndSortFiles.py, cut into shard files by the compiled reference splitter (oracle/_ref travels
+    to the GPU box).  -> dict(work, out, shards, gold)"""
+    from oracle import example_prep as ep
+    if not os.path.exists(os.path.join(ep.REF, "masterSplitter")):
+        pytest.skip("oracle/_ref/masterSplitter not built (oracle/build_ref.sh needs /root/reference)")
+    src = str(tmp_path_factory.mktemp("example_src"))
+    work = str(tmp_path_factory.mktemp("example_work"))
+    ep.unpack(src)
+    ep.sort_and_duplicate(src, work)
+    out = os.path.join(work, "out")
+    rc, shards = ep.reference_split(work, out)
+    assert rc == 0
+    return {"src": src, "work": work, "out": out, "shards": shards, "gold": load_example_golden()}
+
+
+def md5_file(path):
+    import hashlib
+    return hashlib.md5(open(path, "rb").read()).hexdigest()

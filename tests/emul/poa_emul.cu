@@ -65,9 +65,9 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       p1.sc = s;
       p1.Lp = &L1;
       bool exact = true;
-      if (band_w > 0 && cap_r + cap_c <= kBandMaxSpan) {   // diagonal band with the exactness test; run again without it when the test fails
+      if (band_w > 0 && cap_r + cap_c <= band_span_limit(sc.maxabs)) {   // diagonal band with the exactness test; run again without it when the test fails
         const int d = lc - lr;
-        p1.bw = BandW{(d < 0 ? d : 0) - band_w - (int)(w % 3), (d > 0 ? d : 0) + band_w + (int)(w % 2), band_w, true};   // a superset, as in a warp
+        p1.bw = BandW{(d < 0 ? d : 0) - band_w - (int)((w * 7) % 13), (d > 0 ? d : 0) + band_w + (int)((w * 5) % 11), band_w, true};   // the union band of a warp: a superset of the window's own by what other lanes add
       }
       n1 = p1.run_window((const uint8_t *)R.seq.data() + R.rec[w].off, lr, (const uint8_t *)C.seq.data() + C.rec[w].off, lc, nodes_p, s1, spcode, exact);
       if (!exact) {
@@ -124,9 +124,9 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       p2.sc = s;
       p2.Lp = &L2;
       bool exact = true;
-      if (band_w > 0 && cap_n + cap_u <= kBandMaxSpan) {
+      if (band_w > 0 && cap_n + cap_u <= band_span_limit(sc.maxabs)) {
         const int d = lu - n1;
-        p2.bw = BandW{(d < 0 ? d : 0) - band_w - (int)(w % 2), (d > 0 ? d : 0) + band_w + (int)(w % 3), band_w, true};
+        p2.bw = BandW{(d < 0 ? d : 0) - band_w - (int)((w * 3) % 7), (d > 0 ? d : 0) + band_w + (int)((w * 5) % 9), band_w, true};   // union band of a warp
       }
       nring = p2.run_linear((const uint8_t *)R.seq.data() + R.rec[w].off, n1, (const uint8_t *)U.seq.data() + U.rec[w].off, lu, s2, exact);
       if (!exact) {

@@ -221,3 +221,27 @@ def test_full_size_properties():
     assert np.array_equal(res.score1[:k], o["score1"]) and np.array_equal(res.score2[:k], o["score2"])
     for w in range(k):
         assert res.window_rows(w) == oracle.window_rows(o, w)
+
+
+def test_long_windows_equal_reference(ctx, golden_dir, tmp_path):
+    """golden set `long` (reference-generated, oracle/make_golden_long.py): the 3 300-letter window runs the INT32 tier
+    (scores beyond 16 bits), the 33 500-letter one is longer than a 32 KiB FASTA line buffer and than the former
+    32 000-letter cap; PIR bytes, both DP scores and len(P1) equal the reference's"""
+    d = golden_dir
+    out = str(tmp_path / "o.pir")
+    ctx.files(d + "/long.ref.fa", d + "/long.cor.fa", d + "/long.unc.fa", out)
+    assert open(out, "rb").read() == open(d + "/long.pir", "rb").read()
+    recs = [[s for _, s in read_fasta_simple("%s/long.%s.fa" % (d, k))] for k in ("ref", "cor", "unc")]
+    gold = parse_dump(d + "/long.dump")
+    res = ctx.run(recs[0], recs[1], recs[2])
+    for w, g in enumerate(gold):
+        assert (int(res.score1[w]), int(res.score2[w])) == (g["s1"], g["s2"]), w
+        assert int(res.cells[w]) == len(recs[0][w]) * len(recs[1][w]) + g["n1"] * len(recs[2][w])
+
+
+def test_window_beyond_the_cap_is_refused_not_approximated(ctx):
+    """len(ref) + len(cor) > 65 534 (16-bit node indices): ELECTOR_ETOOLARGE with the reason, never a wrong answer"""
+    import elector_b200
+    with pytest.raises(elector_b200.ElectorError) as e:
+        ctx.run(["A" * 40000], ["A" * 30000], ["ACGT"])
+    assert e.value.code == -6 and "65534" in str(e.value)

@@ -167,3 +167,29 @@ def test_pipeline_call_equals_oracle_chain(chunks, workers, monkeypatch):
     o = oracle.batch(sub["ref"], sub["ref_off"], sub["cor"], sub["cor_off"], sub["unc"], sub["unc_off"], nthreads=1)
     for w in range(w0, w1):
         assert res.window_rows(w) == oracle.window_rows(o, w - w0)
+
+
+@pytest.mark.parametrize("cfg,reads", [(1, 60), (3, 10), (4, 240)])
+def test_config_slices_pipeline_equals_oracle_chain(cfg, reads):
+    """slices of BASELINE.json configs 1, 3 (50-100 kb reads: ~1 400 windows per read) and 4 (1-30 kb reads, log-uniform)
+    through elector_pipeline_run: every window's rows and scores and every read's counters equal the oracle chain"""
+    import elector_b200
+    import workloads
+    from elector_b200 import TALLY_FIELDS
+    from oracle import oracle, tally_oracle as to
+    wl = workloads.make_windows(cfg, reads)
+    with elector_b200.PoaContext(0) as c:
+        res, counters, sums = c.pipeline_csr(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"], wl["read_first"])
+    o = oracle.batch(wl["ref"], wl["ref_off"], wl["cor"], wl["cor_off"], wl["unc"], wl["unc_off"], nthreads=os.cpu_count() or 1)
+    assert np.array_equal(res.nring, o["nring"]) and np.array_equal(res.score1, o["score1"]) and np.array_equal(res.score2, o["score2"])
+    assert np.array_equal(res.cells, o["cells"])
+    rf = wl["read_first"]
+    for r in range(len(rf) - 1):
+        rows = [oracle.window_rows(o, w) for w in range(rf[r], rf[r + 1])]
+        for w in range(rf[r], rf[r + 1]):
+            assert res.window_rows(w) == rows[w - rf[r]], (cfg, w)
+        R = "".join(x[0] for x in rows); C = "".join(x[1] for x in rows); U = "".join(x[2] for x in rows)
+        keep = [i for i, ch in enumerate(C) if ch != "n"]
+        R, C, U = ("".join(s[i] for i in keep) for s in (R, C, U))
+        exp = to.tally_read(R, C, U)
+        assert [int(v) for v in counters[r]] == [exp[f] for f in TALLY_FIELDS], (cfg, r)

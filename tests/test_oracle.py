@@ -69,3 +69,14 @@ def test_live_reference_agrees_with_golden_and_generated_matrix(golden_dir, tmp_
                           "-pathMatrix", d + "/blosum80.mat"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert rc == 0
     assert hashlib.md5(open(out, "rb").read()).hexdigest() == hashlib.md5(open(d + "/hard.pir", "rb").read()).hexdigest()
+
+
+def test_oracle_long_windows_equal_reference(golden_dir, tmp_path):
+    """golden set `long` (oracle/make_golden_long.py): a 3 300-letter window, a 33 500-letter window on one FASTA line
+    longer than the reference's 32 KiB line buffer (fasta_format.c:20), wrapped lines with blanks, a window after them"""
+    from conftest import parse_dump
+    from oracle import oracle
+    d = golden_dir
+    out, dump = str(tmp_path / "o.pir"), str(tmp_path / "o.dump")
+    assert oracle.poa_files(d + "/blosum80.mat", d + "/long.ref.fa", d + "/long.cor.fa", d + "/long.unc.fa", out) == 0
+    assert open(out, "rb").read() == open(d + "/long.pir", "rb").read()
