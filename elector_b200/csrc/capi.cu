@@ -57,7 +57,8 @@ struct elector_ctx {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0, resident_ph2p = 0, resident_ph2l = 0, resident_coop = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int resident_ph1 = 0, resident_ph2 = 0, resident_ph1p = 0, resident_ph2l = 0, resident_coop = 0;  // POA kernel CTAs (one warp each) resident per SM
+  int arena_ph1 = 0, arena_ph2 = 0, arena_ph1p = 0, arena_ph2l = 0, arena_ph2d = 0;   // bytes of the per-warp shared-memory arena of each kernel (fast part of the layouts)
   int coop_group = kCoopGroupDefault;  // windows per warp of the warp-cooperative kernel; 0 = the longest windows stay thread-per-window (ELECTOR_COOP_GROUP)
   int64_t *h_totals = nullptr;             // pinned: letters of ref / cor of the current call
   cudaStream_t stream = nullptr;
@@ -70,7 +71,6 @@ struct elector_ctx {
   std::vector<cudaEvent_t> chunk_ev;                    // 2 per chunk: inputs resident, results ready
   ScoreMatrix mat;
   ScoringSetup sc;
-  bool packed2 = false;     // ELECTOR_PACKED2=1: general windows of phase 2 on the packed kernel (A/B measurements)
   bool no_linear2 = false;  // ELECTOR_NO_LINEAR2=1: linear windows of phase 2 on the general kernels
   DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_key2, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
@@ -91,7 +91,6 @@ struct elector_ctx {
   int band_w = 6;          // ELECTOR_BAND_W: base half-width of the diagonal band of the packed linear kernels (+ rows/16 in phase 1, + rows/8 in phase 2; 0 = full DP)
   bool no_dual = false;    // ELECTOR_NO_DUAL=1: general windows of phase 2 on the INT32 kernel with frontier sets
   int resident_ph2d = 0;
-  bool ph2d_alt = false;   // ELECTOR_PH2D_WARPS=20: the 96-register build of the dual-frontier kernel
   bool no_ident = false;   // ELECTOR_NO_IDENT=1: windows whose cor is ref run DP1 like every other window
   // rows of a pipelined chunk in two regions: the windows of the linear segments of phase 2 (most windows, finished early)
   // write theirs behind their own cursor, so that they can leave for the host while the general windows still compute
@@ -140,9 +139,6 @@ const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share 
 #ifndef EL_MIN_WARPS_PH1P
 #define EL_MIN_WARPS_PH1P 28  // packed DP1: register cap 72 (64 spills since the diagonal band: 28 warps measured 0.2 ms per step faster than 32)
 #endif
-#ifndef EL_MIN_WARPS_PH2P
-#define EL_MIN_WARPS_PH2P 24  // packed DP2: register cap 80
-#endif
 #ifndef EL_MIN_WARPS_PH2D
 #define EL_MIN_WARPS_PH2D 20  // dual-frontier packed DP2: register cap 96 (measured: 9.94 ms per config-1 step against 10.26 ms at 24 warps / 80 registers)
 #endif
@@ -156,31 +152,56 @@ const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share 
 enum SegKind { kInt32 = 0, kPacked = 1, kLinear = 2, kCoop = 3, kDual = 4 };
 
 template <bool GS>
-cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab, int coop_group, bool linear_seg) {
-  if (kind == kCoop && phase == 1) poa_dp1_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group);
-  else if (kind == kCoop) poa_dp2_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group, linear_seg);
+cudaError_t launch_phase(int phase, int kind, cudaStream_t st, PoaArgs &a, int grid, const SymbolTables *tab, int coop_group, bool linear_seg,
+                         const elector_ctx *ctx) {
+  auto arena = [&](int bytes) { a.arena_words = (uint32_t)(bytes / 128); return (size_t)bytes; };
+  if (kind == kCoop && phase == 1) { a.arena_words = 0; poa_dp1_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group); }
+  else if (kind == kCoop) { a.arena_words = 0; poa_dp2_coop_kernel<GS><<<grid, 32, 0, st>>>(a, tab, coop_group, linear_seg); }
   else if (phase == 1) {
-    if (kind == kPacked) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, 0, st>>>(a, tab);
-    else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, 0, st>>>(a, tab);
-  } else if (kind == kLinear) poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L><<<grid, 32, 0, st>>>(a, tab);
-  else if (kind == kDual && coop_group < 0) poa_dp2_kernel<Phase2D, 20><<<grid, 32, 0, st>>>(a, tab);   // A/B: register cap 96 (ELECTOR_PH2D_WARPS=20)
-  else if (kind == kDual) poa_dp2_kernel<Phase2D, EL_MIN_WARPS_PH2D><<<grid, 32, 0, st>>>(a, tab);
-  else if (kind == kPacked) poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P><<<grid, 32, 0, st>>>(a, tab);
-  else poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2><<<grid, 32, 0, st>>>(a, tab);
+    if (kind == kPacked) poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P><<<grid, 32, arena(ctx->arena_ph1p), st>>>(a, tab);
+    else poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1><<<grid, 32, arena(ctx->arena_ph1), st>>>(a, tab);
+  } else if (kind == kLinear) poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L><<<grid, 32, arena(ctx->arena_ph2l), st>>>(a, tab);
+  else if (kind == kDual) poa_dp2_kernel<Phase2D, EL_MIN_WARPS_PH2D><<<grid, 32, arena(ctx->arena_ph2d), st>>>(a, tab);
+  else poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2><<<grid, 32, arena(ctx->arena_ph2), st>>>(a, tab);
   return cudaGetLastError();
 }
 
+// Residency of a thread-per-window kernel (one-warp CTAs: registers bound it) and the largest per-warp arena in dynamic
+// shared memory that keeps it: the SM's shared memory divided among the resident CTAs, minus the kernel's static part and
+// the 1 KB the system reserves per CTA.
+template <class K>
+void size_arena(K kernel, size_t smem_per_sm, int cap_warps, int &resident, int &arena_bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32, 0);
+  if (cap_warps > 0 && cap_warps < resident) resident = cap_warps;
+  arena_bytes = 0;
+  if (resident < 1) return;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return;
+  long per_cta = (long)(smem_per_sm / (size_t)resident) - (long)fa.sharedSizeBytes - 1024;
+  per_cta = std::min<long>(per_cta, 40 * 1024) & ~127L;
+  for (; per_cta > 0; per_cta -= 128) {
+    int r = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, kernel, 32, (size_t)per_cta) == cudaSuccess && r >= resident) break;
+  }
+  arena_bytes = per_cta > 0 ? (int)per_cta : 0;
+  if (arena_bytes > 48 * 1024 - (int)fa.sharedSizeBytes) arena_bytes = (48 * 1024 - (int)fa.sharedSizeBytes) & ~127;
+}
+
 template <bool GS>
-void resident_warps_per_sm(int &ph1, int &ph2, int &ph1p, int &ph2p, int &ph2l, int &coop) {
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop, poa_dp2_coop_kernel<GS>, 32, 0);
+void resident_warps_per_sm(elector_ctx *ctx, size_t smem_per_sm) {
+  auto cap = [](const char *name) { const char *e = getenv(name); return e ? atoi(e) : 0; };
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resident_coop, poa_dp2_coop_kernel<GS>, 32, 0);
   int coop1 = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop1, poa_dp1_coop_kernel<GS>, 32, 0);
-  coop = std::min(coop, coop1);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2l, poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L>, 32, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1, poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1>, 32, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2, poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2>, 32, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph1p, poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P>, 32, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ph2p, poa_dp2_kernel<Phase2P, EL_MIN_WARPS_PH2P>, 32, 0);
+  ctx->resident_coop = std::min(ctx->resident_coop, coop1);
+  // experiment knobs ELECTOR_WARPS_*: cap the resident warps per SM of a kernel (scratch footprint and arena size vs. latency hiding)
+  size_arena(poa_dp2_kernel<Phase2L, EL_MIN_WARPS_PH2L>, smem_per_sm, cap("ELECTOR_WARPS_PH2L"), ctx->resident_ph2l, ctx->arena_ph2l);
+  size_arena(poa_dp1_kernel<Phase1<GS>, EL_MIN_WARPS_PH1>, smem_per_sm, cap("ELECTOR_WARPS_PH1"), ctx->resident_ph1, ctx->arena_ph1);
+  size_arena(poa_dp2_kernel<Phase2<GS>, EL_MIN_WARPS_PH2>, smem_per_sm, cap("ELECTOR_WARPS_PH2"), ctx->resident_ph2, ctx->arena_ph2);
+  size_arena(poa_dp1_kernel<Phase1P, EL_MIN_WARPS_PH1P>, smem_per_sm, cap("ELECTOR_WARPS_PH1P"), ctx->resident_ph1p, ctx->arena_ph1p);
+  size_arena(poa_dp2_kernel<Phase2D, EL_MIN_WARPS_PH2D>, smem_per_sm, cap("ELECTOR_WARPS_PH2D"), ctx->resident_ph2d, ctx->arena_ph2d);
+  if (const char *e = getenv("ELECTOR_NO_ARENA")) if (e[0] == '1') ctx->arena_ph1 = ctx->arena_ph2 = ctx->arena_ph1p = ctx->arena_ph2l = ctx->arena_ph2d = 0;
 }
 
 struct SegPlan { int seg, grid; size_t warp_words, scratch_off; int kind; bool region_b; };
@@ -207,15 +228,13 @@ int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<S
       else if (p.kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1p; }
       else { Layout1 L; make_layout1(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1; }
     } else {
-      // windows whose P1 is linear have their own segments and, when 16 bits are enough, their own kernel; the general packed
-      // kernel is opt-in (its out-of-line frontier handling costs more than the packed cells save)
+      // windows whose P1 is linear have their own segments and, when 16 bits are enough, their own kernel
       // the segments of the longest windows (more than 128 rows, general and linear): a warp per window instead of a thread
       const bool longest = s <= kBigTiers || s == kFirstLinSeg2;
-      p.kind = (longest && ctx->coop_group > 0) ? kCoop : !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->packed2 ? kPacked : ctx->no_dual ? kInt32 : kDual;
+      p.kind = (longest && ctx->coop_group > 0) ? kCoop : !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->no_dual ? kInt32 : kDual;
       if (p.kind == kCoop) { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
       else if (p.kind == kDual) { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2d; }
       else if (p.kind == kLinear) { Layout2L L; make_layout2l(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2l; }
-      else if (p.kind == kPacked) { Layout2P L; make_layout2p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2p; }
       else { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2; }
     }
     const int resident = std::max(1, per_sm) * ctx->sm_count;
@@ -273,9 +292,8 @@ int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, 
       if (p.region_b) a.rows_cursor = cursor_b; else a.rows_cap = cap_a;
     }
     const bool linear_seg = phase == 2 && p.seg >= kFirstLinSeg2;
-    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group, linear_seg)
-                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(),
-                                                                    (p.kind == kDual && ctx->ph2d_alt) ? -1 : ctx->coop_group, linear_seg);
+    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group, linear_seg, ctx)
+                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group, linear_seg, ctx);
     if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     ++ctx->last_launches;
     if (ctx->trace) { CU(cudaEventRecord(tr.e1, ls)); ctx->seg_trace.push_back(tr); }
@@ -605,7 +623,6 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   if (const char *e = getenv("ELECTOR_NO_IDENT")) ctx->no_ident = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_DUAL")) ctx->no_dual = e[0] == '1';
   if (const char *e = getenv("ELECTOR_BAND_W")) ctx->band_w = std::max(0, std::min(64, atoi(e)));
-  if (const char *e = getenv("ELECTOR_PACKED2")) ctx->packed2 = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_LINEAR2")) ctx->no_linear2 = e[0] == '1';
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -652,22 +669,16 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
       ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
       return bail(ELECTOR_ECUDA);
     }
-  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l, ctx->resident_coop);
-  else resident_warps_per_sm<false>(ctx->resident_ph1, ctx->resident_ph2, ctx->resident_ph1p, ctx->resident_ph2p, ctx->resident_ph2l, ctx->resident_coop);
+  if (ctx->sc.generic_sub) resident_warps_per_sm<true>(ctx, prop.sharedMemPerMultiprocessor);
+  else resident_warps_per_sm<false>(ctx, prop.sharedMemPerMultiprocessor);
   if (const char *e = getenv("ELECTOR_COOP_GROUP")) ctx->coop_group = std::max(0, std::min(32, atoi(e)));
   if (ctx->resident_coop < 1) ctx->coop_group = 0;
-  // experiment knobs: cap the resident warps per SM of a kernel (scratch footprint vs. latency hiding)
-  auto cap = [](int &v, const char *name) { if (const char *e = getenv(name)) { const int c = atoi(e); if (c > 0 && c < v) v = c; } };
-  cap(ctx->resident_ph1, "ELECTOR_WARPS_PH1"); cap(ctx->resident_ph2, "ELECTOR_WARPS_PH2");
-  cap(ctx->resident_ph1p, "ELECTOR_WARPS_PH1P"); cap(ctx->resident_ph2p, "ELECTOR_WARPS_PH2P"); cap(ctx->resident_ph2l, "ELECTOR_WARPS_PH2L");
-  cap(ctx->resident_coop, "ELECTOR_WARPS_COOP");
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resident_ph2d, poa_dp2_kernel<Phase2D, EL_MIN_WARPS_PH2D>, 32, 0);
-  if (const char *e = getenv("ELECTOR_PH2D_WARPS")) if (atoi(e) == 20) {
-    ctx->ph2d_alt = true;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->resident_ph2d, poa_dp2_kernel<Phase2D, 20>, 32, 0);
-  }
-  cap(ctx->resident_ph2d, "ELECTOR_WARPS_PH2D");
+  if (const char *e = getenv("ELECTOR_WARPS_COOP")) { const int c = atoi(e); if (c > 0 && c < ctx->resident_coop) ctx->resident_coop = c; }
   if (ctx->resident_ph2d < 1) ctx->no_dual = true;
+  if (ctx->trace)
+    fprintf(stderr, "[elector trace] resident warps / arena bytes per warp: Phase1P %d / %d, Phase2L %d / %d, Phase2D %d / %d, Phase1 %d / %d, Phase2 %d / %d, coop %d\n",
+            ctx->resident_ph1p, ctx->arena_ph1p, ctx->resident_ph2l, ctx->arena_ph2l, ctx->resident_ph2d, ctx->arena_ph2d, ctx->resident_ph1, ctx->arena_ph1,
+            ctx->resident_ph2, ctx->arena_ph2, ctx->resident_coop);
   if (ctx->resident_ph1 < 1 || ctx->resident_ph2 < 1) { ctx->fail(ELECTOR_ECUDA, "POA kernel does not fit on this device"); return bail(ELECTOR_ECUDA); }
   *out = ctx;
   return ELECTOR_OK;

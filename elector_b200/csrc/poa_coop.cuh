@@ -49,7 +49,7 @@ struct CoopLane {
 
   EL_HDN void begin(const Phase2<GENERIC_SUB> &win, int r0) {
 #pragma unroll
-    for (int k = 0; k < kCoopRows / 4; ++k) yw[k] = win.scr.w(win.Lp->o_unc + (uint32_t)(r0 >> 2) + k);
+    for (int k = 0; k < kCoopRows / 4; ++k) yw[k] = win.fs.w(win.Lp->f_unc + (uint32_t)(r0 >> 2) + k);
 #pragma unroll
     for (int r = 0; r < kCoopRows; ++r) S[r] = G[r] = 0;
     h = 0; kindA = kindB = 0; bsel = 0;
@@ -115,7 +115,7 @@ EL_HD int coop_passes(int ly) { return (ly + kCoopPassRows - 1) / kCoopPassRows;
 // The owner lane writes lin(ref) as a 16-bit node list (into the window's P1 slot, which fuse 1 overwrites afterwards),
 // prepares it like any P1 and, after the cooperative DP and the traceback of Phase2, runs fuse 1 on the x2y fields.
 struct LayoutC1 {
-  Layout2 l2;        // rows = cor (o_unc holds the cor codes), nodes = lin(ref)
+  Layout2 l2;        // rows = cor (f_unc holds the cor codes), nodes = lin(ref)
   uint32_t o_ref;    // packed ref codes (fuse 1 reads them)
   uint32_t total;
 };
@@ -134,18 +134,21 @@ EL_HDN inline void linear_node_list(const LaneScratch &scr, uint32_t o_ref, int 
   }
   if (lr & 3) out4[lr >> 2] = acc;
 }
-// owner-lane steps of a cooperative phase 1 around the DP
+// owner-lane steps of a cooperative phase 1 around the DP (the fast part of these long windows lives in global scratch)
 template <bool GENERIC_SUB>
 EL_HDN void coop1_before(const Phase2<GENERIC_SUB> &ph, const LayoutC1 &L, const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_slot) {
   ph.scr.pack_codes(ph.sc.tab, ref, lr, L.o_ref);
-  ph.scr.pack_codes(ph.sc.tab, cor, lc, L.l2.o_unc);
+  ph.fs.pack_codes(ph.sc.tab, cor, lc, L.l2.f_unc);
   linear_node_list(ph.scr, L.o_ref, lr, p1_slot);
   ph.prepare(p1_slot, lr);
 }
 template <bool GENERIC_SUB>
 EL_HDN int coop1_after(const Phase2<GENERIC_SUB> &ph, const LayoutC1 &L, int lr, int lc, int best_j, uint16_t *p1_slot, int &spcode) {
-  ph.traceback(lc, best_j);
-  return fuse1(ph.scr, L.o_ref, L.l2.o_unc, ph.rec(0) + R2_X2Y * 32, (ptrdiff_t)L.l2.rec_words * 32, lr, lc, p1_slot, spcode);
+  AlignBits al = ph.bits();
+  ph.traceback(lr, lc, best_j, al);
+  // fuse 1 reads the ref codes from the slow part and the cor codes from the fast part: both through one accessor based at
+  // the slow part (the fast part of these kernels is global scratch at o_fast, so its offsets are plain scratch offsets)
+  return fuse1(ph.scr, L.o_ref, L.l2.o_fast + L.l2.f_unc, al, lr, lc, p1_slot, spcode);
 }
 
 #ifdef __CUDACC__
@@ -236,28 +239,32 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
       __syncwarp();
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
+    c.fs.base = c.scr.base + (size_t)s_layout.o_fast * 32;   // long windows: the fast part stays in global scratch
+    int nrings = 0;
     if (owner) {
-      c.scr.pack_codes(c.sc.tab, a.unc + uo, lu, s_layout.o_unc);
+      c.fs.pack_codes(c.sc.tab, a.unc + uo, lu, s_layout.f_unc);
       uint16_t *p1 = a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w);
-      if (linear_seg) {   // the ref codes pass through the (still unused) MSA row area
-        c.scr.pack_codes(c.sc.tab, a.ref + ro, n1, s_layout.o_rows);
-        linear_node_list(c.scr, s_layout.o_rows, n1, p1, NF_REF | NF_COR);
+      if (linear_seg) {
+        c.scr.pack_codes(c.sc.tab, a.ref + ro, n1, s_layout.o_tmp);
+        linear_node_list(c.scr, s_layout.o_tmp, n1, p1, NF_REF | NF_COR);
       }
-      c.prepare(p1, n1);
+      nrings = c.prepare(p1, n1);
     }
     int s2 = 0, bj = -1;
     for (int i = 0; i < cnt; ++i) {
       const int nx = __shfl_sync(EL_WARP_FULL, n1, i), ly = __shfl_sync(EL_WARP_FULL, lu, i);
       Phase2<GENERIC_SUB> win = c;
       win.scr.base = warp_scratch + i;
+      win.fs.base = win.scr.base + (size_t)s_layout.o_fast * 32;
       int best, best_j;
       coop_dp<GENERIC_SUB>(win, c.bset, nx, ly, best, best_j);
       if (lane == i) { s2 = best; bj = best_j; }
     }
     __syncwarp();
+    AlignBits al = c.bits();
     if (owner) {
-      c.traceback(lu, bj);
-      nring = c.fuse_emit(n1, lu);
+      c.traceback(n1, lu, bj, al);
+      nring = columns_of(nrings, lu, al.nmatch);
       a.nring[w] = nring;
       if (a.score2) a.score2[w] = s2;
       if (a.cells) {
@@ -266,7 +273,8 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
       }
     }
     __syncwarp();
-    store_window_rows(a, c.scr, s_layout.o_rows, s_layout.row_words, owner, w, nring);
+    RowSink out;
+    if (alloc_window_rows(a, owner, w, nring, out)) c.fuse_emit(al, n1, lu, out);
     __syncwarp();
   }
 }
@@ -306,6 +314,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
       __syncwarp();
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
+    c.fs.base = c.scr.base + (size_t)s_layout.l2.o_fast * 32;
     uint16_t *p1_slot = owner ? a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w) : nullptr;
     if (owner) coop1_before<GENERIC_SUB>(c, s_layout, a.ref + ro, lr, a.cor + co, lc, p1_slot);
     int s1 = 0, bj = -1;
@@ -313,6 +322,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
       const int nx = __shfl_sync(EL_WARP_FULL, lr, i), ly = __shfl_sync(EL_WARP_FULL, lc, i);
       Phase2<GENERIC_SUB> win = c;
       win.scr.base = warp_scratch + i;
+      win.fs.base = win.scr.base + (size_t)s_layout.l2.o_fast * 32;
       int best, best_j;
       coop_dp<GENERIC_SUB>(win, c.bset, nx, ly, best, best_j);
       if (lane == i) { s1 = best; bj = best_j; }

@@ -57,7 +57,7 @@ struct Phase2D : Phase2<false> {
   static constexpr int kSetWords = 1;   // no frontier sets in shared memory
   // boundary rows live in the node records in packed form: the biased value in both halves
   static EL_HD void put_row0(uint32_t *p, int bS, int bG) { p[R2_BS * 32] = pk_both((uint32_t)(kBiasP + bS)); p[R2_BG * 32] = pk_both((uint32_t)(kBiasP + bG)); }
-  EL_HDN void prepare(const uint16_t *nodes, int nx) const { prepare_nodes(*this, nodes, nx); }
+  EL_HDN int prepare(const uint16_t *nodes, int nx) const { return prepare_nodes(*this, nodes, nx); }
 
   // one band of R rows of DP2 (align_lpo_po2.c:269-433)
   template <int R>
@@ -68,7 +68,7 @@ struct Phase2D : Phase2<false> {
     uint32_t y2[R], S[R], G[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      y2[r] = pk_both((uint32_t)scr.code_at(Lp->o_unc, r0 + r)) << 4;
+      y2[r] = pk_both((uint32_t)fs.code_at(Lp->f_unc, r0 + r)) << 4;
       S[r] = pk_both((uint32_t)(kBiasP + sc.virt_S(r0 + r)));       // both frontiers start as the virtual column -1
       G[r] = pk_both((uint32_t)(kBiasP + sc.virt_G(r0 + r)));
     }
@@ -144,13 +144,14 @@ struct Phase2D : Phase2<false> {
     return best;
   }
 
-  EL_HDN int run_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2) const {
-    scr.pack_codes(sc.tab, unc, lu, Lp->o_unc);
-    prepare(p1, n1);
+  // everything up to the traceback; returns the number of MSA columns
+  EL_HDN int align_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2, AlignBits &al) const {
+    fs.pack_codes(sc.tab, unc, lu, Lp->f_unc);
+    const int nrings = prepare(p1, n1);
     int bj;
     s2 = dp(n1, lu, bj);
-    traceback(lu, bj);
-    return fuse_emit_rows(*this, n1, lu);
+    traceback(n1, lu, bj, al);
+    return columns_of(nrings, lu, al.nmatch);
   }
 };
 

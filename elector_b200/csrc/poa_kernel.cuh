@@ -60,46 +60,67 @@ EL_HD uint32_t max_u(uint32_t a, uint32_t b) { return a > b ? a : b; }
 // ---- per-thread scratch layouts (32-bit words), one per phase ------------------------------
 // Every term is monotone in each cap, so a layout for the maxima of a launch bounds the
 // layout of any of its 32-window groups (which compute their own, tighter one on the device).
-enum : uint32_t { R1_BS = 0, R1_BG = 1, R1_X2Y = 2, R1_MOVES = 3 };                                      // phase-1 node record
-enum : uint32_t { R2_NODE = 0, R2_BS = 1, R2_BG = 2, R2_PRED = 3, R2_X2Y = 4, R2_MOVES = 5 };            // phase-2 node record
+//
+// A layout has a SLOW part (node records: boundary rows and 2-bit moves, written and read once per band by
+// the DP with loads issued iterations ahead; always global scratch) and a small FAST part that the serial
+// steps of a window walk with dependent accesses (packed letter codes, the alignment bitmaps of the
+// traceback): the fast part lives in a per-warp SHARED-MEMORY arena when the group's fits
+// (f_total <= PoaArgs::arena_words; ~30-cycle loads instead of 250-600), else in global scratch at o_fast.
+// Both are interleaved by lane at 4-byte granularity (word i of a lane at [i * 32]).
+enum : uint32_t { R1_BS = 0, R1_BG = 1, R1_MOVES = 2 };                                      // phase-1 node record
+enum : uint32_t { R2_NODE = 0, R2_BS = 1, R2_BG = 2, R2_PRED = 3, R2_MOVES = 4 };            // phase-2 node record
 
 struct Layout1 {            // phase 1: windows with ref / cor lengths up to (LR, LC)
-  uint32_t o_ref, o_cor;    // packed symbol codes, 4 per word
-  uint32_t o_nodes;         // LR records of rec_words words: boundary S, boundary G, x2y, one moves word per band
+  uint32_t o_nodes;         // LR records of rec_words words: boundary S, boundary G, one moves word per band
   uint32_t rec_words;
-  uint32_t total;
+  uint32_t o_fast;          // the fast part when it lives in global scratch
+  uint32_t f_ref, f_cor;    // fast: packed symbol codes, 4 per word
+  uint32_t f_xb, f_yb;      // fast: alignment bitmaps (bit j of f_xb: ref letter j is aligned; bit r of f_yb: cor letter r is)
+  uint32_t f_total;
+  uint32_t total;           // global words per lane (slow + fast)
 };
 struct Layout2 {            // phase 2: windows with len(P1) / unc length up to (N1, LU)
-  uint32_t o_unc;           // packed symbol codes
-  uint32_t o_nodes;         // N1 records: node flags|letter, boundary S, boundary G, preds, x2y, moves per band
+  uint32_t o_nodes;         // N1 records: node flags|letter, boundary S, boundary G, preds, moves per band
   uint32_t rec_words;
   uint32_t o_ord;           // two words per (combined node, band): winning predecessor ordinals
   uint32_t ord_bands;
   uint32_t o_nt;            // bitmap: node j has a predecessor list other than [j-1]
-  uint32_t o_rows;          // 3 MSA rows, bytes packed 4 per word
-  uint32_t row_words;
+  uint32_t o_tmp;           // N1 letter codes (the warp-cooperative kernel rebuilds lin(ref) from them)
+  uint32_t o_fast;
+  uint32_t f_unc;           // fast: packed symbol codes of unc
+  uint32_t f_xb, f_yb;      // fast: alignment bitmaps (node j of P1 / letter r of unc is aligned)
+  uint32_t f_total;
   uint32_t total;
 };
 
 EL_HD void make_layout1(Layout1 &L, int LR, int LC) {
+  uint32_t f = 0;
+  L.f_ref = f; f += cdiv_u(LR, 4) + 1;
+  L.f_cor = f; f += cdiv_u(LC, 4) + 4;                          // +4: a band reads four code words at once
+  L.f_xb = f; f += cdiv_u(LR, 32) + 1;
+  L.f_yb = f; f += cdiv_u(LC, 32) + 1;
+  L.f_total = f;
   uint32_t o = 0;
-  L.o_ref = o; o += cdiv_u(LR, 4) + 1;
-  L.o_cor = o; o += cdiv_u(LC, 4) + 4;                          // +4: a band reads four code words at once
   L.rec_words = R1_MOVES + cdiv_u(LC, kBand);
   L.o_nodes = o; o += (uint32_t)LR * L.rec_words;
+  L.o_fast = o; o += f;
   L.total = o;
 }
 EL_HD void make_layout2(Layout2 &L, int N1, int LU) {
   const uint32_t nb = cdiv_u(LU, kBand);
+  uint32_t f = 0;
+  L.f_unc = f; f += cdiv_u(LU, 4) + 4;
+  L.f_xb = f; f += cdiv_u(N1, 32) + 1;
+  L.f_yb = f; f += cdiv_u(LU, 32) + 1;
+  L.f_total = f;
   uint32_t o = 0;
-  L.o_unc = o; o += cdiv_u(LU, 4) + 4;
   L.rec_words = R2_MOVES + nb;
   L.o_nodes = o; o += (uint32_t)N1 * L.rec_words;
   L.ord_bands = nb;
   L.o_ord = o; o += ((uint32_t)N1 / 2 + 2) * nb * 2;            // combined nodes carry ref AND cor: at most N1/2, + 2 initial ones
   L.o_nt = o; o += cdiv_u(N1, 32) + 1;
-  L.row_words = cdiv_u(N1 + LU, 4);
-  L.o_rows = o; o += 3 * L.row_words;
+  L.o_tmp = o; o += cdiv_u(N1, 4) + 1;
+  L.o_fast = o; o += f;
   L.total = o;
 }
 
@@ -111,6 +132,7 @@ struct PoaArgs {
   int32_t match, mismatch, open, ext;
   uint32_t *scratch;     // grid x warp_words x 32 words
   uint32_t warp_words;   // scratch words per thread (layout of the segment's maxima)
+  uint32_t arena_words;  // shared-memory arena words per thread (dynamic shared memory of the launch / 128)
   int32_t *work_counter;
   // phase 1 -> phase 2
   uint16_t *p1_nodes;    // P1 node list of window w at [p1_offset(ref_off[w] - ref_off[0], cor_off[w] - cor_off[0], w)], n1[w] entries
@@ -277,7 +299,8 @@ struct LaneScratch {
   EL_HD uint32_t *at(uint32_t i) const { return base + (size_t)i * 32; }
   EL_HD int code_at(uint32_t off, int i) const { return (w(off + (i >> 2)) >> ((i & 3) * 8)) & 0xff; }
   // raw letters -> symbol indices, 4 per scratch word.  Reads the letters as aligned 32-bit
-  // words (only words that hold at least one letter of the sequence), one word ahead.
+  // words (only words that hold at least one letter of the sequence), four loads in flight per step
+  // (the letters come from HBM; a one-word look-ahead left this loop waiting on every load).
   EL_HDN void pack_codes(const SymbolTables *tab, const uint8_t *src, int len, uint32_t off) const {
     const uintptr_t a = reinterpret_cast<uintptr_t>(src);
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
@@ -285,26 +308,87 @@ struct LaneScratch {
     const int nin = (len + mis + 3) >> 2;   // aligned input words that hold letters
     const int nout = (len + 3) >> 2;
     const uint8_t *lut = tab->code_lut;
-    uint32_t cur = wp[0], nxt = nin > 1 ? wp[1] : 0;
+    uint32_t cur = wp[0];
 #pragma unroll 1
-    for (int k = 0; k < nout; ++k) {
-      const uint32_t nn = k + 2 < nin ? wp[k + 2] : 0;
-      const uint32_t v = sh ? (cur >> sh) | (nxt << (32 - sh)) : cur;
-      uint32_t c = (uint32_t)lut[v & 0xff] | ((uint32_t)lut[(v >> 8) & 0xff] << 8) | ((uint32_t)lut[(v >> 16) & 0xff] << 16) |
-                   ((uint32_t)lut[v >> 24] << 24);
-      if (k == nout - 1 && (len & 3)) c &= 0xffffffffu >> (8 * (4 - (len & 3)));
-      w(off + k) = c;
-      cur = nxt; nxt = nn;
+    for (int k = 0; k < nout; k += 4) {
+      uint32_t in[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) in[i] = k + 1 + i < nin ? wp[k + 1 + i] : 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t nxt = in[i];
+        if (k + i < nout) {
+          const uint32_t v = sh ? (cur >> sh) | (nxt << (32 - sh)) : cur;
+          uint32_t c = (uint32_t)lut[v & 0xff] | ((uint32_t)lut[(v >> 8) & 0xff] << 8) | ((uint32_t)lut[(v >> 16) & 0xff] << 16) |
+                       ((uint32_t)lut[v >> 24] << 24);
+          if (k + i == nout - 1 && (len & 3)) c &= 0xffffffffu >> (8 * (4 - (len & 3)));
+          w(off + k + i) = c;
+        }
+        cur = nxt;
+      }
     }
   }
 };
 
-// fuse 1 (lpo.c:413-463,602-656 for two linear sequences): P1's node list, 16 bits per node,
-// to out[] (px = x2y field of node 0, step words between nodes); returns len(P1) and the phase-2 sort code of the window: 0 when ref and cor are
-// identical (P1 is linear), else 1 + 3*min(pos/2, 31) + type of the first node that does not
+// brings the line of a scratch word into L1 ahead of a dependent walk (traceback); no register, no wait
+EL_HD void prefetch_l1(const void *p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+// ---- what the traceback leaves for the fusion: two bitmaps instead of the reference's x_to_y / y_to_x maps ----
+// (align_lpo_po2.c:158-165 fills two integer maps.)  An alignment path is monotone in both sequences: the k-th aligned node
+// of x is aligned to the k-th aligned letter of y, so "node j is aligned" / "letter r is aligned" bits carry the same
+// information in 1/32 of the space -- small enough for the shared-memory arena.  The walk visits nodes and letters in
+// decreasing order, so every bitmap word is completed once and stored once; clear() zeroes the words it may never reach.
+struct AlignBits {
+  LaneScratch st;
+  uint32_t ox, oy;
+  uint32_t xw = 0, yw = 0;
+  int xi = -1, yi = -1, nmatch = 0;
+  EL_HD void clear(int nx, int ny) const {
+    for (uint32_t k = 0; k < cdiv_u((uint32_t)nx, 32); ++k) st.w(ox + k) = 0;
+    for (uint32_t k = 0; k < cdiv_u((uint32_t)ny, 32); ++k) st.w(oy + k) = 0;
+  }
+  EL_HD void mark(int j, int r) {
+    if ((j >> 5) != xi) { if (xi >= 0) st.w(ox + (uint32_t)xi) = xw; xi = j >> 5; xw = 0; }
+    if ((r >> 5) != yi) { if (yi >= 0) st.w(oy + (uint32_t)yi) = yw; yi = r >> 5; yw = 0; }
+    xw |= 1u << (j & 31);
+    yw |= 1u << (r & 31);
+    ++nmatch;
+  }
+  EL_HD void finish() {
+    if (xi >= 0) st.w(ox + (uint32_t)xi) = xw;
+    if (yi >= 0) st.w(oy + (uint32_t)yi) = yw;
+  }
+  EL_HD bool x_at(int j) const { return (st.w(ox + (uint32_t)(j >> 5)) >> (j & 31)) & 1u; }
+};
+// forward reader of one bitmap: sequential positions reuse the word in a register
+struct BitCursor {
+  LaneScratch st;
+  uint32_t off, word = 0;
+  int idx = -1;
+  EL_HD bool at(int i) {
+    if ((i >> 5) != idx) { idx = i >> 5; word = st.w(off + (uint32_t)idx); }
+    return (word >> (i & 31)) & 1u;
+  }
+};
+
+// where the three MSA rows of a window go: 32-bit words, 4 columns each (the caller's row buffer on the device: the
+// fusion writes its output once, in place -- no staging copy)
+struct RowSink {
+  uint32_t *r0, *r1, *r2;
+};
+
+// fuse 1 (lpo.c:413-463,602-656 for two linear sequences): P1's node list, 16 bits per node, to out[]; codes of ref / cor at
+// cd.w(o_ref ..) / cd.w(o_cor ..), alignment bitmaps in `al`.  Returns len(P1) and the phase-2 sort code of the window: 0 when
+// ref and cor are identical (P1 is linear), else 1 + 3*min(pos/2, 31) + type of the first node that does not
 // carry both letters (type 0: ref only, 1: cor only followed by its ref partner = a
 // substitution, 2: cor only = an insertion).
-EL_HDN inline int fuse1(const LaneScratch &scr, uint32_t o_ref, uint32_t o_cor, const uint32_t *px, ptrdiff_t step, int lr, int lc,
+EL_HDN inline int fuse1(const LaneScratch &cd, uint32_t o_ref, uint32_t o_cor, const AlignBits &al, int lr, int lc,
                       uint16_t *out, int &spcode) {
   int n = 0, iy = 0, sp = -1, sptype = 0;
   uint64_t *out4 = reinterpret_cast<uint64_t *>(out);   // 4 nodes per store (the list is 8-byte aligned)
@@ -314,22 +398,23 @@ EL_HDN inline int fuse1(const LaneScratch &scr, uint32_t o_ref, uint32_t o_cor, 
     if ((n & 3) == 3) { out4[n >> 2] = acc; acc = 0; }
     ++n;
   };
+  uint32_t yw = 0;
+  int ywi = -1;
+  auto ycode = [&](int i) { if ((i >> 2) != ywi) { ywi = i >> 2; yw = cd.w(o_cor + (uint32_t)ywi); } return (yw >> ((i & 3) * 8)) & 0xffu; };
   auto cor_only = [&](int iy_) {
-    put((uint32_t)scr.code_at(o_cor, iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
+    put(ycode(iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
   };
-  int q0 = (int)px[0], q1 = lr > 1 ? (int)px[step] : -1;
+  BitCursor xb{al.st, al.ox}, yb{al.st, al.oy};
   uint32_t xw = 0;
   for (int ix = 0; ix < lr; ++ix) {
-    const int q = q0;
-    q0 = q1;
-    q1 = ix + 2 < lr ? (int)px[(ptrdiff_t)(ix + 2) * step] : -1;
-    if ((ix & 3) == 0) xw = scr.w(o_ref + (ix >> 2));
+    const bool aligned = xb.at(ix);
+    if ((ix & 3) == 0) xw = cd.w(o_ref + (ix >> 2));
     const int xl = xw & 0xff; xw >>= 8;
-    if (q >= 0)
-      while (iy < q) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
+    if (aligned)   // its partner is the next aligned letter of cor: the unaligned ones before it come first
+      while (iy < lc && !yb.at(iy)) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
     uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
-    if (q >= 0 && iy < lc) {
-      const int yl = scr.code_at(o_cor, iy);
+    if (aligned && iy < lc) {
+      const int yl = (int)ycode(iy);
       const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
       if (yl == xl) fl |= yf;  // identical letters share the node
       else {                   // own node just before x, same ring
@@ -353,7 +438,8 @@ struct Phase1 {
   static constexpr bool kGenericSub = GENERIC_SUB;
   static constexpr bool kBanded = false;
   static EL_HD void make_layout(Layout1 &L, int LR, int LC) { make_layout1(L, LR, LC); }
-  LaneScratch scr;
+  LaneScratch scr;    // slow part of the layout (global scratch)
+  LaneScratch fs;     // fast part (shared-memory arena, or global scratch at o_fast)
   Scoring sc;
   const Layout1 *Lp;  // layout of the current group (shared memory on the device)
 
@@ -363,7 +449,7 @@ struct Phase1 {
     const int r0 = b * kBand;
     uint32_t yw[R / 4];
 #pragma unroll
-    for (int k = 0; k < R / 4; ++k) yw[k] = scr.w(Lp->o_cor + (r0 >> 2) + k);
+    for (int k = 0; k < R / 4; ++k) yw[k] = fs.w(Lp->f_cor + (r0 >> 2) + k);
     int S[R], G[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { S[r] = sc.virt_S(r0 + r); G[r] = sc.virt_G(r0 + r); }
@@ -374,7 +460,7 @@ struct Phase1 {
     int upS_n = 0, upG_n = 0;
     if (b > 0) { upS_n = (int)p[R1_BS * 32]; upG_n = (int)p[R1_BG * 32]; }
     for (int j = 0; j < lr; ++j, p += step) {
-      if ((j & 3) == 0) xw = scr.w(Lp->o_ref + (j >> 2));
+      if ((j & 3) == 0) xw = fs.w(Lp->f_ref + (j >> 2));
       const int xl = xw & 0xff; xw >>= 8;
       int upS, upG;
       if (b == 0) { upS = -(sc.open + sc.ext * j); upG = upS - sc.ext; }   // row -1 (:275-286)
@@ -399,41 +485,39 @@ struct Phase1 {
     return (ly - (nb - 1) * kBand <= 8) ? band<8>(lr, ly, nb - 1, true) : band<kBand>(lr, ly, nb - 1, true);
   }
 
-  // traceback (align_lpo_po2.c:108-168): fills the x2y field of every record.  The walk reads
+  // traceback (align_lpo_po2.c:108-168): marks the aligned pairs in the bitmaps.  The walk reads
   // one moves word per step; the words of the next three columns of the band are loaded ahead.
-  EL_HDN void traceback(int lr, int ly) const {
+  EL_HDN void traceback(int lr, int ly, AlignBits &al) const {
     const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
-    {
-      uint32_t *p = scr.at(Lp->o_nodes) + R1_X2Y * 32;
-      for (int j = 0; j < lr; ++j, p += step) *p = 0xffffffffu;
-    }
+    al.clear(lr, ly);
     int j = lr - 1, r = ly - 1;
     while (j >= 0 && r >= 0) {
       const int b = r >> 4;
-      uint32_t *p = scr.at(Lp->o_nodes) + (ptrdiff_t)j * step;   // record j
-      const uint32_t *pm = p + (R1_MOVES + b) * 32;
+      const uint32_t *pm = scr.at(Lp->o_nodes) + (ptrdiff_t)j * step + (R1_MOVES + b) * 32;
       uint32_t w0 = pm[0], w1 = j >= 1 ? pm[-step] : 0, w2 = j >= 2 ? pm[-2 * step] : 0, w3 = j >= 3 ? pm[-3 * step] : 0;
       for (;;) {
         const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
-        if (kind & 2u) p[R1_X2Y * 32] = (uint32_t)r;
+        if (kind & 2u) al.mark(j, r);
         if (kind != 1u) --r;
         if (kind) {
-          --j; p -= step; pm -= step;
+          --j; pm -= step;
           w0 = w1; w1 = w2; w2 = w3;
           w3 = j >= 3 ? pm[-3 * step] : 0;
         }
         if (j < 0 || r < 0 || (r >> 4) != b) break;
       }
     }
+    al.finish();
   }
 
   EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode, bool &exact) const {
     exact = true;   // no band in the INT32 kernels
-    scr.pack_codes(sc.tab, ref, lr, Lp->o_ref);
-    scr.pack_codes(sc.tab, cor, lc, Lp->o_cor);
+    fs.pack_codes(sc.tab, ref, lr, Lp->f_ref);
+    fs.pack_codes(sc.tab, cor, lc, Lp->f_cor);
     s1 = dp(lr, lc);
-    traceback(lr, lc);
-    return fuse1(scr, Lp->o_ref, Lp->o_cor, scr.at(Lp->o_nodes) + R1_X2Y * 32, (ptrdiff_t)Lp->rec_words * 32, lr, lc, p1_out, spcode);
+    AlignBits al{fs, Lp->f_xb, Lp->f_yb};
+    traceback(lr, lc, al);
+    return fuse1(fs, Lp->f_ref, Lp->f_cor, al, lr, lc, p1_out, spcode);
   }
 };
 
@@ -511,22 +595,25 @@ __host__ __device__ __noinline__ inline uint32_t arrange_sets(uint32_t *sa, uint
 
 // ---- fuse 2 + MSA emit (lpo.c:413-463 with rings, lpo_format.c:346-371) ----
 // Walks the final node order without materialising P2; a column closes whenever the
-// align ring changes.  Returns nring; rows go to o_rows (3 x row_words words).
+// align ring changes.  Returns nring; the rows go straight to `out` (4 columns per word).
+// The number of columns is known before the walk (columns_of): one per align ring of P1 plus one per
+// unaligned letter of unc -- an aligned letter joins its node's ring whether the letters agree or not.
+EL_HD int columns_of(int nrings, int lu, int nmatch) { return nrings + lu - nmatch; }
+
 template <class PH>
-EL_HDN int fuse_emit_rows(const PH &ph, int n1, int lu) {
-  const LaneScratch &scr = ph.scr;
+EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, const RowSink &out) {
+  const LaneScratch &fs = ph.fs;
   const auto *Lp = ph.Lp;
-  constexpr uint32_t kNode = PH::kRecNode, kX2Y = PH::kRecX2Y;
+  constexpr uint32_t kNode = PH::kRecNode;
   const uint8_t *sym = ph.sc.tab->sym;
   int iy = 0, col = -1, prev_key = -1, rs = 0;
   uint32_t c0 = '.', c1 = '.', c2 = '.';
   uint32_t w0 = 0, w1 = 0, w2 = 0;
-  const uint32_t r0 = Lp->o_rows, r1 = Lp->o_rows + Lp->row_words, r2 = Lp->o_rows + 2 * Lp->row_words;
   auto flush = [&]() {
     if (col >= 0) {
       const int sh = (col & 3) * 8;
       w0 |= c0 << sh; w1 |= c1 << sh; w2 |= c2 << sh;
-      if ((col & 3) == 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; w0 = w1 = w2 = 0; }
+      if ((col & 3) == 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w1; out.r2[col >> 2] = w2; w0 = w1 = w2 = 0; }
     }
   };
   auto emit = [&](int key, uint32_t letter, uint32_t srcmask) {
@@ -536,50 +623,53 @@ EL_HDN int fuse_emit_rows(const PH &ph, int n1, int lu) {
     if (srcmask & 2u) c1 = ch;
     if (srcmask & 4u) c2 = ch;
   };
+  uint32_t yw = 0;
+  int ywi = -1;
+  auto ycode = [&](int i) { if ((i >> 2) != ywi) { ywi = i >> 2; yw = fs.w(Lp->f_unc + (uint32_t)ywi); } return (yw >> ((i & 3) * 8)) & 0xffu; };
+  BitCursor xb{al.st, al.ox}, yb{al.st, al.oy};
   const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
   const uint32_t *pr = ph.node_rec(0);
-  // (node, x2y) of records ix, ix+1 in registers, ix+2 in flight
+  // nodes ix, ix+1 in registers, ix+2 in flight
   uint32_t ra0 = pr[kNode * 32], ra1 = n1 > 1 ? pr[step + kNode * 32] : 0;
-  int q0 = (int)pr[kX2Y * 32], q1 = n1 > 1 ? (int)pr[step + kX2Y * 32] : -1;
   for (int ix = 0; ix < n1; ++ix, pr += step) {
     const uint32_t ra = ra0, ra_next = ra1;
-    const int qx = q0, q_next = q1;
-    ra0 = ra1; q0 = q1;
-    if (ix + 2 < n1) { ra1 = pr[2 * step + kNode * 32]; q1 = (int)pr[2 * step + kX2Y * 32]; }
+    ra0 = ra1;
+    if (ix + 2 < n1) ra1 = pr[2 * step + kNode * 32];
     if (!(ra & NF_SAMERING)) rs = ix;
-    // scan x's ring from ix on: unaligned y letters go before the first aligned member
+    const bool aligned = xb.at(ix);
+    // scan x's ring from ix on: unaligned y letters go before the first aligned member (whose partner is the next aligned letter)
     {
-      int q = qx;
-      if (q < 0 && ix + 1 < n1 && (ra_next & NF_SAMERING)) {
-        q = q_next;
-        for (int ir = ix + 2; q < 0 && ir < n1 && (ph.node_rec(ir)[kNode * 32] & NF_SAMERING); ++ir) q = (int)ph.node_rec(ir)[kX2Y * 32];
+      bool any = aligned;
+      if (!any && ix + 1 < n1 && (ra_next & NF_SAMERING)) {
+        any = al.x_at(ix + 1);
+        for (int ir = ix + 2; !any && ir < n1 && (ph.node_rec(ir)[kNode * 32] & NF_SAMERING); ++ir) any = al.x_at(ir);
       }
-      if (q >= 0) while (iy < q) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
+      if (any) while (iy < lu && !yb.at(iy)) { emit(n1 + iy, ycode(iy), 4u); ++iy; }
     }
     uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
-    if (qx >= 0 && iy < lu) {
-      const uint32_t yl = scr.code_at(Lp->o_unc, iy);
+    if (aligned && iy < lu) {
+      const uint32_t yl = ycode(iy);
       if (yl == (ra & 0xffu)) mask |= 4u;
       else emit(rs, yl, 4u);
       ++iy;
     }
     emit(rs, ra & 0xffu, mask);
   }
-  while (iy < lu) { emit(n1 + iy, scr.code_at(Lp->o_unc, iy), 4u); ++iy; }
+  while (iy < lu) { emit(n1 + iy, ycode(iy), 4u); ++iy; }
   flush();
-  if ((col & 3) != 3) { scr.w(r0 + (col >> 2)) = w0; scr.w(r1 + (col >> 2)) = w1; scr.w(r2 + (col >> 2)) = w2; }
+  if ((col & 3) != 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w1; out.r2[col >> 2] = w2; }
   return col + 1;
 }
 
 // ---- node preparation (align_lpo_po2.c:46-79 + row -1, :272-286) ----
 // Reads P1's 16-bit node list, derives every node's left list from the two frontiers and
 // stores: the node with its shape (NF_VIRT / NF_TWO / NF_NOPRED / NF_PREDC / slot), its real
-// predecessors (for the traceback) and row -1 of the DP as the first boundary row.
+// predecessors (for the traceback) and row -1 of the DP as the first boundary row.  Returns the number of align rings.
 template <class PH>
-EL_HDN void prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
+EL_HDN int prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
   const LaneScratch &scr = ph.scr;
   const auto *Lp = ph.Lp;
-  int lastR = -1, lastC = -1, gR = 0, gC = 0, nslot = 0;
+  int lastR = -1, lastC = -1, gR = 0, gC = 0, nslot = 0, nrings = 0;
   uint32_t *p = ph.node_rec(0);
   const uint32_t step = Lp->rec_words * 32;
   const int open = ph.sc.open, ext = ph.sc.ext;
@@ -591,6 +681,7 @@ EL_HDN void prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
     if (j && (j & 3) == 0) { quad = quad_n; quad_n = j + 4 < nx ? n4[(j >> 2) + 1] : 0; }
     uint32_t ra = (uint32_t)(quad >> (16 * (j & 3))) & 0xffffu;
     const bool hasR = ra & NF_REF, hasC = ra & NF_COR;
+    if (!(ra & NF_SAMERING)) ++nrings;
     int pA = -1, pB = -1, gA = 0, gB = 0;
     if (hasR && lastR >= 0) { pA = lastR; gA = gR; }
     if (hasC && lastC >= 0 && lastC != pA) {
@@ -610,13 +701,13 @@ EL_HDN void prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
     p[PH::kRecNode * 32] = ra;
     p[PH::kRecPred * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
     PH::put_row0(p, bS, bG);
-    p[PH::kRecX2Y * 32] = 0xffffffffu;
     if (pA != j - 1 || (ra & (NF_VIRT | NF_TWO))) nt |= 1u << (j & 31);   // the traceback must look this node up
     if ((j & 31) == 31) { scr.w(Lp->o_nt + (j >> 5)) = nt; nt = 0; }
     if (hasR) { lastR = j; gR = bG; }
     if (hasC) { lastC = j; gC = bG; }
   }
   if (nx & 31) scr.w(Lp->o_nt + (nx >> 5)) = nt;
+  return nrings;
 }
 
 template <bool GENERIC_SUB>
@@ -627,7 +718,8 @@ struct Phase2 {
   static constexpr bool kBanded = false;
   static constexpr int kSetWords = kSlotWords;
   static EL_HD void make_layout(Layout2 &L, int N1, int LU) { make_layout2(L, N1, LU); }
-  LaneScratch scr;
+  LaneScratch scr;    // slow part of the layout (global scratch)
+  LaneScratch fs;     // fast part (shared-memory arena, or global scratch at o_fast)
   uint32_t *bset;     // two frontier-set slots of kSlotWords words, + lane (shared memory on the device)
   Scoring sc;
   const Layout2 *Lp;  // layout of the current group (shared memory on the device)
@@ -635,7 +727,7 @@ struct Phase2 {
   EL_HD uint32_t *rec(uint32_t j) const { return scr.at(Lp->o_nodes + j * Lp->rec_words); }  // field f at [f*32]
 
   static EL_HD void put_row0(uint32_t *p, int bS, int bG) { p[R2_BS * 32] = (uint32_t)bS; p[R2_BG * 32] = (uint32_t)bG; }
-  EL_HDN void prepare(const uint16_t *nodes, int nx) const { prepare_nodes(*this, nodes, nx); }
+  EL_HDN int prepare(const uint16_t *nodes, int nx) const { return prepare_nodes(*this, nodes, nx); }
 
   // ---- DP2: P1 columns x lin(unc) rows, one band (align_lpo_po2.c:269-433) ----
   template <int R>
@@ -643,7 +735,7 @@ struct Phase2 {
     const int r0 = b * kBand;
     uint32_t yw[R / 4];
 #pragma unroll
-    for (int k = 0; k < R / 4; ++k) yw[k] = scr.w(Lp->o_unc + (r0 >> 2) + k);
+    for (int k = 0; k < R / 4; ++k) yw[k] = fs.w(Lp->f_unc + (r0 >> 2) + k);
     int S[R], G[R], h = 0;   // set A
 #pragma unroll
     for (int r = 0; r < R; ++r) S[r] = G[r] = 0;
@@ -699,11 +791,12 @@ struct Phase2 {
     return best;
   }
 
-  // ---- traceback (align_lpo_po2.c:108-168): fills the x2y field of the node records ----
+  // ---- traceback (align_lpo_po2.c:108-168): marks the aligned pairs in the bitmaps ----
   // The walk reads one moves word per step; the words of the next three columns of the band
-  // are loaded ahead.  Only nodes flagged in the bitmap need their record looked up.
-  EL_HDN void traceback(int ly, int best_j) const {
+  // are loaded ahead.  Only nodes flagged in the o_nt bitmap need their record looked up.
+  EL_HDN void traceback(int nx, int ly, int best_j, AlignBits &al) const {
     const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
+    al.clear(nx, ly);
     int j = best_j, r = ly - 1;
     uint32_t ntw = 0;
     int ntbase = -1;
@@ -714,7 +807,7 @@ struct Phase2 {
       uint32_t w0 = pm[0], w1 = j >= 1 ? pm[-step] : 0, w2 = j >= 2 ? pm[-2 * step] : 0, w3 = j >= 3 ? pm[-3 * step] : 0;
       for (;;) {
         const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
-        if (kind & 2u) p[R2_X2Y * 32] = (uint32_t)r;
+        if (kind & 2u) al.mark(j, r);
         bool jump = false;
         if (kind) {  // match or X-gap: step to a predecessor of j
           if ((j >> 5) != ntbase) { ntbase = j >> 5; ntw = scr.w(Lp->o_nt + ntbase); }
@@ -740,19 +833,22 @@ struct Phase2 {
         if (jump || j < 0 || r < 0 || (r >> 4) != b) break;
       }
     }
+    al.finish();
   }
 
-  static constexpr uint32_t kRecNode = R2_NODE, kRecX2Y = R2_X2Y, kRecPred = R2_PRED;
+  static constexpr uint32_t kRecNode = R2_NODE, kRecPred = R2_PRED;
   EL_HD uint32_t *node_rec(int j) const { return rec((uint32_t)j); }
-  EL_HDN int fuse_emit(int n1, int lu) const { return fuse_emit_rows(*this, n1, lu); }
+  EL_HDN int fuse_emit(const AlignBits &al, int n1, int lu, const RowSink &out) const { return fuse_emit_rows(*this, al, n1, lu, out); }
+  EL_HD AlignBits bits() const { return AlignBits{fs, Lp->f_xb, Lp->f_yb}; }
 
-  EL_HDN int run_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2) const {
-    scr.pack_codes(sc.tab, unc, lu, Lp->o_unc);
-    prepare(p1, n1);
+  // everything up to the traceback; returns the number of MSA columns (the rows are emitted once their place is known)
+  EL_HDN int align_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2, AlignBits &al) const {
+    fs.pack_codes(sc.tab, unc, lu, Lp->f_unc);
+    const int nrings = prepare(p1, n1);
     int bj;
     s2 = dp(n1, lu, bj);
-    traceback(lu, bj);
-    return fuse_emit(n1, lu);
+    traceback(n1, lu, bj, al);
+    return columns_of(nrings, lu, al.nmatch);
   }
 };
 
@@ -829,6 +925,14 @@ __device__ __forceinline__ void phase1_epilogue(const PoaArgs &a, bool active, i
 }
 #endif
 
+// the per-warp arena in shared memory (dynamic: the host sizes it so that the kernel's register-bound residency is kept)
+extern __shared__ uint32_t s_arena[];
+// fast part of the group's layout: the arena when it fits, else global scratch
+template <class L>
+__device__ __forceinline__ uint32_t *fast_base(const PoaArgs &a, const L &layout, uint32_t *lane_scratch, int lane) {
+  return layout.f_total <= a.arena_words ? s_arena + lane : lane_scratch + (size_t)layout.o_fast * 32;
+}
+
 // PH = Phase1<GENERIC_SUB> (INT32 cells) or Phase1P (poa_packed.cuh: two 16-bit cells per instruction)
 template <class PH, int MIN_WARPS>
 __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const SymbolTables *g_tab) {
@@ -860,6 +964,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
       if constexpr (PH::kBanded) group_band(c.bw, banded && mr + mc <= a.band_span, a.band_w + (mc >> 4), active, lc - lr);
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
+    c.fs.base = fast_base(a, s_layout, c.scr.base, lane);
     int s1 = 0, spcode = 0, n1 = 0;
     bool exact = true;
     if (active) n1 = c.run_window(a.ref + ro, lr, a.cor + co, lc, a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), s1, spcode, exact);
@@ -885,12 +990,12 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
 }
 
 #ifdef __CUDACC__
-// The MSA rows of a group leave the scratch: output space is allocated with a warp prefix sum of 3*stride and ONE
-// atomic per warp; every lane then copies its three rows (window w, nring columns) as 32-bit words.
-__device__ __forceinline__ void store_window_rows(const PoaArgs &a, const LaneScratch &scr, uint32_t o_rows, uint32_t row_words,
-                                                  bool active, int w, int nring) {
+// Output space for the MSA rows of a group: a warp prefix sum of 3*stride and ONE atomic per warp.  Every lane (active or
+// not) calls it; an active lane gets the sink of its window's three rows (nring columns), or false when the caller's row
+// buffer is too small (the error flag is then set).
+__device__ __forceinline__ bool alloc_window_rows(const PoaArgs &a, bool active, int w, int nring, RowSink &out) {
   const int lane = threadIdx.x;
-  const int stride = (nring + 3) & ~3;
+  const int stride = active ? (nring + 3) & ~3 : 0;
   const int bytes = 3 * stride;
   int incl = bytes;
   for (int d = 1; d < 32; d <<= 1) {
@@ -899,28 +1004,21 @@ __device__ __forceinline__ void store_window_rows(const PoaArgs &a, const LaneSc
   }
   const int total = __shfl_sync(EL_WARP_FULL, incl, 31);
   unsigned long long wbase = 0;
-  if (lane == 0) wbase = atomicAdd(a.rows_cursor, (unsigned long long)total);
+  if (lane == 0 && total) wbase = atomicAdd(a.rows_cursor, (unsigned long long)total);
   wbase = __shfl_sync(EL_WARP_FULL, wbase, 0);
-  if (active) {
-    const int64_t off = (int64_t)wbase + incl - bytes;
-    a.row_off[w] = off;
-    a.row_stride[w] = stride;
-    if (off + bytes > a.rows_cap) atomicExch(a.error_flag, 1);
-    else {
-      uint32_t *dst = reinterpret_cast<uint32_t *>(a.rows_out + off);
-      const int sw4 = stride >> 2;
-      for (int s = 0; s < 3; ++s) {
-        const uint32_t *srow = scr.at(o_rows + s * row_words);
-        uint32_t *drow = dst + s * sw4;
-#pragma unroll 4
-        for (int k = 0; k < sw4; ++k) drow[k] = srow[k * 32];
-      }
-    }
-  }
+  if (!active) return false;
+  const int64_t off = (int64_t)wbase + incl - bytes;
+  a.row_off[w] = off;
+  a.row_stride[w] = stride;
+  if (off + bytes > a.rows_cap) { atomicExch(a.error_flag, 1); return false; }
+  out.r0 = reinterpret_cast<uint32_t *>(a.rows_out + off);
+  out.r1 = out.r0 + (stride >> 2);
+  out.r2 = out.r1 + (stride >> 2);
+  return true;
 }
 
 #endif
-// PH = Phase2<GENERIC_SUB> (INT32 cells) or Phase2P (poa_packed.cuh)
+// PH = Phase2<GENERIC_SUB> (INT32 cells), Phase2D (poa_dual.cuh) or Phase2L (poa_packed.cuh)
 template <class PH, int MIN_WARPS>
 __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const SymbolTables *g_tab) {
   constexpr bool GENERIC_SUB = PH::kGenericSub;
@@ -954,11 +1052,13 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
       if constexpr (PH::kBanded) group_band(c.bw, banded && mn + mu <= a.band_span, a.band_w + (mu >> 3), active, lu - n1);
     }
     if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
+    c.fs.base = fast_base(a, s_layout, c.scr.base, lane);
     bool exact = true;
+    AlignBits al = c.bits();
     if (active) {
       int s2;
-      if constexpr (PH::kLinear) nring = c.run_linear(a.ref + ro, n1, a.unc + uo, lu, s2, exact);   // P1 = lin(ref): no node list needed
-      else nring = c.run_window(a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), n1, a.unc + uo, lu, s2);
+      if constexpr (PH::kLinear) nring = c.align_linear(a.ref + ro, n1, a.unc + uo, lu, s2, exact, al);   // P1 = lin(ref): no node list needed
+      else nring = c.align_window(a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w), n1, a.unc + uo, lu, s2, al);
       if (exact) {
         a.nring[w] = nring;
         if (a.score2) a.score2[w] = s2;
@@ -969,7 +1069,8 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
       } else nring = 0;
     }
     __syncwarp();
-    store_window_rows(a, c.scr, s_layout.o_rows, s_layout.row_words, active && exact, w, nring);
+    RowSink out;
+    if (alloc_window_rows(a, active && exact, w, nring, out)) c.fuse_emit(al, n1, lu, out);
     __syncwarp();
     return active && !exact;
   };

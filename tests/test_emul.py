@@ -9,12 +9,13 @@ import pytest
 from conftest import GOLDEN_SETS, parse_dump
 
 
-@pytest.mark.parametrize("mode", ["int32", "packed", "packed-general", "dual-general", "coop"])
+@pytest.mark.parametrize("mode", ["int32", "packed", "dual-general", "coop"])
 @pytest.mark.parametrize("name", GOLDEN_SETS)
 def test_emulated_kernel_equals_reference(golden_dir, emul_bin, name, mode, tmp_path):
-    """mode packed: the 16-bit packed kernels (poa_packed.cuh) wherever the library would use them (Phase1P, Phase2L for
-    windows whose P1 is linear, Phase2P for the rest); packed-general: Phase2P for every window; packed now means Phase2D (dual-frontier packed, poa_dual.cuh) for the general windows and dual-general Phase2D for every window; coop: DP2 of every window
-    through the warp-cooperative wavefront of poa_coop.cuh (32 lanes of 8 rows, emulated lane by lane)"""
+    """mode packed: the 16-bit packed kernels wherever the library would use them (Phase1P, Phase2L for windows whose P1 is
+    linear, the dual-frontier Phase2D of poa_dual.cuh for the rest); dual-general: Phase2D for every window; coop: both DPs
+    of every window through the warp-cooperative wavefront of poa_coop.cuh (32 lanes of 8 rows, emulated lane by lane).
+    The emulator also checks that the number of MSA columns announced before the fusion equals the number emitted."""
     d = golden_dir
     pir, sc = str(tmp_path / "e.pir"), str(tmp_path / "e.scores")
     cmd = [emul_bin, d + "/blosum80.mat", "%s/%s.ref.fa" % (d, name), "%s/%s.cor.fa" % (d, name),
@@ -70,7 +71,7 @@ def test_emulated_kernel_rejects_unsupported_matrix(golden_dir, emul_bin, tmp_pa
     assert rc == 3
 
 
-@pytest.mark.parametrize("mode", ["int32", "packed", "packed-general", "dual-general", "coop"])
+@pytest.mark.parametrize("mode", ["int32", "packed", "dual-general", "coop"])
 def test_emulated_kernel_long_windows(golden_dir, emul_bin, mode, tmp_path):
     """many bands, 8- and 16-row last bands, long placeholder / trimmed windows, vs the oracle"""
     from oracle import oracle, synth
