@@ -84,11 +84,11 @@ struct Layout2 {            // phase 2: windows with len(P1) / unc length up to 
   uint32_t rec_words;
   uint32_t o_ord;           // two words per (combined node, band): winning predecessor ordinals
   uint32_t ord_bands;
-  uint32_t o_nt;            // bitmap: node j has a predecessor list other than [j-1]
   uint32_t o_tmp;           // N1 letter codes (the warp-cooperative kernel rebuilds lin(ref) from them)
   uint32_t o_fast;
   uint32_t f_unc;           // fast: packed symbol codes of unc
   uint32_t f_xb, f_yb;      // fast: alignment bitmaps (node j of P1 / letter r of unc is aligned)
+  uint32_t f_nt;            // fast: bitmap, node j has a predecessor list other than [j-1]
   uint32_t f_total;
   uint32_t total;
 };
@@ -112,13 +112,13 @@ EL_HD void make_layout2(Layout2 &L, int N1, int LU) {
   L.f_unc = f; f += cdiv_u(LU, 4) + 4;
   L.f_xb = f; f += cdiv_u(N1, 32) + 1;
   L.f_yb = f; f += cdiv_u(LU, 32) + 1;
+  L.f_nt = f; f += cdiv_u(N1, 32) + 1;
   L.f_total = f;
   uint32_t o = 0;
   L.rec_words = R2_MOVES + nb;
   L.o_nodes = o; o += (uint32_t)N1 * L.rec_words;
   L.ord_bands = nb;
   L.o_ord = o; o += ((uint32_t)N1 / 2 + 2) * nb * 2;            // combined nodes carry ref AND cor: at most N1/2, + 2 initial ones
-  L.o_nt = o; o += cdiv_u(N1, 32) + 1;
   L.o_tmp = o; o += cdiv_u(N1, 4) + 1;
   L.o_fast = o; o += f;
   L.total = o;
@@ -343,40 +343,22 @@ EL_HD void prefetch_l1(const void *p) {
 // (align_lpo_po2.c:158-165 fills two integer maps.)  An alignment path is monotone in both sequences: the k-th aligned node
 // of x is aligned to the k-th aligned letter of y, so "node j is aligned" / "letter r is aligned" bits carry the same
 // information in 1/32 of the space -- small enough for the shared-memory arena.  The walk visits nodes and letters in
-// decreasing order, so every bitmap word is completed once and stored once; clear() zeroes the words it may never reach.
+// decreasing order and sets the bits in place (the bitmaps are a few words, in shared memory for all but the longest windows).
 struct AlignBits {
   LaneScratch st;
   uint32_t ox, oy;
-  uint32_t xw = 0, yw = 0;
-  int xi = -1, yi = -1, nmatch = 0;
+  int nmatch = 0;          // aligned pairs (set by the traceback)
   EL_HD void clear(int nx, int ny) const {
     for (uint32_t k = 0; k < cdiv_u((uint32_t)nx, 32); ++k) st.w(ox + k) = 0;
     for (uint32_t k = 0; k < cdiv_u((uint32_t)ny, 32); ++k) st.w(oy + k) = 0;
   }
   EL_HD void mark(int j, int r) {
-    if ((j >> 5) != xi) { if (xi >= 0) st.w(ox + (uint32_t)xi) = xw; xi = j >> 5; xw = 0; }
-    if ((r >> 5) != yi) { if (yi >= 0) st.w(oy + (uint32_t)yi) = yw; yi = r >> 5; yw = 0; }
-    xw |= 1u << (j & 31);
-    yw |= 1u << (r & 31);
+    st.w(ox + (uint32_t)(j >> 5)) |= 1u << (j & 31);
+    st.w(oy + (uint32_t)(r >> 5)) |= 1u << (r & 31);
     ++nmatch;
-  }
-  EL_HD void finish() {
-    if (xi >= 0) st.w(ox + (uint32_t)xi) = xw;
-    if (yi >= 0) st.w(oy + (uint32_t)yi) = yw;
   }
   EL_HD bool x_at(int j) const { return (st.w(ox + (uint32_t)(j >> 5)) >> (j & 31)) & 1u; }
 };
-// forward reader of one bitmap: sequential positions reuse the word in a register
-struct BitCursor {
-  LaneScratch st;
-  uint32_t off, word = 0;
-  int idx = -1;
-  EL_HD bool at(int i) {
-    if ((i >> 5) != idx) { idx = i >> 5; word = st.w(off + (uint32_t)idx); }
-    return (word >> (i & 31)) & 1u;
-  }
-};
-
 // where the three MSA rows of a window go: 32-bit words, 4 columns each (the caller's row buffer on the device: the
 // fusion writes its output once, in place -- no staging copy)
 struct RowSink {
@@ -388,9 +370,11 @@ struct RowSink {
 // ref and cor are identical (P1 is linear), else 1 + 3*min(pos/2, 31) + type of the first node that does not
 // carry both letters (type 0: ref only, 1: cor only followed by its ref partner = a
 // substitution, 2: cor only = an insertion).
+// One uniform step per letter of ref or unaligned letter of cor (an unaligned letter of cor goes before the next ALIGNED
+// letter of ref, or after the last one): no inner loops, so the lanes of a warp stay in step.
 EL_HDN inline int fuse1(const LaneScratch &cd, uint32_t o_ref, uint32_t o_cor, const AlignBits &al, int lr, int lc,
                       uint16_t *out, int &spcode) {
-  int n = 0, iy = 0, sp = -1, sptype = 0;
+  int n = 0, ix = 0, iy = 0, sp = -1, sptype = 0;
   uint64_t *out4 = reinterpret_cast<uint64_t *>(out);   // 4 nodes per store (the list is 8-byte aligned)
   uint64_t acc = 0;
   auto put = [&](uint32_t v) {
@@ -398,34 +382,24 @@ EL_HDN inline int fuse1(const LaneScratch &cd, uint32_t o_ref, uint32_t o_cor, c
     if ((n & 3) == 3) { out4[n >> 2] = acc; acc = 0; }
     ++n;
   };
-  uint32_t yw = 0;
-  int ywi = -1;
-  auto ycode = [&](int i) { if ((i >> 2) != ywi) { ywi = i >> 2; yw = cd.w(o_cor + (uint32_t)ywi); } return (yw >> ((i & 3) * 8)) & 0xffu; };
-  auto cor_only = [&](int iy_) {
-    put(ycode(iy_) | NF_COR | (iy_ == 0 ? NF_INITIAL : 0u) | (iy_ == lc - 1 ? NF_FINAL : 0u));
-  };
-  BitCursor xb{al.st, al.ox}, yb{al.st, al.oy};
-  uint32_t xw = 0;
-  for (int ix = 0; ix < lr; ++ix) {
-    const bool aligned = xb.at(ix);
-    if ((ix & 3) == 0) xw = cd.w(o_ref + (ix >> 2));
-    const int xl = xw & 0xff; xw >>= 8;
-    if (aligned)   // its partner is the next aligned letter of cor: the unaligned ones before it come first
-      while (iy < lc && !yb.at(iy)) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
-    uint32_t fl = NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u);
-    if (aligned && iy < lc) {
-      const int yl = (int)ycode(iy);
-      const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
-      if (yl == xl) fl |= yf;  // identical letters share the node
-      else {                   // own node just before x, same ring
-        if (sp < 0) { sp = n; sptype = 1; }
-        put((uint32_t)yl | yf); fl |= NF_SAMERING;
-      }
-      ++iy;
-    } else if (sp < 0) { sp = n; sptype = 0; }
-    put((uint32_t)xl | fl);
+  while (ix < lr || iy < lc) {
+    const bool xa = ix < lr && ((al.st.w(al.ox + (uint32_t)(ix >> 5)) >> (ix & 31)) & 1u);
+    const bool ya = iy < lc && ((al.st.w(al.oy + (uint32_t)(iy >> 5)) >> (iy & 31)) & 1u);
+    const bool yonly = iy < lc && !ya && (ix >= lr || xa);
+    const uint32_t xl = (cd.w(o_ref + (uint32_t)(ix >> 2)) >> ((ix & 3) * 8)) & 0xffu;
+    const uint32_t yl = (cd.w(o_cor + (uint32_t)(iy >> 2)) >> ((iy & 3) * 8)) & 0xffu;
+    const uint32_t yf = NF_COR | (iy == 0 ? NF_INITIAL : 0u) | (iy == lc - 1 ? NF_FINAL : 0u);
+    const bool diff = !yonly && xa && yl != xl;                // aligned, different letters: own node just before x, same ring
+    if (yonly || diff) {
+      if (sp < 0) { sp = n; sptype = yonly ? 2 : 1; }
+      put(yl | yf);
+    }
+    if (!yonly) {
+      if (!xa && sp < 0) { sp = n; sptype = 0; }
+      put(xl | NF_REF | (ix == 0 ? NF_INITIAL : 0u) | (ix == lr - 1 ? NF_FINAL : 0u) | (xa && !diff ? yf : 0u) | (diff ? NF_SAMERING : 0u));
+    }
+    ix += !yonly; iy += yonly || xa;
   }
-  while (iy < lc) { if (sp < 0) { sp = n; sptype = 2; } cor_only(iy); ++iy; }
   if (n & 3) out4[n >> 2] = acc;
   spcode = sp < 0 ? 0 : 1 + 3 * ((sp >> 1) < 31 ? (sp >> 1) : 31) + sptype;
   return n;
@@ -507,7 +481,6 @@ struct Phase1 {
         if (j < 0 || r < 0 || (r >> 4) != b) break;
       }
     }
-    al.finish();
   }
 
   EL_HDN int run_window(const uint8_t *ref, int lr, const uint8_t *cor, int lc, uint16_t *p1_out, int &s1, int &spcode, bool &exact) const {
@@ -606,7 +579,7 @@ EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, con
   const auto *Lp = ph.Lp;
   constexpr uint32_t kNode = PH::kRecNode;
   const uint8_t *sym = ph.sc.tab->sym;
-  int iy = 0, col = -1, prev_key = -1, rs = 0;
+  int ix = 0, iy = 0, col = -1, prev_key = -1, rs = 0;
   uint32_t c0 = '.', c1 = '.', c2 = '.';
   uint32_t w0 = 0, w1 = 0, w2 = 0;
   auto flush = [&]() {
@@ -618,44 +591,42 @@ EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, con
   };
   auto emit = [&](int key, uint32_t letter, uint32_t srcmask) {
     if (key != prev_key) { flush(); ++col; c0 = c1 = c2 = '.'; prev_key = key; }
-    const uint32_t ch = sym[letter];
+    const uint32_t ch = sym[letter & 31u];
     if (srcmask & 1u) c0 = ch;
     if (srcmask & 2u) c1 = ch;
     if (srcmask & 4u) c2 = ch;
   };
-  uint32_t yw = 0;
-  int ywi = -1;
-  auto ycode = [&](int i) { if ((i >> 2) != ywi) { ywi = i >> 2; yw = fs.w(Lp->f_unc + (uint32_t)ywi); } return (yw >> ((i & 3) * 8)) & 0xffu; };
-  BitCursor xb{al.st, al.ox}, yb{al.st, al.oy};
   const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
   const uint32_t *pr = ph.node_rec(0);
-  // nodes ix, ix+1 in registers, ix+2 in flight
-  uint32_t ra0 = pr[kNode * 32], ra1 = n1 > 1 ? pr[step + kNode * 32] : 0;
-  for (int ix = 0; ix < n1; ++ix, pr += step) {
-    const uint32_t ra = ra0, ra_next = ra1;
-    ra0 = ra1;
-    if (ix + 2 < n1) ra1 = pr[2 * step + kNode * 32];
-    if (!(ra & NF_SAMERING)) rs = ix;
-    const bool aligned = xb.at(ix);
-    // scan x's ring from ix on: unaligned y letters go before the first aligned member (whose partner is the next aligned letter)
-    {
-      bool any = aligned;
-      if (!any && ix + 1 < n1 && (ra_next & NF_SAMERING)) {
-        any = al.x_at(ix + 1);
-        for (int ir = ix + 2; !any && ir < n1 && (ph.node_rec(ir)[kNode * 32] & NF_SAMERING); ++ir) any = al.x_at(ir);
+  // nodes ix, ix+1 in registers, ix+2 in flight.  One uniform step per node of P1 or unaligned letter of unc (which goes
+  // before the first aligned member of the next ring that has one, or after the last node): no inner loops.
+  uint32_t ra0 = pr[kNode * 32], ra1 = n1 > 1 ? pr[step + kNode * 32] : 0, ra2 = n1 > 2 ? pr[2 * step + kNode * 32] : 0;
+  while (ix < n1 || iy < lu) {
+    const bool xa = ix < n1 && al.x_at(ix);
+    const bool ya = iy < lu && ((fs.w(al.oy + (uint32_t)(iy >> 5)) >> (iy & 31)) & 1u);
+    // is a member of x's ring, from ix on, aligned?  (a ring of P1 has at most two nodes; longer ones are walked all the same)
+    bool any = xa;
+    if (!any && ix + 1 < n1 && (ra1 & NF_SAMERING)) {
+      any = al.x_at(ix + 1);
+      for (int ir = ix + 2; !any && ir < n1 && (ph.node_rec(ir)[kNode * 32] & NF_SAMERING); ++ir) any = al.x_at(ir);
+    }
+    const uint32_t yl = (fs.w(Lp->f_unc + (uint32_t)(iy >> 2)) >> ((iy & 3) * 8)) & 0xffu;
+    if (iy < lu && !ya && (ix >= n1 || any)) { emit(n1 + iy, yl, 4u); ++iy; }
+    else {
+      const uint32_t ra = ra0;
+      if (!(ra & NF_SAMERING)) rs = ix;
+      uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
+      if (xa) {
+        if (yl == (ra & 0xffu)) mask |= 4u;
+        else emit(rs, yl, 4u);
+        ++iy;
       }
-      if (any) while (iy < lu && !yb.at(iy)) { emit(n1 + iy, ycode(iy), 4u); ++iy; }
+      emit(rs, ra & 0xffu, mask);
+      ++ix; pr += step;
+      ra0 = ra1; ra1 = ra2;
+      ra2 = ix + 2 < n1 ? pr[2 * step + kNode * 32] : 0;
     }
-    uint32_t mask = ((ra & NF_REF) ? 1u : 0u) | ((ra & NF_COR) ? 2u : 0u);
-    if (aligned && iy < lu) {
-      const uint32_t yl = ycode(iy);
-      if (yl == (ra & 0xffu)) mask |= 4u;
-      else emit(rs, yl, 4u);
-      ++iy;
-    }
-    emit(rs, ra & 0xffu, mask);
   }
-  while (iy < lu) { emit(n1 + iy, ycode(iy), 4u); ++iy; }
   flush();
   if ((col & 3) != 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w1; out.r2[col >> 2] = w2; }
   return col + 1;
@@ -667,7 +638,6 @@ EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, con
 // predecessors (for the traceback) and row -1 of the DP as the first boundary row.  Returns the number of align rings.
 template <class PH>
 EL_HDN int prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
-  const LaneScratch &scr = ph.scr;
   const auto *Lp = ph.Lp;
   int lastR = -1, lastC = -1, gR = 0, gC = 0, nslot = 0, nrings = 0;
   uint32_t *p = ph.node_rec(0);
@@ -702,11 +672,11 @@ EL_HDN int prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
     p[PH::kRecPred * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
     PH::put_row0(p, bS, bG);
     if (pA != j - 1 || (ra & (NF_VIRT | NF_TWO))) nt |= 1u << (j & 31);   // the traceback must look this node up
-    if ((j & 31) == 31) { scr.w(Lp->o_nt + (j >> 5)) = nt; nt = 0; }
+    if ((j & 31) == 31) { ph.fs.w(Lp->f_nt + (j >> 5)) = nt; nt = 0; }
     if (hasR) { lastR = j; gR = bG; }
     if (hasC) { lastC = j; gC = bG; }
   }
-  if (nx & 31) scr.w(Lp->o_nt + (nx >> 5)) = nt;
+  if (nx & 31) ph.fs.w(Lp->f_nt + (nx >> 5)) = nt;
   return nrings;
 }
 
@@ -792,48 +762,43 @@ struct Phase2 {
   }
 
   // ---- traceback (align_lpo_po2.c:108-168): marks the aligned pairs in the bitmaps ----
-  // The walk reads one moves word per step; the words of the next three columns of the band
-  // are loaded ahead.  Only nodes flagged in the o_nt bitmap need their record looked up.
+  // One uniform step per cell of the path (load the moves word of (node, band), decode, mark, move; profiles/r2b: a walk
+  // with an inner loop per band ran ~4x the instructions at warp level).  Only nodes flagged in the f_nt bitmap need their
+  // record looked up; the lines of the cells ahead are requested into L1 as the walk goes.
   EL_HDN void traceback(int nx, int ly, int best_j, AlignBits &al) const {
     const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
     al.clear(nx, ly);
-    int j = best_j, r = ly - 1;
-    uint32_t ntw = 0;
-    int ntbase = -1;
+    int j = best_j, r = ly - 1, nmatch = 0;
     while (j >= 0 && r >= 0) {
       const int b = r >> 4;
-      uint32_t *p = rec((uint32_t)j);
+      const uint32_t *p = rec((uint32_t)j);
       const uint32_t *pm = p + (R2_MOVES + b) * 32;
-      uint32_t w0 = pm[0], w1 = j >= 1 ? pm[-step] : 0, w2 = j >= 2 ? pm[-2 * step] : 0, w3 = j >= 3 ? pm[-3 * step] : 0;
-      for (;;) {
-        const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
-        if (kind & 2u) al.mark(j, r);
-        bool jump = false;
-        if (kind) {  // match or X-gap: step to a predecessor of j
-          if ((j >> 5) != ntbase) { ntbase = j >> 5; ntw = scr.w(Lp->o_nt + ntbase); }
-          if ((ntw >> (j & 31)) & 1u) {
-            const uint32_t ra = p[R2_NODE * 32];
-            int ord = 0;
-            if (ra & (NF_VIRT | NF_TWO)) {
-              const uint32_t *po = scr.at(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
-              ord = (int)((((kind & 2u) ? po[0] : po[32]) >> (2 * (r & 15))) & 3u);
-            }
-            const uint32_t pr = p[R2_PRED * 32];
-            const int pA = (pr & 0xffffu) == 0xffffu ? -1 : (int)(pr & 0xffffu), pB = (pr >> 16) == 0xffffu ? -1 : (int)(pr >> 16);
-            if (ra & NF_VIRT) j = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
-            else j = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
-            jump = true;
-          } else {
-            --j; p -= step; pm -= step;
-            w0 = w1; w1 = w2; w2 = w3;
-            w3 = j >= 3 ? pm[-3 * step] : 0;
-          }
-        }
-        if (kind != 1u) --r;  // match or Y-gap: step up
-        if (jump || j < 0 || r < 0 || (r >> 4) != b) break;
+      const uint32_t w0 = *pm;
+      if (j >= 6) prefetch_l1(pm - 6 * step);
+      if (b > 0 && j >= 2) prefetch_l1(pm - 2 * step - 32);
+      const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
+      if (kind & 2u) {
+        al.st.w(al.ox + (uint32_t)(j >> 5)) |= 1u << (j & 31);
+        al.st.w(al.oy + (uint32_t)(r >> 5)) |= 1u << (r & 31);
+        ++nmatch;
       }
+      if (kind) {  // match or X-gap: step to a predecessor of j
+        if ((fs.w(Lp->f_nt + (uint32_t)(j >> 5)) >> (j & 31)) & 1u) {
+          const uint32_t ra = p[R2_NODE * 32];
+          int ord = 0;
+          if (ra & (NF_VIRT | NF_TWO)) {
+            const uint32_t *po = scr.at(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
+            ord = (int)((((kind & 2u) ? po[0] : po[32]) >> (2 * (r & 15))) & 3u);
+          }
+          const uint32_t pr = p[R2_PRED * 32];
+          const int pA = (pr & 0xffffu) == 0xffffu ? -1 : (int)(pr & 0xffffu), pB = (pr >> 16) == 0xffffu ? -1 : (int)(pr >> 16);
+          if (ra & NF_VIRT) j = (ord == 0) ? -1 : (ord == 1 ? pA : pB);
+          else j = (ord == 0) ? pA : pB;  // pA == -1 when the list is the virtual link alone
+        } else --j;
+      }
+      if (kind != 1u) --r;  // match or Y-gap: step up
     }
-    al.finish();
+    al.nmatch = nmatch;
   }
 
   static constexpr uint32_t kRecNode = R2_NODE, kRecPred = R2_PRED;

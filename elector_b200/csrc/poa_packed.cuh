@@ -248,34 +248,34 @@ struct Phase1P {
     return band<R>(lr, ly, nb - 1, true, bw);
   }
 
-  // traceback (align_lpo_po2.c:108-168): marks the aligned pairs in the bitmaps.  One moves word per column step, the
-  // words of the next three columns in registers; the lines of the columns further ahead, in this band and in the one
-  // above, are requested into L1 as the walk goes (the moves of a launch exceed the L2: profiles/r2a, top stall of this loop)
+  // traceback (align_lpo_po2.c:108-168): marks the aligned pairs in the bitmaps.  One uniform step per cell of the path
+  // (load the moves word of (node, band), decode, mark, move): the lanes of a warp stay in lock step whatever their paths
+  // do -- a walk with a register queue of moves words and an inner loop per band executed ~4x the instructions at warp
+  // level (profiles/r2b: divergence, not work).  The lines of the cells ahead are requested into L1 as the walk goes.
   template <int R>
   EL_HDN void traceback(int lr, int ly, AlignBits &al) const {
-    const ptrdiff_t step = (ptrdiff_t)Lp->rec_words * 32;
     al.clear(lr, ly);
+    const uint32_t *base = rec(0) + P1_MOVES * 32;             // moves word of (node j, band b) at base[(j * rec_words + b) * 32]
+    const int rw = (int)Lp->rec_words;
     int j = lr - 1, r = ly - 1;
+    int b = r / (2 * R), rr = r - b * 2 * R;
+    int nmatch = 0;
     while (j >= 0 && r >= 0) {
-      const int b = r / (2 * R);
-      int rr = r - b * 2 * R;
-      const uint32_t *pm = rec(j) + (P1_MOVES + b) * 32;
-      uint32_t w0 = pm[0], w1 = j >= 1 ? pm[-step] : 0, w2 = j >= 2 ? pm[-2 * step] : 0, w3 = j >= 3 ? pm[-3 * step] : 0;
-      for (;;) {
-        const uint32_t kind = (w0 >> (rr < R ? 2 * rr : 16 + 2 * (rr - R))) & 3u;   // bit 1 match, bit 0 X-gap
-        if (kind & 2u) al.mark(j, r);
-        if (kind != 1u) { --r; --rr; }
-        if (kind) {
-          --j; pm -= step;
-          w0 = w1; w1 = w2; w2 = w3;
-          w3 = j >= 3 ? pm[-3 * step] : 0;
-          if (j >= 8) prefetch_l1(pm - 8 * step);
-          if (b > 0 && j >= 2) prefetch_l1(pm - 2 * step - 32);
-        }
-        if (j < 0 || r < 0 || rr < 0) break;
+      const uint32_t *pm = base + (ptrdiff_t)(j * rw + b) * 32;
+      const uint32_t w = *pm;
+      if (j >= 6) prefetch_l1(pm - (ptrdiff_t)6 * rw * 32);
+      if (b > 0 && j >= 2) prefetch_l1(pm - (ptrdiff_t)2 * rw * 32 - 32);
+      const uint32_t kind = (w >> (rr < R ? 2 * rr : 16 + 2 * (rr - R))) & 3u;   // bit 1 match, bit 0 X-gap
+      if (kind & 2u) {
+        al.st.w(al.ox + (uint32_t)(j >> 5)) |= 1u << (j & 31);
+        al.st.w(al.oy + (uint32_t)(r >> 5)) |= 1u << (r & 31);
+        ++nmatch;
       }
+      const int dr = kind != 1u, dj = kind != 0u;
+      j -= dj; r -= dr; rr -= dr;
+      if (rr < 0) { rr += 2 * R; --b; }
     }
-    al.finish();
+    al.nmatch = nmatch;
   }
 
   template <int R>
@@ -337,32 +337,29 @@ struct Phase2L {
     return d;
   }
 
-  // rows of the MSA from the alignment bitmaps of the traceback, straight to their place; returns nring
+  // rows of the MSA from the alignment bitmaps of the traceback, straight to their place; returns nring.
+  // Column-driven and branch-free: a column is a node of lin(ref) (with the letter of unc aligned to it, if any) or an
+  // unaligned letter of unc, which goes before the next ALIGNED node or after the last node (lpo.c:413-463 for a linear x).
+  // The corrected row of these windows is the reference row.
   EL_HDN int fuse_emit(const AlignBits &al, int n1, int lu, const RowSink &out) const {
     const uint8_t *sym = sc.tab->sym;
-    int col = 0, iy = 0;
-    uint32_t w0 = 0, w1 = 0, w2 = 0;
-    auto put = [&](uint32_t c0, uint32_t c1, uint32_t c2) {
+    int col = 0, ix = 0, iy = 0;
+    uint32_t w0 = 0, w2 = 0;
+    while (ix < n1 || iy < lu) {
+      const bool xa = ix < n1 && ((fs.w(al.ox + (uint32_t)(ix >> 5)) >> (ix & 31)) & 1u);
+      const bool ya = iy < lu && ((fs.w(al.oy + (uint32_t)(iy >> 5)) >> (iy & 31)) & 1u);
+      const bool yonly = iy < lu && !ya && (ix >= n1 || xa);
+      const bool takey = yonly || xa;                          // an aligned node's partner is the current letter of unc
+      const uint32_t xc = sym[(fs.w(Lp->f_ref + (uint32_t)(ix >> 2)) >> ((ix & 3) * 8)) & 31u];
+      const uint32_t yc = sym[(fs.w(Lp->f_cor + (uint32_t)(iy >> 2)) >> ((iy & 3) * 8)) & 31u];
       const int sh = (col & 3) * 8;
-      w0 |= c0 << sh; w1 |= c1 << sh; w2 |= c2 << sh;
-      if ((col & 3) == 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w1; out.r2[col >> 2] = w2; w0 = w1 = w2 = 0; }
+      w0 |= (yonly ? (uint32_t)'.' : xc) << sh;
+      w2 |= (takey ? yc : (uint32_t)'.') << sh;
+      if ((col & 3) == 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w0; out.r2[col >> 2] = w2; w0 = w2 = 0; }
       ++col;
-    };
-    uint32_t yw = 0, xw = 0;
-    int ywi = -1;
-    auto ysym = [&](int i) -> uint32_t { if ((i >> 2) != ywi) { ywi = i >> 2; yw = fs.w(Lp->f_cor + (uint32_t)ywi); } return sym[(yw >> ((i & 3) * 8)) & 0xffu]; };
-    BitCursor xb{al.st, al.ox}, yb{al.st, al.oy};
-    for (int ix = 0; ix < n1; ++ix) {
-      const bool aligned = xb.at(ix);
-      if ((ix & 3) == 0) xw = fs.w(Lp->f_ref + (ix >> 2));
-      const uint32_t xc = sym[xw & 0xff]; xw >>= 8;
-      if (aligned) while (iy < lu && !yb.at(iy)) { put('.', '.', ysym(iy)); ++iy; }   // unaligned unc letters: columns of their own
-      uint32_t c2 = '.';
-      if (aligned && iy < lu) { c2 = ysym(iy); ++iy; }   // aligned: same column (same letter or same ring)
-      put(xc, xc, c2);
+      ix += !yonly; iy += takey;
     }
-    while (iy < lu) { put('.', '.', ysym(iy)); ++iy; }
-    if (col & 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w1; out.r2[col >> 2] = w2; }
+    if (col & 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w0; out.r2[col >> 2] = w2; }
     return col;
   }
 
