@@ -39,14 +39,41 @@ struct SegInfo {      // one launch of a POA kernel
   int32_t pad;
 };
 
+// what a segment's kernel needs to know about its work, computed on the device (plan_segments_kernel) once the sort
+// knows the segment's size and maxima: the host launches every segment with a fixed grid and never reads a table back
+struct SegPlanDev {
+  int32_t start, count;     // the segment's slice of the sorted item list
+  int32_t max_ctas;         // CTAs (one warp each) that take work; the others of the launch leave at once
+  int32_t counter;          // index of the segment's work counter in the control words
+  uint32_t warp_words;      // scratch words per lane (layout of the segment's maxima)
+  uint32_t pad;
+  unsigned long long scratch_off;   // first scratch word of the segment in the phase's pool
+};
+
 struct BinTable {
   SegInfo seg[kMaxSegs + 1];   // [nseg].first_bin = number of bins
   int32_t seg_max[kMaxSegs * 4];  // per segment maxima: phase 1 {lr, lc}, phase 2 {n1, lu}
+  SegPlanDev plan[kMaxSegs];
   int32_t nseg, nbins;
-  int32_t err_code;    // 0 ok, 1 empty sequence, 2 sequence longer than kMaxWindowLen or len(ref) + len(cor) > kMaxNodes
+  int32_t err_code;    // 0 ok, 1 empty sequence, 2 sequence longer than kMaxWindowLen or len(ref) + len(cor) > kMaxNodes, 3 scratch pool too small
   int32_t err_window;  // smallest offending window id
   unsigned long long lin_bytes;  // phase-2 table: row bytes (3 x columns bound, rounded to 4) of the windows in the linear segments
+  unsigned long long need_words; // err_code 3: scratch words the call needs in the pool that was too small
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ bool seg_setup(PoaArgs &a) {
+  const SegPlanDev &pl = a.tab->plan[a.seg];
+  if ((int)blockIdx.x >= pl.max_ctas) return false;
+  a.items = a.items_base + pl.start;
+  a.n_items = pl.count;
+  a.scratch = a.scratch_base + pl.scratch_off;
+  a.warp_words = pl.warp_words;
+  a.work_counter = a.ctrl + pl.counter;
+  if (a.rows_cap_dev) a.rows_cap = *a.rows_cap_dev;
+  return true;
+}
+#endif
 
 __host__ __device__ inline int seg1_of_nb(int nb8) { return kBigTiers + (nb8 > 16 ? 0 : nb8 > 8 ? 1 : 2); }
 __host__ __device__ inline void bin1_of(int lr, int lc, int &bin, int &seg) {
@@ -131,7 +158,7 @@ __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_
       }
       if (ident) {
         int bin2, seg2;
-        bin2_of((int)lr, (int)lu, 0, bin2, seg2);
+        bin2_of((int)lr, (int)lu, 0, true, bin2, seg2);
         id.n1[w] = (int)lr;
         id.key2[w] = bin2;
         if (id.score1) id.score1[w] = 0;
@@ -143,6 +170,7 @@ __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_
       } else {
         int seg;
         bin1_of((int)lr, (int)lc, bin, seg);
+        if (use_ident) id.key2[w] = -1;   // its phase-2 bin comes from phase 1; the early sort of the linear segments must not see a stale key
         warp_hist_add(hist, bin);
         int32_t *mx = &tab->seg_max[seg * 4];
         if ((int)lr > mx[0]) atomicMax(&mx[0], (int)lr);
@@ -157,7 +185,9 @@ __global__ void __launch_bounds__(256) bin1_count_kernel(int32_t n, const int64_
   }
 }
 
-// exclusive scan of each 1024-bin chunk in place + the chunk totals
+// A sort works on a contiguous sub-range of a table's bins and segments (phase 2 is sorted twice: its linear segments as
+// soon as the size sort has seen the windows whose cor is ref, its general segments after phase 1).
+// exclusive scan of each 1024-bin chunk in place + the chunk totals; hist points at the range's first bin
 __global__ void __launch_bounds__(kScanChunk) bin_scan_chunks_kernel(int32_t nbins, int32_t *hist, int32_t *chunk_total) {
   __shared__ int32_t warp_sum[32];
   const int i = blockIdx.x * kScanChunk + threadIdx.x;
@@ -178,8 +208,10 @@ __global__ void __launch_bounds__(kScanChunk) bin_scan_chunks_kernel(int32_t nbi
   if (threadIdx.x == kScanChunk - 1) chunk_total[blockIdx.x] = before + v;
 }
 
-// exclusive scan of the chunk totals (in place -> chunk bases) and the start / count of every segment
-__global__ void __launch_bounds__(1024) bin_scan_totals_kernel(int32_t nchunks, int32_t *chunk_total, const int32_t *hist, BinTable *tab) {
+// exclusive scan of the chunk totals (in place -> chunk bases) and the start / count of the segments seg0 .. seg1-1, whose
+// bins are bin0 .. bin1-1 of the table (hist = the table's histogram, already scanned per chunk from bin0 on)
+__global__ void __launch_bounds__(1024) bin_scan_totals_kernel(int32_t nchunks, int32_t *chunk_total, const int32_t *hist, BinTable *tab,
+                                                                int32_t seg0, int32_t seg1, int32_t bin0, int32_t bin1) {
   __shared__ int32_t part[1024];
   const int32_t v = (int)threadIdx.x < nchunks ? chunk_total[threadIdx.x] : 0;
   part[threadIdx.x] = v;
@@ -193,27 +225,28 @@ __global__ void __launch_bounds__(1024) bin_scan_totals_kernel(int32_t nchunks, 
   const int32_t total = part[1023];
   if ((int)threadIdx.x < nchunks) chunk_total[threadIdx.x] = part[threadIdx.x] - v;
   __syncthreads();
-  if ((int)threadIdx.x < tab->nseg) {
-    const int s = threadIdx.x;
-    auto pos_of = [&](int bin) { return bin >= tab->nbins ? total : chunk_total[bin / kScanChunk] + hist[bin]; };
+  const int s = seg0 + (int)threadIdx.x;
+  if (s < seg1) {
+    auto pos_of = [&](int bin) { return bin >= bin1 ? total : chunk_total[(bin - bin0) / kScanChunk] + hist[bin]; };
     const int32_t p0 = pos_of(tab->seg[s].first_bin), p1 = pos_of(tab->seg[s + 1].first_bin);
     tab->seg[s].start = p0;
     tab->seg[s].count = p1 - p0;
   }
 }
 
+// keys in bin0 .. bin1-1 only; cursor = the table's scanned histogram, chunk_base relative to bin0
 __global__ void __launch_bounds__(256) bin_scatter_kernel(int32_t n, const int32_t *key, int32_t *cursor, const int32_t *chunk_base,
-                                                           int32_t *items) {
+                                                           int32_t *items, int32_t bin0, int32_t bin1) {
   for (int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const int bin = key[w];
-    if (bin < 0) continue;  // invalid window (reported by bin1_count_kernel), or a window that needs no phase 1
+    if (bin < bin0 || bin >= bin1) continue;  // invalid window (reported by bin1_count_kernel), a window that needs no phase 1, or another sort's
     // neighbouring windows often share a bin: one atomic per distinct bin of the warp's active lanes
     const unsigned peers = __match_any_sync(__activemask(), bin);
     const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
     int base = 0;
     if (lane == leader) base = atomicAdd(&cursor[bin], __popc(peers));
     base = __shfl_sync(peers, base, leader);
-    items[chunk_base[bin / kScanChunk] + base + __popc(peers & ((1u << lane) - 1u))] = w;
+    items[chunk_base[(bin - bin0) / kScanChunk] + base + __popc(peers & ((1u << lane) - 1u))] = w;
   }
 }
 

@@ -64,15 +64,16 @@ struct elector_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side[16] = {};   // one per segment that does not run on the main stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr, ev_rows = nullptr;
+  cudaStream_t lin_stream = nullptr;   // the linear segments of phase 2 run next to phase 1
+  cudaEvent_t ev_fork_v[3] = {}, ev_sorted = nullptr, ev_lin_done = nullptr;
   float last_ms_phase1 = 0.f;  // sort 1 + phase-1 kernels of the last run (last_ms covers everything)
   cudaEvent_t ev_join[16] = {};
-  elector::BinTable *h_bintab = nullptr;  // pinned
+  elector::BinTable *h_bintab = nullptr;  // pinned: the two tables of the last call as the device left them (errors, scratch needs)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H of the pipelined host entry point
   std::vector<cudaEvent_t> chunk_ev;                    // 2 per chunk: inputs resident, results ready
   ScoreMatrix mat;
   ScoringSetup sc;
-  bool no_linear2 = false;  // ELECTOR_NO_LINEAR2=1: linear windows of phase 2 on the general kernels
-  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_ctrl, d_hist, d_bintab, d_key, d_key2, d_n1, d_p1;
+  DevBuf d_tab, d_ref, d_cor, d_unc, d_roff, d_coff, d_uoff, d_items, d_scratch, d_scratch_lin, d_scratch2, d_ctrl, d_hist, d_bintab, d_key, d_key2, d_n1, d_p1;
   DevBuf d_rows, d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells;
   int64_t merged_cap = 0;  // bytes per merged-row buffer of the last merge
   // pipelined host entry point: child contexts (one per extra worker thread), per-worker sums and status of the call
@@ -81,13 +82,7 @@ struct elector_ctx {
   int64_t *h_sums = nullptr;   // pinned: global counters of a chunk + the tally overflow flag
   int pipe_rc = 0;
   DevBuf d_wdst, d_sums, d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
-  // ELECTOR_TRACE: start / stop events around every segment launch of the last run_device call
-  struct SegTrace { int phase, seg, kind, grid, count; cudaEvent_t e0, e1; };
-  std::vector<SegTrace> seg_trace;
-  std::vector<cudaEvent_t> seg_ev_pool;
-  size_t seg_ev_used = 0;
   bool trace = false;
-  bool all_side = false;
   int band_w = 6;          // ELECTOR_BAND_W: base half-width of the diagonal band of the packed linear kernels (+ rows/16 in phase 1, + rows/8 in phase 2; 0 = full DP)
   bool no_dual = false;    // ELECTOR_NO_DUAL=1: general windows of phase 2 on the INT32 kernel with frontier sets
   int resident_ph2d = 0;
@@ -100,10 +95,6 @@ struct elector_ctx {
   cudaEvent_t ev_lin = nullptr;     // the linear region is complete and its cursor is in h_totals[7]
   cudaEvent_t wait_in[2] = {nullptr, nullptr};   // run_device: phase 1 / phase 2 wait for these (letters still on their way), when set
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
-  cudaEvent_t trace_event() {
-    if (seg_ev_used == seg_ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); seg_ev_pool.push_back(e); }
-    return seg_ev_pool[seg_ev_used++];
-  }
   std::string err;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -133,7 +124,7 @@ int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uin
                  const int64_t *d_off, const int32_t *d_len, int64_t *d_counters, int64_t total_bytes);
 int check_scan_overflow(elector_ctx *ctx, int64_t n_reads);
 
-const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [3] tally overflow, [4..19] phase-1 and [20..35] phase-2 work counters, [36..37] rows cursor of the linear region
+const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [3] tally overflow, [4..19] phase-1 and [20..35] phase-2 work counters, [36..37] rows cursor of the linear region, [38..39] where that region starts
 const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share a side stream
 
 #ifndef EL_MIN_WARPS_PH1P
@@ -204,145 +195,191 @@ void resident_warps_per_sm(elector_ctx *ctx, size_t smem_per_sm) {
   if (const char *e = getenv("ELECTOR_NO_ARENA")) if (e[0] == '1') ctx->arena_ph1 = ctx->arena_ph2 = ctx->arena_ph1p = ctx->arena_ph2l = ctx->arena_ph2d = 0;
 }
 
-struct SegPlan { int seg, grid; size_t warp_words, scratch_off; int kind; bool region_b; };
+// ---- device-side planning of a sort view's segments --------------------------------------------------------------
+// A sort view = a contiguous range of one table's segments and bins, sorted and launched together: phase 1; the linear
+// segments of phase 2 (windows whose cor is ref: sorted by the size sort itself, launched while phase 1 runs); the
+// general segments of phase 2 (sorted after phase 1).  What the host knows before the sort runs is static: which kernel a
+// segment runs and how many CTAs its launch has.  Everything else -- the segment's slice of the work list, the scratch
+// layout of its maxima, how many CTAs take work and where their scratch starts -- is computed here, on the device.
+struct SegStatic {
+  int8_t kind[kMaxSegs];     // SegKind of the segment's kernel
+  int32_t grid[kMaxSegs];    // CTAs of the segment's launch
+  int32_t seg0, seg1;        // the view's segments
+  int32_t phase;             // 1 or 2
+  int32_t coop_group;
+  int32_t counter0;          // control word of segment 0's work counter
+  unsigned long long pool_words;     // scratch pool of the view
+  unsigned long long budget_words;   // no single segment takes more than this
+};
 
-// grid and scratch of every non-empty segment of one phase
-int plan_segments(elector_ctx *ctx, int phase, const BinTable &bt, std::vector<SegPlan> &plan, size_t &scratch_words) {
-  const size_t budget_words = ((size_t)24 << 30) / 4;
-  plan.clear();
-  scratch_words = 0;
-  for (int s = 0; s < bt.nseg; ++s) {
-    const SegInfo &si = bt.seg[s];
-    if (si.count <= 0) continue;
-    const int m0 = bt.seg_max[s * 4], m1 = bt.seg_max[s * 4 + 1];
-    size_t total;
-    SegPlan p;
-    // 16-bit packed kernel when the matrix allows it and no score of the segment can leave 16 bits
-    // 16-bit packed kernels when the matrix allows it and no score of the segment can leave 16 bits
-    const bool fits16 = ctx->sc.packed_ok && (int64_t)ctx->sc.maxabs * (m0 + m1 + 4) <= kPackedSpan;
-    int per_sm;
-    if (phase == 1) {
-      // the segments of the longest windows (cor longer than 128 letters): a warp per window instead of a thread
-      p.kind = (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : fits16 ? kPacked : kInt32;
-      if (p.kind == kCoop) { LayoutC1 L; make_layout_c1(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
-      else if (p.kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1p; }
-      else { Layout1 L; make_layout1(L, m0, m1); total = L.total; per_sm = ctx->resident_ph1; }
-    } else {
-      // windows whose P1 is linear have their own segments and, when 16 bits are enough, their own kernel
-      // the segments of the longest windows (more than 128 rows, general and linear): a warp per window instead of a thread
-      const bool longest = s <= kBigTiers || s == kFirstLinSeg2;
-      p.kind = (longest && ctx->coop_group > 0) ? kCoop : !fits16 ? kInt32 : (s >= kFirstLinSeg2 && !ctx->no_linear2) ? kLinear : ctx->no_dual ? kInt32 : kDual;
-      if (p.kind == kCoop) { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_coop; }
-      else if (p.kind == kDual) { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2d; }
-      else if (p.kind == kLinear) { Layout2L L; make_layout2l(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2l; }
-      else { Layout2 L; make_layout2(L, m0, m1); total = L.total; per_sm = ctx->resident_ph2; }
-    }
-    const int resident = std::max(1, per_sm) * ctx->sm_count;
-    p.seg = s;
-    p.region_b = phase == 2 && ctx->split_rows && s >= kFirstLinSeg2;
-    p.warp_words = total;
-    const int per_warp_items = p.kind == kCoop ? ctx->coop_group : 32;
-    p.grid = (int)std::min<int64_t>(resident, ((int64_t)si.count + per_warp_items - 1) / per_warp_items);
-    // bound the scratch of segments with huge windows: fewer resident warps
-    const size_t per_warp = total * 32;
-    while (p.grid > 1 && per_warp * (size_t)p.grid > budget_words / 2) p.grid = (p.grid + 1) / 2;
-    if (per_warp * (size_t)p.grid > budget_words)
-      return ctx->fail(ELECTOR_ETOOLARGE, "windows of %d x %d letters need %zu MiB scratch per warp in phase %d", m0, m1, (per_warp * 4) >> 20, phase);
-    p.scratch_off = scratch_words;
-    scratch_words += per_warp * (size_t)p.grid;
-    plan.push_back(p);
+__device__ uint32_t layout_words(int phase, int kind, int m0, int m1) {
+  if (phase == 1) {
+    if (kind == kCoop) { LayoutC1 L; make_layout_c1(L, m0, m1); return L.total; }
+    if (kind == kPacked) { Layout1P L; make_layout1p(L, m0, m1); return L.total; }
+    Layout1 L; make_layout1(L, m0, m1); return L.total;
   }
-  if (scratch_words > 2 * budget_words) return ctx->fail(ELECTOR_ETOOLARGE, "call needs %zu MiB of scratch", (scratch_words * 4) >> 20);
-  // launch order: the warp-cooperative segments first (they hold the longest windows and must not queue behind the bulk)
-  // then the segments that write to the linear region of the rows (it leaves for the host as soon as they are done), then
-  // the rest.  (Measured: starting the 65-128-row general segment, whose groups run longest, before the linear segments
-  // delays the linear region and costs 1.6 ms of a 16 ms config-1 call.)
-  auto rank = [](const SegPlan &q) { return q.kind == kCoop ? 0 : q.region_b ? 1 : 2; };
-  std::stable_sort(plan.begin(), plan.end(), [&](const SegPlan &x, const SegPlan &y) { return rank(x) < rank(y); });
+  if (kind == kLinear) { Layout2L L; make_layout2l(L, m0, m1); return L.total; }
+  Layout2 L; make_layout2(L, m0, m1); return L.total;
+}
+
+// one thread: a dozen segments.  split_rows: the view is the linear one of a call whose rows go to two regions -- the linear
+// segments write [cap_a, rows_cap), the general ones [cursor, cap_a); ctrl64[18] = cursor of the linear region, [19] = cap_a
+__global__ void plan_segments_kernel(BinTable *tab, SegStatic ss, unsigned long long *ctrl64, long long rows_cap, int split_rows) {
+  if (threadIdx.x || blockIdx.x) return;
+  unsigned long long off = 0;
+  bool too_big = false;
+  for (int s = ss.seg0; s < ss.seg1; ++s) {
+    SegPlanDev pl;
+    pl.start = tab->seg[s].start; pl.count = tab->seg[s].count; pl.counter = ss.counter0 + s; pl.pad = 0;
+    pl.warp_words = 0; pl.max_ctas = 0; pl.scratch_off = off;
+    if (pl.count > 0) {
+      pl.warp_words = layout_words(ss.phase, ss.kind[s], tab->seg_max[s * 4], tab->seg_max[s * 4 + 1]);
+      const int per = ss.kind[s] == kCoop ? ss.coop_group : 32;
+      long long ctas = ((long long)pl.count + per - 1) / per;
+      if (ctas > ss.grid[s]) ctas = ss.grid[s];
+      const unsigned long long per_warp = (unsigned long long)pl.warp_words * 32;
+      while (ctas > 1 && per_warp * (unsigned long long)ctas > ss.budget_words / 2) ctas = (ctas + 1) / 2;   // huge windows: fewer warps in flight
+      pl.max_ctas = (int32_t)ctas;
+      off += per_warp * (unsigned long long)ctas;
+      if (per_warp * (unsigned long long)ctas > ss.budget_words) too_big = true;
+    }
+    tab->plan[s] = pl;
+  }
+  if (off > ss.pool_words || too_big) {   // nothing of this view runs; the host grows the pool and runs the call again
+    for (int s = ss.seg0; s < ss.seg1; ++s) tab->plan[s].max_ctas = 0;
+    if (tab->err_code == 0) tab->err_code = too_big ? 4 : 3;
+    if (off > tab->need_words) tab->need_words = off;
+  }
+  if (split_rows) {
+    const unsigned long long cap_a = (unsigned long long)((rows_cap - (long long)tab->lin_bytes) & ~15ll);
+    ctrl64[18] = cap_a;
+    ctrl64[19] = cap_a;
+  }
+}
+
+struct SortView {
+  BinTable *dtab; int phase, seg0, seg1, bin0, bin1;
+  int32_t *hist;      // the table's histogram (all bins)
+  int32_t *chunks;    // chunk totals of this view
+  const int32_t *key; int32_t *items;
+  DevBuf *pool;
+  int counter0;
+};
+
+// kernel of a segment (static: known before the sort runs, see SegStatic)
+int seg_kind(const elector_ctx *ctx, int phase, int s) {
+  const bool small16 = ctx->sc.packed_ok && (int64_t)ctx->sc.maxabs * (kSmallMax + 4 * kN1q + 4) <= kPackedSpan;   // no score of a small window leaves 16 bits
+  if (phase == 1) return (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : (s >= kBigTiers && small16) ? kPacked : kInt32;
+  const bool longest = s <= kBigTiers || s == kFirstLinSeg2;   // more than 128 rows: a warp per window
+  if (longest && ctx->coop_group > 0) return kCoop;
+  if (s < kBigTiers || !small16) return kInt32;
+  return s >= kFirstLinSeg2 ? kLinear : ctx->no_dual ? kInt32 : kDual;
+}
+int seg_resident(const elector_ctx *ctx, int phase, int kind) {
+  switch (kind) {
+    case kCoop: return ctx->resident_coop;
+    case kPacked: return ctx->resident_ph1p;
+    case kLinear: return ctx->resident_ph2l;
+    case kDual: return ctx->resident_ph2d;
+    default: return phase == 1 ? ctx->resident_ph1 : ctx->resident_ph2;
+  }
+}
+
+// scan + scatter + plan of one view, all on `st`
+int sort_view(elector_ctx *ctx, cudaStream_t st, const SortView &v, int32_t n, int bgrid, SegStatic &ss, long long rows_cap, bool split_rows) {
+  const int nb = v.bin1 - v.bin0, nch = (nb + kScanChunk - 1) / kScanChunk;
+  bin_scan_chunks_kernel<<<nch, kScanChunk, 0, st>>>(nb, v.hist + v.bin0, v.chunks);
+  bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch, v.chunks, v.hist, v.dtab, v.seg0, v.seg1, v.bin0, v.bin1);
+  bin_scatter_kernel<<<bgrid, 256, 0, st>>>(n, v.key, v.hist, v.chunks, v.items, v.bin0, v.bin1);
+  memset(&ss, 0, sizeof ss);
+  ss.seg0 = v.seg0; ss.seg1 = v.seg1; ss.phase = v.phase; ss.coop_group = std::max(1, ctx->coop_group); ss.counter0 = v.counter0;
+  ss.pool_words = v.pool->cap / 4;
+  ss.budget_words = ((unsigned long long)24 << 30) / 4;
+  for (int s = v.seg0; s < v.seg1; ++s) {
+    const int kind = seg_kind(ctx, v.phase, s);
+    ss.kind[s] = (int8_t)kind;
+    ss.grid[s] = std::max(1, seg_resident(ctx, v.phase, kind)) * ctx->sm_count;
+  }
+  plan_segments_kernel<<<1, 32, 0, st>>>(v.dtab, ss, ctx->d_ctrl.as<unsigned long long>(), rows_cap, split_rows ? 1 : 0);
+  CU(cudaGetLastError());
+  ctx->last_launches += 4;
   return ELECTOR_OK;
 }
 
-// One phase: the segments holding the largest windows (few items, long per-item time) start
-// first, on side streams, so that their tail overlaps the bulk on the main stream.
-int launch_segments(elector_ctx *ctx, int phase, int64_t n, const BinTable &bt, const std::vector<SegPlan> &plan, PoaArgs base,
-                    unsigned long long *cursor_b = nullptr, int64_t cap_a = 0) {
-  cudaStream_t st = ctx->stream;
-  CU(cudaEventRecord(ctx->ev_fork, st));
-  int side = 0, used_side = 0, nregb = 0;
-  for (size_t k = 0; k < plan.size(); ++k) {
-    const SegPlan &p = plan[k];
-    const SegInfo &si = bt.seg[p.seg];
-    // the last segment and (unless ELECTOR_ALL_SIDE=1) any large share stay on the main stream
-    const bool bulk = k + 1 == plan.size() || (!ctx->all_side && (int64_t)si.count * 8 > n);
-    cudaStream_t ls = st;
-    if (!bulk) {
-      ls = ctx->side[side];
-      if (!(used_side & (1 << side))) { CU(cudaStreamWaitEvent(ls, ctx->ev_fork, 0)); used_side |= 1 << side; }
-      side = (side + 1) % kSideStreams;
-    }
-    elector_ctx::SegTrace tr{phase, p.seg, p.kind, p.grid, si.count, nullptr, nullptr};
-    if (ctx->trace) { tr.e0 = ctx->trace_event(); tr.e1 = ctx->trace_event(); CU(cudaEventRecord(tr.e0, ls)); }
-    PoaArgs a = base;
-    a.items = ctx->d_items.as<int32_t>() + si.start;
-    a.n_items = si.count;
-    a.scratch = ctx->d_scratch.as<uint32_t>() + p.scratch_off;
-    a.warp_words = (uint32_t)p.warp_words;
-    a.work_counter = ctx->d_ctrl.as<int32_t>() + 4 + (phase == 1 ? 0 : 16) + p.seg;
-    if (cursor_b) {   // two row regions: general windows up to cap_a, the linear segments behind their own cursor
-      if (p.region_b) a.rows_cursor = cursor_b; else a.rows_cap = cap_a;
-    }
-    const bool linear_seg = phase == 2 && p.seg >= kFirstLinSeg2;
-    const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group, linear_seg, ctx)
-                                              : launch_phase<false>(phase, p.kind, ls, a, p.grid, ctx->d_tab.as<SymbolTables>(), ctx->coop_group, linear_seg, ctx);
-    if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
-    ++ctx->last_launches;
-    if (ctx->trace) { CU(cudaEventRecord(tr.e1, ls)); ctx->seg_trace.push_back(tr); }
-    if (cursor_b && p.region_b && nregb < 8) {
-      CU(cudaEventRecord(ctx->ev_regb[nregb], ls));
-      CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_regb[nregb], 0));
-      ++nregb;
-    }
-  }
-  if (cursor_b) {   // the copy stream learns where the linear region ends as soon as its last segment is done
-    CU(cudaMemcpyAsync(&ctx->h_totals[7], cursor_b, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_out));
-    CU(cudaEventRecord(ctx->ev_lin, ctx->copy_out));
-  }
-  for (int k = 0; k < kSideStreams; ++k)
-    if (used_side & (1 << k)) {
-      CU(cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
-      CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0));
+// every segment of a view on its own side stream (side[first_side ...]), forked from and joined back into `st`
+int launch_view(elector_ctx *ctx, cudaStream_t st, const SortView &v, const SegStatic &ss, PoaArgs base, int first_side, bool region_b) {
+  cudaEvent_t fork = ctx->ev_fork_v[v.phase == 1 ? 0 : v.seg0 >= kFirstLinSeg2 ? 1 : 2];
+  CU(cudaEventRecord(fork, st));
+  int nregb = 0;
+  // the warp-cooperative segments first (they hold the longest windows and set the latency floor of a call)
+  for (int pass = 0; pass < 2; ++pass)
+    for (int s = v.seg0; s < v.seg1; ++s) {
+      const int kind = ss.kind[s];
+      if ((kind == kCoop) != (pass == 0)) continue;
+      cudaStream_t ls = ctx->side[first_side + (s - v.seg0)];
+      CU(cudaStreamWaitEvent(ls, fork, 0));
+      PoaArgs a = base;
+      a.tab = v.dtab; a.seg = s; a.items_base = v.items; a.scratch_base = v.pool->as<uint32_t>(); a.ctrl = ctx->d_ctrl.as<int32_t>();
+      const bool linear_seg = v.phase == 2 && s >= kFirstLinSeg2;
+      const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(v.phase, kind, ls, a, ss.grid[s], ctx->d_tab.as<SymbolTables>(), ss.coop_group, linear_seg, ctx)
+                                                : launch_phase<false>(v.phase, kind, ls, a, ss.grid[s], ctx->d_tab.as<SymbolTables>(), ss.coop_group, linear_seg, ctx);
+      if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+      ++ctx->last_launches;
+      cudaEvent_t done = ctx->ev_join[first_side + (s - v.seg0)];
+      CU(cudaEventRecord(done, ls));
+      CU(cudaStreamWaitEvent(st, done, 0));
+      if (region_b && nregb < 8) { CU(cudaStreamWaitEvent(ctx->copy_out, done, 0)); ++nregb; }
     }
   return ELECTOR_OK;
 }
 
-// Core: all pointers are device pointers.  Launch structure of one call:
-//   sort 1 (3 kernels) -> table to host -> phase-1 segments -> sort 2 (scan + scatter; its
-//   histogram was filled by phase 1) -> table to host -> phase-2 segments
+// Core: all pointers are device pointers; nothing here waits for the device.  Launch structure of one call:
+//   main stream  : set-up -> size sort (recognises the windows whose cor is ref) -> sort + plan of phase 1 and of the linear
+//                  segments of phase 2 -> phase-1 segments -> sort + plan of the general segments -> general segments
+//   linear stream: the linear segments of phase 2, as soon as their sort is done (they overlap phase 1)
+// Every segment runs on a side stream of its own.  h_roff / h_coff (host copies of the offsets) spare a read-back of four
+// totals; errors (bad window, scratch pool too small) are left in the tables, which travel to h_bintab at the end.
 int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_roff, const char *d_cor,
-               const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, char *d_rows, int64_t rows_cap,
-               int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2, int64_t *d_cells,
-               unsigned long long *d_cursor, int32_t *d_errflag, int64_t cursor_init = 0) {
+               const int64_t *d_coff, const char *d_unc, const int64_t *d_uoff, const int64_t *h_roff, const int64_t *h_coff,
+               char *d_rows, int64_t rows_cap, int64_t *d_rowoff, int32_t *d_stride, int32_t *d_nring, int32_t *d_s1, int32_t *d_s2,
+               int64_t *d_cells, unsigned long long *d_cursor, int32_t *d_errflag, int64_t cursor_init = 0) {
   if (n == 0) return ELECTOR_OK;
   if (n > 0x7fffffff - 64) return ctx->fail(ELECTOR_EINVAL, "too many windows in one call");
   cudaStream_t st = ctx->stream;
-  CU(ctx->d_items.reserve((size_t)n * sizeof(int32_t)));
+  CU(ctx->d_items.reserve((size_t)n * 3 * sizeof(int32_t)));
   CU(ctx->d_key.reserve((size_t)n * sizeof(int32_t)));
   CU(ctx->d_key2.reserve((size_t)n * sizeof(int32_t)));
   CU(ctx->d_n1.reserve((size_t)n * sizeof(int32_t)));
-  CU(ctx->d_hist.reserve((size_t)(kNumBins1 + kNumBins2 + 2 * kMaxChunks) * sizeof(int32_t)));
+  CU(ctx->d_hist.reserve((size_t)(kNumBins1 + kNumBins2 + 3 * kMaxChunks) * sizeof(int32_t)));
   CU(ctx->d_bintab.reserve(2 * sizeof(BinTable)));
-  int32_t *hist1 = ctx->d_hist.as<int32_t>(), *hist2 = hist1 + kNumBins1, *chunks1 = hist2 + kNumBins2, *chunks2 = chunks1 + kMaxChunks;
+  int32_t *hist1 = ctx->d_hist.as<int32_t>(), *hist2 = hist1 + kNumBins1, *chunks1 = hist2 + kNumBins2, *chunksL = chunks1 + kMaxChunks, *chunks2 = chunksL + kMaxChunks;
   BinTable *dtab1 = ctx->d_bintab.as<BinTable>(), *dtab2 = dtab1 + 1;
-  BinTable *htab1 = ctx->h_bintab, *htab2 = ctx->h_bintab + 1;
+  int32_t *items1 = ctx->d_items.as<int32_t>(), *itemsL = items1 + n, *items2 = itemsL + n;
+  // letters of ref and cor of the call (size of the P1 node lists) and their first offsets
+  int64_t tot[4];
+  if (h_roff && h_coff) { tot[0] = h_roff[n]; tot[1] = h_coff[n]; tot[2] = h_roff[0]; tot[3] = h_coff[0]; }
+  else {   // slow path: a read-back
+    CU(cudaMemcpyAsync(&ctx->h_totals[0], d_roff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ctx->h_totals[1], d_coff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ctx->h_totals[2], d_roff, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ctx->h_totals[3], d_coff, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < 4; ++k) tot[k] = ctx->h_totals[k];
+  }
+  CU(ctx->d_p1.reserve((size_t)(tot[0] - tot[2] + tot[1] - tot[3] + 8 * n + 8) * sizeof(uint16_t)));
+  // scratch pools: kept from call to call; a call that needs more says so in its tables and is run again (run_checked)
+  for (DevBuf *pool : {&ctx->d_scratch, &ctx->d_scratch_lin, &ctx->d_scratch2})
+    if (pool->cap == 0) CU(pool->reserve(std::max<size_t>((size_t)64 << 20, std::min<size_t>((size_t)n * 1024, (size_t)2 << 30))));
   CU(cudaEventRecord(ctx->ev0, st));
   // control words, histograms and the two segment tables are set up by a kernel and memsets: nothing of a call's
   // set-up goes through the host-to-device copy engine, where it would queue behind the letters of a pipelined call
   CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)(kNumBins1 + kNumBins2) * sizeof(int32_t), st));
-  memset(htab1, 0, 2 * sizeof(BinTable));
-  fill_segments1(*htab1);
-  fill_segments2(*htab2);
-  htab1->err_window = 0x7fffffff;
   {
+    BinTable stat[2];   // the static part of the tables: first bin of every segment
+    BinTable *htab1 = &stat[0], *htab2 = &stat[1];
+    memset(stat, 0, sizeof stat);
+    fill_segments1(*htab1);
+    fill_segments2(*htab2);
     SegFirstBins fb;
     for (int k = 0; k <= kMaxSegs; ++k) { fb.first1[k] = htab1->seg[k].first_bin; fb.first2[k] = htab2->seg[k].first_bin; }
     fb.nseg1 = htab1->nseg; fb.nbins1 = htab1->nbins; fb.nseg2 = htab2->nseg; fb.nbins2 = htab2->nbins;
@@ -351,102 +388,108 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
     ++ctx->last_launches;
   }
   const int bgrid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
-  const int nch1 = (kNumBins1 + kScanChunk - 1) / kScanChunk, nch2 = (kNumBins2 + kScanChunk - 1) / kScanChunk;
-  // ---- sort 1 ----
+  // ---- size sort ----
   // windows whose corrected letters are the reference letters need no phase 1 (bin_kernel.cuh): the sort then reads the
   // letters, so it waits for them too.  Only when their phase 2 needs no node list: Phase2L for the small linear segments,
   // the warp-cooperative kernel (which rebuilds lin(ref)) for the long ones.
-  const bool ident_ok = ctx->sc.packed_ok && !ctx->no_ident && !ctx->no_linear2 && ctx->coop_group > 0 &&
+  const bool ident_ok = ctx->sc.packed_ok && !ctx->no_ident && ctx->coop_group > 0 &&
                         (int64_t)ctx->sc.maxabs * (kSmallMax + 4 * kN1q + 4) <= kPackedSpan;
   if (ident_ok && ctx->wait_in[0]) CU(cudaStreamWaitEvent(st, ctx->wait_in[0], 0));
   IdentArgs ida{(const uint8_t *)d_ref, (const uint8_t *)d_cor, ctx->d_n1.as<int32_t>(), ctx->d_key2.as<int32_t>(), hist2, dtab2->seg_max, d_s1, &dtab2->lin_bytes};
   bin1_count_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, d_roff, d_coff, d_uoff, ctx->d_key.as<int32_t>(), hist1, dtab1, ident_ok, ida);
-  bin_scan_chunks_kernel<<<nch1, kScanChunk, 0, st>>>(kNumBins1, hist1, chunks1);
-  bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch1, chunks1, hist1, dtab1);
-  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key.as<int32_t>(), hist1, chunks1, ctx->d_items.as<int32_t>());
   CU(cudaGetLastError());
-  ctx->last_launches += 4;
-  CU(cudaMemcpyAsync(htab1, dtab1, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(&ctx->h_totals[0], d_roff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(&ctx->h_totals[1], d_coff + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(&ctx->h_totals[2], d_roff, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(&ctx->h_totals[3], d_coff, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  if (htab1->err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", htab1->err_window);
-  if (htab1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d: a sequence longer than %d letters, or reference + corrected longer than %d (16-bit node indices)", htab1->err_window, kMaxWindowLen, kMaxNodes);
-  CU(ctx->d_p1.reserve((size_t)(ctx->h_totals[0] - ctx->h_totals[2] + ctx->h_totals[1] - ctx->h_totals[3] + 8 * n + 8) * sizeof(uint16_t)));
+  ++ctx->last_launches;
+  const int lin_bin0 = kBigTiers + kSmallBins2;
+  const SortView v1{dtab1, 1, 0, kNumSegs1, 0, kNumBins1, hist1, chunks1, ctx->d_key.as<int32_t>(), items1, &ctx->d_scratch, 4};
+  const SortView vL{dtab2, 2, kFirstLinSeg2, kNumSegs2, lin_bin0, kNumBins2, hist2, chunksL, ctx->d_key2.as<int32_t>(), itemsL, &ctx->d_scratch_lin, 20};
+  const SortView v2{dtab2, 2, 0, kFirstLinSeg2, 0, lin_bin0, hist2, chunks2, ctx->d_key2.as<int32_t>(), items2, &ctx->d_scratch2, 20};
+  SegStatic ss1, ssL, ss2;
+  int rc = sort_view(ctx, st, v1, (int32_t)n, bgrid, ss1, rows_cap, false);
+  if (rc == ELECTOR_OK) rc = sort_view(ctx, st, vL, (int32_t)n, bgrid, ssL, rows_cap, ctx->split_rows);
+  if (rc != ELECTOR_OK) return rc;
 
   PoaArgs a;
   memset(&a, 0, sizeof a);
   a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
   a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
   a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
-  a.ro0 = ctx->h_totals[2]; a.co0 = ctx->h_totals[3];
+  a.ro0 = tot[2]; a.co0 = tot[3];
   a.p1_nodes = ctx->d_p1.as<uint16_t>(); a.n1 = ctx->d_n1.as<int32_t>(); a.key2 = ctx->d_key2.as<int32_t>();
-  a.hist2 = hist2; a.seg2_max = dtab2->seg_max; a.lin_bytes = &dtab2->lin_bytes;
+  a.hist2 = hist2; a.seg2_max = dtab2->seg_max;
   a.rows_out = (uint8_t *)d_rows; a.rows_cursor = d_cursor; a.rows_cap = rows_cap;
   a.row_off = d_rowoff; a.row_stride = d_stride; a.nring = d_nring; a.score1 = d_s1; a.score2 = d_s2; a.cells = d_cells;
   a.error_flag = d_errflag;
   a.band_w = ctx->band_w;
   a.band_span = band_span_limit(ctx->sc.maxabs);
 
+  // ---- linear segments of phase 2: their own stream, next to phase 1 ----
+  cudaStream_t sl = ctx->lin_stream;
+  CU(cudaEventRecord(ctx->ev_sorted, st));
+  CU(cudaStreamWaitEvent(sl, ctx->ev_sorted, 0));
+  if (ctx->wait_in[0]) CU(cudaStreamWaitEvent(sl, ctx->wait_in[0], 0));
+  if (ctx->wait_in[1]) CU(cudaStreamWaitEvent(sl, ctx->wait_in[1], 0));
+  {
+    PoaArgs al = a;
+    if (ctx->split_rows) {   // two row regions: the linear segments behind their own cursor, up to the end of the buffer
+      al.rows_cursor = ctx->d_ctrl.as<unsigned long long>() + 18;
+    }
+    rc = launch_view(ctx, sl, vL, ssL, al, 12, ctx->split_rows);
+    if (rc != ELECTOR_OK) return rc;
+    if (ctx->split_rows) {   // the copy stream learns where the linear region starts and ends as soon as its last segment is done
+      CU(cudaMemcpyAsync(&ctx->h_totals[6], ctx->d_ctrl.as<unsigned long long>() + 18, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+      CU(cudaEventRecord(ctx->ev_lin, ctx->copy_out));
+    }
+    CU(cudaEventRecord(ctx->ev_lin_done, sl));
+  }
   // ---- phase 1 ----
-  std::vector<SegPlan> plan;
-  size_t scratch_words = 0;
-  int rc = plan_segments(ctx, 1, *htab1, plan, scratch_words);
-  if (rc != ELECTOR_OK) return rc;
-  CU(ctx->d_scratch.reserve(scratch_words * 4));
   if (ctx->wait_in[0]) CU(cudaStreamWaitEvent(st, ctx->wait_in[0], 0));
-  rc = launch_segments(ctx, 1, n, *htab1, plan, a);
+  rc = launch_view(ctx, st, v1, ss1, a, 0, false);
   if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev_mid, st));
-  // ---- sort 2 (phase 1 filled key2, hist2 and the segment maxima) ----
-  bin_scan_chunks_kernel<<<nch2, kScanChunk, 0, st>>>(kNumBins2, hist2, chunks2);
-  bin_scan_totals_kernel<<<1, 1024, 0, st>>>(nch2, chunks2, hist2, dtab2);
-  bin_scatter_kernel<<<bgrid, 256, 0, st>>>((int32_t)n, ctx->d_key2.as<int32_t>(), hist2, chunks2, ctx->d_items.as<int32_t>());
-  CU(cudaGetLastError());
-  ctx->last_launches += 3;
-  CU(cudaMemcpyAsync(htab2, dtab2, sizeof(BinTable), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  // ---- phase 2 ----
-  rc = plan_segments(ctx, 2, *htab2, plan, scratch_words);
+  // ---- general segments of phase 2 (phase 1 filled key2, hist2 and the segment maxima) ----
+  rc = sort_view(ctx, st, v2, (int32_t)n, bgrid, ss2, rows_cap, false);
   if (rc != ELECTOR_OK) return rc;
-  CU(ctx->d_scratch.reserve(scratch_words * 4));
   if (ctx->wait_in[1]) CU(cudaStreamWaitEvent(st, ctx->wait_in[1], 0));
-  if (ctx->split_rows) {
-    unsigned long long *cursor_b = reinterpret_cast<unsigned long long *>(ctx->d_ctrl.as<int32_t>() + 36);
-    const int64_t cap_a = (rows_cap - (int64_t)htab2->lin_bytes) & ~(int64_t)15;   // general region: [cursor_init, cap_a), linear region: [cap_a, rows_cap)
-    ctx->region_b_base = cap_a;
-    set_u64_kernel<<<1, 1, 0, st>>>(cursor_b, (unsigned long long)cap_a);
-    CU(cudaGetLastError());
-    ++ctx->last_launches;
-    rc = launch_segments(ctx, 2, n, *htab2, plan, a, cursor_b, cap_a);
-  } else
-  rc = launch_segments(ctx, 2, n, *htab2, plan, a);
-  if (rc != ELECTOR_OK) return rc;
+  {
+    PoaArgs ag = a;
+    if (ctx->split_rows) ag.rows_cap_dev = reinterpret_cast<const long long *>(ctx->d_ctrl.as<unsigned long long>() + 19);   // the general region ends where the linear one starts
+    rc = launch_view(ctx, st, v2, ss2, ag, 0, false);
+    if (rc != ELECTOR_OK) return rc;
+  }
+  CU(cudaStreamWaitEvent(st, ctx->ev_lin_done, 0));
+  CU(cudaMemcpyAsync(ctx->h_bintab, dtab1, 2 * sizeof(BinTable), cudaMemcpyDeviceToHost, st));   // errors and needs of the call
   CU(cudaEventRecord(ctx->ev1, st));
+  return ELECTOR_OK;
+}
+
+// after the stream has been synchronised: what the tables say.  ELECTOR_OK, an error, or 1 = a scratch pool was too small
+// and has been grown: run the call again
+int check_tables(elector_ctx *ctx) {
+  const BinTable *t1 = ctx->h_bintab, *t2 = ctx->h_bintab + 1;
+  if (t1->err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", t1->err_window);
+  if (t1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d: a sequence longer than %d letters, or reference + corrected longer than %d (16-bit node indices)", t1->err_window, kMaxWindowLen, kMaxNodes);
+  if (t1->err_code == 4 || t2->err_code == 4) return ctx->fail(ELECTOR_ETOOLARGE, "a segment of the call needs %llu MiB of scratch (windows too long)", (unsigned long long)((std::max(t1->need_words, t2->need_words) * 4) >> 20));
+  if (t1->err_code == 3 || t2->err_code == 3) {
+    const size_t need1 = (size_t)t1->need_words * 4, need2 = (size_t)t2->need_words * 4;
+    if (need1 > ((size_t)60 << 30) || need2 > ((size_t)60 << 30)) return ctx->fail(ELECTOR_ETOOLARGE, "call needs %zu MiB of scratch", std::max(need1, need2) >> 20);
+    if (need1 > ctx->d_scratch.cap) CU(ctx->d_scratch.reserve(need1));
+    if (need2 > ctx->d_scratch_lin.cap) CU(ctx->d_scratch_lin.reserve(need2));   // the two views of table 2 report one maximum
+    if (need2 > ctx->d_scratch2.cap) CU(ctx->d_scratch2.reserve(need2));
+    return 1;
+  }
   return ELECTOR_OK;
 }
 
 // adds the device time between ev0 and ev1 (both already reached) to the running total of a call
 void add_kernel_ms(elector_ctx *ctx) {
   float ms = 0.f;
-  if (ctx->trace) {   // device timeline of the segment launches, ms after the start of the run_device call
-    static const char *kinds[] = {"int32", "packed", "linear", "coop", "dual"};
+  if (ctx->trace) {
     const char *lvl = getenv("ELECTOR_TRACE");
-    if (lvl && lvl[0] >= '2')   // ELECTOR_TRACE=2: every segment launch
-    for (const auto &t : ctx->seg_trace) {
-      float a = 0.f, b = 0.f;
-      cudaEventElapsedTime(&a, ctx->ev0, t.e0);
-      cudaEventElapsedTime(&b, ctx->ev0, t.e1);
-      fprintf(stderr, "[elector trace]   phase %d segment %2d (%s): %8d windows, grid %5d, %7.3f -> %7.3f ms\n", t.phase, t.seg, kinds[t.kind], t.count, t.grid, a, b);
-    }
     if (lvl && lvl[0] >= '2') {
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) fprintf(stderr, "[elector trace]   phase 1 done %.3f ms", ms);
+      if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_lin_done) == cudaSuccess) fprintf(stderr, ", linear segments of phase 2 done %.3f ms", ms);
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) fprintf(stderr, ", all done %.3f ms\n", ms);
     }
-    ctx->seg_trace.clear();
-    ctx->seg_ev_used = 0;
   }
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms += ms;
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) ctx->last_ms_phase1 += ms;
@@ -509,62 +552,75 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   // the offsets stay those of the whole call: the letter pointers are moved back by the chunk's first offset, the row
   // pointer by the chunk's base in the caller's row buffer (row_off[] then indexes the caller's buffer directly)
   char *d_rows_v = ctx->d_rows.as<char>() - j.rows_base;
-  ctx->split_rows = j.split;
-  ctx->region_b_base = j.rows_base + j.rows_len;
-  ctx->h_totals[7] = ctx->region_b_base;
-  int rc = run_device(ctx, nw, ctx->d_ref.as<char>() - br0, ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>() - bc0, ctx->d_coff.as<int64_t>(),
-                      ctx->d_unc.as<char>() - bu0, ctx->d_uoff.as<int64_t>(), d_rows_v, j.rows_base + j.rows_len, ctx->d_rowoff.as<int64_t>(),
-                      ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(), ctx->d_s2.as<int32_t>(),
-                      ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2, j.rows_base);
-  ctx->wait_in[0] = ctx->wait_in[1] = nullptr;
-  ctx->split_rows = false;
-  if (rc != ELECTOR_OK) { cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(st); return rc; }
-  CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaEventRecord(ctx->ev_rows, st));
-  if (nr > 0) {
-    std::vector<int64_t> rf(pa.read_first + r0, pa.read_first + r1 + 1);
-    for (int64_t &v : rf) v -= w0;
-    CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
-    rc = merge_device(ctx, nr, rf.data(), nw, reinterpret_cast<const uint8_t *>(d_rows_v), 3 * (br + bc + bu), ctx->d_rowoff.as<int64_t>(),
-                      ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>());
-    if (rc == ELECTOR_OK)
-      rc = tally_device(ctx, nr, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(), ctx->d_moff.as<int64_t>(),
-                        ctx->d_mlen.as<int32_t>(), ctx->d_tally_out.as<int64_t>(), ctx->merged_cap);
-    if (rc != ELECTOR_OK) { cudaStreamSynchronize(st); return rc; }
-    tally_sum_kernel<<<std::min<int>(64, (int)((nr + 7) / 8)), 256, 0, st>>>(nr, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
-    CU(cudaGetLastError());
-    ++ctx->last_launches;
-    CU(cudaEventRecord(ctx->ev1, st));   // the chunk's device time covers merge + tally too
-    CU(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ctx->h_sums + ELECTOR_TALLY_K, ctx->d_ctrl.as<int32_t>() + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(pa.counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.p, nr * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
-  }
-  // the alignment results leave on the copy stream while merge and tally run: the host waits for the POA kernels only
-  // to learn how many row bytes the chunk used
   cudaStream_t so = ctx->copy_out;
-  // the linear region first: its segments are launched before the general ones and finish early in phase 2
-  if (j.split) CU(cudaEventSynchronize(ctx->ev_lin));
-  const int64_t base_b = ctx->region_b_base, used_b = ctx->h_totals[7];
-  if (used_b > base_b && used_b <= j.rows_base + j.rows_len)
-    CU(cudaMemcpyAsync(pa.rows_out + base_b, d_rows_v + base_b, used_b - base_b, cudaMemcpyDeviceToHost, so));
-  CU(cudaEventSynchronize(ctx->ev_rows));
-  const int64_t used = ctx->h_totals[4];
-  if ((int32_t)(ctx->h_totals[5] & 0xffffffff) || used > base_b || used_b > j.rows_base + j.rows_len) {
-    cudaStreamSynchronize(st);
-    cudaStreamSynchronize(so);
-    return ctx->fail(ELECTOR_ECAPACITY, "rows of a chunk exceed their bound (%lld + %lld > %lld)", (long long)(used - j.rows_base), (long long)(used_b - base_b),
-                     (long long)j.rows_len);
+  for (int attempt = 0;; ++attempt) {
+    ctx->split_rows = j.split;
+    int rc = run_device(ctx, nw, ctx->d_ref.as<char>() - br0, ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>() - bc0, ctx->d_coff.as<int64_t>(),
+                        ctx->d_unc.as<char>() - bu0, ctx->d_uoff.as<int64_t>(), pa.ro + w0, pa.co + w0, d_rows_v, j.rows_base + j.rows_len,
+                        ctx->d_rowoff.as<int64_t>(), ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(),
+                        ctx->d_s2.as<int32_t>(), ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2, j.rows_base);
+    ctx->split_rows = false;
+    if (rc != ELECTOR_OK) { ctx->wait_in[0] = ctx->wait_in[1] = nullptr; cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(st); return rc; }
+    CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev_rows, st));
+    if (nr > 0) {
+      std::vector<int64_t> rf(pa.read_first + r0, pa.read_first + r1 + 1);
+      for (int64_t &v : rf) v -= w0;
+      CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
+      rc = merge_device(ctx, nr, rf.data(), nw, reinterpret_cast<const uint8_t *>(d_rows_v), 3 * (br + bc + bu), ctx->d_rowoff.as<int64_t>(),
+                        ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>());
+      if (rc == ELECTOR_OK)
+        rc = tally_device(ctx, nr, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(), ctx->d_moff.as<int64_t>(),
+                          ctx->d_mlen.as<int32_t>(), ctx->d_tally_out.as<int64_t>(), ctx->merged_cap);
+      if (rc != ELECTOR_OK) { ctx->wait_in[0] = ctx->wait_in[1] = nullptr; cudaStreamSynchronize(st); return rc; }
+      tally_sum_kernel<<<std::min<int>(64, (int)((nr + 7) / 8)), 256, 0, st>>>(nr, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
+      CU(cudaGetLastError());
+      ++ctx->last_launches;
+      CU(cudaEventRecord(ctx->ev1, st));   // the chunk's device time covers merge + tally too
+      CU(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(ctx->h_sums + ELECTOR_TALLY_K, ctx->d_ctrl.as<int32_t>() + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(pa.counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.p, nr * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+    }
+    // the alignment results leave on the copy stream while merge and tally run: the host waits for the POA kernels only
+    // to learn how many row bytes the chunk used.  The linear region first: its segments run next to phase 1 and finish early.
+    const int64_t end_b = j.rows_base + j.rows_len;
+    int64_t base_b = end_b, used_b = end_b;
+    if (j.split) {
+      CU(cudaEventSynchronize(ctx->ev_lin));
+      used_b = ctx->h_totals[6]; base_b = ctx->h_totals[7];
+      if (base_b >= j.rows_base && used_b > base_b && used_b <= end_b)
+        CU(cudaMemcpyAsync(pa.rows_out + base_b, d_rows_v + base_b, used_b - base_b, cudaMemcpyDeviceToHost, so));
+    }
+    CU(cudaEventSynchronize(ctx->ev_rows));
+    ctx->wait_in[0] = ctx->wait_in[1] = nullptr;   // the letters have arrived: a second attempt does not wait for them again
+    rc = check_tables(ctx);
+    if (rc == 1 && attempt < 3) {   // a scratch pool was too small (first call, or longer windows than before): grown, run the chunk again
+      CU(cudaStreamSynchronize(st));
+      CU(cudaStreamSynchronize(so));
+      if (ctx->trace) fprintf(stderr, "[elector trace] chunk w%lld: scratch pools grown to %zu / %zu / %zu MiB, running it again\n", (long long)w0,
+                              ctx->d_scratch.cap >> 20, ctx->d_scratch_lin.cap >> 20, ctx->d_scratch2.cap >> 20);
+      continue;
+    }
+    if (rc != ELECTOR_OK) { cudaStreamSynchronize(st); cudaStreamSynchronize(so); return rc == 1 ? ctx->fail(ELECTOR_ECUDA, "scratch pools keep overflowing") : rc; }
+    const int64_t used = ctx->h_totals[4];
+    if ((int32_t)(ctx->h_totals[5] & 0xffffffff) || used > base_b || used_b > end_b) {
+      cudaStreamSynchronize(st);
+      cudaStreamSynchronize(so);
+      return ctx->fail(ELECTOR_ECAPACITY, "rows of a chunk exceed their bound (%lld + %lld > %lld)", (long long)(used - j.rows_base), (long long)(used_b - base_b),
+                       (long long)j.rows_len);
+    }
+    CU(cudaMemcpyAsync(pa.rows_out + j.rows_base, ctx->d_rows.p, used - j.rows_base, cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(pa.row_off + w0, ctx->d_rowoff.p, nw * 8, cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(pa.row_stride + w0, ctx->d_stride.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    CU(cudaMemcpyAsync(pa.nring + w0, ctx->d_nring.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    if (pa.score1) CU(cudaMemcpyAsync(pa.score1 + w0, ctx->d_s1.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    if (pa.score2) CU(cudaMemcpyAsync(pa.score2 + w0, ctx->d_s2.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    if (pa.cells) CU(cudaMemcpyAsync(pa.cells + w0, ctx->d_cells.p, nw * 8, cudaMemcpyDeviceToHost, so));
+    if (ctx->trace) CU(cudaEventRecord(ctx->uev1, so));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(so));
+    break;
   }
-  CU(cudaMemcpyAsync(pa.rows_out + j.rows_base, ctx->d_rows.p, used - j.rows_base, cudaMemcpyDeviceToHost, so));
-  CU(cudaMemcpyAsync(pa.row_off + w0, ctx->d_rowoff.p, nw * 8, cudaMemcpyDeviceToHost, so));
-  CU(cudaMemcpyAsync(pa.row_stride + w0, ctx->d_stride.p, nw * 4, cudaMemcpyDeviceToHost, so));
-  CU(cudaMemcpyAsync(pa.nring + w0, ctx->d_nring.p, nw * 4, cudaMemcpyDeviceToHost, so));
-  if (pa.score1) CU(cudaMemcpyAsync(pa.score1 + w0, ctx->d_s1.p, nw * 4, cudaMemcpyDeviceToHost, so));
-  if (pa.score2) CU(cudaMemcpyAsync(pa.score2 + w0, ctx->d_s2.p, nw * 4, cudaMemcpyDeviceToHost, so));
-  if (pa.cells) CU(cudaMemcpyAsync(pa.cells + w0, ctx->d_cells.p, nw * 8, cudaMemcpyDeviceToHost, so));
-  if (ctx->trace) CU(cudaEventRecord(ctx->uev1, so));
-  CU(cudaStreamSynchronize(st));
-  CU(cudaStreamSynchronize(so));
   if (ctx->trace) {   // device timeline of the chunk, ms after the start of the call
     float t[6] = {0, 0, 0, 0, 0, 0};
     cudaEventElapsedTime(&t[0], pa.ev_call, ctx->uev0); cudaEventElapsedTime(&t[1], pa.ev_call, ctx->ev0);
@@ -619,11 +675,9 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   ctx->mat = mat;
   if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
   ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
-  if (const char *e = getenv("ELECTOR_ALL_SIDE")) ctx->all_side = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_IDENT")) ctx->no_ident = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_DUAL")) ctx->no_dual = e[0] == '1';
   if (const char *e = getenv("ELECTOR_BAND_W")) ctx->band_w = std::max(0, std::min(64, atoi(e)));
-  if (const char *e = getenv("ELECTOR_NO_LINEAR2")) ctx->no_linear2 = e[0] == '1';
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0) {
@@ -646,6 +700,12 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->ev_in[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->uev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->uev1)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->lin_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_lin_done)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_fork_v[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_fork_v[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_fork_v[2], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMallocHost((void **)&ctx->h_bintab, 2 * sizeof(BinTable))) != cudaSuccess ||
@@ -693,7 +753,7 @@ void elector_poa_free(elector_ctx *ctx) {
   ctx->workers.clear();
   if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
-                    &ctx->d_items, &ctx->d_scratch, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_key2, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
+                    &ctx->d_items, &ctx->d_scratch, &ctx->d_scratch_lin, &ctx->d_scratch2, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_key2, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
                     &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_wdst, &ctx->d_sums, &ctx->d_tally_scan, &ctx->d_tally_out,
                     &ctx->d_readfirst, &ctx->d_mtot, &ctx->d_moff, &ctx->d_mlen, &ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
   for (DevBuf *b : bufs) b->release();
@@ -707,13 +767,16 @@ void elector_poa_free(elector_ctx *ctx) {
   if (ctx->uev0) cudaEventDestroy(ctx->uev0);
   if (ctx->uev1) cudaEventDestroy(ctx->uev1);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
+  if (ctx->ev_lin_done) cudaEventDestroy(ctx->ev_lin_done);
+  for (int k = 0; k < 3; ++k) if (ctx->ev_fork_v[k]) cudaEventDestroy(ctx->ev_fork_v[k]);
+  if (ctx->lin_stream) cudaStreamDestroy(ctx->lin_stream);
   for (int k = 0; k < kSideStreams; ++k) {
     if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
     if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
   }
   if (ctx->h_bintab) cudaFreeHost(ctx->h_bintab);
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : ctx->seg_ev_pool) cudaEventDestroy(e);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -738,21 +801,27 @@ int elector_poa_run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const
   if (n < 0 || (n > 0 && (!d_ref || !d_cor || !d_unc || !d_roff || !d_coff || !d_uoff || !d_rows || !d_rowoff || !d_stride || !d_nring)))
     return ctx->fail(ELECTOR_EINVAL, "null argument");
   CU(cudaSetDevice(ctx->device));
-  (void)h_roff; (void)h_coff; (void)h_uoff;  // binning happens on the device
+  (void)h_uoff;   // binning happens on the device; the host copies of the ref / cor offsets spare a read-back of their totals
   ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   ctx->last_ms = ctx->last_ms_phase1 = 0.f;
   ctx->last_launches = 0;
-  int rc = run_device(ctx, n, d_ref, d_roff, d_cor, d_coff, d_unc, d_uoff, d_rows, rows_cap,
-                      d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells, ctx->d_ctrl.as<unsigned long long>(),
-                      ctx->d_ctrl.as<int32_t>() + 2);
-  if (rc != ELECTOR_OK) return rc;
-  if (d_rows_used)
-    CU(cudaMemcpyAsync(d_rows_used, ctx->d_ctrl.p, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-  int32_t ctrl[4] = {0, 0, 0, 0};
-  CU(cudaMemcpyAsync(ctrl, ctx->d_ctrl.p, sizeof ctrl, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (n > 0) add_kernel_ms(ctx);
-  if (ctrl[2]) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small", (long long)rows_cap);
+  for (int attempt = 0;; ++attempt) {
+    int rc = run_device(ctx, n, d_ref, d_roff, d_cor, d_coff, d_unc, d_uoff, h_roff, h_coff, d_rows, rows_cap,
+                        d_rowoff, d_stride, d_nring, d_s1, d_s2, d_cells, ctx->d_ctrl.as<unsigned long long>(),
+                        ctx->d_ctrl.as<int32_t>() + 2);
+    if (rc != ELECTOR_OK) return rc;
+    if (d_rows_used)
+      CU(cudaMemcpyAsync(d_rows_used, ctx->d_ctrl.p, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // the one wait of the call
+    if (n == 0) return ELECTOR_OK;
+    rc = check_tables(ctx);
+    if (rc == 1 && attempt < 3) continue;     // a scratch pool was too small and has been grown: run the call again
+    if (rc != ELECTOR_OK) return rc == 1 ? ctx->fail(ELECTOR_ECUDA, "scratch pools keep overflowing") : rc;
+    break;
+  }
+  add_kernel_ms(ctx);
+  if ((int32_t)(ctx->h_totals[5] & 0xffffffff)) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small", (long long)rows_cap);
   return ELECTOR_OK;
 }
 

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
   __shared__ Layout2 s_layout;
   __shared__ uint32_t s_bset[2 * kSlotWords];
   const int lane = threadIdx.x;
+  if (!seg_setup(a)) return;
   Phase2<GENERIC_SUB> c;
   uint32_t *const warp_scratch = a.scratch + (size_t)blockIdx.x * a.warp_words * 32;
   c.scr.base = warp_scratch + lane;
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
   __shared__ LayoutC1 s_layout;
   __shared__ uint32_t s_bset[2 * kSlotWords];
   const int lane = threadIdx.x;
+  if (!seg_setup(a)) return;
   Phase2<GENERIC_SUB> c;
   uint32_t *const warp_scratch = a.scratch + (size_t)blockIdx.x * a.warp_words * 32;
   c.scr.base = warp_scratch + lane;

@@ -127,13 +127,21 @@ EL_HD void make_layout2(Layout2 &L, int N1, int LU) {
 struct PoaArgs {
   const uint8_t *ref, *cor, *unc;  // raw FASTA letters, concatenated
   const int64_t *ref_off, *cor_off, *unc_off;
-  const int32_t *items;  // window ids of this launch (one segment of the sorted list), largest first
-  int32_t n_items;
+  // a launch = one segment of a sorted work list; the five fields marked (plan) are filled in by the kernel itself from the
+  // segment's device-side plan (tab->plan[seg], bin_kernel.cuh): the host launches a fixed grid and never sees the sort's result
+  const struct BinTable *tab;
+  int32_t seg;
+  const int32_t *items_base;   // the sorted work list of the segment's sort
+  uint32_t *scratch_base;      // the scratch pool of the segment's phase
+  int32_t *ctrl;               // control words of the call (work counters, cursors)
+  const long long *rows_cap_dev;   // when set: the end of the segment's row region is read from here (two row regions per call)
+  const int32_t *items;  // (plan) window ids of this launch, largest first
+  int32_t n_items;       // (plan)
   int32_t match, mismatch, open, ext;
-  uint32_t *scratch;     // grid x warp_words x 32 words
-  uint32_t warp_words;   // scratch words per thread (layout of the segment's maxima)
+  uint32_t *scratch;     // (plan) max_ctas x warp_words x 32 words
+  uint32_t warp_words;   // (plan) scratch words per thread (layout of the segment's maxima)
   uint32_t arena_words;  // shared-memory arena words per thread (dynamic shared memory of the launch / 128)
-  int32_t *work_counter;
+  int32_t *work_counter; // (plan)
   // phase 1 -> phase 2
   uint16_t *p1_nodes;    // P1 node list of window w at [p1_offset(ref_off[w] - ref_off[0], cor_off[w] - cor_off[0], w)], n1[w] entries
   int64_t ro0, co0;      // ref_off[0], cor_off[0] of this call (offsets may be absolute positions in a larger buffer)
@@ -141,7 +149,6 @@ struct PoaArgs {
   int32_t *key2;         // phase-2 sort bin of the window
   int32_t *hist2;        // phase-2 histogram (filled by phase 1)
   int32_t *seg2_max;     // phase-2 segment maxima: [seg*4 + {0: n1, 1: lu}]
-  unsigned long long *lin_bytes;  // sum of the row-byte bounds of the windows that go to the linear segments of phase 2
   // results
   uint8_t *rows_out;
   unsigned long long *rows_cursor;
@@ -197,13 +204,15 @@ EL_HD int big_tier(int mx) {            // mx > kSmallMax: 1: <= 512, 2: <= 1024
 EL_HD int seg2_of_nb(int nb8) { return kBigTiers + (nb8 > 16 ? 0 : nb8 > 8 ? 1 : nb8 > 4 ? 2 : 3); }
 // largest first: big tiers, then the small general bins descending in (half-bands of unc, len(P1)/4, spcode),
 // then the small linear bins (spcode 0: DP2 is a linear x linear DP, run by Phase2L) descending in (half-bands, len(P1)/4)
-EL_HD void bin2_of(int n1, int lu, int spcode, int &bin, int &seg) {
+// linear: the window's cor IS its ref (recognised by the size sort, never ran phase 1): Phase2L, sorted and launched
+// while phase 1 still runs.  A window that went through phase 1 goes to the general bins whatever its spcode.
+EL_HD void bin2_of(int n1, int lu, int spcode, bool linear, int &bin, int &seg) {
   if (lu > kSmallMax || n1 >= 4 * kN1q) {
     const int t = big_tier(n1 > lu ? n1 : lu);
     bin = seg = kBigTiers - t;
   } else {
     const int nb8 = (lu + 7) >> 3;
-    if (spcode == 0) {
+    if (linear) {
       int dc = (lu - n1 + 6) >> 2;        // d in [-6,-3] [-2,1] [2,5] [6,9]; the tails join the outer classes
       dc = dc < 0 ? 0 : dc > kDcls - 1 ? kDcls - 1 : dc;
       const int lin = ((nb8 - 1) * kN1q + (n1 >> 2)) * kDcls + dc;
@@ -870,25 +879,25 @@ __device__ __forceinline__ void warp_hist_add(int32_t *hist, int bin) {
 }
 
 // What phase 1 leaves for phase 2 (all lanes call it; inactive lanes pass active = false): len(P1), the sort bin, the
-// histogram and maxima of sort 2, and the row bytes the windows of the linear segments can need (one atomic per warp).
+// histogram and maxima of the sort of the general segments.
 __device__ __forceinline__ void phase1_epilogue(const PoaArgs &a, bool active, int w, int n1, int s1, int spcode, int lr, int lc) {
-  unsigned lb = 0;
+  (void)lr; (void)lc;
   if (active) {
     const int lu = (int)(a.unc_off[w + 1] - a.unc_off[w]);
     int bin, seg;
-    bin2_of(n1, lu, spcode, bin, seg);
+    bin2_of(n1, lu, spcode, false, bin, seg);
     a.n1[w] = n1;
     a.key2[w] = bin;
     if (a.score1) a.score1[w] = s1;
     warp_hist_add(a.hist2, bin);
     if (n1 > a.seg2_max[seg * 4]) atomicMax(&a.seg2_max[seg * 4], n1);
     if (lu > a.seg2_max[seg * 4 + 1]) atomicMax(&a.seg2_max[seg * 4 + 1], lu);
-    if (seg >= kFirstLinSeg2) lb = 3u * (unsigned)((lr + lc + lu + 3) & ~3);
   }
-  for (int d = 16; d > 0; d >>= 1) lb += __shfl_xor_sync(EL_WARP_FULL, lb, d);
-  if (lb && threadIdx.x == 0) atomicAdd(a.lin_bytes, (unsigned long long)lb);
 }
 #endif
+
+// fills the (plan) fields of the launch from the segment's device-side plan; false: this CTA has no work (bin_kernel.cuh)
+__device__ __forceinline__ bool seg_setup(PoaArgs &a);
 
 // the per-warp arena in shared memory (dynamic: the host sizes it so that the kernel's register-bound residency is kept)
 extern __shared__ uint32_t s_arena[];
@@ -905,6 +914,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
   __shared__ uint32_t s_tab[(GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4];
   __shared__ typename PH::Layout s_layout;
   const int lane = threadIdx.x;
+  if (!seg_setup(a)) return;
   PH c;
   c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
@@ -991,6 +1001,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
   __shared__ typename PH::Layout s_layout;
   __shared__ uint32_t s_bset[2 * PH::kSetWords];
   const int lane = threadIdx.x;
+  if (!seg_setup(a)) return;
   PH c;
   c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
   c.bset = s_bset + lane;

@@ -48,6 +48,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     std::vector<uint64_t> nodes64(((size_t)lr + lc) / 4 + 2, 0xdeaddeaddeaddeadull);
     uint16_t *nodes_p = reinterpret_cast<uint16_t *>(nodes64.data());
     int s1, spcode, n1;
+    bool ident = false;   // cor is ref: no phase 1, phase 2 in the linear segments
     const int cap_r = lr + (int)(w % 3), cap_c = lc + (int)(w % 5);
     if (coop) {   // phase 1 through the warp-cooperative wavefront (lin(ref) as a node list)
       LayoutC1 L1;
@@ -67,6 +68,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     } else if (packed && !general_only && sc.packed_ok && lr == lc && lr <= kSmallMax && lu <= kSmallMax && memcmp(ref, cor, (size_t)lr) == 0) {
       // cor is ref: the size sort of the library (bin1_count_kernel) skips phase 1 -- P1 = lin(ref), every node carries both letters
       n1 = lr; s1 = 0; spcode = 0;
+      ident = true;
       ++n_ident1;
     } else if (packed && sc.packed_ok && (long)sc.maxabs * (cap_r + cap_c + 4) <= kPackedSpan) {
       Layout1P L1;
@@ -102,7 +104,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
       n1 = p1.run_window(ref, lr, cor, lc, nodes_p, s1, spcode, exact);
     }
     int bin, seg;
-    bin2_of(n1, lu, spcode, bin, seg);
+    bin2_of(n1, lu, spcode, ident, bin, seg);
     if (bin < 0 || bin >= kNumBins2 || seg < 0 || seg >= kNumSegs2) { fprintf(stderr, "bad phase-2 bin\n"); return 1; }
     // ---- phase 2 ----
     const int cap_n = n1 + (int)(w % 4), cap_u = lu + (int)(w % 2);
