@@ -62,15 +62,18 @@ struct BinTable {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ bool seg_setup(PoaArgs &a) {
+__device__ __forceinline__ bool seg_setup(const PoaArgs &a, SegRun &run) {
   const SegPlanDev &pl = a.tab->plan[a.seg];
-  if ((int)blockIdx.x >= pl.max_ctas) return false;
-  a.items = a.items_base + pl.start;
-  a.n_items = pl.count;
-  a.scratch = a.scratch_base + pl.scratch_off;
-  a.warp_words = pl.warp_words;
-  a.work_counter = a.ctrl + pl.counter;
-  if (a.rows_cap_dev) a.rows_cap = *a.rows_cap_dev;
+  if ((int)blockIdx.x >= pl.max_ctas) return false;   // uniform over the CTA
+  if (threadIdx.x == 0) {
+    run.items = a.items_base + pl.start;
+    run.n_items = pl.count;
+    run.scratch = a.scratch_base + pl.scratch_off;
+    run.warp_words = pl.warp_words;
+    run.work_counter = a.ctrl + pl.counter;
+    run.rows_cap = a.rows_cap_dev ? *a.rows_cap_dev : a.rows_cap;
+  }
+  __syncwarp();
   return true;
 }
 #endif

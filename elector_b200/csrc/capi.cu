@@ -65,7 +65,8 @@ struct elector_ctx {
   cudaStream_t side[16] = {};   // one per segment that does not run on the main stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, uev0 = nullptr, uev1 = nullptr, ev_fork = nullptr, ev_rows = nullptr;
   cudaStream_t lin_stream = nullptr;   // the linear segments of phase 2 run next to phase 1
-  cudaEvent_t ev_fork_v[3] = {}, ev_sorted = nullptr, ev_lin_done = nullptr;
+  cudaEvent_t ev_fork_v[6] = {}, ev_sorted = nullptr, ev_lin_done = nullptr, ev_lin_sorted = nullptr;
+  cudaEvent_t ev_view[3][2][2] = {};   // ELECTOR_TRACE=2: start / end of the launches of a view (phase 1, linear, general) x (cooperative, others)
   float last_ms_phase1 = 0.f;  // sort 1 + phase-1 kernels of the last run (last_ms covers everything)
   cudaEvent_t ev_join[16] = {};
   elector::BinTable *h_bintab = nullptr;  // pinned: the two tables of the last call as the device left them (errors, scratch needs)
@@ -87,6 +88,10 @@ struct elector_ctx {
   bool no_dual = false;    // ELECTOR_NO_DUAL=1: general windows of phase 2 on the INT32 kernel with frontier sets
   int resident_ph2d = 0;
   bool no_ident = false;   // ELECTOR_NO_IDENT=1: windows whose cor is ref run DP1 like every other window
+  unsigned side_used = 0;        // side streams with launches that `st` has not been made to wait for yet
+  bool async_launch = false;     // ELECTOR_ASYNC_LAUNCH=1: no read-back of the plans; every segment is launched with a fixed grid (no host wait inside a call)
+  bool plans_on_host = false;
+  elector::BinTable *h_plan = nullptr;   // pinned: the plans of phase 1 / phase 2 of the current call
   // rows of a pipelined chunk in two regions: the windows of the linear segments of phase 2 (most windows, finished early)
   // write theirs behind their own cursor, so that they can leave for the host while the general windows still compute
   bool split_rows = false;          // set by process_chunk around run_device
@@ -124,7 +129,8 @@ int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uin
                  const int64_t *d_off, const int32_t *d_len, int64_t *d_counters, int64_t total_bytes);
 int check_scan_overflow(elector_ctx *ctx, int64_t n_reads);
 
-const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [3] tally overflow, [4..19] phase-1 and [20..35] phase-2 work counters, [36..37] rows cursor of the linear region, [38..39] where that region starts
+const size_t kCtrlWords = 64;  // d_ctrl: [0..1] rows cursor (u64), [2] error flag, [3] tally overflow, [4..19] phase-1 and [20..35] phase-2 work counters, [36..37] rows cursor of the linear region, [38..39] where that region starts, [41] abort flag
+const int kAbortWord = 41;     // d_ctrl[41]: the alignment kernels of the call did not (all) run; merge and tally leave at once
 const int kSideStreams = 16;   // >= kMaxSegs: no two segments of a phase share a side stream
 
 #ifndef EL_MIN_WARPS_PH1P
@@ -222,16 +228,20 @@ __device__ uint32_t layout_words(int phase, int kind, int m0, int m1) {
   Layout2 L; make_layout2(L, m0, m1); return L.total;
 }
 
-// one thread: a dozen segments.  split_rows: the view is the linear one of a call whose rows go to two regions -- the linear
-// segments write [cap_a, rows_cap), the general ones [cursor, cap_a); ctrl64[18] = cursor of the linear region, [19] = cap_a
+// one warp: a segment per lane, then lane 0 adds up the scratch.  split_rows: the view is the linear one of a call whose rows
+// go to two regions -- the linear segments write [cap_a, rows_cap), the general ones [cursor, cap_a); ctrl64[18] = cursor of
+// the linear region, [19] = cap_a
 __global__ void plan_segments_kernel(BinTable *tab, SegStatic ss, unsigned long long *ctrl64, long long rows_cap, int split_rows) {
-  if (threadIdx.x || blockIdx.x) return;
-  unsigned long long off = 0;
-  bool too_big = false;
-  for (int s = ss.seg0; s < ss.seg1; ++s) {
-    SegPlanDev pl;
-    pl.start = tab->seg[s].start; pl.count = tab->seg[s].count; pl.counter = ss.counter0 + s; pl.pad = 0;
-    pl.warp_words = 0; pl.max_ctas = 0; pl.scratch_off = off;
+  __shared__ unsigned long long s_words[32];
+  __shared__ int s_big;
+  const int lane = threadIdx.x, s = ss.seg0 + lane;
+  if (lane == 0) s_big = 0;
+  __syncwarp();
+  SegPlanDev pl;
+  pl.start = pl.count = pl.max_ctas = pl.counter = 0; pl.warp_words = pl.pad = 0; pl.scratch_off = 0;
+  unsigned long long words = 0;
+  if (s < ss.seg1) {
+    pl.start = tab->seg[s].start; pl.count = tab->seg[s].count; pl.counter = ss.counter0 + s;
     if (pl.count > 0) {
       pl.warp_words = layout_words(ss.phase, ss.kind[s], tab->seg_max[s * 4], tab->seg_max[s * 4 + 1]);
       const int per = ss.kind[s] == kCoop ? ss.coop_group : 32;
@@ -240,20 +250,32 @@ __global__ void plan_segments_kernel(BinTable *tab, SegStatic ss, unsigned long 
       const unsigned long long per_warp = (unsigned long long)pl.warp_words * 32;
       while (ctas > 1 && per_warp * (unsigned long long)ctas > ss.budget_words / 2) ctas = (ctas + 1) / 2;   // huge windows: fewer warps in flight
       pl.max_ctas = (int32_t)ctas;
-      off += per_warp * (unsigned long long)ctas;
-      if (per_warp * (unsigned long long)ctas > ss.budget_words) too_big = true;
+      words = per_warp * (unsigned long long)ctas;
+      if (words > ss.budget_words) s_big = 1;
     }
+  }
+  s_words[lane] = words;
+  __syncwarp();
+  unsigned long long off = 0, total = 0;
+  for (int k = 0; k < 32; ++k) { if (k == lane) off = total; total += s_words[k]; }
+  const bool invalid = ss.phase == 1 && (tab->err_code == 1 || tab->err_code == 2);   // a window the kernels cannot take (the size sort said so)
+  const bool overflow = total > ss.pool_words || s_big;
+  if (s < ss.seg1) {
+    pl.scratch_off = off;
+    if (overflow) pl.max_ctas = 0;   // nothing of this view runs; the host grows the pool and runs the call again
     tab->plan[s] = pl;
   }
-  if (off > ss.pool_words || too_big) {   // nothing of this view runs; the host grows the pool and runs the call again
-    for (int s = ss.seg0; s < ss.seg1; ++s) tab->plan[s].max_ctas = 0;
-    if (tab->err_code == 0) tab->err_code = too_big ? 4 : 3;
-    if (off > tab->need_words) tab->need_words = off;
-  }
-  if (split_rows) {
-    const unsigned long long cap_a = (unsigned long long)((rows_cap - (long long)tab->lin_bytes) & ~15ll);
-    ctrl64[18] = cap_a;
-    ctrl64[19] = cap_a;
+  if (lane == 0) {
+    if (overflow) {
+      if (tab->err_code == 0) tab->err_code = s_big ? 4 : 3;
+      if (total > tab->need_words) tab->need_words = total;
+    }
+    if (overflow || invalid) reinterpret_cast<int32_t *>(ctrl64)[kAbortWord] = 1;   // merge and tally have nothing defined to work on
+    if (split_rows) {
+      const unsigned long long cap_a = (unsigned long long)((rows_cap - (long long)tab->lin_bytes) & ~15ll);
+      ctrl64[18] = cap_a;
+      ctrl64[19] = cap_a;
+    }
   }
 }
 
@@ -307,29 +329,64 @@ int sort_view(elector_ctx *ctx, cudaStream_t st, const SortView &v, int32_t n, i
 }
 
 // every segment of a view on its own side stream (side[first_side ...]), forked from and joined back into `st`
-int launch_view(elector_ctx *ctx, cudaStream_t st, const SortView &v, const SegStatic &ss, PoaArgs base, int first_side, bool region_b) {
-  cudaEvent_t fork = ctx->ev_fork_v[v.phase == 1 ? 0 : v.seg0 >= kFirstLinSeg2 ? 1 : 2];
+// which: 0 = the warp-cooperative segments, 1 = the others, 2 = all (cooperative first).
+// A segment with a large share of the call's windows (bulk) goes to `st` itself, behind the bulk segments launched before it;
+// the others get a side stream each, starting behind what `st` holds at this moment.  (Measured on config 1: two bulk kernels
+// side by side are slower than one after the other -- each alone fills the SMs, together they evict each other's scratch
+// from the L2.)  join_view makes `st` wait for the side streams -- after ALL launches of a phase: a join between two passes
+// would serialise them.
+int launch_view(elector_ctx *ctx, cudaStream_t st, const SortView &v, const SegStatic &ss, PoaArgs base, int first_side, bool region_b, int64_t n, int which = 2) {
+  cudaEvent_t fork = ctx->ev_fork_v[(v.phase == 1 ? 0 : v.seg0 >= kFirstLinSeg2 ? 1 : 2) + (which == 1 ? 3 : 0)];
+  // exact mode (read_plans): only the segments that have work are launched, with the grids the device planned
+  const BinTable *host_tab = ctx->plans_on_host ? &ctx->h_plan[v.phase - 1] : nullptr;
   CU(cudaEventRecord(fork, st));
+  const int vi = v.phase == 1 ? 0 : v.seg0 >= kFirstLinSeg2 ? 1 : 2;
+  if (ctx->trace) for (int w2 = 0; w2 < 2; ++w2) if (which == 2 || which == w2) CU(cudaEventRecord(ctx->ev_view[vi][w2][0], st));
   int nregb = 0;
   // the warp-cooperative segments first (they hold the longest windows and set the latency floor of a call)
   for (int pass = 0; pass < 2; ++pass)
     for (int s = v.seg0; s < v.seg1; ++s) {
       const int kind = ss.kind[s];
-      if ((kind == kCoop) != (pass == 0)) continue;
-      cudaStream_t ls = ctx->side[first_side + (s - v.seg0)];
-      CU(cudaStreamWaitEvent(ls, fork, 0));
+      if ((kind == kCoop) != (pass == 0) || (which != 2 && which != pass)) continue;
+      if (host_tab && host_tab->plan[s].max_ctas == 0) continue;
+      const int grid = host_tab ? host_tab->plan[s].max_ctas : ss.grid[s];
+      // bulk: by its share of the windows when the plans are here, else the segments of the small windows (where the bulk of
+      // ELECTOR's windows is: at most 64 rows)
+      const bool bulk = kind != kCoop && (host_tab ? (int64_t)host_tab->plan[s].count * 8 > n : s >= v.seg1 - 2);
+      const int side = first_side + (s - v.seg0);
+      cudaStream_t ls = bulk ? st : ctx->side[side];
+      if (!bulk) CU(cudaStreamWaitEvent(ls, fork, 0));
       PoaArgs a = base;
       a.tab = v.dtab; a.seg = s; a.items_base = v.items; a.scratch_base = v.pool->as<uint32_t>(); a.ctrl = ctx->d_ctrl.as<int32_t>();
       const bool linear_seg = v.phase == 2 && s >= kFirstLinSeg2;
-      const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(v.phase, kind, ls, a, ss.grid[s], ctx->d_tab.as<SymbolTables>(), ss.coop_group, linear_seg, ctx)
-                                                : launch_phase<false>(v.phase, kind, ls, a, ss.grid[s], ctx->d_tab.as<SymbolTables>(), ss.coop_group, linear_seg, ctx);
+      const cudaError_t e = ctx->sc.generic_sub ? launch_phase<true>(v.phase, kind, ls, a, grid, ctx->d_tab.as<SymbolTables>(), ss.coop_group, linear_seg, ctx)
+                                                : launch_phase<false>(v.phase, kind, ls, a, grid, ctx->d_tab.as<SymbolTables>(), ss.coop_group, linear_seg, ctx);
       if (e != cudaSuccess) return ctx->fail(ELECTOR_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
       ++ctx->last_launches;
-      cudaEvent_t done = ctx->ev_join[first_side + (s - v.seg0)];
-      CU(cudaEventRecord(done, ls));
-      CU(cudaStreamWaitEvent(st, done, 0));
+      cudaEvent_t done = ctx->ev_join[side];
+      if (!bulk || region_b) CU(cudaEventRecord(done, ls));
+      if (!bulk) ctx->side_used |= 1u << side;
       if (region_b && nregb < 8) { CU(cudaStreamWaitEvent(ctx->copy_out, done, 0)); ++nregb; }
     }
+  return ELECTOR_OK;
+}
+// The plans of a phase, read back (one wait of the host per phase): without ELECTOR_ASYNC_LAUNCH=1 the host launches only the
+// segments that have work, with exact grids.  Measured on config 1: fixed-grid launches of all 27 segments (most of them
+// empty, thousands of CTAs that leave at once) cost 0.4 ms per phase, a read-back 0.03 ms.
+int read_plans(elector_ctx *ctx, int phase, BinTable *dtab, cudaStream_t a, cudaStream_t b) {
+  ctx->plans_on_host = false;
+  if (ctx->async_launch) return ELECTOR_OK;
+  if (b) CU(cudaStreamSynchronize(b));
+  CU(cudaMemcpyAsync(&ctx->h_plan[phase - 1], dtab, sizeof(BinTable), cudaMemcpyDeviceToHost, a));
+  CU(cudaStreamSynchronize(a));
+  ctx->plans_on_host = true;
+  return ELECTOR_OK;
+}
+// `st` waits for the side streams side[first .. first + count - 1] that have launched something since the last join
+int join_view(elector_ctx *ctx, cudaStream_t st, int first, int count, int view) {
+  for (int k = first; k < first + count; ++k)
+    if (ctx->side_used & (1u << k)) { CU(cudaStreamWaitEvent(st, ctx->ev_join[k], 0)); ctx->side_used &= ~(1u << k); }
+  if (ctx->trace) { CU(cudaEventRecord(ctx->ev_view[view][0][1], st)); CU(cudaEventRecord(ctx->ev_view[view][1][1], st)); }
   return ELECTOR_OK;
 }
 
@@ -404,9 +461,15 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   const SortView vL{dtab2, 2, kFirstLinSeg2, kNumSegs2, lin_bin0, kNumBins2, hist2, chunksL, ctx->d_key2.as<int32_t>(), itemsL, &ctx->d_scratch_lin, 20};
   const SortView v2{dtab2, 2, 0, kFirstLinSeg2, 0, lin_bin0, hist2, chunks2, ctx->d_key2.as<int32_t>(), items2, &ctx->d_scratch2, 20};
   SegStatic ss1, ssL, ss2;
+  // the sort of phase 1 on the main stream; that of the linear segments of phase 2 (their keys and histogram are complete
+  // after the size sort) on the linear stream, next to phase 1
+  cudaStream_t sl = ctx->lin_stream;
+  CU(cudaEventRecord(ctx->ev_sorted, st));
+  CU(cudaStreamWaitEvent(sl, ctx->ev_sorted, 0));
   int rc = sort_view(ctx, st, v1, (int32_t)n, bgrid, ss1, rows_cap, false);
-  if (rc == ELECTOR_OK) rc = sort_view(ctx, st, vL, (int32_t)n, bgrid, ssL, rows_cap, ctx->split_rows);
+  if (rc == ELECTOR_OK) rc = sort_view(ctx, sl, vL, (int32_t)n, bgrid, ssL, rows_cap, ctx->split_rows);
   if (rc != ELECTOR_OK) return rc;
+  CU(cudaEventRecord(ctx->ev_lin_sorted, sl));
 
   PoaArgs a;
   memset(&a, 0, sizeof a);
@@ -422,41 +485,42 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   a.band_w = ctx->band_w;
   a.band_span = band_span_limit(ctx->sc.maxabs);
 
-  // ---- linear segments of phase 2: their own stream, next to phase 1 ----
-  cudaStream_t sl = ctx->lin_stream;
-  CU(cudaEventRecord(ctx->ev_sorted, st));
-  CU(cudaStreamWaitEvent(sl, ctx->ev_sorted, 0));
-  if (ctx->wait_in[0]) CU(cudaStreamWaitEvent(sl, ctx->wait_in[0], 0));
-  if (ctx->wait_in[1]) CU(cudaStreamWaitEvent(sl, ctx->wait_in[1], 0));
-  {
-    PoaArgs al = a;
-    if (ctx->split_rows) {   // two row regions: the linear segments behind their own cursor, up to the end of the buffer
-      al.rows_cursor = ctx->d_ctrl.as<unsigned long long>() + 18;
-    }
-    rc = launch_view(ctx, sl, vL, ssL, al, 12, ctx->split_rows);
-    if (rc != ELECTOR_OK) return rc;
-    if (ctx->split_rows) {   // the copy stream learns where the linear region starts and ends as soon as its last segment is done
-      CU(cudaMemcpyAsync(&ctx->h_totals[6], ctx->d_ctrl.as<unsigned long long>() + 18, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_out));
-      CU(cudaEventRecord(ctx->ev_lin, ctx->copy_out));
-    }
-    CU(cudaEventRecord(ctx->ev_lin_done, sl));
-  }
   // ---- phase 1 ----
+  rc = read_plans(ctx, 1, dtab1, st, nullptr);
+  if (rc != ELECTOR_OK) return rc;
   if (ctx->wait_in[0]) CU(cudaStreamWaitEvent(st, ctx->wait_in[0], 0));
-  rc = launch_view(ctx, st, v1, ss1, a, 0, false);
+  rc = launch_view(ctx, st, v1, ss1, a, 0, false, n);
+  if (rc == ELECTOR_OK) rc = join_view(ctx, st, 0, 12, 0);
   if (rc != ELECTOR_OK) return rc;
   CU(cudaEventRecord(ctx->ev_mid, st));
-  // ---- general segments of phase 2 (phase 1 filled key2, hist2 and the segment maxima) ----
+  // ---- phase 2: the linear segments (sorted by the size sort; with two row regions theirs leaves for the host as soon as they
+  // are done) on the linear stream, the general segments (phase 1 filled their keys, histogram and maxima) on the main stream.
+  // Launch order: the warp-cooperative segments of both (the longest windows: the latency floor of the call), then the linear
+  // segments, then the general ones.
+  // (Starting the linear segments next to phase 1 was measured slower on config 1, 6.96 against 6.72 ms per step: the kernels of
+  // the two phases evict each other's scratch from the L2.)
+  PoaArgs al = a, ag = a;
+  if (ctx->split_rows) {
+    al.rows_cursor = ctx->d_ctrl.as<unsigned long long>() + 18;   // two row regions: the linear segments behind their own cursor, up to the end of the buffer
+    ag.rows_cap_dev = reinterpret_cast<const long long *>(ctx->d_ctrl.as<unsigned long long>() + 19);   // the general region ends where the linear one starts
+  }
   rc = sort_view(ctx, st, v2, (int32_t)n, bgrid, ss2, rows_cap, false);
+  if (rc == ELECTOR_OK) rc = read_plans(ctx, 2, dtab2, st, sl);
   if (rc != ELECTOR_OK) return rc;
   if (ctx->wait_in[1]) CU(cudaStreamWaitEvent(st, ctx->wait_in[1], 0));
-  {
-    PoaArgs ag = a;
-    if (ctx->split_rows) ag.rows_cap_dev = reinterpret_cast<const long long *>(ctx->d_ctrl.as<unsigned long long>() + 19);   // the general region ends where the linear one starts
-    rc = launch_view(ctx, st, v2, ss2, ag, 0, false);
-    if (rc != ELECTOR_OK) return rc;
+  CU(cudaStreamWaitEvent(st, ctx->ev_lin_sorted, 0));
+  rc = launch_view(ctx, st, vL, ssL, al, 12, ctx->split_rows, n, 0);
+  if (rc == ELECTOR_OK) rc = launch_view(ctx, st, v2, ss2, ag, 0, false, n, 0);
+  if (rc == ELECTOR_OK) rc = launch_view(ctx, st, vL, ssL, al, 12, ctx->split_rows, n, 1);
+  if (rc != ELECTOR_OK) return rc;
+  if (ctx->split_rows) {   // the copy stream learns where the linear region starts and ends as soon as its last segment is done
+    CU(cudaMemcpyAsync(&ctx->h_totals[6], ctx->d_ctrl.as<unsigned long long>() + 18, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    CU(cudaEventRecord(ctx->ev_lin, ctx->copy_out));
   }
-  CU(cudaStreamWaitEvent(st, ctx->ev_lin_done, 0));
+  CU(cudaEventRecord(ctx->ev_lin_done, st));
+  rc = launch_view(ctx, st, v2, ss2, ag, 0, false, n, 1);
+  if (rc == ELECTOR_OK) rc = join_view(ctx, st, 0, 16, 2);
+  if (rc != ELECTOR_OK) return rc;
   CU(cudaMemcpyAsync(ctx->h_bintab, dtab1, 2 * sizeof(BinTable), cudaMemcpyDeviceToHost, st));   // errors and needs of the call
   CU(cudaEventRecord(ctx->ev1, st));
   return ELECTOR_OK;
@@ -466,6 +530,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
 // and has been grown: run the call again
 int check_tables(elector_ctx *ctx) {
   const BinTable *t1 = ctx->h_bintab, *t2 = ctx->h_bintab + 1;
+  if (t1->err_code || t2->err_code) cudaMemsetAsync(ctx->d_ctrl.as<int32_t>() + kAbortWord, 0, sizeof(int32_t), ctx->stream);   // for stand-alone merge / tally calls
   if (t1->err_code == 1) return ctx->fail(ELECTOR_EINVAL, "window %d has an empty sequence (undefined in the reference)", t1->err_window);
   if (t1->err_code == 2) return ctx->fail(ELECTOR_ETOOLARGE, "window %d: a sequence longer than %d letters, or reference + corrected longer than %d (16-bit node indices)", t1->err_window, kMaxWindowLen, kMaxNodes);
   if (t1->err_code == 4 || t2->err_code == 4) return ctx->fail(ELECTOR_ETOOLARGE, "a segment of the call needs %llu MiB of scratch (windows too long)", (unsigned long long)((std::max(t1->need_words, t2->need_words) * 4) >> 20));
@@ -489,6 +554,12 @@ void add_kernel_ms(elector_ctx *ctx) {
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) fprintf(stderr, "[elector trace]   phase 1 done %.3f ms", ms);
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_lin_done) == cudaSuccess) fprintf(stderr, ", linear segments of phase 2 done %.3f ms", ms);
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) fprintf(stderr, ", all done %.3f ms\n", ms);
+      static const char *vn[3] = {"phase 1", "phase 2 linear", "phase 2 general"};
+      for (int v = 0; v < 3; ++v) {
+        float t[4] = {-1, -1, -1, -1};
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], ctx->ev0, ctx->ev_view[v][k >> 1][k & 1]);
+        fprintf(stderr, "[elector trace]     %-16s launched at %.3f (cooperative) / %.3f (others), joined at %.3f ms\n", vn[v], t[0], t[2], t[3] > t[1] ? t[3] : t[1]);
+      }
     }
   }
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms += ms;
@@ -676,6 +747,7 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
   ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   if (const char *e = getenv("ELECTOR_NO_IDENT")) ctx->no_ident = e[0] == '1';
+  if (const char *e = getenv("ELECTOR_ASYNC_LAUNCH")) ctx->async_launch = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_DUAL")) ctx->no_dual = e[0] == '1';
   if (const char *e = getenv("ELECTOR_BAND_W")) ctx->band_w = std::max(0, std::min(64, atoi(e)));
   int ndev = 0;
@@ -703,12 +775,11 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
       (e = cudaStreamCreateWithFlags(&ctx->lin_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_lin_done)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_fork_v[0], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_fork_v[1], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_fork_v[2], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_lin_sorted, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMallocHost((void **)&ctx->h_bintab, 2 * sizeof(BinTable))) != cudaSuccess ||
+      (e = cudaMallocHost((void **)&ctx->h_plan, 2 * sizeof(BinTable))) != cudaSuccess ||
       (e = cudaMallocHost((void **)&ctx->h_totals, 8 * sizeof(int64_t))) != cudaSuccess ||
       (e = cudaMallocHost((void **)&ctx->h_sums, (ELECTOR_TALLY_K + 1) * sizeof(int64_t))) != cudaSuccess ||
       (e = ctx->d_tab.reserve(sizeof(SymbolTables))) != cudaSuccess ||
@@ -718,6 +789,12 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
     ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
     return bail(ELECTOR_ECUDA);
   }
+  for (int k = 0; k < 12; ++k) cudaEventCreate(&ctx->ev_view[k / 4][(k / 2) & 1][k & 1]);
+  for (int k = 0; k < 6; ++k)
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork_v[k], cudaEventDisableTiming)) != cudaSuccess) {
+      ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
+      return bail(ELECTOR_ECUDA);
+    }
   for (int k = 0; k < 8; ++k)
     if ((e = cudaEventCreateWithFlags(&ctx->ev_regb[k], cudaEventDisableTiming)) != cudaSuccess) {
       ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
@@ -769,13 +846,16 @@ void elector_poa_free(elector_ctx *ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
   if (ctx->ev_lin_done) cudaEventDestroy(ctx->ev_lin_done);
-  for (int k = 0; k < 3; ++k) if (ctx->ev_fork_v[k]) cudaEventDestroy(ctx->ev_fork_v[k]);
+  for (int k = 0; k < 6; ++k) if (ctx->ev_fork_v[k]) cudaEventDestroy(ctx->ev_fork_v[k]);
+  if (ctx->ev_lin_sorted) cudaEventDestroy(ctx->ev_lin_sorted);
+  for (int k = 0; k < 12; ++k) if (ctx->ev_view[k / 4][(k / 2) & 1][k & 1]) cudaEventDestroy(ctx->ev_view[k / 4][(k / 2) & 1][k & 1]);
   if (ctx->lin_stream) cudaStreamDestroy(ctx->lin_stream);
   for (int k = 0; k < kSideStreams; ++k) {
     if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
     if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
   }
   if (ctx->h_bintab) cudaFreeHost(ctx->h_bintab);
+  if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
   for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

@@ -210,9 +210,10 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
   __shared__ Layout2 s_layout;
   __shared__ uint32_t s_bset[2 * kSlotWords];
   const int lane = threadIdx.x;
-  if (!seg_setup(a)) return;
+  __shared__ SegRun s_run;
+  if (!seg_setup(a, s_run)) return;
   Phase2<GENERIC_SUB> c;
-  uint32_t *const warp_scratch = a.scratch + (size_t)blockIdx.x * a.warp_words * 32;
+  uint32_t *const warp_scratch = s_run.scratch + (size_t)blockIdx.x * s_run.warp_words * 32;
   c.scr.base = warp_scratch + lane;
   c.bset = s_bset + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
@@ -220,15 +221,15 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
   c.Lp = &s_layout;
   for (;;) {
     int base = 0;
-    if (lane == 0) base = atomicAdd(a.work_counter, group);
+    if (lane == 0) base = atomicAdd(s_run.work_counter, group);
     base = __shfl_sync(EL_WARP_FULL, base, 0);
-    if (base >= a.n_items) break;
-    const int cnt = min(group, a.n_items - base);
+    if (base >= s_run.n_items) break;
+    const int cnt = min(group, s_run.n_items - base);
     const bool owner = lane < cnt;
     int nring = 0, w = -1, n1 = 0, lu = 0;
     int64_t ro = 0, co = 0, uo = 0;
     if (owner) {
-      w = a.items[base + lane];
+      w = s_run.items[base + lane];
       ro = a.ref_off[w]; co = a.cor_off[w]; uo = a.unc_off[w];
       lu = (int)(a.unc_off[w + 1] - uo);
       n1 = a.n1[w];
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
       if (lane == 0) make_layout2(s_layout, mn, mu);
       __syncwarp();
     }
-    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
+    if (s_layout.total > s_run.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     c.fs.base = c.scr.base + (size_t)s_layout.o_fast * 32;   // long windows: the fast part stays in global scratch
     int nrings = 0;
     if (owner) {
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
     }
     __syncwarp();
     RowSink out;
-    if (alloc_window_rows(a, owner, w, nring, out)) c.fuse_emit(al, n1, lu, out);
+    if (alloc_window_rows(a, s_run.rows_cap, owner, w, nring, out)) c.fuse_emit(al, n1, lu, out);
     __syncwarp();
   }
 }
@@ -287,9 +288,10 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
   __shared__ LayoutC1 s_layout;
   __shared__ uint32_t s_bset[2 * kSlotWords];
   const int lane = threadIdx.x;
-  if (!seg_setup(a)) return;
+  __shared__ SegRun s_run;
+  if (!seg_setup(a, s_run)) return;
   Phase2<GENERIC_SUB> c;
-  uint32_t *const warp_scratch = a.scratch + (size_t)blockIdx.x * a.warp_words * 32;
+  uint32_t *const warp_scratch = s_run.scratch + (size_t)blockIdx.x * s_run.warp_words * 32;
   c.scr.base = warp_scratch + lane;
   c.bset = s_bset + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
@@ -297,15 +299,15 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
   c.Lp = &s_layout.l2;
   for (;;) {
     int base = 0;
-    if (lane == 0) base = atomicAdd(a.work_counter, group);
+    if (lane == 0) base = atomicAdd(s_run.work_counter, group);
     base = __shfl_sync(EL_WARP_FULL, base, 0);
-    if (base >= a.n_items) break;
-    const int cnt = min(group, a.n_items - base);
+    if (base >= s_run.n_items) break;
+    const int cnt = min(group, s_run.n_items - base);
     const bool owner = lane < cnt;
     int w = -1, lr = 0, lc = 0;
     int64_t ro = 0, co = 0;
     if (owner) {
-      w = a.items[base + lane];
+      w = s_run.items[base + lane];
       ro = a.ref_off[w]; co = a.cor_off[w];
       lr = (int)(a.ref_off[w + 1] - ro); lc = (int)(a.cor_off[w + 1] - co);
     }
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
       if (lane == 0) make_layout_c1(s_layout, mr, mc);
       __syncwarp();
     }
-    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
+    if (s_layout.total > s_run.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); break; }  // cannot happen (monotone layout)
     c.fs.base = c.scr.base + (size_t)s_layout.l2.o_fast * 32;
     uint16_t *p1_slot = owner ? a.p1_nodes + p1_offset(ro - a.ro0, co - a.co0, w) : nullptr;
     if (owner) coop1_before<GENERIC_SUB>(c, s_layout, a.ref + ro, lr, a.cor + co, lc, p1_slot);

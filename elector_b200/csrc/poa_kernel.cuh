@@ -127,21 +127,16 @@ EL_HD void make_layout2(Layout2 &L, int N1, int LU) {
 struct PoaArgs {
   const uint8_t *ref, *cor, *unc;  // raw FASTA letters, concatenated
   const int64_t *ref_off, *cor_off, *unc_off;
-  // a launch = one segment of a sorted work list; the five fields marked (plan) are filled in by the kernel itself from the
-  // segment's device-side plan (tab->plan[seg], bin_kernel.cuh): the host launches a fixed grid and never sees the sort's result
+  // a launch = one segment of a sorted work list; its slice of the list, scratch and work counter come from the segment's
+  // device-side plan (tab->plan[seg], bin_kernel.cuh; SegRun below)
   const struct BinTable *tab;
   int32_t seg;
   const int32_t *items_base;   // the sorted work list of the segment's sort
   uint32_t *scratch_base;      // the scratch pool of the segment's phase
   int32_t *ctrl;               // control words of the call (work counters, cursors)
-  const long long *rows_cap_dev;   // when set: the end of the segment's row region is read from here (two row regions per call)
-  const int32_t *items;  // (plan) window ids of this launch, largest first
-  int32_t n_items;       // (plan)
+  const long long *rows_cap_dev;   // when set: the end of the segment's row region is read from here instead of rows_cap (two row regions per call)
   int32_t match, mismatch, open, ext;
-  uint32_t *scratch;     // (plan) max_ctas x warp_words x 32 words
-  uint32_t warp_words;   // (plan) scratch words per thread (layout of the segment's maxima)
   uint32_t arena_words;  // shared-memory arena words per thread (dynamic shared memory of the launch / 128)
-  int32_t *work_counter; // (plan)
   // phase 1 -> phase 2
   uint16_t *p1_nodes;    // P1 node list of window w at [p1_offset(ref_off[w] - ref_off[0], cor_off[w] - cor_off[0], w)], n1[w] entries
   int64_t ro0, co0;      // ref_off[0], cor_off[0] of this call (offsets may be absolute positions in a larger buffer)
@@ -896,8 +891,18 @@ __device__ __forceinline__ void phase1_epilogue(const PoaArgs &a, bool active, i
 }
 #endif
 
-// fills the (plan) fields of the launch from the segment's device-side plan; false: this CTA has no work (bin_kernel.cuh)
-__device__ __forceinline__ bool seg_setup(PoaArgs &a);
+// What a CTA reads from its segment's device-side plan (bin_kernel.cuh), kept in SHARED memory: as kernel parameters these
+// were free constant-bank operands; as registers they cost the dual-frontier kernel 60 bytes of spills.
+struct SegRun {
+  const int32_t *items;    // window ids of this launch, largest first
+  int32_t n_items;
+  uint32_t warp_words;     // scratch words per lane (layout of the segment's maxima)
+  uint32_t *scratch;       // max_ctas x warp_words x 32 words
+  int32_t *work_counter;
+  long long rows_cap;      // end of the segment's row region
+};
+// false: this CTA has no work
+__device__ __forceinline__ bool seg_setup(const PoaArgs &a, SegRun &run);
 
 // the per-warp arena in shared memory (dynamic: the host sizes it so that the kernel's register-bound residency is kept)
 extern __shared__ uint32_t s_arena[];
@@ -914,9 +919,10 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
   __shared__ uint32_t s_tab[(GENERIC_SUB ? sizeof(SymbolTables) : offsetof(SymbolTables, sub)) / 4];
   __shared__ typename PH::Layout s_layout;
   const int lane = threadIdx.x;
-  if (!seg_setup(a)) return;
+  __shared__ SegRun s_run;
+  if (!seg_setup(a, s_run)) return;
   PH c;
-  c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
+  c.scr.base = s_run.scratch + (size_t)blockIdx.x * s_run.warp_words * 32 + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
   c.Lp = &s_layout;
@@ -938,7 +944,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
       // half-width: the base plus 1/16 of the rows (cor differs from ref by ~1 %: scores stay near 0)
       if constexpr (PH::kBanded) group_band(c.bw, banded && mr + mc <= a.band_span, a.band_w + (mc >> 4), active, lc - lr);
     }
-    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
+    if (s_layout.total > s_run.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
     c.fs.base = fast_base(a, s_layout, c.scr.base, lane);
     int s1 = 0, spcode = 0, n1 = 0;
     bool exact = true;
@@ -949,11 +955,11 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
   };
   for (;;) {
     int base = 0;
-    if (lane == 0) base = atomicAdd(a.work_counter, 32);
+    if (lane == 0) base = atomicAdd(s_run.work_counter, 32);
     base = __shfl_sync(EL_WARP_FULL, base, 0);
-    if (base >= a.n_items) break;
-    const bool active = base + lane < a.n_items;
-    const int w = active ? a.items[base + lane] : -1;
+    if (base >= s_run.n_items) break;
+    const bool active = base + lane < s_run.n_items;
+    const int w = active ? s_run.items[base + lane] : -1;
     const bool failed = process(w, active, a.band_w > 0);
     if constexpr (PH::kBanded) {
       if (queue_retries(s_retry, nretry, failed, w)) { const int w2 = s_retry[nretry + lane]; __syncwarp(); process(w2, true, false); }
@@ -968,7 +974,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
 // Output space for the MSA rows of a group: a warp prefix sum of 3*stride and ONE atomic per warp.  Every lane (active or
 // not) calls it; an active lane gets the sink of its window's three rows (nring columns), or false when the caller's row
 // buffer is too small (the error flag is then set).
-__device__ __forceinline__ bool alloc_window_rows(const PoaArgs &a, bool active, int w, int nring, RowSink &out) {
+__device__ __forceinline__ bool alloc_window_rows(const PoaArgs &a, long long rows_cap, bool active, int w, int nring, RowSink &out) {
   const int lane = threadIdx.x;
   const int stride = active ? (nring + 3) & ~3 : 0;
   const int bytes = 3 * stride;
@@ -985,7 +991,7 @@ __device__ __forceinline__ bool alloc_window_rows(const PoaArgs &a, bool active,
   const int64_t off = (int64_t)wbase + incl - bytes;
   a.row_off[w] = off;
   a.row_stride[w] = stride;
-  if (off + bytes > a.rows_cap) { atomicExch(a.error_flag, 1); return false; }
+  if (off + bytes > rows_cap) { atomicExch(a.error_flag, 1); return false; }
   out.r0 = reinterpret_cast<uint32_t *>(a.rows_out + off);
   out.r1 = out.r0 + (stride >> 2);
   out.r2 = out.r1 + (stride >> 2);
@@ -1001,9 +1007,10 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
   __shared__ typename PH::Layout s_layout;
   __shared__ uint32_t s_bset[2 * PH::kSetWords];
   const int lane = threadIdx.x;
-  if (!seg_setup(a)) return;
+  __shared__ SegRun s_run;
+  if (!seg_setup(a, s_run)) return;
   PH c;
-  c.scr.base = a.scratch + (size_t)blockIdx.x * a.warp_words * 32 + lane;
+  c.scr.base = s_run.scratch + (size_t)blockIdx.x * s_run.warp_words * 32 + lane;
   c.bset = s_bset + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
@@ -1027,7 +1034,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
       // half-width: the base plus 1/8 of the rows (unc differs from ref by ~10 %: the score is about minus the length)
       if constexpr (PH::kBanded) group_band(c.bw, banded && mn + mu <= a.band_span, a.band_w + (mu >> 3), active, lu - n1);
     }
-    if (s_layout.total > a.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
+    if (s_layout.total > s_run.warp_words) { if (lane == 0) atomicExch(a.error_flag, 2); return false; }  // cannot happen (monotone layout)
     c.fs.base = fast_base(a, s_layout, c.scr.base, lane);
     bool exact = true;
     AlignBits al = c.bits();
@@ -1046,17 +1053,17 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
     }
     __syncwarp();
     RowSink out;
-    if (alloc_window_rows(a, active && exact, w, nring, out)) c.fuse_emit(al, n1, lu, out);
+    if (alloc_window_rows(a, s_run.rows_cap, active && exact, w, nring, out)) c.fuse_emit(al, n1, lu, out);
     __syncwarp();
     return active && !exact;
   };
   for (;;) {
     int base = 0;
-    if (lane == 0) base = atomicAdd(a.work_counter, 32);
+    if (lane == 0) base = atomicAdd(s_run.work_counter, 32);
     base = __shfl_sync(EL_WARP_FULL, base, 0);
-    if (base >= a.n_items) break;
-    const bool active = base + lane < a.n_items;
-    const int w = active ? a.items[base + lane] : -1;
+    if (base >= s_run.n_items) break;
+    const bool active = base + lane < s_run.n_items;
+    const int w = active ? s_run.items[base + lane] : -1;
     const bool failed = process(w, active, a.band_w > 0);
     if constexpr (PH::kBanded) {
       if (queue_retries(s_retry, nretry, failed, w)) { const int w2 = s_retry[nretry + lane]; __syncwarp(); process(w2, true, false); }

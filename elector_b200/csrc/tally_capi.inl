@@ -9,7 +9,7 @@ int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uin
   const int64_t plane_words = (total_bytes >> 5) + n_reads + 2;
   CU(ctx->d_tally_scan.reserve((size_t)plane_words * 3 * sizeof(uint32_t)));
   tally_read_kernel<<<(unsigned)n_reads, 128, 0, ctx->stream>>>(n_reads, dR, dC, dU, d_off, d_len, ctx->d_tally_scan.as<uint32_t>(), plane_words,
-                                                               d_counters, ctx->d_ctrl.as<int32_t>() + 3);
+                                                               d_counters, ctx->d_ctrl.as<int32_t>() + 3, ctx->d_ctrl.as<int32_t>() + kAbortWord);
   CU(cudaGetLastError());
   ctx->last_launches += 1;
 #ifdef ELECTOR_TALLY_TIMING
@@ -37,14 +37,14 @@ int merge_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first,
   CU(ctx->d_mlen.reserve((n_reads + 1) * 4));
   CU(ctx->d_mref.reserve(cap)); CU(ctx->d_mcor.reserve(cap)); CU(ctx->d_munc.reserve(cap));
   CU(cudaMemcpyAsync(ctx->d_readfirst.p, h_read_first, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  read_totals_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_nring, ctx->d_mtot.as<int64_t>());
+  read_totals_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_nring, ctx->d_mtot.as<int64_t>(), ctx->d_ctrl.as<int32_t>() + kAbortWord);
   scan_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(n_reads, ctx->d_mtot.as<int64_t>(), ctx->d_moff.as<int64_t>());
   CU(ctx->d_wdst.reserve((size_t)n_windows * 8));
   merge_plan_kernel<<<(unsigned)((n_reads + 3) / 4), 128, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_rows, d_row_off, d_row_stride, d_nring,
-                                                                            ctx->d_moff.as<int64_t>(), ctx->d_wdst.as<int64_t>(), ctx->d_mlen.as<int32_t>());
+                                                                            ctx->d_moff.as<int64_t>(), ctx->d_wdst.as<int64_t>(), ctx->d_mlen.as<int32_t>(), ctx->d_ctrl.as<int32_t>() + kAbortWord);
   merge_copy_kernel<<<(unsigned)std::min<int64_t>((n_windows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
       n_windows, d_rows, d_row_off, d_row_stride, d_nring, ctx->d_wdst.as<int64_t>(), ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(),
-      ctx->d_munc.as<uint8_t>());
+      ctx->d_munc.as<uint8_t>(), ctx->d_ctrl.as<int32_t>() + kAbortWord);
   CU(cudaGetLastError());
   ctx->last_launches += 4;
   ctx->merged_cap = cap;

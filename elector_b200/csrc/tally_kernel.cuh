@@ -30,9 +30,12 @@ struct ReadScan {   // output of tally_scan_kernel, input of tally_count_kernel
 };
 
 // ---- offsets -------------------------------------------------------------------------
-__global__ void read_totals_kernel(int64_t n_reads, const int64_t *read_first, const int32_t *nring, int64_t *tot) {
+// (abort: control word of the call, set when the alignment kernels did not run -- invalid window, scratch pool too small:
+// their per-window outputs are then undefined and the merge / tally kernels leave at once)
+__global__ void read_totals_kernel(int64_t n_reads, const int64_t *read_first, const int32_t *nring, int64_t *tot, const int32_t *abort) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
+  if (*abort) { tot[r] = 0; return; }
   int64_t t = 0;
   for (int64_t w = read_first[r]; w < read_first[r + 1]; ++w) t += nring[w];
   tot[r] = (t + 15) & ~(int64_t)15;  // 16-byte aligned slots
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(1024) scan_offsets_kernel(int64_t n, const int
 // window keeps (corrected row != 'n') and turn them into the window's destination offset.
 __global__ void __launch_bounds__(128) merge_plan_kernel(int64_t n_reads, const int64_t *read_first, const uint8_t *rows,
                                                           const int64_t *row_off, const int32_t *row_stride, const int32_t *nring,
-                                                          const int64_t *m_off, int64_t *wdst, int32_t *m_len) {
+                                                          const int64_t *m_off, int64_t *wdst, int32_t *m_len, const int32_t *abort) {
+  if (*abort) return;
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_reads) return;
@@ -112,7 +116,8 @@ __global__ void __launch_bounds__(128) merge_plan_kernel(int64_t n_reads, const 
 // copy: one warp per window, lanes over columns, ballot compaction of the kept columns
 __global__ void __launch_bounds__(256) merge_copy_kernel(int64_t n_windows, const uint8_t *rows, const int64_t *row_off,
                                                           const int32_t *row_stride, const int32_t *nring, const int64_t *wdst,
-                                                          uint8_t *m_ref, uint8_t *m_cor, uint8_t *m_unc) {
+                                                          uint8_t *m_ref, uint8_t *m_cor, uint8_t *m_unc, const int32_t *abort) {
+  if (*abort) return;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_windows; w += nwarps) {
@@ -417,9 +422,9 @@ __device__ unsigned long long g_tally_clk[4];
 #endif
 __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const uint8_t *R, const uint8_t *C, const uint8_t *U,
                                                           const int64_t *off, const int32_t *len, uint32_t *bits, int64_t plane_words,
-                                                          int64_t *counters, int32_t *overflow_flag) {
+                                                          int64_t *counters, int32_t *overflow_flag, const int32_t *abort) {
   const int64_t r = blockIdx.x;
-  if (r >= n_reads) return;
+  if (r >= n_reads || *abort) return;
   const int L = len ? len[r] : (int)(off[r + 1] - off[r]);
   const uint8_t *rr = R + off[r], *cc = C + off[r], *uu = U + off[r];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
