@@ -13,8 +13,10 @@ flush is needed between steps.
 
   value     triplets/s with the window arrays already resident in HBM (elector_poa_run_device +
             elector_merge_tally_device + elector_tally_sum_device)
-  e2e       the same through the host-buffer C-ABI call (elector_pipeline_run): pinned host
-            arrays in, MSA rows + per-read counters out, H2D/D2H inside the timed region
+  e2e       the same through the host-buffer C-ABI call (elector_pipeline_run2): pinned host arrays in (letters 2-bit
+            packed once outside the call, 32-bit offsets), merged per-read MSA rows + per-read counters out, H2D/D2H
+            inside the timed region; e2e.modes times the other wire formats of the call (bytes in / window rows out as
+            in round 1, 4-bit merged rows, counters only)
   roofline  INT32 issue roofline of the DP kernel (15 integer ops per DP cell)
             against the peak measured on this device by elector_int32_peak
   cpu_baseline  the reference poa binary (oracle/_ref/poa) or the oracle port, timed on
@@ -135,6 +137,7 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="triplets per GPU (default: the config's full size, capped at 10000)")
     ap.add_argument("--cpu-triplets", type=int, default=0, help="triplets of the CPU baseline sample (default: sized for ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-main-only", action="store_true", help="time only the headline wire format and the byte path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
@@ -257,16 +260,58 @@ def main():
         if world > 1:
             dist.all_reduce(d_sums)       # the one collective of the path: 24 int64 counters
 
-    def step_e2e():
-        """the call a user makes: host buffers in, MSA rows + per-read counters + global counters out"""
-        ctx._check(lib.elector_pipeline_run(ctx._ctx, n, hptr["ref"], hptr["ref_off"], hptr["cor"], hptr["cor_off"], hptr["unc"],
-                                            hptr["unc_off"], n_trip, hptr["read_first"], h_rows.data_ptr(), bound,
-                                            h_out["row_off"].data_ptr(), h_out["stride"].data_ptr(), h_out["nring"].data_ptr(),
-                                            None, None, None, h_out["counters"].data_ptr(), h_out["sums"].data_ptr()))
-        if world > 1:
-            t = h_out["sums"].to(dev)
-            dist.all_reduce(t)
-            h_out["sums"].copy_(t)
+    # ---- end to end: the call a user makes, host buffers in / out, copies inside the timed region ----
+    # Three wire formats of the same call (include/elector_poa.h, elector_pipeline_run2).  The headline `e2e` is the second:
+    # what ELECTOR consumes after alignment.py (the merged per-read MSA that Donatello appends to msa.fa, and the per-read
+    # counters of computeStats.py) from what its caller has (the reads, packed once outside the call).
+    from elector_b200.poa import PipelineIoC, pack_letters
+    packed = [pack_letters(wl[k]) for k in ("ref", "cor", "unc")]      # outside the timed region, like reading the FASTA files
+    pk_pinned = []
+    for pk in packed:
+        t_bits, a_bits = pinned(pk.bits); t_pos, a_pos = pinned(pk.exc_pos if len(pk.exc_pos) else np.zeros(1, np.int64)); t_byt, a_byt = pinned(pk.exc_byte if len(pk.exc_byte) else np.zeros(1, np.uint8))
+        pk_pinned.append((t_bits, t_pos, t_byt))
+        pk.bits, n_e = a_bits, len(pk.exc_pos)
+        pk.exc_pos, pk.exc_byte = a_pos[:n_e], a_byt[:n_e]
+    pk_c = [pk.c_struct() for pk in packed]
+    m_cap = int(lib.elector_merged_bound(n, n_trip, hptr["ref_off"], hptr["cor_off"], hptr["unc_off"]))
+    h_m = [torch.empty(m_cap, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    h_moff, h_mlen = torch.empty(n_trip, dtype=torch.int64).pin_memory(), torch.empty(n_trip, dtype=torch.int32).pin_memory()
+    h_esc_pos, h_esc_byte, h_nesc = torch.empty(1 << 20, dtype=torch.int64).pin_memory(), torch.empty(1 << 20, dtype=torch.uint8).pin_memory(), torch.zeros(1, dtype=torch.int64)
+
+    def make_io(mode):
+        io = PipelineIoC()
+        io.n_windows, io.n_reads = n, n_trip
+        io.ref_off, io.cor_off, io.unc_off, io.read_first = hptr["ref_off"], hptr["cor_off"], hptr["unc_off"], hptr["read_first"]
+        if mode != "packed_in_counters_out":
+            io.nring = h_out["nring"].data_ptr()
+        io.counters_out, io.sums_out = h_out["counters"].data_ptr(), h_out["sums"].data_ptr()
+        if mode == "bytes_in_window_rows_out":
+            io.ref, io.cor, io.unc = hptr["ref"], hptr["cor"], hptr["unc"]
+            io.rows_out, io.rows_cap, io.row_off, io.row_stride = h_rows.data_ptr(), bound, h_out["row_off"].data_ptr(), h_out["stride"].data_ptr()
+        else:
+            io.pref, io.pcor, io.punc = (ctypes.addressof(c) for c in pk_c)
+            if mode != "packed_in_counters_out":
+                io.m_ref, io.m_cor, io.m_unc, io.m_cap = h_m[0].data_ptr(), h_m[1].data_ptr(), h_m[2].data_ptr(), m_cap
+                io.m_off, io.m_len = h_moff.data_ptr(), h_mlen.data_ptr()
+                if mode == "packed_in_merged_nibbles_out":
+                    io.m_nibbles = 1
+                    io.m_esc_pos, io.m_esc_byte, io.m_esc_cap, io.m_n_esc = h_esc_pos.data_ptr(), h_esc_byte.data_ptr(), 1 << 20, h_nesc.data_ptr()
+        return io
+
+    E2E_MODES = ["packed_in_merged_rows_out", "bytes_in_window_rows_out", "packed_in_merged_nibbles_out", "packed_in_counters_out"]
+    ios = {m: make_io(m) for m in E2E_MODES}
+
+    def make_step(mode):
+        io = ios[mode]
+
+        def step():
+            ctx._check(lib.elector_pipeline_run2(ctx._ctx, ctypes.byref(io)))
+            if world > 1:
+                t = h_out["sums"].to(dev)
+                dist.all_reduce(t)
+                h_out["sums"].copy_(t)
+        return step
+    step_e2e = make_step(E2E_MODES[0])
 
     def barrier():
         torch.cuda.synchronize()
@@ -306,11 +351,21 @@ def main():
     cells = int(d_cells.sum().item())
     used = int(d_used.item())
     sums_dev = d_sums.cpu().numpy().copy()
-    for _ in range(args.warmup):
-        step_e2e()
-    e2e_ms, e2e_wall = timed(step_e2e, args.steps)
-    e2e_step_ms = max(e2e_ms, e2e_wall) / args.steps
-    sums_e2e = h_out["sums"].numpy().copy()
+    e2e_modes = {}
+    sums_e2e = None
+    for mode in (E2E_MODES if not args.e2e_main_only else E2E_MODES[:2]):
+        fn = make_step(mode)
+        for _ in range(args.warmup):
+            fn()
+        ms_, wall_ = timed(fn, args.steps)
+        e2e_modes[mode] = max(ms_, wall_) / args.steps
+        if mode == E2E_MODES[0]:
+            sums_e2e = h_out["sums"].numpy().copy()
+            merged_cols = int(h_mlen.numpy().astype(np.int64).sum())
+    e2e_step_ms = e2e_modes[E2E_MODES[0]]
+    # the byte path once more, last: the parity check below reads its window rows
+    step_rows = make_step("bytes_in_window_rows_out")
+    step_rows()
 
     # parity spot check of what was just timed (not in the timed region): first 2000 windows vs the oracle,
     # and the two paths (device-resident / pipelined host call) against each other
@@ -371,8 +426,15 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    in_bytes = int(wl["ref_off"][-1] + wl["cor_off"][-1] + wl["unc_off"][-1]) + 3 * 8 * (n + 1) + 8 * (n_trip + 1)
-    out_bytes = used + n * (8 + 4 + 4) + n_trip * K * 8 + K * 8
+    letters = int(wl["ref_off"][-1] + wl["cor_off"][-1] + wl["unc_off"][-1])
+    in_bytes = letters + 3 * 8 * (n + 1) + 8 * (n_trip + 1)                     # byte path: 1 B per letter, 64-bit offsets
+    in_packed = sum((pk.n_letters + 3) // 4 + 9 * len(pk.exc_pos) for pk in packed) + 3 * 4 * (n + 1) + 8 * (n_trip + 1)
+    out_rows = used + n * (8 + 4 + 4) + n_trip * K * 8 + K * 8                   # byte path: window rows, their offsets, counters
+    out_merged = 3 * merged_cols + n * 4 + n_trip * (8 + 4 + K * 8) + K * 8     # merged rows as bytes, nring, m_off / m_len, counters
+    wire = {"packed_in_merged_rows_out": (in_packed, out_merged), "bytes_in_window_rows_out": (in_bytes, out_rows),
+            "packed_in_merged_nibbles_out": (in_packed, out_merged - 3 * merged_cols + 3 * ((merged_cols + 1) // 2) + 9 * int(h_nesc[0])),
+            "packed_in_counters_out": (in_packed, n_trip * K * 8 + K * 8)}
+    out_bytes = wire[E2E_MODES[0]][1]
     alg_bytes = in_bytes + used + n * 36
 
     value = n_trip * world / (step_ms / 1e3)
@@ -387,8 +449,13 @@ def main():
         "config": {"workload": workload_name, "step": "POA of every window (DP1 + DP2 phases) + per-read merge + tally + counter sum",
                    "windows_per_gpu": n, "cells_per_gpu": cells, "windows_from": wl["source"],
                    "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush" % (in_bytes / 1e6), "parity": parity},
-        "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": e2e_step_ms, "call": "elector_pipeline_run (pinned host buffers in, MSA rows + counters out)"},
+        "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": wire[E2E_MODES[0]][0], "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": e2e_step_ms,
+                "call": "elector_pipeline_run2: 2-bit packed letters + 32-bit offsets in (packed once, outside the call), merged per-read MSA rows (what Donatello appends to msa.fa) + per-read counters + sums out; pinned host buffers",
+                "host_link_gbs": (wire[E2E_MODES[0]][0] + out_bytes) / (e2e_step_ms / 1e3) / 1e9,
+                "limiter": "kernels (%.2f ms resident) + the tail of the last chunk's results; the host link carries %.0f MB per call" % (step_ms, (wire[E2E_MODES[0]][0] + out_bytes) / 1e6),
+                "modes": {m: {"ms_per_step": e2e_modes[m], "value": n_trip * world / (e2e_modes[m] / 1e3), "h2d_bytes_per_step": wire[m][0], "d2h_bytes_per_step": wire[m][1],
+                              "host_link_gbs": (wire[m][0] + wire[m][1]) / (e2e_modes[m] / 1e3) / 1e9} for m in e2e_modes}},
         "gpu_launches": phase["launches"],
         "kernel_ms_per_step": {"sort1+poa_dp1_kernel": phase["p1"] / args.steps, "sort2+poa_dp2_kernel": (phase["tot"] - phase["p1"]) / args.steps,
                                "merge+tally": phase["tally_ms"] / args.steps},

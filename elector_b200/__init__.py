@@ -7,8 +7,8 @@ works anywhere, but creating a context without the built library or without a CU
 device raises.
 """
 from .lib import LibraryNotBuilt, load_library, library_path  # noqa: F401
-from .poa import ElectorError, PoaContext, PoaResult, TALLY_FIELDS, windows_to_csr  # noqa: F401
+from .poa import ElectorError, PackedLetters, PoaContext, PoaResult, TALLY_FIELDS, pack_letters, windows_to_csr  # noqa: F401
 from .matrix import write_default_matrix  # noqa: F401
 
-__all__ = ["PoaContext", "PoaResult", "ElectorError", "LibraryNotBuilt", "load_library", "library_path",
+__all__ = ["PoaContext", "PoaResult", "PackedLetters", "pack_letters", "ElectorError", "LibraryNotBuilt", "load_library", "library_path",
            "windows_to_csr", "write_default_matrix", "TALLY_FIELDS"]

@@ -22,6 +22,7 @@
 #include "bin_kernel.cuh"
 #include "host_setup.hpp"
 #include "tally_kernel.cuh"
+#include "wire_kernel.cuh"
 #include "peak_kernel.cuh"
 
 using namespace elector;
@@ -82,6 +83,8 @@ struct elector_ctx {
   int64_t pipe_sums[ELECTOR_TALLY_K] = {};
   int64_t *h_sums = nullptr;   // pinned: global counters of a chunk + the tally overflow flag
   int pipe_rc = 0;
+  DevBuf d_pk[3], d_exc_pos, d_exc_byte, d_rel, d_nib[3], d_esc_pos, d_esc_byte;   // compact wire format: packed letters, exceptions, 32-bit offsets in; 4-bit merged rows and their escapes out
+  void *h_stage = nullptr; size_t h_stage_cap = 0;   // pinned staging of a chunk's 32-bit offsets
   DevBuf d_wdst, d_sums, d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
   bool trace = false;
   int band_w = 6;          // ELECTOR_BAND_W: base half-width of the diagonal band of the packed linear kernels (+ rows/16 in phase 1, + rows/8 in phase 2; 0 = full DP)
@@ -97,7 +100,8 @@ struct elector_ctx {
   bool split_rows = false;          // set by process_chunk around run_device
   int64_t region_b_base = 0;        // out: where the linear region starts in the caller's row buffer
   cudaEvent_t ev_regb[8] = {};      // after each launch that writes to the linear region
-  cudaEvent_t ev_lin = nullptr;     // the linear region is complete and its cursor is in h_totals[7]
+  cudaEvent_t ev_lin = nullptr;     // the linear region is complete; its cursor and start are in h_totals[6..7]
+  cudaEvent_t ev_merged = nullptr;  // merge + tally of a chunk are done; the merged columns of the chunk are in h_totals[2]
   cudaEvent_t wait_in[2] = {nullptr, nullptr};   // run_device: phase 1 / phase 2 wait for these (letters still on their way), when set
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
   std::string err;
@@ -567,32 +571,65 @@ void add_kernel_ms(elector_ctx *ctx) {
 }
 
 
-struct ChunkJob { int64_t w0, w1, r0, r1, rows_base, rows_len; bool split; int index; };
+struct ChunkJob { int64_t w0, w1, r0, r1, rows_base, rows_len, m_base; bool split; int index; };
 struct PipeArgs {
-  int64_t n;
-  const char *ref; const int64_t *ro; const char *cor; const int64_t *co; const char *unc; const int64_t *uo;
-  int64_t n_reads; const int64_t *read_first;
-  char *rows_out; int64_t *row_off; int32_t *row_stride, *nring, *score1, *score2; int64_t *cells, *counters_out;
+  const elector_pipeline_io *io;
+  const int64_t *ro, *co, *uo;      // = io->ref_off ...
+  bool packed;                      // 2-bit letters + 32-bit offsets on the wire
   cudaEvent_t ev_call;   // start of the call on the device (ELECTOR_TRACE)
   // the chunks' inputs cross PCIe in chunk order (a worker queues its copies when it is its chunk's turn, behind the
   // previous chunk's): chunk 0 computes while chunk 1 is still arriving
   std::atomic<int> *h2d_turn;
   cudaEvent_t *h2d_prev;
   std::atomic<int> *failed;
+  std::atomic<long long> *n_esc;    // escapes of the 4-bit merged rows appended so far (all chunks)
 };
 
 // One chunk of a pipelined call on one worker context: everything is queued on the worker's stream (the segment launches
 // fork to its side streams) and the function returns when the chunk's results are in the caller's host buffers.
 int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   CU(cudaSetDevice(ctx->device));
+  const elector_pipeline_io &io = *pa.io;
   const int64_t w0 = j.w0, w1 = j.w1, nw = w1 - w0, r0 = j.r0, r1 = j.r1, nr = r1 - r0;
-  const int64_t br0 = pa.ro[w0], bc0 = pa.co[w0], bu0 = pa.uo[w0];
-  const int64_t br = pa.ro[w1] - br0, bc = pa.co[w1] - bc0, bu = pa.uo[w1] - bu0;
-  CU(ctx->d_ref.reserve(br)); CU(ctx->d_cor.reserve(bc)); CU(ctx->d_unc.reserve(bu));
-  CU(ctx->d_roff.reserve((nw + 1) * 8)); CU(ctx->d_coff.reserve((nw + 1) * 8)); CU(ctx->d_uoff.reserve((nw + 1) * 8));
+  const int64_t first[3] = {pa.ro[w0], pa.co[w0], pa.uo[w0]};
+  const int64_t len[3] = {pa.ro[w1] - first[0], pa.co[w1] - first[1], pa.uo[w1] - first[2]};
+  const int64_t br0 = first[0], bc0 = first[1], bu0 = first[2], br = len[0], bc = len[1], bu = len[2];
+  DevBuf *d_let[3] = {&ctx->d_ref, &ctx->d_cor, &ctx->d_unc};
+  DevBuf *d_off[3] = {&ctx->d_roff, &ctx->d_coff, &ctx->d_uoff};
+  const int64_t *h_off[3] = {pa.ro, pa.co, pa.uo};
+  const char *h_let[3] = {io.ref, io.cor, io.unc};
+  const elector_packed *h_pk[3] = {io.pref, io.pcor, io.punc};
+  for (int k = 0; k < 3; ++k) { CU(d_let[k]->reserve(len[k] + 8)); CU(d_off[k]->reserve((nw + 1) * 8)); }
   CU(ctx->d_rows.reserve(j.rows_len)); CU(ctx->d_rowoff.reserve(nw * 8)); CU(ctx->d_stride.reserve(nw * 4));
   CU(ctx->d_nring.reserve(nw * 4)); CU(ctx->d_s1.reserve(nw * 4)); CU(ctx->d_s2.reserve(nw * 4)); CU(ctx->d_cells.reserve(nw * 8));
   if (nr > 0) { CU(ctx->d_tally_out.reserve(nr * ELECTOR_TALLY_K * 8)); CU(ctx->d_sums.reserve(ELECTOR_TALLY_K * 8)); }
+  // compact wire format: the 32-bit offsets of the chunk (relative to its first letter) are made here, on the worker's
+  // thread, while the chunks before it are on their way; the exceptions of the chunk are found by binary search
+  int64_t exc0[3] = {0, 0, 0}, exc1[3] = {0, 0, 0};
+  int32_t *stage = nullptr;
+  if (pa.packed) {
+    const size_t need = (size_t)3 * (nw + 1) * sizeof(int32_t);
+    if (need > ctx->h_stage_cap) {
+      if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+      ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+      CU(cudaMallocHost(&ctx->h_stage, need + need / 4));
+      ctx->h_stage_cap = need + need / 4;
+    }
+    stage = static_cast<int32_t *>(ctx->h_stage);
+    for (int k = 0; k < 3; ++k) {
+      if (len[k] > 0x7fffffff) return ctx->fail(ELECTOR_ETOOLARGE, "a chunk holds more than 2^31 letters of one kind");
+      int32_t *dst = stage + (size_t)k * (nw + 1);
+      const int64_t *src = h_off[k] + w0, f = first[k];
+      for (int64_t i = 0; i <= nw; ++i) dst[i] = (int32_t)(src[i] - f);
+      const int64_t *ep = h_pk[k]->exc_pos, ne = h_pk[k]->n_exc;
+      exc0[k] = std::lower_bound(ep, ep + ne, first[k]) - ep;
+      exc1[k] = std::lower_bound(ep, ep + ne, first[k] + len[k]) - ep;
+      CU(ctx->d_pk[k].reserve((size_t)(len[k] / 4 + 8)));
+    }
+    CU(ctx->d_rel.reserve(need));
+    const int64_t ne_tot = (exc1[0] - exc0[0]) + (exc1[1] - exc0[1]) + (exc1[2] - exc0[2]);
+    CU(ctx->d_exc_pos.reserve((size_t)(ne_tot + 1) * 8)); CU(ctx->d_exc_byte.reserve((size_t)ne_tot + 8));
+  }
   cudaStream_t st = ctx->stream;
   while (pa.h2d_turn->load(std::memory_order_acquire) != j.index) {
     if (pa.failed->load() != ELECTOR_OK) return ctx->fail(ELECTOR_ECUDA, "another chunk of the call failed");
@@ -607,16 +644,38 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   if (ctx->trace) CU(cudaEventRecord(ctx->uev0, st));
   // the offsets first, on the compute stream: the size sort needs nothing else.  The letters follow on the copy stream --
   // ref and cor (phase 1 waits for them), then unc (phase 2 waits for it) -- while the sort and phase 1 run.
-  CU(cudaMemcpyAsync(ctx->d_roff.p, pa.ro + w0, (nw + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_coff.p, pa.co + w0, (nw + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_uoff.p, pa.uo + w0, (nw + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (pa.packed) {
+    CU(cudaMemcpyAsync(ctx->d_rel.p, stage, (size_t)3 * (nw + 1) * 4, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 3; ++k)
+      widen_offsets_kernel<<<(unsigned)((nw + 256) / 256), 256, 0, st>>>(nw + 1, ctx->d_rel.as<int32_t>() + (size_t)k * (nw + 1), first[k], d_off[k]->as<int64_t>());
+    CU(cudaGetLastError());
+    ctx->last_launches += 3;
+  } else
+    for (int k = 0; k < 3; ++k) CU(cudaMemcpyAsync(d_off[k]->p, h_off[k] + w0, (nw + 1) * 8, cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(ctx->ev_fork, st));
   CU(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));   // the copy engine serves the offsets first
-  CU(cudaMemcpyAsync(ctx->d_ref.p, pa.ref + br0, br, cudaMemcpyHostToDevice, ctx->copy_in));
-  CU(cudaMemcpyAsync(ctx->d_cor.p, pa.cor + bc0, bc, cudaMemcpyHostToDevice, ctx->copy_in));
-  CU(cudaEventRecord(ctx->ev_in[0], ctx->copy_in));
-  CU(cudaMemcpyAsync(ctx->d_unc.p, pa.unc + bu0, bu, cudaMemcpyHostToDevice, ctx->copy_in));
-  CU(cudaEventRecord(ctx->ev_in[1], ctx->copy_in));
+  int64_t exc_done = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (pa.packed) {   // packed bytes that hold the chunk's letters (+ one of padding), expanded on the device; then the exceptions
+      const int64_t b0 = first[k] >> 2, b1 = (first[k] + len[k] + 3) >> 2;
+      const int64_t have = (h_pk[k]->n_letters + 3) >> 2;
+      CU(cudaMemcpyAsync(ctx->d_pk[k].p, h_pk[k]->bits + b0, (size_t)std::min(b1 + 1, have) - b0, cudaMemcpyHostToDevice, ctx->copy_in));
+      if (len[k] > 0) unpack2_kernel<<<(unsigned)std::min<int64_t>((len[k] / 4 + 256) / 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->copy_in>>>(
+          ctx->d_pk[k].as<uint8_t>(), (int)(first[k] & 3), len[k], d_let[k]->as<uint8_t>());
+      const int64_t ne = exc1[k] - exc0[k];
+      if (ne > 0) {
+        CU(cudaMemcpyAsync(ctx->d_exc_pos.as<int64_t>() + exc_done, h_pk[k]->exc_pos + exc0[k], ne * 8, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(cudaMemcpyAsync(ctx->d_exc_byte.as<uint8_t>() + exc_done, h_pk[k]->exc_byte + exc0[k], ne, cudaMemcpyHostToDevice, ctx->copy_in));
+        patch_letters_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->copy_in>>>(ne, ctx->d_exc_pos.as<int64_t>() + exc_done, ctx->d_exc_byte.as<uint8_t>() + exc_done,
+                                                                                   first[k], d_let[k]->as<uint8_t>());
+        exc_done += ne;
+      }
+      CU(cudaGetLastError());
+      ctx->last_launches += ne > 0 ? 2 : 1;
+    } else
+      CU(cudaMemcpyAsync(d_let[k]->p, h_let[k] + first[k], len[k], cudaMemcpyHostToDevice, ctx->copy_in));
+    if (k >= 1) CU(cudaEventRecord(ctx->ev_in[k - 1], ctx->copy_in));
+  }
   ctx->wait_in[0] = ctx->ev_in[0]; ctx->wait_in[1] = ctx->ev_in[1];
   *pa.h2d_prev = ctx->ev_in[1];
   pass_turn.pass();
@@ -624,18 +683,21 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   // pointer by the chunk's base in the caller's row buffer (row_off[] then indexes the caller's buffer directly)
   char *d_rows_v = ctx->d_rows.as<char>() - j.rows_base;
   cudaStream_t so = ctx->copy_out;
+  const bool want_rows = io.rows_out != nullptr;
+  const bool want_merged = io.m_ref != nullptr;
   for (int attempt = 0;; ++attempt) {
-    ctx->split_rows = j.split;
+    ctx->split_rows = j.split && want_rows;
     int rc = run_device(ctx, nw, ctx->d_ref.as<char>() - br0, ctx->d_roff.as<int64_t>(), ctx->d_cor.as<char>() - bc0, ctx->d_coff.as<int64_t>(),
                         ctx->d_unc.as<char>() - bu0, ctx->d_uoff.as<int64_t>(), pa.ro + w0, pa.co + w0, d_rows_v, j.rows_base + j.rows_len,
                         ctx->d_rowoff.as<int64_t>(), ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(),
                         ctx->d_s2.as<int32_t>(), ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(), ctx->d_ctrl.as<int32_t>() + 2, j.rows_base);
+    const bool split = ctx->split_rows;
     ctx->split_rows = false;
     if (rc != ELECTOR_OK) { ctx->wait_in[0] = ctx->wait_in[1] = nullptr; cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(st); return rc; }
     CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(ctx->ev_rows, st));
     if (nr > 0) {
-      std::vector<int64_t> rf(pa.read_first + r0, pa.read_first + r1 + 1);
+      std::vector<int64_t> rf(io.read_first + r0, io.read_first + r1 + 1);
       for (int64_t &v : rf) v -= w0;
       CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
       rc = merge_device(ctx, nr, rf.data(), nw, reinterpret_cast<const uint8_t *>(d_rows_v), 3 * (br + bc + bu), ctx->d_rowoff.as<int64_t>(),
@@ -647,20 +709,35 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
       tally_sum_kernel<<<std::min<int>(64, (int)((nr + 7) / 8)), 256, 0, st>>>(nr, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
       CU(cudaGetLastError());
       ++ctx->last_launches;
+      if (want_merged && io.m_nibbles) {   // two columns per byte before they leave; the few characters outside the code go to the escape list
+        for (int k = 0; k < 3; ++k) CU(ctx->d_nib[k].reserve((size_t)ctx->merged_cap / 2 + 16));
+        CU(ctx->d_esc_pos.reserve((size_t)(io.m_esc_cap + 1) * 8)); CU(ctx->d_esc_byte.reserve((size_t)io.m_esc_cap + 8));
+        CU(cudaMemsetAsync(ctx->d_ctrl.as<unsigned long long>() + 21, 0, 8, st));
+        nibble_pack_kernel<<<(unsigned)((3 * nr + 3) / 4), 128, 0, st>>>(nr, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
+            ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(), ctx->d_nib[0].as<uint8_t>(), ctx->d_nib[1].as<uint8_t>(), ctx->d_nib[2].as<uint8_t>(), j.m_base,
+            ctx->d_ctrl.as<unsigned long long>() + 21, ctx->d_esc_pos.as<int64_t>(), ctx->d_esc_byte.as<uint8_t>(), io.m_esc_cap, ctx->d_ctrl.as<int32_t>() + kAbortWord);
+        CU(cudaGetLastError());
+        ++ctx->last_launches;
+      }
       CU(cudaEventRecord(ctx->ev1, st));   // the chunk's device time covers merge + tally too
       CU(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
       CU(cudaMemcpyAsync(ctx->h_sums + ELECTOR_TALLY_K, ctx->d_ctrl.as<int32_t>() + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(pa.counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.p, nr * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(&ctx->h_totals[2], ctx->d_moff.as<int64_t>() + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, st));      // merged columns of the chunk
+      CU(cudaMemcpyAsync(&ctx->h_totals[3], ctx->d_ctrl.as<unsigned long long>() + 21, sizeof(int64_t), cudaMemcpyDeviceToHost, st));   // escapes
+      if (io.counters_out) CU(cudaMemcpyAsync(io.counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.p, nr * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+      if (io.m_off) CU(cudaMemcpyAsync(io.m_off + r0, ctx->d_moff.p, nr * 8, cudaMemcpyDeviceToHost, st));
+      if (io.m_len) CU(cudaMemcpyAsync(io.m_len + r0, ctx->d_mlen.p, nr * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaEventRecord(ctx->ev_merged, st));
     }
     // the alignment results leave on the copy stream while merge and tally run: the host waits for the POA kernels only
     // to learn how many row bytes the chunk used.  The linear region first: its segments run next to phase 1 and finish early.
     const int64_t end_b = j.rows_base + j.rows_len;
     int64_t base_b = end_b, used_b = end_b;
-    if (j.split) {
+    if (split) {
       CU(cudaEventSynchronize(ctx->ev_lin));
       used_b = ctx->h_totals[6]; base_b = ctx->h_totals[7];
       if (base_b >= j.rows_base && used_b > base_b && used_b <= end_b)
-        CU(cudaMemcpyAsync(pa.rows_out + base_b, d_rows_v + base_b, used_b - base_b, cudaMemcpyDeviceToHost, so));
+        CU(cudaMemcpyAsync(io.rows_out + base_b, d_rows_v + base_b, used_b - base_b, cudaMemcpyDeviceToHost, so));
     }
     CU(cudaEventSynchronize(ctx->ev_rows));
     ctx->wait_in[0] = ctx->wait_in[1] = nullptr;   // the letters have arrived: a second attempt does not wait for them again
@@ -680,16 +757,39 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
       return ctx->fail(ELECTOR_ECAPACITY, "rows of a chunk exceed their bound (%lld + %lld > %lld)", (long long)(used - j.rows_base), (long long)(used_b - base_b),
                        (long long)j.rows_len);
     }
-    CU(cudaMemcpyAsync(pa.rows_out + j.rows_base, ctx->d_rows.p, used - j.rows_base, cudaMemcpyDeviceToHost, so));
-    CU(cudaMemcpyAsync(pa.row_off + w0, ctx->d_rowoff.p, nw * 8, cudaMemcpyDeviceToHost, so));
-    CU(cudaMemcpyAsync(pa.row_stride + w0, ctx->d_stride.p, nw * 4, cudaMemcpyDeviceToHost, so));
-    CU(cudaMemcpyAsync(pa.nring + w0, ctx->d_nring.p, nw * 4, cudaMemcpyDeviceToHost, so));
-    if (pa.score1) CU(cudaMemcpyAsync(pa.score1 + w0, ctx->d_s1.p, nw * 4, cudaMemcpyDeviceToHost, so));
-    if (pa.score2) CU(cudaMemcpyAsync(pa.score2 + w0, ctx->d_s2.p, nw * 4, cudaMemcpyDeviceToHost, so));
-    if (pa.cells) CU(cudaMemcpyAsync(pa.cells + w0, ctx->d_cells.p, nw * 8, cudaMemcpyDeviceToHost, so));
+    if (want_rows) {
+      CU(cudaMemcpyAsync(io.rows_out + j.rows_base, ctx->d_rows.p, used - j.rows_base, cudaMemcpyDeviceToHost, so));
+      CU(cudaMemcpyAsync(io.row_off + w0, ctx->d_rowoff.p, nw * 8, cudaMemcpyDeviceToHost, so));
+      CU(cudaMemcpyAsync(io.row_stride + w0, ctx->d_stride.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    }
+    if (io.nring) CU(cudaMemcpyAsync(io.nring + w0, ctx->d_nring.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    if (io.score1) CU(cudaMemcpyAsync(io.score1 + w0, ctx->d_s1.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    if (io.score2) CU(cudaMemcpyAsync(io.score2 + w0, ctx->d_s2.p, nw * 4, cudaMemcpyDeviceToHost, so));
+    if (io.cells) CU(cudaMemcpyAsync(io.cells + w0, ctx->d_cells.p, nw * 8, cudaMemcpyDeviceToHost, so));
+    if (nr > 0 && want_merged) {   // the merged rows: their size is known once the merge has run
+      CU(cudaEventSynchronize(ctx->ev_merged));
+      const int64_t cols = ctx->h_totals[2];
+      if (j.m_base + cols > io.m_cap) { cudaStreamSynchronize(st); cudaStreamSynchronize(so); return ctx->fail(ELECTOR_ECAPACITY, "merged rows need more than m_cap = %lld columns", (long long)io.m_cap); }
+      char *dst[3] = {io.m_ref, io.m_cor, io.m_unc};
+      DevBuf *srcb[3] = {&ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
+      for (int k = 0; k < 3; ++k) {
+        if (io.m_nibbles) CU(cudaMemcpyAsync(dst[k] + j.m_base / 2, ctx->d_nib[k].p, (size_t)(cols + 1) / 2, cudaMemcpyDeviceToHost, so));
+        else CU(cudaMemcpyAsync(dst[k] + j.m_base, srcb[k]->p, (size_t)cols, cudaMemcpyDeviceToHost, so));
+      }
+      if (io.m_nibbles) {
+        const int64_t ne = ctx->h_totals[3];
+        if (ne > 0) {
+          const long long at = pa.n_esc->fetch_add(ne);
+          if (at + ne > io.m_esc_cap || ne > io.m_esc_cap) { cudaStreamSynchronize(st); cudaStreamSynchronize(so); return ctx->fail(ELECTOR_ECAPACITY, "more than m_esc_cap = %lld characters outside the 4-bit code", (long long)io.m_esc_cap); }
+          CU(cudaMemcpyAsync(io.m_esc_pos + at, ctx->d_esc_pos.p, (size_t)ne * 8, cudaMemcpyDeviceToHost, so));
+          CU(cudaMemcpyAsync(io.m_esc_byte + at, ctx->d_esc_byte.p, (size_t)ne, cudaMemcpyDeviceToHost, so));
+        }
+      }
+    }
     if (ctx->trace) CU(cudaEventRecord(ctx->uev1, so));
     CU(cudaStreamSynchronize(st));
     CU(cudaStreamSynchronize(so));
+    if (nr > 0 && io.m_off) for (int64_t r = r0; r < r1; ++r) io.m_off[r] += j.m_base;   // chunk-relative -> the caller's buffers
     break;
   }
   if (ctx->trace) {   // device timeline of the chunk, ms after the start of the call
@@ -697,7 +797,7 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
     cudaEventElapsedTime(&t[0], pa.ev_call, ctx->uev0); cudaEventElapsedTime(&t[1], pa.ev_call, ctx->ev0);
     cudaEventElapsedTime(&t[2], pa.ev_call, ctx->ev_mid); cudaEventElapsedTime(&t[3], pa.ev_call, ctx->ev_rows);
     cudaEventElapsedTime(&t[4], pa.ev_call, ctx->ev1); cudaEventElapsedTime(&t[5], pa.ev_call, ctx->uev1);
-    fprintf(stderr, "[elector trace] chunk w%lld: h2d %.2f | sort1 %.2f | phase 1 done %.2f | phase 2 done %.2f | merge+tally done %.2f | rows on host %.2f\n",
+    fprintf(stderr, "[elector trace] chunk w%lld: h2d %.2f | sort1 %.2f | phase 1 done %.2f | phase 2 done %.2f | merge+tally done %.2f | results on host %.2f\n",
             (long long)w0, t[0], t[1], t[2], t[3], t[4], t[5]);
   }
   add_kernel_ms(ctx);
@@ -768,6 +868,7 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
       (e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_rows)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_lin, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_merged, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_in[0], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_in[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->uev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->uev1)) != cudaSuccess ||
@@ -841,6 +942,9 @@ void elector_poa_free(elector_ctx *ctx) {
   for (int k = 0; k < 2; ++k) if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
   for (int k = 0; k < 8; ++k) if (ctx->ev_regb[k]) cudaEventDestroy(ctx->ev_regb[k]);
   if (ctx->ev_lin) cudaEventDestroy(ctx->ev_lin);
+  if (ctx->ev_merged) cudaEventDestroy(ctx->ev_merged);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  for (DevBuf *b : {&ctx->d_pk[0], &ctx->d_pk[1], &ctx->d_pk[2], &ctx->d_nib[0], &ctx->d_nib[1], &ctx->d_nib[2], &ctx->d_exc_pos, &ctx->d_exc_byte, &ctx->d_rel, &ctx->d_esc_pos, &ctx->d_esc_byte}) b->release();
   if (ctx->uev0) cudaEventDestroy(ctx->uev0);
   if (ctx->uev1) cudaEventDestroy(ctx->uev1);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -912,54 +1016,92 @@ int elector_poa_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t 
                               score1, score2, cells, nullptr, nullptr);
 }
 
-// Host buffers in, host buffers out.  The call is cut into chunks of whole reads; every chunk is processed start to
-// finish -- inputs to the device, both POA phases, merge, tally, results back -- by one of a few WORKER contexts (this
-// context and children it creates once), each on its own host thread and streams.  While one worker's chunk computes,
-// another's inputs arrive and a third's results leave, and the idle moments of a chunk (the host reads the segment
-// table of each phase; the longest windows of a phase finish after its bulk) are filled by the other workers' kernels.
 int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ro, const char *cor, const int64_t *co,
                          const char *unc, const int64_t *uo, int64_t n_reads, const int64_t *read_first, char *rows_out,
                          int64_t rows_cap, int64_t *row_off, int32_t *row_stride, int32_t *nring, int32_t *score1,
                          int32_t *score2, int64_t *cells, int64_t *counters_out, int64_t *sums_out) {
   if (!ctx) return ELECTOR_EINVAL;
-  if (n < 0 || n_reads < 0 || (n > 0 && (!ref || !cor || !unc || !ro || !co || !uo || !rows_out || !row_off || !row_stride || !nring)))
-    return ctx->fail(ELECTOR_EINVAL, "null argument");
-  if (n_reads > 0 && (!read_first || !counters_out)) return ctx->fail(ELECTOR_EINVAL, "null argument");
-  if (sums_out) memset(sums_out, 0, ELECTOR_TALLY_K * sizeof(int64_t));
+  if (n > 0 && (!rows_out || !row_off || !row_stride || !nring)) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_reads > 0 && !counters_out) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  elector_pipeline_io io;
+  memset(&io, 0, sizeof io);
+  io.n_windows = n; io.n_reads = n_reads;
+  io.ref = ref; io.cor = cor; io.unc = unc; io.ref_off = ro; io.cor_off = co; io.unc_off = uo; io.read_first = read_first;
+  io.rows_out = rows_out; io.rows_cap = rows_cap; io.row_off = row_off; io.row_stride = row_stride;
+  io.nring = nring; io.score1 = score1; io.score2 = score2; io.cells = cells;
+  io.counters_out = counters_out; io.sums_out = sums_out;
+  return elector_pipeline_run2(ctx, &io);
+}
+
+int64_t elector_merged_bound(int64_t n, int64_t n_reads, const int64_t *ro, const int64_t *co, const int64_t *uo) {
+  if (n <= 0 || !ro || !co || !uo) return 0;
+  return ((ro[n] - ro[0]) + (co[n] - co[0]) + (uo[n] - uo[0]) + 32 * n_reads + 31) & ~(int64_t)15;
+}
+
+int64_t elector_pack_letters(const char *letters, int64_t n, uint8_t *bits, int64_t *exc_pos, uint8_t *exc_byte, int64_t exc_cap) {
+  if (n <= 0 || !letters || !bits) return 0;
+  static const struct Lut { int8_t v[256]; Lut() { memset(v, -1, sizeof v); v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; } } lut;
+  int64_t ne = 0;
+  for (int64_t i = 0; i < n; i += 4) {
+    unsigned b = 0;
+    for (int k = 0; k < 4 && i + k < n; ++k) {
+      const unsigned char c = (unsigned char)letters[i + k];
+      const int v = lut.v[c];
+      if (v < 0) { if (ne < exc_cap && exc_pos && exc_byte) { exc_pos[ne] = i + k; exc_byte[ne] = c; } ++ne; }
+      else b |= (unsigned)v << (2 * k);
+    }
+    bits[i >> 2] = (uint8_t)b;
+  }
+  return ne;
+}
+
+// Host buffers in, host buffers out.  The call is cut into chunks of whole reads; every chunk is processed start to
+// finish -- inputs to the device, both POA phases, merge, tally, results back -- by one of a few WORKER contexts (this
+// context and children it creates once), each on its own host thread and streams.  While one worker's chunk computes,
+// another's inputs arrive and a third's results leave.
+int elector_pipeline_run2(elector_ctx *ctx, const elector_pipeline_io *iop) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (!iop) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  const elector_pipeline_io &io = *iop;
+  const int64_t n = io.n_windows, n_reads = io.n_reads;
+  const int64_t *ro = io.ref_off, *co = io.cor_off, *uo = io.unc_off, *read_first = io.read_first;
+  const bool packed = io.pref || io.pcor || io.punc;
+  if (n < 0 || n_reads < 0) return ctx->fail(ELECTOR_EINVAL, "negative count");
+  if (n > 0 && (!ro || !co || !uo)) return ctx->fail(ELECTOR_EINVAL, "null offsets");
+  if (n > 0 && packed && !(io.pref && io.pcor && io.punc && io.pref->bits && io.pcor->bits && io.punc->bits)) return ctx->fail(ELECTOR_EINVAL, "packed letters: all three kinds or none");
+  if (n > 0 && !packed && !(io.ref && io.cor && io.unc)) return ctx->fail(ELECTOR_EINVAL, "null letters");
+  if (n > 0 && io.rows_out && !(io.row_off && io.row_stride && io.nring)) return ctx->fail(ELECTOR_EINVAL, "rows_out needs row_off, row_stride and nring");
+  if (n_reads > 0 && !read_first) return ctx->fail(ELECTOR_EINVAL, "null read_first");
+  if (io.m_ref && !(io.m_cor && io.m_unc && io.m_off && io.m_len && n_reads > 0)) return ctx->fail(ELECTOR_EINVAL, "merged rows need all three buffers, m_off, m_len and reads");
+  if (io.m_ref && io.m_nibbles && io.m_esc_cap > 0 && !(io.m_esc_pos && io.m_esc_byte)) return ctx->fail(ELECTOR_EINVAL, "null escape arrays");
+  if (io.sums_out) memset(io.sums_out, 0, ELECTOR_TALLY_K * sizeof(int64_t));
+  if (io.m_n_esc) *io.m_n_esc = 0;
   ctx->last_ms = ctx->last_ms_phase1 = 0.f;
   ctx->last_launches = 0;
   if (n == 0) return ELECTOR_OK;
   if (ro[0] != 0 || co[0] != 0 || uo[0] != 0) return ctx->fail(ELECTOR_EINVAL, "offsets must start at 0");
   if (n_reads > 0 && (read_first[0] != 0 || read_first[n_reads] != n)) return ctx->fail(ELECTOR_EINVAL, "read_first must span 0..n_windows");
+  if (packed && (io.pref->n_letters < ro[n] || io.pcor->n_letters < co[n] || io.punc->n_letters < uo[n])) return ctx->fail(ELECTOR_EINVAL, "packed letters shorter than the offsets say");
   CU(cudaSetDevice(ctx->device));
   const bool trace = ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   // ---- chunk boundaries (windows; whole reads when reads are given) ----
   // Large chunks: the kernels run 32 windows of one sorted size class in lock step and finish a class with its slowest
-  // group, so their throughput grows with the number of windows sorted together (config 1, 1.96 M windows: 9 ms of
-  // kernels in one chunk, 11 ms in three, 13 ms in six) -- but chunks on several workers overlap their transfers with
-  // each other's kernels: three chunks of ~0.65 M windows on three workers are the measured best (14.0 ms per call against
-  // 16.0 ms in one chunk).  ELECTOR_PIPELINE_CHUNKS forces a chunk count.
+  // group, so their throughput grows with the number of windows sorted together -- but chunks on several workers overlap
+  // their transfers with each other's kernels: three chunks of ~0.65 M windows on three workers are the measured best for
+  // 10 000 reads of 10 kb.  ELECTOR_PIPELINE_CHUNKS forces a chunk count.
   int64_t chunk_windows = 700000;
   int want_workers = 3;
   if (const char *e = getenv("ELECTOR_PIPELINE_CHUNK_WINDOWS")) chunk_windows = std::max<int64_t>(1024, atoll(e));
   if (const char *e = getenv("ELECTOR_PIPELINE_WORKERS")) want_workers = std::max(1, std::min(8, atoi(e)));
   int64_t want_chunks = (n + chunk_windows - 1) / chunk_windows;
   if (const char *e = getenv("ELECTOR_PIPELINE_CHUNKS")) want_chunks = std::max(1, atoi(e));
-  // ELECTOR_PIPELINE_TAPER=1: the first and the last chunk get half the windows of the others (the call starts computing
-  // and finishes copying sooner), at one more chunk than the size rule gives
-  bool taper = false;
-  if (const char *e = getenv("ELECTOR_PIPELINE_TAPER")) taper = e[0] == '1';
-  if (taper && want_chunks >= 2) ++want_chunks; else taper = false;
-  const double units = taper ? (double)(want_chunks - 1) : (double)want_chunks;   // chunk sizes in units: 0.5 1 ... 1 0.5, or all 1
   std::vector<ChunkJob> jobs;
   {
     int64_t w = 0, r = 0;
-    double done_units = 0.0;
     for (int64_t k = 0; w < n; ++k) {
       ChunkJob j;
       j.w0 = w; j.r0 = r;
-      done_units += (taper && (k == 0 || k == want_chunks - 1)) ? 0.5 : 1.0;
-      int64_t want = k + 1 >= want_chunks ? n : (int64_t)((double)n * done_units / units);
+      int64_t want = k + 1 >= want_chunks ? n : (int64_t)((double)n * (double)(k + 1) / (double)want_chunks);
       want = std::min<int64_t>(n, std::max<int64_t>(want, w + std::min<int64_t>(n, 65536)));
       if (n_reads > 0) {   // first read boundary at or after the target (binary search on read_first)
         int64_t lo = r + 1, hi = n_reads;
@@ -968,12 +1110,14 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
         w = read_first[r];
       } else w = want;
       j.w1 = w; j.r1 = r;
+      // merged rows of the chunk in the caller's buffers: from the bound of the reads before it (letters + 32 per read, 16-aligned)
+      j.m_base = (ro[j.w0] + co[j.w0] + uo[j.w0] + 32 * j.r0) & ~(int64_t)15;
       jobs.push_back(j);
     }
   }
   // rows of chunk k land at rows_out + rows_base(k): the bound of the windows before it.  The O(1) bound when the
-  // caller's buffer allows it, else the exact one (one pass over the offsets).
-  const bool loose = rows_cap >= elector_poa_rows_bound(n, ro, co, uo);
+  // caller's buffer allows it (or takes no rows at all), else the exact one (one pass over the offsets).
+  const bool loose = !io.rows_out || io.rows_cap >= elector_poa_rows_bound(n, ro, co, uo);
   if (loose) {
     // region k = [lo16(bound of the windows before it), lo16(bound of the windows up to its end)): the regions tile the O(1)
     // bound of the call whatever the chunking.  A window's share of the bound is 3 * (letters + 3) bytes and it needs at most
@@ -993,7 +1137,7 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
       j.rows_len = 3 * t;
       base += j.rows_len;
     }
-    if (base > rows_cap) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small (%lld needed)", (long long)rows_cap, (long long)base);
+    if (base > io.rows_cap) return ctx->fail(ELECTOR_ECAPACITY, "rows_out capacity %lld too small (%lld needed)", (long long)io.rows_cap, (long long)base);
   }
   // ---- workers ----
   const int nworkers = (int)std::min<size_t>(jobs.size(), (size_t)want_workers);
@@ -1005,10 +1149,10 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   }
   std::atomic<int> h2d_turn{0};
   std::atomic<int> first_error{ELECTOR_OK};
+  std::atomic<long long> n_esc{0};
   cudaEvent_t h2d_prev = nullptr;
   for (size_t k = 0; k < jobs.size(); ++k) jobs[k].index = (int)k;
-  PipeArgs pa{n, ref, ro, cor, co, unc, uo, n_reads, read_first, rows_out, row_off, row_stride, nring, score1, score2, cells, counters_out, ctx->ev_fork,
-              &h2d_turn, &h2d_prev, &first_error};
+  PipeArgs pa{iop, ro, co, uo, packed, ctx->ev_fork, &h2d_turn, &h2d_prev, &first_error, &n_esc};
   if (trace) {
     while (ctx->chunk_ev.empty()) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->chunk_ev.push_back(e); }
     pa.ev_call = ctx->chunk_ev[0];
@@ -1046,7 +1190,8 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n, const char *ref, const int
   }
   if (ctx->pipe_rc != ELECTOR_OK) return ctx->pipe_rc;
   if (first_error.load() != ELECTOR_OK) return first_error.load();
-  if (sums_out) memcpy(sums_out, ctx->pipe_sums, sizeof ctx->pipe_sums);
+  if (io.sums_out) memcpy(io.sums_out, ctx->pipe_sums, sizeof ctx->pipe_sums);
+  if (io.m_n_esc) *io.m_n_esc = n_esc.load();
   if (trace) fprintf(stderr, "[elector trace] call returned at %.2f ms (host clock), %zu chunks on %d workers\n",
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(), jobs.size(), nworkers);
   return ELECTOR_OK;

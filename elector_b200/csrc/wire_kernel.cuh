@@ -1,0 +1,66 @@
+// wire_kernel.cuh -- the compact wire format of elector_pipeline_run2 (include/elector_poa.h): 2-bit letters and 32-bit
+// offsets in, 4-bit merged columns out.  The alignment kernels keep reading one byte per letter and 64-bit offsets: these
+// kernels expand / pack on the device, where a pass over the letters of a call costs ~0.1 ms of HBM time -- the host link
+// carries a quarter of the bytes.  All are streaming kernels (HBM-bound).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace elector {
+
+// bits: the packed letters from byte (first >> 2) of the call's stream on; out[i] = letter first + i, i < n
+__global__ void __launch_bounds__(256) unpack2_kernel(const uint8_t *bits, int shift, int64_t n, uint8_t *out) {
+  const uint32_t lut = 0x54474341u;   // 'A' 'C' 'G' 'T'
+  const int64_t nw = (n + 3) >> 2;    // output words
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nw; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = 4 * t + shift;  // first letter of the word, counted from bits[0]
+    const uint32_t two = (uint32_t)bits[g >> 2] | ((uint32_t)bits[(g >> 2) + 1] << 8);   // (the caller pads the copy by one byte)
+    const uint32_t v = two >> (2 * (g & 3));
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w |= ((lut >> (8 * ((v >> (2 * k)) & 3u))) & 0xffu) << (8 * k);
+    reinterpret_cast<uint32_t *>(out)[t] = w;   // out is 4-byte aligned and padded to a multiple of 4
+  }
+}
+
+// the letters that are not A, C, G, T: pos = ascending positions in the call's stream, first = position of out[0]
+__global__ void patch_letters_kernel(int64_t n_exc, const int64_t *pos, const uint8_t *byte, int64_t first, uint8_t *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_exc) out[pos[i] - first] = byte[i];
+}
+
+// 32-bit offsets relative to the chunk's first letter -> the 64-bit offsets of the whole call the kernels index with
+__global__ void widen_offsets_kernel(int64_t n, const int32_t *rel, int64_t base, int64_t *off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] = base + rel[i];
+}
+
+// merged rows of the reads -> two columns per byte (ELECTOR_NIBBLE_CHARS; code 15 + an entry in the escape list for any
+// other character).  One warp per (read, row); col_base = column of the chunk's first column in the caller's buffers.
+__global__ void __launch_bounds__(128) nibble_pack_kernel(int64_t n_reads, const uint8_t *m0, const uint8_t *m1, const uint8_t *m2,
+                                                           const int64_t *m_off, const int32_t *m_len, uint8_t *n0, uint8_t *n1, uint8_t *n2,
+                                                           int64_t col_base, unsigned long long *esc_count, int64_t *esc_pos, uint8_t *esc_byte,
+                                                           int64_t esc_cap, const int32_t *abort) {
+  if (*abort) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (job >= 3 * n_reads) return;
+  const int64_t r = job / 3;
+  const int row = (int)(job - 3 * r);
+  const uint8_t *src = (row == 0 ? m0 : row == 1 ? m1 : m2) + m_off[r];
+  uint8_t *dst = (row == 0 ? n0 : row == 1 ? n1 : n2) + (m_off[r] >> 1);
+  const int L = m_len[r];
+  auto code = [&](int i) -> uint32_t {
+    if (i >= L) return 0;
+    const uint8_t c = src[i];
+    const uint32_t k = c == '.' ? 0u : c == 'a' ? 1u : c == 'c' ? 2u : c == 'g' ? 3u : c == 't' ? 4u : c == 'n' ? 5u : c == 'A' ? 6u : 15u;
+    if (k == 15u) {
+      const unsigned long long e = atomicAdd(esc_count, 1ull);
+      if ((int64_t)e < esc_cap) { esc_pos[e] = 3 * (col_base + m_off[r] + i) + row; esc_byte[e] = c; }
+    }
+    return k;
+  };
+  for (int i = 2 * lane; i < L; i += 64) dst[i >> 1] = (uint8_t)(code(i) | (code(i + 1) << 4));
+}
+
+}  // namespace elector

@@ -55,6 +55,12 @@ def load_library():
     lib.elector_merge_tally_device.restype = c.c_int
     lib.elector_pipeline_run.argtypes = [vp, c.c_int64, vp, vp, vp, vp, vp, vp, c.c_int64, vp, vp, c.c_int64] + [vp] * 8
     lib.elector_pipeline_run.restype = c.c_int
+    lib.elector_pipeline_run2.argtypes = [vp, vp]
+    lib.elector_pipeline_run2.restype = c.c_int
+    lib.elector_pack_letters.argtypes = [vp, c.c_int64, vp, vp, vp, c.c_int64]
+    lib.elector_pack_letters.restype = c.c_int64
+    lib.elector_merged_bound.argtypes = [c.c_int64, c.c_int64, vp, vp, vp]
+    lib.elector_merged_bound.restype = c.c_int64
     lib.elector_tally_sum_device.argtypes = [vp, c.c_int64, vp, vp]
     lib.elector_tally_sum_device.restype = c.c_int
     lib.elector_last_phase_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_float)]

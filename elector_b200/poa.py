@@ -18,6 +18,54 @@ TALLY_FIELDS = ["TP", "FP", "FN", "cor", "uncor", "uncorCor", "uncorUncor", "ins
                 "gapsRight", "missing", "extended", "ncols", "assessed"]
 
 
+NIBBLE_CHARS = ".acgtnA"   # ELECTOR_NIBBLE_CHARS: 4-bit column codes of the merged rows; 15 = listed in the escape arrays
+
+
+class PackedC(ctypes.Structure):     # struct elector_packed
+    _fields_ = [("bits", ctypes.c_void_p), ("n_letters", ctypes.c_int64), ("exc_pos", ctypes.c_void_p),
+                ("exc_byte", ctypes.c_void_p), ("n_exc", ctypes.c_int64)]
+
+
+class PipelineIoC(ctypes.Structure):  # struct elector_pipeline_io
+    _fields_ = [("n_windows", ctypes.c_int64), ("n_reads", ctypes.c_int64),
+                ("ref", ctypes.c_void_p), ("cor", ctypes.c_void_p), ("unc", ctypes.c_void_p),
+                ("pref", ctypes.c_void_p), ("pcor", ctypes.c_void_p), ("punc", ctypes.c_void_p),
+                ("ref_off", ctypes.c_void_p), ("cor_off", ctypes.c_void_p), ("unc_off", ctypes.c_void_p), ("read_first", ctypes.c_void_p),
+                ("rows_out", ctypes.c_void_p), ("rows_cap", ctypes.c_int64), ("row_off", ctypes.c_void_p), ("row_stride", ctypes.c_void_p),
+                ("nring", ctypes.c_void_p), ("score1", ctypes.c_void_p), ("score2", ctypes.c_void_p), ("cells", ctypes.c_void_p),
+                ("m_ref", ctypes.c_void_p), ("m_cor", ctypes.c_void_p), ("m_unc", ctypes.c_void_p), ("m_cap", ctypes.c_int64), ("m_nibbles", ctypes.c_int),
+                ("m_off", ctypes.c_void_p), ("m_len", ctypes.c_void_p),
+                ("m_esc_pos", ctypes.c_void_p), ("m_esc_byte", ctypes.c_void_p), ("m_esc_cap", ctypes.c_int64), ("m_n_esc", ctypes.c_void_p),
+                ("counters_out", ctypes.c_void_p), ("sums_out", ctypes.c_void_p)]
+
+
+@dataclass
+class PackedLetters:
+    """2 bits per letter + the exceptions (elector_pack_letters)"""
+    bits: np.ndarray
+    n_letters: int
+    exc_pos: np.ndarray
+    exc_byte: np.ndarray
+
+    def c_struct(self):
+        return PackedC(self.bits.ctypes.data, self.n_letters, self.exc_pos.ctypes.data, self.exc_byte.ctypes.data, len(self.exc_pos))
+
+
+def pack_letters(letters):
+    """uint8 array of FASTA letters -> PackedLetters"""
+    lib = load_library()
+    letters = np.ascontiguousarray(letters, dtype=np.uint8)
+    n = len(letters)
+    bits = np.zeros((n + 3) // 4 + 8, np.uint8)
+    cap = 1024
+    while True:
+        pos, byt = np.zeros(cap, np.int64), np.zeros(cap, np.uint8)
+        ne = int(lib.elector_pack_letters(letters.ctypes.data, n, bits.ctypes.data, pos.ctypes.data, byt.ctypes.data, cap))
+        if ne <= cap:
+            return PackedLetters(bits, n, pos[:ne].copy(), byt[:ne].copy())
+        cap = ne + 16
+
+
 class ElectorError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("elector error %d: %s" % (code, msg))
@@ -122,6 +170,66 @@ class PoaContext:
                                                    _p(res.row_stride), _p(res.nring), _p(res.score1), _p(res.score2), _p(res.cells),
                                                    _p(counters), _p(sums)))
         return res, counters, sums
+
+    def pipeline_io(self, ref, ref_off, cor, cor_off, unc, unc_off, read_first, packed=False, window_rows=False, merged="bytes"):
+        """elector_pipeline_run2: letters as bytes or 2-bit packed (PackedLetters or packed=True to pack here), outputs chosen by
+        the caller: window_rows (PoaResult), merged = "bytes" | "nibbles" | None, always the counters and sums.
+        Returns dict(res, merged (list of (R, C, U) strings or None), counters, sums, m_len)."""
+        lib = self._lib
+        n = len(ref_off) - 1
+        ref_off, cor_off, unc_off, read_first = (np.ascontiguousarray(o, dtype=np.int64) for o in (ref_off, cor_off, unc_off, read_first))
+        n_reads = len(read_first) - 1
+        io = PipelineIoC()
+        io.n_windows, io.n_reads = n, n_reads
+        keep = []
+        if packed:
+            pk = [s if isinstance(s, PackedLetters) else pack_letters(s) for s in (ref, cor, unc)]
+            cs = [p.c_struct() for p in pk]
+            keep += pk + cs
+            io.pref, io.pcor, io.punc = (ctypes.addressof(c) for c in cs)
+        else:
+            ref, cor, unc = (np.ascontiguousarray(s, dtype=np.uint8) for s in (ref, cor, unc))
+            keep += [ref, cor, unc]
+            io.ref, io.cor, io.unc = ref.ctypes.data, cor.ctypes.data, unc.ctypes.data
+        io.ref_off, io.cor_off, io.unc_off, io.read_first = ref_off.ctypes.data, cor_off.ctypes.data, unc_off.ctypes.data, read_first.ctypes.data
+        res = PoaResult(np.zeros(1, np.uint8), np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.int32),
+                        np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int64))
+        if window_rows:
+            bound = lib.elector_poa_rows_bound(n, _p(ref_off), _p(cor_off), _p(unc_off)) if n else 0
+            res.rows = np.empty(max(bound, 1), dtype=np.uint8)
+            io.rows_out, io.rows_cap, io.row_off, io.row_stride = res.rows.ctypes.data, len(res.rows), res.row_off.ctypes.data, res.row_stride.ctypes.data
+        io.nring, io.score1, io.score2, io.cells = res.nring.ctypes.data, res.score1.ctypes.data, res.score2.ctypes.data, res.cells.ctypes.data
+        counters = np.zeros((n_reads, len(TALLY_FIELDS)), dtype=np.int64)
+        sums = np.zeros(len(TALLY_FIELDS), dtype=np.int64)
+        io.counters_out, io.sums_out = counters.ctypes.data, sums.ctypes.data
+        m = m_off = m_len = esc_pos = esc_byte = None
+        n_esc = np.zeros(1, np.int64)
+        if merged:
+            cap = int(lib.elector_merged_bound(n, n_reads, _p(ref_off), _p(cor_off), _p(unc_off)))
+            nib = merged == "nibbles"
+            m = [np.zeros(cap // 2 + 16 if nib else cap, np.uint8) for _ in range(3)]
+            m_off, m_len = np.zeros(n_reads, np.int64), np.zeros(n_reads, np.int32)
+            io.m_ref, io.m_cor, io.m_unc, io.m_cap, io.m_nibbles = m[0].ctypes.data, m[1].ctypes.data, m[2].ctypes.data, cap, int(nib)
+            io.m_off, io.m_len = m_off.ctypes.data, m_len.ctypes.data
+            if nib:
+                esc_pos, esc_byte = np.zeros(65536, np.int64), np.zeros(65536, np.uint8)
+                io.m_esc_pos, io.m_esc_byte, io.m_esc_cap, io.m_n_esc = esc_pos.ctypes.data, esc_byte.ctypes.data, len(esc_pos), n_esc.ctypes.data
+        self._check(lib.elector_pipeline_run2(self._ctx, ctypes.byref(io)))
+        rows = None
+        if merged == "bytes":
+            rows = [tuple(m[s][m_off[r]:m_off[r] + m_len[r]].tobytes().decode("latin-1") for s in range(3)) for r in range(n_reads)]
+        elif merged == "nibbles":
+            lut = np.frombuffer((NIBBLE_CHARS + "?" * (16 - len(NIBBLE_CHARS))).encode(), np.uint8)
+            full = []
+            for s in range(3):
+                b = np.empty(2 * len(m[s]), np.uint8)
+                b[0::2] = lut[m[s] & 15]
+                b[1::2] = lut[m[s] >> 4]
+                full.append(b)
+            for k in range(int(n_esc[0])):
+                full[int(esc_pos[k] % 3)][int(esc_pos[k] // 3)] = esc_byte[k]
+            rows = [tuple(full[s][m_off[r]:m_off[r] + m_len[r]].tobytes().decode("latin-1") for s in range(3)) for r in range(n_reads)]
+        return dict(res=res, merged=rows, counters=counters, sums=sums, m_len=m_len, n_esc=int(n_esc[0]))
 
     def files(self, ref_fasta, cor_fasta, unc_fasta, pir_out, print_perm=False):
         """The body of one `poa` process (main.c:241-287)."""

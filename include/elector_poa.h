@@ -155,6 +155,55 @@ int elector_pipeline_run(elector_ctx *ctx, int64_t n_windows,
                          int32_t *nring, int32_t *score1, int32_t *score2, int64_t *cells,
                          int64_t *counters_out, int64_t *sums_out);
 
+/* ---- compact wire format of the pipelined call ------------------------------------------------------------------------
+ * elector_pipeline_run moves 1 byte per letter and three 8-byte offsets per window to the device and 3 bytes per MSA column
+ * back: at 10 000 triplets of 10 kb that is 0.35 GB each way, and the call is bound by the host link, not by the kernels.
+ * elector_pipeline_run2 is the same call (alignment.py:98-129 + Donatello + the integer part of computeStats.py) with
+ *   - letters as 2 bits each plus a list of the few that are not A, C, G or T (elector_pack_letters; the reads of ELECTOR are
+ *     DNA: `N` placeholder windows and IUPAC codes are the exceptions), window offsets sent as 32-bit values;
+ *   - outputs chosen by the caller: the per-window rows (what `poa -pir` writes; temporary files in ELECTOR,
+ *     alignment.py:128-129), the merged rows per read (what Donatello appends to msa.fa) as bytes or as 4 bits per column,
+ *     the per-read counters and their sums.  Any output pointer may be NULL; with all row pointers NULL only counters return. */
+typedef struct elector_packed {
+  const uint8_t *bits;      /* letter i in bits 2*(i&3)..2*(i&3)+1 of byte i>>2: A/a = 0, C/c = 1, G/g = 2, T/t = 3 */
+  int64_t n_letters;
+  const int64_t *exc_pos;   /* ascending positions of the letters that are none of these (their two bits are ignored) ... */
+  const uint8_t *exc_byte;  /* ... and their bytes, as in the FASTA file */
+  int64_t n_exc;
+} elector_packed;
+
+/* Packs n letters (host side, outside the timed call: the caller packs once what it reads from its FASTA files).  bits must
+ * hold (n + 3) / 4 bytes.  Returns the number of exceptions; when it exceeds exc_cap only the first exc_cap were stored and
+ * the call has to be repeated with larger arrays. */
+int64_t elector_pack_letters(const char *letters, int64_t n, uint8_t *bits, int64_t *exc_pos, uint8_t *exc_byte, int64_t exc_cap);
+
+/* 4-bit column codes of the merged rows (m_nibbles != 0): column i of a row in bits 4*(i&1).. of byte i>>1 */
+#define ELECTOR_NIBBLE_CHARS ".acgtnA"   /* codes 0..6; code 15 = any other character: listed in m_esc_* */
+
+typedef struct elector_pipeline_io {
+  int64_t n_windows, n_reads;
+  /* letters: bytes (ref / cor / unc) or packed (pref / pcor / punc); offsets as in elector_pipeline_run */
+  const char *ref, *cor, *unc;
+  const elector_packed *pref, *pcor, *punc;
+  const int64_t *ref_off, *cor_off, *unc_off, *read_first;
+  /* per window, each may be NULL (rows_out NULL: row_off / row_stride unused) */
+  char *rows_out; int64_t rows_cap; int64_t *row_off; int32_t *row_stride;
+  int32_t *nring, *score1, *score2; int64_t *cells;
+  /* merged rows per read (Donatello.cpp:50-84), each may be NULL: read r's three rows are m_len[r] columns from column
+   * m_off[r] of m_ref / m_cor / m_unc (m_off[r] is a multiple of 16; m_cap columns per buffer, elector_merged_bound()
+   * always suffices).  m_nibbles != 0: two columns per byte (ELECTOR_NIBBLE_CHARS), the buffers hold m_cap / 2 bytes, and the
+   * columns with code 15 are listed in m_esc_pos (3 * column + row, unordered) / m_esc_byte (at most m_esc_cap; *m_n_esc
+   * receives their number). */
+  char *m_ref, *m_cor, *m_unc; int64_t m_cap; int m_nibbles;
+  int64_t *m_off; int32_t *m_len;
+  int64_t *m_esc_pos; uint8_t *m_esc_byte; int64_t m_esc_cap; int64_t *m_n_esc;
+  /* per read / per call */
+  int64_t *counters_out, *sums_out;
+} elector_pipeline_io;
+
+int64_t elector_merged_bound(int64_t n_windows, int64_t n_reads, const int64_t *ref_off, const int64_t *cor_off, const int64_t *unc_off);
+int elector_pipeline_run2(elector_ctx *ctx, const elector_pipeline_io *io);
+
 /* Global counters on the device: d_sums[k] += sum over reads of d_counters[r*ELECTOR_TALLY_K+k]
  * (ELECTOR_T_EXTENDED: extended reads only).  d_sums is ELECTOR_TALLY_K int64 the caller zeroes;
  * with one rank per GPU this vector is what the final all-reduce carries. */

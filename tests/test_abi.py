@@ -5,6 +5,8 @@ import os
 import re
 import subprocess
 
+import numpy as np
+
 import pytest
 
 from conftest import ROOT, has_gpu
@@ -87,3 +89,16 @@ def test_generated_matrix_is_the_shipped_one(tmp_path):
     assert m.nsymbol == d.nsymbol == 31 and m.symbol == d.symbol
     assert [list(r)[:31] for r in list(m.score)[:31]] == [list(r)[:31] for r in list(d.score)[:31]]
     assert list(m.gap_penalty_x)[:17] == [10] + [5] * 15 + [0]
+
+
+def test_pack_letters_roundtrip():
+    import elector_b200
+    s = np.frombuffer(b"ACGTacgtNNRYKACGTTTGA" * 37 + b"n", np.uint8)
+    p = elector_b200.pack_letters(s)
+    assert p.n_letters == len(s)
+    got = np.frombuffer(b"ACGT", np.uint8)[(p.bits[np.arange(len(s)) >> 2] >> (2 * (np.arange(len(s)) & 3))) & 3].copy()
+    got[p.exc_pos] = p.exc_byte
+    up = np.frombuffer(bytes(s).upper(), np.uint8)
+    keep = np.ones(len(s), bool); keep[p.exc_pos] = False
+    assert np.array_equal(got[keep], up[keep]) and np.array_equal(got[p.exc_pos], s[p.exc_pos])
+    assert all(bytes([b]) not in b"ACGTacgt" for b in p.exc_byte)

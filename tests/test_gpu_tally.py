@@ -193,3 +193,30 @@ def test_config_slices_pipeline_equals_oracle_chain(cfg, reads):
         R, C, U = ("".join(s[i] for i in keep) for s in (R, C, U))
         exp = to.tally_read(R, C, U)
         assert [int(v) for v in counters[r]] == [exp[f] for f in TALLY_FIELDS], (cfg, r)
+
+
+@pytest.mark.parametrize("packed,merged,chunks", [(True, "bytes", "1"), (True, "nibbles", "3"), (False, "nibbles", "2"), (True, None, "1")])
+def test_compact_wire_format_equals_byte_path(packed, merged, chunks, monkeypatch):
+    """elector_pipeline_run2: 2-bit letters + exceptions and 32-bit offsets in, merged rows as bytes or 4-bit columns (with
+    escapes) or counters only out -- same windows, merged rows (= Donatello of the window rows) and counters as the byte
+    path, on a config-2 slice (`N` placeholder windows: exceptions on the way in; out-of-code letters forced in: escapes)"""
+    monkeypatch.setenv("ELECTOR_PIPELINE_CHUNKS", chunks)
+    import elector_b200
+    import workloads
+    wl = workloads.make_windows(2, 300)
+    ref, cor, unc = wl["ref"].copy(), wl["cor"].copy(), wl["unc"].copy()
+    # a few letters outside ACGT (IUPAC, lower case, 'u') and outside the 4-bit column code
+    rng = np.random.default_rng(5)
+    for arr, letters in ((ref, b"RYn"), (cor, b"acgtNu"), (unc, b"K?]")):
+        idx = rng.integers(0, len(arr), 40)
+        arr[idx] = np.frombuffer(letters, np.uint8)[rng.integers(0, len(letters), 40)]
+    with elector_b200.PoaContext(0) as c:
+        base_res, base_cnt, base_sums = c.pipeline_csr(ref, wl["ref_off"], cor, wl["cor_off"], unc, wl["unc_off"], wl["read_first"])
+        base_merged = c.merge(base_res, wl["read_first"])
+        out = c.pipeline_io(ref, wl["ref_off"], cor, wl["cor_off"], unc, wl["unc_off"], wl["read_first"], packed=packed, window_rows=False, merged=merged)
+    assert np.array_equal(out["res"].nring, base_res.nring) and np.array_equal(out["res"].score2, base_res.score2)
+    assert np.array_equal(out["counters"], base_cnt) and np.array_equal(out["sums"], base_sums)
+    if merged:
+        assert out["merged"] == base_merged
+        if merged == "nibbles":
+            assert out["n_esc"] > 0
