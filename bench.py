@@ -261,9 +261,9 @@ def main():
             dist.all_reduce(d_sums)       # the one collective of the path: 24 int64 counters
 
     # ---- end to end: the call a user makes, host buffers in / out, copies inside the timed region ----
-    # Three wire formats of the same call (include/elector_poa.h, elector_pipeline_run2).  The headline `e2e` is the second:
-    # what ELECTOR consumes after alignment.py (the merged per-read MSA that Donatello appends to msa.fa, and the per-read
-    # counters of computeStats.py) from what its caller has (the reads, packed once outside the call).
+    # Four wire formats of the same call (include/elector_poa.h, elector_pipeline_run2).  The headline `e2e` is the first:
+    # what ELECTOR consumes after alignment.py (the merged per-read MSA that Donatello appends to msa.fa, losslessly as 4-bit
+    # columns, and the per-read counters of computeStats.py) from what its caller has (the reads, packed once outside the call).
     from elector_b200.poa import PipelineIoC, pack_letters
     packed = [pack_letters(wl[k]) for k in ("ref", "cor", "unc")]      # outside the timed region, like reading the FASTA files
     pk_pinned = []
@@ -273,6 +273,7 @@ def main():
         pk.bits, n_e = a_bits, len(pk.exc_pos)
         pk.exc_pos, pk.exc_byte = a_pos[:n_e], a_byt[:n_e]
     pk_c = [pk.c_struct() for pk in packed]
+    len32 = [pinned(np.diff(wl[k]).astype(np.int32)) for k in ("ref_off", "cor_off", "unc_off")]   # 32-bit window lengths: what crosses the link
     m_cap = int(lib.elector_merged_bound(n, n_trip, hptr["ref_off"], hptr["cor_off"], hptr["unc_off"]))
     h_m = [torch.empty(m_cap, dtype=torch.uint8).pin_memory() for _ in range(3)]
     h_moff, h_mlen = torch.empty(n_trip, dtype=torch.int64).pin_memory(), torch.empty(n_trip, dtype=torch.int32).pin_memory()
@@ -290,6 +291,7 @@ def main():
             io.rows_out, io.rows_cap, io.row_off, io.row_stride = h_rows.data_ptr(), bound, h_out["row_off"].data_ptr(), h_out["stride"].data_ptr()
         else:
             io.pref, io.pcor, io.punc = (ctypes.addressof(c) for c in pk_c)
+            io.ref_len, io.cor_len, io.unc_len = (t[1].ctypes.data for t in len32)
             if mode != "packed_in_counters_out":
                 io.m_ref, io.m_cor, io.m_unc, io.m_cap = h_m[0].data_ptr(), h_m[1].data_ptr(), h_m[2].data_ptr(), m_cap
                 io.m_off, io.m_len = h_moff.data_ptr(), h_mlen.data_ptr()
@@ -298,7 +300,7 @@ def main():
                     io.m_esc_pos, io.m_esc_byte, io.m_esc_cap, io.m_n_esc = h_esc_pos.data_ptr(), h_esc_byte.data_ptr(), 1 << 20, h_nesc.data_ptr()
         return io
 
-    E2E_MODES = ["packed_in_merged_rows_out", "bytes_in_window_rows_out", "packed_in_merged_nibbles_out", "packed_in_counters_out"]
+    E2E_MODES = ["packed_in_merged_nibbles_out", "bytes_in_window_rows_out", "packed_in_merged_rows_out", "packed_in_counters_out"]
     ios = {m: make_io(m) for m in E2E_MODES}
 
     def make_step(mode):
@@ -428,7 +430,7 @@ def main():
         pass
     letters = int(wl["ref_off"][-1] + wl["cor_off"][-1] + wl["unc_off"][-1])
     in_bytes = letters + 3 * 8 * (n + 1) + 8 * (n_trip + 1)                     # byte path: 1 B per letter, 64-bit offsets
-    in_packed = sum((pk.n_letters + 3) // 4 + 9 * len(pk.exc_pos) for pk in packed) + 3 * 4 * (n + 1) + 8 * (n_trip + 1)
+    in_packed = sum((pk.n_letters + 3) // 4 + 9 * len(pk.exc_pos) for pk in packed) + 3 * 4 * n + 8 * (n_trip + 1)
     out_rows = used + n * (8 + 4 + 4) + n_trip * K * 8 + K * 8                   # byte path: window rows, their offsets, counters
     out_merged = 3 * merged_cols + n * 4 + n_trip * (8 + 4 + K * 8) + K * 8     # merged rows as bytes, nring, m_off / m_len, counters
     wire = {"packed_in_merged_rows_out": (in_packed, out_merged), "bytes_in_window_rows_out": (in_bytes, out_rows),
@@ -451,7 +453,7 @@ def main():
                    "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush" % (in_bytes / 1e6), "parity": parity},
         "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": wire[E2E_MODES[0]][0], "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": e2e_step_ms,
-                "call": "elector_pipeline_run2: 2-bit packed letters + 32-bit offsets in (packed once, outside the call), merged per-read MSA rows (what Donatello appends to msa.fa) + per-read counters + sums out; pinned host buffers",
+                "call": "elector_pipeline_run2: 2-bit packed letters + 32-bit window lengths in (packed once, outside the call), merged per-read MSA rows (what Donatello appends to msa.fa) as 4-bit columns + per-read counters + sums out; pinned host buffers",
                 "host_link_gbs": (wire[E2E_MODES[0]][0] + out_bytes) / (e2e_step_ms / 1e3) / 1e9,
                 "limiter": "kernels (%.2f ms resident) + the tail of the last chunk's results; the host link carries %.0f MB per call" % (step_ms, (wire[E2E_MODES[0]][0] + out_bytes) / 1e6),
                 "modes": {m: {"ms_per_step": e2e_modes[m], "value": n_trip * world / (e2e_modes[m] / 1e3), "h2d_bytes_per_step": wire[m][0], "d2h_bytes_per_step": wire[m][1],

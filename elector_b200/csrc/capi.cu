@@ -607,6 +607,7 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   // thread, while the chunks before it are on their way; the exceptions of the chunk are found by binary search
   int64_t exc0[3] = {0, 0, 0}, exc1[3] = {0, 0, 0};
   int32_t *stage = nullptr;
+  bool use_len = false;
   if (pa.packed) {
     const size_t need = (size_t)3 * (nw + 1) * sizeof(int32_t);
     if (need > ctx->h_stage_cap) {
@@ -616,17 +617,21 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
       ctx->h_stage_cap = need + need / 4;
     }
     stage = static_cast<int32_t *>(ctx->h_stage);
+    const int32_t *h_len[3] = {io.ref_len, io.cor_len, io.unc_len};
+    use_len = h_len[0] && h_len[1] && h_len[2] && nw <= 1024 * 1024;   // the caller's 32-bit lengths cross the link as they are
     for (int k = 0; k < 3; ++k) {
       if (len[k] > 0x7fffffff) return ctx->fail(ELECTOR_ETOOLARGE, "a chunk holds more than 2^31 letters of one kind");
-      int32_t *dst = stage + (size_t)k * (nw + 1);
-      const int64_t *src = h_off[k] + w0, f = first[k];
-      for (int64_t i = 0; i <= nw; ++i) dst[i] = (int32_t)(src[i] - f);
+      if (!use_len) {
+        int32_t *dst = stage + (size_t)k * (nw + 1);
+        const int64_t *src = h_off[k] + w0, f = first[k];
+        for (int64_t i = 0; i <= nw; ++i) dst[i] = (int32_t)(src[i] - f);
+      }
       const int64_t *ep = h_pk[k]->exc_pos, ne = h_pk[k]->n_exc;
       exc0[k] = std::lower_bound(ep, ep + ne, first[k]) - ep;
       exc1[k] = std::lower_bound(ep, ep + ne, first[k] + len[k]) - ep;
       CU(ctx->d_pk[k].reserve((size_t)(len[k] / 4 + 8)));
     }
-    CU(ctx->d_rel.reserve(need));
+    CU(ctx->d_rel.reserve(need + 3 * 1032 * sizeof(long long)));
     const int64_t ne_tot = (exc1[0] - exc0[0]) + (exc1[1] - exc0[1]) + (exc1[2] - exc0[2]);
     CU(ctx->d_exc_pos.reserve((size_t)(ne_tot + 1) * 8)); CU(ctx->d_exc_byte.reserve((size_t)ne_tot + 8));
   }
@@ -644,7 +649,20 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   if (ctx->trace) CU(cudaEventRecord(ctx->uev0, st));
   // the offsets first, on the compute stream: the size sort needs nothing else.  The letters follow on the copy stream --
   // ref and cor (phase 1 waits for them), then unc (phase 2 waits for it) -- while the sort and phase 1 run.
-  if (pa.packed) {
+  if (pa.packed && use_len) {   // 32-bit lengths in, added up on the device
+    const int32_t *h_len[3] = {io.ref_len, io.cor_len, io.unc_len};
+    const int nblocks = (int)((nw + 1023) / 1024);
+    long long *totals = reinterpret_cast<long long *>(ctx->d_rel.as<int32_t>() + (size_t)3 * (nw + 1) + ((nw + 1) & 1));
+    for (int k = 0; k < 3; ++k) {
+      int32_t *dl = ctx->d_rel.as<int32_t>() + (size_t)k * (nw + 1);
+      CU(cudaMemcpyAsync(dl, h_len[k] + w0, (size_t)nw * 4, cudaMemcpyHostToDevice, st));
+      len_scan_blocks_kernel<<<nblocks, 1024, 0, st>>>(nw, dl, totals + (size_t)k * 1032);
+      len_scan_totals_kernel<<<1, 1024, 0, st>>>(nblocks, totals + (size_t)k * 1032);
+      len_to_offsets_kernel<<<(unsigned)((nw + 256) / 256), 256, 0, st>>>(nw, dl, totals + (size_t)k * 1032, nblocks, first[k], d_off[k]->as<int64_t>());
+    }
+    CU(cudaGetLastError());
+    ctx->last_launches += 9;
+  } else if (pa.packed) {
     CU(cudaMemcpyAsync(ctx->d_rel.p, stage, (size_t)3 * (nw + 1) * 4, cudaMemcpyHostToDevice, st));
     for (int k = 0; k < 3; ++k)
       widen_offsets_kernel<<<(unsigned)((nw + 256) / 256), 256, 0, st>>>(nw + 1, ctx->d_rel.as<int32_t>() + (size_t)k * (nw + 1), first[k], d_off[k]->as<int64_t>());
@@ -811,7 +829,7 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   return ELECTOR_OK;
 }
 
-int create_context(int device, const ScoreMatrix &mat, elector_ctx **out);
+int create_context(int device, const ScoreMatrix &mat, elector_ctx **out, int worker = 0);
 
 }  // namespace
 
@@ -835,8 +853,10 @@ int elector_poa_init(int device, const char *matrix_path, elector_ctx **out) {
 }  // extern "C"
 
 namespace {
-// a context for `device` with the scoring of `mat` (elector_poa_init; worker contexts of the pipelined entry point)
-int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
+// a context for `device` with the scoring of `mat` (elector_poa_init; worker contexts of the pipelined entry point).
+// worker k > 0: its streams get a lower priority than those of worker k - 1 -- the chunks of a pipelined call then finish one
+// after the other instead of all together, and the results of one leave while the next computes.
+int create_context(int device, const ScoreMatrix &mat, elector_ctx **out, int worker) {
   elector_ctx *ctx = new elector_ctx();
   auto bail = [&](int code) {
     g_init_error = ctx->err;
@@ -863,7 +883,11 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
   cudaGetDeviceProperties(&prop, device);
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority
+  int prio = std::min(prio_lo, prio_hi + worker);
+  if (const char *pe = getenv("ELECTOR_NO_PRIORITIES")) if (pe[0] == '1') prio = prio_lo;
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_rows)) != cudaSuccess ||
@@ -873,7 +897,7 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
       (e = cudaEventCreateWithFlags(&ctx->ev_in[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->uev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->uev1)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->lin_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithPriority(&ctx->lin_stream, cudaStreamNonBlocking, prio)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_lin_done)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_lin_sorted, cudaEventDisableTiming)) != cudaSuccess ||
@@ -902,7 +926,7 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out) {
       return bail(ELECTOR_ECUDA);
     }
   for (int k = 0; k < kSideStreams; ++k)
-    if ((e = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking)) != cudaSuccess ||
+    if ((e = cudaStreamCreateWithPriority(&ctx->side[k], cudaStreamNonBlocking, prio)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming)) != cudaSuccess) {
       ctx->fail(ELECTOR_ECUDA, "context setup: %s", cudaGetErrorString(e));
       return bail(ELECTOR_ECUDA);
@@ -1089,7 +1113,9 @@ int elector_pipeline_run2(elector_ctx *ctx, const elector_pipeline_io *iop) {
   // group, so their throughput grows with the number of windows sorted together -- but chunks on several workers overlap
   // their transfers with each other's kernels: three chunks of ~0.65 M windows on three workers are the measured best for
   // 10 000 reads of 10 kb.  ELECTOR_PIPELINE_CHUNKS forces a chunk count.
-  int64_t chunk_windows = 700000;
+  // With packed letters the inputs are a quarter of the bytes and fewer, larger chunks win: two chunks of ~1 M windows measured
+  // best for all output formats (counters only: 8.9 ms against 9.3 in three chunks and 11.9 in one).
+  int64_t chunk_windows = packed ? 1000000 : 700000;
   int want_workers = 3;
   if (const char *e = getenv("ELECTOR_PIPELINE_CHUNK_WINDOWS")) chunk_windows = std::max<int64_t>(1024, atoll(e));
   if (const char *e = getenv("ELECTOR_PIPELINE_WORKERS")) want_workers = std::max(1, std::min(8, atoi(e)));
@@ -1143,7 +1169,7 @@ int elector_pipeline_run2(elector_ctx *ctx, const elector_pipeline_io *iop) {
   const int nworkers = (int)std::min<size_t>(jobs.size(), (size_t)want_workers);
   while ((int)ctx->workers.size() < nworkers - 1) {
     elector_ctx *child = nullptr;
-    const int rc = create_context(ctx->device, ctx->mat, &child);
+    const int rc = create_context(ctx->device, ctx->mat, &child, (int)ctx->workers.size() + 1);
     if (rc != ELECTOR_OK) return ctx->fail(rc, "worker context: %s", g_init_error.c_str());
     ctx->workers.push_back(child);
   }

@@ -35,6 +35,48 @@ __global__ void widen_offsets_kernel(int64_t n, const int32_t *rel, int64_t base
   if (i < n) off[i] = base + rel[i];
 }
 
+// window lengths -> 64-bit offsets: per 1024-window block an exclusive scan (in place: len becomes the offset inside the
+// block) and the block total; then one CTA scans the block totals (at most 1024 blocks x 1024 windows per chunk); then
+// off[i] = base + block_base[i / 1024] + len[i], off[n] = base + total
+__global__ void __launch_bounds__(1024) len_scan_blocks_kernel(int64_t n, int32_t *len, long long *block_total) {
+  __shared__ int32_t warp_sum[32];
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int32_t v = i < n ? len[i] : 0;
+  int32_t incl = v;
+  for (int d = 1; d < 32; d <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) warp_sum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int32_t s = warp_sum[lane];
+    for (int d = 1; d < 32; d <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += t; }
+    warp_sum[lane] = s;
+  }
+  __syncthreads();
+  const int32_t before = (wid ? warp_sum[wid - 1] : 0) + incl - v;
+  if (i < n) len[i] = before;
+  if (threadIdx.x == 1023) block_total[blockIdx.x] = before + v;
+}
+__global__ void __launch_bounds__(1024) len_scan_totals_kernel(int nblocks, long long *block_total) {
+  __shared__ long long part[1024];
+  const long long v = (int)threadIdx.x < nblocks ? block_total[threadIdx.x] : 0;
+  part[threadIdx.x] = v;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const long long t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < nblocks) block_total[threadIdx.x] = part[threadIdx.x] - v;
+  if (threadIdx.x == 1023) block_total[nblocks] = part[1023];
+}
+__global__ void len_to_offsets_kernel(int64_t n, const int32_t *scanned, const long long *block_base, int nblocks, int64_t base, int64_t *off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) off[i] = base + block_base[i >> 10] + scanned[i];
+  else if (i == n) off[n] = base + block_base[nblocks];
+}
+
 // merged rows of the reads -> two columns per byte (ELECTOR_NIBBLE_CHARS; code 15 + an entry in the escape list for any
 // other character).  One warp per (read, row); col_base = column of the chunk's first column in the caller's buffers.
 __global__ void __launch_bounds__(128) nibble_pack_kernel(int64_t n_reads, const uint8_t *m0, const uint8_t *m1, const uint8_t *m2,

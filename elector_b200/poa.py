@@ -31,6 +31,7 @@ class PipelineIoC(ctypes.Structure):  # struct elector_pipeline_io
                 ("ref", ctypes.c_void_p), ("cor", ctypes.c_void_p), ("unc", ctypes.c_void_p),
                 ("pref", ctypes.c_void_p), ("pcor", ctypes.c_void_p), ("punc", ctypes.c_void_p),
                 ("ref_off", ctypes.c_void_p), ("cor_off", ctypes.c_void_p), ("unc_off", ctypes.c_void_p), ("read_first", ctypes.c_void_p),
+                ("ref_len", ctypes.c_void_p), ("cor_len", ctypes.c_void_p), ("unc_len", ctypes.c_void_p),
                 ("rows_out", ctypes.c_void_p), ("rows_cap", ctypes.c_int64), ("row_off", ctypes.c_void_p), ("row_stride", ctypes.c_void_p),
                 ("nring", ctypes.c_void_p), ("score1", ctypes.c_void_p), ("score2", ctypes.c_void_p), ("cells", ctypes.c_void_p),
                 ("m_ref", ctypes.c_void_p), ("m_cor", ctypes.c_void_p), ("m_unc", ctypes.c_void_p), ("m_cap", ctypes.c_int64), ("m_nibbles", ctypes.c_int),
@@ -171,7 +172,7 @@ class PoaContext:
                                                    _p(counters), _p(sums)))
         return res, counters, sums
 
-    def pipeline_io(self, ref, ref_off, cor, cor_off, unc, unc_off, read_first, packed=False, window_rows=False, merged="bytes"):
+    def pipeline_io(self, ref, ref_off, cor, cor_off, unc, unc_off, read_first, packed=False, window_rows=False, merged="bytes", lengths32=False):
         """elector_pipeline_run2: letters as bytes or 2-bit packed (PackedLetters or packed=True to pack here), outputs chosen by
         the caller: window_rows (PoaResult), merged = "bytes" | "nibbles" | None, always the counters and sums.
         Returns dict(res, merged (list of (R, C, U) strings or None), counters, sums, m_len)."""
@@ -187,6 +188,10 @@ class PoaContext:
             cs = [p.c_struct() for p in pk]
             keep += pk + cs
             io.pref, io.pcor, io.punc = (ctypes.addressof(c) for c in cs)
+            if lengths32:
+                lens = [np.ascontiguousarray(np.diff(o), dtype=np.int32) for o in (ref_off, cor_off, unc_off)]
+                keep += lens
+                io.ref_len, io.cor_len, io.unc_len = (l.ctypes.data for l in lens)
         else:
             ref, cor, unc = (np.ascontiguousarray(s, dtype=np.uint8) for s in (ref, cor, unc))
             keep += [ref, cor, unc]

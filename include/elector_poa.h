@@ -186,6 +186,10 @@ typedef struct elector_pipeline_io {
   const char *ref, *cor, *unc;
   const elector_packed *pref, *pcor, *punc;
   const int64_t *ref_off, *cor_off, *unc_off, *read_first;
+  /* optional with packed letters: the window lengths as 32-bit values (n_windows each), prepared by the caller like the packed
+   * letters.  They are what crosses the link (the device adds them up); without them the call derives 32-bit offsets from the
+   * 64-bit ones itself, a pass over 24 bytes per window on the calling thread. */
+  const int32_t *ref_len, *cor_len, *unc_len;
   /* per window, each may be NULL (rows_out NULL: row_off / row_stride unused) */
   char *rows_out; int64_t rows_cap; int64_t *row_off; int32_t *row_stride;
   int32_t *nring, *score1, *score2; int64_t *cells;
