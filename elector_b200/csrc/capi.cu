@@ -23,6 +23,7 @@
 #include "host_setup.hpp"
 #include "tally_kernel.cuh"
 #include "wire_kernel.cuh"
+#include "split_kernel.cuh"
 #include "peak_kernel.cuh"
 
 using namespace elector;
@@ -104,6 +105,7 @@ struct elector_ctx {
   cudaEvent_t ev_merged = nullptr;  // merge + tally of a chunk are done; the merged columns of the chunk are in h_totals[2]
   cudaEvent_t wait_in[2] = {nullptr, nullptr};   // run_device: phase 1 / phase 2 wait for these (letters still on their way), when set
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
+  void *split_state = nullptr;   // device buffers of the window cutting (split_capi.inl)
   std::string err;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -949,8 +951,10 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out, int wo
 
 extern "C" {
 
+void elector_split_release(elector_ctx *ctx);
 void elector_poa_free(elector_ctx *ctx) {
   if (!ctx) return;
+  elector_split_release(ctx);
   for (elector_ctx *w : ctx->workers) elector_poa_free(w);
   ctx->workers.clear();
   if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
@@ -1334,3 +1338,4 @@ int elector_last_kernel_ms(const elector_ctx *ctx, float *ms, int *launches) {
 }  // extern "C"
 
 #include "tally_capi.inl"
+#include "split_capi.inl"
