@@ -106,6 +106,8 @@ struct elector_ctx {
   cudaEvent_t wait_in[2] = {nullptr, nullptr};   // run_device: phase 1 / phase 2 wait for these (letters still on their way), when set
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
   void *split_state = nullptr;   // device buffers of the window cutting (split_capi.inl)
+  cudaEvent_t ev_split0 = nullptr, ev_split1 = nullptr, ev_mt0 = nullptr, ev_mt1 = nullptr;   // window cutting; merge + tally of elector_reads_run
+  float last_ms_split = 0.f, last_ms_tally = 0.f;
   std::string err;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -892,6 +894,8 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out, int wo
   if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_split0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_split1)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_mt0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_mt1)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev_rows)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_lin, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_merged, cudaEventDisableTiming)) != cudaSuccess ||
@@ -966,6 +970,7 @@ void elector_poa_free(elector_ctx *ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+  for (cudaEvent_t ev : {ctx->ev_split0, ctx->ev_split1, ctx->ev_mt0, ctx->ev_mt1}) if (ev) cudaEventDestroy(ev);
   if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
   for (int k = 0; k < 2; ++k) if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
   for (int k = 0; k < 8; ++k) if (ctx->ev_regb[k]) cudaEventDestroy(ctx->ev_regb[k]);
@@ -1325,6 +1330,14 @@ int elector_last_phase_ms(const elector_ctx *ctx, float *ms_phase1, float *ms_to
   if (!ctx) return ELECTOR_EINVAL;
   if (ms_phase1) *ms_phase1 = ctx->last_ms_phase1;
   if (ms_total) *ms_total = ctx->last_ms;
+  return ELECTOR_OK;
+}
+
+int elector_last_reads_ms(const elector_ctx *ctx, float *ms_split, float *ms_poa, float *ms_merge_tally) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (ms_split) *ms_split = ctx->last_ms_split;
+  if (ms_poa) *ms_poa = ctx->last_ms - ctx->last_ms_split - ctx->last_ms_tally;
+  if (ms_merge_tally) *ms_merge_tally = ctx->last_ms_tally;
   return ELECTOR_OK;
 }
 

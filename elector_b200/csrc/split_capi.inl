@@ -34,23 +34,19 @@ void elector_split_release(elector_ctx *ctx) {
   ctx->split_state = nullptr;
 }
 
-int elector_split_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ref_off, const char *unc, const int64_t *unc_off, const char *cor,
-                      const int64_t *cor_off, const int32_t *header_len, double threshold, int32_t *status, int32_t *k_used, int64_t *read_first,
-                      int64_t win_cap, int64_t *w_ref_off, int64_t *w_unc_off, int64_t *w_cor_off, char *w_ref, int64_t w_ref_cap, char *w_unc,
-                      int64_t w_unc_cap, char *w_cor, int64_t w_cor_cap, int64_t *n_windows) {
-  if (!ctx) return ELECTOR_EINVAL;
-  if (n < 0 || (n > 0 && (!ref || !unc || !cor || !ref_off || !unc_off || !cor_off || !header_len || !read_first || !w_ref_off || !w_unc_off || !w_cor_off || !w_ref ||
-                          !w_unc || !w_cor || !n_windows)))
-    return ctx->fail(ELECTOR_EINVAL, "null argument");
-  if (n_windows) *n_windows = 0;
-  if (n == 0) return ELECTOR_OK;
+}  // extern "C"
+
+namespace {
+// One round of window cutting with the result left on the device: b.w_off[k] / b.w_let[k] (k = 0 ref, 1 unc, 2 cor), b.rf
+// (first window of every triplet), b.status, b.kidx.  tot[0] = windows, tot[1..3] = letters of the three kinds.
+int split_device(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ref_off, const char *unc, const int64_t *unc_off, const char *cor,
+                 const int64_t *cor_off, const int32_t *header_len, double threshold, int64_t tot[4]) {
   if (n > 0x1fffffff) return ctx->fail(ELECTOR_EINVAL, "too many triplets in one call");
-  CU(cudaSetDevice(ctx->device));
   SplitBufs &b = *split_bufs(ctx);
   cudaStream_t st = ctx->stream;
   const char *h_let[3] = {ref, unc, cor};
   const int64_t *h_off[3] = {ref_off, unc_off, cor_off};
-  // the host decides what main() decides before best_split (:412-413,:425-432): a corrected read shorter than the threshold share
+  // the host decides what main() decides before best_split (:414-415,:425-431): a corrected read shorter than the threshold share
   // of its reference is not cut; the longest reference read sizes the tables
   std::vector<int32_t> st_in((size_t)n);
   std::vector<int64_t> win_off((size_t)n + 1);
@@ -64,7 +60,6 @@ int elector_split_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_
     longest = std::max(longest, lr);
     win_off[(size_t)t + 1] = win_off[(size_t)t] + 4 * (lr / 16 + 16);
   }
-  if (win_off[(size_t)n] / 4 > win_cap) return ctx->fail(ELECTOR_ECAPACITY, "win_cap %lld too small (%lld needed)", (long long)win_cap, (long long)(win_off[(size_t)n] / 4));
   uint32_t max_slots = 64;
   while (max_slots < 2 * (uint64_t)longest + 2) max_slots <<= 1;
   const int32_t max_anchors = (int32_t)(longest / 8 + 16);
@@ -97,7 +92,7 @@ int elector_split_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_
   a.wins = b.wins.as<SplitWin>(); a.win_off = b.win_off.as<int64_t>();
   a.job_n = b.job_n.as<int32_t>(); a.job_largest = b.job_l.as<uint32_t>();
   a.counter = b.misc.as<int32_t>();
-  CU(cudaEventRecord(ctx->ev0, st));
+  CU(cudaEventRecord(ctx->ev_split0, st));
   split_jobs_kernel<<<grid, 256, 0, st>>>(a);
   split_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a.status_in, a.job_n, a.job_largest, a.wins, a.win_off, b.status.as<int32_t>(), b.kidx.as<int32_t>(),
                                                                   b.nrec.as<int64_t>(), b.nl[0].as<int64_t>(), b.nl[1].as<int64_t>(), b.nl[2].as<int64_t>(), b.misc.as<int32_t>() + 1);
@@ -105,16 +100,11 @@ int elector_split_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_
   for (int k = 0; k < 3; ++k) scan_offsets_kernel<<<1, 1024, 0, st>>>(n, b.nl[k].as<int64_t>(), b.base[k + 1].as<int64_t>());
   CU(cudaGetLastError());
   // sizes of the outputs, then the windows themselves
-  int64_t tot[4];
   for (int k = 0; k < 4; ++k) CU(cudaMemcpyAsync(&ctx->h_totals[k], b.base[k].as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-  int32_t err = 0;
   CU(cudaMemcpyAsync(&ctx->h_totals[4], b.misc.as<int32_t>() + 1, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   for (int k = 0; k < 4; ++k) tot[k] = ctx->h_totals[k];
-  err = (int32_t)(ctx->h_totals[4] & 0xffffffff);
-  if (err) return ctx->fail(ELECTOR_ECAPACITY, "a triplet has more windows than its share of the record buffer");
-  if (tot[0] > win_cap || tot[1] > w_ref_cap || tot[2] > w_unc_cap || tot[3] > w_cor_cap)
-    return ctx->fail(ELECTOR_ECAPACITY, "output buffers too small: %lld windows, %lld / %lld / %lld letters", (long long)tot[0], (long long)tot[1], (long long)tot[2], (long long)tot[3]);
+  if ((int32_t)(ctx->h_totals[4] & 0xffffffff)) return ctx->fail(ELECTOR_ECAPACITY, "a triplet has more windows than its share of the record buffer");
   for (int k = 0; k < 3; ++k) { CU(b.w_off[k].reserve((size_t)(tot[0] + 1) * 8)); CU(b.w_let[k].reserve((size_t)tot[k + 1] + 16)); }
   CU(b.rf.reserve((size_t)(n + 1) * 8));
   split_emit_kernel<<<(unsigned)n, 128, 0, st>>>(n, a.let[0], a.let[1], a.let[2], a.off[0], a.off[1], a.off[2], b.status.as<int32_t>(), b.kidx.as<int32_t>(), a.wins, a.win_off,
@@ -122,7 +112,33 @@ int elector_split_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_
                                                 b.w_off[1].as<int64_t>(), b.w_off[2].as<int64_t>(), b.w_let[0].as<uint8_t>(), b.w_let[1].as<uint8_t>(), b.w_let[2].as<uint8_t>(),
                                                 b.rf.as<int64_t>());
   CU(cudaGetLastError());
-  CU(cudaEventRecord(ctx->ev1, st));
+  CU(cudaEventRecord(ctx->ev_split1, st));
+  ctx->last_launches += 7;
+  return ELECTOR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int elector_split_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ref_off, const char *unc, const int64_t *unc_off, const char *cor,
+                      const int64_t *cor_off, const int32_t *header_len, double threshold, int32_t *status, int32_t *k_used, int64_t *read_first,
+                      int64_t win_cap, int64_t *w_ref_off, int64_t *w_unc_off, int64_t *w_cor_off, char *w_ref, int64_t w_ref_cap, char *w_unc,
+                      int64_t w_unc_cap, char *w_cor, int64_t w_cor_cap, int64_t *n_windows) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (n < 0 || (n > 0 && (!ref || !unc || !cor || !ref_off || !unc_off || !cor_off || !header_len || !read_first || !w_ref_off || !w_unc_off || !w_cor_off || !w_ref ||
+                          !w_unc || !w_cor || !n_windows)))
+    return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_windows) *n_windows = 0;
+  if (n == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  ctx->last_launches = 0;
+  int64_t tot[4];
+  const int rc = split_device(ctx, n, ref, ref_off, unc, unc_off, cor, cor_off, header_len, threshold, tot);
+  if (rc != ELECTOR_OK) return rc;
+  if (tot[0] > win_cap || tot[1] > w_ref_cap || tot[2] > w_unc_cap || tot[3] > w_cor_cap)
+    return ctx->fail(ELECTOR_ECAPACITY, "output buffers too small: %lld windows, %lld / %lld / %lld letters", (long long)tot[0], (long long)tot[1], (long long)tot[2], (long long)tot[3]);
+  SplitBufs &b = *split_bufs(ctx);
+  cudaStream_t st = ctx->stream;
   int64_t *w_off_h[3] = {w_ref_off, w_unc_off, w_cor_off};
   char *w_let_h[3] = {w_ref, w_unc, w_cor};
   for (int k = 0; k < 3; ++k) {
@@ -136,8 +152,93 @@ int elector_split_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_
   CU(cudaStreamSynchronize(st));
   if (k_used) for (int64_t t = 0; t < n; ++t) k_used[t] = 15 - 2 * kidx[(size_t)t];
   *n_windows = tot[0];
-  ctx->last_launches = 8;
-  cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+  cudaEventElapsedTime(&ctx->last_ms, ctx->ev_split0, ctx->ev_split1);
+  return ELECTOR_OK;
+}
+
+int elector_reads_run(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *ref_off, const char *unc, const int64_t *unc_off, const char *cor,
+                      const int64_t *cor_off, const int32_t *header_len, double threshold, int32_t *status, int32_t *k_used, int64_t *read_first,
+                      int64_t *n_windows, int64_t *counters_out, int64_t *sums_out, char *m_ref, char *m_cor, char *m_unc, int64_t m_cap, int64_t *m_off,
+                      int32_t *m_len) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (n < 0 || (n > 0 && (!ref || !unc || !cor || !ref_off || !unc_off || !cor_off || !header_len || !counters_out))) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if ((m_ref || m_cor || m_unc) && (!m_ref || !m_cor || !m_unc || !m_off || !m_len)) return ctx->fail(ELECTOR_EINVAL, "merged rows need all of m_ref, m_cor, m_unc, m_off, m_len");
+  if (n_windows) *n_windows = 0;
+  if (sums_out) memset(sums_out, 0, ELECTOR_TALLY_K * sizeof(int64_t));
+  if (n == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
+  ctx->last_ms = ctx->last_ms_phase1 = 0.f;
+  ctx->last_launches = 0;
+  int64_t tot[4];
+  int rc = split_device(ctx, n, ref, ref_off, unc, unc_off, cor, cor_off, header_len, threshold, tot);
+  if (rc != ELECTOR_OK) return rc;
+  SplitBufs &b = *split_bufs(ctx);
+  cudaStream_t st = ctx->stream;
+  const int64_t nw = tot[0];
+  std::vector<int64_t> rf((size_t)n + 1);
+  CU(cudaMemcpyAsync(rf.data(), b.rf.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  // the windows go to the alignment where they are: letters and offsets of the three kinds (the alignment takes ref, cor, unc)
+  const int64_t rows_cap = (3 * (tot[1] + tot[2] + tot[3] + 3 * nw) + 31) & ~(int64_t)15;
+  CU(ctx->d_rows.reserve(rows_cap)); CU(ctx->d_rowoff.reserve(nw * 8)); CU(ctx->d_stride.reserve(nw * 4));
+  CU(ctx->d_nring.reserve(nw * 4)); CU(ctx->d_s1.reserve(nw * 4)); CU(ctx->d_s2.reserve(nw * 4)); CU(ctx->d_cells.reserve(nw * 8));
+  CU(ctx->d_tally_out.reserve(n * ELECTOR_TALLY_K * 8)); CU(ctx->d_sums.reserve(ELECTOR_TALLY_K * 8));
+  for (int attempt = 0;; ++attempt) {
+    rc = run_device(ctx, nw, b.w_let[0].as<char>(), b.w_off[0].as<int64_t>(), b.w_let[2].as<char>(), b.w_off[2].as<int64_t>(), b.w_let[1].as<char>(),
+                    b.w_off[1].as<int64_t>(), nullptr, nullptr, ctx->d_rows.as<char>(), rows_cap, ctx->d_rowoff.as<int64_t>(), ctx->d_stride.as<int32_t>(),
+                    ctx->d_nring.as<int32_t>(), ctx->d_s1.as<int32_t>(), ctx->d_s2.as<int32_t>(), ctx->d_cells.as<int64_t>(), ctx->d_ctrl.as<unsigned long long>(),
+                    ctx->d_ctrl.as<int32_t>() + 2);
+    if (rc != ELECTOR_OK) return rc;
+    CU(cudaMemcpyAsync(&ctx->h_totals[4], ctx->d_ctrl.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    rc = check_tables(ctx);
+    if (rc == 1 && attempt < 3) continue;
+    if (rc != ELECTOR_OK) return rc == 1 ? ctx->fail(ELECTOR_ECUDA, "scratch pools keep overflowing") : rc;
+    break;
+  }
+  add_kernel_ms(ctx);
+  if ((int32_t)(ctx->h_totals[5] & 0xffffffff)) return ctx->fail(ELECTOR_ECAPACITY, "row buffer too small (internal bound)");
+  // Donatello + tally: one read per triplet (the records of a triplet share its header, Master_Splitter.cpp:283-285)
+  CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
+  CU(cudaEventRecord(ctx->ev_mt0, st));
+  rc = merge_device(ctx, n, rf.data(), nw, ctx->d_rows.as<uint8_t>(), rows_cap, ctx->d_rowoff.as<int64_t>(), ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>());
+  if (rc == ELECTOR_OK)
+    rc = tally_device(ctx, n, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(), ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(),
+                      ctx->d_tally_out.as<int64_t>(), ctx->merged_cap);
+  if (rc != ELECTOR_OK) return rc;
+  tally_sum_kernel<<<std::min<int>(64, (int)((n + 7) / 8)), 256, 0, st>>>(n, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
+  CU(cudaGetLastError());
+  ++ctx->last_launches;
+  CU(cudaEventRecord(ctx->ev_mt1, st));
+  CU(cudaMemcpyAsync(counters_out, ctx->d_tally_out.p, (size_t)n * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
+  if (status) CU(cudaMemcpyAsync(status, b.status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> kidx;
+  if (k_used) { kidx.resize((size_t)n); CU(cudaMemcpyAsync(kidx.data(), b.kidx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st)); }
+  std::vector<int64_t> moff;
+  if (m_ref) {
+    moff.resize((size_t)n + 1);
+    CU(cudaMemcpyAsync(moff.data(), ctx->d_moff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(m_len, ctx->d_mlen.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  }
+  rc = check_scan_overflow(ctx, n);   // synchronises the stream
+  if (rc != ELECTOR_OK) return rc;
+  float ms = 0.f;
+  ctx->last_ms_split = ctx->last_ms_tally = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_split0, ctx->ev_split1) == cudaSuccess) { ctx->last_ms += ms; ctx->last_ms_split = ms; }
+  if (cudaEventElapsedTime(&ms, ctx->ev_mt0, ctx->ev_mt1) == cudaSuccess) { ctx->last_ms += ms; ctx->last_ms_tally = ms; }
+  if (m_ref) {
+    if (moff[(size_t)n] > m_cap) return ctx->fail(ELECTOR_ECAPACITY, "merged rows need %lld bytes per buffer, capacity %lld", (long long)moff[(size_t)n], (long long)m_cap);
+    memcpy(m_off, moff.data(), (size_t)n * 8);
+    CU(cudaMemcpyAsync(m_ref, ctx->d_mref.p, (size_t)moff[(size_t)n], cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(m_cor, ctx->d_mcor.p, (size_t)moff[(size_t)n], cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(m_unc, ctx->d_munc.p, (size_t)moff[(size_t)n], cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  if (k_used) for (int64_t t = 0; t < n; ++t) k_used[t] = 15 - 2 * kidx[(size_t)t];
+  if (read_first) memcpy(read_first, rf.data(), (size_t)(n + 1) * 8);
+  if (sums_out) memcpy(sums_out, ctx->h_sums, ELECTOR_TALLY_K * sizeof(int64_t));
+  if (n_windows) *n_windows = nw;
   return ELECTOR_OK;
 }
 

@@ -1,5 +1,5 @@
 // split_host.hpp -- host side of the window cutting: the reference's `masterSplitter` command line, its reading of the three
-// read files and its output files (Master_Splitter.cpp main(), :366-478), shared by the drop-in executable
+// read files and its output files (Master_Splitter.cpp main(), :352-472), shared by the drop-in executable
 // (csrc/splitter_main.cpp over the C-ABI) and the CPU emulation harness (tests/emul/split_emul.cu).
 #pragma once
 #include <algorithm>
@@ -70,7 +70,7 @@ struct SplitCli {
     k = atoi(argv[7]); nb_file = atoi(argv[8]); max_amount = (uint64_t)atoi(argv[9]); threshold = atof(argv[10]); out_dir = argv[11];
     return nb_file > 0;
   }
-  // Reads the triplets of one round like main() (:404-433): resumes at progress.txt, two lines per record, stops after the
+  // Reads the triplets of one round like main() (:396-446): resumes at progress.txt, two lines per record, stops after the
   // triplet whose index exceeds max_amount or at the end of a file; records whose reference has at most 2 letters are
   // dropped without being counted.  Returns 0 = all files read to the end ... 1 = more to come, -1 error.
   int read_round(SplitBatch &b) {
@@ -98,10 +98,12 @@ struct SplitCli {
     for (int q = 0; q < 3; ++q) { eof[q] = f[q].eof(); if (!eof[q]) pos[q] = (uint64_t)f[q].tellg(); }
     return (eof[0] || eof[1] || eof[2]) ? 0 : 1;
   }
-  // Writes the round's shard files, the two counters and progress.txt (:386-392,:447-477); returns the reference's exit code.
-  int write_round(const SplitBatch &b, const std::vector<SplitChoice> &choice, const std::vector<std::vector<SplitWin>> &wins, int more) const {
+  // Writes the round's shard files, the two counters and progress.txt (:389-393,:447-471); returns the reference's exit code.
+  // status[t]: SplitChoice::status; count(t) = records of a cut triplet; get(t, i, q, &ptr, &len) = letters of record i, kind q.
+  template <class Count, class Get>
+  int write_round(const SplitBatch &b, const int32_t *status, Count count, Get get, int more) const {
     const int64_t factor = (int64_t)(max_amount / (uint64_t)nb_file) + 1;
-    printf("%llu %d %lld\n", (unsigned long long)max_amount, nb_file, (long long)(factor - 1));   // (:381, before factor += 1)
+    printf("%llu %d %lld\n", (unsigned long long)max_amount, nb_file, (long long)(factor - 1));   // (:367, before factor += 1)
     std::vector<std::string> text[3];
     for (int q = 0; q < 3; ++q) text[q].resize((size_t)nb_file);
     int small_reads = 0, wrong_reads = 0;
@@ -109,20 +111,20 @@ struct SplitCli {
       const size_t shard = (size_t)((int64_t)t / factor);
       if (shard >= (size_t)nb_file) break;
       const std::string &h = b.header[t];
-      if (choice[t].status != 0) {
+      if (status[t] != 0) {
         for (int q = 0; q < 3; ++q) { text[q][shard] += h; text[q][shard] += "\nAAA\n"; }
-        if (choice[t].status == 1) ++small_reads; else ++wrong_reads;
+        if (status[t] == 1) ++small_reads; else ++wrong_reads;
         continue;
       }
-      for (const SplitWin &w : wins[t]) {
-        const int st[3] = {w.r0, w.a0, w.b0}, ln[3] = {w.rn, w.an, w.bn};
+      const int64_t nrec = count(t);
+      for (int64_t i = 0; i < nrec; ++i)
         for (int q = 0; q < 3; ++q) {
+          const char *p = nullptr; size_t len = 0;
+          get(t, i, q, &p, &len);
           text[q][shard] += h; text[q][shard] += '\n';
-          if (st[q] < 0) text[q][shard] += 'N';
-          else text[q][shard].append(reinterpret_cast<const char *>(b.seq(q, t)) + st[q], (size_t)ln[q]);
+          text[q][shard].append(p, len);
           text[q][shard] += '\n';
         }
-      }
     }
     for (int q = 0; q < 3; ++q)
       for (int i = 0; i < nb_file; ++i) {
@@ -131,7 +133,7 @@ struct SplitCli {
       }
     { std::ofstream o(out_dir + "/small_reads.txt"); o << small_reads << std::endl; }
     { std::ofstream o(out_dir + "/wrongly_cor_reads.txt"); o << wrong_reads << std::endl; }
-    // (:466-468 means to remove progress.txt at the end of the input, but hands remove() the buffer of a destroyed temporary:
+    // (:460-463 means to remove progress.txt at the end of the input, but hands remove() the buffer of a destroyed temporary:
     // with glibc the file stays, and so it does here)
     if (!more) return 0;
     std::ofstream o(out_dir + "/progress.txt");

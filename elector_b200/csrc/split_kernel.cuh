@@ -1,25 +1,25 @@
 // split_kernel.cuh -- ELECTOR's window cutting (src/split/Master_Splitter.cpp) on the device: SURVEY.md 8(f)-1.
 //
 // The reference cuts every (reference, uncorrected, corrected) read triplet into ~50-letter windows at k-mers that occur
-// exactly once in each of the three reads (split() :175-332), keeps the cutting with the smallest largest window over
-// k = 15, 13, 11, 9 (best_split() :334-361), and hands the windows to `poa`.  It is a serial 10.7 ms per triplet; with the
+// exactly once in each of the three reads (split() :175-308), keeps the cutting with the smallest largest window over
+// k = 15, 13, 11, 9 (best_split() :310-332), and hands the windows to `poa`.  It is a serial 10.7 ms per triplet; with the
 // alignment at 0.7 us per triplet it is 99.9 % of the stage.
 //
 // Mapping: ONE CTA PER (triplet, k) JOB -- the four k of a triplet run side by side, the choice between them is made
 // afterwards.  Per job:
 //   1. the k-mers of the reference go into an open-addressing hash table in global memory (L2-resident: 20 bytes per slot,
 //      2 slots per k-mer); occurrence flags "seen once" / "seen again" per read are set with atomicOr, so "exactly once in
-//      each read" is a flag pattern (:176-231 keep three std::unordered_maps with -1 for repeats);
+//      each read" is a flag pattern (:176-230 keep three std::unordered_maps with -1 for repeats);
 //   2. the k-mers of the other two reads look their slot up and set their flags and positions;
 //   3. every reference position asks the table whether its k-mer is such an anchor -> a bitmap in reference order;
-//   4. one thread thins the bitmap like the reference's left-to-right scan (:246-254, an anchor at most every minSize + 1
+//   4. one thread thins the bitmap like the reference's left-to-right scan (:242-251, an anchor at most every minSize + 1
 //      letters), the CTA fetches the anchors' positions in the other two reads;
 //   5. the longest chain of anchors that increase by less than 1000 letters in all three reads (:79-126, a memoised
 //      recursion) is a backward dynamic programme over the anchor list: a warp looks at the <= 48 successors of an anchor
 //      at once; ties go to the first, like the reference's strict comparisons;
-//   6. one thread walks the chain and cuts (:262-331), including the two special cases of a corrected read that starts late
+//   6. one thread walks the chain and cuts (:262-306), including the two special cases of a corrected read that starts late
 //      or ends early (the reference then splits reference and uncorrected read alone and pads the corrected side with `N`
-//      records, :268-279 and :305-312): the CTA runs steps 1-5 again on the sub-strings.
+//      records, :268-277 and :295-301): the CTA runs steps 1-5 again on the sub-strings.
 // The same code compiles for the host (tests/emul/split_emul.cu runs it serially against the compiled reference).
 #pragma once
 #include <stdint.h>
@@ -53,7 +53,7 @@ struct SplitScratch {
   int32_t *bl;                                  // the chain: indices into the anchor list
 };
 
-// letter codes of the reference's two encoders: str2num (:23-36) for the first k letters of a read, nuc2int (:39-47) for the rest
+// letter codes of the reference's two encoders: str2num (:26-38) for the first k letters of a read, nuc2int (:41-49) for the rest
 SP_HD inline uint32_t split_code(const SplitSeq &q, int t, int k) {
   const uint8_t c = q.s[t];
   if (t < k) return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : 3u;
@@ -129,7 +129,7 @@ SP_HD inline int split_chain(const SplitScratch &sc, const SplitSeq &ref, const 
     if (sc.flag[s] == (SF_R1 | SF_A1 | SF_B1)) sp_or(&sc.cand[p >> 5], 1u << (p & 31));
   }
   SP_SYNC();
-  // 4. left-to-right thinning (:240-254): position 0 is taken as it is; position j + 1 when j - last > minSize, last = j
+  // 4. left-to-right thinning (:242-251): position 0 is taken as it is; position j + 1 when j - last > minSize, last = j
   SP_SERIAL {
     int n = 0;
     uint32_t last = 0;
@@ -204,7 +204,7 @@ SP_HD inline int split_chain(const SplitScratch &sc, const SplitSeq &ref, const 
   return s_int[1];
 }
 
-// The cutting of one job (split(), :175-332) into out[0 ..); returns the number of records, or -1 when out_cap is too small.
+// The cutting of one job (split(), :175-308) into out[0 ..); returns the number of records, or -1 when out_cap is too small.
 // Positions in the records are relative to the three reads given here.  first_call as in the reference: the late-start /
 // early-end special cases only at the outer level.
 SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, SplitSeq ref, SplitSeq S1, SplitSeq S2, int k, SplitWin *out, int out_cap, int *s_int) {
@@ -224,7 +224,7 @@ SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, Spli
     const int lr = sr < ref.n ? sr : ref.n, la = sa < S1.n ? sa : S1.n, lb = sb < S2.n ? sb : S2.n;
     if ((long long)lb * 2 < lr && (unsigned)(lr - lb) > 200u) {
       // the corrected read starts late: reference and uncorrected prefix are cut on their own (S2 := the reference prefix),
-      // with a minimum window of 1.2 x the corrected prefix; the corrected side gets N records and its prefix last (:268-279)
+      // with a minimum window of 1.2 x the corrected prefix; the corrected side gets N records and its prefix last (:268-277)
       const SplitSeq pr{ref.s, lr}, pa{S1.s, la};
       const uint32_t ms = (uint32_t)(1.2 * (double)lb);
       const int bl2 = split_chain(sc2, pr, pa, pr, k, ms, s_int + 4);
@@ -243,7 +243,7 @@ SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, Spli
               qr = sc2.ar[x] + k; qa = sc2.aa[x] + k; qb = sc2.ab[x] + k;
             }
           }
-          if (nout + n2 < out_cap) out[nout + n2] = SplitWin{qr, pr.n - qr, qa, pa.n - qa, 0, 0};   // first_call is false there: the rest as it is (:313-317)
+          if (nout + n2 < out_cap) out[nout + n2] = SplitWin{qr, pr.n - qr, qa, pa.n - qa, 0, 0};   // first_call is false there: the rest as it is (:302-306)
           ++n2;
         }
         // corrected side: n2 - 1 times N, then the prefix (N when it is empty) -- generate_dumb_str(n2, header, start_S2, "")
@@ -253,11 +253,11 @@ SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, Spli
       }
       SP_SYNC();
       nout += s_int[2];
-      pred_r = sr; pred_a = sa; pred_b = sb;   // (:275-277: the anchor's end, unclamped)
+      pred_r = sr; pred_a = sa; pred_b = sb;   // (:273-275: the anchor's end, unclamped)
       i0 = 1;
     }
   }
-  // the walk (:282-296) and the tail (:298-317); the early-end case needs its own parallel steps, so the walk stops before it
+  // the walk (:280-290) and the tail (:292-306); the early-end case needs its own parallel steps, so the walk stops before it
   SP_SERIAL {
     int n = nout;
     for (int i = i0; i < blen - 1; ++i) {
@@ -278,7 +278,7 @@ SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, Spli
     // substr(pred) of a read that is shorter than pred cannot happen on the chain (positions + k <= length)
     const int er = ref.n - pred_r, ea = S1.n - pred_a, eb = S2.n - pred_b;
     if ((long long)eb * 2 < er && (unsigned)(er - eb) > 200u) {
-      // the corrected read ends early (:305-312): the corrected side gets its tail first, then N records
+      // the corrected read ends early (:295-301): the corrected side gets its tail first, then N records
       const SplitSeq pr{ref.s + pred_r, er}, pa{S1.s + pred_a, ea};
       const uint32_t ms = (uint32_t)(1.2 * (double)eb);
       const int bl2 = split_chain(sc2, pr, pa, pr, k, ms, s_int + 4);
@@ -383,8 +383,8 @@ __global__ void __launch_bounds__(256) split_jobs_kernel(SplitArgs a) {
   }
 }
 
-// best_split (:334-361): k = 15, then 13, 11, 9 as long as the largest fragment gets strictly smaller.  One thread per triplet:
-// the chosen k, the status (2: at most one record -> the AAA placeholder, :417-423), the records and letters of each kind it
+// best_split (:310-332): k = 15, then 13, 11, 9 as long as the largest fragment gets strictly smaller.  One thread per triplet:
+// the chosen k, the status (2: at most one record -> the AAA placeholder, :417-422), the records and letters of each kind it
 // contributes.
 __global__ void split_select_kernel(int64_t n, const int32_t *status_in, const int32_t *job_n, const uint32_t *job_largest, const SplitWin *wins,
                                     const int64_t *win_off, int32_t *status, int32_t *k_idx, int64_t *nrec, int64_t *nlet_r, int64_t *nlet_a, int64_t *nlet_b,

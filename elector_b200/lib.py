@@ -19,6 +19,10 @@ def poa_binary_path():
     return os.path.join(_HERE, "bin", "poa")
 
 
+def splitter_binary_path():
+    return os.path.join(_HERE, "bin", "masterSplitter")
+
+
 def load_library():
     """Returns the ctypes handle; raises LibraryNotBuilt (never falls back) if it is missing."""
     global _LIB
@@ -61,6 +65,14 @@ def load_library():
     lib.elector_pack_letters.restype = c.c_int64
     lib.elector_merged_bound.argtypes = [c.c_int64, c.c_int64, vp, vp, vp]
     lib.elector_merged_bound.restype = c.c_int64
+    lib.elector_split_bounds.argtypes = [c.c_int64, vp, vp, vp, vp, vp, vp, vp]
+    lib.elector_split_bounds.restype = c.c_int
+    lib.elector_split_run.argtypes = [vp, c.c_int64] + [vp] * 7 + [c.c_double, vp, vp, vp, c.c_int64, vp, vp, vp, vp, c.c_int64, vp, c.c_int64, vp, c.c_int64, vp]
+    lib.elector_split_run.restype = c.c_int
+    lib.elector_reads_run.argtypes = [vp, c.c_int64] + [vp] * 7 + [c.c_double] + [vp] * 9 + [c.c_int64, vp, vp]
+    lib.elector_reads_run.restype = c.c_int
+    lib.elector_last_reads_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_float), c.POINTER(c.c_float)]
+    lib.elector_last_reads_ms.restype = c.c_int
     lib.elector_tally_sum_device.argtypes = [vp, c.c_int64, vp, vp]
     lib.elector_tally_sum_device.restype = c.c_int
     lib.elector_last_phase_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_float)]

@@ -236,6 +236,60 @@ class PoaContext:
             rows = [tuple(full[s][m_off[r]:m_off[r] + m_len[r]].tobytes().decode("latin-1") for s in range(3)) for r in range(n_reads)]
         return dict(res=res, merged=rows, counters=counters, sums=sums, m_len=m_len, n_esc=int(n_esc[0]))
 
+    def split_csr(self, ref, ref_off, unc, unc_off, cor, cor_off, header_len, threshold=0.1):
+        """One masterSplitter round on in-memory reads (elector_split_run; Master_Splitter.cpp:352-472 minus the files): the
+        windows of every triplet as CSR letter arrays, in triplet order.  -> dict(status, k_used, read_first, ref, ref_off,
+        unc, unc_off, cor, cor_off)"""
+        n = len(ref_off) - 1
+        ref_off, unc_off, cor_off = (np.ascontiguousarray(o, dtype=np.int64) for o in (ref_off, unc_off, cor_off))
+        ref, unc, cor = (np.ascontiguousarray(s, dtype=np.uint8) for s in (ref, unc, cor))
+        header_len = np.ascontiguousarray(header_len, dtype=np.int32)
+        caps = [ctypes.c_int64() for _ in range(4)]
+        self._check(self._lib.elector_split_bounds(n, _p(ref_off), _p(unc_off), _p(cor_off), *[ctypes.cast(ctypes.byref(c), ctypes.c_void_p) for c in caps]))
+        wcap, rcap, ucap, ccap = (int(c.value) for c in caps)
+        status, k_used = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        read_first = np.zeros(n + 1, np.int64)
+        wo = [np.zeros(wcap + 1, np.int64) for _ in range(3)]
+        wl = [np.empty(max(cap, 1), np.uint8) for cap in (rcap, ucap, ccap)]
+        nw = ctypes.c_int64()
+        self._check(self._lib.elector_split_run(self._ctx, n, _p(ref), _p(ref_off), _p(unc), _p(unc_off), _p(cor), _p(cor_off), _p(header_len),
+                                                float(threshold), _p(status), _p(k_used), _p(read_first), wcap, _p(wo[0]), _p(wo[1]), _p(wo[2]),
+                                                _p(wl[0]), rcap, _p(wl[1]), ucap, _p(wl[2]), ccap, ctypes.cast(ctypes.byref(nw), ctypes.c_void_p)))
+        nw = int(nw.value)
+        out = dict(status=status, k_used=k_used, read_first=read_first, n_windows=nw)
+        for name, o, l in zip(("ref", "unc", "cor"), wo, wl):
+            out[name + "_off"] = o[:nw + 1]
+            out[name] = l[:int(o[nw])] if nw else l[:0]
+        return out
+
+    def reads_run(self, ref, ref_off, unc, unc_off, cor, cor_off, header_len, threshold=0.1, merged=False):
+        """alignment.py:98-129 from the reads on (elector_reads_run): window cutting, alignment, per-triplet merge and tally in one
+        call; the windows stay on the device.  -> dict(status, k_used, read_first, n_windows, counters, sums[, merged rows])"""
+        n = len(ref_off) - 1
+        ref_off, unc_off, cor_off = (np.ascontiguousarray(o, dtype=np.int64) for o in (ref_off, unc_off, cor_off))
+        ref, unc, cor = (np.ascontiguousarray(s, dtype=np.uint8) for s in (ref, unc, cor))
+        header_len = np.ascontiguousarray(header_len, dtype=np.int32)
+        status, k_used = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        read_first = np.zeros(n + 1, np.int64)
+        counters = np.zeros((n, len(TALLY_FIELDS)), dtype=np.int64)
+        sums = np.zeros(len(TALLY_FIELDS), dtype=np.int64)
+        nw = ctypes.c_int64()
+        m_cap = int(ref_off[n] - ref_off[0] + unc_off[n] - unc_off[0] + cor_off[n] - cor_off[0]) + 32 * n + 64 if merged else 0
+        m = [np.empty(max(m_cap, 1), np.uint8) for _ in range(3)] if merged else [None] * 3
+        m_off, m_len = (np.zeros(n, np.int64), np.zeros(n, np.int32)) if merged else (None, None)
+        self._check(self._lib.elector_reads_run(self._ctx, n, _p(ref), _p(ref_off), _p(unc), _p(unc_off), _p(cor), _p(cor_off), _p(header_len),
+                                                float(threshold), _p(status), _p(k_used), _p(read_first), ctypes.cast(ctypes.byref(nw), ctypes.c_void_p),
+                                                _p(counters), _p(sums), _p(m[0]), _p(m[1]), _p(m[2]), m_cap, _p(m_off), _p(m_len)))
+        out = dict(status=status, k_used=k_used, read_first=read_first, n_windows=int(nw.value), counters=counters, sums=sums)
+        if merged:
+            out.update(m_ref=m[0], m_cor=m[1], m_unc=m[2], m_off=m_off, m_len=m_len)
+        return out
+
+    def last_reads_ms(self):
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        self._lib.elector_last_reads_ms(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return a.value, b.value, c.value
+
     def files(self, ref_fasta, cor_fasta, unc_fasta, pir_out, print_perm=False):
         """The body of one `poa` process (main.c:241-287)."""
         self._check(self._lib.elector_poa_files(self._ctx, ref_fasta.encode(), cor_fasta.encode(), unc_fasta.encode(),

@@ -209,13 +209,13 @@ int64_t elector_merged_bound(int64_t n_windows, int64_t n_reads, const int64_t *
 int elector_pipeline_run2(elector_ctx *ctx, const elector_pipeline_io *io);
 
 /* ---- window cutting -----------------------------------------------------------------------------------
- * Replaces: the body of one `masterSplitter` round (src/split/Master_Splitter.cpp:366-478 minus the file I/O) -- best_split
- * (:334-361: split() at k = 15, 13, 11, 9) for each of n triplets, given as three letter arrays with n + 1 offsets each
+ * Replaces: the body of one `masterSplitter` round (src/split/Master_Splitter.cpp:352-472 minus the file I/O) -- best_split
+ * (:310-332: split() at k = 15, 13, 11, 9) for each of n triplets, given as three letter arrays with n + 1 offsets each
  * (reference, uncorrected, corrected: the splitter's argv[1..3]) and the length of each triplet's header line (it takes part
  * in largest_fragment(), :158-169).  threshold = argv[10] (SIZE_CORRECTED_READ_THRESHOLD).  Triplets whose reference read has
  * at most 2 letters are the caller's to drop (:414).
  * Outputs: status[t] (0 cut, 1 corrected read too short = small_reads, 2 not cut = wrongly_cor_reads; 1 and 2 give the
- * placeholder record AAA / AAA / AAA, :417-432), k_used[t], and the windows of all triplets in triplet order as three letter
+ * placeholder record AAA / AAA / AAA, :417-431), k_used[t], and the windows of all triplets in triplet order as three letter
  * arrays with offsets -- the records the reference writes to out1<i> / out2<i> / out3<i>, ready for elector_pipeline_run*
  * (read_first[t] = first window of triplet t).  elector_split_bounds gives capacities that always suffice. */
 int elector_split_bounds(int64_t n_triplets, const int64_t *ref_off, const int64_t *unc_off, const int64_t *cor_off,
@@ -225,6 +225,20 @@ int elector_split_run(elector_ctx *ctx, int64_t n_triplets, const char *ref, con
                       int32_t *status, int32_t *k_used, int64_t *read_first, int64_t win_cap, int64_t *w_ref_off,
                       int64_t *w_unc_off, int64_t *w_cor_off, char *w_ref, int64_t w_ref_cap, char *w_unc, int64_t w_unc_cap,
                       char *w_cor, int64_t w_cor_cap, int64_t *n_windows);
+
+/* Replaces: one round of elector/alignment.py:98-129 from the READS on -- masterSplitter (Master_Splitter.cpp:352-472), Pool(fpoa)
+ * (main.c:265-284 per window), Donatello (Donatello.cpp:50-84) and the integer part of computeStats.py -- as one call in which the
+ * windows never leave the device: cut by elector_split_run's kernels, aligned where they are, merged per triplet (the records of a
+ * triplet share its header, :283-285, so a triplet is one Donatello read) and tallied.  Inputs as elector_split_run.  Outputs:
+ * status / k_used / read_first (n_triplets + 1) / n_windows as elector_split_run (each may be NULL), counters_out[t*ELECTOR_TALLY_K+k],
+ * sums_out[k] (may be NULL), and optionally the merged rows of every triplet (what Donatello appends to msa.fa): m_len[t] columns at
+ * m_off[t] of m_ref / m_cor / m_unc (m_cap bytes each; letters of the call + 32 per triplet suffices). */
+int elector_reads_run(elector_ctx *ctx, int64_t n_triplets, const char *ref, const int64_t *ref_off, const char *unc,
+                      const int64_t *unc_off, const char *cor, const int64_t *cor_off, const int32_t *header_len, double threshold,
+                      int32_t *status, int32_t *k_used, int64_t *read_first, int64_t *n_windows, int64_t *counters_out,
+                      int64_t *sums_out, char *m_ref, char *m_cor, char *m_unc, int64_t m_cap, int64_t *m_off, int32_t *m_len);
+/* Device time of the last elector_reads_run: window cutting, alignment, merge + tally (CUDA events, ms). */
+int elector_last_reads_ms(const elector_ctx *ctx, float *ms_split, float *ms_poa, float *ms_merge_tally);
 
 /* Global counters on the device: d_sums[k] += sum over reads of d_counters[r*ELECTOR_TALLY_K+k]
  * (ELECTOR_T_EXTENDED: extended reads only).  d_sums is ELECTOR_TALLY_K int64 the caller zeroes;

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY -- runs the window cutting of elector_b200/csrc/split_kernel.cuh serially on the CPU (the code is
-// host/device dual) with the reference's own driver logic around it (Master_Splitter.cpp main(), :366-478: one round of at
+// host/device dual) with the reference's own driver logic around it (Master_Splitter.cpp main(), :352-472: one round of at
 // most 10 001 triplets, shard files by triplet index, the two counters), so that its output files can be compared byte for
 // byte with those of the compiled reference (oracle/_ref/masterSplitter) in the GPU-less container.
 // usage: split_emul REF.fa UNC.fa COR.fa OUT1 OUT2 OUT3 k nb_file max_amount threshold OUTDIR      (the reference's arguments)
@@ -47,5 +47,13 @@ int main(int argc, char **argv) {
     if (best.size() <= 1) choice[t].status = 2;
     else wins[t] = best;
   }
-  return cli.write_round(batch, choice, wins, rc_read);
+  std::vector<int32_t> status(batch.n());
+  for (size_t t = 0; t < batch.n(); ++t) status[t] = choice[t].status;
+  return cli.write_round(batch, status.data(), [&](size_t t) { return (int64_t)wins[t].size(); },
+                         [&](size_t t, int64_t i, int q, const char **p, size_t *len) {
+                           const SplitWin &w = wins[t][(size_t)i];
+                           const int st[3] = {w.r0, w.a0, w.b0}, ln[3] = {w.rn, w.an, w.bn};
+                           if (st[q] < 0) { *p = "N"; *len = 1; }
+                           else { *p = reinterpret_cast<const char *>(batch.seq(q, t)) + st[q]; *len = (size_t)ln[q]; }
+                         }, rc_read);
 }
