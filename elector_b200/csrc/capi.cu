@@ -572,6 +572,7 @@ void add_kernel_ms(elector_ctx *ctx) {
   }
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms += ms;
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) ctx->last_ms_phase1 += ms;
+  (void)cudaGetLastError();   // an event of a view that did not run this call has no time: not an error of the call
 }
 
 
@@ -821,6 +822,7 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
     cudaEventElapsedTime(&t[4], pa.ev_call, ctx->ev1); cudaEventElapsedTime(&t[5], pa.ev_call, ctx->uev1);
     fprintf(stderr, "[elector trace] chunk w%lld: h2d %.2f | sort1 %.2f | phase 1 done %.2f | phase 2 done %.2f | merge+tally done %.2f | results on host %.2f\n",
             (long long)w0, t[0], t[1], t[2], t[3], t[4], t[5]);
+    (void)cudaGetLastError();
   }
   add_kernel_ms(ctx);
   if (nr > 0) {

@@ -16,16 +16,18 @@ cmd() { echo "elector_b200/bin/poa -pir /tmp/prof$1.pir -corrected_reads_fasta /
 $(cmd 2000) > /dev/null; echo plain rc=$?
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/${TAG}_launches.csv $(cmd 10000) > /dev/null; echo launches rc=$?
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:poa_dp -c 14 -o $O/${TAG}_full -f $(cmd 2000) > /dev/null; echo full rc=$?
-timeout 900 ncu --set full --clock-control none -k regex:poa_dp2 -c 9 -o $O/${TAG}_dp2_10k -f $(cmd 10000) > /dev/null; echo dp2-10k rc=$?
+# the whole pipelined call (POA + merge + tally) in one chunk on one worker, through the C driver of elector_pipeline_run
+python tools/dump_csr.py 10000 1 /tmp/c1 > /dev/null
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
+# --set full of the phase-2 launch set of the SECOND call (the first one grows the scratch pools and runs segments twice)
+set -- $(python tools/ncu_skip.py $O/${TAG}_launches_pipeline.csv poa_dp2); echo "phase-2 launches: skip $1, capture $2"
+timeout 1200 ncu --set full --clock-control none -k regex:poa_dp2 --launch-skip $1 -c $2 -o $O/${TAG}_dp2_10k -f elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo dp2-10k rc=$?
 python tools/ncu_traffic.py $O/${TAG}_dp2_10k.ncu-rep $O/${TAG}_traffic.json
 # summaries are made here; the reports themselves (30 MB each) stay on the box unless KEEP_REPS=1 (gpurun_out/ is capped at 64 MiB)
 python tools/ncu_summary.py $O/${TAG}_full.ncu-rep > $O/${TAG}_ncu_full_summary_2k_reads.csv
 python tools/ncu_summary.py $O/${TAG}_dp2_10k.ncu-rep > $O/${TAG}_ncu_full_summary_dp2_10k_reads.csv
 python tools/ncu_stalls.py $O/${TAG}_dp2_10k.ncu-rep > $O/${TAG}_ncu_stalls_dp2_10k_reads.txt
 [ "$KEEP_REPS" = 1 ] || rm -f $O/${TAG}_full.ncu-rep $O/${TAG}_dp2_10k.ncu-rep
-# the whole pipelined call (POA + merge + tally) in one chunk on one worker, through the C driver of elector_pipeline_run
-python tools/dump_csr.py 10000 1 /tmp/c1 > /dev/null
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
 unset ELECTOR_PIPELINE_CHUNKS ELECTOR_PIPELINE_WORKERS   # the default pipeline (chunks on worker contexts) for the host-clock numbers
 elector_b200/bin/pipe_driver /tmp/c1 8 > $O/${TAG}_pipe_driver.txt 2>&1
 ELECTOR_TRACE=2 elector_b200/bin/pipe_driver /tmp/c1 3 2>&1 | tail -60 > $O/${TAG}_pipe_trace.txt
