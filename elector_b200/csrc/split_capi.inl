@@ -1,7 +1,7 @@
 // split_capi.inl -- C-ABI entry points of the window cutting (included by capi.cu)
 namespace {
 struct SplitBufs {
-  DevBuf let[3], off[3], hl, st_in, pool, wins, win_off, job_n, job_l, status, kidx, nrec, nl[3], base[4], w_off[3], w_let[3], rf, misc;
+  DevBuf let[3], off[3], order, hl, st_in, pool, wins, win_off, job_n, job_l, status, kidx, nrec, nl[3], base[4], w_off[3], w_let[3], rf, misc;
 };
 SplitBufs *split_bufs(elector_ctx *ctx) {
   if (!ctx->split_state) ctx->split_state = new SplitBufs();
@@ -26,7 +26,7 @@ int elector_split_bounds(int64_t n, const int64_t *ref_off, const int64_t *unc_o
 void elector_split_release(elector_ctx *ctx) {
   if (!ctx || !ctx->split_state) return;
   SplitBufs *b = static_cast<SplitBufs *>(ctx->split_state);
-  for (DevBuf *d : {&b->let[0], &b->let[1], &b->let[2], &b->off[0], &b->off[1], &b->off[2], &b->hl, &b->st_in, &b->pool, &b->wins, &b->win_off, &b->job_n, &b->job_l,
+  for (DevBuf *d : {&b->let[0], &b->let[1], &b->let[2], &b->off[0], &b->off[1], &b->off[2], &b->order, &b->hl, &b->st_in, &b->pool, &b->wins, &b->win_off, &b->job_n, &b->job_l,
                     &b->status, &b->kidx, &b->nrec, &b->nl[0], &b->nl[1], &b->nl[2], &b->base[0], &b->base[1], &b->base[2], &b->base[3], &b->w_off[0], &b->w_off[1],
                     &b->w_off[2], &b->w_let[0], &b->w_let[1], &b->w_let[2], &b->rf, &b->misc})
     d->release();
@@ -48,30 +48,51 @@ int split_device(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *re
   const int64_t *h_off[3] = {ref_off, unc_off, cor_off};
   // the host decides what main() decides before best_split (:414-415,:425-431): a corrected read shorter than the threshold share
   // of its reference is not cut; the longest reference read sizes the tables
-  std::vector<int32_t> st_in((size_t)n);
+  std::vector<int32_t> st_in((size_t)n), order((size_t)n);
   std::vector<int64_t> win_off((size_t)n + 1);
-  int64_t longest = 0;
+  // shared-memory shapes of the cutting kernel: two CTAs of 512 threads per SM with 112 KB each, or one of 1024 threads with 227 KB
+  const uint32_t smem_a = 112u * 1024u / 4u, smem_b = (227u * 1024u - 256u) / 4u;
+  int64_t longest = 0, fit_a = 0;
+  uint64_t need_pool = 0;
   win_off[0] = 0;
+  auto need_words = [](int64_t lr, int64_t la, int64_t lb, int32_t sub, uint64_t slots) {
+    const int32_t ma = split_anchor_bound((int)lr, 20);
+    return split_fixed_words((int)lr, (int)la, (int)std::max(lb, lr), ma, sub ? sub : ma) + slots;
+  };
   for (int64_t t = 0; t < n; ++t) {
-    const int64_t lr = ref_off[t + 1] - ref_off[t], lb = cor_off[t + 1] - cor_off[t];
+    const int64_t lr = ref_off[t + 1] - ref_off[t], la = unc_off[t + 1] - unc_off[t], lb = cor_off[t + 1] - cor_off[t];
     if (lr <= 0) return ctx->fail(ELECTOR_EINVAL, "triplet %lld has an empty reference read", (long long)t);
-    if (lr > 0x3fffffff) return ctx->fail(ELECTOR_ETOOLARGE, "triplet %lld: read too long", (long long)t);
+    if (lr > kSplitMaxRead || la > kSplitMaxRead || lb > kSplitMaxRead) return ctx->fail(ELECTOR_ETOOLARGE, "triplet %lld: read too long", (long long)t);
     st_in[(size_t)t] = ((double)lb / (double)lr >= threshold) ? 0 : 1;
-    longest = std::max(longest, lr);
+    longest = std::max<int64_t>(longest, std::max<int64_t>(lr, std::max<int64_t>(la, lb)));
+    if (need_words(lr, la, lb, 0, split_min_slots((int)lr)) <= smem_a) ++fit_a;
     win_off[(size_t)t + 1] = win_off[(size_t)t] + 4 * (lr / 16 + 16);
   }
-  uint32_t max_slots = 64;
-  while (max_slots < 2 * (uint64_t)longest + 2) max_slots <<= 1;
-  const int32_t max_anchors = (int32_t)(longest / 8 + 16);
-  const uint32_t cand_words = (uint32_t)(longest / 32 + 2);
-  const uint64_t cta_words = 2 * ((split_scratch_words(max_slots, cand_words, max_anchors) + 31) & ~31ull);
-  int grid = (int)std::min<int64_t>(4 * n, (int64_t)ctx->sm_count * 4);
-  while (grid > 1 && cta_words * 4 * (uint64_t)grid > ((uint64_t)16 << 30)) grid = (grid + 1) / 2;
+  const bool shape_a = fit_a * 10 >= n * 9;
+  const uint32_t smem_words = shape_a ? smem_a : smem_b;
+  const int32_t sub_anchors = (int32_t)((longest / 8 + 16 + 3) & ~(int64_t)3);
+  for (int64_t t = 0; t < n; ++t) {   // the pool holds any job of the call with two table slots per k-mer: what does not fit the shared memory runs there
+    const int64_t lr = ref_off[t + 1] - ref_off[t], la = unc_off[t + 1] - unc_off[t], lb = cor_off[t + 1] - cor_off[t];
+    if (!st_in[(size_t)t]) need_pool = std::max<uint64_t>(need_pool, need_words(lr, la, lb, sub_anchors, 2ull * (uint64_t)lr + 64));
+  }
+  {   // the longest reads first: a counting sort by length / 256
+    const size_t nb = (size_t)(longest / 256 + 2);
+    std::vector<int64_t> start(nb + 1, 0);
+    for (int64_t t = 0; t < n; ++t) ++start[nb - 1 - (size_t)((ref_off[t + 1] - ref_off[t]) / 256)];
+    int64_t acc = 0;
+    for (size_t i = 0; i <= nb; ++i) { const int64_t c = start[i]; start[i] = acc; acc += c; }
+    for (int64_t t = 0; t < n; ++t) order[(size_t)start[nb - 1 - (size_t)((ref_off[t + 1] - ref_off[t]) / 256)]++] = (int32_t)t;
+  }
+  const uint64_t cta_words = (need_pool + 31) & ~31ull;
+  const int threads = shape_a ? 512 : 1024;
+  int grid = (int)std::min<int64_t>(4 * n, (int64_t)ctx->sm_count * (shape_a ? 2 : 1));
   for (int k = 0; k < 3; ++k) {
     CU(b.let[k].reserve((size_t)(h_off[k][n] - h_off[k][0]) + 16)); CU(b.off[k].reserve((size_t)(n + 1) * 8));
     CU(cudaMemcpyAsync(b.let[k].p, h_let[k] + h_off[k][0], (size_t)(h_off[k][n] - h_off[k][0]), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b.off[k].p, h_off[k], (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
   }
+  CU(b.order.reserve((size_t)n * 4));
+  CU(cudaMemcpyAsync(b.order.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CU(b.hl.reserve((size_t)n * 4)); CU(b.st_in.reserve((size_t)n * 4)); CU(b.win_off.reserve((size_t)(n + 1) * 8));
   CU(b.pool.reserve((size_t)cta_words * 4 * (size_t)grid));
   CU(b.wins.reserve((size_t)win_off[(size_t)n] * sizeof(SplitWin)));
@@ -88,12 +109,14 @@ int split_device(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *re
   a.n_triplets = n;
   for (int k = 0; k < 3; ++k) { a.let[k] = b.let[k].as<uint8_t>() - h_off[k][0]; a.off[k] = b.off[k].as<int64_t>(); }
   a.header_len = b.hl.as<int32_t>(); a.status_in = b.st_in.as<int32_t>();
-  a.pool = b.pool.as<uint32_t>(); a.cta_words = cta_words; a.max_slots = max_slots; a.max_anchors = max_anchors; a.cand_words = cand_words;
+  a.order = b.order.as<int32_t>();
+  a.pool = b.pool.as<uint32_t>(); a.cta_words = cta_words; a.sub_anchors = sub_anchors; a.smem_words = smem_words;
   a.wins = b.wins.as<SplitWin>(); a.win_off = b.win_off.as<int64_t>();
   a.job_n = b.job_n.as<int32_t>(); a.job_largest = b.job_l.as<uint32_t>();
   a.counter = b.misc.as<int32_t>();
   CU(cudaEventRecord(ctx->ev_split0, st));
-  split_jobs_kernel<<<grid, 256, 0, st>>>(a);
+  CU(cudaFuncSetAttribute(split_jobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_b * 4)));
+  split_jobs_kernel<<<grid, threads, (size_t)smem_words * 4, st>>>(a);
   split_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, a.status_in, a.job_n, a.job_largest, a.wins, a.win_off, b.status.as<int32_t>(), b.kidx.as<int32_t>(),
                                                                   b.nrec.as<int64_t>(), b.nl[0].as<int64_t>(), b.nl[1].as<int64_t>(), b.nl[2].as<int64_t>(), b.misc.as<int32_t>() + 1);
   scan_offsets_kernel<<<1, 1024, 0, st>>>(n, b.nrec.as<int64_t>(), b.base[0].as<int64_t>());

@@ -40,18 +40,25 @@ struct SplitBatch {
   }
 };
 
-struct HostScratch {   // scratch of one job for the host build of the kernels' code
-  std::vector<uint32_t> key, flag, posr, posa, posb, cand;
-  std::vector<int32_t> ar, aa, ab, chain, nxt, bl;
-  SplitScratch sc;
-  explicit HostScratch(size_t longest) {
-    uint32_t slots = 64;
-    while (slots < 2 * longest + 2) slots <<= 1;
-    key.resize(slots); flag.resize(slots); posr.resize(slots); posa.resize(slots); posb.resize(slots);
-    cand.resize(longest / 32 + 2);
-    const size_t ma = longest / 8 + 16;
-    ar.resize(ma); aa.resize(ma); ab.resize(ma); chain.resize(ma); nxt.resize(ma); bl.resize(ma);
-    sc = SplitScratch{key.data(), flag.data(), posr.data(), posa.data(), posb.data(), slots, cand.data(), ar.data(), aa.data(), ab.data(), chain.data(), nxt.data(), (int32_t)ma, bl.data()};
+struct HostScratch {   // scratch of one job for the host build of the kernels' code, laid out like the kernel lays it out
+  std::vector<uint32_t> mem;
+  SplitScratch sc, sc2;
+  bool tight;
+  // longest: the longest read of any kind; tight: the smallest table the kernel accepts (the fullest it ever runs)
+  explicit HostScratch(size_t longest, bool tight_ = false) : tight(tight_) {
+    const int n = (int)longest;
+    mem.resize((size_t)(split_fixed_words(n, n, n, split_anchor_bound(n, 20), sub_anchors(n)) + 2ull * longest + 64) + 4);
+    fit(n, n, n);
+  }
+  static int32_t sub_anchors(int longest) { return (int32_t)((longest / 8 + 16 + 3) & ~3); }
+  // the arrays of one job, like split_jobs_kernel places them in its pool
+  void fit(int nr, int na, int nb) {
+    const int32_t ma = split_anchor_bound(nr, 20), sa = sub_anchors(nr > na ? nr : na);
+    uint32_t *base = mem.data();
+    while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+    uint64_t words = mem.size() - 4;
+    if (tight) words = split_fixed_words(nr, na, nb, ma, sa) + split_min_slots(nr);
+    if (!split_carve(sc, sc2, base, words, nr, na, nb, ma, sa)) abort();
   }
 };
 

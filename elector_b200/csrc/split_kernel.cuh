@@ -6,36 +6,41 @@
 // alignment at 0.7 us per triplet it is 99.9 % of the stage.
 //
 // Mapping: ONE CTA PER (triplet, k) JOB -- the four k of a triplet run side by side, the choice between them is made
-// afterwards.  Per job:
-//   1. the k-mers of the reference go into an open-addressing hash table in global memory (L2-resident: 20 bytes per slot,
-//      2 slots per k-mer); occurrence flags "seen once" / "seen again" per read are set with atomicOr, so "exactly once in
-//      each read" is a flag pattern (:176-230 keep three std::unordered_maps with -1 for repeats);
-//   2. the k-mers of the other two reads look their slot up and set their flags and positions;
-//   3. every reference position asks the table whether its k-mer is such an anchor -> a bitmap in reference order;
+// afterwards.  A job lives in the CTA's shared memory (reads of up to ~14 000 letters with two CTAs per SM, ~28 000 with one;
+// longer ones take the same code through a pool in global memory).  Per job:
+//   0. the three reads are packed to 2 bits per letter (a k-mer is then two word loads and a funnel shift);
+//   1. the k-mers of the reference go into an open-addressing hash table of 4-byte entries: the position of the k-mer's first
+//      occurrence in the reference (the key is read back from the packed read) and six flags "seen once" / "seen again" per
+//      read, set with atomicOr -- "exactly once in each read" is a flag pattern (:176-230 keep three std::unordered_maps
+//      with -1 for repeats);
+//   2. the k-mers of the other two reads look their entry up and set their flags;
+//   3. a sweep over the table sets the bit of every such k-mer's reference position -> the candidates in reference order;
 //   4. one thread thins the bitmap like the reference's left-to-right scan (:242-251, an anchor at most every minSize + 1
-//      letters), the CTA fetches the anchors' positions in the other two reads;
+//      letters) by jumping from anchor to the next set bit; the chosen anchors' entries are marked and a second pass over the
+//      other two reads picks their positions up (no position arrays beside the table);
 //   5. the longest chain of anchors that increase by less than 1000 letters in all three reads (:79-126, a memoised
 //      recursion) is a backward dynamic programme over the anchor list: a warp looks at the <= 48 successors of an anchor
-//      at once; ties go to the first, like the reference's strict comparisons;
+//      at once (one redux.sync for "first maximum", like the reference's strict comparisons);
 //   6. one thread walks the chain and cuts (:262-306), including the two special cases of a corrected read that starts late
 //      or ends early (the reference then splits reference and uncorrected read alone and pads the corrected side with `N`
-//      records, :268-277 and :295-301): the CTA runs steps 1-5 again on the sub-strings.
+//      records, :268-277 and :295-301): the CTA runs steps 0-5 again on the sub-strings.
 // The same code compiles for the host (tests/emul/split_emul.cu runs it serially against the compiled reference).
 #pragma once
 #include <stdint.h>
 
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
-#define SP_HD __host__ __device__
+#define SP_HD __host__ __device__ __forceinline__   // inlined into the kernel: the compiler then sees which arrays are shared memory
 #else
-#define SP_HD
+#define SP_HD inline
 #endif
 
 namespace elector {
 
 constexpr uint32_t kSplitEmpty = 0xffffffffu;
-enum : uint32_t { SF_R1 = 1, SF_R2 = 2, SF_A1 = 4, SF_A2 = 8, SF_B1 = 16, SF_B2 = 32 };   // seen once / again in ref, S1, S2
-constexpr int kChainReach = 1000;   // Master_Splitter.cpp:86-88
+enum : uint32_t { SF_R1 = 1, SF_R2 = 2, SF_A1 = 4, SF_A2 = 8, SF_B1 = 16, SF_B2 = 32, SF_MASK = 63, SF_ONCE = SF_R1 | SF_A1 | SF_B1 };   // seen once / again in ref, S1, S2
+constexpr int kChainReach = 1000;              // Master_Splitter.cpp:86-88
+constexpr int kSplitMaxRead = (1 << 25) - 2;   // a table entry is fingerprint | reference position | 6 flags
 
 struct SplitSeq { const uint8_t *s; int n; };
 
@@ -43,184 +48,400 @@ struct SplitSeq { const uint8_t *s; int n; };
 // placeholder "N" (generate_dumb_str, :139-154)
 struct SplitWin { int32_t r0, rn, a0, an, b0, bn; };
 
-// scratch of one job (global memory; sized for the longest read of the call)
+// an anchor: positions of the k-mer in the three reads, and the length of the best chain that starts at it
+struct alignas(16) SplitAnchor { int32_t r, a, b, chain; };
+
+// scratch of one job: shared memory when the job fits the CTA's share (every array then), the CTA's pool in global memory when
+// it does not (reads of more than ~13 000 / ~27 000 letters)
 struct SplitScratch {
-  uint32_t *key, *flag, *posr, *posa, *posb;   // hash table, `slots` entries each
-  uint32_t slots;                               // power of two
-  uint32_t *cand;                               // bitmap over reference positions
-  int32_t *ar, *aa, *ab, *chain, *nxt;          // anchors (positions in the three reads), chain length from here, successor
+  uint32_t *table;      // open addressing, `slots` entries: kSplitEmpty or fingerprint | position of the k-mer's first occurrence in ref | flags;
+  uint32_t slots;       // a probe compares the fingerprint and only then the k-mer itself, read from the packed reference
+  uint32_t pos_bits;    // width of the position field above the 6 flag bits
+  uint32_t *pk[3];      // the three reads at 2 bits per letter, 16 letters per word (+ 2 words that a k-mer at the end may touch)
+  uint32_t *cand;       // bitmap over reference positions
+  SplitAnchor *anc;     // anchors in reference order
+  int32_t *nxt;         // successor on the best chain
+  int32_t *bl;          // the chain: indices into the anchor list
   int32_t max_anchors;
-  int32_t *bl;                                  // the chain: indices into the anchor list
+  uint32_t *t2_km;      // a second, small table of the chosen anchors' k-mers (t2_slots entries) ...
+  int32_t *t2_idx;      // ... and their indices: the other two reads are looked up in it for the anchors' positions
+  uint32_t t2_slots;
 };
 
-// letter codes of the reference's two encoders: str2num (:26-38) for the first k letters of a read, nuc2int (:41-49) for the rest
-SP_HD inline uint32_t split_code(const SplitSeq &q, int t, int k) {
+// words of scratch that a job needs beside its table
+SP_HD uint32_t split_pk_words(int n) { return (uint32_t)(n >> 4) + 2u; }
+SP_HD uint32_t split_cand_words(int n) { return (uint32_t)(n >> 5) + 2u; }
+SP_HD int32_t split_anchor_bound(int n, uint32_t min_size) { return (int32_t)((((uint32_t)n / (min_size + 1u)) + 6u) & ~3u); }   // anchors are more than min_size apart (:242-251)
+SP_HD uint32_t split_min_slots(int n) { return (uint32_t)n + (uint32_t)(n >> 2) + (uint32_t)(n >> 4) + 64u; }                     // load factor <= 0.76
+SP_HD uint64_t split_fixed_words(int nr, int na, int nb, int32_t max_anchors, int32_t sub_anchors) {
+  return (uint64_t)split_pk_words(nr) + split_pk_words(na) + split_pk_words(nb) + split_cand_words(nr) + 6ull * (uint64_t)max_anchors + 6ull * (uint64_t)sub_anchors +
+         4ull * (uint64_t)(max_anchors > sub_anchors ? max_anchors : sub_anchors);
+}
+// Places the arrays of a job in `base` (`words` 32-bit words) -- sc for the job's own chain, sc2 for the sub-calls of the two
+// special cases (same table and packed reads: the outer table is no longer needed then; own anchor arrays: the outer anchors
+// are) -- and says whether they fit.  The table gets what is left, at most 4 slots per reference k-mer.  na / nb: the longest
+// second / third read the scratch will see (a sub-call puts the reference prefix in the third place).  max_anchors and
+// sub_anchors are multiples of 4.
+SP_HD bool split_carve(SplitScratch &sc, SplitScratch &sc2, uint32_t *base, uint64_t words, int nr, int na, int nb, int32_t max_anchors, int32_t sub_anchors) {
+  const uint64_t fixed = split_fixed_words(nr, na, nb, max_anchors, sub_anchors);
+  if (words < fixed + split_min_slots(nr)) return false;
+  const int32_t most_anchors = max_anchors > sub_anchors ? max_anchors : sub_anchors;
+  uint32_t *p = base;
+  sc.anc = reinterpret_cast<SplitAnchor *>(p); p += 4 * (size_t)max_anchors;     // 16-byte aligned: first
+  SplitAnchor *anc2 = reinterpret_cast<SplitAnchor *>(p); p += 4 * (size_t)sub_anchors;
+  sc.nxt = reinterpret_cast<int32_t *>(p); p += max_anchors;
+  sc.bl = reinterpret_cast<int32_t *>(p); p += max_anchors;
+  int32_t *nxt2 = reinterpret_cast<int32_t *>(p); p += sub_anchors;
+  int32_t *bl2 = reinterpret_cast<int32_t *>(p); p += sub_anchors;
+  sc.t2_km = p; p += 2 * (size_t)most_anchors; sc.t2_idx = reinterpret_cast<int32_t *>(p); p += 2 * (size_t)most_anchors;
+  sc.t2_slots = 2u * (uint32_t)most_anchors;
+  sc.pk[0] = p; p += split_pk_words(nr); sc.pk[1] = p; p += split_pk_words(na); sc.pk[2] = p; p += split_pk_words(nb);
+  sc.cand = p; p += split_cand_words(nr);
+  sc.table = p;
+  const uint64_t left = words - fixed, most = 4ull * (uint64_t)nr + 64ull;
+  sc.slots = (uint32_t)(left < most ? left : most);
+  sc.pos_bits = 1;
+  while ((1u << sc.pos_bits) <= (uint32_t)nr) ++sc.pos_bits;                      // 2^pos_bits > nr: a position field is never all ones
+  sc.max_anchors = max_anchors;
+  sc2 = sc;
+  sc2.anc = anc2; sc2.nxt = nxt2; sc2.bl = bl2; sc2.max_anchors = sub_anchors;
+  return true;
+}
+
+// letter codes of the reference's two encoders: str2num (:20-32) for the first k letters of a read, nuc2int (:35-43) for the rest
+SP_HD uint32_t split_code(const SplitSeq &q, int t, int k) {
   const uint8_t c = q.s[t];
   if (t < k) return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : 3u;
   return c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u;
 }
-// the k-mer that the reference has in `seq` when it is at position p of the read (positions 0 .. kmers(q) - 1)
-SP_HD inline uint32_t split_kmer(const SplitSeq &q, int p, int k) {
-  uint32_t v = 0;
-  const int e = p + k < q.n ? p + k : q.n;     // a read shorter than k has one, shorter, k-mer (substr(0, k), :177)
-  for (int t = p; t < e; ++t) v = (v << 2) | split_code(q, t, k);
-  return v & ((1u << (2 * k)) - 1u);
+SP_HD int split_kmers(const SplitSeq &q, int k) { return q.n > k ? q.n - k + 1 : 1; }
+// The k-mer at position p of a packed read: letter p in the lowest two bits.  The reference keeps the first letter in the highest
+// bits (:22-30,:54-57); k-mers are only ever compared, so any one-to-one code gives the same anchors.  A read of at most k letters
+// has one shorter "k-mer" (substr(0, k), :177) whose value is that of the k-mer with leading A's: the letters sit at the top here.
+SP_HD uint32_t split_kmer(const uint32_t *pk, int p, int k, int n) {
+  const uint32_t lo = pk[p >> 4], hi = pk[(p >> 4) + 1];
+  const int sh = 2 * (p & 15);
+#ifdef __CUDA_ARCH__
+  const uint32_t v = __funnelshift_r(lo, hi, sh);
+#else
+  const uint32_t v = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+  if (n >= k) return v & ((1u << (2 * k)) - 1u);
+  return (v & ((1u << (2 * n)) - 1u)) << (2 * (k - n));
 }
-SP_HD inline int split_kmers(const SplitSeq &q, int k) { return q.n > k ? q.n - k + 1 : 1; }
-SP_HD inline uint32_t split_hash(uint32_t kmer) { kmer *= 0x9E3779B1u; return kmer ^ (kmer >> 15); }
+SP_HD uint32_t split_mulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+SP_HD uint32_t split_mix(uint32_t kmer) { uint32_t h = kmer * 0x9E3779B1u; h ^= h >> 15; return h * 0x85EBCA77u; }
 
 #ifdef __CUDA_ARCH__
-#define SP_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+#define SP_FOR(i, n) for (int i = threadIdx.x; i < (int)(n); i += blockDim.x)
 #define SP_SYNC() __syncthreads()
 #define SP_SERIAL if (threadIdx.x == 0)
-SP_HD inline uint32_t sp_cas(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
-SP_HD inline uint32_t sp_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+SP_HD uint32_t sp_cas(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+SP_HD uint32_t sp_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 #else
-#define SP_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define SP_FOR(i, n) for (int i = 0; i < (int)(n); ++i)
 #define SP_SYNC()
 #define SP_SERIAL
-SP_HD inline uint32_t sp_cas(uint32_t *p, uint32_t cmp, uint32_t v) { const uint32_t o = *p; if (o == cmp) *p = v; return o; }
-SP_HD inline uint32_t sp_or(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p = o | v; return o; }
+SP_HD uint32_t sp_cas(uint32_t *p, uint32_t cmp, uint32_t v) { const uint32_t o = *p; if (o == cmp) *p = v; return o; }
+SP_HD uint32_t sp_or(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p = o | v; return o; }
 #endif
 
-// slot of `kmer`, inserting it when `insert`; kSplitEmpty when absent
-SP_HD inline uint32_t split_slot(const SplitScratch &sc, uint32_t kmer, bool insert) {
-  const uint32_t mask = sc.slots - 1;
-  uint32_t s = split_hash(kmer) & mask;
+// 16 letters of q from position 16 * w as one word
+SP_HD uint32_t split_pack_word(const SplitSeq &q, int w, int k) {
+  uint32_t v = 0;
+  const int t0 = 16 * w, e = t0 + 16 < q.n ? t0 + 16 : q.n;
+  for (int t = t0; t < e; ++t) v |= split_code(q, t, k) << (2 * (t - t0));
+  return v;
+}
+
+// slot of the k-mer `km` in the table of the reference k-mers, kSplitEmpty when absent
+SP_HD uint32_t split_find(const SplitScratch &sc, uint32_t km, int k, int nref) {
+  const uint32_t h = split_mix(km), fsh = 6u + sc.pos_bits, want = (h >> 3) << fsh, pmask = (1u << sc.pos_bits) - 1u;
+  uint32_t s = split_mulhi(h, sc.slots);
   for (;;) {
-    uint32_t cur = sc.key[s];
-    if (cur == kSplitEmpty) {
-      if (!insert) return kSplitEmpty;
-      cur = sp_cas(&sc.key[s], kSplitEmpty, kmer);
-      if (cur == kSplitEmpty) return s;
-    }
-    if (cur == kmer) return s;
-    s = (s + 1) & mask;
+    const uint32_t cur = sc.table[s];
+    if (cur == kSplitEmpty) return kSplitEmpty;
+    if (((cur ^ want) >> fsh) == 0 && split_kmer(sc.pk[0], (int)((cur >> 6) & pmask), k, nref) == km) return s;
+    if (++s == sc.slots) s = 0;
   }
 }
 
-// Steps 1-5 for (ref, S1, S2): the anchor list and its best chain.  Returns the chain length (0: no anchor at all) in every
-// thread; the chain is sc.bl[0 .. len-1].  s_int: four ints of shared scratch (device) / any four ints (host).
-SP_HD inline int split_chain(const SplitScratch &sc, const SplitSeq &ref, const SplitSeq &S1, const SplitSeq &S2, int k, uint32_t min_size, int *s_int) {
-  // 1. table of the reference k-mers
-  SP_FOR(i, (int)sc.slots) { sc.key[i] = kSplitEmpty; sc.flag[i] = 0; }
-  SP_FOR(i, (ref.n + 31) / 32 + 1) sc.cand[i] = 0;
-  SP_SYNC();
+// may the record that ends at an anchor zr / za / zb letters after the last cut be written (:282-283)?  The reference compares
+// doubles (|za - zr| < zr * 0.5); the values are small integers, so twice the difference against zr is the same test.
+SP_HD bool split_cut_ok(int zr, int za, int zb, uint32_t ms) {
+  const long long da = za > zr ? (long long)za - zr : (long long)zr - za, db = zb > zr ? (long long)zb - zr : (long long)zr - zb;
+  return (uint32_t)zr > ms && (uint32_t)za > ms && (uint32_t)zb > ms && 2 * da < (long long)zr && 2 * db < (long long)zr;
+}
+
+// Steps 0-5 for (ref, S1, S2): the anchor list and its best chain.  Returns the chain length (0: no anchor at all, -1: more anchors
+// than the scratch holds) in every thread; the chain is sc.bl[0 .. len-1].  s_int: four ints of shared scratch (device) / any four
+// ints (host).
+SP_HD int split_chain(const SplitScratch &sc, const SplitSeq &ref, const SplitSeq &S1, const SplitSeq &S2, int k, uint32_t min_size, int *s_int) {
   const int nr = split_kmers(ref, k), na = split_kmers(S1, k), nb = split_kmers(S2, k);
+  // 0. the reads at 2 bits per letter, empty tables
+  SP_FOR(w, split_pk_words(ref.n)) sc.pk[0][w] = split_pack_word(ref, w, k);
+  SP_FOR(w, split_pk_words(S1.n)) sc.pk[1][w] = split_pack_word(S1, w, k);
+  SP_FOR(w, split_pk_words(S2.n)) sc.pk[2][w] = split_pack_word(S2, w, k);
+  SP_FOR(i, sc.slots) sc.table[i] = kSplitEmpty;
+  SP_FOR(i, sc.t2_slots) sc.t2_km[i] = kSplitEmpty;
+  SP_FOR(i, split_cand_words(ref.n)) sc.cand[i] = 0;
+  SP_SYNC();
+  const uint32_t fsh = 6u + sc.pos_bits, pmask = (1u << sc.pos_bits) - 1u;
+  // 1. table of the reference k-mers (:176-193: an unordered_map with -1 for repeats)
   SP_FOR(p, nr) {
-    const uint32_t s = split_slot(sc, split_kmer(ref, p, k), true);
-    if (sp_or(&sc.flag[s], SF_R1) & SF_R1) sp_or(&sc.flag[s], SF_R2);
-    sc.posr[s] = (uint32_t)p;   // used only when the k-mer occurs once
+    const uint32_t km = split_kmer(sc.pk[0], p, k, ref.n), h = split_mix(km), want = (h >> 3) << fsh;
+    uint32_t s = split_mulhi(h, sc.slots);
+    for (;;) {
+      uint32_t cur = sc.table[s];
+      if (cur == kSplitEmpty) {
+        cur = sp_cas(&sc.table[s], kSplitEmpty, want | ((uint32_t)p << 6) | SF_R1);
+        if (cur == kSplitEmpty) break;
+      }
+      if (((cur ^ want) >> fsh) == 0 && split_kmer(sc.pk[0], (int)((cur >> 6) & pmask), k, ref.n) == km) { if (!(cur & SF_R2)) sp_or(&sc.table[s], SF_R2); break; }
+      if (++s == sc.slots) s = 0;
+    }
   }
   SP_SYNC();
-  // 2. the other two reads
+  // 2. the other two reads (:194-230)
   SP_FOR(p, na) {
-    const uint32_t s = split_slot(sc, split_kmer(S1, p, k), false);
-    if (s != kSplitEmpty) { if (sp_or(&sc.flag[s], SF_A1) & SF_A1) sp_or(&sc.flag[s], SF_A2); sc.posa[s] = (uint32_t)p; }
+    const uint32_t s = split_find(sc, split_kmer(sc.pk[1], p, k, S1.n), k, ref.n);
+    if (s != kSplitEmpty && (sp_or(&sc.table[s], SF_A1) & SF_A1)) sp_or(&sc.table[s], SF_A2);
   }
   SP_FOR(p, nb) {
-    const uint32_t s = split_slot(sc, split_kmer(S2, p, k), false);
-    if (s != kSplitEmpty) { if (sp_or(&sc.flag[s], SF_B1) & SF_B1) sp_or(&sc.flag[s], SF_B2); sc.posb[s] = (uint32_t)p; }
+    const uint32_t s = split_find(sc, split_kmer(sc.pk[2], p, k, S2.n), k, ref.n);
+    if (s != kSplitEmpty && (sp_or(&sc.table[s], SF_B1) & SF_B1)) sp_or(&sc.table[s], SF_B2);
   }
   SP_SYNC();
   // 3. anchors in reference order: once in each read
-  SP_FOR(p, nr) {
-    const uint32_t s = split_slot(sc, split_kmer(ref, p, k), false);
-    if (sc.flag[s] == (SF_R1 | SF_A1 | SF_B1)) sp_or(&sc.cand[p >> 5], 1u << (p & 31));
+  SP_FOR(s, sc.slots) {
+    const uint32_t e = sc.table[s];
+    if (e != kSplitEmpty && (e & SF_MASK) == SF_ONCE) { const uint32_t r = (e >> 6) & pmask; sp_or(&sc.cand[r >> 5], 1u << (r & 31)); }
   }
   SP_SYNC();
-  // 4. left-to-right thinning (:242-251): position 0 is taken as it is; position j + 1 when j - last > minSize, last = j
+  // 4. left-to-right thinning (:242-251): position 0 is taken as it is; position j + 1 when j - last > min_size, last = j -- the
+  //    next anchor is the first candidate more than min_size after the last one (min_size + 1 after the start)
   SP_SERIAL {
     int n = 0;
-    uint32_t last = 0;
-    const int words = (nr + 31) / 32;
-    for (int w = 0; w < words; ++w) {
-      uint32_t bits = sc.cand[w];
-      while (bits) {
-        int b = 0;
-        while (!((bits >> b) & 1u)) ++b;
-        bits &= bits - 1;
-        const int p = w * 32 + b;
-        if (p == 0) { if (n < sc.max_anchors) sc.ar[n++] = 0; continue; }
-        const uint32_t j = (uint32_t)(p - 1);
-        if (j - last > min_size) { if (n < sc.max_anchors) sc.ar[n++] = p; last = j; }
-      }
+    bool over = false;
+    const uint32_t words = (uint32_t)(nr + 31) >> 5;
+    if (sc.cand[0] & 1u) sc.anc[n++].r = 0;
+    uint64_t pos = (uint64_t)min_size + 2u;
+    uint32_t w = 0xffffffffu, bits = 0;
+    while (pos < (uint64_t)nr) {
+      const uint32_t pw = (uint32_t)(pos >> 5);
+      if (pw != w) { w = pw; bits = sc.cand[w]; }
+      uint32_t m = bits & (0xffffffffu << (pos & 31));
+      while (!m && ++w < words) { bits = sc.cand[w]; m = bits; }
+      if (!m) break;
+      int b = 0;
+#ifdef __CUDA_ARCH__
+      b = __ffs((int)m) - 1;
+#else
+      while (!((m >> b) & 1u)) ++b;
+#endif
+      const int p = (int)(w * 32u) + b;
+      if (n >= sc.max_anchors) { over = true; break; }
+      sc.anc[n++].r = p;
+      pos = (uint64_t)p + min_size + 1u;
     }
-    s_int[0] = n;
+    s_int[0] = over ? -1 : n;
   }
   SP_SYNC();
   const int n = s_int[0];
+  if (n < 0) return -1;
+  // the anchors' k-mers go into the small table; the other two reads are looked up in it once more, for the positions
   SP_FOR(i, n) {
-    const uint32_t s = split_slot(sc, split_kmer(ref, sc.ar[i], k), false);
-    sc.aa[i] = (int32_t)sc.posa[s];
-    sc.ab[i] = (int32_t)sc.posb[s];
+    const uint32_t km = split_kmer(sc.pk[0], sc.anc[i].r, k, ref.n);
+    uint32_t s = split_mulhi(km * 0x9E3779B1u, sc.t2_slots);
+    while (sp_cas(&sc.t2_km[s], kSplitEmpty, km) != kSplitEmpty) { if (++s == sc.t2_slots) s = 0; }
+    sc.t2_idx[s] = i;
+    sc.anc[i].chain = 0;
+  }
+  SP_SYNC();
+  for (int q = 1; q <= 2; ++q) {
+    const int nq = q == 1 ? na : nb, lq = q == 1 ? S1.n : S2.n;
+    SP_FOR(p, nq) {
+      const uint32_t km = split_kmer(sc.pk[q], p, k, lq);
+      uint32_t s = split_mulhi(km * 0x9E3779B1u, sc.t2_slots);
+      for (;;) {
+        const uint32_t e = sc.t2_km[s];
+        if (e == kSplitEmpty) break;
+        if (e == km) { if (q == 1) sc.anc[sc.t2_idx[s]].a = p; else sc.anc[sc.t2_idx[s]].b = p; break; }
+        if (++s == sc.t2_slots) s = 0;
+      }
+    }
   }
   SP_SYNC();
   // 5. longest chain, backwards: chain[i] = 1 + max over the successors within reach (first maximum), 0 when there is none
 #ifdef __CUDA_ARCH__
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    for (int i = n - 1; i >= 0; --i) {
-      const int r = sc.ar[i], a = sc.aa[i], b = sc.ab[i];
-      int best = -1, arg = -1;
-      for (int base = i + 1; base < n; base += 32) {          // successors in list order until the reference distance reaches 1000 (:86,:99)
-        const int c = base + lane;
-        bool in = c < n && sc.ar[c] - r < kChainReach;
-        if (in) {
-          const int da = sc.aa[c] - a, db = sc.ab[c] - b;
-          if (da > 0 && da < kChainReach && db > 0 && db < kChainReach) { const int v = sc.chain[c]; if (v > best) { best = v; arg = c; } }
+    if ((min_size + 1u) * 64u >= (uint32_t)kChainReach) {
+      // at most 64 successors are within reach: they stay in registers, lane l holds the anchors whose index is l modulo 32
+      // (e0 the nearer one), and a step replaces the anchor that has just left the reach by the one that has just been finished
+      SplitAnchor e0{0x3fffffff, 0, 0, 0}, e1{0x3fffffff, 0, 0, 0};
+      int i0x = 0x3fffffff;                                      // index of e0; e1 is 32 further
+      SplitAnchor me = n > 0 ? sc.anc[n - 1] : e0;
+      for (int i = n - 1; i >= 0; --i) {
+        const SplitAnchor nextme = i > 0 ? sc.anc[i - 1] : me;
+        unsigned key = 0;
+        {
+          const int da = e0.a - me.a, db = e0.b - me.b;
+          if (e0.r - me.r < kChainReach && da > 0 && da < kChainReach && db > 0 && db < kChainReach) key = ((unsigned)(e0.chain + 1) << 6) | (unsigned)(63 - (i0x - i - 1));
         }
-        const bool stop = __any_sync(0xffffffffu, c < n && !in) || base + 32 >= n;
-        if (stop) break;
+        {
+          const int da = e1.a - me.a, db = e1.b - me.b;
+          if (e1.r - me.r < kChainReach && da > 0 && da < kChainReach && db > 0 && db < kChainReach) {
+            const unsigned k1 = ((unsigned)(e1.chain + 1) << 6) | (unsigned)(31 - (i0x - i - 1));
+            key = k1 > key ? k1 : key;
+          }
+        }
+        const unsigned top = __reduce_max_sync(0xffffffffu, key);
+        const int best = top ? (int)(top >> 6) - 1 : -1, arg = top ? i + 1 + 63 - (int)(top & 63u) : -1;
+        if (lane == (i & 31)) { e1 = e0; e0 = me; e0.chain = 1 + best; i0x = i; sc.anc[i].chain = 1 + best; sc.nxt[i] = arg; }
+        me = nextme;
       }
-      for (int d = 16; d > 0; d >>= 1) {                       // maximum, ties to the smaller index
-        const int ob = __shfl_xor_sync(0xffffffffu, best, d), oa = __shfl_xor_sync(0xffffffffu, arg, d);
-        if (ob > best || (ob == best && oa >= 0 && (arg < 0 || oa < arg))) { best = ob; arg = oa; }
+    } else {
+      for (int i = n - 1; i >= 0; --i) {
+        const SplitAnchor me = sc.anc[i];
+        int best = -1, arg = -1;
+        for (int base = i + 1; base < n; base += 32) {          // successors in list order until the reference distance reaches 1000 (:86,:99)
+          const int c = base + lane;
+          unsigned key = 0;
+          bool far = false;
+          if (c < n) {
+            const SplitAnchor o = sc.anc[c];
+            far = !(o.r - me.r < kChainReach);
+            const int da = o.a - me.a, db = o.b - me.b;
+            if (!far && da > 0 && da < kChainReach && db > 0 && db < kChainReach) key = ((unsigned)(o.chain + 1) << 5) | (unsigned)(31 - lane);
+          }
+          // anchors are in reference order: once one is too far the rest is
+          const unsigned top = __reduce_max_sync(0xffffffffu, key);
+          if (top) { const int v = (int)(top >> 5) - 1; if (v > best) { best = v; arg = base + 31 - (int)(top & 31u); } }
+          if (__any_sync(0xffffffffu, far)) break;
+        }
+        if (lane == 0) { sc.anc[i].chain = 1 + best; sc.nxt[i] = arg; }
+        __syncwarp();
       }
-      if (lane == 0) { sc.chain[i] = 1 + best; sc.nxt[i] = arg; }
-      __syncwarp();
+    }
+    // the first anchor with the longest chain starts it (:113-119)
+    unsigned long long top = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const unsigned long long key = ((unsigned long long)(unsigned)(sc.anc[i].chain + 1) << 32) | (unsigned)(0x7fffffff - i);
+      if (key > top) top = key;
+    }
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, top, d); if (o > top) top = o; }
+    if (lane == 0) s_int[1] = top ? 0x7fffffff - (int)(unsigned)(top & 0xffffffffu) : -1;
+  }
+  SP_SYNC();
+  // the chain from there, by pointer doubling: round r places the anchors 2^r .. 2^(r+1) - 1 steps down the chain
+  SP_FOR(i, n) sc.t2_idx[i] = sc.nxt[i];
+  SP_SYNC();
+  const int at = s_int[1];
+  const int len = at < 0 ? 0 : sc.anc[at].chain + 1;
+  if (len > 0) {
+    int32_t *jc = sc.t2_idx, *jn = reinterpret_cast<int32_t *>(sc.t2_km);
+    SP_SERIAL sc.bl[0] = at;
+    SP_SYNC();
+    for (int step = 1; step < len; step <<= 1) {
+      const int fill = step < len - step ? step : len - step;
+      SP_FOR(j, fill) sc.bl[j + step] = jc[sc.bl[j]];
+      if (2 * step < len) SP_FOR(i, n) { const int t = jc[i]; jn[i] = t < 0 ? -1 : jc[t]; }
+      SP_SYNC();
+      int32_t *t = jc; jc = jn; jn = t;
     }
   }
+  return len;
 #else
   for (int i = n - 1; i >= 0; --i) {
     int best = -1, arg = -1;
     for (int c = i + 1; c < n; ++c) {
-      if (!(sc.ar[c] - sc.ar[i] < kChainReach)) break;
-      const int da = sc.aa[c] - sc.aa[i], db = sc.ab[c] - sc.ab[i];
-      if (da > 0 && da < kChainReach && db > 0 && db < kChainReach && sc.chain[c] > best) { best = sc.chain[c]; arg = c; }
+      if (!(sc.anc[c].r - sc.anc[i].r < kChainReach)) break;
+      const int da = sc.anc[c].a - sc.anc[i].a, db = sc.anc[c].b - sc.anc[i].b;
+      if (da > 0 && da < kChainReach && db > 0 && db < kChainReach && sc.anc[c].chain > best) { best = sc.anc[c].chain; arg = c; }
     }
-    sc.chain[i] = 1 + best; sc.nxt[i] = arg;
+    sc.anc[i].chain = 1 + best; sc.nxt[i] = arg;
   }
-#endif
-  SP_SYNC();
-  SP_SERIAL {   // the first anchor with the longest chain starts it (:113-119), then the successors
+  {   // the first anchor with the longest chain starts it (:113-119), then the successors
     int best = -1, at = -1;
-    for (int i = 0; i < n; ++i) if (sc.chain[i] > best) { best = sc.chain[i]; at = i; }
+    for (int i = 0; i < n; ++i) if (sc.anc[i].chain > best) { best = sc.anc[i].chain; at = i; }
     int len = 0;
     while (at != -1) { sc.bl[len++] = at; at = sc.nxt[at]; }
     s_int[1] = len;
   }
-  SP_SYNC();
   return s_int[1];
+#endif
 }
 
-// The cutting of one job (split(), :175-308) into out[0 ..); returns the number of records, or -1 when out_cap is too small.
-// Positions in the records are relative to the three reads given here.  first_call as in the reference: the late-start /
-// early-end special cases only at the outer level.
-SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, SplitSeq ref, SplitSeq S1, SplitSeq S2, int k, SplitWin *out, int out_cap, int *s_int) {
+// The walk over chain elements i0 .. i1 - 1 (:280-290): an anchor that may end a record (split_cut_ok) does, and the next record
+// starts behind its k-mer.  q* : where the running record starts (in the walked strings), updated; off_*: where the walked strings
+// start in the job's reads; with_b: the third read is cut too.  Records are written from out[*n] on, *n counts them all.
+SP_HD void split_walk(const SplitScratch &sc, int i0, int i1, int k, uint32_t ms, int off_r, int off_a, int off_b, bool with_b, int &qr, int &qa, int &qb, SplitWin *out,
+                      int out_cap, int &n, int *s_int) {
+#ifdef __CUDA_ARCH__
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int cr = qr, ca = qa, cb = qb, cn = n;
+    for (int base = i0; base < i1; base += 32) {
+      const int idx = base + lane;
+      const bool valid = idx < i1;
+      const SplitAnchor an = sc.anc[valid ? sc.bl[idx] : sc.bl[i0]];
+      unsigned todo = __ballot_sync(0xffffffffu, valid);
+      while (todo) {
+        const int zr = an.r - cr, za = an.a - ca, zb = an.b - cb;
+        const unsigned m = __ballot_sync(0xffffffffu, split_cut_ok(zr, za, zb, ms)) & todo;
+        if (!m) break;
+        const int j = __ffs((int)m) - 1;
+        if (lane == j && cn < out_cap) out[cn] = SplitWin{off_r + cr, zr + k, off_a + ca, za + k, with_b ? off_b + cb : 0, with_b ? zb + k : 0};
+        ++cn;
+        cr = __shfl_sync(0xffffffffu, an.r, j) + k; ca = __shfl_sync(0xffffffffu, an.a, j) + k; cb = __shfl_sync(0xffffffffu, an.b, j) + k;
+        todo &= ~((2u << j) - 1u);
+      }
+    }
+    if (lane == 0) { s_int[2] = cn; s_int[3] = cr; s_int[8] = ca; s_int[9] = cb; }
+  }
+  SP_SYNC();
+  n = s_int[2]; qr = s_int[3]; qa = s_int[8]; qb = s_int[9];
+  SP_SYNC();
+#else
+  (void)s_int;
+  for (int i = i0; i < i1; ++i) {
+    const SplitAnchor an = sc.anc[sc.bl[i]];
+    const int zr = an.r - qr, za = an.a - qa, zb = an.b - qb;
+    if (split_cut_ok(zr, za, zb, ms)) {
+      if (n < out_cap) out[n] = SplitWin{off_r + qr, zr + k, off_a + qa, za + k, with_b ? off_b + qb : 0, with_b ? zb + k : 0};
+      ++n;
+      qr = an.r + k; qa = an.a + k; qb = an.b + k;
+    }
+  }
+#endif
+}
+
+// The cutting of one job (split(), :175-308) into out[0 ..); returns the number of records, or -1 when out_cap or the anchor arrays
+// are too small.  Positions in the records are relative to the three reads given here.  first_call as in the reference: the
+// late-start / early-end special cases only at the outer level.
+SP_HD int split_job(const SplitScratch &sc, const SplitScratch &sc2, SplitSeq ref, SplitSeq S1, SplitSeq S2, int k, SplitWin *out, int out_cap, int *s_int) {
   const uint32_t min_size = 20;
   const int blen = split_chain(sc, ref, S1, S2, k, min_size, s_int);
+  if (blen < 0) return -1;
   if (blen < 1) {   // no anchor: the three reads as one record (:256-261)
-    SP_SERIAL { if (out_cap >= 1) out[0] = SplitWin{0, ref.n, 0, S1.n, 0, S2.n}; s_int[2] = out_cap >= 1 ? 1 : -1; }
+    SP_SERIAL { if (out_cap >= 1) out[0] = SplitWin{0, ref.n, 0, S1.n, 0, S2.n}; }
     SP_SYNC();
-    return s_int[2];
+    return out_cap >= 1 ? 1 : -1;
   }
-  // the sequential walk needs the two special cases first: they run the parallel steps again on sub-strings
+  // the two special cases run the parallel steps again on sub-strings
   int nout = 0;
   int i0 = 0, pred_r = 0, pred_a = 0, pred_b = 0;
   {
     const int f = sc.bl[0];
-    const int sr = sc.ar[f] + k, sa = sc.aa[f] + k, sb = sc.ab[f] + k;   // start_ref / start_S1 / start_S2 lengths (:264-266; substr clamps)
+    const int sr = sc.anc[f].r + k, sa = sc.anc[f].a + k, sb = sc.anc[f].b + k;   // start_ref / start_S1 / start_S2 lengths (:264-266; substr clamps)
     const int lr = sr < ref.n ? sr : ref.n, la = sa < S1.n ? sa : S1.n, lb = sb < S2.n ? sb : S2.n;
     if ((long long)lb * 2 < lr && (unsigned)(lr - lb) > 200u) {
       // the corrected read starts late: reference and uncorrected prefix are cut on their own (S2 := the reference prefix),
@@ -228,52 +449,23 @@ SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, Spli
       const SplitSeq pr{ref.s, lr}, pa{S1.s, la};
       const uint32_t ms = (uint32_t)(1.2 * (double)lb);
       const int bl2 = split_chain(sc2, pr, pa, pr, k, ms, s_int + 4);
+      if (bl2 < 0) return -1;
+      int n2 = 0, qr = 0, qa = 0, qb = 0;
+      if (bl2 >= 1) split_walk(sc2, 0, bl2 - 1, k, ms, 0, 0, 0, false, qr, qa, qb, out, out_cap, n2, s_int);
       SP_SERIAL {
-        int n2 = 0;
-        if (bl2 < 1) { if (nout < out_cap) out[nout] = SplitWin{0, pr.n, 0, pa.n, 0, 0}; n2 = 1; }
-        else {
-          int qr = 0, qa = 0, qb = 0;
-          for (int i = 0; i < bl2 - 1; ++i) {
-            const int x = sc2.bl[i];
-            const int zr = sc2.ar[x] - qr, za = sc2.aa[x] - qa, zb = sc2.ab[x] - qb;
-            auto ab = [](int v) { return v < 0 ? -v : v; };
-            if ((uint32_t)zr > ms && (uint32_t)za > ms && (uint32_t)zb > ms && (double)ab(za - zr) < zr * 0.5 && (double)ab(zb - zr) < zr * 0.5) {
-              if (nout + n2 < out_cap) out[nout + n2] = SplitWin{qr, sc2.ar[x] - qr + k, qa, sc2.aa[x] - qa + k, 0, 0};
-              ++n2;
-              qr = sc2.ar[x] + k; qa = sc2.aa[x] + k; qb = sc2.ab[x] + k;
-            }
-          }
-          if (nout + n2 < out_cap) out[nout + n2] = SplitWin{qr, pr.n - qr, qa, pa.n - qa, 0, 0};   // first_call is false there: the rest as it is (:302-306)
-          ++n2;
-        }
-        // corrected side: n2 - 1 times N, then the prefix (N when it is empty) -- generate_dumb_str(n2, header, start_S2, "")
-        for (int i = 0; i < n2 && nout + i < out_cap; ++i) { out[nout + i].b0 = -1; out[nout + i].bn = 1; }
-        if (lb > 0 && nout + n2 - 1 < out_cap) { out[nout + n2 - 1].b0 = 0; out[nout + n2 - 1].bn = lb; }
-        s_int[2] = n2;
+        if (n2 < out_cap) out[n2] = SplitWin{qr, pr.n - qr, qa, pa.n - qa, 0, 0};   // first_call is false there: the rest as it is (:302-306); all of it without an anchor
+        // corrected side: n2 times N, then the prefix (N when it is empty) -- generate_dumb_str(n2 + 1, header, start_S2, "")
+        for (int i = 0; i <= n2 && i < out_cap; ++i) { out[i].b0 = -1; out[i].bn = 1; }
+        if (lb > 0 && n2 < out_cap) { out[n2].b0 = 0; out[n2].bn = lb; }
       }
       SP_SYNC();
-      nout += s_int[2];
+      nout = n2 + 1;
       pred_r = sr; pred_a = sa; pred_b = sb;   // (:273-275: the anchor's end, unclamped)
       i0 = 1;
     }
   }
-  // the walk (:280-290) and the tail (:292-306); the early-end case needs its own parallel steps, so the walk stops before it
-  SP_SERIAL {
-    int n = nout;
-    for (int i = i0; i < blen - 1; ++i) {
-      const int x = sc.bl[i];
-      const int zr = sc.ar[x] - pred_r, za = sc.aa[x] - pred_a, zb = sc.ab[x] - pred_b;
-      auto ab = [](int v) { return v < 0 ? -v : v; };
-      if ((uint32_t)zr > min_size && (uint32_t)za > min_size && (uint32_t)zb > min_size && (double)ab(za - zr) < zr * 0.5 && (double)ab(zb - zr) < zr * 0.5) {
-        if (n < out_cap) out[n] = SplitWin{pred_r, zr + k, pred_a, za + k, pred_b, zb + k};
-        ++n;
-        pred_r = sc.ar[x] + k; pred_a = sc.aa[x] + k; pred_b = sc.ab[x] + k;
-      }
-    }
-    s_int[2] = n; s_int[3] = pred_r; s_int[8] = pred_a; s_int[9] = pred_b;
-  }
-  SP_SYNC();
-  nout = s_int[2]; pred_r = s_int[3]; pred_a = s_int[8]; pred_b = s_int[9];
+  // the walk (:280-290) and the tail (:292-306)
+  split_walk(sc, i0, blen - 1, k, min_size, 0, 0, 0, true, pred_r, pred_a, pred_b, out, out_cap, nout, s_int);
   {
     // substr(pred) of a read that is shorter than pred cannot happen on the chain (positions + k <= length)
     const int er = ref.n - pred_r, ea = S1.n - pred_a, eb = S2.n - pred_b;
@@ -282,37 +474,21 @@ SP_HD inline int split_job(const SplitScratch &sc, const SplitScratch &sc2, Spli
       const SplitSeq pr{ref.s + pred_r, er}, pa{S1.s + pred_a, ea};
       const uint32_t ms = (uint32_t)(1.2 * (double)eb);
       const int bl2 = split_chain(sc2, pr, pa, pr, k, ms, s_int + 4);
+      if (bl2 < 0) return -1;
+      int n2 = nout, qr = 0, qa = 0, qb = 0;
+      if (bl2 >= 1) split_walk(sc2, 0, bl2 - 1, k, ms, pred_r, pred_a, 0, false, qr, qa, qb, out, out_cap, n2, s_int);
       SP_SERIAL {
-        int n2 = 0;
-        if (bl2 < 1) { if (nout < out_cap) out[nout] = SplitWin{pred_r, er, pred_a, ea, 0, 0}; n2 = 1; }
-        else {
-          int qr = 0, qa = 0, qb = 0;
-          for (int i = 0; i < bl2 - 1; ++i) {
-            const int x = sc2.bl[i];
-            const int zr = sc2.ar[x] - qr, za = sc2.aa[x] - qa, zb = sc2.ab[x] - qb;
-            auto ab = [](int v) { return v < 0 ? -v : v; };
-            if ((uint32_t)zr > ms && (uint32_t)za > ms && (uint32_t)zb > ms && (double)ab(za - zr) < zr * 0.5 && (double)ab(zb - zr) < zr * 0.5) {
-              if (nout + n2 < out_cap) out[nout + n2] = SplitWin{pred_r + qr, sc2.ar[x] - qr + k, pred_a + qa, sc2.aa[x] - qa + k, 0, 0};
-              ++n2;
-              qr = sc2.ar[x] + k; qa = sc2.aa[x] + k; qb = sc2.ab[x] + k;
-            }
-          }
-          if (nout + n2 < out_cap) out[nout + n2] = SplitWin{pred_r + qr, er - qr, pred_a + qa, ea - qa, 0, 0};
-          ++n2;
-        }
-        for (int i = 0; i < n2 && nout + i < out_cap; ++i) { out[nout + i].b0 = -1; out[nout + i].bn = 1; }
+        if (n2 < out_cap) out[n2] = SplitWin{pred_r + qr, er - qr, pred_a + qa, ea - qa, 0, 0};
+        for (int i = nout; i <= n2 && i < out_cap; ++i) { out[i].b0 = -1; out[i].bn = 1; }
         if (eb > 0 && nout < out_cap) { out[nout].b0 = pred_b; out[nout].bn = eb; }
-        s_int[2] = nout + n2;
       }
+      nout = n2 + 1;
     } else {
-      SP_SERIAL {
-        if (nout < out_cap) out[nout] = SplitWin{pred_r, er, pred_a, ea, pred_b, eb};
-        s_int[2] = nout + 1;
-      }
+      SP_SERIAL { if (nout < out_cap) out[nout] = SplitWin{pred_r, er, pred_a, ea, pred_b, eb}; }
+      nout = nout + 1;
     }
   }
   SP_SYNC();
-  nout = s_int[2];
   return nout <= out_cap ? nout : -1;
 }
 
@@ -327,59 +503,57 @@ struct SplitArgs {
   const int64_t *off[3];        // n_triplets + 1 each
   const int32_t *header_len;
   const int32_t *status_in;     // 1: corrected read shorter than the threshold share of the reference (no job)
-  // scratch: per CTA two tables + anchor arrays, sized for the longest reference read of the call
-  uint32_t *pool; uint64_t cta_words; uint32_t max_slots; int32_t max_anchors; uint32_t cand_words;
+  const int32_t *order;         // triplets by falling length (the longest jobs start first), or null
+  // scratch: the job's arrays live in the CTA's dynamic shared memory (smem_words) when they fit, with as many anchors for the
+  // sub-calls as for the job itself; a job that does not fit, or whose sub-call finds more anchors than that, runs in the CTA's
+  // share of the pool in global memory (cta_words; sub_anchors anchors for the sub-calls)
+  uint32_t *pool; uint64_t cta_words; int32_t sub_anchors; uint32_t smem_words;
   // per (triplet, k) job: records, their number (-1: capacity), largest_fragment()
   SplitWin *wins; const int64_t *win_off;   // job (t, ki) at wins[win_off[t] + ki * cap(t)], cap(t) = (win_off[t+1] - win_off[t]) / 4
   int32_t *job_n; uint32_t *job_largest;
   int32_t *counter;
 };
 
-__device__ inline SplitScratch carve_scratch(uint32_t *base, uint32_t max_slots, uint32_t cand_words, int32_t max_anchors, uint32_t slots) {
-  SplitScratch sc;
-  uint32_t *p = base;
-  sc.key = p; p += max_slots; sc.flag = p; p += max_slots; sc.posr = p; p += max_slots; sc.posa = p; p += max_slots; sc.posb = p; p += max_slots;
-  sc.cand = p; p += cand_words;
-  sc.ar = reinterpret_cast<int32_t *>(p); p += max_anchors; sc.aa = reinterpret_cast<int32_t *>(p); p += max_anchors;
-  sc.ab = reinterpret_cast<int32_t *>(p); p += max_anchors; sc.chain = reinterpret_cast<int32_t *>(p); p += max_anchors;
-  sc.nxt = reinterpret_cast<int32_t *>(p); p += max_anchors; sc.bl = reinterpret_cast<int32_t *>(p);
-  sc.slots = slots; sc.max_anchors = max_anchors;
-  return sc;
-}
-inline uint64_t split_scratch_words(uint32_t max_slots, uint32_t cand_words, int32_t max_anchors) { return 5ull * max_slots + cand_words + 6ull * (uint64_t)max_anchors; }
-
-// persistent CTAs; a job = (triplet, k); the table of a job has 2 slots per k-mer of ITS reference read
-__global__ void __launch_bounds__(256) split_jobs_kernel(SplitArgs a) {
+// persistent CTAs; a job = (triplet, k)
+__global__ void __launch_bounds__(1024, 1) split_jobs_kernel(SplitArgs a) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ int s_int[16];
   __shared__ int s_job;
-  uint32_t *base = a.pool + (uint64_t)blockIdx.x * a.cta_words;
-  const uint64_t half = a.cta_words / 2;
+  uint32_t *pool = a.pool + (uint64_t)blockIdx.x * a.cta_words;
   for (;;) {
     if (threadIdx.x == 0) s_job = atomicAdd(a.counter, 1);
     __syncthreads();
     const int64_t job = s_job;
     __syncthreads();
     if (job >= 4 * a.n_triplets) break;
-    const int64_t t = job >> 2;
+    const int64_t t = a.order ? (int64_t)a.order[job >> 2] : job >> 2;
     const int ki = (int)(job & 3), k = 15 - 2 * ki;
-    if (a.status_in[t]) { if (threadIdx.x == 0) { a.job_n[job] = 0; a.job_largest[job] = 0; } continue; }
+    const int64_t slot = 4 * t + ki;
+    if (a.status_in[t]) { if (threadIdx.x == 0) { a.job_n[slot] = 0; a.job_largest[slot] = 0; } continue; }
     const SplitSeq ref{a.let[0] + a.off[0][t], (int)(a.off[0][t + 1] - a.off[0][t])}, S1{a.let[1] + a.off[1][t], (int)(a.off[1][t + 1] - a.off[1][t])},
         S2{a.let[2] + a.off[2][t], (int)(a.off[2][t + 1] - a.off[2][t])};
-    uint32_t slots = 64;
-    while (slots < 2u * (uint32_t)ref.n + 2u) slots <<= 1;
-    if (slots > a.max_slots) slots = a.max_slots;
-    const SplitScratch sc = carve_scratch(base, a.max_slots, a.cand_words, a.max_anchors, slots);
-    const SplitScratch sc2 = carve_scratch(base + half, a.max_slots, a.cand_words, a.max_anchors, slots);
+    const int32_t ma = split_anchor_bound(ref.n, 20);
+    const int nb = S2.n > ref.n ? S2.n : ref.n;
     const int64_t cap = (a.win_off[t + 1] - a.win_off[t]) >> 2;
     SplitWin *out = a.wins + a.win_off[t] + (int64_t)ki * cap;
-    const int n = split_job(sc, sc2, ref, S1, S2, k, out, (int)cap, s_int);
-    if (threadIdx.x == 0) {
-      a.job_n[job] = n;
-      unsigned largest = (unsigned)a.header_len[t] + (n > 1 ? 1u : 0u);     // largest_fragment(), :158-169 (split_host.hpp)
-      for (int i = 0; i < n; ++i) largest = max(largest, (unsigned)out[i].rn + 1u);
-      a.job_largest[job] = largest;
+    int n = -2;
+    {
+      SplitScratch sc, sc2;
+      if (split_carve(sc, sc2, s_dyn, a.smem_words, ref.n, S1.n, nb, ma, ma)) n = split_job(sc, sc2, ref, S1, S2, k, out, (int)cap, s_int);
+    }
+    if (n < 0 && a.cta_words) {   // the same in global memory
+      SplitScratch sc, sc2;
+      __syncthreads();
+      if (split_carve(sc, sc2, pool, a.cta_words, ref.n, S1.n, nb, ma, a.sub_anchors)) n = split_job(sc, sc2, ref, S1, S2, k, out, (int)cap, s_int);
     }
     __syncthreads();
+    if (threadIdx.x == 0) s_int[10] = a.header_len[t] + (n > 1 ? 1 : 0);     // largest_fragment(), :158-169 (split_host.hpp)
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine = max(mine, out[i].rn + 1);
+    if (mine > 0) atomicMax(&s_int[10], mine);
+    __syncthreads();
+    if (threadIdx.x == 0) { a.job_n[slot] = n < 0 ? -1 : n; a.job_largest[slot] = (uint32_t)s_int[10]; }
   }
 }
 

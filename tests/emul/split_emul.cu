@@ -25,19 +25,20 @@ int main(int argc, char **argv) {
   std::vector<SplitChoice> choice(batch.n());
   std::vector<std::vector<SplitWin>> wins(batch.n());
   size_t longest = 0;
-  for (size_t t = 0; t < batch.n(); ++t) longest = std::max(longest, (size_t)batch.len(0, t));
-  HostScratch h1(longest), h2(longest);
+  for (size_t t = 0; t < batch.n(); ++t) for (int q = 0; q < 3; ++q) longest = std::max(longest, (size_t)batch.len(q, t));
+  HostScratch hs(longest, getenv("SPLIT_EMUL_TIGHT") != nullptr);
   for (size_t t = 0; t < batch.n(); ++t) {
     const SplitSeq ref{batch.seq(0, t), batch.len(0, t)}, S1{batch.seq(1, t), batch.len(1, t)}, S2{batch.seq(2, t), batch.len(2, t)};
     choice[t].status = 0;
     if (!((double)S2.n / ref.n >= cli.threshold)) { choice[t].status = 1; continue; }
+    hs.fit(ref.n, S1.n, std::max(S2.n, ref.n));
     std::vector<SplitWin> best;
     unsigned best_largest = 0;
     for (int ki = 0; ki < 4; ++ki) {
       const int k = 15 - 2 * ki;
       std::vector<SplitWin> out((size_t)ref.n / 8 + 16);
       int s_int[16];
-      const int n = split_job(h1.sc, h2.sc, ref, S1, S2, k, out.data(), (int)out.size(), s_int);
+      const int n = split_job(hs.sc, hs.sc2, ref, S1, S2, k, out.data(), (int)out.size(), s_int);
       if (n < 0) { fprintf(stderr, "record capacity\n"); return 3; }
       out.resize(n);
       const unsigned largest = split_largest_fragment(out.data(), n, batch.header_len(t));

@@ -19,7 +19,7 @@ def marks_of(fname):
         else:
             src = open(path).read().split("\n")
             m = [(i + 1, l.strip()[:70]) for i, l in enumerate(src)
-                 if re.match(r"\s*(template|EL_HDN|EL_HD|static EL_HD|__global__|__device__|__host__ __device__)", l) and "(" in l
+                 if re.match(r"\s*(template|EL_HDN|EL_HD|SP_HD|static EL_HD|__global__|__device__|__host__ __device__)", l) and "(" in l
                  and not l.strip().startswith("template <")]
             _marks[fname] = ([x[0] for x in m], m)
     return _marks[fname]
