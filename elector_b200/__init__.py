@@ -9,6 +9,7 @@ device raises.
 from .lib import LibraryNotBuilt, load_library, library_path  # noqa: F401
 from .poa import ElectorError, PackedLetters, PoaContext, PoaResult, TALLY_FIELDS, pack_letters, windows_to_csr  # noqa: F401
 from .matrix import write_default_matrix  # noqa: F401
+from .report import report_run, report_write  # noqa: F401
 
 __all__ = ["PoaContext", "PoaResult", "PackedLetters", "pack_letters", "ElectorError", "LibraryNotBuilt", "load_library", "library_path",
-           "windows_to_csr", "write_default_matrix", "TALLY_FIELDS"]
+           "windows_to_csr", "write_default_matrix", "TALLY_FIELDS", "report_run", "report_write"]

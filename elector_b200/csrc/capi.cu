@@ -25,6 +25,8 @@
 #include "wire_kernel.cuh"
 #include "split_kernel.cuh"
 #include "peak_kernel.cuh"
+#include "report_host.hpp"
+#include "prep_host.hpp"
 
 using namespace elector;
 
@@ -86,6 +88,7 @@ struct elector_ctx {
   int pipe_rc = 0;
   DevBuf d_pk[3], d_exc_pos, d_exc_byte, d_rel, d_nib[3], d_esc_pos, d_esc_byte;   // compact wire format: packed letters, exceptions, 32-bit offsets in; 4-bit merged rows and their escapes out
   void *h_stage = nullptr; size_t h_stage_cap = 0;   // pinned staging of a chunk's 32-bit offsets
+  DevBuf d_stretch; int64_t stretch_reads = 0;
   DevBuf d_wdst, d_sums, d_tally_scan, d_tally_out, d_readfirst, d_mtot, d_moff, d_mlen, d_mref, d_mcor, d_munc;
   bool trace = false;
   int band_w = 6;          // ELECTOR_BAND_W: base half-width of the diagonal band of the packed linear kernels (+ rows/16 in phase 1, + rows/8 in phase 2; 0 = full DP)
@@ -966,7 +969,7 @@ void elector_poa_free(elector_ctx *ctx) {
   if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
   DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_ref, &ctx->d_cor, &ctx->d_unc, &ctx->d_roff, &ctx->d_coff, &ctx->d_uoff,
                     &ctx->d_items, &ctx->d_scratch, &ctx->d_scratch_lin, &ctx->d_scratch2, &ctx->d_ctrl, &ctx->d_hist, &ctx->d_bintab, &ctx->d_key, &ctx->d_key2, &ctx->d_n1, &ctx->d_p1, &ctx->d_rows, &ctx->d_rowoff, &ctx->d_stride,
-                    &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_wdst, &ctx->d_sums, &ctx->d_tally_scan, &ctx->d_tally_out,
+                    &ctx->d_nring, &ctx->d_s1, &ctx->d_s2, &ctx->d_cells, &ctx->d_wdst, &ctx->d_sums, &ctx->d_stretch, &ctx->d_tally_scan, &ctx->d_tally_out,
                     &ctx->d_readfirst, &ctx->d_mtot, &ctx->d_moff, &ctx->d_mlen, &ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
   for (DevBuf *b : bufs) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1354,3 +1357,4 @@ int elector_last_kernel_ms(const elector_ctx *ctx, float *ms, int *launches) {
 
 #include "tally_capi.inl"
 #include "split_capi.inl"
+#include "report_capi.inl"

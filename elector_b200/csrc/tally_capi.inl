@@ -8,8 +8,10 @@ int tally_device(elector_ctx *ctx, int64_t n_reads, const uint8_t *dR, const uin
   // dot bitmasks: read r's words start at (off[r] >> 5) + r in each of the three planes
   const int64_t plane_words = (total_bytes >> 5) + n_reads + 2;
   CU(ctx->d_tally_scan.reserve((size_t)plane_words * 3 * sizeof(uint32_t)));
+  CU(ctx->d_stretch.reserve((size_t)n_reads * ELECTOR_STRETCH_K * sizeof(int32_t)));
+  ctx->stretch_reads = n_reads;
   tally_read_kernel<<<(unsigned)n_reads, 128, 0, ctx->stream>>>(n_reads, dR, dC, dU, d_off, d_len, ctx->d_tally_scan.as<uint32_t>(), plane_words,
-                                                               d_counters, ctx->d_ctrl.as<int32_t>() + 3, ctx->d_ctrl.as<int32_t>() + kAbortWord);
+                                                               d_counters, ctx->d_stretch.as<int32_t>(), ctx->d_ctrl.as<int32_t>() + 3, ctx->d_ctrl.as<int32_t>() + kAbortWord);
   CU(cudaGetLastError());
   ctx->last_launches += 1;
 #ifdef ELECTOR_TALLY_TIMING
@@ -93,6 +95,17 @@ int elector_tally_run(elector_ctx *ctx, int64_t n_reads, const char *row_ref, co
   rc = check_scan_overflow(ctx, n_reads);
   cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
   return rc;
+}
+
+int elector_last_stretches(elector_ctx *ctx, int64_t n_reads, int32_t *stretches_out) {
+  if (!ctx) return ELECTOR_EINVAL;
+  if (n_reads < 0 || (n_reads > 0 && !stretches_out)) return ctx->fail(ELECTOR_EINVAL, "null argument");
+  if (n_reads != ctx->stretch_reads) return ctx->fail(ELECTOR_EINVAL, "the last tally on this context had %lld reads, not %lld", (long long)ctx->stretch_reads, (long long)n_reads);
+  if (n_reads == 0) return ELECTOR_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(stretches_out, ctx->d_stretch.p, (size_t)n_reads * ELECTOR_STRETCH_K * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return ELECTOR_OK;
 }
 
 int elector_merge_run(elector_ctx *ctx, int64_t n_reads, const int64_t *read_first, int64_t n_windows, const char *rows,

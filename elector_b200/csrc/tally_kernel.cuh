@@ -422,7 +422,7 @@ __device__ unsigned long long g_tally_clk[4];
 #endif
 __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const uint8_t *R, const uint8_t *C, const uint8_t *U,
                                                           const int64_t *off, const int32_t *len, uint32_t *bits, int64_t plane_words,
-                                                          int64_t *counters, int32_t *overflow_flag, const int32_t *abort) {
+                                                          int64_t *counters, int32_t *stretches, int32_t *overflow_flag, const int32_t *abort) {
   const int64_t r = blockIdx.x;
   if (r >= n_reads || *abort) return;
   const int L = len ? len[r] : (int)(off[r + 1] - off[r]);
@@ -555,6 +555,11 @@ __global__ void __launch_bounds__(128) tally_read_kernel(int64_t n_reads, const 
       o[ELECTOR_T_MISSING] = missing < 0 ? 0 : missing;
       o[ELECTOR_T_EXTENDED] = sc.ext;
       o[ELECTOR_T_ASSESSED] = 1;
+    }
+    if (stretches) {   // the border gap stretches (findGapStretches' dict): what the report needs to rebuild the column mask
+      int32_t *q = stretches + r * ELECTOR_STRETCH_K;
+      q[0] = assessed ? sc.nkeys : 0;
+      for (int k = 0; k < kMaxStretchKeys; ++k) { q[1 + 2 * k] = sc.key_a[k]; q[2 + 2 * k] = sc.key_b[k]; }
     }
   }
   TT(3)

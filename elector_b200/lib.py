@@ -73,6 +73,17 @@ def load_library():
     lib.elector_reads_run.restype = c.c_int
     lib.elector_last_reads_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_float), c.POINTER(c.c_float)]
     lib.elector_last_reads_ms.restype = c.c_int
+    lib.elector_last_stretches.argtypes = [vp, c.c_int64, vp]
+    lib.elector_last_stretches.restype = c.c_int
+    rep_tail = [c.c_int, c.c_int, c.c_double, c.c_int, c.c_int, c.c_char_p, c.c_char_p, c.c_char_p, c.c_char_p, vp, vp, c.c_int64, vp, c.c_int64]
+    lib.elector_report_write.argtypes = [c.c_int64, vp, vp, vp, vp, vp, vp, vp] + rep_tail
+    lib.elector_report_write.restype = c.c_int
+    lib.elector_report_run.argtypes = [vp, c.c_int64, vp, vp, vp, vp, vp, vp] + rep_tail
+    lib.elector_report_run.restype = c.c_int
+    lib.elector_sort_fasta.argtypes = [c.c_char_p, c.c_char_p, vp]
+    lib.elector_sort_fasta.restype = c.c_int
+    lib.elector_duplicate_reads.argtypes = [c.c_char_p] * 5 + [vp]
+    lib.elector_duplicate_reads.restype = c.c_int
     lib.elector_tally_sum_device.argtypes = [vp, c.c_int64, vp, vp]
     lib.elector_tally_sum_device.restype = c.c_int
     lib.elector_last_phase_ms.argtypes = [vp, c.POINTER(c.c_float), c.POINTER(c.c_float)]

@@ -307,6 +307,12 @@ class PoaContext:
         self._check(self._lib.elector_tally_run(self._ctx, n, _p(r), _p(c), _p(u), _p(off), _p(out)))
         return out
 
+    def last_stretches(self, n_reads):
+        """Border gap stretches of the reads of the last tally on this context: int32[n, 17] (count, then first / last column pairs)."""
+        out = np.zeros((n_reads, 17), dtype=np.int32)
+        self._check(self._lib.elector_last_stretches(self._ctx, n_reads, _p(out)))
+        return out
+
     def merge(self, res, read_first):
         """Donatello's per-read merge of a PoaResult (Donatello.cpp:50-84); returns list of (R, C, U) strings."""
         read_first = np.ascontiguousarray(read_first, dtype=np.int64)

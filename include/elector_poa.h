@@ -240,6 +240,66 @@ int elector_reads_run(elector_ctx *ctx, int64_t n_triplets, const char *ref, con
 /* Device time of the last elector_reads_run: window cutting, alignment, merge + tally (CUDA events, ms). */
 int elector_last_reads_ms(const elector_ctx *ctx, float *ms_split, float *ms_poa, float *ms_merge_tally);
 
+/* ---- report -------------------------------------------------------------------------------------------
+ * The border gap stretches of every read of the last tally on this context (elector_tally_run, elector_merge_tally_device,
+ * elector_reads_run; not the chunked elector_pipeline_run*): what findGapStretches keeps (computeStats.py:179-189), as
+ * stretches_out[r*ELECTOR_STRETCH_K] = their number and (first, last) column pairs behind it.  With gapsLeft / gapsRight they
+ * rebuild the column mask of getCorrectedPositions (:712-752). */
+#define ELECTOR_STRETCH_K 17
+int elector_last_stretches(elector_ctx *ctx, int64_t n_reads, int32_t *stretches_out);
+
+/* What computeStats.outputRecallPrecision returns and prints (computeStats.py:196-264), as numbers. */
+typedef struct elector_report_summary {
+  int64_t assessed_reads, throughput_uncorrected, throughput_corrected;
+  double recall, precision;                 /* means over reads, round(.., 7) */
+  double correct_rate_uncorrected;          /* not rounded by the reference */
+  double correct_rate_corrected, error_rate; /* round(.., 7); error_rate = 1 - corrected bases / all bases (:669) */
+  int64_t trimmed_or_split, split_reads, trimmed_reads;
+  double mean_missing;
+  int64_t extended_reads;
+  double mean_extension, gc_ref, gc_cor;    /* gc_*: per cent */
+  int64_t small_reads, wrongly_cor_reads;
+  int64_t ins_u, del_u, subs_u, ins_c, del_c, subs_c;
+  double homopolymer_ratio;
+  int32_t size_distribution_complete;       /* 0: trimmed / split reads present but corrected_fasta missing: no "sequences" lines */
+} elector_report_summary;
+
+/* Replaces: computeStats.outputRecallPrecision (computeStats.py:196-264) with computeMetrics (:519-675), outputMetrics (:444-468)
+ * and outputReadSizeDistribution (:273-288) on the per-record counters of the device tally instead of a Python pass over msa.fa.
+ * Records are those of msa.fa in file order: headers (without '>', header_off[n + 1] offsets into `headers`), counters
+ * [n][ELECTOR_TALLY_K], stretches [n][ELECTOR_STRETCH_K], and the merged rows (m_ref / m_cor, record i at m_off[i]): rows are
+ * read for split reads (consecutive records with one header: the missing size of :595-599) and for the last read (the homopolymer
+ * ratio: the reference keeps the last read's only, :560); m_cor == NULL leaves the ratio at 1.  small_reads / wrongly_cor_reads: the
+ * splitter's two counters; size_threshold: SIZE_CORRECTED_READ_THRESHOLD; homopolymer_threshold: reportedHomopolThreshold;
+ * compensated_sum: 0 adds the per-read ratios left to right like sum() of Python < 3.12 (the README example of the reference),
+ * 1 with Neumaier's compensation like Python >= 3.12 (the means can differ in their 16th digit);
+ * corrected_fasta: the sorted corrected reads (read for the "sequences" lines when there are trimmed / split reads; may be NULL).
+ * Writes <out_dir>/[<soft>_]per_read_metrics.txt and <out_dir>/<size_file_name> (out_dir NULL: nothing is written), the text the
+ * reference appends to its log file (log_text) and the text it prints (stdout_text); host only, no device needed.
+ * Errors: elector_last_error(NULL). */
+int elector_report_write(int64_t n_records, const char *headers, const int64_t *header_off, const int64_t *counters,
+                         const int32_t *stretches, const char *m_ref, const char *m_cor, const int64_t *m_off,
+                         int small_reads, int wrongly_cor_reads, double size_threshold, int homopolymer_threshold, int compensated_sum,
+                         const char *corrected_fasta, const char *out_dir, const char *soft, const char *size_file_name,
+                         elector_report_summary *summary, char *log_text, int64_t log_cap, char *stdout_text, int64_t stdout_cap);
+
+/* The same from the merged rows alone (the records of msa.fa in memory): the tally runs on the device, the report on its counters. */
+int elector_report_run(elector_ctx *ctx, int64_t n_records, const char *headers, const int64_t *header_off, const char *m_ref,
+                       const char *m_cor, const char *m_unc, const int64_t *m_off, int small_reads, int wrongly_cor_reads,
+                       double size_threshold, int homopolymer_threshold, int compensated_sum, const char *corrected_fasta, const char *out_dir,
+                       const char *soft, const char *size_file_name, elector_report_summary *summary, char *log_text,
+                       int64_t log_cap, char *stdout_text, int64_t stdout_cap);
+
+/* ---- file preparation in front of the splitter (host only) ---------------------------------------------
+ * Replaces: readAndSortFasta (elector/readAndSortFiles.py:150-166): the records of a FASTA file (Bio.SeqIO semantics: multi-line
+ * sequences joined, blanks dropped) sorted by their whole header line, ties in file order, written two lines per record. */
+int elector_sort_fasta(const char *in_path, const char *out_path, int64_t *n_records);
+/* Replaces: duplicateRefReads (:171-191) fed by the occurrence table readAndSortFasta returns for the corrected reads (:520-522):
+ * every reference / uncorrected record with k corrected records of the same header is written k times as header_0 .. header_(k-1),
+ * the others are dropped: as many triplets as there are corrected reads. */
+int elector_duplicate_reads(const char *sorted_ref, const char *sorted_unc, const char *sorted_cor, const char *new_ref,
+                            const char *new_unc, int64_t *n_triplets);
+
 /* Global counters on the device: d_sums[k] += sum over reads of d_counters[r*ELECTOR_TALLY_K+k]
  * (ELECTOR_T_EXTENDED: extended reads only).  d_sums is ELECTOR_TALLY_K int64 the caller zeroes;
  * with one rank per GPU this vector is what the final all-reduce carries. */

@@ -136,6 +136,29 @@ def example_chain(tmp_path_factory):
     return {"src": src, "work": work, "out": out, "shards": shards, "gold": load_example_golden()}
 
 
+@pytest.fixture(scope="session")
+def example_oracle_msa(example_chain, tmp_path_factory):
+    """The example through the ORACLE chain (plain-C restatement of `poa` per shard, Donatello restated): the smsa files and the
+    merged records [(header, R, C, U)] in msa.fa order.  tests/test_example_full.py holds both to the reference's md5s."""
+    from oracle import oracle, tally_oracle as to
+    oracle.build()
+    ex = example_chain
+    out = str(tmp_path_factory.mktemp("example_oracle"))
+    cli = os.path.join(ROOT, "oracle", "poa_oracle_cli")
+    mat = os.path.join(out, "blosum80.mat")
+    import elector_b200
+    elector_b200.write_default_matrix(mat)
+    procs = [subprocess.Popen([cli, "-pir", "%s/smsa%d" % (out, i), "-corrected_reads_fasta", "%s/out3%d" % (ex["out"], i), "-reference_reads_fasta",
+                               "%s/out1%d" % (ex["out"], i), "-uncorrected_reads_fasta", "%s/out2%d" % (ex["out"], i), "-pathMatrix", mat],
+                              stdout=subprocess.DEVNULL) for i in ex["shards"]]
+    for p in procs:
+        assert p.wait() == 0
+    recs = []
+    for i in ex["shards"]:
+        recs += to.merge_windows(parse_pir("%s/smsa%d" % (out, i)))
+    return {"dir": out, "records": recs}
+
+
 def md5_file(path):
     import hashlib
     return hashlib.md5(open(path, "rb").read()).hexdigest()

@@ -20,28 +20,18 @@ def test_sorted_inputs_and_reference_splitter_reproduce_the_golden(example_chain
     assert int(open(ex["out"] + "/small_reads.txt").read()) == g["small_reads"]
 
 
-def test_oracle_chain_equals_reference_on_every_example_window(example_chain, golden_dir, tmp_path):
-    from oracle import oracle, tally_oracle as to
-    oracle.build()
+def test_oracle_chain_equals_reference_on_every_example_window(example_chain, example_oracle_msa):
+    from oracle import tally_oracle as to
     ex = example_chain
     g = ex["gold"]
-    cli = os.path.join(ROOT, "oracle", "poa_oracle_cli")
-    procs = []
-    for i in ex["shards"]:
-        procs.append(subprocess.Popen([cli, "-pir", str(tmp_path / ("smsa%d" % i)), "-corrected_reads_fasta", "%s/out3%d" % (ex["out"], i),
-                                       "-reference_reads_fasta", "%s/out1%d" % (ex["out"], i), "-uncorrected_reads_fasta",
-                                       "%s/out2%d" % (ex["out"], i), "-pathMatrix", golden_dir + "/blosum80.mat"], stdout=subprocess.DEVNULL))
-    for p in procs:
-        assert p.wait() == 0
     # poa: byte-identical PIR of every shard
     for i in ex["shards"]:
-        assert md5_file(str(tmp_path / ("smsa%d" % i))) == g["smsa_md5"][str(i)], i
+        assert md5_file("%s/smsa%d" % (example_oracle_msa["dir"], i)) == g["smsa_md5"][str(i)], i
     # Donatello: byte-identical msa.fa (shard by shard, appended, alignment.py:121-127)
-    msa, recs = [], []
-    for i in ex["shards"]:
-        for h, a, b, c in to.merge_windows(parse_pir(str(tmp_path / ("smsa%d" % i)))):
-            msa += [h, a, h, b, h, c]
-            recs.append((h, a, b, c))
+    recs = example_oracle_msa["records"]
+    msa = []
+    for h, a, b, c in recs:
+        msa += [h, a, h, b, h, c]
     assert hashlib.md5(("\n".join(msa) + "\n").encode()).hexdigest() == g["msa_md5"]
     # computeStats: the integer counters of ALL merged records
     assert len(recs) == len(g["records"]) == 484

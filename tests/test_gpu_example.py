@@ -78,3 +78,53 @@ def test_pipeline_msa_md5_and_all_459_read_counters(example_chain):
     exp_sums = counters.sum(axis=0)
     exp_sums[ext] = counters[:, ext][counters[:, ext] >= 0].sum()
     assert np.array_equal(sums, exp_sums)
+
+
+def test_example_from_the_read_files_to_the_report(example_chain, tmp_path):
+    """SURVEY.md 8f-1 + 8f-2 in one go: the three sorted read files -> elector_reads_run (window cutting, alignment, Donatello merge and
+    tally, windows never leave the device) -> elector_report_write.  msa.fa bytes, per_read_metrics.txt (md5 5507a652...),
+    read_size_distribution.txt, the log block and the printed block == what the unmodified reference chain wrote."""
+    import os
+
+    import elector_b200
+    import workloads
+    from test_report import README_BLOCK, check_against_golden
+    ex = example_chain
+    g, work = ex["gold"], ex["work"]
+    hr, ref, ro = workloads.parse_two_line_fasta(work + "/ref.fa")
+    _, unc, uo = workloads.parse_two_line_fasta(work + "/unc.fa")
+    _, cor, co = workloads.parse_two_line_fasta(work + "/cor.fa")
+    n = len(hr)
+    assert n == 484
+    with elector_b200.PoaContext(0) as ctx:
+        got = ctx.reads_run(ref, ro, unc, uo, cor, co, [len(h) for h in hr], 0.1, merged=True)
+        stretches = ctx.last_stretches(n)
+        assert got["n_windows"] == 82804
+        small, wrong = int((got["status"] == 1).sum()), int((got["status"] == 2).sum())
+        assert (small, wrong) == (g["small_reads"], g["wrongly_cor_reads"])
+        heads, rows, keep = [], [], []
+        for t in range(n):
+            o, l = int(got["m_off"][t]), int(got["m_len"][t])
+            if l <= 1:                      # Donatello.cpp:70 writes nothing for such a read
+                continue
+            h = hr[t] if isinstance(hr[t], str) else hr[t].decode()
+            h = (h if h.startswith(">") else ">" + h) + " untitled"
+            heads.append(h[:len(h) - 11] + " ")
+            rows.append(tuple(got[k][o:o + l].tobytes().decode() for k in ("m_ref", "m_cor", "m_unc")))
+            keep.append(t)
+        msa = []
+        for h, (a, b, c) in zip(heads, rows):
+            msa += [h, a, h, b, h, c]
+        assert hashlib.md5(("\n".join(msa) + "\n").encode()).hexdigest() == g["msa_md5"]
+        out1, out2 = str(tmp_path / "a"), str(tmp_path / "b")
+        os.makedirs(out1); os.makedirs(out2)
+        common = dict(small_reads=small, wrongly_cor_reads=wrong, size_threshold=0.1, homopolymer_threshold=5, corrected_fasta=work + "/cor.fa")
+        # from the counters of the chained call
+        res = elector_b200.report_write([h[1:] for h in heads], got["counters"][keep], stretches[keep], [r[0] for r in rows], [r[1] for r in rows],
+                                        out_dir=out1, compensated_sum=True, **common)
+        check_against_golden(res, out1, g)
+        # from the rows alone (msa.fa in memory): tally on the device, then the report
+        res = elector_b200.report_run(ctx, [h[1:] for h in heads], [r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows],
+                                      out_dir=out2, compensated_sum=False, **common)
+        assert res["stdout"] == "None\n" + README_BLOCK
+        assert md5_file(out2 + "/per_read_metrics.txt") == g["report"]["per_read_metrics_md5"]
