@@ -9,12 +9,17 @@
  * exit status 0 on success, 1 when the matrix or a FASTA file cannot be read or holds no
  * record (main.c:149-155,245-262).  stdout carries the reference's "0 1 2 " line per
  * window (buildup_lpo.c:545).  The GPU is chosen with ELECTOR_DEVICE (default 0).
+ * By default the work is done by a persistent server process that the first call starts (csrc/service.h): alignment.py starts
+ * a process per shard, and a CUDA context per process costs more than the reference's whole CPU run of the shard.
  */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../../include/elector_poa.h"
+#ifndef ELECTOR_SERVER
+#include "service.h"
+#endif
 
 int main(int argc, char **argv)
 {
@@ -36,6 +41,10 @@ int main(int argc, char **argv)
             argv[0]);
     exit(-1);
   }
+#ifndef ELECTOR_SERVER
+  /* the persistent service runs this very function with its long-lived context (service.h); ELECTOR_SERVICE=0: here, as before */
+  if (svc_try_call(SVC_KIND_POA, argc, argv, &rc)) return rc;
+#endif
   for (i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "-pir")) { pir = argv[++i]; continue; }
     if (!strcmp(argv[i], "-corrected_reads_fasta")) { cor = argv[++i]; continue; }

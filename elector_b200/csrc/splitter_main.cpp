@@ -10,11 +10,17 @@
 
 #include "../../include/elector_poa.h"
 #include "split_host.hpp"
+#ifndef ELECTOR_SERVER
+#include "service.h"
+#endif
 
 using namespace elector;
 
 int main(int argc, char **argv) {
   SplitCli cli;
+#ifndef ELECTOR_SERVER
+  { int code; if (argc >= 12 && svc_try_call(SVC_KIND_SPLITTER, argc, argv, &code)) return code; }   // the persistent service (service.h)
+#endif
   if (!cli.parse(argc, argv)) { fprintf(stderr, "usage: %s REF UNC COR OUT1 OUT2 OUT3 k nb_file max_amount threshold OUTDIR\n", argv[0]); return 2; }
   SplitBatch b;
   const int more = cli.read_round(b);

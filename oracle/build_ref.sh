@@ -11,6 +11,11 @@
 #                               the reference's own objects: dumps DP scores and
 #                               alignments that the poa binary never prints
 #   oracle/_ref/blosum80.mat    the matrix file (data, 42 lines) next to the binaries
+#   oracle/_ref/elector_tree/   an ELECTOR installation as install.sh lays it out, for running the reference's OWN Python
+#                               (alignment.getPOA, computeStats.outputRecallPrecision) next to the replacements on the GPU box:
+#                               elector/*.py (unmodified copies), bin/{poa,masterSplitter,Donatello} (the builds above),
+#                               src/poa-graph/blosum80.mat, and an empty Bio/ stub (the modules import Bio.SeqIO at the top
+#                               but the two functions never use it; Biopython is not in the image)
 #
 # Flag-level workarounds only: -fcommon (GCC>=10 vs
 # black_flag.h tentative definitions), -include cstdint (Master_Splitter.cpp).
@@ -38,5 +43,14 @@ gcc -o "$OUT/ref_dump" "$OUT/obj/ref_harness.o" "$OUT/obj/align_score.o" $OBJS -
 g++ -w -Ofast -std=c++11 -fopenmp -include cstdint "$REF/src/split/Master_Splitter.cpp" -o "$OUT/masterSplitter"
 g++ -w -Ofast -std=c++11 "$REF/src/split/Donatello.cpp" -o "$OUT/Donatello"
 cp "$P/blosum80.mat" "$OUT/blosum80.mat"
+T="$OUT/elector_tree"
+rm -rf "$T"
+mkdir -p "$T/elector" "$T/bin" "$T/src/poa-graph" "$T/Bio"
+cp "$REF"/elector/*.py "$T/elector/"
+cp "$OUT/poa" "$OUT/masterSplitter" "$OUT/Donatello" "$T/bin/"
+cp "$P/blosum80.mat" "$T/src/poa-graph/blosum80.mat"
+printf '' > "$T/Bio/__init__.py"
+printf '' > "$T/Bio/SeqIO.py"
+printf 'class Seq(str):\n    pass\n' > "$T/Bio/Seq.py"
 rm -rf "$OUT/obj"
 echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')"
