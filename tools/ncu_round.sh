@@ -21,8 +21,9 @@ python tools/dump_csr.py 10000 1 /tmp/c1 > /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
 # --set full of the phase-2 launch set of the SECOND call (the first one grows the scratch pools and runs segments twice)
 set -- $(python tools/ncu_skip.py $O/${TAG}_launches_pipeline.csv poa_dp2); echo "phase-2 launches: skip $1, capture $2"
-timeout 1200 ncu --set full --clock-control none -k regex:poa_dp2 --launch-skip $1 -c $2 -o $O/${TAG}_dp2_10k -f elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo dp2-10k rc=$?
-python tools/ncu_traffic.py $O/${TAG}_dp2_10k.ncu-rep $O/${TAG}_traffic.json
+# (every poa_dp2 launch of the run is captured and the last $2 are kept: under the full set the first call's launch pattern differs)
+timeout 1500 ncu --set full --clock-control none -k regex:poa_dp2 -c 80 -o $O/${TAG}_dp2_10k -f elector_b200/bin/pipe_driver /tmp/c1 3 > /dev/null; echo dp2-10k rc=$?
+python tools/ncu_traffic.py $O/${TAG}_dp2_10k.ncu-rep $O/${TAG}_traffic.json $2
 # summaries are made here; the reports themselves (30 MB each) stay on the box unless KEEP_REPS=1 (gpurun_out/ is capped at 64 MiB)
 python tools/ncu_summary.py $O/${TAG}_full.ncu-rep > $O/${TAG}_ncu_full_summary_2k_reads.csv
 python tools/ncu_summary.py $O/${TAG}_dp2_10k.ncu-rep > $O/${TAG}_ncu_full_summary_dp2_10k_reads.csv

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""DRAM traffic of the phase-2 launch set from an `ncu --set full` report of one call -> profiles/traffic.json
-  python tools/ncu_traffic.py REPORT.ncu-rep OUT.json"""
+"""DRAM traffic of the phase-2 launch set from an `ncu --set full` report -> profiles/traffic.json.  With K the report holds
+the poa_dp2 launches of several calls and the LAST K of them are the set of one steady-state call (the first call of a process
+grows the scratch pools and runs some segments twice).
+  python tools/ncu_traffic.py REPORT.ncu-rep OUT.json [K]"""
 import csv
 import json
 import subprocess
@@ -20,7 +22,10 @@ def to_bytes(v, u):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 
 
-for r in rows[2:]:
+body = rows[2:]
+if len(sys.argv) > 3 and int(sys.argv[3]) > 0:
+    body = body[-int(sys.argv[3]):]
+for r in body:
     name = r[ix["Kernel Name"]]
     rd = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]])
     wr = to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
