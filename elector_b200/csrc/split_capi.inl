@@ -1,7 +1,7 @@
 // split_capi.inl -- C-ABI entry points of the window cutting (included by capi.cu)
 namespace {
 struct SplitBufs {
-  DevBuf let[3], off[3], order, hl, st_in, pool, wins, win_off, job_n, job_l, status, kidx, nrec, nl[3], base[4], w_off[3], w_let[3], rf, misc;
+  DevBuf let[3], pk[3], off[3], order, hl, st_in, pool, wins, win_off, job_n, job_l, status, kidx, nrec, nl[3], base[4], w_off[3], w_let[3], rf, misc;
 };
 SplitBufs *split_bufs(elector_ctx *ctx) {
   if (!ctx->split_state) ctx->split_state = new SplitBufs();
@@ -26,7 +26,7 @@ int elector_split_bounds(int64_t n, const int64_t *ref_off, const int64_t *unc_o
 void elector_split_release(elector_ctx *ctx) {
   if (!ctx || !ctx->split_state) return;
   SplitBufs *b = static_cast<SplitBufs *>(ctx->split_state);
-  for (DevBuf *d : {&b->let[0], &b->let[1], &b->let[2], &b->off[0], &b->off[1], &b->off[2], &b->order, &b->hl, &b->st_in, &b->pool, &b->wins, &b->win_off, &b->job_n, &b->job_l,
+  for (DevBuf *d : {&b->let[0], &b->let[1], &b->let[2], &b->pk[0], &b->pk[1], &b->pk[2], &b->off[0], &b->off[1], &b->off[2], &b->order, &b->hl, &b->st_in, &b->pool, &b->wins, &b->win_off, &b->job_n, &b->job_l,
                     &b->status, &b->kidx, &b->nrec, &b->nl[0], &b->nl[1], &b->nl[2], &b->base[0], &b->base[1], &b->base[2], &b->base[3], &b->w_off[0], &b->w_off[1],
                     &b->w_off[2], &b->w_let[0], &b->w_let[1], &b->w_let[2], &b->rf, &b->misc})
     d->release();
@@ -73,7 +73,7 @@ int split_device(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *re
   const int32_t sub_anchors = (int32_t)((longest / 8 + 16 + 3) & ~(int64_t)3);
   for (int64_t t = 0; t < n; ++t) {   // the pool holds any job of the call with two table slots per k-mer: what does not fit the shared memory runs there
     const int64_t lr = ref_off[t + 1] - ref_off[t], la = unc_off[t + 1] - unc_off[t], lb = cor_off[t + 1] - cor_off[t];
-    if (!st_in[(size_t)t]) need_pool = std::max<uint64_t>(need_pool, need_words(lr, la, lb, sub_anchors, 2ull * (uint64_t)lr + 64));
+    if (!st_in[(size_t)t]) need_pool = std::max<uint64_t>(need_pool, need_words(lr, la, lb, sub_anchors, (uint64_t)split_min_slots((int)lr) + (uint64_t)lr / 4));   // ~1.55 slots per k-mer: the tables of all CTAs stay in the L2
   }
   {   // the longest reads first: a counting sort by length / 256
     const size_t nb = (size_t)(longest / 256 + 2);
@@ -110,6 +110,12 @@ int split_device(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *re
   for (int k = 0; k < 3; ++k) { a.let[k] = b.let[k].as<uint8_t>() - h_off[k][0]; a.off[k] = b.off[k].as<int64_t>(); }
   a.header_len = b.hl.as<int32_t>(); a.status_in = b.st_in.as<int32_t>();
   a.order = b.order.as<int32_t>();
+  for (int k = 0; k < 3; ++k) {   // the letters once at 2 bits each: the four jobs of a triplet read these
+    const int64_t nl = h_off[k][n] - h_off[k][0], nwords = nl / 16 + 3;
+    CU(b.pk[k].reserve((size_t)nwords * 4));
+    split_prepack_kernel<<<(unsigned)std::min<int64_t>((nwords + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, st>>>(b.let[k].as<uint8_t>(), nl, b.pk[k].as<uint32_t>(), nwords);
+    a.pk[k] = b.pk[k].as<uint32_t>(); a.base[k] = h_off[k][0];
+  }
   a.pool = b.pool.as<uint32_t>(); a.cta_words = cta_words; a.sub_anchors = sub_anchors; a.smem_words = smem_words;
   a.wins = b.wins.as<SplitWin>(); a.win_off = b.win_off.as<int64_t>();
   a.job_n = b.job_n.as<int32_t>(); a.job_largest = b.job_l.as<uint32_t>();
@@ -122,6 +128,22 @@ int split_device(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *re
   scan_offsets_kernel<<<1, 1024, 0, st>>>(n, b.nrec.as<int64_t>(), b.base[0].as<int64_t>());
   for (int k = 0; k < 3; ++k) scan_offsets_kernel<<<1, 1024, 0, st>>>(n, b.nl[k].as<int64_t>(), b.base[k + 1].as<int64_t>());
   CU(cudaGetLastError());
+#ifdef SPLIT_TIMING
+  {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_split_clk, sizeof h);
+    static const char *name[14] = {"pack+clear", "insert ref", "look up S1+S2", "candidates", "next pointers", "thinning (serial)", "clear bloom", "anchor table", "positions", "chain DP", "copy nxt",
+                                   "chain extraction", "walk", "rest of job"};
+    double tot = 0;
+    for (int k = 0; k < 14; ++k) tot += (double)h[k];
+    fprintf(stderr, "[split timing] %lld jobs, cycles per job (thread 0 of the CTA):", (long long)(4 * n));
+    for (int k = 0; k < 14; ++k) fprintf(stderr, "  %s %.0f (%.1f%%)", name[k], (double)h[k] / (4.0 * n), 100.0 * (double)h[k] / tot);
+    fprintf(stderr, "  | total %.0f\n", tot / (4.0 * n));
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_split_clk, z, sizeof z);
+  }
+#endif
   // sizes of the outputs, then the windows themselves
   for (int k = 0; k < 4; ++k) CU(cudaMemcpyAsync(&ctx->h_totals[k], b.base[k].as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(&ctx->h_totals[4], b.misc.as<int32_t>() + 1, 4, cudaMemcpyDeviceToHost, st));
@@ -136,7 +158,7 @@ int split_device(elector_ctx *ctx, int64_t n, const char *ref, const int64_t *re
                                                 b.rf.as<int64_t>());
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_split1, st));
-  ctx->last_launches += 7;
+  ctx->last_launches += 10;
   return ELECTOR_OK;
 }
 }  // namespace

@@ -42,7 +42,9 @@ enum : uint32_t { SF_R1 = 1, SF_R2 = 2, SF_A1 = 4, SF_A2 = 8, SF_B1 = 16, SF_B2 
 constexpr int kChainReach = 1000;              // Master_Splitter.cpp:86-88
 constexpr int kSplitMaxRead = (1 << 25) - 2;   // a table entry is fingerprint | reference position | 6 flags
 
-struct SplitSeq { const uint8_t *s; int n; };
+// a read (or a piece of one): its letters, and -- on the device -- where they sit in the call's letters packed once at 2 bits each
+// (split_prepack_kernel): letter g + t of the kind's array is letter t of this read
+struct SplitSeq { const uint8_t *s; int n; const uint32_t *pk = nullptr; int64_t g = 0; };
 
 // one output record of a job: three (start, length) pairs into the job's three reads; b0 = -1: the corrected side is the
 // placeholder "N" (generate_dumb_str, :139-154)
@@ -54,8 +56,11 @@ struct alignas(16) SplitAnchor { int32_t r, a, b, chain; };
 // scratch of one job: shared memory when the job fits the CTA's share (every array then), the CTA's pool in global memory when
 // it does not (reads of more than ~13 000 / ~27 000 letters)
 struct SplitScratch {
-  uint32_t *table;      // open addressing, `slots` entries: kSplitEmpty or fingerprint | position of the k-mer's first occurrence in ref | flags;
-  uint32_t slots;       // a probe compares the fingerprint and only then the k-mer itself, read from the packed reference
+  uint32_t *table;      // open addressing in buckets of 4 slots (one 16-byte load per probe), `slots` entries: kSplitEmpty or
+  uint32_t slots;       // fingerprint | position of the k-mer's first occurrence in ref | flags; a probe compares the fingerprints and only
+                        // then the k-mer itself, read from the packed reference.  A bucket fills from its first slot on: an empty last
+                        // slot ends a search.  After step 3 the table is dead and its words hold the thinning's pointers, then the chain
+                        // DP's eligibility masks
   uint32_t pos_bits;    // width of the position field above the 6 flag bits
   uint32_t *pk[3];      // the three reads at 2 bits per letter, 16 letters per word (+ 2 words that a k-mer at the end may touch)
   uint32_t *cand;       // bitmap over reference positions
@@ -95,11 +100,12 @@ SP_HD bool split_carve(SplitScratch &sc, SplitScratch &sc2, uint32_t *base, uint
   int32_t *bl2 = reinterpret_cast<int32_t *>(p); p += sub_anchors;
   sc.t2_km = p; p += 2 * (size_t)most_anchors; sc.t2_idx = reinterpret_cast<int32_t *>(p); p += 2 * (size_t)most_anchors;
   sc.t2_slots = 2u * (uint32_t)most_anchors;
+  sc.table = p;                                                                   // 16-byte aligned: everything before it is a multiple of 4 words
+  const uint64_t left = words - fixed, most = 4ull * (uint64_t)nr + 64ull;
+  sc.slots = (uint32_t)(left < most ? left : most) & ~3u;                          // buckets of 4 slots
+  p += sc.slots;
   sc.pk[0] = p; p += split_pk_words(nr); sc.pk[1] = p; p += split_pk_words(na); sc.pk[2] = p; p += split_pk_words(nb);
   sc.cand = p; p += split_cand_words(nr);
-  sc.table = p;
-  const uint64_t left = words - fixed, most = 4ull * (uint64_t)nr + 64ull;
-  sc.slots = (uint32_t)(left < most ? left : most);
   sc.pos_bits = 1;
   while ((1u << sc.pos_bits) <= (uint32_t)nr) ++sc.pos_bits;                      // 2^pos_bits > nr: a position field is never all ones
   sc.max_anchors = max_anchors;
@@ -129,6 +135,16 @@ SP_HD uint32_t split_kmer(const uint32_t *pk, int p, int k, int n) {
   if (n >= k) return v & ((1u << (2 * k)) - 1u);
   return (v & ((1u << (2 * n)) - 1u)) << (2 * (k - n));
 }
+// the same for a read of at least k letters, with the mask (1 << 2k) - 1 at hand
+SP_HD uint32_t split_kmer_full(const uint32_t *pk, int p, uint32_t mask) {
+  const uint32_t lo = pk[p >> 4], hi = pk[(p >> 4) + 1];
+  const int sh = 2 * (p & 15);
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, sh) & mask;
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & mask;
+#endif
+}
 SP_HD uint32_t split_mulhi(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
   return __umulhi(a, b);
@@ -137,14 +153,33 @@ SP_HD uint32_t split_mulhi(uint32_t a, uint32_t b) {
 #endif
 }
 SP_HD uint32_t split_mix(uint32_t kmer) { uint32_t h = kmer * 0x9E3779B1u; h ^= h >> 15; return h * 0x85EBCA77u; }
+// the fingerprint field of an entry for hash h (fsh = 6 + pos_bits): never all ones, so that kSplitEmpty fails every fingerprint test
+SP_HD uint32_t split_want(uint32_t h, uint32_t fsh) { const uint32_t w = (h >> 3) << fsh; return w == (0xffffffffu << fsh) ? 0u : w; }
+
+#if defined(SPLIT_TIMING) && defined(__CUDACC__)
+// phase clocks of the cutting kernel (a diagnostic build: -DSPLIT_TIMING): cycles of thread 0 between the marks, summed over jobs
+__device__ unsigned long long g_split_clk[16];
+__host__ __device__ __forceinline__ void split_mark(int k, long long &prev) {
+#ifdef __CUDA_ARCH__
+  if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_split_clk[k], (unsigned long long)(t - prev)); prev = t; }
+#endif
+}
+#define ST(k) split_mark(k, *reinterpret_cast<long long *>(s_int + 12))
+#else
+#define ST(k)
+#endif
 
 #ifdef __CUDA_ARCH__
+#define SP_FIRST ((int)threadIdx.x)
+#define SP_STRIDE ((int)blockDim.x)
 #define SP_FOR(i, n) for (int i = threadIdx.x; i < (int)(n); i += blockDim.x)
 #define SP_SYNC() __syncthreads()
 #define SP_SERIAL if (threadIdx.x == 0)
 SP_HD uint32_t sp_cas(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
 SP_HD uint32_t sp_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 #else
+#define SP_FIRST 0
+#define SP_STRIDE 1
 #define SP_FOR(i, n) for (int i = 0; i < (int)(n); ++i)
 #define SP_SYNC()
 #define SP_SERIAL
@@ -152,31 +187,36 @@ SP_HD uint32_t sp_cas(uint32_t *p, uint32_t cmp, uint32_t v) { const uint32_t o 
 SP_HD uint32_t sp_or(uint32_t *p, uint32_t v) { const uint32_t o = *p; *p = o | v; return o; }
 #endif
 
-// 16 letters of q from position 16 * w as one word
+// 16 letters of q from position 16 * w as one word: from the bytes, or from the packed letters of the call (every letter coded
+// like nuc2int there; the first k letters of a read take str2num's code, so the first word is patched from the bytes)
 SP_HD uint32_t split_pack_word(const SplitSeq &q, int w, int k) {
   uint32_t v = 0;
   const int t0 = 16 * w, e = t0 + 16 < q.n ? t0 + 16 : q.n;
+  if (q.pk) {
+    if (e <= t0) return 0;
+    const int64_t g = q.g + t0;
+    const uint32_t lo = q.pk[g >> 4], hi = q.pk[(g >> 4) + 1];
+    const int sh = 2 * (int)(g & 15);
+#ifdef __CUDA_ARCH__
+    v = __funnelshift_r(lo, hi, sh);
+#else
+    v = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+    if (e - t0 < 16) v &= (1u << (2 * (e - t0))) - 1u;
+    if (w == 0) { const int f = k < e ? k : e; for (int t = 0; t < f; ++t) v = (v & ~(3u << (2 * t))) | (split_code(q, t, k) << (2 * t)); }
+    return v;
+  }
   for (int t = t0; t < e; ++t) v |= split_code(q, t, k) << (2 * (t - t0));
   return v;
 }
 
-// slot of the k-mer `km` in the table of the reference k-mers, kSplitEmpty when absent
-SP_HD uint32_t split_find(const SplitScratch &sc, uint32_t km, int k, int nref) {
-  const uint32_t h = split_mix(km), fsh = 6u + sc.pos_bits, want = (h >> 3) << fsh, pmask = (1u << sc.pos_bits) - 1u;
-  uint32_t s = split_mulhi(h, sc.slots);
-  for (;;) {
-    const uint32_t cur = sc.table[s];
-    if (cur == kSplitEmpty) return kSplitEmpty;
-    if (((cur ^ want) >> fsh) == 0 && split_kmer(sc.pk[0], (int)((cur >> 6) & pmask), k, nref) == km) return s;
-    if (++s == sc.slots) s = 0;
-  }
-}
+struct alignas(16) SplitBucket { uint32_t e[4]; };
 
 // may the record that ends at an anchor zr / za / zb letters after the last cut be written (:282-283)?  The reference compares
 // doubles (|za - zr| < zr * 0.5); the values are small integers, so twice the difference against zr is the same test.
 SP_HD bool split_cut_ok(int zr, int za, int zb, uint32_t ms) {
-  const long long da = za > zr ? (long long)za - zr : (long long)zr - za, db = zb > zr ? (long long)zb - zr : (long long)zr - zb;
-  return (uint32_t)zr > ms && (uint32_t)za > ms && (uint32_t)zb > ms && 2 * da < (long long)zr && 2 * db < (long long)zr;
+  const int da = za > zr ? za - zr : zr - za, db = zb > zr ? zb - zr : zr - zb;     // positions are below 2^25: no overflow
+  return (uint32_t)zr > ms && (uint32_t)za > ms && (uint32_t)zb > ms && 2 * da < zr && 2 * db < zr;
 }
 
 // Steps 0-5 for (ref, S1, S2): the anchor list and its best chain.  Returns the chain length (0: no anchor at all, -1: more anchors
@@ -191,84 +231,152 @@ SP_HD int split_chain(const SplitScratch &sc, const SplitSeq &ref, const SplitSe
   SP_FOR(i, sc.slots) sc.table[i] = kSplitEmpty;
   SP_FOR(i, sc.t2_slots) sc.t2_km[i] = kSplitEmpty;
   SP_FOR(i, split_cand_words(ref.n)) sc.cand[i] = 0;
-  SP_SYNC();
-  const uint32_t fsh = 6u + sc.pos_bits, pmask = (1u << sc.pos_bits) - 1u;
+  SP_SYNC(); ST(0);
+  const uint32_t fsh = 6u + sc.pos_bits, pmask = (1u << sc.pos_bits) - 1u, flim = 1u << fsh, kmask = (1u << (2 * k)) - 1u;
+  // k-mers of the three reads: two loads, a funnel shift and a mask when the read has at least k letters
+  const bool full0 = ref.n >= k, full1 = S1.n >= k, full2 = S2.n >= k;
+  auto vkmer = [&](const uint32_t *pk, int p) { return full0 ? split_kmer_full(pk, p, kmask) : split_kmer(pk, p, k, ref.n); };
   // 1. table of the reference k-mers (:176-193: an unordered_map with -1 for repeats)
-  SP_FOR(p, nr) {
-    const uint32_t km = split_kmer(sc.pk[0], p, k, ref.n), h = split_mix(km), want = (h >> 3) << fsh;
-    uint32_t s = split_mulhi(h, sc.slots);
-    for (;;) {
-      uint32_t cur = sc.table[s];
-      if (cur == kSplitEmpty) {
-        cur = sp_cas(&sc.table[s], kSplitEmpty, want | ((uint32_t)p << 6) | SF_R1);
-        if (cur == kSplitEmpty) break;
+  // (steps 1 and 2 are flat loops: a lane goes on to its next k-mer as soon as its own probe sequence ends, it does not wait for
+  // the longest sequence of its warp)
+  const uint32_t nbuckets = sc.slots >> 2;
+  {
+    int p = SP_FIRST;
+    bool fresh = true;
+    uint32_t km = 0, want = 0, mine = 0, b = 0;
+    while (p < nr) {
+      if (fresh) {
+        km = vkmer(sc.pk[0], p);
+        const uint32_t h = split_mix(km);
+        want = split_want(h, fsh); mine = want | ((uint32_t)p << 6) | SF_R1; b = split_mulhi(h, nbuckets);
+        fresh = false;
       }
-      if (((cur ^ want) >> fsh) == 0 && split_kmer(sc.pk[0], (int)((cur >> 6) & pmask), k, ref.n) == km) { if (!(cur & SF_R2)) sp_or(&sc.table[s], SF_R2); break; }
-      if (++s == sc.slots) s = 0;
+      const SplitBucket v = reinterpret_cast<const SplitBucket *>(sc.table)[b];
+      bool done = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (done) continue;
+        uint32_t cur = v.e[j];
+        if (cur == kSplitEmpty) {
+          cur = sp_cas(&sc.table[4u * b + (uint32_t)j], kSplitEmpty, mine);
+          if (cur == kSplitEmpty) { done = true; continue; }
+        }
+        if ((cur ^ want) < flim && vkmer(sc.pk[0], (int)((cur >> 6) & pmask)) == km) {
+          if (!(cur & SF_R2)) sp_or(&sc.table[4u * b + (uint32_t)j], SF_R2);
+          done = true;
+        }
+      }
+      if (done) { p += SP_STRIDE; fresh = true; }
+      else if (++b == nbuckets) b = 0;
     }
   }
-  SP_SYNC();
-  // 2. the other two reads (:194-230)
-  SP_FOR(p, na) {
-    const uint32_t s = split_find(sc, split_kmer(sc.pk[1], p, k, S1.n), k, ref.n);
-    if (s != kSplitEmpty && (sp_or(&sc.table[s], SF_A1) & SF_A1)) sp_or(&sc.table[s], SF_A2);
+  SP_SYNC(); ST(1);
+  // 2. the other two reads (:194-230), one index space: 0 .. na - 1 is S1, na .. na + nb - 1 is S2
+  {
+    const int total = na + nb;
+    int p = SP_FIRST;
+    bool fresh = true;
+    uint32_t km = 0, want = 0, fl = 0, b = 0;
+    while (p < total) {
+      if (fresh) {
+        const bool first = p < na;
+        km = first ? (full1 ? split_kmer_full(sc.pk[1], p, kmask) : split_kmer(sc.pk[1], p, k, S1.n))
+                   : (full2 ? split_kmer_full(sc.pk[2], p - na, kmask) : split_kmer(sc.pk[2], p - na, k, S2.n));
+        const uint32_t h = split_mix(km);
+        want = split_want(h, fsh); fl = first ? (uint32_t)SF_A1 : (uint32_t)SF_B1; b = split_mulhi(h, nbuckets);
+        fresh = false;
+      }
+      const SplitBucket v = reinterpret_cast<const SplitBucket *>(sc.table)[b];
+      int hit = -1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (hit < 0 && (v.e[j] ^ want) < flim && vkmer(sc.pk[0], (int)((v.e[j] >> 6) & pmask)) == km) hit = j;
+      if (hit >= 0) {
+        const uint32_t s = 4u * b + (uint32_t)hit;
+        if (sp_or(&sc.table[s], fl) & fl) sp_or(&sc.table[s], fl << 1);     // SF_A2 / SF_B2: seen again
+        p += SP_STRIDE; fresh = true;
+      } else if (v.e[3] == kSplitEmpty) { p += SP_STRIDE; fresh = true; }
+      else if (++b == nbuckets) b = 0;
+    }
   }
-  SP_FOR(p, nb) {
-    const uint32_t s = split_find(sc, split_kmer(sc.pk[2], p, k, S2.n), k, ref.n);
-    if (s != kSplitEmpty && (sp_or(&sc.table[s], SF_B1) & SF_B1)) sp_or(&sc.table[s], SF_B2);
-  }
-  SP_SYNC();
+  SP_SYNC(); ST(2);
   // 3. anchors in reference order: once in each read
   SP_FOR(s, sc.slots) {
     const uint32_t e = sc.table[s];
     if (e != kSplitEmpty && (e & SF_MASK) == SF_ONCE) { const uint32_t r = (e >> 6) & pmask; sp_or(&sc.cand[r >> 5], 1u << (r & 31)); }
   }
-  SP_SYNC();
+  SP_SYNC(); ST(3);
   // 4. left-to-right thinning (:242-251): position 0 is taken as it is; position j + 1 when j - last > min_size, last = j -- the
-  //    next anchor is the first candidate more than min_size after the last one (min_size + 1 after the start)
+  //    next anchor is the first candidate more than min_size after the last one (min_size + 1 after the start).  Every candidate
+  //    learns its successor in parallel (in the words of the table, which is dead now); one thread then only follows pointers.
+  const uint32_t cwords = (uint32_t)(nr + 31) >> 5;
+  int32_t *jump = reinterpret_cast<int32_t *>(sc.table);
+  auto first_from = [&](uint64_t pos) -> int32_t {             // first candidate at or after pos, -1 when there is none
+    if (pos >= (uint64_t)nr) return -1;
+    uint32_t w = (uint32_t)(pos >> 5);
+    uint32_t m = sc.cand[w] & (0xffffffffu << (pos & 31));
+    while (!m && ++w < cwords) m = sc.cand[w];
+    if (!m) return -1;
+    int b = 0;
+#ifdef __CUDA_ARCH__
+    b = __ffs((int)m) - 1;
+#else
+    while (!((m >> b) & 1u)) ++b;
+#endif
+    return (int32_t)(w * 32u) + b;
+  };
+  SP_FOR(w, cwords) {
+    uint32_t bits = sc.cand[w];
+    while (bits) {
+      int b = 0;
+#ifdef __CUDA_ARCH__
+      b = __ffs((int)bits) - 1;
+#else
+      while (!((bits >> b) & 1u)) ++b;
+#endif
+      bits &= bits - 1;
+      const int c = w * 32 + b;
+      jump[c] = first_from((uint64_t)c + min_size + 1u);
+    }
+  }
+  SP_SYNC(); ST(4);
   SP_SERIAL {
     int n = 0;
     bool over = false;
-    const uint32_t words = (uint32_t)(nr + 31) >> 5;
     if (sc.cand[0] & 1u) sc.anc[n++].r = 0;
-    uint64_t pos = (uint64_t)min_size + 2u;
-    uint32_t w = 0xffffffffu, bits = 0;
-    while (pos < (uint64_t)nr) {
-      const uint32_t pw = (uint32_t)(pos >> 5);
-      if (pw != w) { w = pw; bits = sc.cand[w]; }
-      uint32_t m = bits & (0xffffffffu << (pos & 31));
-      while (!m && ++w < words) { bits = sc.cand[w]; m = bits; }
-      if (!m) break;
-      int b = 0;
-#ifdef __CUDA_ARCH__
-      b = __ffs((int)m) - 1;
-#else
-      while (!((m >> b) & 1u)) ++b;
-#endif
-      const int p = (int)(w * 32u) + b;
+    int32_t p = first_from((uint64_t)min_size + 2u);
+    while (p >= 0) {
       if (n >= sc.max_anchors) { over = true; break; }
       sc.anc[n++].r = p;
-      pos = (uint64_t)p + min_size + 1u;
+      p = jump[p];
     }
     s_int[0] = over ? -1 : n;
   }
-  SP_SYNC();
+  SP_SYNC(); ST(5);
   const int n = s_int[0];
   if (n < 0) return -1;
-  // the anchors' k-mers go into the small table; the other two reads are looked up in it once more, for the positions
+  // the anchors' k-mers go into the small table; the other two reads are looked up in it once more, for the positions.  A one-hash
+  // Bloom bitmap (the words of the candidate bitmap, free now) answers most of those look-ups with one load.
+  const uint32_t bloom_bits = split_cand_words(ref.n) * 32u;
+  SP_FOR(i, split_cand_words(ref.n)) sc.cand[i] = 0;
+  SP_SYNC(); ST(6);
   SP_FOR(i, n) {
-    const uint32_t km = split_kmer(sc.pk[0], sc.anc[i].r, k, ref.n);
-    uint32_t s = split_mulhi(km * 0x9E3779B1u, sc.t2_slots);
+    const uint32_t km = split_kmer(sc.pk[0], sc.anc[i].r, k, ref.n), h = km * 0x9E3779B1u;
+    uint32_t s = split_mulhi(h, sc.t2_slots);
     while (sp_cas(&sc.t2_km[s], kSplitEmpty, km) != kSplitEmpty) { if (++s == sc.t2_slots) s = 0; }
     sc.t2_idx[s] = i;
+    const uint32_t bit = split_mulhi(h ^ (h >> 13), bloom_bits);
+    sp_or(&sc.cand[bit >> 5], 1u << (bit & 31));
     sc.anc[i].chain = 0;
   }
-  SP_SYNC();
+  SP_SYNC(); ST(7);
   for (int q = 1; q <= 2; ++q) {
     const int nq = q == 1 ? na : nb, lq = q == 1 ? S1.n : S2.n;
     SP_FOR(p, nq) {
-      const uint32_t km = split_kmer(sc.pk[q], p, k, lq);
-      uint32_t s = split_mulhi(km * 0x9E3779B1u, sc.t2_slots);
+      const uint32_t km = (q == 1 ? full1 : full2) ? split_kmer_full(sc.pk[q], p, kmask) : split_kmer(sc.pk[q], p, k, lq), h = km * 0x9E3779B1u;
+      const uint32_t bit = split_mulhi(h ^ (h >> 13), bloom_bits);
+      if (!((sc.cand[bit >> 5] >> (bit & 31)) & 1u)) continue;
+      uint32_t s = split_mulhi(h, sc.t2_slots);
       for (;;) {
         const uint32_t e = sc.t2_km[s];
         if (e == kSplitEmpty) break;
@@ -277,37 +385,67 @@ SP_HD int split_chain(const SplitScratch &sc, const SplitSeq &ref, const SplitSe
       }
     }
   }
-  SP_SYNC();
+  SP_SYNC(); ST(8);
   // 5. longest chain, backwards: chain[i] = 1 + max over the successors within reach (first maximum), 0 when there is none
 #ifdef __CUDA_ARCH__
+  const bool fast = (min_size + 1u) * 64u >= (uint32_t)kChainReach && 2u * (uint32_t)n <= sc.slots;
+  uint32_t *elig = sc.table;                                   // bit j of anchor i's 64: anchor i + 1 + j may follow it (:86-88)
+  if (fast) {
+    const int total = n * 64, lane_ = threadIdx.x & 31;
+    for (int t = threadIdx.x; t - lane_ < total; t += blockDim.x) {
+      const int i = t >> 6, c = i + 1 + (t & 63);
+      bool ok = false;
+      if (t < total && c < n) {
+        const SplitAnchor me = sc.anc[i], o = sc.anc[c];
+        const int da = o.a - me.a, db = o.b - me.b;
+        ok = o.r - me.r < kChainReach && da > 0 && da < kChainReach && db > 0 && db < kChainReach;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (lane_ == 0 && t < total) elig[t >> 5] = m;
+    }
+    __syncthreads();
+  }
+  if (fast) {
+    // at most 63 successors are within reach and their eligibility (a pure function of the positions) is in the masks.  Blocks of
+    // 32 anchors from the end, lane l = anchor b + l: first the whole CTA takes, for every anchor of the block, the maximum over its
+    // successors BEHIND the block (their chain lengths are final), then one warp settles the block from its last anchor down -- one
+    // shuffle per anchor hands its final length to the lanes before it.  key = (chain length of the successor + 1) << 6 |
+    // (63 - distance): the maximum is the longest chain and, among equals, the nearest successor (the reference's first strict
+    // maximum).
+    const uint2 *elig2 = reinterpret_cast<const uint2 *>(elig);
+    unsigned *skey = reinterpret_cast<unsigned *>(sc.t2_km);                // 32 words of the small table (free during the DP)
+    if (threadIdx.x < 32) skey[threadIdx.x] = 0;
+    __syncthreads();
+    for (int b = ((n - 1) >> 5) << 5; b >= 0; b -= 32) {
+      const int cend = b + 95 < n ? b + 95 : n, span = cend - (b + 32);
+      for (int t = threadIdx.x; t < span * 32; t += blockDim.x) {           // a warp = one successor c, its lanes = the block's anchors
+        const int c = b + 32 + (t >> 5), l = t & 31, i = b + l;
+        const unsigned off = (unsigned)(c - i - 1);
+        if (i < n && off < 63u) {
+          const uint2 e = elig2[i];
+          if (((off < 32u ? e.x >> off : e.y >> (off - 32u)) & 1u)) atomicMax(&skey[l], ((unsigned)(sc.anc[c].chain + 1) << 6) | (63u - off));
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, i = b + lane;
+        const unsigned ex = i < n ? elig2[i].x : 0u;
+        unsigned key = skey[lane];
+        for (int t = 31; t >= 1; --t) {
+          const unsigned vt = __shfl_sync(0xffffffffu, key >> 6, t) + 1u;    // final: every anchor behind b + t has been seen
+          const unsigned off = (unsigned)(t - lane - 1);
+          const unsigned cand = (vt << 6) | (63u - off);
+          if (lane < t && ((ex >> off) & 1u) && cand > key) key = cand;
+        }
+        if (i < n) { sc.anc[i].chain = (int)(key >> 6); sc.nxt[i] = key ? i + 1 + 63 - (int)(key & 63u) : -1; }
+        skey[lane] = 0;
+      }
+      __syncthreads();
+    }
+  }
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    if ((min_size + 1u) * 64u >= (uint32_t)kChainReach) {
-      // at most 64 successors are within reach: they stay in registers, lane l holds the anchors whose index is l modulo 32
-      // (e0 the nearer one), and a step replaces the anchor that has just left the reach by the one that has just been finished
-      SplitAnchor e0{0x3fffffff, 0, 0, 0}, e1{0x3fffffff, 0, 0, 0};
-      int i0x = 0x3fffffff;                                      // index of e0; e1 is 32 further
-      SplitAnchor me = n > 0 ? sc.anc[n - 1] : e0;
-      for (int i = n - 1; i >= 0; --i) {
-        const SplitAnchor nextme = i > 0 ? sc.anc[i - 1] : me;
-        unsigned key = 0;
-        {
-          const int da = e0.a - me.a, db = e0.b - me.b;
-          if (e0.r - me.r < kChainReach && da > 0 && da < kChainReach && db > 0 && db < kChainReach) key = ((unsigned)(e0.chain + 1) << 6) | (unsigned)(63 - (i0x - i - 1));
-        }
-        {
-          const int da = e1.a - me.a, db = e1.b - me.b;
-          if (e1.r - me.r < kChainReach && da > 0 && da < kChainReach && db > 0 && db < kChainReach) {
-            const unsigned k1 = ((unsigned)(e1.chain + 1) << 6) | (unsigned)(31 - (i0x - i - 1));
-            key = k1 > key ? k1 : key;
-          }
-        }
-        const unsigned top = __reduce_max_sync(0xffffffffu, key);
-        const int best = top ? (int)(top >> 6) - 1 : -1, arg = top ? i + 1 + 63 - (int)(top & 63u) : -1;
-        if (lane == (i & 31)) { e1 = e0; e0 = me; e0.chain = 1 + best; i0x = i; sc.anc[i].chain = 1 + best; sc.nxt[i] = arg; }
-        me = nextme;
-      }
-    } else {
+    if (!fast) {
       for (int i = n - 1; i >= 0; --i) {
         const SplitAnchor me = sc.anc[i];
         int best = -1, arg = -1;
@@ -340,10 +478,10 @@ SP_HD int split_chain(const SplitScratch &sc, const SplitSeq &ref, const SplitSe
     for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, top, d); if (o > top) top = o; }
     if (lane == 0) s_int[1] = top ? 0x7fffffff - (int)(unsigned)(top & 0xffffffffu) : -1;
   }
-  SP_SYNC();
+  SP_SYNC(); ST(9);
   // the chain from there, by pointer doubling: round r places the anchors 2^r .. 2^(r+1) - 1 steps down the chain
   SP_FOR(i, n) sc.t2_idx[i] = sc.nxt[i];
-  SP_SYNC();
+  SP_SYNC(); ST(10);
   const int at = s_int[1];
   const int len = at < 0 ? 0 : sc.anc[at].chain + 1;
   if (len > 0) {
@@ -358,6 +496,7 @@ SP_HD int split_chain(const SplitScratch &sc, const SplitSeq &ref, const SplitSe
       int32_t *t = jc; jc = jn; jn = t;
     }
   }
+  ST(11);
   return len;
 #else
   for (int i = n - 1; i >= 0; --i) {
@@ -386,30 +525,61 @@ SP_HD int split_chain(const SplitScratch &sc, const SplitSeq &ref, const SplitSe
 SP_HD void split_walk(const SplitScratch &sc, int i0, int i1, int k, uint32_t ms, int off_r, int off_a, int off_b, bool with_b, int &qr, int &qa, int &qb, SplitWin *out,
                       int out_cap, int &n, int *s_int) {
 #ifdef __CUDA_ARCH__
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    int cr = qr, ca = qa, cb = qb, cn = n;
-    for (int base = i0; base < i1; base += 32) {
-      const int idx = base + lane;
-      const bool valid = idx < i1;
-      const SplitAnchor an = sc.anc[valid ? sc.bl[idx] : sc.bl[i0]];
-      unsigned todo = __ballot_sync(0xffffffffu, valid);
-      while (todo) {
-        const int zr = an.r - cr, za = an.a - ca, zb = an.b - cb;
-        const unsigned m = __ballot_sync(0xffffffffu, split_cut_ok(zr, za, zb, ms)) & todo;
-        if (!m) break;
-        const int j = __ffs((int)m) - 1;
-        if (lane == j && cn < out_cap) out[cn] = SplitWin{off_r + cr, zr + k, off_a + ca, za + k, with_b ? off_b + cb : 0, with_b ? zb + k : 0};
-        ++cn;
-        cr = __shfl_sync(0xffffffffu, an.r, j) + k; ca = __shfl_sync(0xffffffffu, an.a, j) + k; cb = __shfl_sync(0xffffffffu, an.b, j) + k;
-        todo &= ~((2u << j) - 1u);
-      }
-    }
-    if (lane == 0) { s_int[2] = cn; s_int[3] = cr; s_int[8] = ca; s_int[9] = cb; }
+  // On the device the walk is not walked: every chain anchor learns in parallel where the next cut would be if a cut were made at
+  // it; the cuts of the walk are then the anchors reachable from the first cut -- marked by pointer doubling, compacted in index
+  // order (the pointers only go forward) -- and every record is written by its own thread.
+  const int m = i1 - i0;
+  if (m <= 0) return;
+  SplitAnchor *ca = reinterpret_cast<SplitAnchor *>(sc.table);             // the chain's anchors in chain order (the table is dead)
+  int32_t *mark = reinterpret_cast<int32_t *>(sc.table) + 4 * (size_t)m, *acc = mark + m;
+  int32_t *jc = sc.t2_idx, *jn = reinterpret_cast<int32_t *>(sc.t2_km);
+  SP_FOR(i, m) { ca[i] = sc.anc[sc.bl[i0 + i]]; mark[i] = 0; }
+  if (threadIdx.x == 0) s_int[2] = 0x7fffffff;
+  SP_SYNC();
+  SP_FOR(i, m) {
+    const SplitAnchor me = ca[i];
+    if (split_cut_ok(me.r - qr, me.a - qa, me.b - qb, ms)) atomicMin(&s_int[2], i);
+    const int pr = me.r + k, pa = me.a + k, pb = me.b + k;
+    int j = i + 1;
+    for (; j < m; ++j) { const SplitAnchor o = ca[j]; if (split_cut_ok(o.r - pr, o.a - pa, o.b - pb, ms)) break; }
+    jc[i] = j < m ? j : -1;
   }
   SP_SYNC();
-  n = s_int[2]; qr = s_int[3]; qa = s_int[8]; qb = s_int[9];
+  const int first = s_int[2];
   SP_SYNC();
+  if (first == 0x7fffffff) return;                                          // no anchor ends a record
+  if (threadIdx.x == 0) mark[first] = 1;
+  SP_SYNC();
+  for (int span = 1; span < m; span <<= 1) {
+    SP_FOR(i, m) { const int t = jc[i]; if (t >= 0 && mark[i]) mark[t] = 1; jn[i] = t < 0 ? -1 : jc[t]; }
+    SP_SYNC();
+    int32_t *t = jc; jc = jn; jn = t;
+  }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int count = 0;
+    for (int base = 0; base < m; base += 32) {
+      const bool on = base + lane < m && mark[base + lane];
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      if (on) acc[count + __popc(bal & ((1u << lane) - 1u))] = base + lane;
+      count += __popc(bal);
+    }
+    if (lane == 0) s_int[3] = count;
+  }
+  SP_SYNC();
+  const int cuts = s_int[3];
+  SP_FOR(t, cuts) {
+    const SplitAnchor cur = ca[acc[t]];
+    int sr = qr, sa = qa, sb = qb;
+    if (t > 0) { const SplitAnchor prev = ca[acc[t - 1]]; sr = prev.r + k; sa = prev.a + k; sb = prev.b + k; }
+    if (n + t < out_cap) out[n + t] = SplitWin{off_r + sr, cur.r - sr + k, off_a + sa, cur.a - sa + k, with_b ? off_b + sb : 0, with_b ? cur.b - sb + k : 0};
+  }
+  {
+    const SplitAnchor last = ca[acc[cuts - 1]];
+    qr = last.r + k; qa = last.a + k; qb = last.b + k;
+    n += cuts;
+  }
+  SP_SYNC(); ST(12);
 #else
   (void)s_int;
   for (int i = i0; i < i1; ++i) {
@@ -446,7 +616,7 @@ SP_HD int split_job(const SplitScratch &sc, const SplitScratch &sc2, SplitSeq re
     if ((long long)lb * 2 < lr && (unsigned)(lr - lb) > 200u) {
       // the corrected read starts late: reference and uncorrected prefix are cut on their own (S2 := the reference prefix),
       // with a minimum window of 1.2 x the corrected prefix; the corrected side gets N records and its prefix last (:268-277)
-      const SplitSeq pr{ref.s, lr}, pa{S1.s, la};
+      const SplitSeq pr{ref.s, lr, ref.pk, ref.g}, pa{S1.s, la, S1.pk, S1.g};
       const uint32_t ms = (uint32_t)(1.2 * (double)lb);
       const int bl2 = split_chain(sc2, pr, pa, pr, k, ms, s_int + 4);
       if (bl2 < 0) return -1;
@@ -471,7 +641,7 @@ SP_HD int split_job(const SplitScratch &sc, const SplitScratch &sc2, SplitSeq re
     const int er = ref.n - pred_r, ea = S1.n - pred_a, eb = S2.n - pred_b;
     if ((long long)eb * 2 < er && (unsigned)(er - eb) > 200u) {
       // the corrected read ends early (:295-301): the corrected side gets its tail first, then N records
-      const SplitSeq pr{ref.s + pred_r, er}, pa{S1.s + pred_a, ea};
+      const SplitSeq pr{ref.s + pred_r, er, ref.pk, ref.g + pred_r}, pa{S1.s + pred_a, ea, S1.pk, S1.g + pred_a};
       const uint32_t ms = (uint32_t)(1.2 * (double)eb);
       const int bl2 = split_chain(sc2, pr, pa, pr, k, ms, s_int + 4);
       if (bl2 < 0) return -1;
@@ -504,6 +674,8 @@ struct SplitArgs {
   const int32_t *header_len;
   const int32_t *status_in;     // 1: corrected read shorter than the threshold share of the reference (no job)
   const int32_t *order;         // triplets by falling length (the longest jobs start first), or null
+  const uint32_t *pk[3];        // the letters of the call at 2 bits each (split_prepack_kernel), or null; letter let[q][i] is letter i - base[q] there
+  int64_t base[3];
   // scratch: the job's arrays live in the CTA's dynamic shared memory (smem_words) when they fit, with as many anchors for the
   // sub-calls as for the job itself; a job that does not fit, or whose sub-call finds more anchors than that, runs in the CTA's
   // share of the pool in global memory (cta_words; sub_anchors anchors for the sub-calls)
@@ -513,6 +685,24 @@ struct SplitArgs {
   int32_t *job_n; uint32_t *job_largest;
   int32_t *counter;
 };
+
+// the letters of one kind at 2 bits each, coded like nuc2int (:35-43): the four jobs of a triplet read these words instead of
+// coding the bytes four times.  let: 16-byte aligned; one thread per word of 16 letters.
+__global__ void __launch_bounds__(256) split_prepack_kernel(const uint8_t *let, int64_t n_letters, uint32_t *pk, int64_t n_words) {
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    const int64_t t0 = 16 * w;
+    if (t0 + 16 <= n_letters) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(let + t0);
+      const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const uint32_t c = (x[j >> 2] >> (8 * (j & 3))) & 0xffu; v |= (c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u) << (2 * j); }
+    } else {
+      for (int64_t t = t0; t < n_letters; ++t) { const uint32_t c = let[t]; v |= (c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u) << (2 * (int)(t - t0)); }
+    }
+    pk[w] = v;
+  }
+}
 
 // persistent CTAs; a job = (triplet, k)
 __global__ void __launch_bounds__(1024, 1) split_jobs_kernel(SplitArgs a) {
@@ -526,12 +716,16 @@ __global__ void __launch_bounds__(1024, 1) split_jobs_kernel(SplitArgs a) {
     const int64_t job = s_job;
     __syncthreads();
     if (job >= 4 * a.n_triplets) break;
+#ifdef SPLIT_TIMING
+    if (threadIdx.x == 0) *reinterpret_cast<long long *>(s_int + 12) = clock64();
+#endif
     const int64_t t = a.order ? (int64_t)a.order[job >> 2] : job >> 2;
     const int ki = (int)(job & 3), k = 15 - 2 * ki;
     const int64_t slot = 4 * t + ki;
     if (a.status_in[t]) { if (threadIdx.x == 0) { a.job_n[slot] = 0; a.job_largest[slot] = 0; } continue; }
-    const SplitSeq ref{a.let[0] + a.off[0][t], (int)(a.off[0][t + 1] - a.off[0][t])}, S1{a.let[1] + a.off[1][t], (int)(a.off[1][t + 1] - a.off[1][t])},
-        S2{a.let[2] + a.off[2][t], (int)(a.off[2][t + 1] - a.off[2][t])};
+    const SplitSeq ref{a.let[0] + a.off[0][t], (int)(a.off[0][t + 1] - a.off[0][t]), a.pk[0], a.off[0][t] - a.base[0]},
+        S1{a.let[1] + a.off[1][t], (int)(a.off[1][t + 1] - a.off[1][t]), a.pk[1], a.off[1][t] - a.base[1]},
+        S2{a.let[2] + a.off[2][t], (int)(a.off[2][t + 1] - a.off[2][t]), a.pk[2], a.off[2][t] - a.base[2]};
     const int32_t ma = split_anchor_bound(ref.n, 20);
     const int nb = S2.n > ref.n ? S2.n : ref.n;
     const int64_t cap = (a.win_off[t + 1] - a.win_off[t]) >> 2;
@@ -554,6 +748,7 @@ __global__ void __launch_bounds__(1024, 1) split_jobs_kernel(SplitArgs a) {
     if (mine > 0) atomicMax(&s_int[10], mine);
     __syncthreads();
     if (threadIdx.x == 0) { a.job_n[slot] = n < 0 ? -1 : n; a.job_largest[slot] = (uint32_t)s_int[10]; }
+    ST(13);
   }
 }
 

@@ -27,8 +27,21 @@ int main(int argc, char **argv) {
   size_t longest = 0;
   for (size_t t = 0; t < batch.n(); ++t) for (int q = 0; q < 3; ++q) longest = std::max(longest, (size_t)batch.len(q, t));
   HostScratch hs(longest, getenv("SPLIT_EMUL_TIGHT") != nullptr);
+  // SPLIT_EMUL_PACKED: the reads come from letters packed once at 2 bits each, like split_prepack_kernel leaves them on the device
+  std::vector<uint32_t> packed[3];
+  if (getenv("SPLIT_EMUL_PACKED"))
+    for (int q = 0; q < 3; ++q) {
+      packed[q].assign(batch.letters[q].size() / 16 + 3, 0u);
+      for (size_t t = 0; t < batch.letters[q].size(); ++t) {
+        const uint8_t c = batch.letters[q][t];
+        packed[q][t >> 4] |= (c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u) << (2 * (t & 15));
+      }
+    }
   for (size_t t = 0; t < batch.n(); ++t) {
-    const SplitSeq ref{batch.seq(0, t), batch.len(0, t)}, S1{batch.seq(1, t), batch.len(1, t)}, S2{batch.seq(2, t), batch.len(2, t)};
+    SplitSeq ref{batch.seq(0, t), batch.len(0, t)}, S1{batch.seq(1, t), batch.len(1, t)}, S2{batch.seq(2, t), batch.len(2, t)};
+    if (!packed[0].empty()) {
+      ref.pk = packed[0].data(); ref.g = batch.off[0][t]; S1.pk = packed[1].data(); S1.g = batch.off[1][t]; S2.pk = packed[2].data(); S2.g = batch.off[2][t];
+    }
     choice[t].status = 0;
     if (!((double)S2.n / ref.n >= cli.threshold)) { choice[t].status = 1; continue; }
     hs.fit(ref.n, S1.n, std::max(S2.n, ref.n));

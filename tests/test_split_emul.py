@@ -63,6 +63,21 @@ def test_emulated_cutting_of_the_example_equals_reference_md5(split_emul_bin, tm
 
 
 @pytest.mark.skipif(not os.path.exists(REF_SPLITTER), reason="oracle/_ref/masterSplitter not built")
+@pytest.mark.parametrize("mode", ["SPLIT_EMUL_TIGHT", "SPLIT_EMUL_PACKED"])
+def test_emulated_cutting_with_the_fullest_table_and_with_packed_letters(split_emul_bin, tmp_path, mode, monkeypatch):
+    """the two shapes the kernel runs in that the default emulation does not: the smallest table it accepts, and reads taken from the
+    letters packed once per call (split_prepack_kernel) -- config 2 has N placeholders, trimmed and split reads (sub-strings at odd offsets)"""
+    import workloads
+    monkeypatch.setenv(mode, "1")
+    pre = str(tmp_path / "r")
+    subprocess.check_call([workloads.ensure_gen(), "2", "120", "0", pre])
+    files = [pre + ".ref.fa", pre + ".unc.fa", pre + ".cor.fa"]
+    a, b = str(tmp_path / "ref"), str(tmp_path / "emu")
+    assert run_splitter(REF_SPLITTER, files, a) == run_splitter(split_emul_bin, files, b) == 0
+    compare_dirs(a, b)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SPLITTER), reason="oracle/_ref/masterSplitter not built")
 @pytest.mark.parametrize("cfg,reads,amount,thr", [(1, 60, 10000, "0.1"), (2, 150, 10000, "0.1"), (3, 6, 10000, "0.1"), (4, 200, 10000, "0.1"),
                                                   (2, 150, 60, "0.4"), (4, 120, 50, "0.9")])
 def test_emulated_cutting_equals_compiled_reference_on_synthetic_reads(split_emul_bin, tmp_path, cfg, reads, amount, thr):
