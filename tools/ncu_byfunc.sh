@@ -5,7 +5,7 @@
 #   ${TAG}_src_summary.csv / ${TAG}_src_stalls.txt : per-launch summary and stall reasons of the same capture
 set +e
 O=gpurun_out; TAG=${1:-r2a}; FILTER=${2:-regex:poa_dp[12]_kernel}; COUNT=${3:-9}; READS=${4:-10000}; mkdir -p $O
-export ELECTOR_PIPELINE_CHUNKS=1 ELECTOR_PIPELINE_WORKERS=1
+export ELECTOR_PIPELINE_CHUNKS=1 ELECTOR_PIPELINE_WORKERS=1 ELECTOR_SERVICE=0   # (the executables run in process: ncu follows no server)
 python -c "import elector_b200; elector_b200.write_default_matrix('/tmp/blosum80.mat')"
 [ -f /tmp/prof$READS.ref.fa ] || python tools/dump_fasta.py $READS 1 /tmp/prof$READS
 timeout 1200 ncu --set full --clock-control none --import-source on -k $FILTER -c $COUNT -o /tmp/${TAG}_src -f elector_b200/bin/poa -pir /tmp/prof$READS.pir -corrected_reads_fasta /tmp/prof$READS.cor.fa -reference_reads_fasta /tmp/prof$READS.ref.fa -uncorrected_reads_fasta /tmp/prof$READS.unc.fa -pathMatrix /tmp/blosum80.mat > /dev/null

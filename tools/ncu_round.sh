@@ -9,7 +9,7 @@ set +e
 O=gpurun_out; TAG=${1:-r1d}; mkdir -p $O
 exec > $O/${TAG}_ncu.log 2>&1
 # the profiled calls run in ONE chunk on one worker, like the device-resident step bench.py's `value` and roofline time
-export ELECTOR_PIPELINE_CHUNKS=1 ELECTOR_PIPELINE_WORKERS=1
+export ELECTOR_PIPELINE_CHUNKS=1 ELECTOR_PIPELINE_WORKERS=1 ELECTOR_SERVICE=0   # (the executables run in process: ncu follows no server)
 python -c "import elector_b200; elector_b200.write_default_matrix('/tmp/blosum80.mat')"
 for R in 10000 2000; do python tools/dump_fasta.py $R 1 /tmp/prof$R; done
 cmd() { echo "elector_b200/bin/poa -pir /tmp/prof$1.pir -corrected_reads_fasta /tmp/prof$1.cor.fa -reference_reads_fasta /tmp/prof$1.ref.fa -uncorrected_reads_fasta /tmp/prof$1.unc.fa -pathMatrix /tmp/blosum80.mat"; }
