@@ -487,6 +487,7 @@ int run_device(elector_ctx *ctx, int64_t n, const char *d_ref, const int64_t *d_
   a.ref = (const uint8_t *)d_ref; a.cor = (const uint8_t *)d_cor; a.unc = (const uint8_t *)d_unc;
   a.ref_off = d_roff; a.cor_off = d_coff; a.unc_off = d_uoff;
   a.match = ctx->sc.match; a.mismatch = ctx->sc.mismatch; a.open = ctx->sc.open; a.ext = ctx->sc.ext;
+  { Scoring pk; pk.set(a.match, a.mismatch, a.open, a.ext); a.mis2 = pk.mis2; a.nopen2 = pk.nopen2; a.ext2 = pk.ext2; }
   a.ro0 = tot[2]; a.co0 = tot[3];
   a.p1_nodes = ctx->d_p1.as<uint16_t>(); a.n1 = ctx->d_n1.as<int32_t>(); a.key2 = ctx->d_key2.as<int32_t>();
   a.hist2 = hist2; a.seg2_max = dtab2->seg_max;

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp2_coop_kernel(Poa
   c.bset = s_bset + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
+  c.sc.mis2 = a.mis2; c.sc.nopen2 = a.nopen2; c.sc.ext2 = a.ext2;
   c.Lp = &s_layout;
   for (;;) {
     int base = 0;
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(32, EL_MIN_WARPS_COOP) poa_dp1_coop_kernel(Poa
   c.bset = s_bset + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
+  c.sc.mis2 = a.mis2; c.sc.nopen2 = a.nopen2; c.sc.ext2 = a.ext2;
   c.Lp = &s_layout.l2;
   for (;;) {
     int base = 0;

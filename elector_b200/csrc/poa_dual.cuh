@@ -1,4 +1,4 @@
-// poa_dual.cuh -- DP2 of the GENERAL windows (ref and cor differ) without frontier-set juggling.
+// poa_dual.cuh -- DP2 of the GENERAL windows (ref and cor differ) without frontier-set juggling, two cells per instruction.
 //
 // P1 is the partial order of two sequences: every node has its predecessor on the ref path (the latest
 // ref-carrying node), on the cor path (the latest cor-carrying node), or both.  Phase2 (poa_kernel.cuh)
@@ -6,146 +6,201 @@
 // out of line whenever a node needs the other frontier -- the whole warp waits each time one lane does
 // (profiles/r1c_ncu_dp2_int32_by_function.txt: 43 % of the kernel's instructions, the column update 37 %).
 //
-// Here the two halves of every 16-bit packed register ARE the two frontiers: the low half holds the column
-// of the latest ref-carrying node, the high half the column of the latest cor-carrying node (both start as
-// the virtual column -1, align_lpo_po2.c:272-302).  A node then is one straight-line packed update:
-//   * a node carrying both letters updates both halves (after a merge, below, they are equal and stay so);
-//   * a ref-only node updates the low half and keeps the high half (one bit-select per register), a cor-only
-//     node the other way round -- no data moves, no branch;
-//   * only a both-node that FOLLOWS a one-letter node (the end of a bubble) takes the maximum of the two
-//     halves first: the first strict maximum over its left list (align_lpo_po2.c:334-371), which is
-//     [ref predecessor, cor predecessor], or [virtual -1, the one real predecessor] for an INITIAL node --
-//     the half that is still the virtual column then plays the virtual link.  One VIMNMX.S16x2 on (x, x with
-//     swapped halves) yields the maximum in both halves and both strict comparisons as predicates; the
-//     winning predecessor ordinals go to the ordinal words the traceback of Phase2 reads.
+// Here both frontiers live in registers all the time, as two register sets: Sr/Gr hold the column of the latest
+// ref-carrying node, Sc/Gc the column of the latest cor-carrying node (both start as the virtual column -1,
+// align_lpo_po2.c:272-302).  The two 16-bit halves of a register are two ROWS of that column, skewed like the bands of
+// poa_packed.cuh: a band of 2R rows, the low half holds row r0 + k and works on node j, the high half holds row
+// r0 + R + k and works on node j - 1 (its first row takes "up" and "diagonal" from the low half's last row of the
+// iteration before).  A node then is one straight-line packed update, 2 cells per instruction:
+//   * the input column is picked per half by a bit-select (the ref frontier for a node carrying a ref letter, else the cor
+//     one), the result is written back, again by bit-selects, to the frontier(s) of the letters the node carries: a node
+//     with both letters replaces both, a one-letter node replaces its own and keeps the other -- no data moves, no branch;
+//   * only a both-node that FOLLOWS a one-letter node (the end of a bubble) first takes the maximum of the two frontiers:
+//     the first strict maximum over its left list (align_lpo_po2.c:334-371), which is [ref predecessor, cor predecessor],
+//     or [virtual -1, the one real predecessor] for an INITIAL node -- the frontier that is still the virtual column then
+//     plays the virtual link.  Two VIMNMX.S16x2 (a, b) / (b, a) yield the maximum and both strict comparisons as
+//     predicates; the winning predecessor ordinals go to the ordinal words the traceback of Phase2 reads.  The low half
+//     of a node merges in iteration j, its high half in iteration j + 1 (the ordinals of the low rows wait in registers).
+// (Round 1 kept the two frontiers in the two HALVES of one register set: one cell per instruction, 13 instructions per
+// cell against 17 per pair of cells here.)
 // Arithmetic, bias and matrix class are those of poa_packed.cuh (exact for packed_ok() matrices and scores
-// that stay inside 16 bits; everything else runs Phase2).  Node records, moves words, ordinals, traceback,
-// fuse and emit are Phase2's: only the band sweep differs.
+// that stay inside 16 bits; everything else runs Phase2).  Node records (the boundary row S | G << 16 in ONE word), moves
+// words, ordinals, traceback, fuse and emit are Phase2's: only the band sweep differs.
 #pragma once
 #include "poa_kernel.cuh"
 #include "poa_packed.cuh"
 
 namespace elector {
 
-// per-half signed max(a, b); ORs bit into mv_lo / mv_hi where b beats a (b > a) in the low / high half
-EL_HD uint32_t pk_maxs_flag2(uint32_t a, uint32_t b, uint32_t &mv_lo, uint32_t &mv_hi, uint32_t bit) {
+EL_HD uint32_t pk_select(uint32_t fresh, uint32_t old, uint32_t take) { return (fresh & take) | (old & ~take); }   // one LOP3
+// PRMT: result byte i = byte (sel >> 4i & 7) of {a: 0-3, b: 4-7}, or that byte's sign bit replicated when bit 3 of the nibble is set
+EL_HD uint32_t pk_prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #ifdef __CUDA_ARCH__
-  uint32_t val;
-  asm("{.reg .pred pu, pv;\n\t"
-      ".reg .s16 rs0, rs1, rs2, rs3;\n\t"
-      "max.s16x2 %0, %3, %4;\n\t"
-      "mov.b32 {rs0, rs1}, %0;\n\t"
-      "mov.b32 {rs2, rs3}, %3;\n\t"
-      "setp.eq.s16 pv, rs0, rs2;\n\t"
-      "setp.eq.s16 pu, rs1, rs3;\n\t"
-      "@!pv or.b32 %1, %1, %5;\n\t"
-      "@!pu or.b32 %2, %2, %5;}\n\t"
-      : "=&r"(val), "+r"(mv_lo), "+r"(mv_hi) : "r"(a), "r"(b), "r"(bit));   // early clobber: a is read after val is written
-  return val;
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));   // (__byte_perm drops the replicate bit)
+  return r;
 #else
-  const int16_t al = (int16_t)(a & 0xffffu), bl = (int16_t)(b & 0xffffu), ah = (int16_t)(a >> 16), bh = (int16_t)(b >> 16);
-  if (bl > al) mv_lo |= bit;
-  if (bh > ah) mv_hi |= bit;
-  return (uint32_t)(uint16_t)(al >= bl ? al : bl) | ((uint32_t)(uint16_t)(ah >= bh ? ah : bh) << 16);
+  const uint64_t ab = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t n = (sel >> (4 * i)) & 0xfu;
+    uint32_t byte = (uint32_t)(ab >> (8 * (n & 7u))) & 0xffu;
+    if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+    r |= byte << (8 * i);
+  }
+  return r;
 #endif
 }
-EL_HD uint32_t pk_swap(uint32_t x) { return (x >> 16) | (x << 16); }
-EL_HD uint32_t pk_both(uint32_t half) { return (half & 0xffffu) * 0x00010001u; }          // a 16-bit value in both halves
-EL_HD uint32_t pk_select(uint32_t fresh, uint32_t old, uint32_t keep) { return (fresh & ~keep) | (old & keep); }   // one LOP3
+
+// shape word of a node (record field R2_BG, free in this kernel), made by the node preparation so that the band loop
+// derives everything it needs per node with one PRMT each: bit 7 = carries a ref letter, bit 15 = carries a cor letter,
+// bit 23 = closes a bubble (a both-node after a one-letter node: exactly the nodes with an ordinal slot, NF_VIRT | NF_TWO),
+// byte 3 = the letter code, bit 0 = NF_FINAL
+enum : uint32_t { NM_REF = 1u << 7, NM_COR = 1u << 15, NM_MERGE = 1u << 23, NM_FINAL = 1u };
 
 struct Phase2D : Phase2<false> {
   static constexpr int kSetWords = 1;   // no frontier sets in shared memory
-  // boundary rows live in the node records in packed form: the biased value in both halves
-  static EL_HD void put_row0(uint32_t *p, int bS, int bG) { p[R2_BS * 32] = pk_both((uint32_t)(kBiasP + bS)); p[R2_BG * 32] = pk_both((uint32_t)(kBiasP + bG)); }
+  // boundary rows live in the node records in packed form: biased S in the low half, biased G in the high half of R2_BS
+  static EL_HD void put_row0(uint32_t *p, int bS, int bG) { p[R2_BS * 32] = pk2(kBiasP + bS, kBiasP + bG); }
+  static EL_HD void put_shape(uint32_t *p, uint32_t ra) {
+    p[R2_BG * 32] = ((ra & NF_REF) ? NM_REF : 0u) | ((ra & NF_COR) ? NM_COR : 0u) | ((ra & (NF_VIRT | NF_TWO)) ? NM_MERGE : 0u) |
+                    ((ra & NF_FINAL) ? NM_FINAL : 0u) | ((ra & 0xffu) << 24);
+  }
   EL_HDN int prepare(const uint16_t *nodes, int nx) const { return prepare_nodes(*this, nodes, nx); }
 
-  // one band of R rows of DP2 (align_lpo_po2.c:269-433)
+  // the ref set := per-half maximum of the two frontiers in the halves of `take`; ORs a 1 into the ordinal words where the
+  // SECOND entry of the left list wins (strictly): the cor frontier, or the ref frontier when REF_SECOND
+  template <int R, bool REF_SECOND>
+  static EL_HD void merge(uint32_t (&Sr)[R], uint32_t (&Gr)[R], const uint32_t (&Sc)[R], const uint32_t (&Gc)[R], uint32_t &hr, uint32_t hc,
+                          uint32_t take, uint32_t &oM, uint32_t &oX) {
+    const uint32_t hm = REF_SECOND ? pk_maxs_flag(hc, hr, oM, 1u, 0u) : pk_maxs_flag(hr, hc, oM, 1u, 0u);
+    if (take & 0xffffu) hr = hm;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const uint32_t bMl = 4u << (2 * k), bMh = R + k + 1 < kBand ? 4u << (2 * (R + k)) : 0u;   // the match of the NEXT row starts from this cell
+      const uint32_t bXl = 1u << (2 * k), bXh = 1u << (2 * (R + k));
+      const uint32_t ms = REF_SECOND ? pk_maxs_flag(Sc[k], Sr[k], oM, bMl, bMh) : pk_maxs_flag(Sr[k], Sc[k], oM, bMl, bMh);
+      const uint32_t mx = REF_SECOND ? pk_maxs_flag(Gc[k], Gr[k], oX, bXl, bXh) : pk_maxs_flag(Gr[k], Gc[k], oX, bXl, bXh);
+      Sr[k] = pk_select(ms, Sr[k], take);
+      Gr[k] = pk_select(mx, Gr[k], take);
+    }
+  }
+
+  // one band of 2R rows of DP2 (align_lpo_po2.c:269-433).  Moves words: row rr of the band at bits 2 * (15 - rr) (+1: match);
+  // ordinal words: the match ordinal of row rr at bits 2 * rr of po[0] (the S cell of row rr - 1 decides it), the X-gap
+  // ordinal of row rr at bits 2 * rr of po[32] -- the formats Phase2::traceback reads.
   template <int R>
   EL_HDN void band(int nx, int ly, int b, bool last, int &best, int &best_j) const {
+    constexpr uint32_t kLowMoves = ~0u << (32 - 2 * R);        // moves bits of the low half's rows (0 .. R-1)
+    constexpr uint32_t kLowOrdM = (4u << (2 * R)) - 1u;        // match ordinals decided by the low half: rows 0 .. R
+    constexpr uint32_t kLowOrdX = (1u << (2 * R)) - 1u;        // X-gap ordinals of rows 0 .. R-1
     const int r0 = b * kBand;
     PackedConsts pc;
     pc.set(sc);
-    uint32_t y2[R], S[R], G[R];
+    uint32_t y2[R], Sr[R], Gr[R], Sc[R], Gc[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      y2[r] = pk_both((uint32_t)fs.code_at(Lp->f_unc, r0 + r)) << 4;
-      S[r] = pk_both((uint32_t)(kBiasP + sc.virt_S(r0 + r)));       // both frontiers start as the virtual column -1
-      G[r] = pk_both((uint32_t)(kBiasP + sc.virt_G(r0 + r)));
+    for (int k = 0; k < R; ++k) {
+      y2[k] = ((uint32_t)fs.code_at(Lp->f_unc, r0 + k) | ((uint32_t)fs.code_at(Lp->f_unc, r0 + R + k) << 16)) * 0x0101u;   // the code in both bytes of its half
+      Sr[k] = Sc[k] = pk2(kBiasP + sc.virt_S(r0 + k), kBiasP + sc.virt_S(r0 + R + k));   // both frontiers start as the virtual column -1
+      Gr[k] = Gc[k] = pk2(kBiasP + sc.virt_G(r0 + k), kBiasP + sc.virt_G(r0 + R + k));
     }
-    uint32_t h = pk_both((uint32_t)(kBiasP + sc.virt_S(r0 - 1)));   // S of the row above the band, per frontier
-    bool synced = true;                                             // both halves hold the same column
-    const int rr = ly - 1 - r0;
-    uint32_t *p = rec(0);
-    const uint32_t step = Lp->rec_words * 32;
-    // node j + 2 is loaded in iteration j (the scratch of a launch exceeds the L2; the long-scoreboard stall was this loop's top stall)
-    uint32_t ra = p[R2_NODE * 32], bs = p[R2_BS * 32], bg = p[R2_BG * 32];
-    const uint32_t *p1 = nx > 1 ? p + step : p;
-    uint32_t ra_n = p1[R2_NODE * 32], bs_n = p1[R2_BS * 32], bg_n = p1[R2_BG * 32];
-    for (int j = 0; j < nx; ++j, p += step) {
-      const uint32_t *pn = j + 2 < nx ? p + 2 * step : p;
-      const uint32_t ra_n2 = pn[R2_NODE * 32], bs_n2 = pn[R2_BS * 32], bg_n2 = pn[R2_BG * 32];
-      const bool has_r = ra & NF_REF, both = has_r && (ra & NF_COR);
-      if (both && !synced) {
-        // end of a bubble: first strict maximum over [low half, high half]; for an INITIAL node whose real predecessor is
-        // the ref one the virtual link (the high half) comes first in the list, so the low half has to win strictly
-        uint32_t gtM = 0, ltM = 0, gtX = 0, ltX = 0;
-        h = pk_maxs_flag2(h, pk_swap(h), gtM, ltM, 1u);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (r + 1 < kBand) S[r] = pk_maxs_flag2(S[r], pk_swap(S[r]), gtM, ltM, 1u << (2 * (r + 1)));   // row r+1's match starts here
-          else { uint32_t d0 = 0, d1 = 0; S[r] = pk_maxs_flag2(S[r], pk_swap(S[r]), d0, d1, 0u); }       // the next band's halo
-          G[r] = pk_maxs_flag2(G[r], pk_swap(G[r]), gtX, ltX, 1u << (2 * r));
+    uint32_t hr = (uint32_t)(kBiasP + sc.virt_S(r0 - 1)), hc = hr;   // S of the row above the band, per frontier (low halves)
+    const int rr = ly - 1 - r0;                                // row of the final cells inside this band (when last)
+    const bool lowrow = rr < R;
+    uint32_t *p = rec(0);                                      // record of node j
+    const int32_t step = (int32_t)(Lp->rec_words * 32);
+    const int32_t o_bs = (int32_t)(R2_BS * 32) - step, o_mv = (int32_t)((R2_MOVES + (uint32_t)b) * 32) - step;   // fields of node j - 1
+    // per half (low: node j, high: node j - 1): mr = the node carries a ref letter (input and output frontier), mc = it
+    // carries a cor letter, mg = it closes a bubble; x2 = the nodes' letters (like y2); nm_h = shape of node j - 1
+    uint32_t mr = 0, mc = 0, mg = 0, x2 = 0, nm_h = 0;
+    uint32_t d7 = 0, g7 = 0, mlo = 0, ordM_lo = 0, ordX_lo = 0;
+    // node j + 2 is loaded in iteration j (the scratch of a launch exceeds the L2; the long-scoreboard stall was this loop's
+    // top stall).  The loads run up to two records past the last node: still this lane's scratch, values never used.
+    uint32_t nm = p[R2_BG * 32], bsg = p[R2_BS * 32];
+    uint32_t nm_n = p[step + R2_BG * 32], bsg_n = p[step + R2_BS * 32];
+    for (int j = 0; j <= nx; ++j, p += step) {                 // the last iteration only completes the high half
+      const uint32_t nm_n2 = p[2 * step + R2_BG * 32], bsg_n2 = p[2 * step + R2_BS * 32];
+      if (j >= nx) nm = 0;
+      mr = pk_prmt(mr, nm, 0x10ccu);                           // low half := bit 7 of nm replicated, high half := the old low half
+      mc = pk_prmt(mc, nm, 0x10ddu);
+      mg = pk_prmt(mg, nm, 0x10eeu);
+      x2 = pk_prmt(x2, nm, 0x1077u);
+      if (mg) {
+        // end of a bubble in one of the halves: first strict maximum over [ref frontier, cor frontier]; for an INITIAL node
+        // whose real predecessor is the ref one the virtual link (the cor frontier) comes first in the list, so the ref
+        // frontier has to win strictly.  Only the ref set takes the maximum: the node carries both letters, reads its
+        // input there and replaces both frontiers.
+        const uint32_t ram = ((mg & 0xffffu) ? p : p - step)[R2_NODE * 32];   // the merging node (a node never merges in both halves at once)
+        uint32_t oM = 0, oX = 0;                               // ordinal 1 = the second entry of the list won
+        if ((ram & NF_VIRT) && !(ram & NF_PREDC)) merge<R, true>(Sr, Gr, Sc, Gc, hr, hc, mg, oM, oX);
+        else merge<R, false>(Sr, Gr, Sc, Gc, hr, hc, mg, oM, oX);
+        if (mg & 0xffffu) { ordM_lo = oM & kLowOrdM; ordX_lo = oX & kLowOrdX; }
+        else {
+          uint32_t *po = scr.at(Lp->o_ord + ((ram >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
+          po[0] = ordM_lo | (oM & ~kLowOrdM);
+          po[32] = ordX_lo | (oX & ~kLowOrdX);
         }
-        const bool low_must_win = (ra & NF_VIRT) && !(ra & NF_PREDC);
-        uint32_t *po = scr.at(Lp->o_ord + ((ra >> NF_SLOT_SHIFT) * Lp->ord_bands + (uint32_t)b) * 2);
-        po[0] = low_must_win ? ltM : gtM;
-        po[32] = low_must_win ? ltX : gtX;
       }
-      synced = both;
-      const uint32_t keep = both ? 0u : has_r ? 0xffff0000u : 0x0000ffffu;   // the half this node does not replace
-      const uint32_t x2 = pk_both(ra & 0xffu) << 4;
-      uint32_t mvl = 0, mvh = 0;
-      uint32_t diag = h, up = bg;
+      // the packed update: low halves on node j, high halves on node j - 1
+      const uint32_t diag0 = pk_prmt(pk_select(hr, hc, mr), d7, 0x5410u);   // S(r0-1, pred j) | S(r0+R-1, pred (j-1))
+      const uint32_t up0 = pk_prmt(bsg, g7, 0x5432u);                       // G(r0-1, j)      | G(r0+R-1, j-1)
+      d7 = pk_select(Sr[R - 1], Sc[R - 1], mr);
+      uint32_t mv = 0, diag = diag0, up = up0, s = 0, g = 0;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const uint32_t pS = S[r], pG = G[r];
-        const uint32_t t = pk_minu(x2 ^ y2[r], pc.mis2);
+      for (int k = 0; k < R; ++k) {
+        const uint32_t pS = pk_select(Sr[k], Sc[k], mr), pG = pk_select(Gr[k], Gc[k], mr);
+        const uint32_t t = pk_minu(x2 ^ y2[k], pc.mis2);
         const uint32_t M = diag - t;
-        const uint32_t gap = pk_maxs_flag2(up, pG, mvl, mvh, 1u << (2 * (kBand - 1 - r)));        // X-gap only when it beats the Y-gap
-        const uint32_t s = pk_maxs_flag2(gap, M, mvl, mvh, 2u << (2 * (kBand - 1 - r)));          // match only when it beats both
-        const uint32_t g = pk_addmaxs(M, pc.nopen2, gap - pc.ext2);
-        S[r] = pk_select(s, pS, keep); G[r] = pk_select(g, pG, keep);
+        const uint32_t gap = pk_maxs_flag(up, pG, mv, 1u << (2 * (kBand - 1 - k)), 1u << (2 * (kBand - 1 - R - k)));   // X-gap only when it beats the Y-gap
+        s = pk_maxs_flag(gap, M, mv, 2u << (2 * (kBand - 1 - k)), 2u << (2 * (kBand - 1 - R - k)));                 // match only when it beats both
+        g = pk_addmaxs(M, pc.nopen2, gap - pc.ext2);
+        Sr[k] = pk_select(s, Sr[k], mr); Sc[k] = pk_select(s, Sc[k], mc);
+        Gr[k] = pk_select(g, Gr[k], mr); Gc[k] = pk_select(g, Gc[k], mc);
         diag = pS; up = g;
       }
-      h = pk_select(bs, h, keep);
-      // the node's own column is in the low half for a ref-carrying node, in the high half for a cor-only one
-      const uint32_t vS = has_r ? S[R - 1] : pk_swap(S[R - 1]), vG = has_r ? G[R - 1] : pk_swap(G[R - 1]);
-      if (!last) { p[R2_BS * 32] = pk_both(vS); p[R2_BG * 32] = pk_both(vG); }
-      p[(R2_MOVES + b) * 32] = has_r ? mvl : mvh;
-      if (last && (ra & NF_FINAL)) {
-        uint32_t v = S[0];
-#pragma unroll
-        for (int r = 1; r < R; ++r) if (rr == r) v = S[r];
-        const int s = (int)((has_r ? v : v >> 16) & 0xffffu) - kBiasP;
-        if (s > best) { best = s; best_j = j; }   // ties keep the smaller j (align_lpo_po2.c:410-417)
+      g7 = g;
+      hr = pk_select(bsg, hr, mr);                             // (only the low halves of hr / hc are read)
+      hc = pk_select(bsg, hc, mc);
+      // node j - 1 is now complete in the high half (s, g: its last row)
+      if (j > 0) {
+        if (!last) p[o_bs] = pk_prmt(s, g, 0x7632u);
+        st_stream(p + o_mv, (mlo & kLowMoves) | (mv & ~kLowMoves));
       }
-      ra = ra_n; bs = bs_n; bg = bg_n;
-      ra_n = ra_n2; bs_n = bs_n2; bg_n = bg_n2;
+      mlo = mv;
+      if (last && ((lowrow ? nm : nm_h) & NM_FINAL)) {
+        const int kk = lowrow ? rr : rr - R;
+        uint32_t v = pk_select(Sr[0], Sc[0], mr);               // the node's own column
+#pragma unroll
+        for (int k = 1; k < R; ++k) if (kk == k) v = pk_select(Sr[k], Sc[k], mr);
+        const int sf = (int)(lowrow ? v & 0xffffu : v >> 16) - kBiasP;
+        if (sf > best) { best = sf; best_j = lowrow ? j : j - 1; }   // ties keep the smaller j (align_lpo_po2.c:410-417)
+      }
+      nm_h = nm;
+      nm = nm_n; bsg = bsg_n;
+      nm_n = nm_n2; bsg_n = bsg_n2;
     }
   }
+
+  // the fusion reads the nodes (letter, NF_REF / NF_COR / NF_SAMERING) from P1's compact 16-bit list, a line or two per window,
+  // instead of one scratch record per node (its top stall, profiles/r3b)
+  mutable const uint16_t *p1n = nullptr;
+  EL_HD uint32_t node_flags(const uint32_t *, int j) const { return p1n[j]; }
+  EL_HDN int fuse_emit(const AlignBits &al, int n1, int lu, const RowSink &out) const { return fuse_emit_rows(*this, al, n1, lu, out); }
 
   EL_HDN int dp(int nx, int ly, int &best_j) const {
     const int nb = (ly + kBand - 1) / kBand;
     int best = -999999;
     best_j = -1;
-    for (int b = 0; b < nb - 1; ++b) band<kBand>(nx, ly, b, false, best, best_j);
-    if (ly - (nb - 1) * kBand <= 8) band<8>(nx, ly, nb - 1, true, best, best_j);
-    else band<kBand>(nx, ly, nb - 1, true, best, best_j);
+    for (int b = 0; b < nb - 1; ++b) band<8>(nx, ly, b, false, best, best_j);
+    if (ly - (nb - 1) * kBand <= 8) band<4>(nx, ly, nb - 1, true, best, best_j);
+    else band<8>(nx, ly, nb - 1, true, best, best_j);
     return best;
   }
 
   // everything up to the traceback; returns the number of MSA columns
   EL_HDN int align_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2, AlignBits &al) const {
+    p1n = p1;
+    for (int k = 0; k < n1; k += 64) prefetch_l1(p1 + k);      // the node list, for the node preparation (and the fusion)
     fs.pack_codes(sc.tab, unc, lu, Lp->f_unc);
     const int nrings = prepare(p1, n1);
     int bj;

@@ -136,6 +136,7 @@ struct PoaArgs {
   int32_t *ctrl;               // control words of the call (work counters, cursors)
   const long long *rows_cap_dev;   // when set: the end of the segment's row region is read from here instead of rows_cap (two row regions per call)
   int32_t match, mismatch, open, ext;
+  uint32_t mis2, nopen2, ext2;   // Scoring::mis2 / nopen2 / ext2
   uint32_t arena_words;  // shared-memory arena words per thread (dynamic shared memory of the launch / 128)
   // phase 1 -> phase 2
   uint16_t *p1_nodes;    // P1 node list of window w at [p1_offset(ref_off[w] - ref_off[0], cor_off[w] - cor_off[0], w)], n1[w] entries
@@ -236,6 +237,12 @@ EL_HD uint32_t shift_in_sign(uint32_t mv, int t) {
 struct Scoring {
   const SymbolTables *tab;
   int match, mismatch, open, ext;
+  uint32_t mis2, nopen2, ext2;   // |mismatch|, -open, ext in both 16-bit halves (packed kernels; kernel arguments, so that the
+                                 // loops read them from the constant bank instead of rebuilding them)
+  EL_HD void set(int m, int mm, int o, int e) {
+    match = m; mismatch = mm; open = o; ext = e;
+    mis2 = ((uint32_t)(-mm) & 0xffffu) * 0x10001u; nopen2 = ((uint32_t)(-o) & 0xffffu) * 0x10001u; ext2 = ((uint32_t)e & 0xffffu) * 0x10001u;
+  }
   // virtual column -1 (align_lpo_po2.c:272-273,290-302) at row `row` (-1 = the corner)
   EL_HD int virt_S(int row) const { return row < 0 ? 0 : -(open + ext * row); }
   EL_HD int virt_G(int row) const { return row < 0 ? -open : -(open + ext * row) - ext; }
@@ -340,6 +347,22 @@ EL_HD void prefetch_l1(const void *p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 #else
   (void)p;
+#endif
+}
+EL_HD void prefetch_l2(const void *p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// a store of data this kernel will not read again soon (moves words: re-read once, by the traceback; MSA rows: never):
+// evict-first in the L2, so that the boundary rows and node records of the resident groups stay there
+EL_HD void st_stream(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  __stcs(p, v);
+#else
+  *p = v;
 #endif
 }
 
@@ -581,7 +604,6 @@ template <class PH>
 EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, const RowSink &out) {
   const LaneScratch &fs = ph.fs;
   const auto *Lp = ph.Lp;
-  constexpr uint32_t kNode = PH::kRecNode;
   const uint8_t *sym = ph.sc.tab->sym;
   int ix = 0, iy = 0, col = -1, prev_key = -1, rs = 0;
   uint32_t c0 = '.', c1 = '.', c2 = '.';
@@ -590,7 +612,7 @@ EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, con
     if (col >= 0) {
       const int sh = (col & 3) * 8;
       w0 |= c0 << sh; w1 |= c1 << sh; w2 |= c2 << sh;
-      if ((col & 3) == 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w1; out.r2[col >> 2] = w2; w0 = w1 = w2 = 0; }
+      if ((col & 3) == 3) { st_stream(out.r0 + (col >> 2), w0); st_stream(out.r1 + (col >> 2), w1); st_stream(out.r2 + (col >> 2), w2); w0 = w1 = w2 = 0; }
     }
   };
   auto emit = [&](int key, uint32_t letter, uint32_t srcmask) {
@@ -604,7 +626,7 @@ EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, con
   const uint32_t *pr = ph.node_rec(0);
   // nodes ix, ix+1 in registers, ix+2 in flight.  One uniform step per node of P1 or unaligned letter of unc (which goes
   // before the first aligned member of the next ring that has one, or after the last node): no inner loops.
-  uint32_t ra0 = pr[kNode * 32], ra1 = n1 > 1 ? pr[step + kNode * 32] : 0, ra2 = n1 > 2 ? pr[2 * step + kNode * 32] : 0;
+  uint32_t ra0 = ph.node_flags(pr, 0), ra1 = n1 > 1 ? ph.node_flags(pr + step, 1) : 0, ra2 = n1 > 2 ? ph.node_flags(pr + 2 * step, 2) : 0;
   while (ix < n1 || iy < lu) {
     const bool xa = ix < n1 && al.x_at(ix);
     const bool ya = iy < lu && ((fs.w(al.oy + (uint32_t)(iy >> 5)) >> (iy & 31)) & 1u);
@@ -612,7 +634,7 @@ EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, con
     bool any = xa;
     if (!any && ix + 1 < n1 && (ra1 & NF_SAMERING)) {
       any = al.x_at(ix + 1);
-      for (int ir = ix + 2; !any && ir < n1 && (ph.node_rec(ir)[kNode * 32] & NF_SAMERING); ++ir) any = al.x_at(ir);
+      for (int ir = ix + 2; !any && ir < n1 && (ph.node_flags(ph.node_rec(ir), ir) & NF_SAMERING); ++ir) any = al.x_at(ir);
     }
     const uint32_t yl = (fs.w(Lp->f_unc + (uint32_t)(iy >> 2)) >> ((iy & 3) * 8)) & 0xffu;
     if (iy < lu && !ya && (ix >= n1 || any)) { emit(n1 + iy, yl, 4u); ++iy; }
@@ -628,11 +650,11 @@ EL_HDN int fuse_emit_rows(const PH &ph, const AlignBits &al, int n1, int lu, con
       emit(rs, ra & 0xffu, mask);
       ++ix; pr += step;
       ra0 = ra1; ra1 = ra2;
-      ra2 = ix + 2 < n1 ? pr[2 * step + kNode * 32] : 0;
+      ra2 = ix + 2 < n1 ? ph.node_flags(pr + 2 * step, ix + 2) : 0;
     }
   }
   flush();
-  if ((col & 3) != 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w1; out.r2[col >> 2] = w2; }
+  if ((col & 3) != 3) { st_stream(out.r0 + (col >> 2), w0); st_stream(out.r1 + (col >> 2), w1); st_stream(out.r2 + (col >> 2), w2); }
   return col + 1;
 }
 
@@ -675,6 +697,7 @@ EL_HDN int prepare_nodes(const PH &ph, const uint16_t *nodes, int nx) {
     p[PH::kRecNode * 32] = ra;
     p[PH::kRecPred * 32] = ((uint32_t)pA & 0xffffu) | ((uint32_t)pB << 16);
     PH::put_row0(p, bS, bG);
+    PH::put_shape(p, ra);
     if (pA != j - 1 || (ra & (NF_VIRT | NF_TWO))) nt |= 1u << (j & 31);   // the traceback must look this node up
     if ((j & 31) == 31) { ph.fs.w(Lp->f_nt + (j >> 5)) = nt; nt = 0; }
     if (hasR) { lastR = j; gR = bG; }
@@ -701,6 +724,7 @@ struct Phase2 {
   EL_HD uint32_t *rec(uint32_t j) const { return scr.at(Lp->o_nodes + j * Lp->rec_words); }  // field f at [f*32]
 
   static EL_HD void put_row0(uint32_t *p, int bS, int bG) { p[R2_BS * 32] = (uint32_t)bS; p[R2_BG * 32] = (uint32_t)bG; }
+  static EL_HD void put_shape(uint32_t *, uint32_t) {}   // (the dual kernel keeps a shape word per node, poa_dual.cuh)
   EL_HDN int prepare(const uint16_t *nodes, int nx) const { return prepare_nodes(*this, nodes, nx); }
 
   // ---- DP2: P1 columns x lin(unc) rows, one band (align_lpo_po2.c:269-433) ----
@@ -780,6 +804,9 @@ struct Phase2 {
       const uint32_t w0 = *pm;
       if (j >= 6) prefetch_l1(pm - 6 * step);
       if (b > 0 && j >= 2) prefetch_l1(pm - 2 * step - 32);
+#ifdef EL_TB_PF2
+      if (j >= EL_TB_PF2 && r >= EL_TB_PF2) prefetch_l2(p - EL_TB_PF2 * step + (R2_MOVES + ((r - EL_TB_PF2) >> 4)) * 32);   // the cell EL_TB_PF2 diagonal steps ahead
+#endif
       const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
       if (kind & 2u) {
         al.st.w(al.ox + (uint32_t)(j >> 5)) |= 1u << (j & 31);
@@ -807,6 +834,7 @@ struct Phase2 {
 
   static constexpr uint32_t kRecNode = R2_NODE, kRecPred = R2_PRED;
   EL_HD uint32_t *node_rec(int j) const { return rec((uint32_t)j); }
+  EL_HD uint32_t node_flags(const uint32_t *rec_j, int) const { return rec_j[R2_NODE * 32]; }   // what the fusion reads of node j: letter, NF_REF / NF_COR / NF_SAMERING
   EL_HDN int fuse_emit(const AlignBits &al, int n1, int lu, const RowSink &out) const { return fuse_emit_rows(*this, al, n1, lu, out); }
   EL_HD AlignBits bits() const { return AlignBits{fs, Lp->f_xb, Lp->f_yb}; }
 
@@ -925,6 +953,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp1_kernel(PoaArgs a, const
   c.scr.base = s_run.scratch + (size_t)blockIdx.x * s_run.warp_words * 32 + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
+  c.sc.mis2 = a.mis2; c.sc.nopen2 = a.nopen2; c.sc.ext2 = a.ext2;
   c.Lp = &s_layout;
   __shared__ int32_t s_retry[64];   // windows whose band-restricted DP failed its exactness test: run again without the band
   int nretry = 0;
@@ -1014,6 +1043,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
   c.bset = s_bset + lane;
   c.sc.tab = stage_tables<GENERIC_SUB>(s_tab, g_tab);
   c.sc.match = a.match; c.sc.mismatch = a.mismatch; c.sc.open = a.open; c.sc.ext = a.ext;
+  c.sc.mis2 = a.mis2; c.sc.nopen2 = a.nopen2; c.sc.ext2 = a.ext2;
   c.Lp = &s_layout;
   __shared__ int32_t s_retry[64];   // windows whose band-restricted DP failed its exactness test: run again without the band
   int nretry = 0;

@@ -93,9 +93,7 @@ EL_HD uint32_t pk_lo_hi(uint32_t lo_src, uint32_t hi_src) {   // low half of lo_
 struct PackedConsts {
   uint32_t mis2, nopen2, ext2;   // |mismatch|, -open, ext in both halves
   EL_HD void set(const Scoring &sc) {
-    mis2 = pk2(-sc.mismatch, -sc.mismatch);
-    nopen2 = pk2(-sc.open, -sc.open);
-    ext2 = pk2(sc.ext, sc.ext);
+    mis2 = sc.mis2; nopen2 = sc.nopen2; ext2 = sc.ext2;
   }
 };
 
@@ -229,7 +227,7 @@ struct Phase1P {
       const uint32_t mv = update_packed<R>(pc, S, G, y2, x2, diag0, up0);
       // node j - 1 is now complete in the high half
       if (!last) p[P1_BSG * 32] = (S[R - 1] >> 16) | (G[R - 1] & 0xffff0000u);
-      p[(P1_MOVES + b) * 32] = pk_lo_hi(mlo, mv);
+      st_stream(p + (P1_MOVES + b) * 32, pk_lo_hi(mlo, mv));
       mlo = mv;
       if (last && j == lr - 1 && rr < R) best = pick_half<R>(S, rr, false);
     }
@@ -265,6 +263,9 @@ struct Phase1P {
       const uint32_t w = *pm;
       if (j >= 6) prefetch_l1(pm - (ptrdiff_t)6 * rw * 32);
       if (b > 0 && j >= 2) prefetch_l1(pm - (ptrdiff_t)2 * rw * 32 - 32);
+#ifdef EL_TB_PF2
+      if (j >= EL_TB_PF2 && r >= EL_TB_PF2) prefetch_l2(base + (ptrdiff_t)((j - EL_TB_PF2) * rw + (r - EL_TB_PF2) / (2 * R)) * 32);   // the cell EL_TB_PF2 diagonal steps ahead
+#endif
       const uint32_t kind = (w >> (rr < R ? 2 * rr : 16 + 2 * (rr - R))) & 3u;   // bit 1 match, bit 0 X-gap
       if (kind & 2u) {
         al.st.w(al.ox + (uint32_t)(j >> 5)) |= 1u << (j & 31);
@@ -355,11 +356,11 @@ struct Phase2L {
       const int sh = (col & 3) * 8;
       w0 |= (yonly ? (uint32_t)'.' : xc) << sh;
       w2 |= (takey ? yc : (uint32_t)'.') << sh;
-      if ((col & 3) == 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w0; out.r2[col >> 2] = w2; w0 = w2 = 0; }
+      if ((col & 3) == 3) { st_stream(out.r0 + (col >> 2), w0); st_stream(out.r1 + (col >> 2), w0); st_stream(out.r2 + (col >> 2), w2); w0 = w2 = 0; }
       ++col;
       ix += !yonly; iy += takey;
     }
-    if (col & 3) { out.r0[col >> 2] = w0; out.r1[col >> 2] = w0; out.r2[col >> 2] = w2; }
+    if (col & 3) { st_stream(out.r0 + (col >> 2), w0); st_stream(out.r1 + (col >> 2), w0); st_stream(out.r2 + (col >> 2), w2); }
     return col;
   }
 

@@ -42,7 +42,7 @@ static int run(const ScoringSetup &sc, FastaFile &R, FastaFile &C, FastaFile &U,
     const uint8_t *ref = (const uint8_t *)R.seq.data() + R.rec[w].off, *cor = (const uint8_t *)C.seq.data() + C.rec[w].off,
                   *unc = (const uint8_t *)U.seq.data() + U.rec[w].off;
     Scoring s;
-    s.tab = &sc.tab; s.match = sc.match; s.mismatch = sc.mismatch; s.open = sc.open; s.ext = sc.ext;
+    s.tab = &sc.tab; s.set(sc.match, sc.mismatch, sc.open, sc.ext);
     FastPart fp;
     // ---- phase 1 (caps deliberately larger than the window, as in a real group) ----
     std::vector<uint64_t> nodes64(((size_t)lr + lc) / 4 + 2, 0xdeaddeaddeaddeadull);
