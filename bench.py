@@ -295,12 +295,12 @@ def main():
             if mode != "packed_in_counters_out":
                 io.m_ref, io.m_cor, io.m_unc, io.m_cap = h_m[0].data_ptr(), h_m[1].data_ptr(), h_m[2].data_ptr(), m_cap
                 io.m_off, io.m_len = h_moff.data_ptr(), h_mlen.data_ptr()
-                if mode == "packed_in_merged_nibbles_out":
-                    io.m_nibbles = 1
+                if mode in ("packed_in_merged_nibbles_out", "packed_in_merged_columns_out"):
+                    io.m_nibbles = 1 if mode == "packed_in_merged_nibbles_out" else 2
                     io.m_esc_pos, io.m_esc_byte, io.m_esc_cap, io.m_n_esc = h_esc_pos.data_ptr(), h_esc_byte.data_ptr(), 1 << 20, h_nesc.data_ptr()
         return io
 
-    E2E_MODES = ["packed_in_merged_nibbles_out", "bytes_in_window_rows_out", "packed_in_merged_rows_out", "packed_in_counters_out"]
+    E2E_MODES = ["packed_in_merged_columns_out", "packed_in_merged_nibbles_out", "bytes_in_window_rows_out", "packed_in_merged_rows_out", "packed_in_counters_out"]
     ios = {m: make_io(m) for m in E2E_MODES}
 
     def make_step(mode):
@@ -354,13 +354,16 @@ def main():
     used = int(d_used.item())
     sums_dev = d_sums.cpu().numpy().copy()
     e2e_modes = {}
+    nesc = {"packed_in_merged_nibbles_out": 0, "packed_in_merged_columns_out": 0}
     sums_e2e = None
-    for mode in (E2E_MODES if not args.e2e_main_only else E2E_MODES[:2]):
+    for mode in (E2E_MODES if not args.e2e_main_only else E2E_MODES[:3]):
         fn = make_step(mode)
         for _ in range(args.warmup):
             fn()
         ms_, wall_ = timed(fn, args.steps)
         e2e_modes[mode] = max(ms_, wall_) / args.steps
+        if mode in nesc:
+            nesc[mode] = int(h_nesc[0])
         if mode == E2E_MODES[0]:
             sums_e2e = h_out["sums"].numpy().copy()
             merged_cols = int(h_mlen.numpy().astype(np.int64).sum())
@@ -428,13 +431,20 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue = None
+    try:   # ncu view of the same launch set (tools/ncu_issue.py on the launch list of the round's evidence run)
+        issue = json.load(open(os.path.join(ROOT, "profiles", "issue.json")))
+    except Exception:
+        pass
     letters = int(wl["ref_off"][-1] + wl["cor_off"][-1] + wl["unc_off"][-1])
     in_bytes = letters + 3 * 8 * (n + 1) + 8 * (n_trip + 1)                     # byte path: 1 B per letter, 64-bit offsets
     in_packed = sum((pk.n_letters + 3) // 4 + 9 * len(pk.exc_pos) for pk in packed) + 3 * 4 * n + 8 * (n_trip + 1)
     out_rows = used + n * (8 + 4 + 4) + n_trip * K * 8 + K * 8                   # byte path: window rows, their offsets, counters
     out_merged = 3 * merged_cols + n * 4 + n_trip * (8 + 4 + K * 8) + K * 8     # merged rows as bytes, nring, m_off / m_len, counters
     wire = {"packed_in_merged_rows_out": (in_packed, out_merged), "bytes_in_window_rows_out": (in_bytes, out_rows),
-            "packed_in_merged_nibbles_out": (in_packed, out_merged - 3 * merged_cols + 3 * ((merged_cols + 1) // 2) + 9 * int(h_nesc[0])),
+            "packed_in_merged_nibbles_out": (in_packed, out_merged - 3 * merged_cols + 3 * ((merged_cols + 1) // 2) + 9 * nesc["packed_in_merged_nibbles_out"]),
+            "packed_in_merged_columns_out": (in_packed, out_merged - 2 * merged_cols + 9 * nesc["packed_in_merged_columns_out"]),
             "packed_in_counters_out": (in_packed, n_trip * K * 8 + K * 8)}
     out_bytes = wire[E2E_MODES[0]][1]
     alg_bytes = in_bytes + used + n * 36
@@ -453,7 +463,7 @@ def main():
                    "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush" % (in_bytes / 1e6), "parity": parity},
         "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": wire[E2E_MODES[0]][0], "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": e2e_step_ms,
-                "call": "elector_pipeline_run2: 2-bit packed letters + 32-bit window lengths in (packed once, outside the call), merged per-read MSA rows (what Donatello appends to msa.fa) as 4-bit columns + per-read counters + sums out; pinned host buffers",
+                "call": "elector_pipeline_run2: 2-bit packed letters + 32-bit window lengths in (packed once, outside the call), merged per-read MSA rows (what Donatello appends to msa.fa) as one byte per column (the three rows' characters base 6, ELECTOR_COLUMN_CHARS) + per-read counters + sums out; pinned host buffers",
                 "host_link_gbs": (wire[E2E_MODES[0]][0] + out_bytes) / (e2e_step_ms / 1e3) / 1e9,
                 "limiter": "kernels (%.2f ms resident) + the tail of the last chunk's results; the host link carries %.0f MB per call" % (step_ms, (wire[E2E_MODES[0]][0] + out_bytes) / 1e6),
                 "modes": {m: {"ms_per_step": e2e_modes[m], "value": n_trip * world / (e2e_modes[m] / 1e3), "h2d_bytes_per_step": wire[m][0], "d2h_bytes_per_step": wire[m][1],
@@ -467,6 +477,15 @@ def main():
                      "traffic": (traffic or {}).get("poa_dp2_kernel_bytes_per_launch_set"),
                      "kernel": "poa_dp2_kernel (all segment launches of one step, with its sort)",
                      "ops_per_cell": INT_OPS_PER_CELL, "cells_per_step": cells2,
+                     "cells_swept_per_step": cells2,   # every window runs DP2 (the diagonal band of the linear kernels skips cells inside a window; not counted)
+                     "issue": None if not issue else {
+                         "warp_instructions_per_step": issue["phase2_warp_instructions_per_launch_set"],
+                         "thread_instructions_per_cell": issue["phase2_warp_instructions_per_launch_set"] * 32 / cells2,
+                         "ipc_active": issue["ipc_active_time_weighted"], "ipc_peak": 4.0,
+                         "issue_slot_utilisation": issue["phase2_warp_instructions_per_launch_set"] / (p2_s * (clocks.get("sm_mhz") or 1965.0) * 1e6 * n_sm * 4),
+                         "issue_slot_utilisation_note": "warp instructions of the launch set (ncu) / (4 issue slots x SMs x SM clock x the phase-2 time measured live)",
+                         "alu_pipe_pct": issue["alu_pipe_pct_time_weighted"],
+                         "source": "profiles/issue.json (ncu launch list of the same command, cold-cache and serialised)"},
                      "peak_alu_pipe_only": alu.value,
                      "peak_source": "measured on this device by elector_int32_peak (IMAD/IADD3/VIMNMX/LOP3 chains)",
                      "also": {"kernel": "poa_dp1_kernel", "achieved": ach1, "frac": ach1 / mixed.value if mixed.value else None,

@@ -736,7 +736,16 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
       tally_sum_kernel<<<std::min<int>(64, (int)((nr + 7) / 8)), 256, 0, st>>>(nr, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
       CU(cudaGetLastError());
       ++ctx->last_launches;
-      if (want_merged && io.m_nibbles) {   // two columns per byte before they leave; the few characters outside the code go to the escape list
+      if (want_merged && io.m_nibbles == 2) {   // one byte per column for the three rows together; characters outside the code go to the escape list
+        CU(ctx->d_nib[0].reserve((size_t)ctx->merged_cap + 16));
+        CU(ctx->d_esc_pos.reserve((size_t)(io.m_esc_cap + 3) * 8)); CU(ctx->d_esc_byte.reserve((size_t)io.m_esc_cap + 8));
+        CU(cudaMemsetAsync(ctx->d_ctrl.as<unsigned long long>() + 21, 0, 8, st));
+        column_pack_kernel<<<(unsigned)nr, 128, 0, st>>>(nr, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(),
+            ctx->d_moff.as<int64_t>(), ctx->d_mlen.as<int32_t>(), ctx->d_nib[0].as<uint8_t>(), j.m_base,
+            ctx->d_ctrl.as<unsigned long long>() + 21, ctx->d_esc_pos.as<int64_t>(), ctx->d_esc_byte.as<uint8_t>(), io.m_esc_cap, ctx->d_ctrl.as<int32_t>() + kAbortWord);
+        CU(cudaGetLastError());
+        ++ctx->last_launches;
+      } else if (want_merged && io.m_nibbles) {   // two columns per byte before they leave; the few characters outside the code go to the escape list
         for (int k = 0; k < 3; ++k) CU(ctx->d_nib[k].reserve((size_t)ctx->merged_cap / 2 + 16));
         CU(ctx->d_esc_pos.reserve((size_t)(io.m_esc_cap + 1) * 8)); CU(ctx->d_esc_byte.reserve((size_t)io.m_esc_cap + 8));
         CU(cudaMemsetAsync(ctx->d_ctrl.as<unsigned long long>() + 21, 0, 8, st));
@@ -799,7 +808,8 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
       if (j.m_base + cols > io.m_cap) { cudaStreamSynchronize(st); cudaStreamSynchronize(so); return ctx->fail(ELECTOR_ECAPACITY, "merged rows need more than m_cap = %lld columns", (long long)io.m_cap); }
       char *dst[3] = {io.m_ref, io.m_cor, io.m_unc};
       DevBuf *srcb[3] = {&ctx->d_mref, &ctx->d_mcor, &ctx->d_munc};
-      for (int k = 0; k < 3; ++k) {
+      if (io.m_nibbles == 2) CU(cudaMemcpyAsync(dst[0] + j.m_base, ctx->d_nib[0].p, (size_t)cols, cudaMemcpyDeviceToHost, so));
+      else for (int k = 0; k < 3; ++k) {
         if (io.m_nibbles) CU(cudaMemcpyAsync(dst[k] + j.m_base / 2, ctx->d_nib[k].p, (size_t)(cols + 1) / 2, cudaMemcpyDeviceToHost, so));
         else CU(cudaMemcpyAsync(dst[k] + j.m_base, srcb[k]->p, (size_t)cols, cudaMemcpyDeviceToHost, so));
       }
@@ -1077,6 +1087,15 @@ int64_t elector_merged_bound(int64_t n, int64_t n_reads, const int64_t *ro, cons
   return ((ro[n] - ro[0]) + (co[n] - co[0]) + (uo[n] - uo[0]) + 32 * n_reads + 31) & ~(int64_t)15;
 }
 
+void elector_unpack_columns(const uint8_t *codes, int64_t n, char *ref, char *cor, char *unc) {
+  static const char sym[] = ELECTOR_COLUMN_CHARS;
+  for (int64_t i = 0; i < n; ++i) {
+    const unsigned c = codes[i];
+    if (c < 216) { ref[i] = sym[c % 6]; cor[i] = sym[(c / 6) % 6]; unc[i] = sym[c / 36]; }
+    else ref[i] = cor[i] = unc[i] = '?';   // 255: the three characters are in the escape list
+  }
+}
+
 int64_t elector_pack_letters(const char *letters, int64_t n, uint8_t *bits, int64_t *exc_pos, uint8_t *exc_byte, int64_t exc_cap) {
   if (n <= 0 || !letters || !bits) return 0;
   static const struct Lut { int8_t v[256]; Lut() { memset(v, -1, sizeof v); v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; } } lut;
@@ -1111,7 +1130,8 @@ int elector_pipeline_run2(elector_ctx *ctx, const elector_pipeline_io *iop) {
   if (n > 0 && !packed && !(io.ref && io.cor && io.unc)) return ctx->fail(ELECTOR_EINVAL, "null letters");
   if (n > 0 && io.rows_out && !(io.row_off && io.row_stride && io.nring)) return ctx->fail(ELECTOR_EINVAL, "rows_out needs row_off, row_stride and nring");
   if (n_reads > 0 && !read_first) return ctx->fail(ELECTOR_EINVAL, "null read_first");
-  if (io.m_ref && !(io.m_cor && io.m_unc && io.m_off && io.m_len && n_reads > 0)) return ctx->fail(ELECTOR_EINVAL, "merged rows need all three buffers, m_off, m_len and reads");
+  if (io.m_nibbles < 0 || io.m_nibbles > 2) return ctx->fail(ELECTOR_EINVAL, "m_nibbles must be 0, 1 or 2");
+  if (io.m_ref && !((io.m_nibbles == 2 || (io.m_cor && io.m_unc)) && io.m_off && io.m_len && n_reads > 0)) return ctx->fail(ELECTOR_EINVAL, "merged rows need all three buffers (one with m_nibbles = 2), m_off, m_len and reads");
   if (io.m_ref && io.m_nibbles && io.m_esc_cap > 0 && !(io.m_esc_pos && io.m_esc_byte)) return ctx->fail(ELECTOR_EINVAL, "null escape arrays");
   if (io.sums_out) memset(io.sums_out, 0, ELECTOR_TALLY_K * sizeof(int64_t));
   if (io.m_n_esc) *io.m_n_esc = 0;

@@ -181,11 +181,47 @@ struct Phase2D : Phase2<false> {
     }
   }
 
-  // the fusion reads the nodes (letter, NF_REF / NF_COR / NF_SAMERING) from P1's compact 16-bit list, a line or two per window,
-  // instead of one scratch record per node (its top stall, profiles/r3b)
+  // fuse 2 + MSA emit for a P1 made of TWO sequences (lpo.c:413-463, lpo_format.c:346-371): an align ring of P1 has one node
+  // (both letters, or one) or two (a ref-only and a cor-only node: a substitution), so a ring is one MSA column holding ref's
+  // and cor's letter, and the walk is column-driven and branch-free like Phase2L's: per step one ring of P1 (with the letter of
+  // unc aligned to one of its nodes, if any) or one unaligned letter of unc, which goes before the next ring that has an
+  // ALIGNED node, or after the last node.  The nodes are read from P1's compact 16-bit list (a line or two per window) instead
+  // of one scratch record per node (the generic fuse_emit_rows: 170 warp instructions per column and this kernel's top stall,
+  // profiles/r3b).  Returns the number of columns.
   mutable const uint16_t *p1n = nullptr;
-  EL_HD uint32_t node_flags(const uint32_t *, int j) const { return p1n[j]; }
-  EL_HDN int fuse_emit(const AlignBits &al, int n1, int lu, const RowSink &out) const { return fuse_emit_rows(*this, al, n1, lu, out); }
+  EL_HDN int fuse_emit(const AlignBits &al, int n1, int lu, const RowSink &out) const {
+    const uint8_t *sym = sc.tab->sym;
+    int col = 0, ix = 0, iy = 0;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    uint32_t ra0 = n1 > 0 ? p1n[0] : 0u, ra1 = n1 > 1 ? p1n[1] : 0u, ra2 = n1 > 2 ? p1n[2] : 0u, ra3 = n1 > 3 ? p1n[3] : 0u;   // nodes ix .. ix + 3
+    while (ix < n1 || iy < lu) {
+      const bool two = ix + 1 < n1 && (ra1 & NF_SAMERING);
+      const bool xa = ix < n1 && (al.x_at(ix) || (two && al.x_at(ix + 1)));
+      const bool ya = iy < lu && ((fs.w(al.oy + (uint32_t)(iy >> 5)) >> (iy & 31)) & 1u);
+      const bool yonly = iy < lu && !ya && (ix >= n1 || xa);
+      const bool takey = yonly || xa;                          // an aligned ring's partner is the current letter of unc
+      const uint32_t rb = two ? (ra0 | ra1) : ra0;             // which letters the ring carries
+      const uint32_t rl = (ra0 & NF_REF) ? ra0 : ra1, cl = (ra0 & NF_COR) ? ra0 : ra1;
+      const uint32_t rc = (rb & NF_REF) ? (uint32_t)sym[rl & 31u] : (uint32_t)'.';
+      const uint32_t cc = (rb & NF_COR) ? (uint32_t)sym[cl & 31u] : (uint32_t)'.';
+      const uint32_t yc = sym[(fs.w(Lp->f_unc + (uint32_t)(iy >> 2)) >> ((iy & 3) * 8)) & 31u];
+      const int sh = (col & 3) * 8;
+      w0 |= (yonly ? (uint32_t)'.' : rc) << sh;
+      w1 |= (yonly ? (uint32_t)'.' : cc) << sh;
+      w2 |= (takey ? yc : (uint32_t)'.') << sh;
+      if ((col & 3) == 3) { st_stream(out.r0 + (col >> 2), w0); st_stream(out.r1 + (col >> 2), w1); st_stream(out.r2 + (col >> 2), w2); w0 = w1 = w2 = 0; }
+      ++col;
+      iy += takey;
+      if (!yonly) {
+        const int adv = two ? 2 : 1;
+        ix += adv;
+        if (two) { ra0 = ra2; ra1 = ra3; ra2 = ix + 2 < n1 ? p1n[ix + 2] : 0u; ra3 = ix + 3 < n1 ? p1n[ix + 3] : 0u; }
+        else { ra0 = ra1; ra1 = ra2; ra2 = ra3; ra3 = ix + 3 < n1 ? p1n[ix + 3] : 0u; }
+      }
+    }
+    if (col & 3) { st_stream(out.r0 + (col >> 2), w0); st_stream(out.r1 + (col >> 2), w1); st_stream(out.r2 + (col >> 2), w2); }
+    return col;
+  }
 
   EL_HDN int dp(int nx, int ly, int &best_j) const {
     const int nb = (ly + kBand - 1) / kBand;

@@ -349,13 +349,6 @@ EL_HD void prefetch_l1(const void *p) {
   (void)p;
 #endif
 }
-EL_HD void prefetch_l2(const void *p) {
-#ifdef __CUDA_ARCH__
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
 // a store of data this kernel will not read again soon (moves words: re-read once, by the traceback; MSA rows: never):
 // evict-first in the L2, so that the boundary rows and node records of the resident groups stay there
 EL_HD void st_stream(uint32_t *p, uint32_t v) {
@@ -804,9 +797,6 @@ struct Phase2 {
       const uint32_t w0 = *pm;
       if (j >= 6) prefetch_l1(pm - 6 * step);
       if (b > 0 && j >= 2) prefetch_l1(pm - 2 * step - 32);
-#ifdef EL_TB_PF2
-      if (j >= EL_TB_PF2 && r >= EL_TB_PF2) prefetch_l2(p - EL_TB_PF2 * step + (R2_MOVES + ((r - EL_TB_PF2) >> 4)) * 32);   // the cell EL_TB_PF2 diagonal steps ahead
-#endif
       const uint32_t kind = (w0 >> (2 * (15 - (r & 15)))) & 3u;   // bit 1 match, bit 0 X-gap
       if (kind & 2u) {
         al.st.w(al.ox + (uint32_t)(j >> 5)) |= 1u << (j & 31);

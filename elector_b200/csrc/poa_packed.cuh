@@ -263,9 +263,6 @@ struct Phase1P {
       const uint32_t w = *pm;
       if (j >= 6) prefetch_l1(pm - (ptrdiff_t)6 * rw * 32);
       if (b > 0 && j >= 2) prefetch_l1(pm - (ptrdiff_t)2 * rw * 32 - 32);
-#ifdef EL_TB_PF2
-      if (j >= EL_TB_PF2 && r >= EL_TB_PF2) prefetch_l2(base + (ptrdiff_t)((j - EL_TB_PF2) * rw + (r - EL_TB_PF2) / (2 * R)) * 32);   // the cell EL_TB_PF2 diagonal steps ahead
-#endif
       const uint32_t kind = (w >> (rr < R ? 2 * rr : 16 + 2 * (rr - R))) & 3u;   // bit 1 match, bit 0 X-gap
       if (kind & 2u) {
         al.st.w(al.ox + (uint32_t)(j >> 5)) |= 1u << (j & 31);

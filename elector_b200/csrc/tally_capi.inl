@@ -44,7 +44,7 @@ int merge_device(elector_ctx *ctx, int64_t n_reads, const int64_t *h_read_first,
   CU(ctx->d_wdst.reserve((size_t)n_windows * 8));
   merge_plan_kernel<<<(unsigned)((n_reads + 3) / 4), 128, 0, ctx->stream>>>(n_reads, ctx->d_readfirst.as<int64_t>(), d_rows, d_row_off, d_row_stride, d_nring,
                                                                             ctx->d_moff.as<int64_t>(), ctx->d_wdst.as<int64_t>(), ctx->d_mlen.as<int32_t>(), ctx->d_ctrl.as<int32_t>() + kAbortWord);
-  merge_copy_kernel<<<(unsigned)std::min<int64_t>((n_windows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+  merge_copy_kernel<<<(unsigned)std::min<int64_t>((n_windows + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(   // a warp takes 32 windows at a time
       n_windows, d_rows, d_row_off, d_row_stride, d_nring, ctx->d_wdst.as<int64_t>(), ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(),
       ctx->d_munc.as<uint8_t>(), ctx->d_ctrl.as<int32_t>() + kAbortWord);
   CU(cudaGetLastError());

@@ -105,4 +105,50 @@ __global__ void __launch_bounds__(128) nibble_pack_kernel(int64_t n_reads, const
   for (int i = 2 * lane; i < L; i += 64) dst[i >> 1] = (uint8_t)(code(i) | (code(i + 1) << 4));
 }
 
+// merged rows of the reads -> ONE byte per column for the three rows together (m_nibbles = 2): ref + 6 * cor + 36 * unc with
+// each row's character coded over ELECTOR_COLUMN_CHARS; a column with any other character gets 255 and its three
+// characters go to the escape list.  A thread packs four columns (read regions start at multiples of 16 columns);
+// one warp per 128 columns of a read.
+__device__ __forceinline__ uint32_t column_code6(uint32_t c) {
+  return c == '.' ? 0u : c == 'a' ? 1u : c == 'c' ? 2u : c == 'g' ? 3u : c == 't' ? 4u : c == 'n' ? 5u : 15u;
+}
+__global__ void __launch_bounds__(128) column_pack_kernel(int64_t n_reads, const uint8_t *m0, const uint8_t *m1, const uint8_t *m2,
+                                                           const int64_t *m_off, const int32_t *m_len, uint8_t *out, int64_t col_base,
+                                                           unsigned long long *esc_count, int64_t *esc_pos, uint8_t *esc_byte, int64_t esc_cap,
+                                                           const int32_t *abort) {
+  if (*abort) return;
+  const int64_t r = blockIdx.x;
+  if (r >= n_reads) return;
+  const int64_t off = m_off[r];
+  const int L = m_len[r];
+  const uint32_t *a4 = reinterpret_cast<const uint32_t *>(m0 + off), *c4 = reinterpret_cast<const uint32_t *>(m1 + off),
+                 *u4 = reinterpret_cast<const uint32_t *>(m2 + off);
+  uint32_t *o4 = reinterpret_cast<uint32_t *>(out + off);
+  for (int q = threadIdx.x; 4 * q < L; q += blockDim.x) {
+    const uint32_t a = a4[q], c = c4[q], u = u4[q];
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 4 * q + k;
+      if (i < L) {
+        const uint32_t ca = (a >> (8 * k)) & 0xffu, cc = (c >> (8 * k)) & 0xffu, cu = (u >> (8 * k)) & 0xffu;
+        const uint32_t ka = column_code6(ca), kc = column_code6(cc), ku = column_code6(cu);
+        uint32_t code = ka + 6u * kc + 36u * ku;
+        if ((ka | kc | ku) == 15u) {
+          code = 255u;
+          const unsigned long long e = atomicAdd(esc_count, 3ull);
+          if ((int64_t)e + 3 <= esc_cap) {
+            const int64_t col = col_base + off + i;
+            esc_pos[e] = 3 * col; esc_byte[e] = (uint8_t)ca;
+            esc_pos[e + 1] = 3 * col + 1; esc_byte[e + 1] = (uint8_t)cc;
+            esc_pos[e + 2] = 3 * col + 2; esc_byte[e + 2] = (uint8_t)cu;
+          }
+        }
+        w |= code << (8 * k);
+      }
+    }
+    o4[q] = w;
+  }
+}
+
 }  // namespace elector

@@ -53,6 +53,8 @@ def load_library():
     lib.elector_poa_files.restype = c.c_int
     lib.elector_tally_run.argtypes = [vp, c.c_int64, vp, vp, vp, vp, vp]
     lib.elector_tally_run.restype = c.c_int
+    lib.elector_unpack_columns.argtypes = [vp, c.c_int64, vp, vp, vp]
+    lib.elector_unpack_columns.restype = None
     lib.elector_merge_run.argtypes = [vp, c.c_int64, vp, c.c_int64, vp, c.c_int64, vp, vp, vp, vp, vp, vp, c.c_int64, vp, vp]
     lib.elector_merge_run.restype = c.c_int
     lib.elector_merge_tally_device.argtypes = [vp, c.c_int64, vp, c.c_int64, vp, c.c_int64, vp, vp, vp, vp]

@@ -211,10 +211,10 @@ class PoaContext:
         n_esc = np.zeros(1, np.int64)
         if merged:
             cap = int(lib.elector_merged_bound(n, n_reads, _p(ref_off), _p(cor_off), _p(unc_off)))
-            nib = merged == "nibbles"
-            m = [np.zeros(cap // 2 + 16 if nib else cap, np.uint8) for _ in range(3)]
+            nib = merged in ("nibbles", "columns")
+            m = [np.zeros(cap // 2 + 16 if merged == "nibbles" else cap, np.uint8) for _ in range(3)]
             m_off, m_len = np.zeros(n_reads, np.int64), np.zeros(n_reads, np.int32)
-            io.m_ref, io.m_cor, io.m_unc, io.m_cap, io.m_nibbles = m[0].ctypes.data, m[1].ctypes.data, m[2].ctypes.data, cap, int(nib)
+            io.m_ref, io.m_cor, io.m_unc, io.m_cap, io.m_nibbles = m[0].ctypes.data, m[1].ctypes.data, m[2].ctypes.data, cap, {"nibbles": 1, "columns": 2}.get(merged, 0)
             io.m_off, io.m_len = m_off.ctypes.data, m_len.ctypes.data
             if nib:
                 esc_pos, esc_byte = np.zeros(65536, np.int64), np.zeros(65536, np.uint8)
@@ -231,6 +231,12 @@ class PoaContext:
                 b[0::2] = lut[m[s] & 15]
                 b[1::2] = lut[m[s] >> 4]
                 full.append(b)
+            for k in range(int(n_esc[0])):
+                full[int(esc_pos[k] % 3)][int(esc_pos[k] // 3)] = esc_byte[k]
+            rows = [tuple(full[s][m_off[r]:m_off[r] + m_len[r]].tobytes().decode("latin-1") for s in range(3)) for r in range(n_reads)]
+        elif merged == "columns":   # one byte per column: elector_unpack_columns + the escape list
+            full = [np.empty(cap, np.uint8) for _ in range(3)]
+            lib.elector_unpack_columns(ctypes.c_void_p(m[0].ctypes.data), ctypes.c_int64(cap), *(ctypes.c_void_p(f.ctypes.data) for f in full))
             for k in range(int(n_esc[0])):
                 full[int(esc_pos[k] % 3)][int(esc_pos[k] // 3)] = esc_byte[k]
             rows = [tuple(full[s][m_off[r]:m_off[r] + m_len[r]].tobytes().decode("latin-1") for s in range(3)) for r in range(n_reads)]

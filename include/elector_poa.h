@@ -179,6 +179,12 @@ int64_t elector_pack_letters(const char *letters, int64_t n, uint8_t *bits, int6
 
 /* 4-bit column codes of the merged rows (m_nibbles != 0): column i of a row in bits 4*(i&1).. of byte i>>1 */
 #define ELECTOR_NIBBLE_CHARS ".acgtnA"   /* codes 0..6; code 15 = any other character: listed in m_esc_* */
+/* one byte per column for the three rows together (m_nibbles == 2): ref + 6 * cor + 36 * unc, each row's character coded
+ * 0..5 over ELECTOR_COLUMN_CHARS; 255 = some character of the column is outside the code: its three characters are listed
+ * in m_esc_*.  A third of the bytes of the 4-bit form: what Donatello appends to msa.fa (Donatello.cpp:50-84) in 1 B / column. */
+#define ELECTOR_COLUMN_CHARS ".acgtn"
+/* host side: the three rows of n columns back from their codes (escaped columns come out as '?': patch them from m_esc_*) */
+void elector_unpack_columns(const uint8_t *codes, int64_t n, char *ref, char *cor, char *unc);
 
 typedef struct elector_pipeline_io {
   int64_t n_windows, n_reads;
@@ -195,9 +201,10 @@ typedef struct elector_pipeline_io {
   int32_t *nring, *score1, *score2; int64_t *cells;
   /* merged rows per read (Donatello.cpp:50-84), each may be NULL: read r's three rows are m_len[r] columns from column
    * m_off[r] of m_ref / m_cor / m_unc (m_off[r] is a multiple of 16; m_cap columns per buffer, elector_merged_bound()
-   * always suffices).  m_nibbles != 0: two columns per byte (ELECTOR_NIBBLE_CHARS), the buffers hold m_cap / 2 bytes, and the
+   * always suffices).  m_nibbles == 1: two columns per byte (ELECTOR_NIBBLE_CHARS), the buffers hold m_cap / 2 bytes, and the
    * columns with code 15 are listed in m_esc_pos (3 * column + row, unordered) / m_esc_byte (at most m_esc_cap; *m_n_esc
-   * receives their number). */
+   * receives their number).  m_nibbles == 2: the three rows in one byte per column (ELECTOR_COLUMN_CHARS) in m_ref alone
+   * (m_cap bytes; m_cor / m_unc unused), code 255 = the column's three characters are in the escape list. */
   char *m_ref, *m_cor, *m_unc; int64_t m_cap; int m_nibbles;
   int64_t *m_off; int32_t *m_len;
   int64_t *m_esc_pos; uint8_t *m_esc_byte; int64_t m_esc_cap; int64_t *m_n_esc;

@@ -195,7 +195,7 @@ def test_config_slices_pipeline_equals_oracle_chain(cfg, reads):
         assert [int(v) for v in counters[r]] == [exp[f] for f in TALLY_FIELDS], (cfg, r)
 
 
-@pytest.mark.parametrize("packed,merged,chunks", [(True, "bytes", "1"), (True, "nibbles", "3"), (False, "nibbles", "2"), (True, None, "1")])
+@pytest.mark.parametrize("packed,merged,chunks", [(True, "bytes", "1"), (True, "nibbles", "3"), (False, "nibbles", "2"), (True, "columns", "3"), (False, "columns", "1"), (True, None, "1")])
 def test_compact_wire_format_equals_byte_path(packed, merged, chunks, monkeypatch):
     """elector_pipeline_run2: 2-bit letters + exceptions and 32-bit offsets in, merged rows as bytes or 4-bit columns (with
     escapes) or counters only out -- same windows, merged rows (= Donatello of the window rows) and counters as the byte
@@ -218,5 +218,5 @@ def test_compact_wire_format_equals_byte_path(packed, merged, chunks, monkeypatc
     assert np.array_equal(out["counters"], base_cnt) and np.array_equal(out["sums"], base_sums)
     if merged:
         assert out["merged"] == base_merged
-        if merged == "nibbles":
+        if merged in ("nibbles", "columns"):
             assert out["n_esc"] > 0
