@@ -274,6 +274,8 @@ def main():
         pk.exc_pos, pk.exc_byte = a_pos[:n_e], a_byt[:n_e]
     pk_c = [pk.c_struct() for pk in packed]
     len32 = [pinned(np.diff(wl[k]).astype(np.int32)) for k in ("ref_off", "cor_off", "unc_off")]   # 32-bit window lengths: what crosses the link
+    len16 = [pinned(np.diff(wl[k]).astype(np.uint16)) for k in ("ref_off", "cor_off", "unc_off")]  # ... or 16-bit ones (the headline mode)
+    assert max(int(np.diff(wl[k]).max()) for k in ("ref_off", "cor_off", "unc_off")) < 65536
     m_cap = int(lib.elector_merged_bound(n, n_trip, hptr["ref_off"], hptr["cor_off"], hptr["unc_off"]))
     h_m = [torch.empty(m_cap, dtype=torch.uint8).pin_memory() for _ in range(3)]
     h_moff, h_mlen = torch.empty(n_trip, dtype=torch.int64).pin_memory(), torch.empty(n_trip, dtype=torch.int32).pin_memory()
@@ -291,7 +293,10 @@ def main():
             io.rows_out, io.rows_cap, io.row_off, io.row_stride = h_rows.data_ptr(), bound, h_out["row_off"].data_ptr(), h_out["stride"].data_ptr()
         else:
             io.pref, io.pcor, io.punc = (ctypes.addressof(c) for c in pk_c)
-            io.ref_len, io.cor_len, io.unc_len = (t[1].ctypes.data for t in len32)
+            if mode == "packed_in_merged_columns_out":
+                io.ref_len16, io.cor_len16, io.unc_len16 = (t[1].ctypes.data for t in len16)
+            else:
+                io.ref_len, io.cor_len, io.unc_len = (t[1].ctypes.data for t in len32)
             if mode != "packed_in_counters_out":
                 io.m_ref, io.m_cor, io.m_unc, io.m_cap = h_m[0].data_ptr(), h_m[1].data_ptr(), h_m[2].data_ptr(), m_cap
                 io.m_off, io.m_len = h_moff.data_ptr(), h_mlen.data_ptr()
@@ -444,7 +449,7 @@ def main():
     out_merged = 3 * merged_cols + n * 4 + n_trip * (8 + 4 + K * 8) + K * 8     # merged rows as bytes, nring, m_off / m_len, counters
     wire = {"packed_in_merged_rows_out": (in_packed, out_merged), "bytes_in_window_rows_out": (in_bytes, out_rows),
             "packed_in_merged_nibbles_out": (in_packed, out_merged - 3 * merged_cols + 3 * ((merged_cols + 1) // 2) + 9 * nesc["packed_in_merged_nibbles_out"]),
-            "packed_in_merged_columns_out": (in_packed, out_merged - 2 * merged_cols + 9 * nesc["packed_in_merged_columns_out"]),
+            "packed_in_merged_columns_out": (in_packed - 3 * 2 * n, out_merged - 2 * merged_cols + 9 * nesc["packed_in_merged_columns_out"]),
             "packed_in_counters_out": (in_packed, n_trip * K * 8 + K * 8)}
     out_bytes = wire[E2E_MODES[0]][1]
     alg_bytes = in_bytes + used + n * 36
@@ -463,7 +468,7 @@ def main():
                    "l2": "inputs (%.0f MB per step) larger than the 126 MB L2, no flush" % (in_bytes / 1e6), "parity": parity},
         "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": wire[E2E_MODES[0]][0], "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": e2e_step_ms,
-                "call": "elector_pipeline_run2: 2-bit packed letters + 32-bit window lengths in (packed once, outside the call), merged per-read MSA rows (what Donatello appends to msa.fa) as one byte per column (the three rows' characters base 6, ELECTOR_COLUMN_CHARS) + per-read counters + sums out; pinned host buffers",
+                "call": "elector_pipeline_run2: 2-bit packed letters + 16-bit window lengths in (packed once, outside the call), merged per-read MSA rows (what Donatello appends to msa.fa) as one byte per column (the three rows' characters base 6, ELECTOR_COLUMN_CHARS) + per-read counters + sums out; pinned host buffers",
                 "host_link_gbs": (wire[E2E_MODES[0]][0] + out_bytes) / (e2e_step_ms / 1e3) / 1e9,
                 "limiter": "kernels (%.2f ms resident) + the tail of the last chunk's results; the host link carries %.0f MB per call" % (step_ms, (wire[E2E_MODES[0]][0] + out_bytes) / 1e6),
                 "modes": {m: {"ms_per_step": e2e_modes[m], "value": n_trip * world / (e2e_modes[m] / 1e3), "h2d_bytes_per_step": wire[m][0], "d2h_bytes_per_step": wire[m][1],

@@ -627,7 +627,8 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
     }
     stage = static_cast<int32_t *>(ctx->h_stage);
     const int32_t *h_len[3] = {io.ref_len, io.cor_len, io.unc_len};
-    use_len = h_len[0] && h_len[1] && h_len[2] && nw <= 1024 * 1024;   // the caller's 32-bit lengths cross the link as they are
+    const bool len16 = io.ref_len16 && io.cor_len16 && io.unc_len16;
+    use_len = ((h_len[0] && h_len[1] && h_len[2]) || len16) && nw <= 1024 * 1024;   // the caller's 32-bit (or 16-bit) lengths cross the link as they are
     for (int k = 0; k < 3; ++k) {
       if (len[k] > 0x7fffffff) return ctx->fail(ELECTOR_ETOOLARGE, "a chunk holds more than 2^31 letters of one kind");
       if (!use_len) {
@@ -640,7 +641,7 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
       exc1[k] = std::lower_bound(ep, ep + ne, first[k] + len[k]) - ep;
       CU(ctx->d_pk[k].reserve((size_t)(len[k] / 4 + 8)));
     }
-    CU(ctx->d_rel.reserve(need + 3 * 1032 * sizeof(long long)));
+    CU(ctx->d_rel.reserve(need + 3 * 1032 * sizeof(long long) + (size_t)3 * (nw + 4) * sizeof(uint16_t)));
     const int64_t ne_tot = (exc1[0] - exc0[0]) + (exc1[1] - exc0[1]) + (exc1[2] - exc0[2]);
     CU(ctx->d_exc_pos.reserve((size_t)(ne_tot + 1) * 8)); CU(ctx->d_exc_byte.reserve((size_t)ne_tot + 8));
   }
@@ -660,11 +661,19 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
   // ref and cor (phase 1 waits for them), then unc (phase 2 waits for it) -- while the sort and phase 1 run.
   if (pa.packed && use_len) {   // 32-bit lengths in, added up on the device
     const int32_t *h_len[3] = {io.ref_len, io.cor_len, io.unc_len};
+    const uint16_t *h_len16[3] = {io.ref_len16, io.cor_len16, io.unc_len16};
+    const bool len16 = h_len16[0] && h_len16[1] && h_len16[2];
     const int nblocks = (int)((nw + 1023) / 1024);
     long long *totals = reinterpret_cast<long long *>(ctx->d_rel.as<int32_t>() + (size_t)3 * (nw + 1) + ((nw + 1) & 1));
+    uint16_t *d16 = reinterpret_cast<uint16_t *>(totals + 3 * 1032);
     for (int k = 0; k < 3; ++k) {
       int32_t *dl = ctx->d_rel.as<int32_t>() + (size_t)k * (nw + 1);
-      CU(cudaMemcpyAsync(dl, h_len[k] + w0, (size_t)nw * 4, cudaMemcpyHostToDevice, st));
+      if (len16) {
+        uint16_t *dk = d16 + (size_t)k * (nw + 4);
+        CU(cudaMemcpyAsync(dk, h_len16[k] + w0, (size_t)nw * 2, cudaMemcpyHostToDevice, st));
+        widen_len16_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(nw, dk, dl);
+      } else
+        CU(cudaMemcpyAsync(dl, h_len[k] + w0, (size_t)nw * 4, cudaMemcpyHostToDevice, st));
       len_scan_blocks_kernel<<<nblocks, 1024, 0, st>>>(nw, dl, totals + (size_t)k * 1032);
       len_scan_totals_kernel<<<1, 1024, 0, st>>>(nblocks, totals + (size_t)k * 1032);
       len_to_offsets_kernel<<<(unsigned)((nw + 256) / 256), 256, 0, st>>>(nw, dl, totals + (size_t)k * 1032, nblocks, first[k], d_off[k]->as<int64_t>());

@@ -35,6 +35,12 @@ __global__ void widen_offsets_kernel(int64_t n, const int32_t *rel, int64_t base
   if (i < n) off[i] = base + rel[i];
 }
 
+// 16-bit window lengths -> the 32-bit ones the scan below works on
+__global__ void widen_len16_kernel(int64_t n, const uint16_t *len16, int32_t *len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) len[i] = len16[i];
+}
+
 // window lengths -> 64-bit offsets: per 1024-window block an exclusive scan (in place: len becomes the offset inside the
 // block) and the block total; then one CTA scans the block totals (at most 1024 blocks x 1024 windows per chunk); then
 // off[i] = base + block_base[i / 1024] + len[i], off[n] = base + total

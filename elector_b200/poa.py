@@ -37,7 +37,8 @@ class PipelineIoC(ctypes.Structure):  # struct elector_pipeline_io
                 ("m_ref", ctypes.c_void_p), ("m_cor", ctypes.c_void_p), ("m_unc", ctypes.c_void_p), ("m_cap", ctypes.c_int64), ("m_nibbles", ctypes.c_int),
                 ("m_off", ctypes.c_void_p), ("m_len", ctypes.c_void_p),
                 ("m_esc_pos", ctypes.c_void_p), ("m_esc_byte", ctypes.c_void_p), ("m_esc_cap", ctypes.c_int64), ("m_n_esc", ctypes.c_void_p),
-                ("counters_out", ctypes.c_void_p), ("sums_out", ctypes.c_void_p)]
+                ("counters_out", ctypes.c_void_p), ("sums_out", ctypes.c_void_p),
+                ("ref_len16", ctypes.c_void_p), ("cor_len16", ctypes.c_void_p), ("unc_len16", ctypes.c_void_p)]
 
 
 @dataclass
@@ -172,7 +173,7 @@ class PoaContext:
                                                    _p(counters), _p(sums)))
         return res, counters, sums
 
-    def pipeline_io(self, ref, ref_off, cor, cor_off, unc, unc_off, read_first, packed=False, window_rows=False, merged="bytes", lengths32=False):
+    def pipeline_io(self, ref, ref_off, cor, cor_off, unc, unc_off, read_first, packed=False, window_rows=False, merged="bytes", lengths32=False, lengths16=False):
         """elector_pipeline_run2: letters as bytes or 2-bit packed (PackedLetters or packed=True to pack here), outputs chosen by
         the caller: window_rows (PoaResult), merged = "bytes" | "nibbles" | None, always the counters and sums.
         Returns dict(res, merged (list of (R, C, U) strings or None), counters, sums, m_len)."""
@@ -188,7 +189,11 @@ class PoaContext:
             cs = [p.c_struct() for p in pk]
             keep += pk + cs
             io.pref, io.pcor, io.punc = (ctypes.addressof(c) for c in cs)
-            if lengths32:
+            if lengths16:
+                lens = [np.ascontiguousarray(np.diff(o), dtype=np.uint16) for o in (ref_off, cor_off, unc_off)]
+                keep += lens
+                io.ref_len16, io.cor_len16, io.unc_len16 = (l.ctypes.data for l in lens)
+            elif lengths32:
                 lens = [np.ascontiguousarray(np.diff(o), dtype=np.int32) for o in (ref_off, cor_off, unc_off)]
                 keep += lens
                 io.ref_len, io.cor_len, io.unc_len = (l.ctypes.data for l in lens)

@@ -210,6 +210,9 @@ typedef struct elector_pipeline_io {
   int64_t *m_esc_pos; uint8_t *m_esc_byte; int64_t m_esc_cap; int64_t *m_n_esc;
   /* per read / per call */
   int64_t *counters_out, *sums_out;
+  /* optional, instead of ref_len / cor_len / unc_len: the window lengths as 16-bit values (every window shorter than 65 536
+   * letters, which the alignment requires anyway: 16-bit node indices).  Half the bytes of the 32-bit lengths on the link. */
+  const uint16_t *ref_len16, *cor_len16, *unc_len16;
 } elector_pipeline_io;
 
 int64_t elector_merged_bound(int64_t n_windows, int64_t n_reads, const int64_t *ref_off, const int64_t *cor_off, const int64_t *unc_off);

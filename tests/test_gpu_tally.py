@@ -213,7 +213,7 @@ def test_compact_wire_format_equals_byte_path(packed, merged, chunks, monkeypatc
     with elector_b200.PoaContext(0) as c:
         base_res, base_cnt, base_sums = c.pipeline_csr(ref, wl["ref_off"], cor, wl["cor_off"], unc, wl["unc_off"], wl["read_first"])
         base_merged = c.merge(base_res, wl["read_first"])
-        out = c.pipeline_io(ref, wl["ref_off"], cor, wl["cor_off"], unc, wl["unc_off"], wl["read_first"], packed=packed, window_rows=False, merged=merged, lengths32=(chunks != "1"))
+        out = c.pipeline_io(ref, wl["ref_off"], cor, wl["cor_off"], unc, wl["unc_off"], wl["read_first"], packed=packed, window_rows=False, merged=merged, lengths32=(chunks != "1"), lengths16=(merged == "columns"))
     assert np.array_equal(out["res"].nring, base_res.nring) and np.array_equal(out["res"].score2, base_res.score2)
     assert np.array_equal(out["counters"], base_cnt) and np.array_equal(out["sums"], base_sums)
     if merged:
