@@ -94,6 +94,7 @@ struct elector_ctx {
   int band_w = 6;          // ELECTOR_BAND_W: base half-width of the diagonal band of the packed linear kernels (+ rows/16 in phase 1, + rows/8 in phase 2; 0 = full DP)
   bool no_dual = false;    // ELECTOR_NO_DUAL=1: general windows of phase 2 on the INT32 kernel with frontier sets
   int resident_ph2d = 0;
+  int coop_mid = 3;        // ELECTOR_COOP_MID: bit 0 / bit 1 = the windows of 129 .. 256 rows run a warp per window in phase 1 / phase 2 (else thread-per-window, packed kernels)
   bool no_ident = false;   // ELECTOR_NO_IDENT=1: windows whose cor is ref run DP1 like every other window
   unsigned side_used = 0;        // side streams with launches that `st` has not been made to wait for yet
   bool async_launch = false;     // ELECTOR_ASYNC_LAUNCH=1: no read-back of the plans; every segment is launched with a fixed grid (no host wait inside a call)
@@ -302,8 +303,9 @@ struct SortView {
 // kernel of a segment (static: known before the sort runs, see SegStatic)
 int seg_kind(const elector_ctx *ctx, int phase, int s) {
   const bool small16 = ctx->sc.packed_ok && (int64_t)ctx->sc.maxabs * (kSmallMax + 4 * kN1q + 4) <= kPackedSpan;   // no score of a small window leaves 16 bits
-  if (phase == 1) return (s <= kBigTiers && ctx->coop_group > 0) ? kCoop : (s >= kBigTiers && small16) ? kPacked : kInt32;
-  const bool longest = s <= kBigTiers || s == kFirstLinSeg2;   // more than 128 rows: a warp per window
+  const int coop_last = (ctx->coop_mid & (phase == 1 ? 1 : 2)) ? kBigTiers : kBigTiers - 1;   // last segment that runs a warp per window
+  if (phase == 1) return (s <= coop_last && ctx->coop_group > 0) ? kCoop : (s >= kBigTiers && small16) ? kPacked : kInt32;
+  const bool longest = s <= coop_last || (s == kFirstLinSeg2 && (ctx->coop_mid & 2));   // more than 128 rows: a warp per window
   if (longest && ctx->coop_group > 0) return kCoop;
   if (s < kBigTiers || !small16) return kInt32;
   return s >= kFirstLinSeg2 ? kLinear : ctx->no_dual ? kInt32 : kDual;
@@ -563,6 +565,21 @@ void add_kernel_ms(elector_ctx *ctx) {
   if (ctx->trace) {
     const char *lvl = getenv("ELECTOR_TRACE");
     if (lvl && lvl[0] >= '2') {
+#ifdef EL_DP_CLOCKS
+      {
+        unsigned long long h[2][8], z[2][8] = {};
+        cudaMemcpyFromSymbol(h, g_dp_clk, sizeof h);
+        cudaMemcpyToSymbol(g_dp_clk, z, sizeof z);
+        static const char *ph[8] = {"set-up", "pack", "prepare", "dp", "traceback", "alloc+fuse+emit", "rest", ""};
+        for (int k = 0; k < 2; ++k) {
+          double tot = 0;
+          for (int i = 0; i < 7; ++i) tot += (double)h[k][i];
+          fprintf(stderr, "[elector clocks] %s:", k ? "Phase2D" : "Phase2L");
+          for (int i = 0; i < 7; ++i) fprintf(stderr, " %s %.1f%%", ph[i], tot > 0 ? 100.0 * h[k][i] / tot : 0.0);
+          fprintf(stderr, " (%.3g warp cycles)\n", tot);
+        }
+      }
+#endif
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) fprintf(stderr, "[elector trace]   phase 1 done %.3f ms", ms);
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_lin_done) == cudaSuccess) fprintf(stderr, ", linear segments of phase 2 done %.3f ms", ms);
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) fprintf(stderr, ", all done %.3f ms\n", ms);
@@ -896,6 +913,7 @@ int create_context(int device, const ScoreMatrix &mat, elector_ctx **out, int wo
   if (!ctx->sc.analyse(ctx->mat)) { ctx->err = ctx->sc.error; return bail(ELECTOR_EUNSUPPORTED); }
   ctx->trace = getenv("ELECTOR_TRACE") != nullptr;
   if (const char *e = getenv("ELECTOR_NO_IDENT")) ctx->no_ident = e[0] == '1';
+  if (const char *e = getenv("ELECTOR_COOP_MID")) ctx->coop_mid = atoi(e) & 3;
   if (const char *e = getenv("ELECTOR_ASYNC_LAUNCH")) ctx->async_launch = e[0] == '1';
   if (const char *e = getenv("ELECTOR_NO_DUAL")) ctx->no_dual = e[0] == '1';
   if (const char *e = getenv("ELECTOR_BAND_W")) ctx->band_w = std::max(0, std::min(64, atoi(e)));

@@ -238,10 +238,14 @@ struct Phase2D : Phase2<false> {
     p1n = p1;
     for (int k = 0; k < n1; k += 64) prefetch_l1(p1 + k);      // the node list, for the node preparation (and the fusion)
     fs.pack_codes(sc.tab, unc, lu, Lp->f_unc);
+    EL_TICK(*this, 1);
     const int nrings = prepare(p1, n1);
+    EL_TICK(*this, 2);
     int bj;
     s2 = dp(n1, lu, bj);
+    EL_TICK(*this, 3);
     traceback(n1, lu, bj, al);
+    EL_TICK(*this, 4);
     return columns_of(nrings, lu, al.nmatch);
   }
 };

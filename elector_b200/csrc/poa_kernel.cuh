@@ -234,6 +234,27 @@ EL_HD uint32_t shift_in_sign(uint32_t mv, int t) {
 #endif
 }
 
+// Diagnostic build (-DEL_DP_CLOCKS): SM cycles per phase of the thread-per-window DP2 kernels, summed over warps by lane 0
+// (g_dp_clk[kind][phase]; kind 0 = Phase2L, 1 = Phase2D / Phase2; phases: 0 group set-up, 1 pack, 2 node preparation, 3 DP,
+// 4 traceback, 5 row allocation + fusion + emit, 6 the rest).  ELECTOR_TRACE prints them after a call (capi.cu).
+#ifdef EL_DP_CLOCKS
+__device__ unsigned long long g_dp_clk[2][8];
+struct PhaseClock {
+  mutable long long prev = 0;
+  int kind = 0;
+  __host__ __device__ void tick(int ph) const {
+#ifdef __CUDA_ARCH__
+    if ((threadIdx.x & 31) == 0) { const long long t = clock64(); atomicAdd(&g_dp_clk[kind][ph], (unsigned long long)(t - prev)); prev = t; }
+#else
+    (void)ph;
+#endif
+  }
+};
+#define EL_TICK(obj, ph) (obj).pclk.tick(ph)
+#else
+#define EL_TICK(obj, ph) ((void)0)
+#endif
+
 struct Scoring {
   const SymbolTables *tab;
   int match, mismatch, open, ext;
@@ -713,6 +734,9 @@ struct Phase2 {
   uint32_t *bset;     // two frontier-set slots of kSlotWords words, + lane (shared memory on the device)
   Scoring sc;
   const Layout2 *Lp;  // layout of the current group (shared memory on the device)
+#ifdef EL_DP_CLOCKS
+  PhaseClock pclk;
+#endif
 
   EL_HD uint32_t *rec(uint32_t j) const { return scr.at(Lp->o_nodes + j * Lp->rec_words); }  // field f at [f*32]
 
@@ -831,10 +855,14 @@ struct Phase2 {
   // everything up to the traceback; returns the number of MSA columns (the rows are emitted once their place is known)
   EL_HDN int align_window(const uint16_t *p1, int n1, const uint8_t *unc, int lu, int &s2, AlignBits &al) const {
     fs.pack_codes(sc.tab, unc, lu, Lp->f_unc);
+    EL_TICK(*this, 1);
     const int nrings = prepare(p1, n1);
+    EL_TICK(*this, 2);
     int bj;
     s2 = dp(n1, lu, bj);
+    EL_TICK(*this, 3);
     traceback(n1, lu, bj, al);
+    EL_TICK(*this, 4);
     return columns_of(nrings, lu, al.nmatch);
   }
 };
@@ -1058,6 +1086,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
     c.fs.base = fast_base(a, s_layout, c.scr.base, lane);
     bool exact = true;
     AlignBits al = c.bits();
+    EL_TICK(c, 0);
     if (active) {
       int s2;
       if constexpr (PH::kLinear) nring = c.align_linear(a.ref + ro, n1, a.unc + uo, lu, s2, exact, al);   // P1 = lin(ref): no node list needed
@@ -1075,8 +1104,13 @@ __global__ void __launch_bounds__(32, MIN_WARPS) poa_dp2_kernel(PoaArgs a, const
     RowSink out;
     if (alloc_window_rows(a, s_run.rows_cap, active && exact, w, nring, out)) c.fuse_emit(al, n1, lu, out);
     __syncwarp();
+    EL_TICK(c, 5);
     return active && !exact;
   };
+#ifdef EL_DP_CLOCKS
+  c.pclk.kind = PH::kLinear ? 0 : 1;
+  c.pclk.prev = clock64();
+#endif
   for (;;) {
     int base = 0;
     if (lane == 0) base = atomicAdd(s_run.work_counter, 32);

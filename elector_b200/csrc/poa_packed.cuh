@@ -327,6 +327,9 @@ struct Phase2L {
   Scoring sc;
   const Layout2L *Lp;
   BandW bw = {0, 0, 0, false};   // set per group by the kernel
+#ifdef EL_DP_CLOCKS
+  PhaseClock pclk;
+#endif
 
   EL_HD AlignBits bits() const { return AlignBits{fs, Lp->f_xb, Lp->f_yb}; }
   EL_HD Phase1P core() const {
@@ -364,9 +367,11 @@ struct Phase2L {
   template <int R>
   EL_HDN int run_r(const Phase1P &d, int n1, int lu, int &s2, bool &exact, AlignBits &al) const {
     s2 = d.dp<R>(n1, lu, d.bw);
+    EL_TICK(*this, 3);
     exact = d.band_exact(s2, n1, lu);
     if (!exact) return 0;
     d.traceback<R>(n1, lu, al);
+    EL_TICK(*this, 4);
     return columns_of(n1, lu, al.nmatch);   // lin(ref): every node is a ring of its own
   }
 
@@ -374,6 +379,7 @@ struct Phase2L {
   EL_HDN int align_linear(const uint8_t *ref, int n1, const uint8_t *unc, int lu, int &s2, bool &exact, AlignBits &al) const {
     const Phase1P d = core();
     d.pack(ref, n1, unc, lu);
+    EL_TICK(*this, 1);
     if (Lp->R == 6) return run_r<6>(d, n1, lu, s2, exact, al);   // R is uniform over the warp
     if (Lp->R == 7) return run_r<7>(d, n1, lu, s2, exact, al);
     return run_r<8>(d, n1, lu, s2, exact, al);

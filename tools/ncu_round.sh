@@ -4,6 +4,7 @@
 #   ${TAG}_full.ncu-rep : --set full of the first POA launches of a 2 000-read call (bulk launches included)
 #   ${TAG}_launches_pipeline.csv : launch list of two pipelined calls (POA + merge + tally) through tools/pipe_driver.c
 #   ${TAG}_pipe_driver.txt / ${TAG}_pipe_trace.txt : host-clock time of 8 calls; device timeline (ELECTOR_TRACE=2) of one
+#   ${TAG}_launches_metrics.csv / ${TAG}_issue.json / ${TAG}_launch_table.csv : the pipelined call's launches with instruction counts, IPC, ALU-pipe use, DRAM bytes
 #   ${TAG}_dp2_10k.ncu-rep + ${TAG}_traffic.json : --set full of the phase-2 launch set of the 10 000-read call (DRAM bytes per launch)
 set +e
 O=gpurun_out; TAG=${1:-r1d}; mkdir -p $O
@@ -19,6 +20,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:poa_
 # the whole pipelined call (POA + merge + tally) in one chunk on one worker, through the C driver of elector_pipeline_run
 python tools/dump_csr.py 10000 1 /tmp/c1 > /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_pipeline.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo pipeline launches rc=$?
+# the same two calls with instruction counts, IPC and ALU-pipe use per launch -> ${TAG}_issue.json (bench.py: roofline.issue)
+timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed.avg.per_cycle_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_metrics.csv elector_b200/bin/pipe_driver /tmp/c1 2 > /dev/null; echo launch metrics rc=$?
+python tools/ncu_issue.py $O/${TAG}_launches_metrics.csv $O/${TAG}_issue.json
+python tools/launch_metrics.py $O/${TAG}_launches_metrics.csv "poa_dp|merge|tally|bin" > $O/${TAG}_launch_table.csv
 # --set full of the phase-2 launch set of the SECOND call (the first one grows the scratch pools and runs segments twice)
 set -- $(python tools/ncu_skip.py $O/${TAG}_launches_pipeline.csv poa_dp2); echo "phase-2 launches: skip $1, capture $2"
 # (every poa_dp2 launch of the run is captured and the last $2 are kept: under the full set the first call's launch pattern differs)
