@@ -114,65 +114,107 @@ __global__ void __launch_bounds__(128) merge_plan_kernel(int64_t n_reads, const 
 }
 
 // copy: a warp takes 32 consecutive windows at a time (their row places, strides, lengths and destinations in one
-// coalesced round trip, handed round by shuffles), then one window after the other: lanes over columns, ballot compaction
-// of the kept columns.  The first 128 columns of the NEXT window are loaded before the current one is stored, so that a
-// warp always has a window's rows in flight (one dependent round trip per window made this kernel latency bound:
-// 0.43 ms for 0.6 GB in round 1).
+// coalesced round trip, handed round by shuffles) and copies them four at a time, EIGHT LANES PER WINDOW.  The rows of a
+// window are 4-byte aligned and padded, so a lane loads one WORD of each row per pass (4 columns; two passes cover the usual
+// 56 columns, all loads of the four windows are issued before the first store).  A window without dropped columns (no 'n' in
+// its corrected row: all but the placeholder windows) is a plain copy to a byte-unaligned place: the lanes realign their words
+// with a funnel shift against the neighbour's (8-lane shuffles) and store aligned words; the partial words at the two ends are
+// handed to lanes 0-3 / 4-7 of the group, one byte each.  Windows that drop columns, or longer than 124 columns, take the
+// byte-wise ballot compaction on the whole warp.  (One warp per window with byte accesses made this kernel instruction bound:
+// 181 warp instructions per window, ALU pipe 76 %, profiles/r3k_launch_table.csv.)
+__device__ __forceinline__ void merge_copy_bytes(const uint8_t *src, int k, int st, int64_t o, int lane, uint8_t *m_ref, uint8_t *m_cor, uint8_t *m_unc) {
+  for (int c0 = 0; c0 < k; c0 += 32) {
+    const int i = c0 + lane;
+    uint8_t c = 'n', a = 0, u = 0;
+    if (i < k) { a = src[i]; c = src[st + i]; u = src[2 * st + i]; }
+    const unsigned keep = __ballot_sync(0xffffffffu, c != 'n');
+    if (c != 'n') {
+      const int64_t d = o + __popc(keep & ((1u << lane) - 1u));
+      m_ref[d] = a; m_cor[d] = c; m_unc[d] = u;
+    }
+    o += __popc(keep);
+  }
+}
 __global__ void __launch_bounds__(256) merge_copy_kernel(int64_t n_windows, const uint8_t *__restrict__ rows, const int64_t *__restrict__ row_off,
                                                           const int32_t *__restrict__ row_stride, const int32_t *__restrict__ nring,
                                                           const int64_t *__restrict__ wdst, uint8_t *__restrict__ m_ref,
                                                           uint8_t *__restrict__ m_cor, uint8_t *__restrict__ m_unc, const int32_t *abort) {
   if (*abort) return;
-  constexpr int kAhead = 4;   // 32-column passes of a window loaded ahead
-  const int lane = threadIdx.x & 31;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, g = lane >> 3, l = lane & 7;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(m_ref) | reinterpret_cast<uintptr_t>(m_cor) | reinterpret_cast<uintptr_t>(m_unc)) & 3u) == 0;
   for (int64_t wb = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; wb < n_windows; wb += nwarps * 32) {
     const int64_t wl = wb + lane;
     int k_l = 0, st_l = 0;
     int64_t ro_l = 0, o_l = 0;
     if (wl < n_windows) { k_l = nring[wl]; st_l = row_stride[wl]; ro_l = row_off[wl]; o_l = wdst[wl]; }
-    const int nw = (int)(n_windows - wb < 32 ? n_windows - wb : 32);
-    uint8_t na[kAhead], nc[kAhead], nu[kAhead];
-    auto load_ahead = [&](int t) {   // the first kAhead passes of window wb + t
-      const int k = __shfl_sync(0xffffffffu, k_l, t), st = __shfl_sync(0xffffffffu, st_l, t);
-      const uint8_t *src = rows + __shfl_sync(0xffffffffu, ro_l, t);
+    const int nwin = (int)(n_windows - wb < 32 ? n_windows - wb : 32);
+    for (int r = 0; 4 * r < nwin; ++r) {
+      const int t = 4 * r + g;                                 // my group's window
+      int k = __shfl_sync(kFull, k_l, t);
+      const int st = __shfl_sync(kFull, st_l, t);
+      const int64_t ro = __shfl_sync(kFull, ro_l, t), o = __shfl_sync(kFull, o_l, t);
+      if (t >= nwin) k = 0;
+      const int a = (int)(o & 3), words = st >> 2;
+      bool slow = k > 0 && (!aligned || a + k > 128);
+      const int nq = (k > 0 && !slow) ? (a + k + 3) >> 2 : 0;   // destination words of my window (at most 32)
+      const int its = (__reduce_max_sync(kFull, (unsigned)nq) + 7) >> 3;
+      const uint32_t *s4 = reinterpret_cast<const uint32_t *>(rows + ro);
+      uint32_t wa[4], wc[4], wu[4];
+      bool hasn = false;
 #pragma unroll
-      for (int q = 0; q < kAhead; ++q) {
-        const int i = q * 32 + lane;
-        na[q] = 0; nc[q] = 'n'; nu[q] = 0;
-        if (i < k) { na[q] = src[i]; nc[q] = src[st + i]; nu[q] = src[2 * st + i]; }
+      for (int it = 0; it < 4; ++it) {
+        wa[it] = wc[it] = wu[it] = 0;
+        if (it < its) {
+          const int q = 8 * it + l;
+          if (q < words && nq > 0) { wa[it] = s4[q]; wc[it] = s4[words + q]; wu[it] = s4[2 * words + q]; }
+          const uint32_t x = wc[it] ^ 0x6e6e6e6eu;             // 'n' bytes of the corrected row become 0
+          hasn |= ((x - 0x01010101u) & ~x & 0x80808080u) != 0;
+        }
       }
-    };
-    load_ahead(0);
-    for (int t = 0; t < nw; ++t) {
-      const int k = __shfl_sync(0xffffffffu, k_l, t), st = __shfl_sync(0xffffffffu, st_l, t);
-      const uint8_t *src = rows + __shfl_sync(0xffffffffu, ro_l, t);
-      int64_t o = __shfl_sync(0xffffffffu, o_l, t);
-      uint8_t ca[kAhead], cc[kAhead], cu[kAhead];
+      if ((__ballot_sync(kFull, hasn) >> (8 * g)) & 0xffu) slow = true;   // my window drops columns
+      // destination word q covers the bytes (o - a) + 4q .. + 3 = source bytes 4q - a .. 4q - a + 3
+      const int sh = 8 * (4 - a);
+      const int64_t d0 = o - a;
+      uint32_t ca = 0, cc = 0, cu = 0;                         // source word 8 it - 1
+      uint32_t ha = 0, hc = 0, hu = 0, ta = 0, tc = 0, tu = 0; // the first / last destination word, on the lane that made it
 #pragma unroll
-      for (int q = 0; q < kAhead; ++q) { ca[q] = na[q]; cc[q] = nc[q]; cu[q] = nu[q]; }
-      if (t + 1 < nw) load_ahead(t + 1);
-#pragma unroll
-      for (int q = 0; q < kAhead; ++q) {
-        if (q * 32 < k) {
-          const unsigned keep = __ballot_sync(0xffffffffu, cc[q] != 'n');
-          if (cc[q] != 'n') {
-            const int64_t d = o + __popc(keep & ((1u << lane) - 1u));
-            m_ref[d] = ca[q]; m_cor[d] = cc[q]; m_unc[d] = cu[q];
+      for (int it = 0; it < 4; ++it) {
+        if (it < its) {
+          uint32_t pa = __shfl_up_sync(kFull, wa[it], 1, 8), pc = __shfl_up_sync(kFull, wc[it], 1, 8), pu = __shfl_up_sync(kFull, wu[it], 1, 8);
+          if (l == 0) { pa = ca; pc = cc; pu = cu; }
+          ca = __shfl_sync(kFull, wa[it], 7, 8); cc = __shfl_sync(kFull, wc[it], 7, 8); cu = __shfl_sync(kFull, wu[it], 7, 8);
+          const uint32_t da = a ? __funnelshift_r(pa, wa[it], sh) : wa[it], dc = a ? __funnelshift_r(pc, wc[it], sh) : wc[it],
+                         du = a ? __funnelshift_r(pu, wu[it], sh) : wu[it];
+          const int q = 8 * it + l, b0 = 4 * q - a;
+          if (!slow && q < nq) {
+            if (b0 >= 0 && b0 + 4 <= k) {
+              const int64_t d = d0 + 4 * q;
+              *reinterpret_cast<uint32_t *>(m_ref + d) = da; *reinterpret_cast<uint32_t *>(m_cor + d) = dc; *reinterpret_cast<uint32_t *>(m_unc + d) = du;
+            } else if (q == 0) { ha = da; hc = dc; hu = du; }
+            else { ta = da; tc = dc; tu = du; }
           }
-          o += __popc(keep);
         }
       }
-      for (int c0 = kAhead * 32; c0 < k; c0 += 32) {   // long windows: the rest, pass by pass
-        const int i = c0 + lane;
-        uint8_t c = 'n', a = 0, u = 0;
-        if (i < k) { a = src[i]; c = src[st + i]; u = src[2 * st + i]; }
-        const unsigned keep = __ballot_sync(0xffffffffu, c != 'n');
-        if (c != 'n') {
-          const int64_t d = o + __popc(keep & ((1u << lane) - 1u));
-          m_ref[d] = a; m_cor[d] = c; m_unc[d] = u;
+      if (its > 0) {   // the partial words at the ends: lanes 0-3 of the group take the bytes of the first word, lanes 4-7 those of the last
+        const int qt = nq > 1 ? nq - 1 : 0, lt = qt & 7;
+        const uint32_t Ha = __shfl_sync(kFull, ha, 0, 8), Hc = __shfl_sync(kFull, hc, 0, 8), Hu = __shfl_sync(kFull, hu, 0, 8);
+        const uint32_t Ta = __shfl_sync(kFull, ta, lt, 8), Tc = __shfl_sync(kFull, tc, lt, 8), Tu = __shfl_sync(kFull, tu, lt, 8);
+        const bool tail = l >= 4;
+        const int j = l & 3, q = tail ? qt : 0, b = 4 * q - a + j;
+        const int bq = 4 * q - a;
+        const bool partial = !(bq >= 0 && bq + 4 <= k);        // (a full word went out above)
+        if (!slow && nq > 0 && partial && (!tail || qt > 0) && b >= 0 && b < k) {
+          const int64_t d = d0 + 4 * q + j;
+          m_ref[d] = (uint8_t)((tail ? Ta : Ha) >> (8 * j)); m_cor[d] = (uint8_t)((tail ? Tc : Hc) >> (8 * j)); m_unc[d] = (uint8_t)((tail ? Tu : Hu) >> (8 * j));
         }
-        o += __popc(keep);
+      }
+      const unsigned slow_groups = __ballot_sync(kFull, slow && l == 0);
+      for (int gg = 0; gg < 4; ++gg) {
+        if (!((slow_groups >> (8 * gg)) & 1u)) continue;       // uniform
+        const int t2 = 4 * r + gg;
+        merge_copy_bytes(rows + __shfl_sync(kFull, ro_l, t2), __shfl_sync(kFull, k_l, t2), __shfl_sync(kFull, st_l, t2), __shfl_sync(kFull, o_l, t2), lane, m_ref, m_cor, m_unc);
       }
     }
   }
