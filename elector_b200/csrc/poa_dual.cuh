@@ -55,8 +55,9 @@ EL_HD uint32_t pk_prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // shape word of a node (record field R2_BG, free in this kernel), made by the node preparation so that the band loop
 // derives everything it needs per node with one PRMT each: bit 7 = carries a ref letter, bit 15 = carries a cor letter,
 // bit 23 = closes a bubble (a both-node after a one-letter node: exactly the nodes with an ordinal slot, NF_VIRT | NF_TWO),
-// byte 3 = the letter code, bit 0 = NF_FINAL
-enum : uint32_t { NM_REF = 1u << 7, NM_COR = 1u << 15, NM_MERGE = 1u << 23, NM_FINAL = 1u };
+// byte 3 = the letter code, bit 0 = NF_FINAL, bit 1 = a bubble-closing INITIAL node whose real predecessor is the ref one
+// (the virtual link, played by the cor frontier, comes first in its left list)
+enum : uint32_t { NM_REF = 1u << 7, NM_COR = 1u << 15, NM_MERGE = 1u << 23, NM_FINAL = 1u, NM_REFWINS = 2u };
 
 struct Phase2D : Phase2<false> {
   static constexpr int kSetWords = 1;   // no frontier sets in shared memory
@@ -64,7 +65,7 @@ struct Phase2D : Phase2<false> {
   static EL_HD void put_row0(uint32_t *p, int bS, int bG) { p[R2_BS * 32] = pk2(kBiasP + bS, kBiasP + bG); }
   static EL_HD void put_shape(uint32_t *p, uint32_t ra) {
     p[R2_BG * 32] = ((ra & NF_REF) ? NM_REF : 0u) | ((ra & NF_COR) ? NM_COR : 0u) | ((ra & (NF_VIRT | NF_TWO)) ? NM_MERGE : 0u) |
-                    ((ra & NF_FINAL) ? NM_FINAL : 0u) | ((ra & 0xffu) << 24);
+                    ((ra & NF_FINAL) ? NM_FINAL : 0u) | (((ra & NF_VIRT) && !(ra & NF_PREDC)) ? NM_REFWINS : 0u) | ((ra & 0xffu) << 24);
   }
   EL_HDN int prepare(const uint16_t *nodes, int nx) const { return prepare_nodes(*this, nodes, nx); }
 
@@ -130,9 +131,10 @@ struct Phase2D : Phase2<false> {
         // whose real predecessor is the ref one the virtual link (the cor frontier) comes first in the list, so the ref
         // frontier has to win strictly.  Only the ref set takes the maximum: the node carries both letters, reads its
         // input there and replaces both frontiers.
-        const uint32_t ram = ((mg & 0xffffu) ? p : p - step)[R2_NODE * 32];   // the merging node (a node never merges in both halves at once)
+        const bool low = mg & 0xffffu;                         // the merging node is node j (a node never merges in both halves at once)
+        const uint32_t ram = low ? 0u : (p - step)[R2_NODE * 32];   // node j - 1: its ordinal slot (loaded ahead of the merge, used after it)
         uint32_t oM = 0, oX = 0;                               // ordinal 1 = the second entry of the list won
-        if ((ram & NF_VIRT) && !(ram & NF_PREDC)) merge<R, true>(Sr, Gr, Sc, Gc, hr, hc, mg, oM, oX);
+        if ((low ? nm : nm_h) & NM_REFWINS) merge<R, true>(Sr, Gr, Sc, Gc, hr, hc, mg, oM, oX);
         else merge<R, false>(Sr, Gr, Sc, Gc, hr, hc, mg, oM, oX);
         if (mg & 0xffffu) { ordM_lo = oM & kLowOrdM; ordX_lo = oX & kLowOrdX; }
         else {
