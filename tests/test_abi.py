@@ -102,3 +102,24 @@ def test_pack_letters_roundtrip():
     keep = np.ones(len(s), bool); keep[p.exc_pos] = False
     assert np.array_equal(got[keep], up[keep]) and np.array_equal(got[p.exc_pos], s[p.exc_pos])
     assert all(bytes([b]) not in b"ACGTacgt" for b in p.exc_byte)
+
+
+def test_unpack_columns_is_the_inverse_of_the_column_code():
+    """elector_unpack_columns (host helper of the one-byte-per-column wire format, include/elector_poa.h): byte = ref + 6 cor +
+    36 unc over ELECTOR_COLUMN_CHARS; 255 (a column with a character outside the code) comes out as '?' in the three rows"""
+    import elector_b200
+    lib = elector_b200.load_library()
+    chars = np.frombuffer(b".acgtn", np.uint8)
+    rng = np.random.default_rng(3)
+    n = 10007
+    k = rng.integers(0, 6, size=(3, n))
+    codes = (k[0] + 6 * k[1] + 36 * k[2]).astype(np.uint8)
+    esc = rng.integers(0, n, 50)
+    codes[esc] = 255
+    out = [np.zeros(n, np.uint8) for _ in range(3)]
+    lib.elector_unpack_columns(ctypes.c_void_p(codes.ctypes.data), ctypes.c_int64(n), *(ctypes.c_void_p(o.ctypes.data) for o in out))
+    keep = np.ones(n, bool)
+    keep[esc] = False
+    for s in range(3):
+        assert np.array_equal(out[s][keep], chars[k[s]][keep])
+        assert (out[s][esc] == ord("?")).all()
