@@ -220,3 +220,42 @@ def test_compact_wire_format_equals_byte_path(packed, merged, chunks, monkeypatc
         assert out["merged"] == base_merged
         if merged in ("nibbles", "columns"):
             assert out["n_esc"] > 0
+
+
+@pytest.mark.gpu
+def test_merge_copy_on_synthetic_rows(ctx):
+    """merge_copy_kernel's paths on hand-made window rows (Donatello.cpp:50-84: concatenate a read's windows, drop the columns
+    whose corrected row is 'n'): every destination alignment, windows of 1 .. 300 columns (the word path takes up to 124, the
+    byte path the rest), windows with dropped columns, windows that are all 'n', reads of one window"""
+    from elector_b200.poa import PoaResult
+    rng = np.random.default_rng(17)
+    n_win = 5000
+    k = rng.integers(1, 70, n_win)
+    k[rng.integers(0, n_win, 200)] = rng.integers(120, 301, 200)      # around and beyond the word path's limit
+    k[rng.integers(0, n_win, 300)] = rng.integers(1, 5, 300)          # shorter than one word
+    stride = (k + 3) & ~3
+    off = np.concatenate([[0], np.cumsum(3 * stride)]).astype(np.int64)
+    perm = rng.permutation(n_win)                                        # rows lie in the buffer in another order than the windows
+    row_off = np.empty(n_win, np.int64)
+    row_off[perm] = np.concatenate([[0], np.cumsum(3 * stride[perm])])[:-1]
+    rows = np.zeros(int(off[-1]), np.uint8)
+    letters = np.frombuffer(b".acgt", np.uint8)
+    wins = []
+    for w in range(n_win):
+        r = [letters[rng.integers(0, 5, k[w])] for _ in range(3)]
+        mode = rng.integers(0, 10)
+        if mode == 0:
+            r[1][:] = ord("n")                                          # a placeholder window: every column dropped
+        elif mode == 1:
+            r[1][rng.integers(0, k[w], max(1, k[w] // 5))] = ord("n")   # some columns dropped
+        for s in range(3):
+            rows[row_off[w] + s * stride[w]:row_off[w] + s * stride[w] + k[w]] = r[s]
+        wins.append(r)
+    cuts = np.unique(np.concatenate([[0, n_win], rng.integers(1, n_win, 400), np.arange(10, 40)]))
+    res = PoaResult(rows, row_off, stride.astype(np.int32), k.astype(np.int32), np.zeros(n_win, np.int32), np.zeros(n_win, np.int32), np.zeros(n_win, np.int64))
+    got = ctx.merge(res, cuts)
+    for i in range(len(cuts) - 1):
+        cat = [np.concatenate([wins[w][s] for w in range(cuts[i], cuts[i + 1])]) for s in range(3)]
+        keep = cat[1] != ord("n")
+        exp = tuple(c[keep].tobytes().decode("latin-1") for c in cat)
+        assert got[i] == exp, i
