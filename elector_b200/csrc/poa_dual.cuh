@@ -116,7 +116,8 @@ struct Phase2D : Phase2<false> {
     uint32_t mr = 0, mc = 0, mg = 0, x2 = 0, nm_h = 0;
     uint32_t d7 = 0, g7 = 0, mlo = 0, ordM_lo = 0, ordX_lo = 0;
     // node j + 2 is loaded in iteration j (the scratch of a launch exceeds the L2; the long-scoreboard stall was this loop's
-    // top stall).  The loads run up to two records past the last node: still this lane's scratch, values never used.
+    // top stall).  The loads run up to three records past the last node: still this lane's scratch (make_layout2 keeps one
+    // spare record; the ordinal words, the letter codes and the fast part behind it are longer than the other two), values never used.
     uint32_t nm = p[R2_BG * 32], bsg = p[R2_BS * 32];
     uint32_t nm_n = p[step + R2_BG * 32], bsg_n = p[step + R2_BS * 32];
     for (int j = 0; j <= nx; ++j, p += step) {                 // the last iteration only completes the high half

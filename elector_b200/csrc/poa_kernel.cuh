@@ -116,7 +116,7 @@ EL_HD void make_layout2(Layout2 &L, int N1, int LU) {
   L.f_total = f;
   uint32_t o = 0;
   L.rec_words = R2_MOVES + nb;
-  L.o_nodes = o; o += (uint32_t)N1 * L.rec_words;
+  L.o_nodes = o; o += ((uint32_t)N1 + 1) * L.rec_words;         // + 1: the dual kernel's look-ahead loads (node j + 2, j <= N1) stay inside the lane's scratch
   L.ord_bands = nb;
   L.o_ord = o; o += ((uint32_t)N1 / 2 + 2) * nb * 2;            // combined nodes carry ref AND cor: at most N1/2, + 2 initial ones
   L.o_tmp = o; o += cdiv_u(N1, 4) + 1;
