@@ -96,3 +96,38 @@ def test_emulated_kernel_long_windows(golden_dir, emul_bin, mode, tmp_path):
     assert subprocess.call([emul_bin, mp, paths[0], paths[1], paths[2], pir] + (["-", mode] if mode != "int32" else [])) == 0
     assert oracle.poa_files(mp, paths[0], paths[1], paths[2], opir) == 0
     assert open(pir, "rb").read() == open(opir, "rb").read()
+
+
+@pytest.mark.parametrize("mode", ["packed", "dual-general"])
+def test_emulated_dual_kernel_on_bubble_windows(golden_dir, emul_bin, mode, tmp_path):
+    """the skewed two-set dual kernel (poa_dual.cuh) on ELECTOR-like windows: a corrected sequence with a few differences (bubbles
+    that open and close at every position of a band, in the low and in the high half, back to back, at the first and at the last
+    node; late starts and early ends of either sequence) against a noisier uncorrected one, lengths around the band sizes"""
+    from oracle import oracle, synth
+    rng = synth.SplitMix64(20261018)
+    wins = []
+    for i in range(6000):
+        L = [7, 8, 9, 15, 16, 17, 23, 24, 25, 31, 32, 33, 40, 48, 50, 55, 64, 65, 80, 100, 127][rng.below(21)]
+        ref = "".join("ACGT"[rng.below(4)] for _ in range(L))
+        cor = synth.mutate(rng, ref, [0.01, 0.02, 0.05, 0.1, 0.2][rng.below(5)], "ACGT")
+        t = rng.below(8)
+        if t == 0:
+            cor = cor[1 + rng.below(3):]                      # cor starts late: INITIAL node with the virtual link first
+        elif t == 1:
+            cor = cor[:max(1, len(cor) - 1 - rng.below(3))]   # cor ends early: several FINAL nodes
+        elif t == 2:
+            cor = "ACGT"[rng.below(4)] * (1 + rng.below(3)) + cor   # cor starts with an insertion
+        unc = synth.mutate(rng, ref, [0.05, 0.1, 0.2][rng.below(3)], "ACGT")
+        wins.append((ref, cor or "A", unc or "C"))
+    paths = []
+    for k, key in enumerate(("ref", "cor", "unc")):
+        p = str(tmp_path / (key + ".fa"))
+        with open(p, "w") as f:
+            for i, w in enumerate(wins):
+                f.write(">w%d\n%s\n" % (i, w[k]))
+        paths.append(p)
+    pir, opir = str(tmp_path / "e.pir"), str(tmp_path / "o.pir")
+    mp = golden_dir + "/blosum80.mat"
+    assert subprocess.call([emul_bin, mp, paths[0], paths[1], paths[2], pir, "-", mode], stderr=subprocess.DEVNULL) == 0
+    assert oracle.poa_files(mp, paths[0], paths[1], paths[2], opir) == 0
+    assert open(pir, "rb").read() == open(opir, "rb").read()
