@@ -106,7 +106,7 @@ struct elector_ctx {
   int64_t region_b_base = 0;        // out: where the linear region starts in the caller's row buffer
   cudaEvent_t ev_regb[8] = {};      // after each launch that writes to the linear region
   cudaEvent_t ev_lin = nullptr;     // the linear region is complete; its cursor and start are in h_totals[6..7]
-  cudaEvent_t ev_merged = nullptr;  // merge + tally of a chunk are done; the merged columns of the chunk are in h_totals[2]
+  cudaEvent_t ev_merged = nullptr;  // the merge of a chunk is done and its rows are packed for the wire (before the tally); the merged columns of the chunk are in h_totals[2]
   cudaEvent_t wait_in[2] = {nullptr, nullptr};   // run_device: phase 1 / phase 2 wait for these (letters still on their way), when set
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
   void *split_state = nullptr;   // device buffers of the window cutting (split_capi.inl)
@@ -755,13 +755,8 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
       CU(cudaMemsetAsync(ctx->d_sums.p, 0, ELECTOR_TALLY_K * 8, st));
       rc = merge_device(ctx, nr, rf.data(), nw, reinterpret_cast<const uint8_t *>(d_rows_v), 3 * (br + bc + bu), ctx->d_rowoff.as<int64_t>(),
                         ctx->d_stride.as<int32_t>(), ctx->d_nring.as<int32_t>());
-      if (rc == ELECTOR_OK)
-        rc = tally_device(ctx, nr, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(), ctx->d_moff.as<int64_t>(),
-                          ctx->d_mlen.as<int32_t>(), ctx->d_tally_out.as<int64_t>(), ctx->merged_cap);
       if (rc != ELECTOR_OK) { ctx->wait_in[0] = ctx->wait_in[1] = nullptr; cudaStreamSynchronize(st); return rc; }
-      tally_sum_kernel<<<std::min<int>(64, (int)((nr + 7) / 8)), 256, 0, st>>>(nr, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
-      CU(cudaGetLastError());
-      ++ctx->last_launches;
+      // the merged rows are packed and on their way before the tally runs: the copy stream takes them while the tally kernels run
       if (want_merged && io.m_nibbles == 2) {   // one byte per column for the three rows together; characters outside the code go to the escape list
         CU(ctx->d_nib[0].reserve((size_t)ctx->merged_cap + 16));
         CU(ctx->d_esc_pos.reserve((size_t)(io.m_esc_cap + 3) * 8)); CU(ctx->d_esc_byte.reserve((size_t)io.m_esc_cap + 8));
@@ -781,15 +776,21 @@ int process_chunk(elector_ctx *ctx, const PipeArgs &pa, const ChunkJob &j) {
         CU(cudaGetLastError());
         ++ctx->last_launches;
       }
+      CU(cudaMemcpyAsync(&ctx->h_totals[2], ctx->d_moff.as<int64_t>() + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, st));      // merged columns of the chunk
+      CU(cudaMemcpyAsync(&ctx->h_totals[3], ctx->d_ctrl.as<unsigned long long>() + 21, sizeof(int64_t), cudaMemcpyDeviceToHost, st));   // escapes
+      CU(cudaEventRecord(ctx->ev_merged, st));
+      rc = tally_device(ctx, nr, ctx->d_mref.as<uint8_t>(), ctx->d_mcor.as<uint8_t>(), ctx->d_munc.as<uint8_t>(), ctx->d_moff.as<int64_t>(),
+                        ctx->d_mlen.as<int32_t>(), ctx->d_tally_out.as<int64_t>(), ctx->merged_cap);
+      if (rc != ELECTOR_OK) { ctx->wait_in[0] = ctx->wait_in[1] = nullptr; cudaStreamSynchronize(st); return rc; }
+      tally_sum_kernel<<<std::min<int>(64, (int)((nr + 7) / 8)), 256, 0, st>>>(nr, ctx->d_tally_out.as<int64_t>(), ctx->d_sums.as<unsigned long long>());
+      CU(cudaGetLastError());
+      ++ctx->last_launches;
       CU(cudaEventRecord(ctx->ev1, st));   // the chunk's device time covers merge + tally too
       CU(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums.p, ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
       CU(cudaMemcpyAsync(ctx->h_sums + ELECTOR_TALLY_K, ctx->d_ctrl.as<int32_t>() + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(&ctx->h_totals[2], ctx->d_moff.as<int64_t>() + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, st));      // merged columns of the chunk
-      CU(cudaMemcpyAsync(&ctx->h_totals[3], ctx->d_ctrl.as<unsigned long long>() + 21, sizeof(int64_t), cudaMemcpyDeviceToHost, st));   // escapes
       if (io.counters_out) CU(cudaMemcpyAsync(io.counters_out + r0 * ELECTOR_TALLY_K, ctx->d_tally_out.p, nr * ELECTOR_TALLY_K * 8, cudaMemcpyDeviceToHost, st));
       if (io.m_off) CU(cudaMemcpyAsync(io.m_off + r0, ctx->d_moff.p, nr * 8, cudaMemcpyDeviceToHost, st));
       if (io.m_len) CU(cudaMemcpyAsync(io.m_len + r0, ctx->d_mlen.p, nr * 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaEventRecord(ctx->ev_merged, st));
     }
     // the alignment results leave on the copy stream while merge and tally run: the host waits for the POA kernels only
     // to learn how many row bytes the chunk used.  The linear region first: its segments run next to phase 1 and finish early.
